@@ -1,0 +1,403 @@
+// hg_mel.cu — mel_spectrogram (src/meldataset.py:56-85) as ONE fused kernel:
+//   reflect-pad -> frame x periodic Hann -> rFFT(1024) -> |X|^2 -> HTK mel (sparse) -> log(clamp(.,1e-5))
+// The reference goes through torchaudio.transforms.MelSpectrogram (meldataset.py:59-71): >= 6 library
+// launches and three HBM round trips of the [B,513,F] spectrum.  Here a block of 256 threads owns 8
+// consecutive frames: the 2816-sample input window is staged once in shared memory, each 64-thread
+// group runs a 512-point complex Stockham FFT (radix 8 x 8 x 8) per frame on the even/odd packed
+// samples, un-packs the real spectrum, accumulates the triangular mel filters from a CSR table and the
+// block writes [80][8] outputs with 32-byte contiguous runs.
+//
+// The per-thread phases are __host__ __device__ so tests can run the exact same arithmetic on the CPU
+// (hg_mel_emulate_host below) — there is no GPU in the development container.
+#include "hg_common.cuh"
+
+#include <atomic>
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+
+#include "../../include/hifigan_b200.h"
+
+extern std::atomic<int64_t> g_hg_launches;
+
+struct hg_mel_plan {
+  int n_fft, num_mels, sampling_rate, hop, win, pad;
+  double fmin, fmax;
+  int nnz;
+  // device tables
+  float* window;     // [n_fft]
+  float2* tw512;     // [512]  exp(-2*pi*i*m/512)
+  float2* tw1024;    // [513]  exp(-2*pi*i*k/1024)
+  int* mel_start;    // [num_mels] first rFFT bin with a non-zero weight
+  int* mel_off;      // [num_mels+1] CSR offsets into mel_w
+  float* mel_w;      // [nnz]
+  // host copies (CPU emulation for tests, and geometry queries)
+  std::vector<float> h_window;
+  std::vector<float2> h_tw512, h_tw1024;
+  std::vector<int> h_mel_start, h_mel_off;
+  std::vector<float> h_mel_w;
+};
+
+namespace {
+
+constexpr int kNfft = 1024;
+constexpr int kHalf = 512;
+constexpr int kFramesPerBlock = 8;
+constexpr int kGroups = 4;
+constexpr int kGroupThreads = 64;
+constexpr int kMelThreads = kGroups * kGroupThreads;
+constexpr int kPadLen = kHalf + kHalf / 16;  // PADI(511) + 1 = 543 -> 544
+
+__host__ __device__ __forceinline__ int padi(int i) { return i + (i >> 4); }
+
+struct cpx {
+  float x, y;
+};
+__host__ __device__ __forceinline__ cpx cadd(cpx a, cpx b) { return {a.x + b.x, a.y + b.y}; }
+__host__ __device__ __forceinline__ cpx csub(cpx a, cpx b) { return {a.x - b.x, a.y - b.y}; }
+__host__ __device__ __forceinline__ cpx cmul(cpx a, cpx b) {
+  return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+}
+__host__ __device__ __forceinline__ cpx mul_negi(cpx a) { return {a.y, -a.x}; }  // a * (-i)
+
+__host__ __device__ __forceinline__ void fft4(cpx& x0, cpx& x1, cpx& x2, cpx& x3) {
+  const cpx b0 = cadd(x0, x2), b2 = csub(x0, x2), b1 = cadd(x1, x3), b3 = mul_negi(csub(x1, x3));
+  x0 = cadd(b0, b1);
+  x2 = csub(b0, b1);
+  x1 = cadd(b2, b3);
+  x3 = csub(b2, b3);
+}
+
+// in-place 8-point DFT (forward, e^{-i...}), natural order out
+__host__ __device__ __forceinline__ void fft8(cpx (&v)[8]) {
+  const float h = 0.70710678118654752440f;
+  cpx a0 = cadd(v[0], v[4]), a4 = csub(v[0], v[4]);
+  cpx a1 = cadd(v[1], v[5]), a5 = csub(v[1], v[5]);
+  cpx a2 = cadd(v[2], v[6]), a6 = csub(v[2], v[6]);
+  cpx a3 = cadd(v[3], v[7]), a7 = csub(v[3], v[7]);
+  a5 = cpx{(a5.x + a5.y) * h, (a5.y - a5.x) * h};    // * (1 - i)/sqrt2
+  a6 = mul_negi(a6);                                 // * (-i)
+  a7 = cpx{(a7.y - a7.x) * h, -(a7.x + a7.y) * h};   // * (-1 - i)/sqrt2
+  fft4(a0, a1, a2, a3);
+  fft4(a4, a5, a6, a7);
+  v[0] = a0; v[2] = a1; v[4] = a2; v[6] = a3;
+  v[1] = a4; v[3] = a5; v[5] = a6; v[7] = a7;
+}
+
+// One Stockham radix-8 pass of a 512-point FFT for butterfly j in [0,64).
+//   FIRST: inputs come from the staged real samples (even/odd packing + window), Ns = 1.
+template <bool FIRST>
+__host__ __device__ __forceinline__ void fft_pass(int j, int ns, const cpx* __restrict__ in,
+                                                  cpx* __restrict__ out,
+                                                  const float* __restrict__ samples,
+                                                  const float* __restrict__ window,
+                                                  const float2* __restrict__ tw512) {
+  cpx v[8];
+  const int k = j & (ns - 1);
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int n = j + r * 64;
+    if (FIRST) {
+      v[r] = cpx{samples[2 * n] * window[2 * n], samples[2 * n + 1] * window[2 * n + 1]};
+    } else {
+      v[r] = in[padi(n)];
+      if (r) {
+        const float2 w = tw512[r * k * (64 / ns)];
+        v[r] = cmul(v[r], cpx{w.x, w.y});
+      }
+    }
+  }
+  fft8(v);
+  const int j0 = (j / ns) * ns * 8 + k;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) out[padi(j0 + r * ns)] = v[r];
+}
+
+// real-FFT un-packing + power for bins k = tid, tid+64, ... (0..512); z = FFT512 of packed samples
+__host__ __device__ __forceinline__ void unpack_power(int tid, const cpx* __restrict__ z,
+                                                      float* __restrict__ power,
+                                                      const float2* __restrict__ tw1024) {
+  for (int k = tid; k <= kHalf; k += kGroupThreads) {
+    const cpx zk = z[padi(k & (kHalf - 1))];
+    cpx zc = z[padi((kHalf - k) & (kHalf - 1))];
+    zc.y = -zc.y;
+    const cpx e = cpx{0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y)};
+    const cpx d = csub(zk, zc);
+    const cpx o = cpx{0.5f * d.y, -0.5f * d.x};  // (zk - zc) / (2i)
+    const float2 w = tw1024[k];
+    const cpx x = cadd(e, cmul(o, cpx{w.x, w.y}));
+    power[k] = x.x * x.x + x.y * x.y;
+  }
+}
+
+__host__ __device__ __forceinline__ void mel_project(int tid, int num_mels,
+                                                     const float* __restrict__ power,
+                                                     const int* __restrict__ mel_start,
+                                                     const int* __restrict__ mel_off,
+                                                     const float* __restrict__ mel_w,
+                                                     float* __restrict__ out_col, int out_stride) {
+  for (int m = tid; m < num_mels; m += kGroupThreads) {
+    const int s = mel_start[m], o = mel_off[m], n = mel_off[m + 1] - o;
+    float acc = 0.f;
+    for (int i = 0; i < n; ++i) acc += mel_w[o + i] * power[s + i];
+    out_col[m * out_stride] = logf(fmaxf(acc, 1e-5f));
+  }
+}
+
+__host__ __device__ __forceinline__ int reflect_index(int i, int t) {
+  if (i < 0) i = -i;
+  if (i >= t) i = 2 * (t - 1) - i;
+  return i;
+}
+
+__device__ __forceinline__ void atomic_min_f32(float* addr, float v) {
+  if (v >= 0.f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f32(float* addr, float v) {
+  if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+struct MelArgs {
+  const float* y;
+  float* out;
+  float* minmax;
+  int batch, t, frames, hop, pad, num_mels;
+  const float* window;
+  const float2* tw512;
+  const float2* tw1024;
+  const int* mel_start;
+  const int* mel_off;
+  const float* mel_w;
+  int stage_len;  // samples staged per block = (kFramesPerBlock-1)*hop + n_fft
+};
+
+__global__ void __launch_bounds__(kMelThreads) mel_kernel(const MelArgs a) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  float* stage = reinterpret_cast<float*>(sm);                                 // [stage_len]
+  cpx* buf0 = reinterpret_cast<cpx*>(sm + ((a.stage_len * 4 + 15) & ~15));     // [groups][kPadLen]
+  cpx* buf1 = buf0 + kGroups * kPadLen;                                        // [groups][kPadLen]
+  float* outs = reinterpret_cast<float*>(buf1 + kGroups * kPadLen);            // [num_mels][8]
+
+  const int b = blockIdx.y;
+  const int f0 = blockIdx.x * kFramesPerBlock;
+  const int tid = threadIdx.x;
+  const float* yb = a.y + static_cast<size_t>(b) * a.t;
+  const int base = f0 * a.hop - a.pad;
+  float vmin = INFINITY, vmax = -INFINITY;
+  for (int i = tid; i < a.stage_len; i += kMelThreads) {
+    // samples past the last frame of this batch item are never used; clamp keeps the index legal
+    int src = reflect_index(base + i, a.t);
+    src = src < 0 ? 0 : (src >= a.t ? a.t - 1 : src);
+    const float v = yb[src];
+    stage[i] = v;
+    vmin = fminf(vmin, v);
+    vmax = fmaxf(vmax, v);
+  }
+  if (a.minmax) {
+    for (int o = 16; o > 0; o >>= 1) {
+      vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+      vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    }
+    if ((tid & 31) == 0) {
+      atomic_min_f32(a.minmax, vmin);
+      atomic_max_f32(a.minmax + 1, vmax);
+    }
+  }
+  __syncthreads();
+
+  const int g = tid / kGroupThreads, j = tid % kGroupThreads;
+  cpx* z0 = buf0 + g * kPadLen;
+  cpx* z1 = buf1 + g * kPadLen;
+  for (int it = 0; it < kFramesPerBlock / kGroups; ++it) {
+    const int fl = it * kGroups + g;  // frame within the block
+    const float* smp = stage + fl * a.hop;
+    fft_pass<true>(j, 1, nullptr, z0, smp, a.window, a.tw512);
+    __syncthreads();
+    fft_pass<false>(j, 8, z0, z1, nullptr, nullptr, a.tw512);
+    __syncthreads();
+    fft_pass<false>(j, 64, z1, z0, nullptr, nullptr, a.tw512);
+    __syncthreads();
+    float* power = reinterpret_cast<float*>(z1);  // 513 floats fit in the 544-cpx scratch
+    unpack_power(j, z0, power, a.tw1024);
+    __syncthreads();
+    mel_project(j, a.num_mels, power, a.mel_start, a.mel_off, a.mel_w, outs + fl, kFramesPerBlock);
+    __syncthreads();
+  }
+  // outs[m][fl] -> out[b][m][f0 + fl]
+  float* ob = a.out + static_cast<size_t>(b) * a.num_mels * a.frames;
+  for (int i = tid; i < a.num_mels * kFramesPerBlock; i += kMelThreads) {
+    const int m = i / kFramesPerBlock, fl = i % kFramesPerBlock;
+    if (f0 + fl < a.frames) ob[static_cast<size_t>(m) * a.frames + f0 + fl] = outs[i];
+  }
+}
+
+double hz_to_mel_htk(double f) { return 2595.0 * std::log10(1.0 + f / 700.0); }
+double mel_to_hz_htk(double m) { return 700.0 * (std::pow(10.0, m / 2595.0) - 1.0); }
+
+}  // namespace
+
+extern "C" int hg_mel_num_frames(const hg_mel_plan* plan, int t) {
+  if (!plan || t <= 0) return 0;
+  const int padded = t + 2 * plan->pad;
+  if (padded < plan->n_fft) return 0;
+  return 1 + (padded - plan->n_fft) / plan->hop;
+}
+
+extern "C" int hg_mel_plan_create(hg_mel_plan** out_plan, int n_fft, int num_mels, int sampling_rate,
+                                  int hop_size, int win_size, double fmin, double fmax,
+                                  void* stream) {
+  HG_REQUIRE(out_plan, "hg_mel_plan_create: null out_plan");
+  HG_REQUIRE(n_fft == kNfft, "hg_mel_plan_create: only n_fft == 1024 is implemented (got %d)", n_fft);
+  HG_REQUIRE(num_mels > 0 && num_mels <= 128, "hg_mel_plan_create: num_mels out of range");
+  HG_REQUIRE(win_size > 0 && win_size <= n_fft, "hg_mel_plan_create: win_size must be <= n_fft");
+  HG_REQUIRE(hop_size > 0 && hop_size <= n_fft, "hg_mel_plan_create: bad hop_size");
+  hg_mel_plan* p = new hg_mel_plan();
+  p->n_fft = n_fft; p->num_mels = num_mels; p->sampling_rate = sampling_rate;
+  p->hop = hop_size; p->win = win_size; p->pad = (n_fft - hop_size) / 2;
+  p->fmin = fmin;
+  p->fmax = fmax < 0 ? static_cast<double>(sampling_rate / 2) : fmax;  // torchaudio: sr // 2
+
+  // periodic Hann of win_size, centred inside n_fft like torch.stft does
+  p->h_window.assign(n_fft, 0.f);
+  const int left = (n_fft - win_size) / 2;
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int i = 0; i < win_size; ++i)
+    p->h_window[left + i] = static_cast<float>(0.5 - 0.5 * std::cos(two_pi * i / win_size));
+  p->h_tw512.resize(kHalf);
+  for (int m = 0; m < kHalf; ++m)
+    p->h_tw512[m] = make_float2(static_cast<float>(std::cos(two_pi * m / kHalf)),
+                                static_cast<float>(-std::sin(two_pi * m / kHalf)));
+  p->h_tw1024.resize(kHalf + 1);
+  for (int k = 0; k <= kHalf; ++k)
+    p->h_tw1024[k] = make_float2(static_cast<float>(std::cos(two_pi * k / kNfft)),
+                                 static_cast<float>(-std::sin(two_pi * k / kNfft)));
+
+  // HTK triangles, norm=None (torchaudio.functional.melscale_fbanks), as CSR per mel bin
+  const int n_freqs = n_fft / 2 + 1;
+  const double nyq = static_cast<double>(sampling_rate / 2);
+  const double m_min = hz_to_mel_htk(p->fmin), m_max = hz_to_mel_htk(p->fmax);
+  std::vector<double> f_pts(num_mels + 2);
+  for (int i = 0; i < num_mels + 2; ++i)
+    f_pts[i] = mel_to_hz_htk(m_min + (m_max - m_min) * i / (num_mels + 1));
+  p->h_mel_start.assign(num_mels, 0);
+  p->h_mel_off.assign(num_mels + 1, 0);
+  for (int m = 0; m < num_mels; ++m) {
+    const double lo = f_pts[m], ce = f_pts[m + 1], hi = f_pts[m + 2];
+    int first = -1, last = -2;
+    std::vector<float> wts(n_freqs, 0.f);
+    for (int k = 0; k < n_freqs; ++k) {
+      const double f = nyq * k / (n_freqs - 1);
+      const double down = (f - lo) / (ce - lo), up = (hi - f) / (hi - ce);
+      const double w = std::fmax(0.0, std::fmin(down, up));
+      const float wf = static_cast<float>(w);
+      if (wf > 0.f) {
+        if (first < 0) first = k;
+        last = k;
+        wts[k] = wf;
+      }
+    }
+    if (first < 0) { first = 0; last = -1; }
+    p->h_mel_start[m] = first;
+    for (int k = first; k <= last; ++k) p->h_mel_w.push_back(wts[k]);
+    p->h_mel_off[m + 1] = static_cast<int>(p->h_mel_w.size());
+  }
+  p->nnz = static_cast<int>(p->h_mel_w.size());
+  if (p->h_mel_w.empty()) p->h_mel_w.push_back(0.f);
+
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    // host-only plan (CPU emulation in tests); device tables stay null
+    (void)cudaGetLastError();
+    p->window = nullptr; p->tw512 = nullptr; p->tw1024 = nullptr;
+    p->mel_start = nullptr; p->mel_off = nullptr; p->mel_w = nullptr;
+    *out_plan = p;
+    return HG_OK;
+  }
+#define HG_UP(dst, src, type)                                                               \
+  HG_CHECK_CUDA(cudaMalloc(&p->dst, p->src.size() * sizeof(type)));                         \
+  HG_CHECK_CUDA(cudaMemcpyAsync(p->dst, p->src.data(), p->src.size() * sizeof(type),        \
+                                cudaMemcpyHostToDevice, st));
+  HG_UP(window, h_window, float)
+  HG_UP(tw512, h_tw512, float2)
+  HG_UP(tw1024, h_tw1024, float2)
+  HG_UP(mel_start, h_mel_start, int)
+  HG_UP(mel_off, h_mel_off, int)
+  HG_UP(mel_w, h_mel_w, float)
+#undef HG_UP
+  HG_CHECK_CUDA(cudaStreamSynchronize(st));
+  *out_plan = p;
+  return HG_OK;
+}
+
+extern "C" int hg_mel_plan_destroy(hg_mel_plan* p) {
+  if (!p) return HG_OK;
+  if (p->window) cudaFree(p->window);
+  if (p->tw512) cudaFree(p->tw512);
+  if (p->tw1024) cudaFree(p->tw1024);
+  if (p->mel_start) cudaFree(p->mel_start);
+  if (p->mel_off) cudaFree(p->mel_off);
+  if (p->mel_w) cudaFree(p->mel_w);
+  delete p;
+  return HG_OK;
+}
+
+extern "C" int hg_mel_fwd(const hg_mel_plan* plan, const float* y, int batch, int t, float* out,
+                          float* minmax, void* stream) {
+  HG_REQUIRE(plan && y && out, "hg_mel_fwd: null pointer");
+  HG_REQUIRE(plan->window, "hg_mel_fwd: plan has no device tables (created without a GPU)");
+  HG_REQUIRE(batch > 0 && batch <= 65535, "hg_mel_fwd: bad batch %d", batch);
+  HG_REQUIRE(t > plan->pad, "hg_mel_fwd: reflect padding %d needs more than %d samples", plan->pad, t);
+  const int frames = hg_mel_num_frames(plan, t);
+  HG_REQUIRE(frames > 0, "hg_mel_fwd: input too short for one frame");
+  MelArgs a{};
+  a.y = y; a.out = out; a.minmax = minmax;
+  a.batch = batch; a.t = t; a.frames = frames; a.hop = plan->hop; a.pad = plan->pad;
+  a.num_mels = plan->num_mels;
+  a.window = plan->window; a.tw512 = plan->tw512; a.tw1024 = plan->tw1024;
+  a.mel_start = plan->mel_start; a.mel_off = plan->mel_off; a.mel_w = plan->mel_w;
+  a.stage_len = (kFramesPerBlock - 1) * plan->hop + plan->n_fft;
+  const size_t smem = ((a.stage_len * 4 + 15) & ~15) + 2 * kGroups * kPadLen * sizeof(cpx) +
+                      static_cast<size_t>(plan->num_mels) * kFramesPerBlock * sizeof(float);
+  if (smem > 48 * 1024)
+    HG_CHECK_CUDA(cudaFuncSetAttribute(mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+  dim3 grid((frames + kFramesPerBlock - 1) / kFramesPerBlock, batch);
+  mel_kernel<<<grid, kMelThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  HG_CHECK_CUDA(cudaGetLastError());
+  g_hg_launches.fetch_add(1, std::memory_order_relaxed);
+  return HG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// CPU emulation of the kernel's arithmetic (same phase functions, threads serialised).  Test-only
+// entry point: lets the CPU test-suite pin the FFT / un-pack / CSR-mel logic without a GPU.
+// y, out are HOST pointers here.
+extern "C" int hg_mel_emulate_host(const hg_mel_plan* plan, const float* host_y, int batch, int t,
+                                   float* host_out) {
+  HG_REQUIRE(plan && host_y && host_out, "hg_mel_emulate_host: null pointer");
+  const int frames = hg_mel_num_frames(plan, t);
+  HG_REQUIRE(frames > 0 && t > plan->pad, "hg_mel_emulate_host: input too short");
+  std::vector<float> smp(plan->n_fft);
+  std::vector<cpx> z0(kPadLen), z1(kPadLen);
+  std::vector<float> power(kHalf + 1);
+  for (int b = 0; b < batch; ++b)
+    for (int f = 0; f < frames; ++f) {
+      for (int n = 0; n < plan->n_fft; ++n)
+        smp[n] = host_y[static_cast<size_t>(b) * t + reflect_index(f * plan->hop - plan->pad + n, t)];
+      for (int j = 0; j < 64; ++j)
+        fft_pass<true>(j, 1, nullptr, z0.data(), smp.data(), plan->h_window.data(), plan->h_tw512.data());
+      for (int j = 0; j < 64; ++j)
+        fft_pass<false>(j, 8, z0.data(), z1.data(), nullptr, nullptr, plan->h_tw512.data());
+      for (int j = 0; j < 64; ++j)
+        fft_pass<false>(j, 64, z1.data(), z0.data(), nullptr, nullptr, plan->h_tw512.data());
+      for (int j = 0; j < 64; ++j) unpack_power(j, z0.data(), power.data(), plan->h_tw1024.data());
+      float* col = host_out + static_cast<size_t>(b) * plan->num_mels * frames + f;
+      for (int j = 0; j < 64; ++j)
+        mel_project(j, plan->num_mels, power.data(), plan->h_mel_start.data(), plan->h_mel_off.data(),
+                    plan->h_mel_w.data(), col, frames);
+    }
+  return HG_OK;
+}

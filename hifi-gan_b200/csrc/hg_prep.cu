@@ -1,0 +1,245 @@
+// hg_prep.cu — bandwidth-bound helpers around the implicit-GEMM conv:
+//   * weight_norm fold + GEMM-ready bf16 packing (Conv1d and polyphase ConvTranspose1d)
+//   * [B][C][T] fp32 <-> [B][T][C] bf16 layout edges
+//   * conv_post + tanh (src/models.py:113-114)
+#include "hg_common.cuh"
+
+#include <atomic>
+
+#include "../../include/hifigan_b200.h"
+
+extern std::atomic<int64_t> g_hg_launches;
+
+namespace {
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float s = 0.f;
+  for (int i = 0; i < nw; ++i) s += red[i];
+  __syncthreads();
+  return s;
+}
+
+// one block per output channel: w[co] = g[co] * v[co] / ||v[co]||  ->  out[j][co][ci]
+__global__ void pack_conv1d_weight_kernel(const float* __restrict__ v, const float* __restrict__ g,
+                                          int cout, int cin, int k, int cin_pad,
+                                          __nv_bfloat16* __restrict__ out) {
+  __shared__ float red[32];
+  const int co = blockIdx.x;
+  const float* vc = v + static_cast<size_t>(co) * cin * k;
+  float scale = 1.f;
+  if (g) {
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < cin * k; i += blockDim.x) ss += vc[i] * vc[i];
+    ss = block_sum(ss, red);
+    scale = ss > 0.f ? g[co] / sqrtf(ss) : 0.f;  // all-zero rows only exist as channel padding
+  }
+  for (int j = 0; j < k; ++j) {
+    __nv_bfloat16* o = out + (static_cast<size_t>(j) * cout + co) * cin_pad;
+    for (int ci = threadIdx.x; ci < cin_pad; ci += blockDim.x)
+      o[ci] = __float2bfloat16(ci < cin ? vc[ci * k + j] * scale : 0.f);
+  }
+}
+
+// one block per input channel (weight_norm dim 0 of ConvTranspose1d): polyphase scatter
+__global__ void pack_convtr1d_weight_kernel(const float* __restrict__ v, const float* __restrict__ g,
+                                            int cin, int cout, int k, int stride, int padding,
+                                            int nshift, int shift_min,
+                                            __nv_bfloat16* __restrict__ out) {
+  __shared__ float red[32];
+  const int ci = blockIdx.x;
+  const float* vc = v + static_cast<size_t>(ci) * cout * k;
+  float scale = 1.f;
+  if (g) {
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < cout * k; i += blockDim.x) ss += vc[i] * vc[i];
+    ss = block_sum(ss, red);
+    scale = ss > 0.f ? g[ci] / sqrtf(ss) : 0.f;
+  }
+  const int n_total = stride * cout;
+  for (int idx = threadIdx.x; idx < nshift * n_total; idx += blockDim.x) {
+    const int s = idx / n_total;
+    const int n = idx % n_total;
+    const int p = n / cout, co = n % cout;
+    const int j = p + padding - (shift_min + s) * stride;
+    const float w = (j >= 0 && j < k) ? vc[co * k + j] * scale : 0.f;
+    out[(static_cast<size_t>(s) * n_total + n) * cin + ci] = __float2bfloat16(w);
+  }
+}
+
+// fp32 [B][C][T] -> bf16 [B][T][c_pad]; 32x32 smem transpose tiles
+__global__ void ncl_to_nlc_kernel(const float* __restrict__ x, int c, int t, int c_pad,
+                                  __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_act,
+                                  float slope) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int cc = c0 + i, tt = t0 + tx;
+    tile[i][tx] = (cc < c && tt < t) ? x[(static_cast<size_t>(b) * c + cc) * t + tt] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int tt = t0 + i, cc = c0 + tx;
+    if (tt < t && cc < c_pad) {
+      const size_t o = (static_cast<size_t>(b) * t + tt) * c_pad + cc;
+      const float v = tile[tx][i];
+      if (out) out[o] = __float2bfloat16(v);
+      if (out_act) out_act[o] = __float2bfloat16(hg::lrelu(v, slope));
+    }
+  }
+}
+
+// bf16 [B][T][C] -> fp32 [B][C][T]
+__global__ void nlc_to_ncl_kernel(const __nv_bfloat16* __restrict__ x, int t, int c,
+                                  float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int i = ty; i < 32; i += 8) {
+    const int tt = t0 + i, cc = c0 + tx;
+    tile[i][tx] = (tt < t && cc < c) ? __bfloat162float(x[(static_cast<size_t>(b) * t + tt) * c + cc]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int cc = c0 + i, tt = t0 + tx;
+    if (cc < c && tt < t) out[(static_cast<size_t>(b) * c + cc) * t + tt] = tile[tx][i];
+  }
+}
+
+// conv_post + tanh: y[b,t] = tanh(bias + sum_{j,c} x[b, t + j - k/2, c] * w[c][j]).
+// One thread per output sample; the (TT + k - 1) x C input window is staged in shared memory with
+// a 16-byte row pad so the 128-bit row reads of a quarter-warp hit distinct banks.
+constexpr int kPostTile = 256;
+
+__global__ void __launch_bounds__(kPostTile)
+conv_post_tanh_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                      const float* __restrict__ bias, int t, int c, int k, float* __restrict__ y) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  const int pitch = c * 2 + 16;                 // bytes per staged row
+  const int rows = kPostTile + k - 1;
+  float* ws = reinterpret_cast<float*>(sm);     // [k][c]
+  uint8_t* xs = sm + ((k * c * 4 + 15) & ~15);  // [rows][pitch]
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * kPostTile;
+  const int half = k / 2;
+  for (int i = threadIdx.x; i < k * c; i += blockDim.x) {
+    const int j = i / c, cc = i % c;
+    ws[i] = w[cc * k + j];
+  }
+  const int vec_per_row = c / 8;  // uint4 = 8 bf16
+  const __nv_bfloat16* xb = x + static_cast<size_t>(b) * t * c;
+  for (int i = threadIdx.x; i < rows * vec_per_row; i += blockDim.x) {
+    const int r = i / vec_per_row, vq = i % vec_per_row;
+    const int tt = t0 + r - half;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (tt >= 0 && tt < t) val = *reinterpret_cast<const uint4*>(xb + static_cast<size_t>(tt) * c + vq * 8);
+    *reinterpret_cast<uint4*>(xs + r * pitch + vq * 16) = val;
+  }
+  __syncthreads();
+  const int tt = t0 + threadIdx.x;
+  if (tt >= t) return;
+  float acc = bias ? bias[0] : 0.f;
+  for (int j = 0; j < k; ++j) {
+    const uint8_t* row = xs + (threadIdx.x + j) * pitch;
+    const float* wj = ws + j * c;
+    for (int vq = 0; vq < vec_per_row; ++vq) {
+      const uint4 r = *reinterpret_cast<const uint4*>(row + vq * 16);
+      const float2 a = hg::unpack_bf16x2(r.x), bb = hg::unpack_bf16x2(r.y),
+                   cc2 = hg::unpack_bf16x2(r.z), d = hg::unpack_bf16x2(r.w);
+      const float* wq = wj + vq * 8;
+      acc += a.x * wq[0] + a.y * wq[1] + bb.x * wq[2] + bb.y * wq[3] + cc2.x * wq[4] +
+             cc2.y * wq[5] + d.x * wq[6] + d.y * wq[7];
+    }
+  }
+  y[static_cast<size_t>(b) * t + tt] = tanhf(acc);
+}
+
+}  // namespace
+
+extern "C" int hg_pack_conv1d_weight(const float* v, const float* g, int cout, int cin, int k,
+                                     int cin_pad, void* w_packed, void* stream) {
+  HG_REQUIRE(v && w_packed, "hg_pack_conv1d_weight: null pointer");
+  HG_REQUIRE(cout > 0 && cin > 0 && k > 0 && cin_pad >= cin, "hg_pack_conv1d_weight: bad shape");
+  pack_conv1d_weight_kernel<<<cout, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      v, g, cout, cin, k, cin_pad, static_cast<__nv_bfloat16*>(w_packed));
+  HG_CHECK_CUDA(cudaGetLastError());
+  g_hg_launches.fetch_add(1, std::memory_order_relaxed);
+  return HG_OK;
+}
+
+extern "C" int hg_convtr1d_geometry(int k, int stride, int padding, int* host_nshift,
+                                    int* host_shift_min) {
+  HG_REQUIRE(k > 0 && stride > 0 && padding >= 0, "hg_convtr1d_geometry: bad arguments");
+  // shift s = (p + padding - j) / stride for phases p in [0,stride), taps j in [0,k)
+  auto floordiv = [](int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); };
+  const int s_max = floordiv(stride - 1 + padding, stride);
+  const int s_min = -floordiv(k - 1 - padding, stride);  // ceil((padding-(k-1))/stride)
+  if (host_nshift) *host_nshift = s_max - s_min + 1;
+  if (host_shift_min) *host_shift_min = s_min;
+  return HG_OK;
+}
+
+extern "C" int hg_pack_convtr1d_weight(const float* v, const float* g, int cin, int cout, int k,
+                                       int stride, int padding, void* w_packed, void* stream) {
+  HG_REQUIRE(v && w_packed, "hg_pack_convtr1d_weight: null pointer");
+  int nshift = 0, shift_min = 0;
+  int rc = hg_convtr1d_geometry(k, stride, padding, &nshift, &shift_min);
+  if (rc) return rc;
+  pack_convtr1d_weight_kernel<<<cin, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      v, g, cin, cout, k, stride, padding, nshift, shift_min,
+      static_cast<__nv_bfloat16*>(w_packed));
+  HG_CHECK_CUDA(cudaGetLastError());
+  g_hg_launches.fetch_add(1, std::memory_order_relaxed);
+  return HG_OK;
+}
+
+extern "C" int hg_ncl_to_nlc(const float* x, int batch, int c, int t, int c_pad, void* out,
+                             void* out_act, float act_slope, void* stream) {
+  HG_REQUIRE(x && (out || out_act), "hg_ncl_to_nlc: null pointer");
+  HG_REQUIRE(batch > 0 && c > 0 && t > 0 && c_pad >= c, "hg_ncl_to_nlc: bad shape");
+  HG_REQUIRE(batch <= 65535, "hg_ncl_to_nlc: batch too large");
+  dim3 grid((t + 31) / 32, (c_pad + 31) / 32, batch), block(32, 8);
+  ncl_to_nlc_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, c, t, c_pad, static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(out_act),
+      act_slope);
+  HG_CHECK_CUDA(cudaGetLastError());
+  g_hg_launches.fetch_add(1, std::memory_order_relaxed);
+  return HG_OK;
+}
+
+extern "C" int hg_nlc_to_ncl(const void* x, int batch, int t, int c, float* out, void* stream) {
+  HG_REQUIRE(x && out, "hg_nlc_to_ncl: null pointer");
+  HG_REQUIRE(batch > 0 && c > 0 && t > 0, "hg_nlc_to_ncl: bad shape");
+  HG_REQUIRE(batch <= 65535 && (t + 31) / 32 <= 65535, "hg_nlc_to_ncl: grid too large");
+  dim3 grid((c + 31) / 32, (t + 31) / 32, batch), block(32, 8);
+  nlc_to_ncl_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), t, c, out);
+  HG_CHECK_CUDA(cudaGetLastError());
+  g_hg_launches.fetch_add(1, std::memory_order_relaxed);
+  return HG_OK;
+}
+
+extern "C" int hg_conv_post_tanh_fwd(const void* x, const float* w, const float* bias, int batch,
+                                     int t, int c, int k, float* y, void* stream) {
+  HG_REQUIRE(x && w && y, "hg_conv_post_tanh_fwd: null pointer");
+  HG_REQUIRE(batch > 0 && t > 0 && c > 0 && c % 8 == 0 && k > 0 && (k & 1),
+             "hg_conv_post_tanh_fwd: bad shape (c %% 8 == 0, odd k required)");
+  HG_REQUIRE(batch <= 65535, "hg_conv_post_tanh_fwd: batch too large");
+  const size_t smem = ((k * c * 4 + 15) & ~15) + static_cast<size_t>(kPostTile + k - 1) * (c * 2 + 16);
+  HG_REQUIRE(smem <= 200 * 1024, "hg_conv_post_tanh_fwd: window does not fit shared memory");
+  if (smem > 48 * 1024)
+    HG_CHECK_CUDA(cudaFuncSetAttribute(conv_post_tanh_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((t + kPostTile - 1) / kPostTile, batch);
+  conv_post_tanh_kernel<<<grid, kPostTile, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), w, bias, t, c, k, y);
+  HG_CHECK_CUDA(cudaGetLastError());
+  g_hg_launches.fetch_add(1, std::memory_order_relaxed);
+  return HG_OK;
+}

@@ -1,0 +1,172 @@
+"""mel front-end + training-segment sampler — drop-in for the reference's src/meldataset.py.
+
+`mel_spectrogram` keeps the reference signature (meldataset.py:56) and result (log of the HTK power-mel
+of a reflect-padded, Hann-windowed STFT, :59-85) but runs as ONE fused sm_100a kernel (hg_mel_fwd) instead
+of torchaudio's >= 6 launches.  There is no CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import math
+import random
+from ctypes import byref, c_void_p
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+
+MAX_WAV_VALUE = 32768.0
+
+# module-level caches, same names as the reference (meldataset.py:50-53)
+mel_basis: Dict[str, object] = {}
+hann_window: Dict[str, object] = {}
+torch_mels: Dict[str, "_MelPlan"] = {}
+
+_pending_range_checks = []
+
+
+class _MelPlan:
+    """Owns one hg_mel_plan (window, twiddles, CSR filterbank) on one device."""
+
+    def __init__(self, device, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin, fmax):
+        self.device = device
+        self.num_mels = num_mels
+        self.handle = c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib().hg_mel_plan_create(byref(self.handle), n_fft, num_mels, sampling_rate,
+                                                     hop_size, win_size, float(fmin),
+                                                     -1.0 if fmax is None else float(fmax),
+                                                     torch.cuda.current_stream().cuda_stream),
+                       "hg_mel_plan_create")
+
+    def frames(self, t: int) -> int:
+        return _lib.lib().hg_mel_num_frames(self.handle, t)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.lib().hg_mel_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+
+def flush_range_warnings(block: bool = True) -> None:
+    """Print the reference's out-of-range messages (meldataset.py:74-77) for finished calls.  The reference
+    pays two blocking host syncs per call for this; here the min/max come from a fused reduction and are read
+    lazily — on the next call for whatever already finished, or here with block=True."""
+    keep = []
+    for ev, host in _pending_range_checks:
+        if block:
+            ev.synchronize()
+        elif not ev.query():
+            keep.append((ev, host))
+            continue
+        lo, hi = host[0].item(), host[1].item()
+        if lo < -1.:
+            print('min value is ', torch.tensor(lo))
+        if hi > 1.:
+            print('max value is ', torch.tensor(hi))
+    _pending_range_checks[:] = keep
+
+
+def mel_spectrogram(y, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin, fmax, center=False):
+    """y [B,T] fp32 on a CUDA device -> [B,num_mels,frames] fp32 (reference meldataset.py:56-85)."""
+    if not y.is_cuda:
+        raise RuntimeError(f"mel_spectrogram: hifigan_b200 has no CPU path (got {y.device})")
+    if center:
+        raise NotImplementedError("center=True is never used by the reference (meldataset.py:152-176)")
+    mel_key = f'{str(y.device)}_{n_fft}_{num_mels}_{sampling_rate}_{hop_size}_{win_size}_{fmin}_{fmax}_{center}'
+    plan = torch_mels.get(mel_key)
+    if plan is None:
+        plan = _MelPlan(y.device, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin, fmax)
+        torch_mels[mel_key] = plan
+    squeeze = y.dim() == 1
+    y2 = y.reshape(1, -1) if squeeze else y
+    if y2.dim() != 2:
+        raise ValueError(f"mel_spectrogram expects [B,T], got {tuple(y.shape)}")
+    y2 = y2.contiguous()
+    if y2.dtype != torch.float32:
+        y2 = y2.float()
+    b, t = y2.shape
+    frames = plan.frames(t)
+    out = torch.empty(b, num_mels, frames, dtype=torch.float32, device=y.device)
+    minmax = torch.tensor([float("inf"), float("-inf")], dtype=torch.float32, device=y.device)
+    stream = torch.cuda.current_stream()
+    _lib.check(_lib.lib().hg_mel_fwd(plan.handle, y2.data_ptr(), b, t, out.data_ptr(), minmax.data_ptr(),
+                                     stream.cuda_stream), "hg_mel_fwd")
+    host = torch.empty(2, dtype=torch.float32, pin_memory=True)
+    host.copy_(minmax, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(stream)
+    _pending_range_checks.append((ev, host))
+    flush_range_warnings(block=False)
+    return out[0] if squeeze else out
+
+
+def load_wav(full_path):
+    """reference meldataset.py:15-17 (file IO is outside the accelerated path)."""
+    import torchaudio
+    data, sampling_rate = torchaudio.load(full_path, normalize=True)
+    return data, sampling_rate
+
+
+def save_wav(full_path, data, sampling_rate):
+    import torchaudio
+    torchaudio.save(full_path, data, sampling_rate)
+
+
+def dynamic_range_compression_torch(x, C=1, clip_val=1e-5):
+    return torch.log(torch.clamp(x, min=clip_val) * C)
+
+
+def dynamic_range_decompression_torch(x, C=1):
+    return torch.exp(x) / C
+
+
+def spectral_normalize_torch(magnitudes):
+    return dynamic_range_compression_torch(magnitudes)
+
+
+def spectral_de_normalize_torch(magnitudes):
+    return dynamic_range_decompression_torch(magnitudes)
+
+
+class SegmentSampler:
+    """Batched GPU form of MelDataset.__getitem__'s crop/pad rule (reference meldataset.py:141-150):
+    utterances live in one resident device pool; a batch is B (utterance, start) pairs drawn with the
+    reference's `random.randint(0, len - seg)` rule, gathered into [B, seg] and fed to two fused mel calls
+    (input mel with fmax, loss mel with fmax_loss, meldataset.py:152-154,174-176)."""
+
+    def __init__(self, utterances, segment_length, n_fft, num_mels, hop_size, win_size, sampling_rate, fmin,
+                 fmax, fmax_loss=None, seed=1234, device="cuda"):
+        self.device = torch.device(device)
+        self.segment_length = segment_length
+        self.mel_args = (n_fft, num_mels, sampling_rate, hop_size, win_size, fmin)
+        self.fmax, self.fmax_loss = fmax, fmax_loss
+        self.lengths = [int(u.numel()) for u in utterances]
+        self.offsets = [0]
+        for n in self.lengths:
+            self.offsets.append(self.offsets[-1] + n)
+        self.pool = torch.cat([u.reshape(-1).float() for u in utterances]).to(self.device)
+        self.rng = random.Random(seed)
+
+    def draw(self, indices):
+        """(pool offset, valid length) per item, following the reference's inclusive randint rule."""
+        seg, picks = self.segment_length, []
+        for i in indices:
+            n = self.lengths[i]
+            start = self.rng.randint(0, n - seg) if n >= seg else 0
+            picks.append((self.offsets[i] + start, min(n, seg)))
+        return picks
+
+    def batch(self, indices):
+        picks = self.draw(indices)
+        seg = self.segment_length
+        starts = torch.tensor([p[0] for p in picks], device=self.device).unsqueeze(1)
+        valid = torch.tensor([p[1] for p in picks], device=self.device).unsqueeze(1)
+        ar = torch.arange(seg, device=self.device).unsqueeze(0)
+        idx = (starts + ar).clamp_(max=self.pool.numel() - 1)
+        audio = torch.where(ar < valid, self.pool[idx], torch.zeros((), device=self.device))
+        mel = mel_spectrogram(audio, *self.mel_args, self.fmax, center=False)
+        mel_loss = mel_spectrogram(audio, *self.mel_args, self.fmax_loss, center=False)
+        return mel, audio, mel_loss

@@ -1,0 +1,522 @@
+"""HiFi-GAN vocoder models on hand-written sm_100a kernels — drop-in for the reference's src/models.py.
+
+Same public names, constructor arguments, attribute names and state_dict keys as the reference
+(`Generator` models.py:75-125, `ResBlock1` :11-48, `ResBlock2` :51-72, the discriminators :128-248 and the
+three losses :251-282), so existing configs and checkpoints load unchanged.  The torch modules held by
+these classes are *parameter containers only*: their `forward` is never called.  All arithmetic of
+`Generator.forward` runs in libhifigan_b200.so (include/hifigan_b200.h):
+
+    mel fp32 [B,80,F] --hg_ncl_to_nlc--> bf16 [B,F,128]
+      --hg_conv1d_fwd (conv_pre, epilogue: bias + leaky_relu 0.1)-->
+      per stage: hg_conv1d_fwd on polyphase-packed ConvTranspose1d weights  (raw + leaky_relu'd outputs)
+                 3 MRF branches x (conv, conv) x 3 via hg_conv1d_fwd; residual add, branch average and the
+                 next leaky_relu are fused into the last conv's epilogue
+      --hg_conv_post_tanh_fwd--> fp32 [B,1,T]
+
+Numerics (declared): bf16 operands and bf16-stored activations, fp32 accumulation and epilogue math.
+There is no CPU path and no fallback: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import warnings
+from ctypes import byref, c_int
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+from torch.nn import AvgPool1d, Conv1d, Conv2d, ConvTranspose1d
+from torch.nn.utils import remove_weight_norm, spectral_norm, weight_norm
+
+from . import _lib
+from .utils import get_padding, init_weights
+
+LRELU_SLOPE = 0.1
+
+
+def _wn(module: nn.Module) -> nn.Module:
+    """Old-style weight_norm (keys weight_g / weight_v) — the checkpoint contract."""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return weight_norm(module)
+
+
+def _pad_ch(c: int) -> int:
+    """Channel count as laid out in HBM: 32, or a multiple of 64 (one 128-byte swizzle row per 64)."""
+    return 32 if c <= 32 else (c + 63) // 64 * 64
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(x: torch.Tensor, what: str) -> None:
+    if not x.is_cuda:
+        raise RuntimeError(f"{what}: hifigan_b200 has no CPU path; move the tensor to a B200 (got {x.device})")
+
+
+def _g_v(m: nn.Module) -> Tuple[Optional[torch.Tensor], torch.Tensor]:
+    """(g, v) while weight_norm is attached, (None, weight) after remove_weight_norm."""
+    if hasattr(m, "weight_g"):
+        return m.weight_g, m.weight_v
+    return None, m.weight
+
+
+class _PackedConv:
+    """One conv layer in GEMM-ready form: bf16 [taps][cout_p][cin_p] + fp32 bias [cout_p]."""
+
+    __slots__ = ("module", "kind", "cin", "cout", "cin_p", "cout_p", "taps", "dil", "pad_left", "stride",
+                 "w", "bias", "key")
+
+    def __init__(self, module: nn.Module, kind: str, device):
+        self.module, self.kind = module, kind
+        g, v = _g_v(module)
+        if kind == "conv":
+            cout, cin, k = v.shape
+            self.cin, self.cout, self.taps = cin, cout, k
+            self.dil = module.dilation[0]
+            self.pad_left = module.padding[0]
+            self.stride = 1
+            self.cin_p, self.cout_p = _pad_ch(cin), _pad_ch(cout)
+            n_rows = self.cout_p
+        else:  # ConvTranspose1d -> polyphase 1-D conv producing [T_in][stride*cout_p]
+            cin, cout, k = v.shape
+            u, pad = module.stride[0], module.padding[0]
+            nshift, smin = c_int(), c_int()
+            _lib.check(_lib.lib().hg_convtr1d_geometry(k, u, pad, byref(nshift), byref(smin)))
+            if k - 2 * pad != u or module.output_padding[0] != 0:
+                raise NotImplementedError("ConvTranspose1d must satisfy out_len == stride * in_len")
+            self.cin, self.cout, self.taps = cin, cout, nshift.value
+            self.dil, self.pad_left, self.stride = 1, -smin.value, u
+            self.cin_p, self.cout_p = _pad_ch(cin), _pad_ch(cout)
+            n_rows = u * self.cout_p
+        self.w = torch.empty(self.taps, n_rows, self.cin_p, dtype=torch.bfloat16, device=device)
+        self.bias = torch.zeros(n_rows, dtype=torch.float32, device=device)
+        self.key = None
+
+    def _fingerprint(self):
+        g, v = _g_v(self.module)
+        b = self.module.bias
+        return tuple((t.data_ptr(), t._version) for t in (g, v, b) if t is not None)
+
+    def refresh(self) -> None:
+        """(Re)pack when a parameter changed: weight_norm fold + bf16 GEMM layout (hg_pack_*)."""
+        key = self._fingerprint()
+        if key == self.key:
+            return
+        L = _lib.lib()
+        m = self.module
+        g, v = _g_v(m)
+        dev = self.w.device
+        v = v.detach().to(device=dev, dtype=torch.float32)
+        g = None if g is None else g.detach().to(device=dev, dtype=torch.float32).reshape(-1)
+        b = m.bias.detach().to(device=dev, dtype=torch.float32) if m.bias is not None else None
+        if self.kind == "conv":
+            if self.cout_p != self.cout:  # zero rows for padded output channels
+                v = torch.cat([v, v.new_zeros(self.cout_p - self.cout, *v.shape[1:])], 0)
+                if g is not None:
+                    g = torch.cat([g, g.new_zeros(self.cout_p - self.cout)], 0)
+            v = v.contiguous()
+            _lib.check(L.hg_pack_conv1d_weight(v.data_ptr(), 0 if g is None else g.contiguous().data_ptr(),
+                                               self.cout_p, self.cin, self.taps, self.cin_p,
+                                               self.w.data_ptr(), _stream()), "hg_pack_conv1d_weight")
+            self.bias.zero_()
+            if b is not None:
+                self.bias[: self.cout].copy_(b)
+        else:
+            k = m.kernel_size[0]
+            if self.cout_p != self.cout or self.cin_p != self.cin:
+                vp = v.new_zeros(self.cin_p, self.cout_p, k)
+                vp[: self.cin, : self.cout] = v
+                v = vp
+                if g is not None:
+                    g = torch.cat([g, g.new_zeros(self.cin_p - self.cin)], 0)
+            v = v.contiguous()
+            _lib.check(L.hg_pack_convtr1d_weight(v.data_ptr(), 0 if g is None else g.contiguous().data_ptr(),
+                                                 self.cin_p, self.cout_p, k, self.stride, m.padding[0],
+                                                 self.w.data_ptr(), _stream()), "hg_pack_convtr1d_weight")
+            self.bias.zero_()
+            if b is not None:
+                self.bias.view(self.stride, self.cout_p)[:, : self.cout].copy_(b.unsqueeze(0).expand(self.stride, -1))
+        self.key = key
+
+
+def _conv(L, x, pc: _PackedConv, batch: int, t: int, *, res=(None, None, None), scale=1.0,
+          out_raw=None, out_act=None, slope=LRELU_SLOPE) -> None:
+    p = [0 if r is None else r.data_ptr() for r in res]
+    _lib.check(L.hg_conv1d_fwd(x.data_ptr(), pc.w.data_ptr(), pc.bias.data_ptr(), batch, t, pc.cin_p,
+                               pc.w.shape[1], pc.taps, pc.dil, pc.pad_left, p[0], p[1], p[2], scale,
+                               0 if out_raw is None else out_raw.data_ptr(),
+                               0 if out_act is None else out_act.data_ptr(), slope, _stream()),
+               "hg_conv1d_fwd")
+
+
+def _resblock_chain(L, block: "nn.Module", packs: List[_PackedConv], batch: int, t: int, c_p: int,
+                    x_raw, x_act, bufs: Dict[str, torch.Tensor], final) -> None:
+    """Run one ResBlock (type 1: packs = [c1_0, c2_0, c1_1, ...]; type 2: packs = [c_0, c_1, ...]).
+    `final(conv_kwargs)` issues the LAST conv of the block (so the caller can fuse the MRF average)."""
+    two_conv = isinstance(block, ResBlock1)
+    steps = len(packs) // 2 if two_conv else len(packs)
+    cur_raw, cur_act = x_raw, x_act
+    ping = [(bufs["a_raw"], bufs["a_act"]), (bufs["b_raw"], bufs["b_act"])]
+    for i in range(steps):
+        last = i == steps - 1
+        if two_conv:
+            _conv(L, cur_act, packs[2 * i], batch, t, out_act=bufs["t1"])
+            src, pc = bufs["t1"], packs[2 * i + 1]
+        else:
+            src, pc = cur_act, packs[i]
+        if last:
+            final(dict(x=src, pc=pc, res0=cur_raw))
+        else:
+            nr, na = ping[i & 1]
+            _conv(L, src, pc, batch, t, res=(cur_raw, None, None), out_raw=nr, out_act=na)
+            cur_raw, cur_act = nr, na
+
+
+class _StandaloneBlockMixin:
+    """forward() for a ResBlock used on its own (x fp32 [B,C,T] -> fp32 [B,C,T]) on the same kernels."""
+
+    def _packs(self, device) -> List[_PackedConv]:
+        cache = self.__dict__.setdefault("_hg_packs", None)
+        convs = self._ordered_convs()
+        if cache is None or cache[0].w.device != device:
+            cache = [_PackedConv(m, "conv", device) for m in convs]
+            self.__dict__["_hg_packs"] = cache
+        for pc in cache:
+            pc.refresh()
+        return cache
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        _require_cuda(x, type(self).__name__)
+        L = _lib.lib()
+        b, c, t = x.shape
+        packs = self._packs(x.device)
+        c_p = packs[0].cin_p
+        mk = lambda: torch.empty(b, t, c_p, dtype=torch.bfloat16, device=x.device)
+        bufs = {k: mk() for k in ("x_raw", "x_act", "t1", "a_raw", "a_act", "b_raw", "b_act", "out")}
+        xin = x.contiguous().float()
+        _lib.check(L.hg_ncl_to_nlc(xin.data_ptr(), b, c, t, c_p, bufs["x_raw"].data_ptr(),
+                                   bufs["x_act"].data_ptr(), LRELU_SLOPE, _stream()), "hg_ncl_to_nlc")
+
+        def final(kw):
+            _conv(L, kw["x"], kw["pc"], b, t, res=(kw["res0"], None, None), out_raw=bufs["out"])
+
+        _resblock_chain(L, self, packs, b, t, c_p, bufs["x_raw"], bufs["x_act"], bufs, final)
+        y = torch.empty(b, c_p, t, dtype=torch.float32, device=x.device)
+        _lib.check(L.hg_nlc_to_ncl(bufs["out"].data_ptr(), b, t, c_p, y.data_ptr(), _stream()), "hg_nlc_to_ncl")
+        return y[:, :c].contiguous() if c_p != c else y
+
+
+class ResBlock1(_StandaloneBlockMixin, torch.nn.Module):
+    """3 x (lrelu -> dilated conv -> lrelu -> conv -> + x); reference src/models.py:11-48."""
+
+    def __init__(self, h, channels, kernel_size=3, dilation=(1, 3, 5)):
+        super().__init__()
+        self.h = h
+
+        def conv(d):
+            return _wn(Conv1d(channels, channels, kernel_size, 1, dilation=d,
+                              padding=get_padding(kernel_size, d)))
+
+        # creation / init order fixes the RNG stream; it is part of same-seed parity
+        self.convs1 = nn.ModuleList([conv(d) for d in dilation[:3]])
+        self.convs1.apply(init_weights)
+        self.convs2 = nn.ModuleList([conv(1) for _ in dilation[:3]])
+        self.convs2.apply(init_weights)
+
+    def _ordered_convs(self):
+        out = []
+        for c1, c2 in zip(self.convs1, self.convs2):
+            out += [c1, c2]
+        return out
+
+    def remove_weight_norm(self):
+        for m in list(self.convs1) + list(self.convs2):
+            remove_weight_norm(m)
+
+
+class ResBlock2(_StandaloneBlockMixin, torch.nn.Module):
+    """2 x (lrelu -> dilated conv -> + x); reference src/models.py:51-72."""
+
+    def __init__(self, h, channels, kernel_size=3, dilation=(1, 3)):
+        super().__init__()
+        self.h = h
+        self.convs = nn.ModuleList([
+            _wn(Conv1d(channels, channels, kernel_size, 1, dilation=d, padding=get_padding(kernel_size, d)))
+            for d in dilation[:2]])
+        self.convs.apply(init_weights)
+
+    def _ordered_convs(self):
+        return list(self.convs)
+
+    def remove_weight_norm(self):
+        for m in self.convs:
+            remove_weight_norm(m)
+
+
+class _GeneratorEngine:
+    """Packed weights, workspaces and the kernel sequence of one Generator on one device."""
+
+    def __init__(self, gen: "Generator", device):
+        self.gen, self.device = gen, device
+        self.pre = _PackedConv(gen.conv_pre, "conv", device)
+        self.ups = [_PackedConv(m, "convtr", device) for m in gen.ups]
+        self.blocks = [[_PackedConv(m, "conv", device) for m in rb._ordered_convs()] for rb in gen.resblocks]
+        post = gen.conv_post
+        self.post_cin_p = _pad_ch(post.in_channels)
+        self.post_w = torch.zeros(self.post_cin_p, post.kernel_size[0], dtype=torch.float32, device=device)
+        self.post_b = torch.zeros(1, dtype=torch.float32, device=device)
+        self.post_key = None
+        self.ws: Dict[Tuple[int, int], Dict[str, torch.Tensor]] = {}
+
+    def refresh(self) -> None:
+        self.pre.refresh()
+        for pc in self.ups:
+            pc.refresh()
+        for blk in self.blocks:
+            for pc in blk:
+                pc.refresh()
+        post = self.gen.conv_post
+        g, v = _g_v(post)
+        key = tuple((t.data_ptr(), t._version) for t in (g, v, post.bias) if t is not None)
+        if key != self.post_key:
+            # single output channel: fold on the device with torch (4 x 224 floats, not a hot path)
+            v32 = v.detach().to(self.device, torch.float32)
+            w = v32 if g is None else v32 * (g.detach().to(self.device, torch.float32)
+                                             / v32.pow(2).sum(dim=(1, 2), keepdim=True).sqrt())
+            self.post_w.zero_()
+            self.post_w[: post.in_channels].copy_(w[0])
+            self.post_b.copy_(post.bias.detach().to(self.device, torch.float32))
+            self.post_key = key
+
+    def workspace(self, batch: int, frames: int) -> Dict[str, torch.Tensor]:
+        key = (batch, frames)
+        ws = self.ws.get(key)
+        if ws is not None:
+            return ws
+        gen = self.gen
+        dev = self.device
+        t, sizes = frames, []
+        for pc in self.ups:
+            t *= pc.stride
+            sizes.append(batch * t * pc.cout_p)
+        biggest = max(sizes)
+        bf = lambda n: torch.empty(n, dtype=torch.bfloat16, device=dev)
+        ws = {"mel": bf(batch * frames * self.pre.cin_p), "pre": bf(batch * frames * self.pre.cout_p)}
+        names = ["x_raw", "x_act", "t1", "a_raw", "a_act", "b_raw", "b_act", "stage_out"]
+        names += [f"r{j}" for j in range(max(1, gen.num_kernels - 1))]
+        for n in names:
+            ws[n] = bf(biggest)
+        ws["y"] = torch.empty(batch, 1, t, dtype=torch.float32, device=dev)
+        if len(self.ws) >= 4:  # bound the cache: workspaces for config 2 are ~10 GB
+            self.ws.pop(next(iter(self.ws)))
+        self.ws[key] = ws
+        return ws
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        L = _lib.lib()
+        gen = self.gen
+        self.refresh()
+        b, c, frames = x.shape
+        ws = self.workspace(b, frames)
+        xin = x.contiguous()
+        if xin.dtype != torch.float32:
+            xin = xin.float()
+        _lib.check(L.hg_ncl_to_nlc(xin.data_ptr(), b, c, frames, self.pre.cin_p, ws["mel"].data_ptr(), 0, 0.0,
+                                   _stream()), "hg_ncl_to_nlc")
+        # conv_pre; its only consumer is leaky_relu -> ups[0] (models.py:101-104)
+        _conv(L, ws["mel"], self.pre, b, frames, out_act=ws["pre"])
+        cur, t = ws["pre"], frames
+        nk = gen.num_kernels
+        for i, up in enumerate(self.ups):
+            _conv(L, cur, up, b, t, out_raw=ws["x_raw"], out_act=ws["x_act"])
+            t *= up.stride
+            c_p = up.cout_p
+            last_stage = i == len(self.ups) - 1
+            out_slope = 0.01 if last_stage else LRELU_SLOPE  # models.py:112 uses the default slope
+            for j in range(nk):
+                blk = gen.resblocks[i * nk + j]
+                packs = self.blocks[i * nk + j]
+
+                def final(kw, j=j):
+                    if j < nk - 1:
+                        # branch result; branches >= 2 of a wide MRF chain onto the running sum
+                        extra = ws[f"r{j - 1}"] if (nk > 3 and j > 0) else None
+                        _conv(L, kw["x"], kw["pc"], b, t, res=(kw["res0"], extra, None), out_raw=ws[f"r{j}"])
+                    else:
+                        if nk > 3:
+                            others = (ws[f"r{nk - 2}"], None)
+                        else:
+                            others = tuple(ws[f"r{q}"] for q in range(nk - 1)) + (None,) * (3 - nk)
+                        _conv(L, kw["x"], kw["pc"], b, t, res=(kw["res0"],) + others, scale=1.0 / nk,
+                              out_act=ws["stage_out"], slope=out_slope)
+
+                _resblock_chain(L, blk, packs, b, t, c_p, ws["x_raw"], ws["x_act"], ws, final)
+            cur = ws["stage_out"]
+        post = gen.conv_post
+        _lib.check(L.hg_conv_post_tanh_fwd(cur.data_ptr(), self.post_w.data_ptr(), self.post_b.data_ptr(), b, t,
+                                           self.post_cin_p, post.kernel_size[0], ws["y"].data_ptr(), _stream()),
+                   "hg_conv_post_tanh_fwd")
+        return ws["y"]
+
+
+class Generator(torch.nn.Module):
+    """mel [B,80,F] -> waveform [B,1,F*prod(upsample_rates)]; reference src/models.py:75-125."""
+
+    def __init__(self, h):
+        super().__init__()
+        self.h = h
+        self.num_kernels = len(h.resblock_kernel_sizes)
+        self.num_upsamples = len(h.upsample_rates)
+        width = h.upsample_initial_channel
+        self.conv_pre = _wn(Conv1d(80, width, 7, 1, padding=3))
+        block_cls = ResBlock1 if h.resblock == '1' else ResBlock2  # string compare, as the reference
+
+        self.ups = nn.ModuleList()
+        for level, (rate, ksize) in enumerate(zip(h.upsample_rates, h.upsample_kernel_sizes)):
+            self.ups.append(_wn(ConvTranspose1d(width >> level, width >> (level + 1), ksize, rate,
+                                                padding=(ksize - rate) // 2)))
+        self.resblocks = nn.ModuleList()
+        for level in range(len(self.ups)):
+            ch = width >> (level + 1)
+            for ksize, dil in zip(h.resblock_kernel_sizes, h.resblock_dilation_sizes):
+                self.resblocks.append(block_cls(h, ch, ksize, dil))
+        self.conv_post = _wn(Conv1d(ch, 1, 7, 1, padding=3))
+        self.ups.apply(init_weights)
+        self.conv_post.apply(init_weights)
+        self.__dict__["_hg_engines"] = {}
+
+    def _engine(self, device) -> _GeneratorEngine:
+        engines = self.__dict__.setdefault("_hg_engines", {})
+        eng = engines.get(device)
+        if eng is None:
+            eng = _GeneratorEngine(self, device)
+            engines[device] = eng
+        return eng
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """Returns a view of an engine-owned buffer that the next forward() with the same shape
+        overwrites; `.clone()` it to keep it (the reference allocates a fresh tensor per call)."""
+        _require_cuda(x, "Generator.forward")
+        if torch.is_grad_enabled() and self.training and (
+                x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError("Generator backward kernels are not built yet (SURVEY §8 row T); "
+                                      "call under torch.no_grad() or .eval()")
+        if x.dim() != 3 or x.shape[1] != self.conv_pre.in_channels:
+            raise ValueError(f"expected [B,{self.conv_pre.in_channels},F], got {tuple(x.shape)}")
+        return self._engine(x.device).forward(x)
+
+    def _drop_engines(self):
+        self.__dict__["_hg_engines"] = {}
+
+    def remove_weight_norm(self):
+        print('Removing weight norm...')
+        for m in self.ups:
+            remove_weight_norm(m)
+        for blk in self.resblocks:
+            blk.remove_weight_norm()
+        remove_weight_norm(self.conv_pre)
+        remove_weight_norm(self.conv_post)
+        self._drop_engines()
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._drop_engines()
+        return out
+
+
+# --------------------------------------------------------------------------------------------------
+# Discriminators: parameter containers with the reference's exact module tree / state_dict keys
+# (src/models.py:128-248).  Their CUDA forward/backward kernels (SURVEY §8 rows PD/MPD/SD/MSD, K5-K8)
+# are not built yet, and there is deliberately no library fallback: forward raises.
+# --------------------------------------------------------------------------------------------------
+class DiscriminatorP(torch.nn.Module):
+    def __init__(self, period, kernel_size=5, stride=3, use_spectral_norm=False):
+        super().__init__()
+        self.period = period
+        norm_f = spectral_norm if use_spectral_norm else _wn
+        widths = [1, 32, 128, 512, 1024]
+        layers = [norm_f(Conv2d(ci, co, (kernel_size, 1), (stride, 1), padding=(get_padding(5, 1), 0)))
+                  for ci, co in zip(widths[:-1], widths[1:])]
+        layers.append(norm_f(Conv2d(1024, 1024, (kernel_size, 1), 1, padding=(2, 0))))
+        self.convs = nn.ModuleList(layers)
+        self.conv_post = norm_f(Conv2d(1024, 1, (3, 1), 1, padding=(1, 0)))
+
+    def forward(self, x):
+        raise NotImplementedError("DiscriminatorP CUDA kernels (hg_mpd_conv_*) are not built yet; "
+                                  "hifigan_b200 has no library/CPU fallback")
+
+
+class MultiPeriodDiscriminator(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.discriminators = nn.ModuleList([DiscriminatorP(p) for p in (2, 3, 5, 7, 11)])
+
+    def forward(self, y, y_hat):
+        y_d_rs, y_d_gs, fmap_rs, fmap_gs = [], [], [], []
+        for d in self.discriminators:
+            y_d_r, fmap_r = d(y)
+            y_d_g, fmap_g = d(y_hat)
+            y_d_rs.append(y_d_r); fmap_rs.append(fmap_r)
+            y_d_gs.append(y_d_g); fmap_gs.append(fmap_g)
+        return y_d_rs, y_d_gs, fmap_rs, fmap_gs
+
+
+class DiscriminatorS(torch.nn.Module):
+    _SPEC = [(1, 128, 15, 1, 1, 7), (128, 128, 41, 2, 4, 20), (128, 256, 41, 2, 16, 20),
+             (256, 512, 41, 4, 16, 20), (512, 1024, 41, 4, 16, 20), (1024, 1024, 41, 1, 16, 20),
+             (1024, 1024, 5, 1, 1, 2)]
+
+    def __init__(self, use_spectral_norm=False):
+        super().__init__()
+        norm_f = spectral_norm if use_spectral_norm else _wn
+        self.convs = nn.ModuleList([norm_f(Conv1d(ci, co, k, s, groups=g, padding=p))
+                                    for ci, co, k, s, g, p in self._SPEC])
+        self.conv_post = norm_f(Conv1d(1024, 1, 3, 1, padding=1))
+
+    def forward(self, x):
+        raise NotImplementedError("DiscriminatorS CUDA kernels (grouped/strided conv) are not built yet; "
+                                  "hifigan_b200 has no library/CPU fallback")
+
+
+class MultiScaleDiscriminator(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.discriminators = nn.ModuleList([DiscriminatorS(use_spectral_norm=True), DiscriminatorS(),
+                                             DiscriminatorS()])
+        self.meanpools = nn.ModuleList([AvgPool1d(4, 2, padding=2), AvgPool1d(4, 2, padding=2)])
+
+    def forward(self, y, y_hat):
+        raise NotImplementedError("MultiScaleDiscriminator CUDA kernels are not built yet; "
+                                  "hifigan_b200 has no library/CPU fallback")
+
+
+def feature_loss(fmap_r, fmap_g):
+    """2 * sum of mean |r - g| over all feature maps; reference src/models.py:251-257."""
+    total = 0
+    for maps_r, maps_g in zip(fmap_r, fmap_g):
+        for r, g in zip(maps_r, maps_g):
+            total = total + torch.mean(torch.abs(r - g))
+    return total * 2
+
+
+def discriminator_loss(disc_real_outputs, disc_generated_outputs):
+    """LSGAN discriminator loss; per-sub-discriminator floats for logging; reference :260-271.
+    The 2*N scalars cross to the host in ONE transfer instead of the reference's 2*N `.item()` syncs."""
+    total, parts = 0, []
+    for dr, dg in zip(disc_real_outputs, disc_generated_outputs):
+        r_loss = torch.mean((1 - dr) ** 2)
+        g_loss = torch.mean(dg ** 2)
+        total = total + (r_loss + g_loss)
+        parts += [r_loss.detach(), g_loss.detach()]
+    host = torch.stack(parts).tolist() if parts else []
+    return total, host[0::2], host[1::2]
+
+
+def generator_loss(disc_outputs):
+    """LSGAN generator loss; returns (sum, [per-sub-discriminator tensors]); reference :274-282."""
+    gen_losses = [torch.mean((1 - dg) ** 2) for dg in disc_outputs]
+    total = 0
+    for l in gen_losses:
+        total = total + l
+    return total, gen_losses

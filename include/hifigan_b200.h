@@ -1,0 +1,133 @@
+/* hifigan_b200.h — C-ABI of libhifigan_b200.so (sm_100a kernels for the HiFi-GAN vocoder hot path).
+ *
+ * The reference (AlonKellner/hifi-gan) has no FFI layer: its hot path is the Python module API
+ * of src/models.py and src/meldataset.py, whose arithmetic is delegated to torch / torchaudio
+ * library ops.  Each entry point below replaces one of those library call
+ * sites; the Python host in hifi-gan_b200/ mirrors the reference classes and calls these through
+ * ctypes.  No torch types cross this boundary: plain device pointers, sizes and a cudaStream_t
+ * passed as void*.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative code on failure; hg_last_error() returns
+ *     the message of the last failure on the calling thread.
+ *   - all pointers are DEVICE pointers unless the parameter name starts with `host_`.
+ *   - the library never allocates device memory; workspaces are supplied by the caller.
+ *   - activations between kernels are channels-last in time: bf16 [B][T][C] ("NLC"), so that the
+ *     GEMM K dimension (channels) is contiguous for TMA / UMMA.  The public Python API keeps the
+ *     reference's fp32 [B][C][T] tensors at its edges.
+ *   - arithmetic: bf16 operands, fp32 accumulate (tcgen05.mma kind::f16), fp32 epilogue math.
+ */
+#ifndef HIFIGAN_B200_H
+#define HIFIGAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HG_ABI_VERSION 1
+
+/* Library identity / diagnostics. */
+const char* hg_version(void);
+const char* hg_last_error(void);
+int hg_abi_version(void);
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+int64_t hg_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Weight preparation (replaces torch.nn.utils.weight_norm's per-forward recompute,
+ * reference call sites src/models.py:16-31,56-59,81,86-88,96; fold = remove_weight_norm
+ * src/models.py:44-48,70-72,118-125).
+ *
+ * hg_pack_conv1d_weight: v fp32 [Cout][Cin][k] (+ optional g fp32 [Cout]; w = g * v / ||v||_2
+ * over (Cin,k) per output channel) -> bf16 [k][Cout][cin_pad], zero-filled for ci >= Cin.
+ * With g == NULL, v is taken as the already-folded `weight`.
+ */
+int hg_pack_conv1d_weight(const float* v, const float* g, int cout, int cin, int k, int cin_pad,
+                          void* w_packed, void* stream);
+
+/* Polyphase geometry of ConvTranspose1d(k, stride, padding) (src/models.py:84-88): every output
+ * phase p in [0,stride) of out[t*stride + p] reads inputs x[t + s] for a few shifts s; the union
+ * over phases is the contiguous range [shift_min, shift_min + nshift).  Host-only helper. */
+int hg_convtr1d_geometry(int k, int stride, int padding, int* host_nshift, int* host_shift_min);
+
+/* hg_pack_convtr1d_weight: v fp32 [Cin][Cout][k] (+ optional g fp32 [Cin]; weight_norm dim 0 of a
+ * ConvTranspose1d is the INPUT channel) -> bf16
+ * [nshift][stride*Cout][Cin]: slot (s, p*Cout+co, ci) holds w[ci][co][j] with
+ * j = p + padding - (shift_min + s)*stride when 0 <= j < k, else 0.  Running hg_conv1d_fwd with
+ * ktaps = nshift, pad_left = -shift_min on it yields [B][T_in][stride*Cout] == [B][T_in*stride][Cout]. */
+int hg_pack_convtr1d_weight(const float* v, const float* g, int cin, int cout, int k, int stride,
+                            int padding, void* w_packed, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * hg_conv1d_fwd — stride-1 dilated Conv1d as a tcgen05/TMEM implicit GEMM fed by TMA.
+ * Replaces torch Conv1d at src/models.py:35-42,63-68 (ResBlock1/2), :101 (conv_pre) and, through
+ * the polyphase packing above, ConvTranspose1d at :104.
+ *
+ *   acc[b,t,co] = sum_{j<ktaps} sum_{ci<cin} x[b, t + j*dilation - pad_left, ci] * w[j][co][ci]
+ *   v           = (acc + bias[co] + res0 + res1 + res2) * scale        (absent terms = 0)
+ *   out_raw     = bf16(v)                     if out_raw != NULL
+ *   out_act     = bf16(leaky_relu(v, slope))  if out_act != NULL
+ *
+ * x is read with zero padding outside [0,T).  x, res*, out_* are bf16 [B][T][C]; w_packed is
+ * bf16 [ktaps][cout][cin]; bias fp32 [cout].  cin % 32 == 0, cout % 32 == 0.
+ * The fused epilogue covers F.leaky_relu (models.py:36,38,64,103,112), the residual add (:41,67),
+ * and the MRF branch average xs / num_kernels (:105-111).
+ */
+int hg_conv1d_fwd(const void* x, const void* w_packed, const float* bias, int batch, int t, int cin,
+                  int cout, int ktaps, int dilation, int pad_left, const void* res0,
+                  const void* res1, const void* res2, float scale, void* out_raw, void* out_act,
+                  float act_slope, void* stream);
+
+/* Debug knob for hardware bring-up of the row-shifted UMMA descriptors (0 or 1). */
+int hg_debug_set_desc_mode(int mode);
+
+/* ------------------------------------------------------------------------------------------
+ * Layout edges.
+ * hg_ncl_to_nlc: fp32 [B][C][T] -> bf16 [B][T][c_pad] (zero-filled channels >= C); the mel input of
+ *   Generator.forward (src/models.py:100-101).  `out` receives the values, `out_act` (optional)
+ *   leaky_relu(., act_slope) of them; either may be NULL.
+ * hg_nlc_to_ncl: bf16 [B][T][C] -> fp32 [B][C][T]; used by tests / feature-map export.
+ */
+int hg_ncl_to_nlc(const float* x, int batch, int c, int t, int c_pad, void* out, void* out_act,
+                  float act_slope, void* stream);
+int hg_nlc_to_ncl(const void* x, int batch, int t, int c, float* out, void* stream);
+
+/* hg_conv_post_tanh_fwd — conv_post + tanh (src/models.py:113-114).  x bf16 [B][T][C] already
+ * holds leaky_relu(., 0.01) (models.py:112, fused into the producer's epilogue).  w fp32 [C][k]
+ * (folded weight of the single output channel), y fp32 [B][T] == the reference's [B,1,T].
+ * Bandwidth-bound CUDA-core kernel. */
+int hg_conv_post_tanh_fwd(const void* x, const float* w, const float* bias, int batch, int t, int c,
+                          int k, float* y, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * mel_spectrogram (src/meldataset.py:56-85): reflect-pad (n_fft-hop)/2, frames of win_size with a
+ * periodic Hann window, rFFT(n_fft), |X|^2, HTK mel filterbank (un-normalised triangles), and
+ * log(clamp(., 1e-5)) in ONE kernel.  The plan owns the immutable tables (window, twiddles, sparse
+ * filterbank), keyed like the reference's cache key (meldataset.py:57).
+ * Supported: n_fft == 1024, win_size <= n_fft, hop_size | anything, num_mels <= 128.
+ */
+typedef struct hg_mel_plan hg_mel_plan;
+int hg_mel_plan_create(hg_mel_plan** out_plan, int n_fft, int num_mels, int sampling_rate,
+                       int hop_size, int win_size, double fmin, double fmax /* <0: sr/2 */,
+                       void* stream);
+int hg_mel_plan_destroy(hg_mel_plan* plan);
+/* frames produced for t input samples (center=False after the manual reflect pad) */
+int hg_mel_num_frames(const hg_mel_plan* plan, int t);
+/* y fp32 [B][T] -> out fp32 [B][num_mels][frames]; minmax (optional, fp32[2], must be preset to
+ * {+inf,-inf}) receives min/max of y so the caller can reproduce the reference's range warning
+ * (meldataset.py:74-77) without a blocking sync per call. */
+int hg_mel_fwd(const hg_mel_plan* plan, const float* y, int batch, int t, float* out,
+               float* minmax, void* stream);
+
+/* Test hook: runs the mel kernel's per-thread phase functions on the HOST (threads serialised) so
+ * the FFT / un-pack / CSR-mel arithmetic can be pinned without a GPU.  host_y, host_out are HOST
+ * pointers; works on a plan created without a device. */
+int hg_mel_emulate_host(const hg_mel_plan* plan, const float* host_y, int batch, int t,
+                        float* host_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIFIGAN_B200_H */

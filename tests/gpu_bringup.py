@@ -1,0 +1,157 @@
+"""Hardware bring-up script (run under gpurun; not collected by pytest).
+
+    python tests/gpu_bringup.py <stage> [...]
+
+Each stage runs in its own process (see tests/run_bringup.sh) so a faulting kernel cannot poison the rest.
+Prints one JSON line per check to stdout and appends it to gpurun_out/bringup.jsonl.
+"""
+import json
+import os
+import sys
+import time
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import hifigan_b200 as H  # noqa: E402
+from hifigan_b200 import _lib  # noqa: E402
+from oracle import hifigan_oracle as O  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+os.makedirs(OUT, exist_ok=True)
+
+
+def emit(**kw):
+    line = json.dumps(kw)
+    print(line, flush=True)
+    with open(os.path.join(OUT, "bringup.jsonl"), "a") as f:
+        f.write(line + "\n")
+
+
+def stage_mel():
+    dev = torch.device("cuda")
+    for (b, t) in [(4, 8192), (1, 22050), (3, 40000)]:
+        y = O.synthetic_audio(b, t, seed=b)
+        for fmax in (8000, None):
+            ref = O.mel_spectrogram(y.double(), 1024, 80, 22050, 256, 1024, 0, fmax)
+            got = H.mel_spectrogram(y.to(dev), 1024, 80, 22050, 256, 1024, 0, fmax).cpu().double()
+            emit(stage="mel", b=b, t=t, fmax=fmax, shape=list(got.shape), max_abs=(got - ref).abs().max().item())
+    H.meldataset.flush_range_warnings()
+
+
+def conv_case(L, b, t, cin, cout, k, d, mode, seed=0, with_res=True):
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(b, t, cin, generator=g).to(dev).bfloat16()
+    w = (torch.randn(cout, cin, k, generator=g) / (cin * k) ** 0.5).to(dev)
+    bias = torch.randn(cout, generator=g).to(dev)
+    res = torch.randn(b, t, cout, generator=g).to(dev).bfloat16() if with_res else None
+    wp = torch.empty(k, cout, cin, dtype=torch.bfloat16, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.hg_pack_conv1d_weight(w.data_ptr(), 0, cout, cin, k, cin, wp.data_ptr(), st))
+    out_raw = torch.zeros(b, t, cout, dtype=torch.bfloat16, device=dev)
+    out_act = torch.zeros(b, t, cout, dtype=torch.bfloat16, device=dev)
+    L.hg_debug_set_desc_mode(mode)
+    pad = (k - 1) * d // 2
+    _lib.check(L.hg_conv1d_fwd(x.data_ptr(), wp.data_ptr(), bias.data_ptr(), b, t, cin, cout, k, d, pad,
+                               0 if res is None else res.data_ptr(), 0, 0, 0.5, out_raw.data_ptr(),
+                               out_act.data_ptr(), 0.1, st))
+    torch.cuda.synchronize()
+    wr = wp.float().permute(1, 2, 0).contiguous()  # [cout, cin, k] bf16-rounded
+    ref = F.conv1d(x.float().transpose(1, 2), wr, bias, dilation=d, padding=pad).transpose(1, 2)
+    if res is not None:
+        ref = ref + res.float()
+    ref = ref * 0.5
+    e_raw = (out_raw.float() - ref).abs().max().item()
+    e_act = (out_act.float() - F.leaky_relu(ref, 0.1)).abs().max().item()
+    return e_raw, e_act, ref.abs().max().item()
+
+
+def stage_conv(mode):
+    L = _lib.lib()
+    cases = [
+        # b, t, cin, cout, k, d
+        (1, 128, 64, 64, 1, 1),
+        (1, 128, 64, 64, 3, 1),
+        (2, 256, 64, 64, 3, 3),
+        (2, 384, 128, 128, 7, 5),
+        (1, 512, 256, 256, 11, 5),
+        (3, 200, 128, 256, 3, 1),
+        (2, 256, 32, 32, 3, 1),
+        (2, 256, 32, 32, 11, 5),
+        (2, 256, 32, 64, 7, 3),
+        (1, 100, 128, 512, 7, 1),
+    ]
+    for c in cases:
+        try:
+            e_raw, e_act, mag = conv_case(L, *c, mode)
+            emit(stage="conv", mode=mode, case=list(c), err_raw=e_raw, err_act=e_act, ref_max=mag,
+                 ok=bool(e_raw < 0.03 * max(mag, 1.0)))
+        except Exception as e:  # noqa: BLE001
+            emit(stage="conv", mode=mode, case=list(c), error=str(e)[:300])
+            raise
+
+
+def stage_gen(version, b, frames, mode):
+    _lib.lib().hg_debug_set_desc_mode(mode)
+    h = H.AttrDict(O.config(version))
+    torch.manual_seed(1234)
+    G = H.Generator(h)
+    sd = {k: v.detach().clone() for k, v in G.state_dict().items()}
+    torch.manual_seed(0)
+    x = torch.randn(b, 80, frames)
+    taps = {}
+    with torch.no_grad():
+        ref = O.generator_forward(sd, h, x, taps)
+    G = G.cuda().eval()
+    with torch.no_grad():
+        y = G(x.cuda()).float().cpu()
+    torch.cuda.synchronize()
+    err = (y - ref).abs().max().item()
+    num = (ref - ref.mean()).pow(2).sum()
+    snr = 10 * torch.log10(num / (y - ref).pow(2).sum()).item()
+    emit(stage="gen", version=version, b=b, frames=frames, mode=mode, max_abs=err, ref_max=ref.abs().max().item(),
+         snr_db=snr)
+    # after remove_weight_norm the result must not move
+    G.remove_weight_norm()
+    with torch.no_grad():
+        y2 = G(x.cuda()).float().cpu()
+    emit(stage="gen_folded", version=version, max_abs_vs_wn=(y2 - y).abs().max().item())
+
+
+def stage_time(version, b, frames, mode, iters=5):
+    _lib.lib().hg_debug_set_desc_mode(mode)
+    h = H.AttrDict(O.config(version))
+    torch.manual_seed(1234)
+    G = H.Generator(h).cuda().eval()
+    G.remove_weight_norm()
+    x = torch.randn(b, 80, frames, device="cuda")
+    with torch.no_grad():
+        for _ in range(2):
+            G(x)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            G(x)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    samples = b * frames * 256
+    emit(stage="time", version=version, b=b, frames=frames, ms=ms, samples_per_s=samples / ms * 1e3,
+         xrt=samples / ms * 1e3 / 22050, tflops=samples * (2398848 if version == "v1" else 175648) / ms / 1e9)
+
+
+if __name__ == "__main__":
+    st = sys.argv[1]
+    t0 = time.time()
+    if st == "mel":
+        stage_mel()
+    elif st == "conv":
+        stage_conv(int(sys.argv[2]))
+    elif st == "gen":
+        stage_gen(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]))
+    elif st == "time":
+        stage_time(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]))
+    emit(stage="done", which=sys.argv[1:], seconds=time.time() - t0)
