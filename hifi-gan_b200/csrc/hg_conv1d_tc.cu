@@ -8,7 +8,10 @@
 // * activations are channels-last bf16 [B][T][C]; ONE TMA box of (128 + (k-1)*dil) time rows x KC
 //   channels is loaded per K chunk and every tap reads it through a row-shifted UMMA descriptor, so
 //   the halo is fetched once instead of k times; TMA zero-fills rows outside [0,T) which implements
-//   the conv's "same" zero padding.
+//   the conv's "same" zero padding.  Row-shifting works because both TMA and UMMA apply the 128B/64B
+//   swizzle as a function of the absolute shared-memory address: a start address moved by r rows
+//   (r*128 B, any r) with base_offset = 0 and SBO = 8 rows addresses logical rows r..r+127 of the box.
+//   Verified on B200 for SW128 and SW64, dilations 1..5, k up to 11 (profiles/r01_bringup.md).
 // * weights are bf16 [k][Cout][Cin] (K-major), streamed tap by tap through a multi-stage ring.
 // * warp 0 = TMA producer, warp 1 = MMA issuer (one thread) + TMEM owner, warps 2..5 = epilogue.
 //   Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
@@ -18,12 +21,6 @@
 #include <atomic>
 
 extern std::atomic<int64_t> g_hg_launches;
-static int g_desc_mode = 0;
-
-extern "C" int hg_debug_set_desc_mode(int mode) {
-  g_desc_mode = mode;
-  return HG_OK;
-}
 
 namespace {
 
@@ -38,7 +35,6 @@ struct ConvArgs {
   int tiles_t, tiles_n, num_tiles;
   int stages;
   uint32_t a_slot_bytes, w_stage_bytes;
-  int desc_mode;
   const float* bias;
   const __nv_bfloat16* res0;
   const __nv_bfloat16* res1;
@@ -166,10 +162,9 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             hg::tc_fence_after();
             const uint32_t a_tap = a_base + static_cast<uint32_t>(j * p.dil) * kRowBytes;
             const uint32_t w_base = hg::smem_u32(w_buf + s * p.w_stage_bytes);
-            const uint32_t boff = p.desc_mode ? ((a_tap >> 7) & 7u) : 0u;
 #pragma unroll
             for (int kk = 0; kk < KC / 16; ++kk) {
-              const uint64_t da = hg::umma_smem_desc(a_tap + kk * 32, kSbo, kLayout, boff);
+              const uint64_t da = hg::umma_smem_desc(a_tap + kk * 32, kSbo, kLayout, 0);
               const uint64_t db = hg::umma_smem_desc(w_base + kk * 32, kSbo, kLayout, 0);
               hg::umma_bf16_ss(d_tmem, da, db, idesc, accumulate);
               accumulate = 1;
@@ -303,7 +298,6 @@ extern "C" int hg_conv1d_fwd(const void* x, const void* w_packed, const float* b
   if (stages > kMaxStages) stages = kMaxStages;
   HG_REQUIRE(stages >= 2, "hg_conv1d_fwd: not enough shared memory for the weight ring");
   p.stages = stages;
-  p.desc_mode = g_desc_mode;
   p.bias = bias;
   p.res0 = static_cast<const __nv_bfloat16*>(res0);
   p.res1 = static_cast<const __nv_bfloat16*>(res1);

@@ -313,7 +313,9 @@ class _GeneratorEngine:
         self.ws[key] = ws
         return ws
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, time_convs: bool = False) -> torch.Tensor:
+        """time_convs=True brackets the tensor-core conv launches (everything between the input transposition
+        and conv_post) with CUDA events on the launching stream -> self.last_conv_events (bench.py roofline)."""
         L = _lib.lib()
         gen = self.gen
         self.refresh()
@@ -324,6 +326,9 @@ class _GeneratorEngine:
             xin = xin.float()
         _lib.check(L.hg_ncl_to_nlc(xin.data_ptr(), b, c, frames, self.pre.cin_p, ws["mel"].data_ptr(), 0, 0.0,
                                    _stream()), "hg_ncl_to_nlc")
+        if time_convs:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         # conv_pre; its only consumer is leaky_relu -> ups[0] (models.py:101-104)
         _conv(L, ws["mel"], self.pre, b, frames, out_act=ws["pre"])
         cur, t = ws["pre"], frames
@@ -353,6 +358,9 @@ class _GeneratorEngine:
 
                 _resblock_chain(L, blk, packs, b, t, c_p, ws["x_raw"], ws["x_act"], ws, final)
             cur = ws["stage_out"]
+        if time_convs:
+            ev1.record()
+            self.last_conv_events = (ev0, ev1)
         post = gen.conv_post
         _lib.check(L.hg_conv_post_tanh_fwd(cur.data_ptr(), self.post_w.data_ptr(), self.post_b.data_ptr(), b, t,
                                            self.post_cin_p, post.kernel_size[0], ws["y"].data_ptr(), _stream()),

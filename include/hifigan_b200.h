@@ -80,9 +80,6 @@ int hg_conv1d_fwd(const void* x, const void* w_packed, const float* bias, int ba
                   const void* res1, const void* res2, float scale, void* out_raw, void* out_act,
                   float act_slope, void* stream);
 
-/* Debug knob for hardware bring-up of the row-shifted UMMA descriptors (0 or 1). */
-int hg_debug_set_desc_mode(int mode);
-
 /* ------------------------------------------------------------------------------------------
  * Layout edges.
  * hg_ncl_to_nlc: fp32 [B][C][T] -> bf16 [B][T][c_pad] (zero-filled channels >= C); the mel input of

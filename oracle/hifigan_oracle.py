@@ -101,6 +101,18 @@ def fold_weight_norm(g: Tensor, v: Tensor) -> Tensor:
     return v * (g / v.pow(2).sum(dim=dims, keepdim=True).sqrt())
 
 
+def spectral_norm_step(w: Tensor, u: Tensor, v: Tensor, n_iter: int = 1, eps: float = 1e-12
+                       ) -> Tuple[Tensor, Tensor, Tensor]:
+    """One train-mode forward of torch.nn.utils.spectral_norm (dim=0, n_power_iterations=1, eps=1e-12):
+    v <- normalize(W^T u); u <- normalize(W v); sigma = u . (W v).  Returns (W / sigma, u, v)."""
+    wm = w.flatten(1)
+    for _ in range(n_iter):
+        v = F.normalize(torch.mv(wm.t(), u), dim=0, eps=eps)
+        u = F.normalize(torch.mv(wm, v), dim=0, eps=eps)
+    sigma = torch.dot(u, torch.mv(wm, v))
+    return w / sigma, u, v
+
+
 def weight_of(sd: StateDict, prefix: str) -> Tensor:
     """Effective conv weight for `prefix` from a reference state_dict, whichever form it is in:
     weight_g/weight_v (weight_norm attached), weight (after remove_weight_norm,
@@ -203,15 +215,27 @@ def discriminator_p_forward(sd: StateDict, prefix: str, x: Tensor, period: int
     return torch.flatten(x, 1, -1), fmap
 
 
-def discriminator_s_forward(sd: StateDict, prefix: str, x: Tensor) -> Tuple[Tensor, List[Tensor]]:
+def _sn_weight(sd: StateDict, prefix: str, train: bool) -> Tensor:
+    """Spectral-norm layers in train mode run one power iteration per forward and update the u/v buffers
+    in place; `sd` is mutated accordingly."""
+    if train and prefix + ".weight_orig" in sd:
+        w, u, v = spectral_norm_step(sd[prefix + ".weight_orig"], sd[prefix + ".weight_u"],
+                                     sd[prefix + ".weight_v"])
+        sd[prefix + ".weight_u"], sd[prefix + ".weight_v"] = u, v
+        return w
+    return weight_of(sd, prefix)
+
+
+def discriminator_s_forward(sd: StateDict, prefix: str, x: Tensor, train: bool = False
+                            ) -> Tuple[Tensor, List[Tensor]]:
     """src/models.py:206-216."""
     fmap = []
     for l, (_, _, k, s, g, p) in enumerate(_DS_LAYERS):
-        x = F.conv1d(x, weight_of(sd, f"{prefix}.convs.{l}"), sd[f"{prefix}.convs.{l}.bias"],
+        x = F.conv1d(x, _sn_weight(sd, f"{prefix}.convs.{l}", train), sd[f"{prefix}.convs.{l}.bias"],
                      stride=s, padding=p, groups=g)
         x = F.leaky_relu(x, LRELU_SLOPE)
         fmap.append(x)
-    x = F.conv1d(x, weight_of(sd, f"{prefix}.conv_post"), sd[f"{prefix}.conv_post.bias"], padding=1)
+    x = F.conv1d(x, _sn_weight(sd, f"{prefix}.conv_post", train), sd[f"{prefix}.conv_post.bias"], padding=1)
     fmap.append(x)
     return torch.flatten(x, 1, -1), fmap
 
@@ -229,15 +253,16 @@ def mpd_forward(sd: StateDict, y: Tensor, y_hat: Tensor):
     return y_d_rs, y_d_gs, fmap_rs, fmap_gs
 
 
-def msd_forward(sd: StateDict, y: Tensor, y_hat: Tensor):
-    """src/models.py:232-248 (AvgPool1d(4,2,padding=2) cumulatively between scales)."""
+def msd_forward(sd: StateDict, y: Tensor, y_hat: Tensor, train: bool = False):
+    """src/models.py:232-248 (AvgPool1d(4,2,padding=2) cumulatively between scales).  With train=True the
+    spectral-norm scale (discriminators.0) runs its power iterations call by call and `sd` is updated."""
     y_d_rs, y_d_gs, fmap_rs, fmap_gs = [], [], [], []
     for i in range(3):
         if i != 0:
             y = F.avg_pool1d(y, 4, 2, padding=2)
             y_hat = F.avg_pool1d(y_hat, 4, 2, padding=2)
-        r, fr = discriminator_s_forward(sd, f"discriminators.{i}", y)
-        g, fg = discriminator_s_forward(sd, f"discriminators.{i}", y_hat)
+        r, fr = discriminator_s_forward(sd, f"discriminators.{i}", y, train)
+        g, fg = discriminator_s_forward(sd, f"discriminators.{i}", y_hat, train)
         y_d_rs.append(r); fmap_rs.append(fr); y_d_gs.append(g); fmap_gs.append(fg)
     return y_d_rs, y_d_gs, fmap_rs, fmap_gs
 

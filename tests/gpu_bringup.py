@@ -52,7 +52,6 @@ def conv_case(L, b, t, cin, cout, k, d, mode, seed=0, with_res=True):
     _lib.check(L.hg_pack_conv1d_weight(w.data_ptr(), 0, cout, cin, k, cin, wp.data_ptr(), st))
     out_raw = torch.zeros(b, t, cout, dtype=torch.bfloat16, device=dev)
     out_act = torch.zeros(b, t, cout, dtype=torch.bfloat16, device=dev)
-    L.hg_debug_set_desc_mode(mode)
     pad = (k - 1) * d // 2
     _lib.check(L.hg_conv1d_fwd(x.data_ptr(), wp.data_ptr(), bias.data_ptr(), b, t, cin, cout, k, d, pad,
                                0 if res is None else res.data_ptr(), 0, 0, 0.5, out_raw.data_ptr(),
@@ -94,7 +93,6 @@ def stage_conv(mode):
 
 
 def stage_gen(version, b, frames, mode):
-    _lib.lib().hg_debug_set_desc_mode(mode)
     h = H.AttrDict(O.config(version))
     torch.manual_seed(1234)
     G = H.Generator(h)
@@ -121,7 +119,6 @@ def stage_gen(version, b, frames, mode):
 
 
 def stage_time(version, b, frames, mode, iters=5):
-    _lib.lib().hg_debug_set_desc_mode(mode)
     h = H.AttrDict(O.config(version))
     torch.manual_seed(1234)
     G = H.Generator(h).cuda().eval()
@@ -143,6 +140,45 @@ def stage_time(version, b, frames, mode, iters=5):
          xrt=samples / ms * 1e3 / 22050, tflops=samples * (2398848 if version == "v1" else 175648) / ms / 1e9)
 
 
+def stage_layers(b, frames):
+    """Per-layer-shape timing of hg_conv1d_fwd at the V1 stage shapes (CUDA events, 5 iterations)."""
+    L = _lib.lib()
+    dev = torch.device("cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    shapes = [(512, 512 * 0 + 2048, 3, 1, frames, "ups0 polyphase"), (256, 1024, 3, 1, frames * 8, "ups1 polyphase"),
+              (128, 128, 3, 1, frames * 64, "ups2 polyphase"), (64, 64, 3, 1, frames * 128, "ups3 polyphase")]
+    for c, t in ((256, frames * 8), (128, frames * 64), (64, frames * 128), (32, frames * 256)):
+        for k in (3, 7, 11):
+            for d in (1, 5):
+                shapes.append((c, c, k, d, t, "resblock"))
+    for cin, cout, k, d, t, name in shapes:
+        x = torch.randn(b, t, cin, device=dev).bfloat16()
+        wp = (torch.randn(k, cout, cin, device=dev) / (cin * k) ** 0.5).bfloat16()
+        bias = torch.zeros(cout, device=dev)
+        res = torch.randn(b, t, cout, device=dev).bfloat16()
+        o1 = torch.empty(b, t, cout, dtype=torch.bfloat16, device=dev)
+        o2 = torch.empty(b, t, cout, dtype=torch.bfloat16, device=dev)
+        pad = (k - 1) * d // 2
+        def run():
+            _lib.check(L.hg_conv1d_fwd(x.data_ptr(), wp.data_ptr(), bias.data_ptr(), b, t, cin, cout, k, d, pad,
+                                       res.data_ptr(), 0, 0, 1.0, o1.data_ptr(), o2.data_ptr(), 0.1, st))
+        for _ in range(2):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        flops = 2.0 * b * t * cin * cout * k
+        byts = 2.0 * b * t * (cin + 3 * cout)
+        emit(stage="layer", name=name, cin=cin, cout=cout, k=k, d=d, t=t, b=b, ms=round(ms, 4),
+             tflops=round(flops / ms / 1e9, 1), gbs=round(byts / ms / 1e6, 1))
+        del x, wp, res, o1, o2
+
+
 if __name__ == "__main__":
     st = sys.argv[1]
     t0 = time.time()
@@ -152,6 +188,8 @@ if __name__ == "__main__":
         stage_conv(int(sys.argv[2]))
     elif st == "gen":
         stage_gen(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]))
+    elif st == "layers":
+        stage_layers(int(sys.argv[2]), int(sys.argv[3]))
     elif st == "time":
         stage_time(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]))
     emit(stage="done", which=sys.argv[1:], seconds=time.time() - t0)

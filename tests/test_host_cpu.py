@@ -1,0 +1,189 @@
+"""Host-side logic that needs no GPU: the module/state_dict contract, same-seed construction against the
+reference-generated fingerprints, the C-ABI surface, the mel kernel's arithmetic through its host emulation."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import hifigan_b200 as H
+from conftest import ROOT, load_npz
+from hifigan_b200 import _lib
+from oracle import hifigan_oracle as O
+
+
+def _stats(sd):
+    keys = sorted(sd)
+    return np.array([[float(sd[k].double().sum()), float(sd[k].double().abs().sum()), sd[k].numel()] for k in keys]), keys
+
+
+@pytest.mark.parametrize("ver", ["v1", "v2", "v3"])
+def test_same_seed_construction_matches_reference(ver):
+    """torch.manual_seed(1234); Generator(h) must reproduce the reference's parameters bit for bit: the RNG draw
+    order (incl. init_weights' no-op normal_ draws) is part of the contract."""
+    z = load_npz(f"gen_{ver}_seed1234.npz")
+    torch.manual_seed(1234)
+    G = H.Generator(H.AttrDict(O.config(ver)))
+    stats, keys = _stats(G.state_dict())
+    assert keys == list(z["sd_keys"])
+    assert np.array_equal(stats, z["sd_stats"])
+
+
+def test_discriminator_same_seed_construction():
+    z = load_npz("disc_seed1234.npz")
+    torch.manual_seed(1234)
+    H.Generator(H.AttrDict(O.config("v1")))
+    mpd, msd = H.MultiPeriodDiscriminator(), H.MultiScaleDiscriminator()
+    for name, D in (("mpd", mpd), ("msd", msd)):
+        stats, keys = _stats(D.state_dict())
+        assert keys == list(z[f"{name}_sd_keys"])
+        assert np.array_equal(stats, z[f"{name}_sd_stats"])
+
+
+def test_state_dict_contract_v1():
+    G = H.Generator(H.AttrDict(O.config("v1")))
+    sd = G.state_dict()
+    assert len(sd) == 234
+    assert tuple(sd["conv_pre.weight_g"].shape) == (512, 1, 1) and tuple(sd["conv_pre.weight_v"].shape) == (512, 80, 7)
+    assert tuple(sd["ups.0.weight_g"].shape) == (512, 1, 1)  # ConvTranspose: dim 0 = input channel
+    assert tuple(sd["ups.0.weight_v"].shape) == (512, 256, 16)
+    assert "resblocks.11.convs2.2.weight_v" in sd and tuple(sd["conv_post.weight_v"].shape) == (1, 32, 7)
+    assert sum(p.numel() for p in G.parameters()) == 13936130
+    G.remove_weight_norm()
+    sd2 = G.state_dict()
+    assert "conv_pre.weight" in sd2 and not any(k.endswith("weight_g") for k in sd2)
+    assert sum(p.numel() for p in G.parameters()) == 13926017
+
+
+def test_state_dict_contract_v3_and_discriminators():
+    G = H.Generator(H.AttrDict(O.config("v3")))
+    assert "resblocks.0.convs.1.weight_g" in G.state_dict()
+    assert sum(p.numel() for p in G.parameters()) == 1464322
+    mpd, msd = H.MultiPeriodDiscriminator(), H.MultiScaleDiscriminator()
+    assert len(mpd.state_dict()) == 90 and len(msd.state_dict()) == 80
+    assert sum(p.numel() for p in mpd.parameters()) == 41105770
+    assert "discriminators.0.convs.1.weight_orig" in msd.state_dict()
+    assert "discriminators.0.convs.1.weight_u" in dict(msd.named_buffers())
+    assert tuple(mpd.state_dict()["discriminators.4.convs.3.weight_v"].shape) == (1024, 512, 5, 1)
+
+
+def test_resblock_selector_is_a_string_compare():
+    h = H.AttrDict(O.config("tiny"))
+    h.resblock = 1  # int, not '1'  -> ResBlock2, exactly like the reference (models.py:82)
+    G = H.Generator(h)
+    assert type(G.resblocks[0]).__name__ == "ResBlock2"
+
+
+def test_load_reference_style_checkpoint(tmp_path):
+    z = load_npz("gen_tiny.npz")
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    path = tmp_path / "g_00000001"
+    H.save_checkpoint(str(path), {"generator": sd})
+    G = H.Generator(H.AttrDict(O.config("tiny")))
+    G.load_state_dict(H.load_checkpoint(str(path), "cpu")["generator"])
+    for k, v in G.state_dict().items():
+        assert torch.equal(v, sd[k])
+    assert H.scan_checkpoint(str(tmp_path), "g_") == str(path)
+    assert H.scan_checkpoint(str(tmp_path), "do_") is None
+    with pytest.raises(AssertionError):
+        H.load_checkpoint(str(tmp_path / "missing"), "cpu")
+
+
+def test_no_cpu_path():
+    G = H.Generator(H.AttrDict(O.config("tiny"))).eval()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        G(torch.zeros(1, 80, 8))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        H.mel_spectrogram(torch.zeros(1, 8192), 1024, 80, 22050, 256, 1024, 0, 8000)
+    with pytest.raises(NotImplementedError):
+        H.MultiScaleDiscriminator()(torch.zeros(1, 1, 64), torch.zeros(1, 1, 64))
+
+
+def test_helpers():
+    assert H.get_padding(11, 5) == 25 and H.get_padding(3) == 1
+    h = H.AttrDict({"a": 1})
+    h.b = 2
+    assert h["b"] == 2 and h.a == 1
+    assert H.LRELU_SLOPE == 0.1 and H.MAX_WAV_VALUE == 32768.0
+
+
+def test_losses_match_oracle():
+    g = torch.Generator().manual_seed(0)
+    fr = [[torch.randn(2, 4, 9, generator=g) for _ in range(3)] for _ in range(2)]
+    fg = [[torch.randn(2, 4, 9, generator=g) for _ in range(3)] for _ in range(2)]
+    assert torch.allclose(H.feature_loss(fr, fg), O.feature_loss(fr, fg))
+    dr = [torch.randn(2, 7, generator=g) for _ in range(3)]
+    dg = [torch.randn(2, 7, generator=g) for _ in range(3)]
+    a, b = H.discriminator_loss(dr, dg), O.discriminator_loss(dr, dg)
+    assert torch.allclose(a[0], b[0]) and np.allclose(a[1], b[1]) and np.allclose(a[2], b[2])
+    assert all(isinstance(v, float) for v in a[1] + a[2])
+    ga, gb = H.generator_loss(dg), O.generator_loss(dg)
+    assert torch.allclose(ga[0], gb[0]) and all(torch.is_tensor(t) for t in ga[1])
+
+
+# ------------------------------------------------------------------------------------------- C-ABI surface
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "hifigan_b200.h")).read()
+    declared = set(re.findall(r"\b(hg_[a-z0-9_]+)\s*\(", header))
+    declared -= {"hg_mel_plan"}
+    lib = ctypes.CDLL(_lib.build())
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/hifigan_b200.h but not exported"
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    assert _lib.lib().hg_abi_version() == 1
+
+
+def test_convtr_geometry():
+    from ctypes import byref, c_int
+    L = _lib.lib()
+    for k, u, pad, want in [(16, 8, 4, (3, -1)), (4, 2, 1, (3, -1)), (8, 4, 2, (3, -1)), (3, 1, 1, (3, -1)),
+                            (4, 4, 0, (1, 0))]:
+        n, s = c_int(), c_int()
+        assert L.hg_convtr1d_geometry(k, u, pad, byref(n), byref(s)) == 0
+        assert (n.value, s.value) == want
+    assert L.hg_convtr1d_geometry(0, 1, 0, None, None) != 0
+    assert b"bad arguments" in L.hg_last_error()
+
+
+@pytest.mark.parametrize("name", ["y", "special", "odd"])
+@pytest.mark.parametrize("fmax", [8000, None])
+def test_mel_kernel_arithmetic_on_host_vs_reference(name, fmax):
+    """hg_mel_emulate_host runs the CUDA kernel's own phase functions (Stockham radix-8 FFT, real un-packing,
+    CSR mel, log-clamp) with threads serialised; it must reproduce the reference-generated fixtures."""
+    from test_oracle_cpu import mel_close
+    z = load_npz("mel.npz")
+    L = _lib.lib()
+    plan = ctypes.c_void_p()
+    assert L.hg_mel_plan_create(ctypes.byref(plan), 1024, 80, 22050, 256, 1024, 0.0,
+                                -1.0 if fmax is None else float(fmax), None) == 0
+    y = np.ascontiguousarray(z[name])
+    b, t = y.shape
+    frames = L.hg_mel_num_frames(plan, t)
+    out = np.zeros((b, 80, frames), np.float32)
+    assert L.hg_mel_emulate_host(plan, y.ctypes.data, b, t, out.ctypes.data) == 0
+    L.hg_mel_plan_destroy(plan)
+    ref = z[f"mel_{name}_fmax{fmax}"]
+    assert out.shape == ref.shape
+    mel_close(out.astype(np.float64), ref, 2e-4)
+
+
+def test_mel_plan_rejects_unsupported():
+    L = _lib.lib()
+    plan = ctypes.c_void_p()
+    assert L.hg_mel_plan_create(ctypes.byref(plan), 512, 80, 22050, 128, 512, 0.0, 8000.0, None) != 0
+    assert b"n_fft == 1024" in L.hg_last_error()
+
+
+def test_segment_sampler_draw_rule_matches_reference():
+    """MelDataset.__getitem__ draws random.randint(0, len - seg) inclusive (meldataset.py:145-146) and right
+    zero-pads short utterances (:150)."""
+    import random
+    from hifigan_b200.meldataset import SegmentSampler
+    s = SegmentSampler.__new__(SegmentSampler)
+    s.segment_length, s.lengths, s.offsets, s.rng = 8, [20, 5, 8], [0, 20, 25, 33], random.Random(1234)
+    picks = s.draw([0, 1, 2, 0])
+    ref = random.Random(1234)
+    want = [(0 + ref.randint(0, 12), 8), (20, 5), (25 + ref.randint(0, 0), 8), (0 + ref.randint(0, 12), 8)]
+    assert picks == want
