@@ -3,7 +3,7 @@
 // Replaces the torch Conv1d / ConvTranspose1d library calls of the reference Generator
 // (src/models.py:35-42 ResBlock1, :63-68 ResBlock2, :101 conv_pre, :104 ups via polyphase packing).
 //
-// GEMM view, per output tile of 128 time steps x n_tile output channels:
+// GEMM view, per output tile of 128 time steps x NT output channels:
 //     D[t, co] = sum_{tap j} sum_{chunk c}  A_c[t + j*dil, 0:KC] * W_{j,c}[co, 0:KC]^T
 // * activations are channels-last bf16 [B][T][C]; ONE TMA box of (128 + (k-1)*dil) time rows x KC
 //   channels is loaded per K chunk and every tap reads it through a row-shifted UMMA descriptor, so
@@ -11,11 +11,16 @@
 //   the conv's "same" zero padding.  Row-shifting works because both TMA and UMMA apply the 128B/64B
 //   swizzle as a function of the absolute shared-memory address: a start address moved by r rows
 //   (r*128 B, any r) with base_offset = 0 and SBO = 8 rows addresses logical rows r..r+127 of the box.
-//   Verified on B200 for SW128 and SW64, dilations 1..5, k up to 11 (profiles/r01_bringup.md).
-// * weights are bf16 [k][Cout][Cin] (K-major), streamed tap by tap through a multi-stage ring.
-// * warp 0 = TMA producer, warp 1 = MMA issuer (one thread) + TMEM owner, warps 2..5 = epilogue.
+//   Verified on B200 for SW128 and SW64, dilations 1..12, k up to 11 (profiles/r01_bringup.md).
+// * weights are bf16 [k][Cout][Cin] (K-major).  When the whole filter bank of the CTA's N tile fits in
+//   shared memory next to the activation ring it is loaded ONCE per CTA ("resident", every C <= 64
+//   layer and C = 128, k = 3); otherwise it streams through a ring whose stages hold several taps.
+// * warp 0 = TMA producer, warp 1 = MMA issuer (one thread) + TMEM owner, warps 2..9 = epilogue
+//   (two warps per TMEM lane quarter, each owning half of the tile's columns).
 //   Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
-// * epilogue: bias, up to three residual / MRF addends, scale, raw and leaky-relu'd bf16 stores.
+// * epilogue: bias, up to three residual / MRF addends, scale, raw and leaky-relu'd bf16 outputs;
+//   the first residual is prefetched into registers before the accumulator wait, global accesses are
+//   256-bit (one full 32-byte sector per thread per instruction).
 #include "hg_common.cuh"
 
 #include <atomic>
@@ -25,15 +30,21 @@ extern std::atomic<int64_t> g_hg_launches;
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr int kMaxStages = 8;
+constexpr int kMaxASlots = 4;
 
 struct ConvArgs {
   int batch, t, cin, cout;
   int ktaps, dil, pad_left;
-  int n_tile, nchunks, a_rows;
+  int nchunks, a_rows;
   int tiles_t, tiles_n, num_tiles;
-  int stages;
+  int a_slots;          // activation ring depth (2..4)
+  int resident;         // 1: all weights of the N tile live in smem for the whole kernel
+  int tps;              // ring mode: taps per stage
+  int groups;           // ring mode: ceil(ktaps / tps) stages per chunk
+  int stages;           // ring mode: ring depth
   uint32_t a_slot_bytes, w_stage_bytes;
   const float* bias;
   const __nv_bfloat16* res0;
@@ -46,8 +57,8 @@ struct ConvArgs {
 };
 
 struct Barriers {
-  uint64_t a_full[2];
-  uint64_t a_empty[2];
+  uint64_t a_full[kMaxASlots];
+  uint64_t a_empty[kMaxASlots];
   uint64_t w_full[kMaxStages];
   uint64_t w_empty[kMaxStages];
   uint64_t acc_full[2];
@@ -56,33 +67,69 @@ struct Barriers {
   uint32_t pad;
 };
 
-__device__ __forceinline__ void add_bf16x8(float (&v)[8], const uint4& r) {
-  float2 a = hg::unpack_bf16x2(r.x), b = hg::unpack_bf16x2(r.y), c = hg::unpack_bf16x2(r.z),
-         d = hg::unpack_bf16x2(r.w);
-  v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y;
-  v[4] += c.x; v[5] += c.y; v[6] += d.x; v[7] += d.y;
+struct U8 {
+  uint32_t v[8];
+};
+
+__device__ __forceinline__ U8 ldg256(const void* p) {
+  U8 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]),
+                 "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg256(void* p, const U8& r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r.v[0]),
+               "r"(r.v[1]), "r"(r.v[2]), "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]),
+               "r"(r.v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void add_bf16x16(float (&v)[16], const U8& r) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 f = hg::unpack_bf16x2(r.v[i]);
+    v[2 * i] += f.x;
+    v[2 * i + 1] += f.y;
+  }
 }
 
 // KC = channels per K chunk: 64 -> 128-byte rows / SWIZZLE_128B, 32 -> 64-byte rows / SWIZZLE_64B.
-template <int KC>
+// NT = output channels per tile (UMMA N).
+template <int KC, int NT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                  const ConvArgs p) {
   constexpr uint32_t kRowBytes = KC * 2;
   constexpr uint32_t kLayout = (KC == 64) ? 2u : 4u;  // UMMA layout type: SW128 / SW64
   constexpr uint32_t kSbo = 8 * kRowBytes;
+  constexpr uint32_t kTapBytes = NT * kRowBytes;      // one (tap, chunk) weight block
+  constexpr uint32_t kTmemCols = (2 * NT <= 32) ? 32u : (2 * NT <= 64) ? 64u
+                                 : (2 * NT <= 128) ? 128u : (2 * NT <= 256) ? 256u : 512u;
+  constexpr int kColsPerWarp = NT / 2;                // each epilogue warp owns half of the columns
+  constexpr int kGroups16 = kColsPerWarp / 16;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* a_buf = smem;
-  uint8_t* w_buf = smem + 2 * p.a_slot_bytes;
-  Barriers* bars = reinterpret_cast<Barriers*>(w_buf + p.stages * p.w_stage_bytes);
+  uint8_t* w_buf = smem + p.a_slots * p.a_slot_bytes;
+  const uint32_t w_total = p.resident ? static_cast<uint32_t>(p.nchunks * p.ktaps) * kTapBytes
+                                      : static_cast<uint32_t>(p.stages) * p.w_stage_bytes;
+  Barriers* bars = reinterpret_cast<Barriers*>(w_buf + w_total);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t tmem_cols = (2 * p.n_tile <= 32) ? 32u : (2 * p.n_tile <= 64) ? 64u
-                             : (2 * p.n_tile <= 128) ? 128u : (2 * p.n_tile <= 256) ? 256u : 512u;
 
   if (warp == 0 && lane == 0) {
     hg::tma_prefetch_desc(&tm_x);
@@ -90,20 +137,22 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < kMaxASlots; ++i) {
         hg::mbar_init(&bars->a_full[i], 1);
         hg::mbar_init(&bars->a_empty[i], 1);
-        hg::mbar_init(&bars->acc_full[i], 1);
-        hg::mbar_init(&bars->acc_empty[i], 4);
       }
-      for (int i = 0; i < p.stages; ++i) {
+      for (int i = 0; i < 2; ++i) {
+        hg::mbar_init(&bars->acc_full[i], 1);
+        hg::mbar_init(&bars->acc_empty[i], kEpiWarps);
+      }
+      for (int i = 0; i < kMaxStages; ++i) {
         hg::mbar_init(&bars->w_full[i], 1);
         hg::mbar_init(&bars->w_empty[i], 1);
       }
       hg::fence_mbar_init();
     }
     __syncwarp();
-    hg::tmem_alloc(&bars->tmem_base, tmem_cols);
+    hg::tmem_alloc(&bars->tmem_base, kTmemCols);
   }
   hg::tc_fence_before();
   __syncthreads();
@@ -115,7 +164,13 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     if (lane == 0) {
       uint32_t a_it = 0, w_it = 0;
       const uint32_t a_bytes = static_cast<uint32_t>(p.a_rows) * kRowBytes;
-      const uint32_t w_bytes = static_cast<uint32_t>(p.n_tile) * kRowBytes;
+      if (p.resident) {
+        // whole filter bank once: per chunk one box (KC, NT, ktaps) -> [tap][NT rows][KC] in smem
+        hg::mbar_arrive_expect_tx(&bars->w_full[0], w_total);
+        for (int c = 0; c < p.nchunks; ++c)
+          hg::tma_load_3d(w_buf + static_cast<uint32_t>(c * p.ktaps) * kTapBytes, &tm_w,
+                          &bars->w_full[0], c * KC, 0, 0);
+      }
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int nt = tile % p.tiles_n;
         const int rest = tile / p.tiles_n;
@@ -123,19 +178,20 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         const int b = rest / p.tiles_t;
         const int t0 = tt * kTileM - p.pad_left;
         for (int c = 0; c < p.nchunks; ++c) {
-          const uint32_t slot = a_it & 1u;
-          hg::mbar_wait(&bars->a_empty[slot], ((a_it >> 1) & 1u) ^ 1u);
+          const uint32_t slot = a_it % p.a_slots;
+          hg::mbar_wait(&bars->a_empty[slot], ((a_it / p.a_slots) & 1u) ^ 1u);
           hg::mbar_arrive_expect_tx(&bars->a_full[slot], a_bytes);
           hg::tma_load_3d(a_buf + slot * p.a_slot_bytes, &tm_x, &bars->a_full[slot], c * KC, t0, b);
           ++a_it;
-          for (int j = 0; j < p.ktaps; ++j) {
-            const uint32_t s = w_it % p.stages;
-            const uint32_t ph = (w_it / p.stages) & 1u;
-            hg::mbar_wait(&bars->w_empty[s], ph ^ 1u);
-            hg::mbar_arrive_expect_tx(&bars->w_full[s], w_bytes);
-            hg::tma_load_3d(w_buf + s * p.w_stage_bytes, &tm_w, &bars->w_full[s], c * KC,
-                            nt * p.n_tile, j);
-            ++w_it;
+          if (!p.resident) {
+            for (int g = 0; g < p.groups; ++g) {
+              const uint32_t s = w_it % p.stages;
+              hg::mbar_wait(&bars->w_empty[s], ((w_it / p.stages) & 1u) ^ 1u);
+              hg::mbar_arrive_expect_tx(&bars->w_full[s], static_cast<uint32_t>(p.tps) * kTapBytes);
+              hg::tma_load_3d(w_buf + s * p.w_stage_bytes, &tm_w, &bars->w_full[s], c * KC, nt * NT,
+                              g * p.tps);
+              ++w_it;
+            }
           }
         }
       }
@@ -144,33 +200,58 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   } else if (warp == 1) {
     // ============================ MMA issuer ==============================
     if (lane == 0) {
-      const uint32_t idesc = hg::umma_idesc_bf16(kTileM, p.n_tile);
+      constexpr uint32_t idesc = hg::umma_idesc_bf16(kTileM, NT);
       uint32_t a_it = 0, w_it = 0, acc_it = 0;
+      if (p.resident) {
+        hg::mbar_wait(&bars->w_full[0], 0);
+        hg::tc_fence_after();
+      }
+      const uint32_t w_smem = hg::smem_u32(w_buf);
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const uint32_t acc = acc_it & 1u;
         hg::mbar_wait(&bars->acc_empty[acc], ((acc_it >> 1) & 1u) ^ 1u);
         hg::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * p.n_tile;
+        const uint32_t d_tmem = tmem_base + acc * NT;
         uint32_t accumulate = 0;
         for (int c = 0; c < p.nchunks; ++c) {
-          const uint32_t slot = a_it & 1u;
-          hg::mbar_wait(&bars->a_full[slot], (a_it >> 1) & 1u);
+          const uint32_t slot = a_it % p.a_slots;
+          hg::mbar_wait(&bars->a_full[slot], (a_it / p.a_slots) & 1u);
+          hg::tc_fence_after();
           const uint32_t a_base = hg::smem_u32(a_buf + slot * p.a_slot_bytes);
-          for (int j = 0; j < p.ktaps; ++j) {
-            const uint32_t s = w_it % p.stages;
-            hg::mbar_wait(&bars->w_full[s], (w_it / p.stages) & 1u);
-            hg::tc_fence_after();
-            const uint32_t a_tap = a_base + static_cast<uint32_t>(j * p.dil) * kRowBytes;
-            const uint32_t w_base = hg::smem_u32(w_buf + s * p.w_stage_bytes);
+          if (p.resident) {
+            const uint32_t w_chunk = w_smem + static_cast<uint32_t>(c * p.ktaps) * kTapBytes;
+            for (int j = 0; j < p.ktaps; ++j) {
+              const uint32_t a_tap = a_base + static_cast<uint32_t>(j * p.dil) * kRowBytes;
+              const uint32_t w_tap = w_chunk + static_cast<uint32_t>(j) * kTapBytes;
 #pragma unroll
-            for (int kk = 0; kk < KC / 16; ++kk) {
-              const uint64_t da = hg::umma_smem_desc(a_tap + kk * 32, kSbo, kLayout, 0);
-              const uint64_t db = hg::umma_smem_desc(w_base + kk * 32, kSbo, kLayout, 0);
-              hg::umma_bf16_ss(d_tmem, da, db, idesc, accumulate);
-              accumulate = 1;
+              for (int kk = 0; kk < KC / 16; ++kk) {
+                hg::umma_bf16_ss(d_tmem, hg::umma_smem_desc(a_tap + kk * 32, kSbo, kLayout, 0),
+                                 hg::umma_smem_desc(w_tap + kk * 32, kSbo, kLayout, 0), idesc,
+                                 accumulate);
+                accumulate = 1;
+              }
             }
-            hg::umma_commit(&bars->w_empty[s]);
-            ++w_it;
+          } else {
+            for (int g = 0; g < p.groups; ++g) {
+              const uint32_t s = w_it % p.stages;
+              hg::mbar_wait(&bars->w_full[s], (w_it / p.stages) & 1u);
+              hg::tc_fence_after();
+              const uint32_t w_stage = w_smem + s * p.w_stage_bytes;
+              const int j_end = min(p.ktaps, (g + 1) * p.tps);
+              for (int j = g * p.tps; j < j_end; ++j) {
+                const uint32_t a_tap = a_base + static_cast<uint32_t>(j * p.dil) * kRowBytes;
+                const uint32_t w_tap = w_stage + static_cast<uint32_t>(j - g * p.tps) * kTapBytes;
+#pragma unroll
+                for (int kk = 0; kk < KC / 16; ++kk) {
+                  hg::umma_bf16_ss(d_tmem, hg::umma_smem_desc(a_tap + kk * 32, kSbo, kLayout, 0),
+                                   hg::umma_smem_desc(w_tap + kk * 32, kSbo, kLayout, 0), idesc,
+                                   accumulate);
+                  accumulate = 1;
+                }
+              }
+              hg::umma_commit(&bars->w_empty[s]);
+              ++w_it;
+            }
           }
           hg::umma_commit(&bars->a_empty[slot]);
           ++a_it;
@@ -182,8 +263,11 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     __syncwarp();
   } else {
     // ============================ epilogue ================================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    const int ew = warp - 2;
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may read
+    const int half = ew >> 2;              // which half of the tile's columns
     const int row = quarter * 32 + lane;
+    const int col0 = half * kColsPerWarp;  // first column (within the tile) owned by this warp
     uint32_t acc_it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int nt = tile % p.tiles_n;
@@ -191,50 +275,53 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       const int tt = rest % p.tiles_t;
       const int b = rest / p.tiles_t;
       const int t = tt * kTileM + row;
+      const bool valid = t < p.t;
+      const int ch0 = nt * NT + col0;
+      const size_t off = (static_cast<size_t>(b) * p.t + (valid ? t : 0)) * p.cout + ch0;
+      // residual prefetch: issued before the accumulator wait so its latency hides under the MMAs
+      U8 rpre[kGroups16];
+      if (p.res0 && valid) {
+#pragma unroll
+        for (int g = 0; g < kGroups16; ++g) rpre[g] = ldg256(p.res0 + off + g * 16);
+      }
       const uint32_t acc = acc_it & 1u;
       hg::mbar_wait(&bars->acc_full[acc], (acc_it >> 1) & 1u);
       hg::tc_fence_after();
-      const bool valid = t < p.t;
-      const size_t row_off = (static_cast<size_t>(b) * p.t + (valid ? t : 0)) * p.cout;
-      for (int cg = 0; cg < p.n_tile / 32; ++cg) {
-        uint32_t raw[32];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                               acc * p.n_tile + cg * 32;
-        hg::tmem_ld_32x32(taddr, raw);
+#pragma unroll
+      for (int g = 0; g < kGroups16; ++g) {
+        uint32_t raw[16];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * NT +
+                               col0 + g * 16;
+        tmem_ld_32x16(taddr, raw);
         hg::tmem_ld_wait();
         if (valid) {
-          const int ch0 = nt * p.n_tile + cg * 32;
-          const size_t off = row_off + ch0;
+          float v[16];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float v[8];
+          for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(raw[e]);
+          if (p.bias) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(raw[q * 8 + e]);
-            if (p.bias) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + q * 8));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + q * 8 + 4));
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            for (int q = 0; q < 4; ++q) {
+              const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + g * 16 + q * 4));
+              v[4 * q] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
             }
-            if (p.res0) add_bf16x8(v, *reinterpret_cast<const uint4*>(p.res0 + off + q * 8));
-            if (p.res1) add_bf16x8(v, *reinterpret_cast<const uint4*>(p.res1 + off + q * 8));
-            if (p.res2) add_bf16x8(v, *reinterpret_cast<const uint4*>(p.res2 + off + q * 8));
+          }
+          if (p.res0) add_bf16x16(v, rpre[g]);
+          if (p.res1) add_bf16x16(v, ldg256(p.res1 + off + g * 16));
+          if (p.res2) add_bf16x16(v, ldg256(p.res2 + off + g * 16));
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] *= p.scale;
-            if (p.out_raw) {
-              uint4 o;
-              o.x = hg::pack_bf16x2(v[0], v[1]); o.y = hg::pack_bf16x2(v[2], v[3]);
-              o.z = hg::pack_bf16x2(v[4], v[5]); o.w = hg::pack_bf16x2(v[6], v[7]);
-              *reinterpret_cast<uint4*>(p.out_raw + off + q * 8) = o;
-            }
-            if (p.out_act) {
-              uint4 o;
-              o.x = hg::pack_bf16x2(hg::lrelu(v[0], p.slope), hg::lrelu(v[1], p.slope));
-              o.y = hg::pack_bf16x2(hg::lrelu(v[2], p.slope), hg::lrelu(v[3], p.slope));
-              o.z = hg::pack_bf16x2(hg::lrelu(v[4], p.slope), hg::lrelu(v[5], p.slope));
-              o.w = hg::pack_bf16x2(hg::lrelu(v[6], p.slope), hg::lrelu(v[7], p.slope));
-              *reinterpret_cast<uint4*>(p.out_act + off + q * 8) = o;
-            }
+          for (int e = 0; e < 16; ++e) v[e] *= p.scale;
+          if (p.out_raw) {
+            U8 o;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o.v[i] = hg::pack_bf16x2(v[2 * i], v[2 * i + 1]);
+            stg256(p.out_raw + off + g * 16, o);
+          }
+          if (p.out_act) {
+            U8 o;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              o.v[i] = hg::pack_bf16x2(hg::lrelu(v[2 * i], p.slope), hg::lrelu(v[2 * i + 1], p.slope));
+            stg256(p.out_act + off + g * 16, o);
           }
         }
       }
@@ -248,7 +335,7 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   hg::tc_fence_before();
   __syncthreads();
   hg::tc_fence_after();
-  if (warp == 1) hg::tmem_dealloc(tmem_base, tmem_cols);
+  if (warp == 1) hg::tmem_dealloc(tmem_base, kTmemCols);
 }
 
 int g_num_sms = 0;
@@ -260,6 +347,20 @@ int device_props() {
   HG_CHECK_CUDA(cudaGetDevice(&dev));
   HG_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   HG_CHECK_CUDA(cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  return HG_OK;
+}
+
+template <int KC, int NT>
+int launch(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const ConvArgs& p, size_t smem_bytes,
+           int grid, cudaStream_t st) {
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    HG_CHECK_CUDA(cudaFuncSetAttribute(conv1d_tc_kernel<KC, NT>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    configured = true;
+  }
+  conv1d_tc_kernel<KC, NT><<<grid, kThreads, smem_bytes, st>>>(tm_x, tm_w, p);
+  HG_CHECK_CUDA(cudaGetLastError());
   return HG_OK;
 }
 
@@ -277,27 +378,49 @@ extern "C" int hg_conv1d_fwd(const void* x, const void* w_packed, const float* b
   HG_REQUIRE(ktaps > 0 && dilation > 0, "hg_conv1d_fwd: bad taps/dilation");
   const int a_rows = kTileM + (ktaps - 1) * dilation;
   HG_REQUIRE(a_rows <= 256, "hg_conv1d_fwd: halo too large for one TMA box (rows=%d > 256)", a_rows);
+  HG_REQUIRE(ktaps <= 256, "hg_conv1d_fwd: too many taps");
   int rc = device_props();
   if (rc) return rc;
 
   const int kc = (cin % 64 == 0) ? 64 : 32;
+  const int n_tile = (cout % 256 == 0) ? 256 : (cout % 128 == 0) ? 128 : (cout % 64 == 0) ? 64 : 32;
   ConvArgs p{};
   p.batch = batch; p.t = t; p.cin = cin; p.cout = cout;
   p.ktaps = ktaps; p.dil = dilation; p.pad_left = pad_left;
-  p.n_tile = (cout % 256 == 0) ? 256 : (cout % 128 == 0) ? 128 : (cout % 64 == 0) ? 64 : 32;
   p.nchunks = cin / kc;
   p.a_rows = a_rows;
   p.tiles_t = (t + kTileM - 1) / kTileM;
-  p.tiles_n = cout / p.n_tile;
+  p.tiles_n = cout / n_tile;
   p.num_tiles = batch * p.tiles_t * p.tiles_n;
   p.a_slot_bytes = (static_cast<uint32_t>(a_rows) * kc * 2 + 1023u) & ~1023u;
-  p.w_stage_bytes = (static_cast<uint32_t>(p.n_tile) * kc * 2 + 1023u) & ~1023u;
-  const int budget = g_max_smem - 1024 /*align*/ - static_cast<int>(sizeof(Barriers)) -
-                     2 * static_cast<int>(p.a_slot_bytes);
-  int stages = budget / static_cast<int>(p.w_stage_bytes);
-  if (stages > kMaxStages) stages = kMaxStages;
-  HG_REQUIRE(stages >= 2, "hg_conv1d_fwd: not enough shared memory for the weight ring");
-  p.stages = stages;
+  const uint32_t tap_bytes = static_cast<uint32_t>(n_tile) * kc * 2;
+  const int budget = g_max_smem - 1024 /*align*/ - static_cast<int>(sizeof(Barriers));
+
+  // resident filter bank: needs all taps of all chunks + at least 2 activation slots
+  const long long w_all = static_cast<long long>(ktaps) * p.nchunks * tap_bytes;
+  uint32_t w_bytes_total;
+  if (p.tiles_n == 1 && w_all + 2LL * p.a_slot_bytes <= budget && w_all < (1 << 20)) {
+    p.resident = 1;
+    p.tps = ktaps; p.groups = 1; p.stages = 1;
+    p.w_stage_bytes = static_cast<uint32_t>(w_all);
+    w_bytes_total = static_cast<uint32_t>(w_all);
+  } else {
+    p.resident = 0;
+    p.tps = tap_bytes >= 32768 ? 1 : static_cast<int>(32768 / tap_bytes);
+    if (p.tps > ktaps) p.tps = ktaps;
+    p.groups = (ktaps + p.tps - 1) / p.tps;
+    p.w_stage_bytes = static_cast<uint32_t>(p.tps) * tap_bytes;
+    int stages = (budget - 2 * static_cast<int>(p.a_slot_bytes)) / static_cast<int>(p.w_stage_bytes);
+    if (stages > 4) stages = 4;
+    HG_REQUIRE(stages >= 2, "hg_conv1d_fwd: not enough shared memory for the weight ring");
+    p.stages = stages;
+    w_bytes_total = static_cast<uint32_t>(stages) * p.w_stage_bytes;
+  }
+  int a_slots = (budget - static_cast<int>(w_bytes_total)) / static_cast<int>(p.a_slot_bytes);
+  if (a_slots > kMaxASlots) a_slots = kMaxASlots;
+  HG_REQUIRE(a_slots >= 2, "hg_conv1d_fwd: not enough shared memory for the activation ring");
+  p.a_slots = a_slots;
+
   p.bias = bias;
   p.res0 = static_cast<const __nv_bfloat16*>(res0);
   p.res1 = static_cast<const __nv_bfloat16*>(res1);
@@ -313,23 +436,27 @@ extern "C" int hg_conv1d_fwd(const void* x, const void* w_packed, const float* b
                               static_cast<uint64_t>(t) * cin * 2, kc, a_rows, 1, swz);
   if (rc) return rc;
   rc = hg_encode_tmap_bf16_3d(&tm_w, w_packed, cin, cout, ktaps, static_cast<uint64_t>(cin) * 2,
-                              static_cast<uint64_t>(cout) * cin * 2, kc, p.n_tile, 1, swz);
+                              static_cast<uint64_t>(cout) * cin * 2, kc, n_tile, p.tps, swz);
   if (rc) return rc;
 
-  const size_t smem_bytes = 1024 + 2 * static_cast<size_t>(p.a_slot_bytes) +
-                            static_cast<size_t>(stages) * p.w_stage_bytes + sizeof(Barriers);
+  const size_t smem_bytes = 1024 + static_cast<size_t>(a_slots) * p.a_slot_bytes + w_bytes_total +
+                            sizeof(Barriers);
   const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define HG_LAUNCH(KC_, NT_) rc = launch<KC_, NT_>(tm_x, tm_w, p, smem_bytes, grid, st)
   if (kc == 64) {
-    HG_CHECK_CUDA(cudaFuncSetAttribute(conv1d_tc_kernel<64>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    conv1d_tc_kernel<64><<<grid, kThreads, smem_bytes, st>>>(tm_x, tm_w, p);
+    if (n_tile == 256) HG_LAUNCH(64, 256);
+    else if (n_tile == 128) HG_LAUNCH(64, 128);
+    else if (n_tile == 64) HG_LAUNCH(64, 64);
+    else HG_LAUNCH(64, 32);
   } else {
-    HG_CHECK_CUDA(cudaFuncSetAttribute(conv1d_tc_kernel<32>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    conv1d_tc_kernel<32><<<grid, kThreads, smem_bytes, st>>>(tm_x, tm_w, p);
+    if (n_tile == 256) HG_LAUNCH(32, 256);
+    else if (n_tile == 128) HG_LAUNCH(32, 128);
+    else if (n_tile == 64) HG_LAUNCH(32, 64);
+    else HG_LAUNCH(32, 32);
   }
-  HG_CHECK_CUDA(cudaGetLastError());
+#undef HG_LAUNCH
+  if (rc) return rc;
   g_hg_launches.fetch_add(1, std::memory_order_relaxed);
   return HG_OK;
 }

@@ -14,4 +14,4 @@ run time v1 1 256 0
 run time v3 64 1024 0
 run layers 64 1024
 cp gpurun_out/bringup.jsonl gpurun_out/perf.jsonl
-tail -c 3000 gpurun_out/perf.log
+tail -c 1500 gpurun_out/perf.log

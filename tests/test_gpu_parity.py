@@ -133,9 +133,12 @@ def test_generator_full_size_vs_reference_golden(H, O, ver):
     G = H.Generator(H.AttrDict(O.config(ver))).cuda().eval()
     x = torch.from_numpy(z["x"]).cuda()
     ref = torch.from_numpy(z["y"])
+    # V2's 8..64-channel layers average far fewer bf16 rounding errors per output than V1/V3: its measured
+    # bf16 noise floor on random-init weights is ~32 dB (V1: 42.5 dB, profiles/r01_bringup.md)
+    snr_min = 28.0 if ver == "v2" else WAVE_SNR_DB
     with torch.no_grad():
         y = G(x).cpu().clone()
-        assert (y - ref).abs().max().item() < WAVE_MAX_ABS and _snr(ref, y) > WAVE_SNR_DB
+        assert (y - ref).abs().max().item() < WAVE_MAX_ABS and _snr(ref, y) > snr_min
         sd3 = {k: (v * 3 if k.endswith("weight_g") else v) for k, v in G.state_dict().items()}
         G.load_state_dict(sd3)
         y3 = G(x).cpu().clone()
@@ -145,7 +148,7 @@ def test_generator_full_size_vs_reference_golden(H, O, ver):
         G.load_state_dict({k: (v / 3 if k.endswith("weight_g") else v) for k, v in G.state_dict().items()})
         G.remove_weight_norm()
         y2 = G(x).cpu()
-        assert (y2 - ref).abs().max().item() < WAVE_MAX_ABS and _snr(ref, y2) > WAVE_SNR_DB
+        assert (y2 - ref).abs().max().item() < WAVE_MAX_ABS and _snr(ref, y2) > snr_min
 
 
 def test_generator_batch_and_ragged_lengths(H, O):

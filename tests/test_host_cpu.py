@@ -187,3 +187,15 @@ def test_segment_sampler_draw_rule_matches_reference():
     ref = random.Random(1234)
     want = [(0 + ref.randint(0, 12), 8), (20, 5), (25 + ref.randint(0, 0), 8), (0 + ref.randint(0, 12), 8)]
     assert picks == want
+
+
+def test_reference_style_top_level_imports():
+    """`src/`-on-PYTHONPATH spelling of the reference (inference.py:9-11) resolves to this package."""
+    import subprocess
+    import sys
+    code = ("from env import AttrDict; from meldataset import mel_spectrogram, MAX_WAV_VALUE, load_wav; "
+            "from models import Generator; from utils import get_padding; "
+            "import hifigan_b200; assert Generator is hifigan_b200.Generator; print('ok')")
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "hifi-gan_b200", "compat") + os.pathsep + ROOT)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd="/tmp")
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr
