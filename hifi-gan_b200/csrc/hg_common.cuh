@@ -153,6 +153,30 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, u
       : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same MMA with the descriptors given as (low word, shared high word): the low word holds the 14-bit
+// start address (>>4) so advancing an operand by `bytes` is `lo + (bytes >> 4)` — two integer adds per
+// MMA instead of rebuilding two 64-bit descriptors (the issuing thread is instruction-bound otherwise).
+__device__ __forceinline__ void umma_bf16_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo,
+                                                uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+      "}\n"
+      :
+      : "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) {
+  return ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
+}
+__device__ __forceinline__ uint32_t umma_desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | ((layout_type & 7u) << 29);
+}
 // mbarrier arrives once every MMA issued so far by this thread has completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
@@ -211,6 +235,44 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t w) {
   __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&w);
   return __bfloat1622float2(h);
 }
+
+struct U8 {
+  uint32_t v[8];
+};
+
+__device__ __forceinline__ U8 ldg256(const void* p) {
+  U8 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]),
+                 "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg256(void* p, const U8& r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r.v[0]),
+               "r"(r.v[1]), "r"(r.v[2]), "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]),
+               "r"(r.v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void add_bf16x16(float (&v)[16], const U8& r) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 f = unpack_bf16x2(r.v[i]);
+    v[2 * i] += f.x;
+    v[2 * i + 1] += f.y;
+  }
+}
+
 
 }  // namespace hg
 

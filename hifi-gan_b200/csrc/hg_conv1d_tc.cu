@@ -67,43 +67,6 @@ struct Barriers {
   uint32_t pad;
 };
 
-struct U8 {
-  uint32_t v[8];
-};
-
-__device__ __forceinline__ U8 ldg256(const void* p) {
-  U8 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]),
-                 "=r"(r.v[6]), "=r"(r.v[7])
-               : "l"(p));
-  return r;
-}
-__device__ __forceinline__ void stg256(void* p, const U8& r) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r.v[0]),
-               "r"(r.v[1]), "r"(r.v[2]), "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]),
-               "r"(r.v[7])
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-        "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void add_bf16x16(float (&v)[16], const U8& r) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float2 f = hg::unpack_bf16x2(r.v[i]);
-    v[2 * i] += f.x;
-    v[2 * i + 1] += f.y;
-  }
-}
-
 // KC = channels per K chunk: 64 -> 128-byte rows / SWIZZLE_128B, 32 -> 64-byte rows / SWIZZLE_64B.
 // NT = output channels per tile (UMMA N).
 template <int KC, int NT>
@@ -199,68 +162,81 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     __syncwarp();
   } else if (warp == 1) {
     // ============================ MMA issuer ==============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = hg::umma_idesc_bf16(kTileM, NT);
-      uint32_t a_it = 0, w_it = 0, acc_it = 0;
-      if (p.resident) {
-        hg::mbar_wait(&bars->w_full[0], 0);
+    // The whole warp walks the loop converged (so addresses stay in uniform registers); one elected
+    // lane issues.  Descriptors: constant high word, low word advanced by plain adds.
+    constexpr uint32_t idesc = hg::umma_idesc_bf16(kTileM, NT);
+    constexpr uint32_t kTapLo = kTapBytes >> 4;
+    const uint32_t desc_hi = hg::umma_desc_hi(kSbo, kLayout);
+    const uint32_t a_tap_step = static_cast<uint32_t>(p.dil) * (kRowBytes >> 4);
+    const uint32_t w_lo0 = hg::umma_desc_lo(hg::smem_u32(w_buf));
+    uint32_t a_it = 0, w_it = 0, acc_it = 0;
+    if (p.resident) {
+      hg::mbar_wait(&bars->w_full[0], 0);
+      hg::tc_fence_after();
+    }
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const uint32_t acc = acc_it & 1u;
+      hg::mbar_wait(&bars->acc_empty[acc], ((acc_it >> 1) & 1u) ^ 1u);
+      hg::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * NT;
+      uint32_t accumulate = 0;
+      for (int c = 0; c < p.nchunks; ++c) {
+        const uint32_t slot = a_it % p.a_slots;
+        hg::mbar_wait(&bars->a_full[slot], (a_it / p.a_slots) & 1u);
         hg::tc_fence_after();
-      }
-      const uint32_t w_smem = hg::smem_u32(w_buf);
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const uint32_t acc = acc_it & 1u;
-        hg::mbar_wait(&bars->acc_empty[acc], ((acc_it >> 1) & 1u) ^ 1u);
-        hg::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * NT;
-        uint32_t accumulate = 0;
-        for (int c = 0; c < p.nchunks; ++c) {
-          const uint32_t slot = a_it % p.a_slots;
-          hg::mbar_wait(&bars->a_full[slot], (a_it / p.a_slots) & 1u);
-          hg::tc_fence_after();
-          const uint32_t a_base = hg::smem_u32(a_buf + slot * p.a_slot_bytes);
-          if (p.resident) {
-            const uint32_t w_chunk = w_smem + static_cast<uint32_t>(c * p.ktaps) * kTapBytes;
+        const uint32_t a_lo0 = hg::umma_desc_lo(hg::smem_u32(a_buf + slot * p.a_slot_bytes));
+        if (p.resident) {
+          if (hg::elect_one()) {
+            uint32_t a_lo = a_lo0;
+            uint32_t w_lo = w_lo0 + static_cast<uint32_t>(c * p.ktaps) * kTapLo;
+            uint32_t acc_flag = accumulate;
             for (int j = 0; j < p.ktaps; ++j) {
-              const uint32_t a_tap = a_base + static_cast<uint32_t>(j * p.dil) * kRowBytes;
-              const uint32_t w_tap = w_chunk + static_cast<uint32_t>(j) * kTapBytes;
 #pragma unroll
               for (int kk = 0; kk < KC / 16; ++kk) {
-                hg::umma_bf16_ss(d_tmem, hg::umma_smem_desc(a_tap + kk * 32, kSbo, kLayout, 0),
-                                 hg::umma_smem_desc(w_tap + kk * 32, kSbo, kLayout, 0), idesc,
-                                 accumulate);
-                accumulate = 1;
+                hg::umma_bf16_ss_lo(d_tmem, a_lo + kk * 2, w_lo + kk * 2, desc_hi, idesc, acc_flag);
+                acc_flag = 1;
               }
-            }
-          } else {
-            for (int g = 0; g < p.groups; ++g) {
-              const uint32_t s = w_it % p.stages;
-              hg::mbar_wait(&bars->w_full[s], (w_it / p.stages) & 1u);
-              hg::tc_fence_after();
-              const uint32_t w_stage = w_smem + s * p.w_stage_bytes;
-              const int j_end = min(p.ktaps, (g + 1) * p.tps);
-              for (int j = g * p.tps; j < j_end; ++j) {
-                const uint32_t a_tap = a_base + static_cast<uint32_t>(j * p.dil) * kRowBytes;
-                const uint32_t w_tap = w_stage + static_cast<uint32_t>(j - g * p.tps) * kTapBytes;
-#pragma unroll
-                for (int kk = 0; kk < KC / 16; ++kk) {
-                  hg::umma_bf16_ss(d_tmem, hg::umma_smem_desc(a_tap + kk * 32, kSbo, kLayout, 0),
-                                   hg::umma_smem_desc(w_tap + kk * 32, kSbo, kLayout, 0), idesc,
-                                   accumulate);
-                  accumulate = 1;
-                }
-              }
-              hg::umma_commit(&bars->w_empty[s]);
-              ++w_it;
+              a_lo += a_tap_step;
+              w_lo += kTapLo;
             }
           }
-          hg::umma_commit(&bars->a_empty[slot]);
-          ++a_it;
+          accumulate = 1;
+          __syncwarp();
+        } else {
+          for (int g = 0; g < p.groups; ++g) {
+            const uint32_t s = w_it % p.stages;
+            hg::mbar_wait(&bars->w_full[s], (w_it / p.stages) & 1u);
+            hg::tc_fence_after();
+            if (hg::elect_one()) {
+              const int j0 = g * p.tps;
+              const int j_end = min(p.ktaps, j0 + p.tps);
+              uint32_t a_lo = a_lo0 + static_cast<uint32_t>(j0) * a_tap_step;
+              uint32_t w_lo = w_lo0 + ((s * p.w_stage_bytes) >> 4);
+              uint32_t acc_flag = accumulate;
+              for (int j = j0; j < j_end; ++j) {
+#pragma unroll
+                for (int kk = 0; kk < KC / 16; ++kk) {
+                  hg::umma_bf16_ss_lo(d_tmem, a_lo + kk * 2, w_lo + kk * 2, desc_hi, idesc, acc_flag);
+                  acc_flag = 1;
+                }
+                a_lo += a_tap_step;
+                w_lo += kTapLo;
+              }
+              hg::umma_commit(&bars->w_empty[s]);
+            }
+            accumulate = 1;
+            __syncwarp();
+            ++w_it;
+          }
         }
-        hg::umma_commit(&bars->acc_full[acc]);
-        ++acc_it;
+        if (hg::elect_one()) hg::umma_commit(&bars->a_empty[slot]);
+        __syncwarp();
+        ++a_it;
       }
+      if (hg::elect_one()) hg::umma_commit(&bars->acc_full[acc]);
+      __syncwarp();
+      ++acc_it;
     }
-    __syncwarp();
   } else {
     // ============================ epilogue ================================
     const int ew = warp - 2;
@@ -279,10 +255,10 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       const int ch0 = nt * NT + col0;
       const size_t off = (static_cast<size_t>(b) * p.t + (valid ? t : 0)) * p.cout + ch0;
       // residual prefetch: issued before the accumulator wait so its latency hides under the MMAs
-      U8 rpre[kGroups16];
+      hg::U8 rpre[kGroups16];
       if (p.res0 && valid) {
 #pragma unroll
-        for (int g = 0; g < kGroups16; ++g) rpre[g] = ldg256(p.res0 + off + g * 16);
+        for (int g = 0; g < kGroups16; ++g) rpre[g] = hg::ldg256(p.res0 + off + g * 16);
       }
       const uint32_t acc = acc_it & 1u;
       hg::mbar_wait(&bars->acc_full[acc], (acc_it >> 1) & 1u);
@@ -292,7 +268,7 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         uint32_t raw[16];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * NT +
                                col0 + g * 16;
-        tmem_ld_32x16(taddr, raw);
+        hg::tmem_ld_32x16(taddr, raw);
         hg::tmem_ld_wait();
         if (valid) {
           float v[16];
@@ -305,23 +281,23 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
               v[4 * q] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
             }
           }
-          if (p.res0) add_bf16x16(v, rpre[g]);
-          if (p.res1) add_bf16x16(v, ldg256(p.res1 + off + g * 16));
-          if (p.res2) add_bf16x16(v, ldg256(p.res2 + off + g * 16));
+          if (p.res0) hg::add_bf16x16(v, rpre[g]);
+          if (p.res1) hg::add_bf16x16(v, hg::ldg256(p.res1 + off + g * 16));
+          if (p.res2) hg::add_bf16x16(v, hg::ldg256(p.res2 + off + g * 16));
 #pragma unroll
           for (int e = 0; e < 16; ++e) v[e] *= p.scale;
           if (p.out_raw) {
-            U8 o;
+            hg::U8 o;
 #pragma unroll
             for (int i = 0; i < 8; ++i) o.v[i] = hg::pack_bf16x2(v[2 * i], v[2 * i + 1]);
-            stg256(p.out_raw + off + g * 16, o);
+            hg::stg256(p.out_raw + off + g * 16, o);
           }
           if (p.out_act) {
-            U8 o;
+            hg::U8 o;
 #pragma unroll
             for (int i = 0; i < 8; ++i)
               o.v[i] = hg::pack_bf16x2(hg::lrelu(v[2 * i], p.slope), hg::lrelu(v[2 * i + 1], p.slope));
-            stg256(p.out_act + off + g * 16, o);
+            hg::stg256(p.out_act + off + g * 16, o);
           }
         }
       }

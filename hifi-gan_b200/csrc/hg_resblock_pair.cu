@@ -1,0 +1,457 @@
+// hg_resblock_pair.cu — one fused ResBlock1 step on tcgen05/TMEM/TMA (sm_100a):
+//
+//     y = conv2(leaky_relu(conv1(leaky_relu(x)) + b1)) + b2 + x          (src/models.py:36-41)
+//
+// for the narrow stages (C = 32 or 64), where the two convolutions run back to back inside one
+// persistent CTA and the intermediate never leaves the SM.  HBM traffic per step drops from six
+// activation-sized transfers (conv1: read act, write act; conv2: read act + residual, write raw + act)
+// to two (read x, write y); both leaky_relus are applied on chip.
+//
+// Per tile of R = 129 - k output steps (conv2, dilation 1, needs (k-1)/2 halo rows of t1 on each side,
+// so conv1 produces exactly 128 rows):
+//   producer warp   TMA box of 128 + (k-1)*d1 raw rows of x           -> X[slot]          (x_full)
+//   transform warps in-place leaky_relu on the box (generic proxy), fence.proxy.async      (x_ready)
+//   MMA thread      acc1 = sum_j X[slot][r + j*d1] * W1_j   (row-shifted descriptors)      (acc1_full)
+//   E1 warps (8)    t1 = leaky_relu(acc1 + b1), zero outside [0,T), bf16 -> T1[i&1] in the swizzled
+//                   K-major layout UMMA expects, fence.proxy.async                         (t1_full)
+//   MMA thread      acc2 = sum_j T1[i&1][r + j] * W2_j                                     (acc2_full)
+//   E2 warps (8)    y = (acc2 + b2 + x + res1 + res2) * scale -> raw / leaky_relu'd bf16 outputs
+// The MMA thread issues conv1 of tile i+1 before conv2 of tile i, and the two epilogue groups work on
+// different tiles concurrently, so the tensor pipe stays busy while an intermediate is being written.  Both filter banks stay
+// resident in shared memory for the whole kernel.  The residual x is re-read from global memory
+// (L2-hot: the same CTA has just pulled those rows in through TMA).
+#include "hg_common.cuh"
+
+#include <atomic>
+
+#include "../../include/hifigan_b200.h"
+
+extern std::atomic<int64_t> g_hg_launches;
+
+namespace {
+
+constexpr int kM = 128;
+constexpr int kXformWarps = 4;
+// epilogue fan-out per role (E1 = intermediate writers, E2 = output writers): C = 64 -> 8 + 8 warps (two per
+// TMEM lane quarter, half the columns each), C = 32 -> 4 + 4 (measured best, profiles/r01_pair_trace.md)
+__host__ __device__ constexpr int epi_halves(int c) { return c == 64 ? 2 : 1; }
+__host__ __device__ constexpr int pair_threads(int c) { return 64 + (kXformWarps + 8 * epi_halves(c)) * 32; }
+constexpr int kMaxXSlots = 4;
+
+struct PairArgs {
+  int batch, t, c;
+  int ktaps, dil1;
+  int r_out;            // output rows per tile = 129 - k
+  int pad1, pad2;       // (k-1)*d1/2, (k-1)/2
+  int a_rows;           // 128 + (k-1)*d1
+  int tiles_t, num_tiles;
+  int x_slots;
+  uint32_t x_slot_bytes, t1_slot_bytes, w_bytes;  // w_bytes: one filter bank
+  const __nv_bfloat16* x;
+  const float* b1;
+  const float* b2;
+  const __nv_bfloat16* res1;
+  const __nv_bfloat16* res2;
+  float scale, in_slope, out_slope;
+  __nv_bfloat16* out_raw;
+  __nv_bfloat16* out_act;
+};
+
+struct PairBarriers {
+  uint64_t x_full[kMaxXSlots], x_ready[kMaxXSlots], x_empty[kMaxXSlots];
+  uint64_t w_full;
+  uint64_t acc1_full[2], acc1_empty[2], t1_full[2], t1_empty[2], acc2_full[2], acc2_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+  float b1[64], b2[64];   // biases, read back as shared-memory broadcasts by the epilogue warps
+};
+
+__device__ __forceinline__ uint32_t lrelu_bf16x2(uint32_t w, __nv_bfloat162 slope2) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&w);
+  v = __hmax2(v, __hmul2(v, slope2));  // slope < 1: max(x, slope*x) == leaky_relu(x)
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// C = channels = UMMA N = K-chunk width: 64 -> SWIZZLE_128B rows of 128 B, 32 -> SWIZZLE_64B rows of 64 B.
+template <int C>
+__global__ void __launch_bounds__(pair_threads(C), 1)
+resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
+                     const __grid_constant__ CUtensorMap tm_w2, const PairArgs p) {
+  constexpr uint32_t kRowBytes = C * 2;
+  constexpr uint32_t kLayout = (C == 64) ? 2u : 4u;
+  constexpr uint32_t kSbo = 8 * kRowBytes;
+  constexpr uint32_t kTapBytes = C * kRowBytes;
+  constexpr uint32_t kTmemCols = 4 * C <= 128 ? 128u : 256u;   // acc1[2] + acc2[2]
+  constexpr int kChunksPerRow = kRowBytes / 16;
+  constexpr int kHalves = epi_halves(C);
+  constexpr int kRoleWarps = 4 * kHalves;      // warps per epilogue role
+  constexpr int kThreads = pair_threads(C);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* x_buf = smem;
+  uint8_t* t1_buf = x_buf + p.x_slots * p.x_slot_bytes;
+  uint8_t* w1_buf = t1_buf + 2 * p.t1_slot_bytes;
+  uint8_t* w2_buf = w1_buf + p.w_bytes;
+  PairBarriers* bars = reinterpret_cast<PairBarriers*>(w2_buf + p.w_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    hg::tma_prefetch_desc(&tm_x);
+    hg::tma_prefetch_desc(&tm_w1);
+    hg::tma_prefetch_desc(&tm_w2);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < kMaxXSlots; ++i) {
+        hg::mbar_init(&bars->x_full[i], 1);
+        hg::mbar_init(&bars->x_ready[i], kXformWarps);
+        hg::mbar_init(&bars->x_empty[i], 1);
+      }
+      hg::mbar_init(&bars->w_full, 1);
+      for (int i = 0; i < 2; ++i) {
+        hg::mbar_init(&bars->acc1_full[i], 1);
+        hg::mbar_init(&bars->acc1_empty[i], kRoleWarps);
+        hg::mbar_init(&bars->t1_full[i], kRoleWarps);
+        hg::mbar_init(&bars->t1_empty[i], 1);
+        hg::mbar_init(&bars->acc2_full[i], 1);
+        hg::mbar_init(&bars->acc2_empty[i], kRoleWarps);
+      }
+      hg::fence_mbar_init();
+    }
+    __syncwarp();
+    hg::tmem_alloc(&bars->tmem_base, kTmemCols);
+  }
+  if (threadIdx.x < C) {
+    bars->b1[threadIdx.x] = p.b1[threadIdx.x];
+    bars->b2[threadIdx.x] = p.b2[threadIdx.x];
+  }
+  // zero the intermediate buffers once: rows 128.. of T1 are read by conv2's last taps (they only feed
+  // discarded output rows) and must stay finite
+  for (uint32_t i = threadIdx.x * 16; i < 2 * p.t1_slot_bytes; i += kThreads * 16)
+    *reinterpret_cast<uint4*>(t1_buf + i) = make_uint4(0, 0, 0, 0);
+  hg::fence_proxy_async_smem();
+  hg::tc_fence_before();
+  __syncthreads();
+  hg::tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&bars->tmem_base);
+  const int n_local = (p.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                      static_cast<int>(gridDim.x);
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      hg::mbar_arrive_expect_tx(&bars->w_full, 2 * p.w_bytes);
+      hg::tma_load_3d(w1_buf, &tm_w1, &bars->w_full, 0, 0, 0);
+      hg::tma_load_3d(w2_buf, &tm_w2, &bars->w_full, 0, 0, 0);
+      const uint32_t x_bytes = static_cast<uint32_t>(p.a_rows) * kRowBytes;
+      for (int i = 0; i < n_local; ++i) {
+        const int tile = blockIdx.x + i * gridDim.x;
+        const int tt = tile % p.tiles_t, b = tile / p.tiles_t;
+        const uint32_t slot = i % p.x_slots;
+        hg::mbar_wait(&bars->x_empty[slot], ((i / p.x_slots) & 1u) ^ 1u);
+        hg::mbar_arrive_expect_tx(&bars->x_full[slot], x_bytes);
+        hg::tma_load_3d(x_buf + slot * p.x_slot_bytes, &tm_x, &bars->x_full[slot], 0,
+                        tt * p.r_out - p.pad2 - p.pad1, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ============================ MMA issuer ==============================
+    // whole warp converged, one elected lane issues; descriptors advanced by adds on the low word
+    constexpr uint32_t idesc = hg::umma_idesc_bf16(kM, C);
+    constexpr uint32_t kTapLo = kTapBytes >> 4;
+    const uint32_t desc_hi = hg::umma_desc_hi(kSbo, kLayout);
+    const uint32_t w1_lo = hg::umma_desc_lo(hg::smem_u32(w1_buf));
+    const uint32_t w2_lo = hg::umma_desc_lo(hg::smem_u32(w2_buf));
+    const uint32_t x_tap_step = static_cast<uint32_t>(p.dil1) * (kRowBytes >> 4);
+    hg::mbar_wait(&bars->w_full, 0);
+    hg::tc_fence_after();
+    auto issue = [&](uint32_t d, uint32_t a_lo, uint32_t w_lo, uint32_t a_step) {
+      uint32_t accumulate = 0;
+      for (int j = 0; j < p.ktaps; ++j) {
+#pragma unroll
+        for (int kk = 0; kk < C / 16; ++kk) {
+          hg::umma_bf16_ss_lo(d, a_lo + kk * 2, w_lo + kk * 2, desc_hi, idesc, accumulate);
+          accumulate = 1;
+        }
+        a_lo += a_step;
+        w_lo += kTapLo;
+      }
+    };
+    auto conv1 = [&](int i) {
+      const uint32_t slot = i % p.x_slots, a = i & 1u, ph = (i >> 1) & 1u;
+      hg::mbar_wait(&bars->x_ready[slot], (i / p.x_slots) & 1u);
+      hg::mbar_wait(&bars->acc1_empty[a], ph ^ 1u);
+      hg::tc_fence_after();
+      if (hg::elect_one()) {
+        issue(tmem_base + a * C, hg::umma_desc_lo(hg::smem_u32(x_buf + slot * p.x_slot_bytes)), w1_lo,
+              x_tap_step);
+        hg::umma_commit(&bars->x_empty[slot]);
+        hg::umma_commit(&bars->acc1_full[a]);
+      }
+      __syncwarp();
+    };
+    auto conv2 = [&](int i) {
+      const uint32_t a = i & 1u, ph = (i >> 1) & 1u;
+      hg::mbar_wait(&bars->t1_full[a], ph);
+      hg::mbar_wait(&bars->acc2_empty[a], ph ^ 1u);
+      hg::tc_fence_after();
+      if (hg::elect_one()) {
+        issue(tmem_base + 2 * C + a * C, hg::umma_desc_lo(hg::smem_u32(t1_buf + a * p.t1_slot_bytes)), w2_lo,
+              kRowBytes >> 4);
+        hg::umma_commit(&bars->t1_empty[a]);
+        hg::umma_commit(&bars->acc2_full[a]);
+      }
+      __syncwarp();
+    };
+    if (n_local > 0) conv1(0);
+    for (int i = 0; i < n_local; ++i) {
+      if (i + 1 < n_local) conv1(i + 1);
+      conv2(i);
+    }
+  } else if (warp < 2 + kXformWarps) {
+    // ============================ transform: in-place leaky_relu ==========
+    const int tid = (warp - 2) * 32 + lane;
+    const __nv_bfloat162 slope2 = __float2bfloat162_rn(p.in_slope);
+    const int n_chunks = p.a_rows * kChunksPerRow;
+    for (int i = 0; i < n_local; ++i) {
+      const uint32_t slot = i % p.x_slots;
+      hg::mbar_wait(&bars->x_full[slot], (i / p.x_slots) & 1u);
+      uint4* xs = reinterpret_cast<uint4*>(x_buf + slot * p.x_slot_bytes);
+      for (int q = tid; q < n_chunks; q += kXformWarps * 32) {
+        uint4 v = xs[q];
+        v.x = lrelu_bf16x2(v.x, slope2); v.y = lrelu_bf16x2(v.y, slope2);
+        v.z = lrelu_bf16x2(v.z, slope2); v.w = lrelu_bf16x2(v.w, slope2);
+        xs[q] = v;
+      }
+      hg::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) hg::mbar_arrive(&bars->x_ready[slot]);
+    }
+  } else {
+    // ============================ epilogue ================================
+    // Two specialised groups of 8 warps (two warps per TMEM lane quarter, half of the C columns each) so
+    // the intermediate writer (E1) and the output writer (E2) of consecutive tiles run concurrently.  The
+    // epilogue is instruction-issue bound per warp (clock64 traces, profiles/r01_pair_trace.md), hence the
+    // wide fan-out.
+    const int ew = warp - (2 + kXformWarps);
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may read
+    const int half = (ew >> 2) % kHalves;  // which slice of the C columns this warp owns
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    constexpr int kG = C / (16 * kHalves);  // 16-column groups per warp
+    const int col0 = half * (C / kHalves);
+
+    if (ew < kRoleWarps) {
+      // ---- E1: t1 = leaky_relu(acc1 + b1), zero outside [0,T)  ->  swizzled K-major smem tile
+      const float* bias = bars->b1;
+      const uint32_t swz = (C == 64) ? (row & 7) : ((row >> 1) & 3);
+      for (int i = 0; i < n_local; ++i) {
+        const int tile = blockIdx.x + i * gridDim.x;
+        const int tt = tile % p.tiles_t;
+        const uint32_t a = i & 1u, ph = (i >> 1) & 1u;
+        const int time = tt * p.r_out - p.pad2 + row;      // time step of t1 row `row`
+        const bool inside = time >= 0 && time < p.t;
+        hg::mbar_wait(&bars->acc1_full[a], ph);
+        hg::mbar_wait(&bars->t1_empty[a], ph ^ 1u);
+        hg::tc_fence_after();
+        uint8_t* trow = t1_buf + a * p.t1_slot_bytes + static_cast<uint32_t>(row) * kRowBytes;
+#pragma unroll
+        for (int g = 0; g < kG; ++g) {
+          uint32_t raw[16];
+          hg::tmem_ld_32x16(tmem_base + lane_base + a * C + col0 + g * 16, raw);
+          hg::tmem_ld_wait();
+          if (g == kG - 1) {   // accumulator fully read: hand it back before the stores
+            hg::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) hg::mbar_arrive(&bars->acc1_empty[a]);
+          }
+          uint32_t o[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float v0 = hg::lrelu(__uint_as_float(raw[2 * q]) + bias[col0 + g * 16 + 2 * q], p.in_slope);
+            const float v1 = hg::lrelu(__uint_as_float(raw[2 * q + 1]) + bias[col0 + g * 16 + 2 * q + 1], p.in_slope);
+            o[q] = inside ? hg::pack_bf16x2(v0, v1) : 0u;
+          }
+          const uint32_t chunk = (col0 >> 3) + g * 2;  // 16-byte chunk index within the row
+          *reinterpret_cast<uint4*>(trow + ((chunk ^ swz) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(trow + (((chunk + 1) ^ swz) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+        hg::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) hg::mbar_arrive(&bars->t1_full[a]);
+      }
+    } else {
+      // ---- E2: y = (acc2 + b2 + x + res1 + res2) * scale  ->  global
+      const float* bias = bars->b2;
+      auto tile_off = [&](int i, bool& valid) -> size_t {
+        const int tile = blockIdx.x + i * gridDim.x;
+        const int tt = tile % p.tiles_t, b = tile / p.tiles_t;
+        const int time = tt * p.r_out + row;
+        valid = row < p.r_out && time < p.t;
+        return (static_cast<size_t>(b) * p.t + (valid ? time : 0)) * C + col0;
+      };
+      // residual rows are fetched one tile ahead so their (L2) latency hides under the previous tile
+      hg::U8 rcur[kG], rnext[kG];
+      bool valid = false, valid_next = false;
+      size_t off = 0, off_next = 0;
+      if (n_local > 0) {
+        off_next = tile_off(0, valid_next);
+        if (valid_next) {
+#pragma unroll
+          for (int g = 0; g < kG; ++g) rnext[g] = hg::ldg256(p.x + off_next + g * 16);
+        }
+      }
+      for (int i = 0; i < n_local; ++i) {
+        const uint32_t a = i & 1u, ph = (i >> 1) & 1u;
+        off = off_next; valid = valid_next;
+#pragma unroll
+        for (int g = 0; g < kG; ++g) rcur[g] = rnext[g];
+        if (i + 1 < n_local) {
+          off_next = tile_off(i + 1, valid_next);
+          if (valid_next) {
+#pragma unroll
+            for (int g = 0; g < kG; ++g) rnext[g] = hg::ldg256(p.x + off_next + g * 16);
+          }
+        }
+        hg::mbar_wait(&bars->acc2_full[a], ph);
+        hg::tc_fence_after();
+#pragma unroll
+        for (int g = 0; g < kG; ++g) {
+          uint32_t raw[16];
+          hg::tmem_ld_32x16(tmem_base + lane_base + 2 * C + a * C + col0 + g * 16, raw);
+          hg::tmem_ld_wait();
+          if (g == kG - 1) {
+            hg::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) hg::mbar_arrive(&bars->acc2_empty[a]);
+          }
+          if (valid) {
+            float v[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(raw[e]) + bias[col0 + g * 16 + e];
+            hg::add_bf16x16(v, rcur[g]);
+            if (p.res1) hg::add_bf16x16(v, hg::ldg256(p.res1 + off + g * 16));
+            if (p.res2) hg::add_bf16x16(v, hg::ldg256(p.res2 + off + g * 16));
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] *= p.scale;
+            if (p.out_raw) {
+              hg::U8 o;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) o.v[q] = hg::pack_bf16x2(v[2 * q], v[2 * q + 1]);
+              hg::stg256(p.out_raw + off + g * 16, o);
+            }
+            if (p.out_act) {
+              hg::U8 o;
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                o.v[q] = hg::pack_bf16x2(hg::lrelu(v[2 * q], p.out_slope), hg::lrelu(v[2 * q + 1], p.out_slope));
+              hg::stg256(p.out_act + off + g * 16, o);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  hg::tc_fence_before();
+  __syncthreads();
+  hg::tc_fence_after();
+  if (warp == 1) hg::tmem_dealloc(tmem_base, kTmemCols);
+}
+
+int g_sms = 0, g_smem = 0;
+
+template <int C>
+int launch_pair(const CUtensorMap& tx, const CUtensorMap& tw1, const CUtensorMap& tw2, const PairArgs& p,
+                size_t smem_bytes, int grid, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    HG_CHECK_CUDA(cudaFuncSetAttribute(resblock_pair_kernel<C>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem));
+    configured = true;
+  }
+  resblock_pair_kernel<C><<<grid, pair_threads(C), smem_bytes, st>>>(tx, tw1, tw2, p);
+  HG_CHECK_CUDA(cudaGetLastError());
+  return HG_OK;
+}
+
+size_t pair_smem_bytes(int c, int ktaps, int dil1, int x_slots, PairArgs* out) {
+  const uint32_t row = static_cast<uint32_t>(c) * 2;
+  const uint32_t a_rows = kM + (ktaps - 1) * dil1;
+  const uint32_t x_slot = (a_rows * row + 1023u) & ~1023u;
+  const uint32_t t1_slot = ((kM + ktaps - 1) * row + 1023u) & ~1023u;
+  const uint32_t w_bytes = static_cast<uint32_t>(ktaps) * c * row;
+  if (out) {
+    out->a_rows = a_rows; out->x_slot_bytes = x_slot; out->t1_slot_bytes = t1_slot; out->w_bytes = w_bytes;
+  }
+  return 1024 + static_cast<size_t>(x_slots) * x_slot + 2 * static_cast<size_t>(t1_slot) +
+         2 * static_cast<size_t>(w_bytes) + sizeof(PairBarriers);
+}
+
+}  // namespace
+
+extern "C" int hg_resblock_pair_supported(int c, int ktaps, int dil1) {
+  if (!(c == 32 || c == 64) || ktaps < 1 || !(ktaps & 1) || dil1 < 1) return 0;
+  if (kM + (ktaps - 1) * dil1 > 256 || ktaps > 65) return 0;
+  if (!g_smem) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&g_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  }
+  return pair_smem_bytes(c, ktaps, dil1, 2, nullptr) <= static_cast<size_t>(g_smem) ? 1 : 0;
+}
+
+extern "C" int hg_resblock_pair_fwd(const void* x, const void* w1_packed, const float* b1,
+                                    const void* w2_packed, const float* b2, int batch, int t, int c,
+                                    int ktaps, int dil1, float in_slope, const void* res1,
+                                    const void* res2, float scale, void* out_raw, void* out_act,
+                                    float out_slope, void* stream) {
+  HG_REQUIRE(x && w1_packed && w2_packed && b1 && b2, "hg_resblock_pair_fwd: null input");
+  HG_REQUIRE(out_raw || out_act, "hg_resblock_pair_fwd: no output requested");
+  HG_REQUIRE(batch > 0 && t > 0, "hg_resblock_pair_fwd: empty batch/time");
+  HG_REQUIRE(hg_resblock_pair_supported(c, ktaps, dil1),
+             "hg_resblock_pair_fwd: unsupported shape c=%d k=%d d=%d (use hg_conv1d_fwd)", c, ktaps, dil1);
+  PairArgs p{};
+  p.batch = batch; p.t = t; p.c = c; p.ktaps = ktaps; p.dil1 = dil1;
+  p.r_out = kM + 1 - ktaps;
+  p.pad1 = (ktaps - 1) * dil1 / 2;
+  p.pad2 = (ktaps - 1) / 2;
+  p.tiles_t = (t + p.r_out - 1) / p.r_out;
+  p.num_tiles = batch * p.tiles_t;
+  int slots = kMaxXSlots;
+  while (slots > 2 && pair_smem_bytes(c, ktaps, dil1, slots, nullptr) > static_cast<size_t>(g_smem)) --slots;
+  p.x_slots = slots;
+  const size_t smem_bytes = pair_smem_bytes(c, ktaps, dil1, slots, &p);
+  p.x = static_cast<const __nv_bfloat16*>(x);
+  p.b1 = b1; p.b2 = b2;
+  p.res1 = static_cast<const __nv_bfloat16*>(res1);
+  p.res2 = static_cast<const __nv_bfloat16*>(res2);
+  p.scale = scale; p.in_slope = in_slope; p.out_slope = out_slope;
+  p.out_raw = static_cast<__nv_bfloat16*>(out_raw);
+  p.out_act = static_cast<__nv_bfloat16*>(out_act);
+
+  CUtensorMap tx, tw1, tw2;
+  const int swz = c * 2;
+  int rc = hg_encode_tmap_bf16_3d(&tx, x, c, t, batch, static_cast<uint64_t>(c) * 2,
+                                  static_cast<uint64_t>(t) * c * 2, c, p.a_rows, 1, swz);
+  if (rc) return rc;
+  rc = hg_encode_tmap_bf16_3d(&tw1, w1_packed, c, c, ktaps, static_cast<uint64_t>(c) * 2,
+                              static_cast<uint64_t>(c) * c * 2, c, c, ktaps, swz);
+  if (rc) return rc;
+  rc = hg_encode_tmap_bf16_3d(&tw2, w2_packed, c, c, ktaps, static_cast<uint64_t>(c) * 2,
+                              static_cast<uint64_t>(c) * c * 2, c, c, ktaps, swz);
+  if (rc) return rc;
+  const int grid = p.num_tiles < g_sms ? p.num_tiles : g_sms;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = (c == 64) ? launch_pair<64>(tx, tw1, tw2, p, smem_bytes, grid, st)
+                 : launch_pair<32>(tx, tw1, tw2, p, smem_bytes, grid, st);
+  if (rc) return rc;
+  g_hg_launches.fetch_add(1, std::memory_order_relaxed);
+  return HG_OK;
+}

@@ -150,27 +150,65 @@ def _conv(L, x, pc: _PackedConv, batch: int, t: int, *, res=(None, None, None), 
                "hg_conv1d_fwd")
 
 
+def _pair(L, x, pc1: _PackedConv, pc2: _PackedConv, batch: int, t: int, *, res=(None, None), scale=1.0,
+          out_raw=None, out_act=None, slope=LRELU_SLOPE) -> None:
+    """One fused ResBlock1 step: conv2(lrelu(conv1(lrelu(x)) + b1)) + b2 + x (+ res) — hg_resblock_pair_fwd."""
+    p = [0 if r is None else r.data_ptr() for r in res]
+    _lib.check(L.hg_resblock_pair_fwd(x.data_ptr(), pc1.w.data_ptr(), pc1.bias.data_ptr(), pc2.w.data_ptr(),
+                                      pc2.bias.data_ptr(), batch, t, pc1.cin_p, pc1.taps, pc1.dil, LRELU_SLOPE,
+                                      p[0], p[1], scale, 0 if out_raw is None else out_raw.data_ptr(),
+                                      0 if out_act is None else out_act.data_ptr(), slope, _stream()),
+               "hg_resblock_pair_fwd")
+
+
+_FUSE_PAIRS = True  # tests flip this to compare the fused and the two-launch paths
+
+
+def _pair_ok(L, pc1: _PackedConv, pc2: _PackedConv) -> bool:
+    return bool(_FUSE_PAIRS and pc1.cin_p == pc1.cout_p == pc2.cin_p == pc2.cout_p and pc1.taps == pc2.taps
+                and pc2.dil == 1 and L.hg_resblock_pair_supported(pc1.cin_p, pc1.taps, pc1.dil))
+
+
+def _block_plan(L, block: "nn.Module", packs: List[_PackedConv]) -> List[bool]:
+    """Per ResBlock step: True when it runs as ONE fused pair launch."""
+    if not isinstance(block, ResBlock1):
+        return [False] * len(packs)
+    return [_pair_ok(L, packs[2 * i], packs[2 * i + 1]) for i in range(len(packs) // 2)]
+
+
 def _resblock_chain(L, block: "nn.Module", packs: List[_PackedConv], batch: int, t: int, c_p: int,
                     x_raw, x_act, bufs: Dict[str, torch.Tensor], final) -> None:
     """Run one ResBlock (type 1: packs = [c1_0, c2_0, c1_1, ...]; type 2: packs = [c_0, c_1, ...]).
-    `final(conv_kwargs)` issues the LAST conv of the block (so the caller can fuse the MRF average)."""
+    `final(kw)` issues the LAST launch of the block (so the caller can fuse the MRF average): kw is either
+    dict(pair=(pc1, pc2), x=raw_input) or dict(pc=conv, x=activated_input, res0=raw_residual).
+    x_act may be None when the first step is fused (fused steps read the raw tensor)."""
     two_conv = isinstance(block, ResBlock1)
-    steps = len(packs) // 2 if two_conv else len(packs)
+    fused = _block_plan(L, block, packs)
+    steps = len(fused)
     cur_raw, cur_act = x_raw, x_act
     ping = [(bufs["a_raw"], bufs["a_act"]), (bufs["b_raw"], bufs["b_act"])]
     for i in range(steps):
         last = i == steps - 1
-        if two_conv:
-            _conv(L, cur_act, packs[2 * i], batch, t, out_act=bufs["t1"])
-            src, pc = bufs["t1"], packs[2 * i + 1]
+        nr, na = ping[i & 1]
+        want_act = (not last) and (not fused[i + 1])  # only an unfused consumer needs the activated copy
+        if fused[i]:
+            pc1, pc2 = packs[2 * i], packs[2 * i + 1]
+            if last:
+                final(dict(pair=(pc1, pc2), x=cur_raw))
+            else:
+                _pair(L, cur_raw, pc1, pc2, batch, t, out_raw=nr, out_act=na if want_act else None)
         else:
-            src, pc = cur_act, packs[i]
-        if last:
-            final(dict(x=src, pc=pc, res0=cur_raw))
-        else:
-            nr, na = ping[i & 1]
-            _conv(L, src, pc, batch, t, res=(cur_raw, None, None), out_raw=nr, out_act=na)
-            cur_raw, cur_act = nr, na
+            if two_conv:
+                _conv(L, cur_act, packs[2 * i], batch, t, out_act=bufs["t1"])
+                src, pc = bufs["t1"], packs[2 * i + 1]
+            else:
+                src, pc = cur_act, packs[i]
+            if last:
+                final(dict(pc=pc, x=src, res0=cur_raw))
+            else:
+                _conv(L, src, pc, batch, t, res=(cur_raw, None, None), out_raw=nr,
+                      out_act=na if (want_act or not two_conv) else None)
+        cur_raw, cur_act = nr, na
 
 
 class _StandaloneBlockMixin:
@@ -199,7 +237,10 @@ class _StandaloneBlockMixin:
                                    bufs["x_act"].data_ptr(), LRELU_SLOPE, _stream()), "hg_ncl_to_nlc")
 
         def final(kw):
-            _conv(L, kw["x"], kw["pc"], b, t, res=(kw["res0"], None, None), out_raw=bufs["out"])
+            if "pair" in kw:
+                _pair(L, kw["x"], *kw["pair"], b, t, out_raw=bufs["out"])
+            else:
+                _conv(L, kw["x"], kw["pc"], b, t, res=(kw["res0"], None, None), out_raw=bufs["out"])
 
         _resblock_chain(L, self, packs, b, t, c_p, bufs["x_raw"], bufs["x_act"], bufs, final)
         y = torch.empty(b, c_p, t, dtype=torch.float32, device=x.device)
@@ -334,7 +375,10 @@ class _GeneratorEngine:
         cur, t = ws["pre"], frames
         nk = gen.num_kernels
         for i, up in enumerate(self.ups):
-            _conv(L, cur, up, b, t, out_raw=ws["x_raw"], out_act=ws["x_act"])
+            # the leaky_relu'd copy of the stage input is only needed by branches whose first step is unfused
+            need_act = any(not _block_plan(L, gen.resblocks[i * nk + j], self.blocks[i * nk + j])[0]
+                           for j in range(nk))
+            _conv(L, cur, up, b, t, out_raw=ws["x_raw"], out_act=ws["x_act"] if need_act else None)
             t *= up.stride
             c_p = up.cout_p
             last_stage = i == len(self.ups) - 1
@@ -346,15 +390,18 @@ class _GeneratorEngine:
                 def final(kw, j=j):
                     if j < nk - 1:
                         # branch result; branches >= 2 of a wide MRF chain onto the running sum
-                        extra = ws[f"r{j - 1}"] if (nk > 3 and j > 0) else None
-                        _conv(L, kw["x"], kw["pc"], b, t, res=(kw["res0"], extra, None), out_raw=ws[f"r{j}"])
+                        others = (ws[f"r{j - 1}"] if (nk > 3 and j > 0) else None, None)
+                        outs = dict(out_raw=ws[f"r{j}"])
                     else:
                         if nk > 3:
                             others = (ws[f"r{nk - 2}"], None)
                         else:
                             others = tuple(ws[f"r{q}"] for q in range(nk - 1)) + (None,) * (3 - nk)
-                        _conv(L, kw["x"], kw["pc"], b, t, res=(kw["res0"],) + others, scale=1.0 / nk,
-                              out_act=ws["stage_out"], slope=out_slope)
+                        outs = dict(scale=1.0 / nk, out_act=ws["stage_out"], slope=out_slope)
+                    if "pair" in kw:
+                        _pair(L, kw["x"], *kw["pair"], b, t, res=others, **outs)
+                    else:
+                        _conv(L, kw["x"], kw["pc"], b, t, res=(kw["res0"],) + others, **outs)
 
                 _resblock_chain(L, blk, packs, b, t, c_p, ws["x_raw"], ws["x_act"], ws, final)
             cur = ws["stage_out"]

@@ -81,6 +81,24 @@ int hg_conv1d_fwd(const void* x, const void* w_packed, const float* bias, int ba
                   float act_slope, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * hg_resblock_pair_fwd — one fused ResBlock1 step (src/models.py:36-41) for the narrow stages:
+ *
+ *   t1 = leaky_relu(conv1d(leaky_relu(x, in_slope), w1, dilation=dil1) + b1, in_slope)
+ *   v  = (conv1d(t1, w2, dilation=1) + b2 + x + res1 + res2) * scale
+ *   out_raw = bf16(v), out_act = bf16(leaky_relu(v, out_slope))        (either may be NULL)
+ *
+ * x, res*, out_* bf16 [B][T][c]; w*_packed bf16 [ktaps][c][c] (hg_pack_conv1d_weight); b* fp32 [c].
+ * Both convolutions use "same" zero padding ((k-1)*d/2).  The intermediate t1 stays in shared memory;
+ * HBM traffic is one read of x and one write per requested output.  out_* must not alias x.
+ * hg_resblock_pair_supported(c, ktaps, dil1) tells whether the shape fits (c in {32,64}, both filter
+ * banks resident in shared memory); otherwise the caller composes two hg_conv1d_fwd calls. */
+int hg_resblock_pair_supported(int c, int ktaps, int dil1);
+int hg_resblock_pair_fwd(const void* x, const void* w1_packed, const float* b1, const void* w2_packed,
+                         const float* b2, int batch, int t, int c, int ktaps, int dil1, float in_slope,
+                         const void* res1, const void* res2, float scale, void* out_raw, void* out_act,
+                         float out_slope, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Layout edges.
  * hg_ncl_to_nlc: fp32 [B][C][T] -> bf16 [B][T][c_pad] (zero-filled channels >= C); the mel input of
  *   Generator.forward (src/models.py:100-101).  `out` receives the values, `out_act` (optional)

@@ -179,6 +179,42 @@ def stage_layers(b, frames):
         del x, wp, res, o1, o2
 
 
+def stage_pairs(b, frames, debug=0):
+    """Timing of hg_resblock_pair_fwd at the V1 narrow-stage shapes vs the two-launch path."""
+    L = _lib.lib()
+    dev = torch.device("cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for c, t in ((64, frames * 128), (32, frames * 256)):
+        for k in (3, 7, 11):
+            for d in (1, 5):
+                if not L.hg_resblock_pair_supported(c, k, d):
+                    emit(stage="pair", c=c, k=k, d=d, supported=False)
+                    continue
+                x = torch.randn(b, t, c, device=dev).bfloat16()
+                w1 = (torch.randn(k, c, c, device=dev) / (c * k) ** 0.5).bfloat16()
+                w2 = (torch.randn(k, c, c, device=dev) / (c * k) ** 0.5).bfloat16()
+                b1 = torch.zeros(c, device=dev)
+                o1 = torch.empty(b, t, c, dtype=torch.bfloat16, device=dev)
+                def run():
+                    _lib.check(L.hg_resblock_pair_fwd(x.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                                                      b1.data_ptr(), b, t, c, k, d, 0.1, 0, 0, 1.0, o1.data_ptr(), 0,
+                                                      0.1, st))
+                for _ in range(2):
+                    run()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(5):
+                    run()
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 5
+                flops = 2.0 * 2 * b * t * c * c * k
+                emit(stage="pair", debug=debug, c=c, k=k, d=d, t=t, b=b, ms=round(ms, 4), tflops=round(flops / ms / 1e9, 1),
+                     gbs=round(2.0 * b * t * c * 2 / ms / 1e6, 1))
+                del x, o1
+
+
 if __name__ == "__main__":
     st = sys.argv[1]
     t0 = time.time()
@@ -188,6 +224,8 @@ if __name__ == "__main__":
         stage_conv(int(sys.argv[2]))
     elif st == "gen":
         stage_gen(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]))
+    elif st == "pairs":
+        stage_pairs(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]) if len(sys.argv) > 4 else 0)
     elif st == "layers":
         stage_layers(int(sys.argv[2]), int(sys.argv[3]))
     elif st == "time":

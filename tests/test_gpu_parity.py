@@ -89,6 +89,66 @@ def test_conv1d_rejects_bad_arguments(H):
     assert rc != 0 and b"halo" in L.hg_last_error()
 
 
+PAIR_CASES = [(64, 3, 1), (64, 3, 5), (64, 7, 3), (64, 7, 5), (32, 3, 1), (32, 7, 5), (32, 11, 1), (32, 11, 5)]
+
+
+@pytest.mark.parametrize("c,k,d", PAIR_CASES)
+@pytest.mark.parametrize("b,t", [(2, 500), (1, 118), (3, 1)])
+def test_resblock_pair_vs_torch_fp32(H, c, k, d, b, t):
+    """hg_resblock_pair_fwd (fused conv-lrelu-conv-residual) vs fp32 torch on the same bf16-rounded inputs,
+    with the intermediate rounded to bf16 exactly where the kernel rounds it.  Covers ragged T (not a multiple
+    of the 129-k row tile), T smaller than one tile and T == 1."""
+    from hifigan_b200 import _lib
+    L = _lib.lib()
+    assert L.hg_resblock_pair_supported(c, k, d) == 1
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(c * 1000 + k * 10 + d)
+    x = torch.randn(b, t, c, generator=g).to(dev).bfloat16()
+    w1 = (torch.randn(c, c, k, generator=g) / (c * k) ** 0.5).to(dev)
+    w2 = (torch.randn(c, c, k, generator=g) / (c * k) ** 0.5).to(dev)
+    b1, b2 = torch.randn(c, generator=g).to(dev), torch.randn(c, generator=g).to(dev)
+    r1 = torch.randn(b, t, c, generator=g).to(dev).bfloat16()
+    r2 = torch.randn(b, t, c, generator=g).to(dev).bfloat16()
+    st = torch.cuda.current_stream().cuda_stream
+    wp1 = torch.empty(k, c, c, dtype=torch.bfloat16, device=dev)
+    wp2 = torch.empty(k, c, c, dtype=torch.bfloat16, device=dev)
+    _lib.check(L.hg_pack_conv1d_weight(w1.data_ptr(), 0, c, c, k, c, wp1.data_ptr(), st))
+    _lib.check(L.hg_pack_conv1d_weight(w2.data_ptr(), 0, c, c, k, c, wp2.data_ptr(), st))
+    out_raw = torch.full((b, t, c), 7.0, dtype=torch.bfloat16, device=dev)
+    out_act = torch.full((b, t, c), 7.0, dtype=torch.bfloat16, device=dev)
+    _lib.check(L.hg_resblock_pair_fwd(x.data_ptr(), wp1.data_ptr(), b1.data_ptr(), wp2.data_ptr(), b2.data_ptr(),
+                                      b, t, c, k, d, 0.1, r1.data_ptr(), r2.data_ptr(), 1.0 / 3,
+                                      out_raw.data_ptr(), out_act.data_ptr(), 0.01, st))
+    torch.cuda.synchronize()
+    xa = F.leaky_relu(x.float(), 0.1).bfloat16().float().transpose(1, 2)
+    t1 = F.conv1d(xa, wp1.float().permute(1, 2, 0).contiguous(), b1, dilation=d, padding=(k - 1) * d // 2)
+    t1 = F.leaky_relu(t1, 0.1).bfloat16().float()
+    y = F.conv1d(t1, wp2.float().permute(1, 2, 0).contiguous(), b2, padding=(k - 1) // 2).transpose(1, 2)
+    ref = (y + x.float() + r1.float() + r2.float()) / 3
+    # one bf16 ulp of the output + the effect of 1-ulp flips of the bf16 intermediate
+    tol = 2.0 ** -8 * ref.abs() + 1.5e-2
+    assert bool(((out_raw.float() - ref).abs() <= tol).all())
+    assert bool(((out_act.float() - F.leaky_relu(ref, 0.01)).abs() <= tol).all())
+    assert (out_raw.float() - ref).abs().mean().item() < 2e-3
+
+
+def test_fused_and_unfused_generator_paths_agree(H, O):
+    """The Generator through fused ResBlock pairs vs the same Generator through two-launch convs."""
+    from hifigan_b200 import models
+    h = H.AttrDict(O.config("v1"))
+    torch.manual_seed(1234)
+    G = H.Generator(h).cuda().eval()
+    x = torch.randn(2, 80, 40, device="cuda")
+    with torch.no_grad():
+        a = G(x).clone()
+        models._FUSE_PAIRS = False
+        try:
+            b = G(x).clone()
+        finally:
+            models._FUSE_PAIRS = True
+    assert (a - b).abs().max().item() < 1e-3 and _snr(b.cpu(), a.cpu()) > 38.0
+
+
 @pytest.mark.parametrize("k,u", [(16, 8), (4, 2), (8, 4)])
 def test_polyphase_conv_transpose_vs_torch(H, k, u):
     from hifigan_b200.models import _PackedConv, _conv
