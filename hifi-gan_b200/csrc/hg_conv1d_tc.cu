@@ -35,10 +35,24 @@ constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr int kMaxStages = 8;
 constexpr int kMaxASlots = 4;
 
+constexpr int kMaxBoxes = 4;
+
 struct ConvArgs {
-  int batch, t, cin, cout;
+  int batch, t, cin, cout;       // t = OUTPUT length; cin = input channels consumed per N tile
+  int t_pitch;                   // rows per batch item in the output / residual tensors (>= t)
   int ktaps, dil, pad_left;
   int nchunks, a_rows;
+  // Strided convs read the activations through the view [B][T_in/stride][stride*C]: output step t and tap j
+  // touch input row stride*t + j - pad = stride*(t + q) + rho, i.e. view row t + q, channel block rho.  Taps
+  // are grouped by residue rho into "boxes"; inside a box consecutive taps are one view row apart, so the
+  // row-shifted-descriptor trick applies per box.  stride == 1: one box, taps `dil` rows apart.
+  int nboxes;
+  int box_col[kMaxBoxes];        // channel-coordinate offset of the box (rho * C_total)
+  int box_row[kMaxBoxes];        // view-row offset of the box relative to the tile's first output step
+  int box_ntaps[kMaxBoxes];      // packed taps [box_tap0, box_tap0 + ntaps) belong to this box
+  int box_tap0[kMaxBoxes];
+  int tap_step;                  // view rows between consecutive taps of a box
+  int grouped;                   // 1: N tile nt reads input channels [nt*cin, (nt+1)*cin)
   int tiles_t, tiles_n, num_tiles;
   int a_slots;          // activation ring depth (2..4)
   int resident;         // 1: all weights of the N tile live in smem for the whole kernel
@@ -139,21 +153,27 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         const int rest = tile / p.tiles_n;
         const int tt = rest % p.tiles_t;
         const int b = rest / p.tiles_t;
-        const int t0 = tt * kTileM - p.pad_left;
+        const int t0 = tt * kTileM;
+        const int chan0 = p.grouped ? nt * p.cin : 0;
         for (int c = 0; c < p.nchunks; ++c) {
-          const uint32_t slot = a_it % p.a_slots;
-          hg::mbar_wait(&bars->a_empty[slot], ((a_it / p.a_slots) & 1u) ^ 1u);
-          hg::mbar_arrive_expect_tx(&bars->a_full[slot], a_bytes);
-          hg::tma_load_3d(a_buf + slot * p.a_slot_bytes, &tm_x, &bars->a_full[slot], c * KC, t0, b);
-          ++a_it;
-          if (!p.resident) {
-            for (int g = 0; g < p.groups; ++g) {
-              const uint32_t s = w_it % p.stages;
-              hg::mbar_wait(&bars->w_empty[s], ((w_it / p.stages) & 1u) ^ 1u);
-              hg::mbar_arrive_expect_tx(&bars->w_full[s], static_cast<uint32_t>(p.tps) * kTapBytes);
-              hg::tma_load_3d(w_buf + s * p.w_stage_bytes, &tm_w, &bars->w_full[s], c * KC, nt * NT,
-                              g * p.tps);
-              ++w_it;
+          for (int bx = 0; bx < p.nboxes; ++bx) {
+            const uint32_t slot = a_it % p.a_slots;
+            hg::mbar_wait(&bars->a_empty[slot], ((a_it / p.a_slots) & 1u) ^ 1u);
+            hg::mbar_arrive_expect_tx(&bars->a_full[slot], a_bytes);
+            hg::tma_load_3d(a_buf + slot * p.a_slot_bytes, &tm_x, &bars->a_full[slot],
+                            p.box_col[bx] + chan0 + c * KC, t0 + p.box_row[bx], b);
+            ++a_it;
+            if (!p.resident) {
+              // weight stages are issued in the order the MMA warp consumes packed taps
+              const int q_end = p.box_tap0[bx] + p.box_ntaps[bx];
+              for (int q = p.box_tap0[bx]; q < q_end; ++q) {
+                if (q % p.tps) continue;
+                const uint32_t s = w_it % p.stages;
+                hg::mbar_wait(&bars->w_empty[s], ((w_it / p.stages) & 1u) ^ 1u);
+                hg::mbar_arrive_expect_tx(&bars->w_full[s], static_cast<uint32_t>(p.tps) * kTapBytes);
+                hg::tma_load_3d(w_buf + s * p.w_stage_bytes, &tm_w, &bars->w_full[s], c * KC, nt * NT, q);
+                ++w_it;
+              }
             }
           }
         }
@@ -167,13 +187,14 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     constexpr uint32_t idesc = hg::umma_idesc_bf16(kTileM, NT);
     constexpr uint32_t kTapLo = kTapBytes >> 4;
     const uint32_t desc_hi = hg::umma_desc_hi(kSbo, kLayout);
-    const uint32_t a_tap_step = static_cast<uint32_t>(p.dil) * (kRowBytes >> 4);
+    const uint32_t a_tap_step = static_cast<uint32_t>(p.tap_step) * (kRowBytes >> 4);
     const uint32_t w_lo0 = hg::umma_desc_lo(hg::smem_u32(w_buf));
     uint32_t a_it = 0, w_it = 0, acc_it = 0;
     if (p.resident) {
       hg::mbar_wait(&bars->w_full[0], 0);
       hg::tc_fence_after();
     }
+    const bool leader = hg::elect_one();
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const uint32_t acc = acc_it & 1u;
       hg::mbar_wait(&bars->acc_empty[acc], ((acc_it >> 1) & 1u) ^ 1u);
@@ -181,39 +202,17 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       const uint32_t d_tmem = tmem_base + acc * NT;
       uint32_t accumulate = 0;
       for (int c = 0; c < p.nchunks; ++c) {
-        const uint32_t slot = a_it % p.a_slots;
-        hg::mbar_wait(&bars->a_full[slot], (a_it / p.a_slots) & 1u);
-        hg::tc_fence_after();
-        const uint32_t a_lo0 = hg::umma_desc_lo(hg::smem_u32(a_buf + slot * p.a_slot_bytes));
-        if (p.resident) {
-          if (hg::elect_one()) {
-            uint32_t a_lo = a_lo0;
-            uint32_t w_lo = w_lo0 + static_cast<uint32_t>(c * p.ktaps) * kTapLo;
-            uint32_t acc_flag = accumulate;
-            for (int j = 0; j < p.ktaps; ++j) {
-#pragma unroll
-              for (int kk = 0; kk < KC / 16; ++kk) {
-                hg::umma_bf16_ss_lo(d_tmem, a_lo + kk * 2, w_lo + kk * 2, desc_hi, idesc, acc_flag);
-                acc_flag = 1;
-              }
-              a_lo += a_tap_step;
-              w_lo += kTapLo;
-            }
-          }
-          accumulate = 1;
-          __syncwarp();
-        } else {
-          for (int g = 0; g < p.groups; ++g) {
-            const uint32_t s = w_it % p.stages;
-            hg::mbar_wait(&bars->w_full[s], (w_it / p.stages) & 1u);
-            hg::tc_fence_after();
-            if (hg::elect_one()) {
-              const int j0 = g * p.tps;
-              const int j_end = min(p.ktaps, j0 + p.tps);
-              uint32_t a_lo = a_lo0 + static_cast<uint32_t>(j0) * a_tap_step;
-              uint32_t w_lo = w_lo0 + ((s * p.w_stage_bytes) >> 4);
+        for (int bx = 0; bx < p.nboxes; ++bx) {
+          const uint32_t slot = a_it % p.a_slots;
+          hg::mbar_wait(&bars->a_full[slot], (a_it / p.a_slots) & 1u);
+          hg::tc_fence_after();
+          uint32_t a_lo = hg::umma_desc_lo(hg::smem_u32(a_buf + slot * p.a_slot_bytes));
+          const int q0 = p.box_tap0[bx], q_end = q0 + p.box_ntaps[bx];
+          if (p.resident) {
+            if (leader) {
+              uint32_t w_lo = w_lo0 + static_cast<uint32_t>(c * p.ktaps + q0) * kTapLo;
               uint32_t acc_flag = accumulate;
-              for (int j = j0; j < j_end; ++j) {
+              for (int q = q0; q < q_end; ++q) {
 #pragma unroll
                 for (int kk = 0; kk < KC / 16; ++kk) {
                   hg::umma_bf16_ss_lo(d_tmem, a_lo + kk * 2, w_lo + kk * 2, desc_hi, idesc, acc_flag);
@@ -222,18 +221,37 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 a_lo += a_tap_step;
                 w_lo += kTapLo;
               }
-              hg::umma_commit(&bars->w_empty[s]);
             }
             accumulate = 1;
-            __syncwarp();
-            ++w_it;
+          } else {
+            for (int q = q0; q < q_end; ++q) {
+              const uint32_t s = w_it % p.stages;
+              const int in_stage = q % p.tps;
+              if (in_stage == 0) {
+                hg::mbar_wait(&bars->w_full[s], (w_it / p.stages) & 1u);
+                hg::tc_fence_after();
+              }
+              const bool stage_done = (in_stage == p.tps - 1) || (q == p.ktaps - 1);
+              if (leader) {
+                const uint32_t w_lo = w_lo0 + ((s * p.w_stage_bytes) >> 4) + static_cast<uint32_t>(in_stage) * kTapLo;
+#pragma unroll
+                for (int kk = 0; kk < KC / 16; ++kk) {
+                  hg::umma_bf16_ss_lo(d_tmem, a_lo + kk * 2, w_lo + kk * 2, desc_hi, idesc, accumulate);
+                  accumulate = 1;
+                }
+                if (stage_done) hg::umma_commit(&bars->w_empty[s]);
+              }
+              accumulate = 1;
+              a_lo += a_tap_step;
+              if (stage_done) ++w_it;
+            }
           }
+          if (leader) hg::umma_commit(&bars->a_empty[slot]);
+          __syncwarp();
+          ++a_it;
         }
-        if (hg::elect_one()) hg::umma_commit(&bars->a_empty[slot]);
-        __syncwarp();
-        ++a_it;
       }
-      if (hg::elect_one()) hg::umma_commit(&bars->acc_full[acc]);
+      if (leader) hg::umma_commit(&bars->acc_full[acc]);
       __syncwarp();
       ++acc_it;
     }
@@ -253,7 +271,7 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       const int t = tt * kTileM + row;
       const bool valid = t < p.t;
       const int ch0 = nt * NT + col0;
-      const size_t off = (static_cast<size_t>(b) * p.t + (valid ? t : 0)) * p.cout + ch0;
+      const size_t off = (static_cast<size_t>(b) * p.t_pitch + (valid ? t : 0)) * p.cout + ch0;
       // residual prefetch: issued before the accumulator wait so its latency hides under the MMAs
       hg::U8 rpre[kGroups16];
       if (p.res0 && valid) {
@@ -340,32 +358,88 @@ int launch(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const ConvArgs& p, 
   return HG_OK;
 }
 
-}  // namespace
+// Packed tap order / residue boxes of a (ktaps, stride, dilation, pad_left) convolution.
+struct TapPlan {
+  int nboxes;
+  int box_col_mult[kMaxBoxes];  // residue rho (multiplied by C_total by the caller)
+  int box_row[kMaxBoxes], box_ntaps[kMaxBoxes], box_tap0[kMaxBoxes];
+  int tap_step, max_ntaps;
+  int order[256];               // packed index -> original tap j
+};
 
-extern "C" int hg_conv1d_fwd(const void* x, const void* w_packed, const float* bias, int batch, int t,
-                             int cin, int cout, int ktaps, int dilation, int pad_left,
-                             const void* res0, const void* res1, const void* res2, float scale,
-                             void* out_raw, void* out_act, float act_slope, void* stream) {
-  HG_REQUIRE(x && w_packed, "hg_conv1d_fwd: null input");
-  HG_REQUIRE(out_raw || out_act, "hg_conv1d_fwd: no output requested");
-  HG_REQUIRE(batch > 0 && t > 0, "hg_conv1d_fwd: empty batch/time (%d,%d)", batch, t);
-  HG_REQUIRE(cin % 32 == 0 && cin > 0, "hg_conv1d_fwd: cin=%d must be a multiple of 32", cin);
-  HG_REQUIRE(cout % 32 == 0 && cout > 0, "hg_conv1d_fwd: cout=%d must be a multiple of 32", cout);
-  HG_REQUIRE(ktaps > 0 && dilation > 0, "hg_conv1d_fwd: bad taps/dilation");
-  const int a_rows = kTileM + (ktaps - 1) * dilation;
-  HG_REQUIRE(a_rows <= 256, "hg_conv1d_fwd: halo too large for one TMA box (rows=%d > 256)", a_rows);
-  HG_REQUIRE(ktaps <= 256, "hg_conv1d_fwd: too many taps");
+int make_tap_plan(int ktaps, int stride, int dilation, int pad_left, TapPlan* tp) {
+  if (ktaps < 1 || ktaps > 256 || stride < 1 || stride > kMaxBoxes || dilation < 1) return -1;
+  if (stride > 1 && dilation != 1) return -1;
+  tp->nboxes = 0;
+  tp->max_ntaps = 0;
+  if (stride == 1) {
+    tp->nboxes = 1;
+    tp->box_col_mult[0] = 0; tp->box_row[0] = -pad_left; tp->box_ntaps[0] = ktaps; tp->box_tap0[0] = 0;
+    tp->tap_step = dilation; tp->max_ntaps = ktaps;
+    for (int j = 0; j < ktaps; ++j) tp->order[j] = j;
+    return 0;
+  }
+  tp->tap_step = 1;
+  int q_packed = 0;
+  for (int rho = 0; rho < stride; ++rho) {
+    int n = 0, qmin = 0;
+    for (int j = 0; j < ktaps; ++j) {
+      const int e = j - pad_left;
+      const int r = ((e % stride) + stride) % stride;
+      if (r != rho) continue;
+      const int q = (e - r) / stride;
+      if (n == 0) qmin = q;
+      tp->order[q_packed + n] = j;
+      ++n;
+    }
+    if (!n) continue;
+    const int b = tp->nboxes++;
+    tp->box_col_mult[b] = rho; tp->box_row[b] = qmin; tp->box_ntaps[b] = n; tp->box_tap0[b] = q_packed;
+    q_packed += n;
+    if (n > tp->max_ntaps) tp->max_ntaps = n;
+  }
+  return 0;
+}
+
+int conv_forward(const void* x, const void* w_packed, const float* bias, int batch, int t_in_rows,
+                 int c_total, int t_out, int t_out_rows, int cin_tile, int cout, int n_tile, int grouped, int ktaps,
+                 int stride, int dilation, int pad_left, const void* res0, const void* res1,
+                 const void* res2, float scale, void* out_raw, void* out_act, float act_slope,
+                 void* stream) {
+  HG_REQUIRE(x && w_packed, "conv: null input");
+  HG_REQUIRE(out_raw || out_act, "conv: no output requested");
+  HG_REQUIRE(batch > 0 && t_out > 0 && t_in_rows > 0, "conv: empty batch/time");
+  HG_REQUIRE(cin_tile % 32 == 0 && cin_tile > 0, "conv: cin=%d must be a multiple of 32", cin_tile);
+  HG_REQUIRE(cout % 32 == 0 && cout > 0, "conv: cout=%d must be a multiple of 32", cout);
+  HG_REQUIRE(n_tile == 32 || n_tile == 64 || n_tile == 128 || n_tile == 256, "conv: bad N tile %d", n_tile);
+  HG_REQUIRE(cout % n_tile == 0, "conv: cout %d is not a multiple of the N tile %d", cout, n_tile);
+  HG_REQUIRE(t_in_rows % stride == 0, "conv: input rows %d must be a multiple of the stride %d",
+             t_in_rows, stride);
+  TapPlan tp;
+  HG_REQUIRE(make_tap_plan(ktaps, stride, dilation, pad_left, &tp) == 0,
+             "conv: unsupported taps/stride/dilation (%d,%d,%d)", ktaps, stride, dilation);
+  const int a_rows = kTileM + (tp.max_ntaps - 1) * tp.tap_step;
+  HG_REQUIRE(a_rows <= 256, "conv: halo too large for one TMA box (rows=%d > 256)", a_rows);
   int rc = device_props();
   if (rc) return rc;
 
-  const int kc = (cin % 64 == 0) ? 64 : 32;
-  const int n_tile = (cout % 256 == 0) ? 256 : (cout % 128 == 0) ? 128 : (cout % 64 == 0) ? 64 : 32;
+  const int kc = (cin_tile % 64 == 0) ? 64 : 32;
   ConvArgs p{};
-  p.batch = batch; p.t = t; p.cin = cin; p.cout = cout;
+  HG_REQUIRE(t_out_rows >= t_out, "conv: output pitch %d < rows %d", t_out_rows, t_out);
+  p.batch = batch; p.t = t_out; p.t_pitch = t_out_rows; p.cin = cin_tile; p.cout = cout;
   p.ktaps = ktaps; p.dil = dilation; p.pad_left = pad_left;
-  p.nchunks = cin / kc;
+  p.nchunks = cin_tile / kc;
   p.a_rows = a_rows;
-  p.tiles_t = (t + kTileM - 1) / kTileM;
+  p.nboxes = tp.nboxes;
+  for (int b = 0; b < tp.nboxes; ++b) {
+    p.box_col[b] = tp.box_col_mult[b] * c_total;
+    p.box_row[b] = tp.box_row[b];
+    p.box_ntaps[b] = tp.box_ntaps[b];
+    p.box_tap0[b] = tp.box_tap0[b];
+  }
+  p.tap_step = tp.tap_step;
+  p.grouped = grouped;
+  p.tiles_t = (t_out + kTileM - 1) / kTileM;
   p.tiles_n = cout / n_tile;
   p.num_tiles = batch * p.tiles_t * p.tiles_n;
   p.a_slot_bytes = (static_cast<uint32_t>(a_rows) * kc * 2 + 1023u) & ~1023u;
@@ -388,13 +462,13 @@ extern "C" int hg_conv1d_fwd(const void* x, const void* w_packed, const float* b
     p.w_stage_bytes = static_cast<uint32_t>(p.tps) * tap_bytes;
     int stages = (budget - 2 * static_cast<int>(p.a_slot_bytes)) / static_cast<int>(p.w_stage_bytes);
     if (stages > 4) stages = 4;
-    HG_REQUIRE(stages >= 2, "hg_conv1d_fwd: not enough shared memory for the weight ring");
+    HG_REQUIRE(stages >= 2, "conv: not enough shared memory for the weight ring");
     p.stages = stages;
     w_bytes_total = static_cast<uint32_t>(stages) * p.w_stage_bytes;
   }
   int a_slots = (budget - static_cast<int>(w_bytes_total)) / static_cast<int>(p.a_slot_bytes);
   if (a_slots > kMaxASlots) a_slots = kMaxASlots;
-  HG_REQUIRE(a_slots >= 2, "hg_conv1d_fwd: not enough shared memory for the activation ring");
+  HG_REQUIRE(a_slots >= 2, "conv: not enough shared memory for the activation ring");
   p.a_slots = a_slots;
 
   p.bias = bias;
@@ -408,11 +482,13 @@ extern "C" int hg_conv1d_fwd(const void* x, const void* w_packed, const float* b
 
   CUtensorMap tm_x, tm_w;
   const int swz = kc * 2;
-  rc = hg_encode_tmap_bf16_3d(&tm_x, x, cin, t, batch, static_cast<uint64_t>(cin) * 2,
-                              static_cast<uint64_t>(t) * cin * 2, kc, a_rows, 1, swz);
+  // activations through the strided view [B][T_in/stride][stride*C_total]
+  rc = hg_encode_tmap_bf16_3d(&tm_x, x, static_cast<uint64_t>(stride) * c_total, t_in_rows / stride, batch,
+                              static_cast<uint64_t>(stride) * c_total * 2,
+                              static_cast<uint64_t>(t_in_rows) * c_total * 2, kc, a_rows, 1, swz);
   if (rc) return rc;
-  rc = hg_encode_tmap_bf16_3d(&tm_w, w_packed, cin, cout, ktaps, static_cast<uint64_t>(cin) * 2,
-                              static_cast<uint64_t>(cout) * cin * 2, kc, n_tile, p.tps, swz);
+  rc = hg_encode_tmap_bf16_3d(&tm_w, w_packed, cin_tile, cout, ktaps, static_cast<uint64_t>(cin_tile) * 2,
+                              static_cast<uint64_t>(cout) * cin_tile * 2, kc, n_tile, p.tps, swz);
   if (rc) return rc;
 
   const size_t smem_bytes = 1024 + static_cast<size_t>(a_slots) * p.a_slot_bytes + w_bytes_total +
@@ -435,4 +511,47 @@ extern "C" int hg_conv1d_fwd(const void* x, const void* w_packed, const float* b
   if (rc) return rc;
   g_hg_launches.fetch_add(1, std::memory_order_relaxed);
   return HG_OK;
+}
+
+}  // namespace
+
+extern "C" int hg_conv1d_fwd(const void* x, const void* w_packed, const float* bias, int batch, int t,
+                             int cin, int cout, int ktaps, int dilation, int pad_left,
+                             const void* res0, const void* res1, const void* res2, float scale,
+                             void* out_raw, void* out_act, float act_slope, void* stream) {
+  HG_REQUIRE(cout > 0 && cout % 32 == 0, "hg_conv1d_fwd: cout=%d must be a multiple of 32", cout);
+  HG_REQUIRE(cin > 0 && cin % 32 == 0, "hg_conv1d_fwd: cin=%d must be a multiple of 32", cin);
+  HG_REQUIRE(ktaps > 0 && dilation > 0 && 128 + (ktaps - 1) * dilation <= 256,
+             "hg_conv1d_fwd: halo too large for one TMA box (taps=%d dilation=%d)", ktaps, dilation);
+  const int n_tile = (cout % 256 == 0) ? 256 : (cout % 128 == 0) ? 128 : (cout % 64 == 0) ? 64 : 32;
+  return conv_forward(x, w_packed, bias, batch, t, cin, t, t, cin, cout, n_tile, 0, ktaps, 1, dilation, pad_left,
+                      res0, res1, res2, scale, out_raw, out_act, act_slope, stream);
+}
+
+extern "C" int hg_conv1d_tap_order(int ktaps, int stride, int pad_left, int* host_order) {
+  TapPlan tp;
+  HG_REQUIRE(host_order && make_tap_plan(ktaps, stride, 1, pad_left, &tp) == 0,
+             "hg_conv1d_tap_order: unsupported (taps=%d stride=%d)", ktaps, stride);
+  for (int q = 0; q < ktaps; ++q) host_order[q] = tp.order[q];
+  return HG_OK;
+}
+
+extern "C" int hg_conv1d_general_fwd(const void* x, const void* w_packed, const float* bias, int batch,
+                                     int t_in_rows, int c_total, int t_out, int t_out_rows, int groups,
+                                     int cout, int ktaps,
+                                     int stride, int pad_left, void* out_act, float act_slope,
+                                     void* out_raw, void* stream) {
+  HG_REQUIRE(groups >= 1 && c_total % groups == 0 && cout % groups == 0, "hg_conv1d_general_fwd: bad groups");
+  const int cin_tile = c_total / groups, n_tile_g = cout / groups;
+  if (groups == 1) {
+    const int n_tile = (cout % 256 == 0) ? 256 : (cout % 128 == 0) ? 128 : (cout % 64 == 0) ? 64 : 32;
+    return conv_forward(x, w_packed, bias, batch, t_in_rows, c_total, t_out, t_out_rows, c_total, cout, n_tile, 0,
+                        ktaps,
+                        stride, 1, pad_left, nullptr, nullptr, nullptr, 1.f, out_raw, out_act, act_slope,
+                        stream);
+  }
+  return conv_forward(x, w_packed, bias, batch, t_in_rows, c_total, t_out, t_out_rows, cin_tile, cout, n_tile_g, 1,
+                      ktaps,
+                      stride, 1, pad_left, nullptr, nullptr, nullptr, 1.f, out_raw, out_act, act_slope,
+                      stream);
 }

@@ -481,10 +481,135 @@ class Generator(torch.nn.Module):
 
 
 # --------------------------------------------------------------------------------------------------
-# Discriminators: parameter containers with the reference's exact module tree / state_dict keys
-# (src/models.py:128-248).  Their CUDA forward/backward kernels (SURVEY §8 rows PD/MPD/SD/MSD, K5-K8)
-# are not built yet, and there is deliberately no library fallback: forward raises.
+# Discriminators (reference src/models.py:128-248).  Same module tree / state_dict keys as the reference; the
+# forward pass runs on libhifigan_b200.so: Cin = 1 and Cout = 1 ends on CUDA-core kernels (hg_disc_*), every
+# wide layer on the tcgen05 implicit-GEMM kernel (hg_conv1d_general_fwd) — strided layers through residue
+# boxes, grouped layers as per-group N tiles (narrow groups merged into block-diagonal 32-wide ones).
+# Activations live as bf16 [B*period][rows][C]: one independent 1-D sequence per period column.
 # --------------------------------------------------------------------------------------------------
+def _effective_weight(m: nn.Module) -> torch.Tensor:
+    """fp32 conv weight of a weight_norm / spectral_norm / plain module, computed on the module's device.
+    weight_norm: g * v / ||v|| (dim 0).  spectral_norm: W / sigma with ONE power iteration per call in
+    train mode, updating the `weight_u` / `weight_v` buffers in place exactly like
+    torch.nn.utils.spectral_norm (eps 1e-12) — the reference relies on that call-by-call behaviour
+    (SURVEY.md Appendix B.11); eval mode uses the stored buffers.
+    (Weight preparation is a handful of tiny device ops per layer, not the conv hot path.)"""
+    with torch.no_grad():
+        if hasattr(m, "weight_g"):
+            v, g = m.weight_v, m.weight_g
+            dims = tuple(range(1, v.dim()))
+            return (v * (g / v.pow(2).sum(dim=dims, keepdim=True).sqrt())).float()
+        if hasattr(m, "weight_orig"):
+            w = m.weight_orig
+            wm = w.flatten(1)
+            u, v = m.weight_u, m.weight_v
+            if m.training:
+                v.copy_(torch.nn.functional.normalize(torch.mv(wm.t(), u), dim=0, eps=1e-12))
+                u.copy_(torch.nn.functional.normalize(torch.mv(wm, v), dim=0, eps=1e-12))
+            sigma = torch.dot(u, torch.mv(wm, v))
+            return (w / sigma).float()
+        return m.weight.float()
+
+
+def _round_up(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+class _DiscLayer:
+    """One wide discriminator conv in GEMM-ready form (taps in the kernel's residue order, narrow groups
+    merged into block-diagonal tiles)."""
+
+    def __init__(self, cin, cout, k, stride, pad, groups):
+        self.cin, self.cout, self.k, self.stride, self.pad = cin, cout, k, stride, pad
+        cin_g, cout_g = cin // groups, cout // groups
+        merge = 1
+        if groups == 1:
+            if cin % 32 or cout % 32:
+                raise NotImplementedError(f"conv {cin}->{cout}: channel counts must be multiples of 32")
+        else:
+            while (cin_g * merge) % 32 or (cout_g * merge) not in (32, 64, 128, 256):
+                merge *= 2
+                if merge > groups:
+                    raise NotImplementedError(f"cannot tile conv {cin}->{cout} groups={groups}")
+        self.groups, self.merge = groups, merge
+        self.groups_eff = groups // merge
+        self.cin_tile = cin if groups == 1 else cin_g * merge
+        order = (c_int * k)()
+        _lib.check(_lib.lib().hg_conv1d_tap_order(k, stride, pad, order), "hg_conv1d_tap_order")
+        self.order = list(order)
+
+    def pack(self, w: torch.Tensor) -> torch.Tensor:
+        """w fp32 [cout][cin/groups][k] -> bf16 [k (kernel order)][cout][cin_tile]."""
+        cout, cin_g, k = w.shape
+        w = w[:, :, self.order]
+        if self.groups > 1 and self.merge > 1:
+            full = w.new_zeros(cout, self.cin_tile, k)
+            cout_g = cout // self.groups
+            slot = (torch.arange(cout, device=w.device) // cout_g) % self.merge   # position inside the merged tile
+            idx = slot.unsqueeze(1) * cin_g + torch.arange(cin_g, device=w.device).unsqueeze(0)  # [cout][cin_g]
+            full.scatter_(1, idx.unsqueeze(2).expand(-1, -1, k), w)
+            w = full
+        return w.permute(2, 0, 1).contiguous().to(torch.bfloat16)
+
+
+def _disc_forward(L, y: torch.Tensor, period: int, first, mids, last, mods):
+    """Shared body of DiscriminatorP / DiscriminatorS.  y fp32 [B,1,T] -> (logits [B, H*p], fmaps fp32 NCHW-like).
+    first = (k, stride, pad, cout), mids = [_DiscLayer], last = (k,), mods = conv modules in order."""
+    b, c, t = y.shape
+    if c != 1:
+        raise ValueError("discriminators take [B,1,T] audio")
+    dev = y.device
+    yin = y.reshape(b, t).contiguous().float()
+    st = _stream()
+    k0, s0, p0, c0 = first
+    h = (t + period - 1) // period
+    if (h * period - t) >= t:
+        raise RuntimeError("reflect padding needs n_pad < t (reference F.pad behaviour)")
+    h = (h + 2 * p0 - k0) // s0 + 1
+    nseq = b * period
+    rows = _round_up(h, mids[0].stride)
+    act = torch.zeros(nseq, rows, c0, dtype=torch.bfloat16, device=dev)
+    w0 = _effective_weight(mods[0]).reshape(c0, k0).contiguous()
+    _lib.check(L.hg_disc_first_conv_fwd(yin.data_ptr(), w0.data_ptr(), mods[0].bias.detach().float().data_ptr(), b, t,
+                                        period, k0, s0, p0, c0, rows, act.data_ptr(), LRELU_SLOPE, st),
+               "hg_disc_first_conv_fwd")
+    feats = [(act, h, rows, c0)]
+    for li, layer in enumerate(mids):
+        m = mods[1 + li]
+        w = _effective_weight(m)
+        w = layer.pack(w.reshape(w.shape[0], w.shape[1], layer.k))
+        bias = m.bias.detach().float().contiguous()
+        h_out = (h + 2 * layer.pad - layer.k) // layer.stride + 1
+        nxt_stride = mids[li + 1].stride if li + 1 < len(mids) else 1
+        rows_out = _round_up(h_out, nxt_stride)
+        out = torch.zeros(nseq, rows_out, layer.cout, dtype=torch.bfloat16, device=dev)
+        _lib.check(L.hg_conv1d_general_fwd(act.data_ptr(), w.data_ptr(), bias.data_ptr(), nseq, rows, layer.cin, h_out,
+                                           rows_out, layer.groups_eff, layer.cout, layer.k, layer.stride, layer.pad,
+                                           out.data_ptr(), LRELU_SLOPE, 0, st), "hg_conv1d_general_fwd")
+        act, h, rows = out, h_out, rows_out
+        feats.append((act, h, rows, layer.cout))
+    mp = mods[-1]
+    kp = last[0]
+    wp = _effective_weight(mp).reshape(feats[-1][3], kp).contiguous()
+    post = torch.empty(nseq, h, dtype=torch.float32, device=dev)
+    _lib.check(L.hg_disc_last_conv_fwd(act.data_ptr(), wp.data_ptr(), mp.bias.detach().float().data_ptr(), nseq, h, rows,
+                                       feats[-1][3], kp, post.data_ptr(), st), "hg_disc_last_conv_fwd")
+    fmap = []
+    for a_, h_, rows_, c_ in feats:
+        f = torch.empty(b, c_, h_, period, dtype=torch.float32, device=dev)
+        _lib.check(L.hg_disc_export_fmap(a_.data_ptr(), b, period, h_, rows_, c_, f.data_ptr(), st), "hg_disc_export_fmap")
+        fmap.append(f)
+    post = post.view(b, period, h).permute(0, 2, 1).contiguous().unsqueeze(1)  # [B,1,H,p]
+    fmap.append(post)
+    return torch.flatten(post, 1, -1), fmap
+
+
+def _check_disc_input(x: torch.Tensor, what: str) -> None:
+    _require_cuda(x, what)
+    if torch.is_grad_enabled() and x.requires_grad:
+        raise NotImplementedError(f"{what}: backward kernels are not built yet (SURVEY §8 row T)")
+
+
 class DiscriminatorP(torch.nn.Module):
     def __init__(self, period, kernel_size=5, stride=3, use_spectral_norm=False):
         super().__init__()
@@ -498,8 +623,14 @@ class DiscriminatorP(torch.nn.Module):
         self.conv_post = norm_f(Conv2d(1024, 1, (3, 1), 1, padding=(1, 0)))
 
     def forward(self, x):
-        raise NotImplementedError("DiscriminatorP CUDA kernels (hg_mpd_conv_*) are not built yet; "
-                                  "hifigan_b200 has no library/CPU fallback")
+        _check_disc_input(x, "DiscriminatorP.forward")
+        convs = list(self.convs)
+        first = (convs[0].kernel_size[0], convs[0].stride[0], convs[0].padding[0], convs[0].out_channels)
+        mids = [_DiscLayer(m.in_channels, m.out_channels, m.kernel_size[0], m.stride[0], m.padding[0], 1)
+                for m in convs[1:]]
+        out, fmap = _disc_forward(_lib.lib(), x, self.period, first, mids, (self.conv_post.kernel_size[0],),
+                                  convs + [self.conv_post])
+        return out, fmap
 
 
 class MultiPeriodDiscriminator(torch.nn.Module):
@@ -530,8 +661,14 @@ class DiscriminatorS(torch.nn.Module):
         self.conv_post = norm_f(Conv1d(1024, 1, 3, 1, padding=1))
 
     def forward(self, x):
-        raise NotImplementedError("DiscriminatorS CUDA kernels (grouped/strided conv) are not built yet; "
-                                  "hifigan_b200 has no library/CPU fallback")
+        _check_disc_input(x, "DiscriminatorS.forward")
+        convs = list(self.convs)
+        first = (convs[0].kernel_size[0], convs[0].stride[0], convs[0].padding[0], convs[0].out_channels)
+        mids = [_DiscLayer(m.in_channels, m.out_channels, m.kernel_size[0], m.stride[0], m.padding[0], m.groups)
+                for m in convs[1:]]
+        out, fmap = _disc_forward(_lib.lib(), x, 1, first, mids, (self.conv_post.kernel_size[0],),
+                                  convs + [self.conv_post])
+        return out, [f.squeeze(-1) for f in fmap]   # [B,C,T,1] -> the reference's [B,C,T]
 
 
 class MultiScaleDiscriminator(torch.nn.Module):
@@ -539,11 +676,30 @@ class MultiScaleDiscriminator(torch.nn.Module):
         super().__init__()
         self.discriminators = nn.ModuleList([DiscriminatorS(use_spectral_norm=True), DiscriminatorS(),
                                              DiscriminatorS()])
+        # kept for state_dict / attribute parity; the pooling itself runs in hg_avgpool_4_2_2_fwd
         self.meanpools = nn.ModuleList([AvgPool1d(4, 2, padding=2), AvgPool1d(4, 2, padding=2)])
 
+    @staticmethod
+    def _pool(x: torch.Tensor) -> torch.Tensor:
+        b, c, t = x.shape
+        xin = x.reshape(b * c, t).contiguous().float()
+        out = torch.empty(b * c, t // 2 + 1, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().hg_avgpool_4_2_2_fwd(xin.data_ptr(), b * c, t, out.data_ptr(), _stream()),
+                   "hg_avgpool_4_2_2_fwd")
+        return out.view(b, c, -1)
+
     def forward(self, y, y_hat):
-        raise NotImplementedError("MultiScaleDiscriminator CUDA kernels are not built yet; "
-                                  "hifigan_b200 has no library/CPU fallback")
+        _check_disc_input(y, "MultiScaleDiscriminator.forward")
+        _check_disc_input(y_hat, "MultiScaleDiscriminator.forward")
+        y_d_rs, y_d_gs, fmap_rs, fmap_gs = [], [], [], []
+        for i, d in enumerate(self.discriminators):
+            if i != 0:
+                y, y_hat = self._pool(y), self._pool(y_hat)
+            y_d_r, fmap_r = d(y)
+            y_d_g, fmap_g = d(y_hat)
+            y_d_rs.append(y_d_r); fmap_rs.append(fmap_r)
+            y_d_gs.append(y_d_g); fmap_gs.append(fmap_g)
+        return y_d_rs, y_d_gs, fmap_rs, fmap_gs
 
 
 def feature_loss(fmap_r, fmap_g):

@@ -80,6 +80,25 @@ int hg_conv1d_fwd(const void* x, const void* w_packed, const float* bias, int ba
                   const void* res1, const void* res2, float scale, void* out_raw, void* out_act,
                   float act_slope, void* stream);
 
+/* hg_conv1d_general_fwd — strided and/or grouped Conv1d on the same tcgen05 kernel (the discriminator stacks:
+ * DiscriminatorS src/models.py:195-204 — k=41, stride 1/2/4, groups 4/16; DiscriminatorP :133-140 — (5,1)
+ * kernels with stride (3,1), one independent 1-D problem per period column).
+ *
+ *   out[b,t,co] = leaky_relu(bias[co] + sum_{j,ci in group(co)} x[b, stride*t + j - pad_left, ci] * w[j][co][ci])
+ *
+ * x bf16 [B][t_in_rows][c_total] with t_in_rows a multiple of `stride` and rows past the true length zero
+ * (they are the conv's zero padding); the kernel reads it through the view [B][t_in_rows/stride][stride*c_total]
+ * so that taps of equal residue mod stride are row-shifted views of one TMA box.  w_packed bf16
+ * [ktaps][cout][c_total/groups] with the taps in the order given by hg_conv1d_tap_order (identity for stride 1).
+ * Per-group widths must be multiples of 32 (cin) and one of 32/64/128/256 (cout): callers merge narrower
+ * groups into block-diagonal ones.  out_act / out_raw bf16 [B][t_out_rows][cout] (rows >= t_out are left
+ * untouched so a zero-initialised buffer keeps its zero padding), either may be NULL. */
+int hg_conv1d_tap_order(int ktaps, int stride, int pad_left, int* host_order);
+int hg_conv1d_general_fwd(const void* x, const void* w_packed, const float* bias, int batch, int t_in_rows,
+                          int c_total, int t_out, int t_out_rows, int groups, int cout, int ktaps, int stride,
+                          int pad_left,
+                          void* out_act, float act_slope, void* out_raw, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * hg_resblock_pair_fwd — one fused ResBlock1 step (src/models.py:36-41) for the narrow stages:
  *
@@ -97,6 +116,25 @@ int hg_resblock_pair_fwd(const void* x, const void* w1_packed, const float* b1, 
                          const float* b2, int batch, int t, int c, int ktaps, int dil1, float in_slope,
                          const void* res1, const void* res2, float scale, void* out_raw, void* out_act,
                          float out_slope, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Discriminator ends (bandwidth-bound CUDA-core kernels).
+ * hg_disc_first_conv_fwd: the Cin = 1 layers — DiscriminatorS convs[0] (src/models.py:196; period = 1) and
+ *   DiscriminatorP convs[0] (:134) with the right-side reflect pad and the [B,1,T] -> [B,1,H,p] view
+ *   (:146-151) folded into the addressing.  y fp32 [B][T]; w fp32 [cout][k]; out bf16
+ *   [B*period][h_rows_out][cout] = leaky_relu(conv + bias); rows >= H_out are not written.
+ * hg_disc_last_conv_fwd: the Cout = 1 layers (conv_post :141,204): x bf16 [S][h_rows][c], w fp32 [c][k],
+ *   out fp32 [S][h] (no activation).
+ * hg_avgpool_4_2_2_fwd: AvgPool1d(4,2,padding=2), zero padding counted (:227-230); out length t/2 + 1.
+ * hg_disc_export_fmap: bf16 [B*period][h_rows][c] -> the reference's fp32 [B][c][H][period]. */
+int hg_disc_first_conv_fwd(const float* y, const float* w, const float* bias, int batch, int t, int period,
+                           int k, int stride, int pad, int cout, int h_rows_out, void* out, float slope,
+                           void* stream);
+int hg_disc_last_conv_fwd(const void* x, const float* w, const float* bias, int nseq, int h, int h_rows, int c,
+                          int k, float* out, void* stream);
+int hg_avgpool_4_2_2_fwd(const float* x, int batch, int t, float* out, void* stream);
+int hg_disc_export_fmap(const void* x, int batch, int period, int h, int h_rows, int c, float* out,
+                        void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Layout edges.

@@ -215,6 +215,29 @@ def stage_pairs(b, frames, debug=0):
                 del x, o1
 
 
+def stage_disc(b, t):
+    """Timing of the discriminator forwards (both inputs), CUDA events."""
+    torch.manual_seed(1234)
+    mpd, msd = H.MultiPeriodDiscriminator().cuda().eval(), H.MultiScaleDiscriminator().cuda().eval()
+    y = O.synthetic_audio(b, t, seed=1).unsqueeze(1).cuda()
+    y_hat = O.synthetic_audio(b, t, seed=2).unsqueeze(1).cuda()
+    for name, D, macs in (("mpd", mpd, 4719952768), ("msd", msd, 3930822400)):
+        with torch.no_grad():
+            for _ in range(2):
+                D(y, y_hat)
+            torch.cuda.synchronize()
+            n0 = _lib.launch_count()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                D(y, y_hat)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        emit(stage="disc", which=name, b=b, t=t, ms=round(ms, 3), launches=(_lib.launch_count() - n0) // 5,
+             tflops=round(2 * 2 * b * macs * (t / 8192) / ms / 1e9, 1))
+
+
 if __name__ == "__main__":
     st = sys.argv[1]
     t0 = time.time()
@@ -224,6 +247,8 @@ if __name__ == "__main__":
         stage_conv(int(sys.argv[2]))
     elif st == "gen":
         stage_gen(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]))
+    elif st == "disc":
+        stage_disc(int(sys.argv[2]), int(sys.argv[3]))
     elif st == "pairs":
         stage_pairs(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]) if len(sys.argv) > 4 else 0)
     elif st == "layers":

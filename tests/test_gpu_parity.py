@@ -20,6 +20,9 @@ def H():
         pytest.skip("no GPU")
     import hifigan_b200
     hifigan_b200._lib.lib()  # the extension must load: there is no fallback
+    # torch references in this file must be true fp32 (cuDNN / cuBLAS default to TF32 on this GPU)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     return hifigan_b200
 
 
@@ -333,3 +336,141 @@ def test_segment_sampler_batch(H, O):
         assert torch.equal(audio[i].cpu(), want)
     ref = O.mel_spectrogram(audio.cpu().double(), 1024, 80, 22050, 256, 1024, 0, None)
     assert (mel_loss.cpu().double() - ref).abs().max().item() < 1e-3
+
+
+# --------------------------------------------------------------------------------------------- discriminators
+GENERAL_CASES = [
+    # b, t_in, cin, cout, k, stride, pad, groups
+    (3, 300, 32, 128, 5, 3, 2, 1),      # DiscriminatorP layer 1 shape class (KC=32, residue boxes)
+    (2, 911, 128, 512, 5, 3, 2, 1),
+    (2, 100, 512, 1024, 5, 3, 2, 1),
+    (2, 51, 1024, 1024, 5, 1, 2, 1),
+    (2, 1000, 128, 128, 41, 2, 20, 4),   # DiscriminatorS grouped / strided layers
+    (2, 600, 128, 256, 41, 2, 20, 16),   # 8-channel groups -> merged block-diagonal tiles
+    (1, 700, 256, 512, 41, 4, 20, 16),
+    (1, 515, 512, 1024, 41, 4, 20, 16),
+    (1, 130, 1024, 1024, 41, 1, 20, 16),
+]
+
+
+@pytest.mark.parametrize("case", GENERAL_CASES)
+def test_general_conv_vs_torch(H, case):
+    """hg_conv1d_general_fwd (strided through residue boxes, grouped through per-group N tiles) vs fp32
+    F.conv1d on the same bf16-rounded inputs and weights."""
+    from hifigan_b200 import _lib
+    from hifigan_b200.models import _DiscLayer, _round_up
+    L = _lib.lib()
+    b, t, cin, cout, k, s, pad, g = case
+    dev = torch.device("cuda")
+    gen = torch.Generator().manual_seed(sum(case))
+    rows = _round_up(t, s)
+    x = torch.zeros(b, rows, cin, dtype=torch.bfloat16, device=dev)
+    x[:, :t] = torch.randn(b, t, cin, generator=gen).to(dev).bfloat16()
+    w = (torch.randn(cout, cin // g, k, generator=gen) / (cin // g * k) ** 0.5).to(dev).bfloat16().float()
+    bias = torch.randn(cout, generator=gen).to(dev)
+    layer = _DiscLayer(cin, cout, k, s, pad, g)
+    wp = layer.pack(w)
+    t_out = (t + 2 * pad - k) // s + 1
+    rows_out = t_out + 5
+    out = torch.full((b, rows_out, cout), 7.0, dtype=torch.bfloat16, device=dev)
+    _lib.check(L.hg_conv1d_general_fwd(x.data_ptr(), wp.data_ptr(), bias.data_ptr(), b, rows, cin, t_out, rows_out,
+                                       layer.groups_eff, cout, k, s, pad, out.data_ptr(), 0.1, 0,
+                                       torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = F.leaky_relu(F.conv1d(x[:, :t].float().transpose(1, 2), w, bias, stride=s, padding=pad, groups=g), 0.1)
+    ref = ref.transpose(1, 2)
+    assert ref.shape[1] == t_out
+    assert bool(((out[:, :t_out].float() - ref).abs() <= 2.0 ** -8 * ref.abs() + 2e-3).all())
+    assert bool((out[:, t_out:] == 7.0).all())  # pitch rows are left untouched
+
+
+def test_disc_end_kernels_vs_torch(H):
+    from hifigan_b200 import _lib
+    L = _lib.lib()
+    dev = torch.device("cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(9)
+    for (b, t, period, k, s, pad, cout) in [(3, 8192, 1, 15, 1, 7, 128), (2, 8192, 3, 5, 3, 2, 32),
+                                             (2, 1000, 7, 5, 3, 2, 32), (2, 4097, 1, 15, 1, 7, 128)]:
+        y = torch.randn(b, t, generator=g).to(dev)
+        w = torch.randn(cout, k, generator=g).to(dev) * 0.3
+        bias = torch.randn(cout, generator=g).to(dev)
+        tp = (t + period - 1) // period * period
+        hin = tp // period
+        hout = (hin + 2 * pad - k) // s + 1
+        out = torch.zeros(b * period, hout + 2, cout, dtype=torch.bfloat16, device=dev)
+        _lib.check(L.hg_disc_first_conv_fwd(y.data_ptr(), w.data_ptr(), bias.data_ptr(), b, t, period, k, s, pad, cout,
+                                            hout + 2, out.data_ptr(), 0.1, st))
+        yp = F.pad(y.unsqueeze(1), (0, tp - t), "reflect") if tp != t else y.unsqueeze(1)
+        x4 = yp.view(b, 1, hin, period)
+        ref = F.leaky_relu(F.conv2d(x4, w.view(cout, 1, k, 1), bias, stride=(s, 1), padding=(pad, 0)), 0.1)
+        got = out[:, :hout].float().view(b, period, hout, cout).permute(0, 3, 2, 1)
+        assert (got - ref).abs().max().item() < 2.0 ** -7 * ref.abs().max().item() + 1e-3
+    # last conv
+    x = torch.randn(6, 55, 1024, generator=g).to(dev).bfloat16()
+    w = torch.randn(1024, 3, generator=g).to(dev) * 0.05
+    bias = torch.randn(1, generator=g).to(dev)
+    out = torch.empty(6, 51, dtype=torch.float32, device=dev)
+    _lib.check(L.hg_disc_last_conv_fwd(x.data_ptr(), w.data_ptr(), bias.data_ptr(), 6, 51, 55, 1024, 3, out.data_ptr(), st))
+    ref = F.conv1d(x[:, :51].float().transpose(1, 2), w.unsqueeze(0), bias, padding=1)[:, 0]
+    assert (out - ref).abs().max().item() < 2e-3
+    # avg pool incl. odd length and the 0.5-weighted edges
+    for t in (8192, 4097, 9):
+        y = torch.randn(2, t, generator=g).to(dev)
+        out = torch.empty(2, t // 2 + 1, device=dev)
+        _lib.check(L.hg_avgpool_4_2_2_fwd(y.data_ptr(), 2, t, out.data_ptr(), st))
+        assert torch.allclose(out, F.avg_pool1d(y.unsqueeze(1), 4, 2, padding=2)[:, 0], atol=1e-6)
+
+
+def _seeded_discs(H, O):
+    torch.manual_seed(1234)
+    H.Generator(H.AttrDict(O.config("v1")))
+    return H.MultiPeriodDiscriminator(), H.MultiScaleDiscriminator()
+
+
+def test_discriminators_vs_reference_golden(H, O):
+    """MPD / MSD forward on the CUDA path vs the REFERENCE's stored logits, feature-map magnitudes and losses
+    (tests/golden/disc_seed1234.npz; MSD in train mode so the spectral-norm power iterations are exercised).
+    bf16 operands: logits within 3e-2 abs, losses within 2 % rel."""
+    z = load_npz("disc_seed1234.npz")
+    mpd, msd = _seeded_discs(H, O)
+    mpd, msd = mpd.cuda().eval(), msd.cuda().train()
+    y, y_hat = torch.from_numpy(z["y"]).cuda(), torch.from_numpy(z["y_hat"]).cuda()
+    with torch.no_grad():
+        for name, D in (("mpd", mpd), ("msd", msd)):
+            rs, gs, fr, fg = D(y, y_hat)
+            for i, (r, g) in enumerate(zip(rs, gs)):
+                ref_r, ref_g = z[f"{name}_logits_r{i}"], z[f"{name}_logits_g{i}"]
+                assert tuple(r.shape) == ref_r.shape
+                assert np.abs(r.cpu().numpy() - ref_r).max() < 3e-2 * max(1.0, np.abs(ref_r).max())
+                assert np.abs(g.cpu().numpy() - ref_g).max() < 3e-2 * max(1.0, np.abs(ref_g).max())
+            mags = np.array([[float(f.abs().mean()) for f in fl] + [0.0] * (8 - len(fl)) for fl in fr])
+            assert np.allclose(mags, z[f"{name}_fmap_abs_mean_r"], rtol=2e-2, atol=1e-4)
+            fl = H.feature_loss(fr, fg).item()
+            assert abs(fl - float(z[f"{name}_feature_loss"])) < 2e-2 * abs(float(z[f"{name}_feature_loss"]))
+            dl, rl, gl = H.discriminator_loss(rs, gs)
+            assert abs(dl.item() - float(z[f"{name}_disc_loss"])) < 2e-2 * abs(float(z[f"{name}_disc_loss"]))
+            gt, _ = H.generator_loss(gs)
+            assert abs(gt.item() - float(z[f"{name}_gen_loss"])) < 2e-2 * abs(float(z[f"{name}_gen_loss"]))
+
+
+def test_discriminator_fmaps_vs_oracle(H, O):
+    """Every one of the 54 feature maps against the fp32 oracle on the same weights (odd length: reflect pad)."""
+    mpd, msd = _seeded_discs(H, O)
+    sd_p = {k: v.detach().clone() for k, v in mpd.state_dict().items()}
+    sd_s = {k: v.detach().clone() for k, v in msd.state_dict().items()}
+    y = O.synthetic_audio(2, 8000, seed=21).unsqueeze(1)
+    y_hat = O.synthetic_audio(2, 8000, seed=22).unsqueeze(1)
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        ref_p = O.mpd_forward(sd_p, y, y_hat)
+        ref_s = O.msd_forward(sd_s, y, y_hat, train=False)
+        got_p = mpd.cuda().eval()(y.cuda(), y_hat.cuda())
+        got_s = msd.cuda().eval()(y.cuda(), y_hat.cuda())
+    for ref, got in ((ref_p, got_p), (ref_s, got_s)):
+        for fl_ref, fl_got in zip(ref[2] + ref[3], got[2] + got[3]):
+            assert len(fl_ref) == len(fl_got)
+            for fr, fg in zip(fl_ref, fl_got):
+                assert fr.shape == fg.shape
+                scale = fr.abs().max().item() + 1e-6
+                assert (fg.cpu() - fr).abs().max().item() < 4e-2 * scale

@@ -97,8 +97,10 @@ def test_no_cpu_path():
         G(torch.zeros(1, 80, 8))
     with pytest.raises(RuntimeError, match="no CPU path"):
         H.mel_spectrogram(torch.zeros(1, 8192), 1024, 80, 22050, 256, 1024, 0, 8000)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="no CPU path"):
         H.MultiScaleDiscriminator()(torch.zeros(1, 1, 64), torch.zeros(1, 1, 64))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        H.MultiPeriodDiscriminator()(torch.zeros(1, 1, 64), torch.zeros(1, 1, 64))
 
 
 def test_helpers():
