@@ -552,7 +552,26 @@ class _DiscLayer:
         return w.permute(2, 0, 1).contiguous().to(torch.bfloat16)
 
 
-def _disc_forward(L, y: torch.Tensor, period: int, first, mids, last, mods):
+def _param_key(m: nn.Module):
+    ts = [getattr(m, n, None) for n in ("weight_g", "weight_v", "weight_orig", "weight", "bias")]
+    return tuple((t.data_ptr(), t._version) for t in ts if isinstance(t, torch.Tensor))
+
+
+def _disc_weights(owner: nn.Module, idx: int, m: nn.Module, build):
+    """Per-layer cache of the GEMM-ready weight: rebuilt when a parameter changed, and on every call for a
+    spectral-norm layer in train mode (its power iteration must advance call by call)."""
+    cache = owner.__dict__.setdefault("_hg_wcache", {})
+    live_sn = hasattr(m, "weight_orig") and m.training
+    key = None if live_sn else _param_key(m)
+    hit = cache.get(idx)
+    if hit is not None and key is not None and hit[0] == key:
+        return hit[1]
+    val = build()
+    cache[idx] = (key, val)
+    return val
+
+
+def _disc_forward(L, owner: nn.Module, y: torch.Tensor, period: int, first, mids, last, mods):
     """Shared body of DiscriminatorP / DiscriminatorS.  y fp32 [B,1,T] -> (logits [B, H*p], fmaps fp32 NCHW-like).
     first = (k, stride, pad, cout), mids = [_DiscLayer], last = (k,), mods = conv modules in order."""
     b, c, t = y.shape
@@ -567,35 +586,48 @@ def _disc_forward(L, y: torch.Tensor, period: int, first, mids, last, mods):
         raise RuntimeError("reflect padding needs n_pad < t (reference F.pad behaviour)")
     h = (h + 2 * p0 - k0) // s0 + 1
     nseq = b * period
-    rows = _round_up(h, mids[0].stride)
-    act = torch.zeros(nseq, rows, c0, dtype=torch.bfloat16, device=dev)
-    w0 = _effective_weight(mods[0]).reshape(c0, k0).contiguous()
-    _lib.check(L.hg_disc_first_conv_fwd(yin.data_ptr(), w0.data_ptr(), mods[0].bias.detach().float().data_ptr(), b, t,
-                                        period, k0, s0, p0, c0, rows, act.data_ptr(), LRELU_SLOPE, st),
-               "hg_disc_first_conv_fwd")
-    feats = [(act, h, rows, c0)]
+    # geometry + zero-initialised activation buffers (rows past the valid length are the next conv's zero
+    # padding and are never written), cached per input shape
+    ws_cache = owner.__dict__.setdefault("_hg_ws", {})
+    ws = ws_cache.get((b, t, dev))
+    if ws is None:
+        geo, hh = [], h
+        rows = _round_up(hh, mids[0].stride)
+        geo.append((hh, rows, c0))
+        for li, layer in enumerate(mids):
+            hh = (hh + 2 * layer.pad - layer.k) // layer.stride + 1
+            nxt = mids[li + 1].stride if li + 1 < len(mids) else 1
+            geo.append((hh, _round_up(hh, nxt), layer.cout))
+        ws = [(torch.zeros(nseq, r_, c_, dtype=torch.bfloat16, device=dev), h_, r_, c_) for h_, r_, c_ in geo]
+        if len(ws_cache) >= 4:
+            ws_cache.pop(next(iter(ws_cache)))
+        ws_cache[(b, t, dev)] = ws
+    w0, b0 = _disc_weights(owner, 0, mods[0], lambda: (_effective_weight(mods[0]).reshape(c0, k0).contiguous(),
+                                                         mods[0].bias.detach().float().contiguous()))
+    act, h, rows, _ = ws[0]
+    _lib.check(L.hg_disc_first_conv_fwd(yin.data_ptr(), w0.data_ptr(), b0.data_ptr(), b, t, period, k0, s0, p0, c0,
+                                        rows, act.data_ptr(), LRELU_SLOPE, st), "hg_disc_first_conv_fwd")
     for li, layer in enumerate(mids):
         m = mods[1 + li]
-        w = _effective_weight(m)
-        w = layer.pack(w.reshape(w.shape[0], w.shape[1], layer.k))
-        bias = m.bias.detach().float().contiguous()
-        h_out = (h + 2 * layer.pad - layer.k) // layer.stride + 1
-        nxt_stride = mids[li + 1].stride if li + 1 < len(mids) else 1
-        rows_out = _round_up(h_out, nxt_stride)
-        out = torch.zeros(nseq, rows_out, layer.cout, dtype=torch.bfloat16, device=dev)
+
+        def build(m=m, layer=layer):
+            w = _effective_weight(m)
+            return layer.pack(w.reshape(w.shape[0], w.shape[1], layer.k)), m.bias.detach().float().contiguous()
+
+        w, bias = _disc_weights(owner, 1 + li, m, build)
+        out, h_out, rows_out, _ = ws[1 + li]
         _lib.check(L.hg_conv1d_general_fwd(act.data_ptr(), w.data_ptr(), bias.data_ptr(), nseq, rows, layer.cin, h_out,
                                            rows_out, layer.groups_eff, layer.cout, layer.k, layer.stride, layer.pad,
                                            out.data_ptr(), LRELU_SLOPE, 0, st), "hg_conv1d_general_fwd")
         act, h, rows = out, h_out, rows_out
-        feats.append((act, h, rows, layer.cout))
-    mp = mods[-1]
-    kp = last[0]
-    wp = _effective_weight(mp).reshape(feats[-1][3], kp).contiguous()
+    mp, kp, c_last = mods[-1], last[0], ws[-1][3]
+    wp, bp = _disc_weights(owner, len(mods) - 1, mp, lambda: (_effective_weight(mp).reshape(c_last, kp).contiguous(),
+                                                               mp.bias.detach().float().contiguous()))
     post = torch.empty(nseq, h, dtype=torch.float32, device=dev)
-    _lib.check(L.hg_disc_last_conv_fwd(act.data_ptr(), wp.data_ptr(), mp.bias.detach().float().data_ptr(), nseq, h, rows,
-                                       feats[-1][3], kp, post.data_ptr(), st), "hg_disc_last_conv_fwd")
+    _lib.check(L.hg_disc_last_conv_fwd(act.data_ptr(), wp.data_ptr(), bp.data_ptr(), nseq, h, rows, c_last, kp,
+                                       post.data_ptr(), st), "hg_disc_last_conv_fwd")
     fmap = []
-    for a_, h_, rows_, c_ in feats:
+    for a_, h_, rows_, c_ in ws:
         f = torch.empty(b, c_, h_, period, dtype=torch.float32, device=dev)
         _lib.check(L.hg_disc_export_fmap(a_.data_ptr(), b, period, h_, rows_, c_, f.data_ptr(), st), "hg_disc_export_fmap")
         fmap.append(f)
@@ -626,9 +658,12 @@ class DiscriminatorP(torch.nn.Module):
         _check_disc_input(x, "DiscriminatorP.forward")
         convs = list(self.convs)
         first = (convs[0].kernel_size[0], convs[0].stride[0], convs[0].padding[0], convs[0].out_channels)
-        mids = [_DiscLayer(m.in_channels, m.out_channels, m.kernel_size[0], m.stride[0], m.padding[0], 1)
-                for m in convs[1:]]
-        out, fmap = _disc_forward(_lib.lib(), x, self.period, first, mids, (self.conv_post.kernel_size[0],),
+        mids = self.__dict__.get("_hg_layers")
+        if mids is None:
+            mids = [_DiscLayer(m.in_channels, m.out_channels, m.kernel_size[0], m.stride[0], m.padding[0], 1)
+                    for m in convs[1:]]
+            self.__dict__["_hg_layers"] = mids
+        out, fmap = _disc_forward(_lib.lib(), self, x, self.period, first, mids, (self.conv_post.kernel_size[0],),
                                   convs + [self.conv_post])
         return out, fmap
 
@@ -664,9 +699,12 @@ class DiscriminatorS(torch.nn.Module):
         _check_disc_input(x, "DiscriminatorS.forward")
         convs = list(self.convs)
         first = (convs[0].kernel_size[0], convs[0].stride[0], convs[0].padding[0], convs[0].out_channels)
-        mids = [_DiscLayer(m.in_channels, m.out_channels, m.kernel_size[0], m.stride[0], m.padding[0], m.groups)
-                for m in convs[1:]]
-        out, fmap = _disc_forward(_lib.lib(), x, 1, first, mids, (self.conv_post.kernel_size[0],),
+        mids = self.__dict__.get("_hg_layers")
+        if mids is None:
+            mids = [_DiscLayer(m.in_channels, m.out_channels, m.kernel_size[0], m.stride[0], m.padding[0], m.groups)
+                    for m in convs[1:]]
+            self.__dict__["_hg_layers"] = mids
+        out, fmap = _disc_forward(_lib.lib(), self, x, 1, first, mids, (self.conv_post.kernel_size[0],),
                                   convs + [self.conv_post])
         return out, [f.squeeze(-1) for f in fmap]   # [B,C,T,1] -> the reference's [B,C,T]
 
