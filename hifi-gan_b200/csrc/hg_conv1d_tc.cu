@@ -81,6 +81,35 @@ struct Barriers {
   uint32_t pad;
 };
 
+// (n tile, time tile, batch) of the CTA's current tile, advanced by gridDim.x per step with mixed-radix
+// carries instead of four integer divisions per tile (those dominated the per-tile cost of every warp role).
+struct TileIter {
+  int nt, tt, b, tile;
+  int step_n, step_t, step_b;
+  int tiles_n, tiles_t;
+  __device__ __forceinline__ TileIter(const ConvArgs& p) {
+    tiles_n = p.tiles_n; tiles_t = p.tiles_t;
+    tile = blockIdx.x;
+    nt = tile % tiles_n;
+    const int r = tile / tiles_n;
+    tt = r % tiles_t; b = r / tiles_t;
+    const int g = gridDim.x;
+    step_n = g % tiles_n;
+    const int gr = g / tiles_n;
+    step_t = gr % tiles_t; step_b = gr / tiles_t;
+  }
+  __device__ __forceinline__ void next() {
+    tile += gridDim.x;
+    nt += step_n;
+    int carry = 0;
+    if (nt >= tiles_n) { nt -= tiles_n; carry = 1; }
+    tt += step_t + carry;
+    carry = 0;
+    if (tt >= tiles_t) { tt -= tiles_t; carry = 1; }
+    b += step_b + carry;
+  }
+};
+
 // KC = channels per K chunk: 64 -> 128-byte rows / SWIZZLE_128B, 32 -> 64-byte rows / SWIZZLE_64B.
 // NT = output channels per tile (UMMA N).
 template <int KC, int NT>
@@ -139,7 +168,7 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   if (warp == 0) {
     // ============================ TMA producer ============================
     if (lane == 0) {
-      uint32_t a_it = 0, w_it = 0;
+      uint32_t a_slot = 0, a_phase = 0, w_slot = 0, w_phase = 0;   // ring positions, no divisions
       const uint32_t a_bytes = static_cast<uint32_t>(p.a_rows) * kRowBytes;
       if (p.resident) {
         // whole filter bank once: per chunk one box (KC, NT, ktaps) -> [tap][NT rows][KC] in smem
@@ -148,31 +177,31 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           hg::tma_load_3d(w_buf + static_cast<uint32_t>(c * p.ktaps) * kTapBytes, &tm_w,
                           &bars->w_full[0], c * KC, 0, 0);
       }
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int nt = tile % p.tiles_n;
-        const int rest = tile / p.tiles_n;
-        const int tt = rest % p.tiles_t;
-        const int b = rest / p.tiles_t;
-        const int t0 = tt * kTileM;
+      for (TileIter it(p); it.tile < p.num_tiles; it.next()) {
+        const int nt = it.nt, b = it.b;
+        const int t0 = it.tt * kTileM;
         const int chan0 = p.grouped ? nt * p.cin : 0;
         for (int c = 0; c < p.nchunks; ++c) {
+          int in_stage = 0;   // position of the next packed tap inside its weight stage (no modulo per tap)
           for (int bx = 0; bx < p.nboxes; ++bx) {
-            const uint32_t slot = a_it % p.a_slots;
-            hg::mbar_wait(&bars->a_empty[slot], ((a_it / p.a_slots) & 1u) ^ 1u);
+            const uint32_t slot = a_slot;
+            hg::mbar_wait(&bars->a_empty[slot], a_phase ^ 1u);
             hg::mbar_arrive_expect_tx(&bars->a_full[slot], a_bytes);
             hg::tma_load_3d(a_buf + slot * p.a_slot_bytes, &tm_x, &bars->a_full[slot],
                             p.box_col[bx] + chan0 + c * KC, t0 + p.box_row[bx], b);
-            ++a_it;
+            if (++a_slot == static_cast<uint32_t>(p.a_slots)) { a_slot = 0; a_phase ^= 1u; }
             if (!p.resident) {
               // weight stages are issued in the order the MMA warp consumes packed taps
               const int q_end = p.box_tap0[bx] + p.box_ntaps[bx];
               for (int q = p.box_tap0[bx]; q < q_end; ++q) {
-                if (q % p.tps) continue;
-                const uint32_t s = w_it % p.stages;
-                hg::mbar_wait(&bars->w_empty[s], ((w_it / p.stages) & 1u) ^ 1u);
+                const bool first_of_stage = in_stage == 0;
+                if (++in_stage == p.tps) in_stage = 0;
+                if (!first_of_stage) continue;
+                const uint32_t s = w_slot;
+                hg::mbar_wait(&bars->w_empty[s], w_phase ^ 1u);
                 hg::mbar_arrive_expect_tx(&bars->w_full[s], static_cast<uint32_t>(p.tps) * kTapBytes);
                 hg::tma_load_3d(w_buf + s * p.w_stage_bytes, &tm_w, &bars->w_full[s], c * KC, nt * NT, q);
-                ++w_it;
+                if (++w_slot == static_cast<uint32_t>(p.stages)) { w_slot = 0; w_phase ^= 1u; }
               }
             }
           }
@@ -189,7 +218,9 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const uint32_t desc_hi = hg::umma_desc_hi(kSbo, kLayout);
     const uint32_t a_tap_step = static_cast<uint32_t>(p.tap_step) * (kRowBytes >> 4);
     const uint32_t w_lo0 = hg::umma_desc_lo(hg::smem_u32(w_buf));
-    uint32_t a_it = 0, w_it = 0, acc_it = 0;
+    uint32_t acc_it = 0;
+    uint32_t a_slot = 0, a_phase = 0;
+    uint32_t w_slot = 0, w_phase = 0;   // weight-ring position, advanced without divisions
     if (p.resident) {
       hg::mbar_wait(&bars->w_full[0], 0);
       hg::tc_fence_after();
@@ -202,9 +233,11 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       const uint32_t d_tmem = tmem_base + acc * NT;
       uint32_t accumulate = 0;
       for (int c = 0; c < p.nchunks; ++c) {
+        int in_stage = 0;     // position of the current packed tap inside its weight stage
+        uint32_t w_stage_lo = 0;
         for (int bx = 0; bx < p.nboxes; ++bx) {
-          const uint32_t slot = a_it % p.a_slots;
-          hg::mbar_wait(&bars->a_full[slot], (a_it / p.a_slots) & 1u);
+          const uint32_t slot = a_slot;
+          hg::mbar_wait(&bars->a_full[slot], a_phase);
           hg::tc_fence_after();
           uint32_t a_lo = hg::umma_desc_lo(hg::smem_u32(a_buf + slot * p.a_slot_bytes));
           const int q0 = p.box_tap0[bx], q_end = q0 + p.box_ntaps[bx];
@@ -225,30 +258,34 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             accumulate = 1;
           } else {
             for (int q = q0; q < q_end; ++q) {
-              const uint32_t s = w_it % p.stages;
-              const int in_stage = q % p.tps;
               if (in_stage == 0) {
-                hg::mbar_wait(&bars->w_full[s], (w_it / p.stages) & 1u);
+                hg::mbar_wait(&bars->w_full[w_slot], w_phase);
                 hg::tc_fence_after();
+                w_stage_lo = w_lo0 + ((w_slot * p.w_stage_bytes) >> 4);
               }
               const bool stage_done = (in_stage == p.tps - 1) || (q == p.ktaps - 1);
               if (leader) {
-                const uint32_t w_lo = w_lo0 + ((s * p.w_stage_bytes) >> 4) + static_cast<uint32_t>(in_stage) * kTapLo;
 #pragma unroll
                 for (int kk = 0; kk < KC / 16; ++kk) {
-                  hg::umma_bf16_ss_lo(d_tmem, a_lo + kk * 2, w_lo + kk * 2, desc_hi, idesc, accumulate);
+                  hg::umma_bf16_ss_lo(d_tmem, a_lo + kk * 2, w_stage_lo + kk * 2, desc_hi, idesc, accumulate);
                   accumulate = 1;
                 }
-                if (stage_done) hg::umma_commit(&bars->w_empty[s]);
+                if (stage_done) hg::umma_commit(&bars->w_empty[w_slot]);
               }
               accumulate = 1;
               a_lo += a_tap_step;
-              if (stage_done) ++w_it;
+              w_stage_lo += kTapLo;
+              if (stage_done) {
+                in_stage = 0;
+                if (++w_slot == static_cast<uint32_t>(p.stages)) { w_slot = 0; w_phase ^= 1u; }
+              } else {
+                ++in_stage;
+              }
             }
           }
           if (leader) hg::umma_commit(&bars->a_empty[slot]);
           __syncwarp();
-          ++a_it;
+          if (++a_slot == static_cast<uint32_t>(p.a_slots)) { a_slot = 0; a_phase ^= 1u; }
         }
       }
       if (leader) hg::umma_commit(&bars->acc_full[acc]);
@@ -263,12 +300,9 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const int row = quarter * 32 + lane;
     const int col0 = half * kColsPerWarp;  // first column (within the tile) owned by this warp
     uint32_t acc_it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int nt = tile % p.tiles_n;
-      const int rest = tile / p.tiles_n;
-      const int tt = rest % p.tiles_t;
-      const int b = rest / p.tiles_t;
-      const int t = tt * kTileM + row;
+    for (TileIter it(p); it.tile < p.num_tiles; it.next()) {
+      const int nt = it.nt, b = it.b;
+      const int t = it.tt * kTileM + row;
       const bool valid = t < p.t;
       const int ch0 = nt * NT + col0;
       const size_t off = (static_cast<size_t>(b) * p.t_pitch + (valid ? t : 0)) * p.cout + ch0;

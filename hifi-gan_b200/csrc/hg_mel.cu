@@ -200,9 +200,11 @@ __global__ void __launch_bounds__(kMelThreads) mel_kernel(const MelArgs a) {
       vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
       vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
     }
+    // almost every warp loses against the running extrema: peek first (a stale read only costs one
+    // redundant atomic), otherwise 2 x 8 same-address atomics per block serialise in L2
     if ((tid & 31) == 0) {
-      atomic_min_f32(a.minmax, vmin);
-      atomic_max_f32(a.minmax + 1, vmax);
+      if (vmin < *reinterpret_cast<volatile float*>(a.minmax)) atomic_min_f32(a.minmax, vmin);
+      if (vmax > *reinterpret_cast<volatile float*>(a.minmax + 1)) atomic_max_f32(a.minmax + 1, vmax);
     }
   }
   __syncthreads();

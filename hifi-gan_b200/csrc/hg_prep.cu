@@ -160,7 +160,28 @@ conv_post_tanh_kernel(const __nv_bfloat16* __restrict__ x, const float* __restri
   y[static_cast<size_t>(b) * t + tt] = tanhf(acc);
 }
 
+// out[b][i] = i < valid[b] ? pool[start[b] + i] : 0   (MelDataset crop / right zero-pad, meldataset.py:141-150)
+__global__ void segment_gather_kernel(const float* __restrict__ pool, const long long* __restrict__ start,
+                                      const int* __restrict__ valid, int seg, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const long long s0 = start[b];
+  const int nv = valid[b];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < seg; i += gridDim.x * blockDim.x)
+    out[static_cast<size_t>(b) * seg + i] = i < nv ? pool[s0 + i] : 0.f;
+}
+
 }  // namespace
+
+extern "C" int hg_segment_gather(const float* pool, const long long* start, const int* valid, int batch,
+                                 int seg, float* out, void* stream) {
+  HG_REQUIRE(pool && start && valid && out && batch > 0 && batch <= 65535 && seg > 0,
+             "hg_segment_gather: bad arguments");
+  dim3 grid((seg + 1023) / 1024 < 64 ? (seg + 1023) / 1024 : 64, batch);
+  segment_gather_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(pool, start, valid, seg, out);
+  HG_CHECK_CUDA(cudaGetLastError());
+  g_hg_launches.fetch_add(1, std::memory_order_relaxed);
+  return HG_OK;
+}
 
 extern "C" int hg_pack_conv1d_weight(const float* v, const float* g, int cout, int cin, int k,
                                      int cin_pad, void* w_packed, void* stream) {

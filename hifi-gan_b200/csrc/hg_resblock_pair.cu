@@ -41,9 +41,11 @@ constexpr int kMaxXSlots = 4;
 struct PairArgs {
   int batch, t, c;
   int ktaps, dil1;
-  int r_out;            // output rows per tile = 129 - k
+  int subs;             // 128-row sub-tiles per pipeline item (1, 2 or 4): one barrier hand-off covers all
+  int r_out;            // output rows per item = subs*128 - (k-1)
   int pad1, pad2;       // (k-1)*d1/2, (k-1)/2
-  int a_rows;           // 128 + (k-1)*d1
+  int a_rows;           // rows of x an item needs: subs*128 + (k-1)*d1
+  int x_boxes, x_box_rows;  // the item's x rows arrive as x_boxes TMA boxes of x_box_rows (<= 256) rows
   int tiles_t, num_tiles;
   int x_slots;
   uint32_t x_slot_bytes, t1_slot_bytes, w_bytes;  // w_bytes: one filter bank
@@ -63,7 +65,8 @@ struct PairBarriers {
   uint64_t acc1_full[2], acc1_empty[2], t1_full[2], t1_empty[2], acc2_full[2], acc2_empty[2];
   uint32_t tmem_base;
   uint32_t pad;
-  float b1[64], b2[64];   // biases, read back as shared-memory broadcasts by the epilogue warps
+  __align__(16) float b1[64];
+  __align__(16) float b2[64];   // biases, read back as shared-memory broadcasts by the epilogue warps
 };
 
 __device__ __forceinline__ uint32_t lrelu_bf16x2(uint32_t w, __nv_bfloat162 slope2) {
@@ -81,7 +84,6 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   constexpr uint32_t kLayout = (C == 64) ? 2u : 4u;
   constexpr uint32_t kSbo = 8 * kRowBytes;
   constexpr uint32_t kTapBytes = C * kRowBytes;
-  constexpr uint32_t kTmemCols = 4 * C <= 128 ? 128u : 256u;   // acc1[2] + acc2[2]
   constexpr int kChunksPerRow = kRowBytes / 16;
   constexpr int kHalves = epi_halves(C);
   constexpr int kRoleWarps = 4 * kHalves;      // warps per epilogue role
@@ -98,6 +100,9 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int S = p.subs;
+  const uint32_t acc_cols = static_cast<uint32_t>(S) * C;          // one accumulator set (all sub-tiles)
+  const uint32_t tmem_cols = 4 * acc_cols <= 128 ? 128u : 4 * acc_cols <= 256 ? 256u : 512u;  // acc1[2] + acc2[2]
 
   if (warp == 0 && lane == 0) {
     hg::tma_prefetch_desc(&tm_x);
@@ -123,7 +128,7 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       hg::fence_mbar_init();
     }
     __syncwarp();
-    hg::tmem_alloc(&bars->tmem_base, kTmemCols);
+    hg::tmem_alloc(&bars->tmem_base, tmem_cols);
   }
   if (threadIdx.x < C) {
     bars->b1[threadIdx.x] = p.b1[threadIdx.x];
@@ -147,15 +152,19 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       hg::mbar_arrive_expect_tx(&bars->w_full, 2 * p.w_bytes);
       hg::tma_load_3d(w1_buf, &tm_w1, &bars->w_full, 0, 0, 0);
       hg::tma_load_3d(w2_buf, &tm_w2, &bars->w_full, 0, 0, 0);
-      const uint32_t x_bytes = static_cast<uint32_t>(p.a_rows) * kRowBytes;
+      const uint32_t box_bytes = static_cast<uint32_t>(p.x_box_rows) * kRowBytes;
+      int tt = blockIdx.x % p.tiles_t, b = blockIdx.x / p.tiles_t;
+      const int tt_step = gridDim.x % p.tiles_t, b_step = gridDim.x / p.tiles_t;
+      uint32_t slot = 0, phase = 0;
       for (int i = 0; i < n_local; ++i) {
-        const int tile = blockIdx.x + i * gridDim.x;
-        const int tt = tile % p.tiles_t, b = tile / p.tiles_t;
-        const uint32_t slot = i % p.x_slots;
-        hg::mbar_wait(&bars->x_empty[slot], ((i / p.x_slots) & 1u) ^ 1u);
-        hg::mbar_arrive_expect_tx(&bars->x_full[slot], x_bytes);
-        hg::tma_load_3d(x_buf + slot * p.x_slot_bytes, &tm_x, &bars->x_full[slot], 0,
-                        tt * p.r_out - p.pad2 - p.pad1, b);
+        hg::mbar_wait(&bars->x_empty[slot], phase ^ 1u);
+        hg::mbar_arrive_expect_tx(&bars->x_full[slot], box_bytes * p.x_boxes);
+        for (int bx = 0; bx < p.x_boxes; ++bx)
+          hg::tma_load_3d(x_buf + slot * p.x_slot_bytes + bx * box_bytes, &tm_x, &bars->x_full[slot], 0,
+                          tt * p.r_out - p.pad2 - p.pad1 + bx * p.x_box_rows, b);
+        if (++slot == static_cast<uint32_t>(p.x_slots)) { slot = 0; phase ^= 1u; }
+        tt += tt_step; b += b_step;
+        if (tt >= p.tiles_t) { tt -= p.tiles_t; ++b; }
       }
     }
     __syncwarp();
@@ -182,14 +191,17 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         w_lo += kTapLo;
       }
     };
+    uint32_t x_slot = 0, x_phase = 0;   // conv1 visits items in order: ring position without divisions
     auto conv1 = [&](int i) {
-      const uint32_t slot = i % p.x_slots, a = i & 1u, ph = (i >> 1) & 1u;
-      hg::mbar_wait(&bars->x_ready[slot], (i / p.x_slots) & 1u);
+      const uint32_t slot = x_slot, a = i & 1u, ph = (i >> 1) & 1u;
+      hg::mbar_wait(&bars->x_ready[slot], x_phase);
+      if (++x_slot == static_cast<uint32_t>(p.x_slots)) { x_slot = 0; x_phase ^= 1u; }
       hg::mbar_wait(&bars->acc1_empty[a], ph ^ 1u);
       hg::tc_fence_after();
       if (hg::elect_one()) {
-        issue(tmem_base + a * C, hg::umma_desc_lo(hg::smem_u32(x_buf + slot * p.x_slot_bytes)), w1_lo,
-              x_tap_step);
+        const uint32_t x_lo = hg::umma_desc_lo(hg::smem_u32(x_buf + slot * p.x_slot_bytes));
+        for (int m = 0; m < S; ++m)
+          issue(tmem_base + a * acc_cols + m * C, x_lo + m * (kM * (kRowBytes >> 4)), w1_lo, x_tap_step);
         hg::umma_commit(&bars->x_empty[slot]);
         hg::umma_commit(&bars->acc1_full[a]);
       }
@@ -201,8 +213,10 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       hg::mbar_wait(&bars->acc2_empty[a], ph ^ 1u);
       hg::tc_fence_after();
       if (hg::elect_one()) {
-        issue(tmem_base + 2 * C + a * C, hg::umma_desc_lo(hg::smem_u32(t1_buf + a * p.t1_slot_bytes)), w2_lo,
-              kRowBytes >> 4);
+        const uint32_t t_lo = hg::umma_desc_lo(hg::smem_u32(t1_buf + a * p.t1_slot_bytes));
+        for (int m = 0; m < S; ++m)
+          issue(tmem_base + 2 * acc_cols + a * acc_cols + m * C, t_lo + m * (kM * (kRowBytes >> 4)), w2_lo,
+                kRowBytes >> 4);
         hg::umma_commit(&bars->t1_empty[a]);
         hg::umma_commit(&bars->acc2_full[a]);
       }
@@ -218,9 +232,9 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     const int tid = (warp - 2) * 32 + lane;
     const __nv_bfloat162 slope2 = __float2bfloat162_rn(p.in_slope);
     const int n_chunks = p.a_rows * kChunksPerRow;
+    uint32_t slot = 0, phase = 0;
     for (int i = 0; i < n_local; ++i) {
-      const uint32_t slot = i % p.x_slots;
-      hg::mbar_wait(&bars->x_full[slot], (i / p.x_slots) & 1u);
+      hg::mbar_wait(&bars->x_full[slot], phase);
       uint4* xs = reinterpret_cast<uint4*>(x_buf + slot * p.x_slot_bytes);
       for (int q = tid; q < n_chunks; q += kXformWarps * 32) {
         uint4 v = xs[q];
@@ -231,6 +245,7 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       hg::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) hg::mbar_arrive(&bars->x_ready[slot]);
+      if (++slot == static_cast<uint32_t>(p.x_slots)) { slot = 0; phase ^= 1u; }
     }
   } else {
     // ============================ epilogue ================================
@@ -250,82 +265,104 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       // ---- E1: t1 = leaky_relu(acc1 + b1), zero outside [0,T)  ->  swizzled K-major smem tile
       const float* bias = bars->b1;
       const uint32_t swz = (C == 64) ? (row & 7) : ((row >> 1) & 3);
+      int tt = blockIdx.x % p.tiles_t;   // time-tile index of the current item, advanced without divisions
+      const int tt_step = gridDim.x % p.tiles_t;
       for (int i = 0; i < n_local; ++i) {
-        const int tile = blockIdx.x + i * gridDim.x;
-        const int tt = tile % p.tiles_t;
         const uint32_t a = i & 1u, ph = (i >> 1) & 1u;
-        const int time = tt * p.r_out - p.pad2 + row;      // time step of t1 row `row`
-        const bool inside = time >= 0 && time < p.t;
         hg::mbar_wait(&bars->acc1_full[a], ph);
         hg::mbar_wait(&bars->t1_empty[a], ph ^ 1u);
         hg::tc_fence_after();
-        uint8_t* trow = t1_buf + a * p.t1_slot_bytes + static_cast<uint32_t>(row) * kRowBytes;
+        for (int m = 0; m < S; ++m) {
+          const int grow = m * kM + row;                       // row of the item's t1 tile
+          const int time = tt * p.r_out - p.pad2 + grow;       // its time step
+          const bool inside = time >= 0 && time < p.t;
+          uint8_t* trow = t1_buf + a * p.t1_slot_bytes + static_cast<uint32_t>(grow) * kRowBytes;
 #pragma unroll
-        for (int g = 0; g < kG; ++g) {
-          uint32_t raw[16];
-          hg::tmem_ld_32x16(tmem_base + lane_base + a * C + col0 + g * 16, raw);
-          hg::tmem_ld_wait();
-          if (g == kG - 1) {   // accumulator fully read: hand it back before the stores
-            hg::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) hg::mbar_arrive(&bars->acc1_empty[a]);
-          }
-          uint32_t o[8];
+          for (int g = 0; g < kG; ++g) {
+            uint32_t raw[16];
+            hg::tmem_ld_32x16(tmem_base + lane_base + a * acc_cols + m * C + col0 + g * 16, raw);
+            hg::tmem_ld_wait();
+            if (g == kG - 1 && m == S - 1) {   // accumulators fully read: hand them back before the stores
+              hg::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) hg::mbar_arrive(&bars->acc1_empty[a]);
+            }
+            uint32_t o[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float v0 = hg::lrelu(__uint_as_float(raw[2 * q]) + bias[col0 + g * 16 + 2 * q], p.in_slope);
-            const float v1 = hg::lrelu(__uint_as_float(raw[2 * q + 1]) + bias[col0 + g * 16 + 2 * q + 1], p.in_slope);
-            o[q] = inside ? hg::pack_bf16x2(v0, v1) : 0u;
+            for (int q = 0; q < 4; ++q) {
+              const float4 bq = *reinterpret_cast<const float4*>(bias + col0 + g * 16 + 4 * q);
+              const float v0 = hg::lrelu(__uint_as_float(raw[4 * q]) + bq.x, p.in_slope);
+              const float v1 = hg::lrelu(__uint_as_float(raw[4 * q + 1]) + bq.y, p.in_slope);
+              const float v2 = hg::lrelu(__uint_as_float(raw[4 * q + 2]) + bq.z, p.in_slope);
+              const float v3 = hg::lrelu(__uint_as_float(raw[4 * q + 3]) + bq.w, p.in_slope);
+              o[2 * q] = inside ? hg::pack_bf16x2(v0, v1) : 0u;
+              o[2 * q + 1] = inside ? hg::pack_bf16x2(v2, v3) : 0u;
+            }
+            const uint32_t chunk = (col0 >> 3) + g * 2;  // 16-byte chunk index within the row
+            *reinterpret_cast<uint4*>(trow + ((chunk ^ swz) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(trow + (((chunk + 1) ^ swz) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
           }
-          const uint32_t chunk = (col0 >> 3) + g * 2;  // 16-byte chunk index within the row
-          *reinterpret_cast<uint4*>(trow + ((chunk ^ swz) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-          *reinterpret_cast<uint4*>(trow + (((chunk + 1) ^ swz) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
         }
         hg::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) hg::mbar_arrive(&bars->t1_full[a]);
+        tt += tt_step;
+        if (tt >= p.tiles_t) tt -= p.tiles_t;
       }
     } else {
       // ---- E2: y = (acc2 + b2 + x + res1 + res2) * scale  ->  global
       const float* bias = bars->b2;
-      auto tile_off = [&](int i, bool& valid) -> size_t {
-        const int tile = blockIdx.x + i * gridDim.x;
-        const int tt = tile % p.tiles_t, b = tile / p.tiles_t;
-        const int time = tt * p.r_out + row;
-        valid = row < p.r_out && time < p.t;
-        return (static_cast<size_t>(b) * p.t + (valid ? time : 0)) * C + col0;
+      // unit = (item, sub-tile m); residual rows are fetched one unit ahead so their (L2) latency hides.
+      // The (time tile, batch, sub-tile) of the NEXT unit is advanced incrementally: integer divisions per unit
+      // were the single largest cost of this warp role (clock64 traces).
+      int n_tt = blockIdx.x % p.tiles_t, n_b = blockIdx.x / p.tiles_t, n_m = 0;
+      const int tt_step = gridDim.x % p.tiles_t, b_step = gridDim.x / p.tiles_t;
+      auto next_unit_off = [&](bool& valid) -> size_t {
+        const int grow = n_m * kM + row;
+        const int time = n_tt * p.r_out + grow;
+        valid = grow < p.r_out && time < p.t;
+        const size_t o = (static_cast<size_t>(n_b) * p.t + (valid ? time : 0)) * C + col0;
+        if (++n_m == S) {
+          n_m = 0;
+          n_tt += tt_step; n_b += b_step;
+          if (n_tt >= p.tiles_t) { n_tt -= p.tiles_t; ++n_b; }
+        }
+        return o;
       };
-      // residual rows are fetched one tile ahead so their (L2) latency hides under the previous tile
       hg::U8 rcur[kG], rnext[kG];
       bool valid = false, valid_next = false;
       size_t off = 0, off_next = 0;
-      if (n_local > 0) {
-        off_next = tile_off(0, valid_next);
+      const int n_units = n_local * S;
+      if (n_units > 0) {
+        off_next = next_unit_off(valid_next);
         if (valid_next) {
 #pragma unroll
           for (int g = 0; g < kG; ++g) rnext[g] = hg::ldg256(p.x + off_next + g * 16);
         }
       }
-      for (int i = 0; i < n_local; ++i) {
+      int i = 0, m = 0;
+      for (int u = 0; u < n_units; ++u) {
         const uint32_t a = i & 1u, ph = (i >> 1) & 1u;
         off = off_next; valid = valid_next;
 #pragma unroll
         for (int g = 0; g < kG; ++g) rcur[g] = rnext[g];
-        if (i + 1 < n_local) {
-          off_next = tile_off(i + 1, valid_next);
+        if (u + 1 < n_units) {
+          off_next = next_unit_off(valid_next);
           if (valid_next) {
 #pragma unroll
             for (int g = 0; g < kG; ++g) rnext[g] = hg::ldg256(p.x + off_next + g * 16);
           }
         }
-        hg::mbar_wait(&bars->acc2_full[a], ph);
-        hg::tc_fence_after();
+        if (m == 0) {
+          hg::mbar_wait(&bars->acc2_full[a], ph);
+          hg::tc_fence_after();
+        }
 #pragma unroll
         for (int g = 0; g < kG; ++g) {
           uint32_t raw[16];
-          hg::tmem_ld_32x16(tmem_base + lane_base + 2 * C + a * C + col0 + g * 16, raw);
+          hg::tmem_ld_32x16(tmem_base + lane_base + 2 * acc_cols + a * acc_cols + m * C + col0 + g * 16, raw);
           hg::tmem_ld_wait();
-          if (g == kG - 1) {
+          if (g == kG - 1 && m == S - 1) {
             hg::tc_fence_before();
             __syncwarp();
             if (lane == 0) hg::mbar_arrive(&bars->acc2_empty[a]);
@@ -333,7 +370,13 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
           if (valid) {
             float v[16];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(raw[e]) + bias[col0 + g * 16 + e];
+            for (int q = 0; q < 4; ++q) {
+              const float4 bq = *reinterpret_cast<const float4*>(bias + col0 + g * 16 + 4 * q);
+              v[4 * q] = __uint_as_float(raw[4 * q]) + bq.x;
+              v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + bq.y;
+              v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + bq.z;
+              v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + bq.w;
+            }
             hg::add_bf16x16(v, rcur[g]);
             if (p.res1) hg::add_bf16x16(v, hg::ldg256(p.res1 + off + g * 16));
             if (p.res2) hg::add_bf16x16(v, hg::ldg256(p.res2 + off + g * 16));
@@ -354,6 +397,7 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             }
           }
         }
+        if (++m == S) { m = 0; ++i; }
       }
     }
   }
@@ -361,7 +405,7 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   hg::tc_fence_before();
   __syncthreads();
   hg::tc_fence_after();
-  if (warp == 1) hg::tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == 1) hg::tmem_dealloc(tmem_base, tmem_cols);
 }
 
 int g_sms = 0, g_smem = 0;
@@ -380,17 +424,28 @@ int launch_pair(const CUtensorMap& tx, const CUtensorMap& tw1, const CUtensorMap
   return HG_OK;
 }
 
-size_t pair_smem_bytes(int c, int ktaps, int dil1, int x_slots, PairArgs* out) {
+size_t pair_smem_bytes(int c, int ktaps, int dil1, int subs, int x_slots, PairArgs* out) {
   const uint32_t row = static_cast<uint32_t>(c) * 2;
-  const uint32_t a_rows = kM + (ktaps - 1) * dil1;
-  const uint32_t x_slot = (a_rows * row + 1023u) & ~1023u;
-  const uint32_t t1_slot = ((kM + ktaps - 1) * row + 1023u) & ~1023u;
+  const uint32_t a_rows = subs * kM + (ktaps - 1) * dil1;
+  const uint32_t boxes = (a_rows + 255) / 256;
+  const uint32_t box_rows = ((a_rows + boxes - 1) / boxes + 15) & ~15u;   // 16-row multiples keep every box
+  const uint32_t x_slot = (boxes * box_rows * row + 1023u) & ~1023u;      // 1024-byte aligned in smem
+  const uint32_t t1_slot = ((subs * kM + ktaps - 1) * row + 1023u) & ~1023u;
   const uint32_t w_bytes = static_cast<uint32_t>(ktaps) * c * row;
+  if (box_rows > 256) return ~static_cast<size_t>(0);
   if (out) {
-    out->a_rows = a_rows; out->x_slot_bytes = x_slot; out->t1_slot_bytes = t1_slot; out->w_bytes = w_bytes;
+    out->subs = subs; out->a_rows = a_rows; out->x_boxes = boxes; out->x_box_rows = box_rows;
+    out->x_slot_bytes = x_slot; out->t1_slot_bytes = t1_slot; out->w_bytes = w_bytes;
   }
   return 1024 + static_cast<size_t>(x_slots) * x_slot + 2 * static_cast<size_t>(t1_slot) +
          2 * static_cast<size_t>(w_bytes) + sizeof(PairBarriers);
+}
+
+// Largest sub-tile count whose TMEM (4*subs*C columns <= 512) and shared memory (>= 2 x slots) fit.
+int pick_subs(int c, int ktaps, int dil1) {
+  for (int subs = 512 / (4 * c); subs >= 1; subs >>= 1)
+    if (pair_smem_bytes(c, ktaps, dil1, subs, 2, nullptr) <= static_cast<size_t>(g_smem)) return subs;
+  return 0;
 }
 
 }  // namespace
@@ -404,7 +459,7 @@ extern "C" int hg_resblock_pair_supported(int c, int ktaps, int dil1) {
     cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&g_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   }
-  return pair_smem_bytes(c, ktaps, dil1, 2, nullptr) <= static_cast<size_t>(g_smem) ? 1 : 0;
+  return pick_subs(c, ktaps, dil1) > 0 ? 1 : 0;
 }
 
 extern "C" int hg_resblock_pair_fwd(const void* x, const void* w1_packed, const float* b1,
@@ -419,15 +474,16 @@ extern "C" int hg_resblock_pair_fwd(const void* x, const void* w1_packed, const 
              "hg_resblock_pair_fwd: unsupported shape c=%d k=%d d=%d (use hg_conv1d_fwd)", c, ktaps, dil1);
   PairArgs p{};
   p.batch = batch; p.t = t; p.c = c; p.ktaps = ktaps; p.dil1 = dil1;
-  p.r_out = kM + 1 - ktaps;
+  const int subs = pick_subs(c, ktaps, dil1);
+  p.r_out = subs * kM + 1 - ktaps;
   p.pad1 = (ktaps - 1) * dil1 / 2;
   p.pad2 = (ktaps - 1) / 2;
   p.tiles_t = (t + p.r_out - 1) / p.r_out;
   p.num_tiles = batch * p.tiles_t;
   int slots = kMaxXSlots;
-  while (slots > 2 && pair_smem_bytes(c, ktaps, dil1, slots, nullptr) > static_cast<size_t>(g_smem)) --slots;
+  while (slots > 2 && pair_smem_bytes(c, ktaps, dil1, subs, slots, nullptr) > static_cast<size_t>(g_smem)) --slots;
   p.x_slots = slots;
-  const size_t smem_bytes = pair_smem_bytes(c, ktaps, dil1, slots, &p);
+  const size_t smem_bytes = pair_smem_bytes(c, ktaps, dil1, subs, slots, &p);
   p.x = static_cast<const __nv_bfloat16*>(x);
   p.b1 = b1; p.b2 = b2;
   p.res1 = static_cast<const __nv_bfloat16*>(res1);
@@ -439,7 +495,7 @@ extern "C" int hg_resblock_pair_fwd(const void* x, const void* w1_packed, const 
   CUtensorMap tx, tw1, tw2;
   const int swz = c * 2;
   int rc = hg_encode_tmap_bf16_3d(&tx, x, c, t, batch, static_cast<uint64_t>(c) * 2,
-                                  static_cast<uint64_t>(t) * c * 2, c, p.a_rows, 1, swz);
+                                  static_cast<uint64_t>(t) * c * 2, c, p.x_box_rows, 1, swz);
   if (rc) return rc;
   rc = hg_encode_tmap_bf16_3d(&tw1, w1_packed, c, c, ktaps, static_cast<uint64_t>(c) * 2,
                               static_cast<uint64_t>(c) * c * 2, c, c, ktaps, swz);

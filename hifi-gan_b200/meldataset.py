@@ -32,6 +32,12 @@ class _MelPlan:
         self.device = device
         self.num_mels = num_mels
         self.handle = c_void_p()
+        # ring of (device min/max, pinned host copy) pairs for the lazy range check: allocating pinned memory per
+        # call costs more than the kernel for small inputs
+        self._ring = [(torch.empty(2, dtype=torch.float32, device=device),
+                       torch.empty(2, dtype=torch.float32).pin_memory()) for _ in range(8)]
+        self._ring_pos = 0
+        self._init = torch.tensor([float("inf"), float("-inf")], dtype=torch.float32, device=device)
         with torch.cuda.device(device):
             _lib.check(_lib.lib().hg_mel_plan_create(byref(self.handle), n_fft, num_mels, sampling_rate,
                                                      hop_size, win_size, float(fmin),
@@ -41,6 +47,12 @@ class _MelPlan:
 
     def frames(self, t: int) -> int:
         return _lib.lib().hg_mel_num_frames(self.handle, t)
+
+    def next_minmax(self):
+        dev, host = self._ring[self._ring_pos]
+        self._ring_pos = (self._ring_pos + 1) % len(self._ring)
+        dev.copy_(self._init)
+        return dev, host
 
     def __del__(self):
         try:
@@ -90,11 +102,12 @@ def mel_spectrogram(y, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin,
     b, t = y2.shape
     frames = plan.frames(t)
     out = torch.empty(b, num_mels, frames, dtype=torch.float32, device=y.device)
-    minmax = torch.tensor([float("inf"), float("-inf")], dtype=torch.float32, device=y.device)
+    if len(_pending_range_checks) >= 6:   # never let a ring slot be reused while its check is pending
+        flush_range_warnings(block=True)
+    minmax, host = plan.next_minmax()
     stream = torch.cuda.current_stream()
     _lib.check(_lib.lib().hg_mel_fwd(plan.handle, y2.data_ptr(), b, t, out.data_ptr(), minmax.data_ptr(),
                                      stream.cuda_stream), "hg_mel_fwd")
-    host = torch.empty(2, dtype=torch.float32, pin_memory=True)
     host.copy_(minmax, non_blocking=True)
     ev = torch.cuda.Event()
     ev.record(stream)
@@ -162,11 +175,12 @@ class SegmentSampler:
     def batch(self, indices):
         picks = self.draw(indices)
         seg = self.segment_length
-        starts = torch.tensor([p[0] for p in picks], device=self.device).unsqueeze(1)
-        valid = torch.tensor([p[1] for p in picks], device=self.device).unsqueeze(1)
-        ar = torch.arange(seg, device=self.device).unsqueeze(0)
-        idx = (starts + ar).clamp_(max=self.pool.numel() - 1)
-        audio = torch.where(ar < valid, self.pool[idx], torch.zeros((), device=self.device))
+        starts = torch.tensor([p[0] for p in picks], dtype=torch.int64).to(self.device, non_blocking=True)
+        valid = torch.tensor([p[1] for p in picks], dtype=torch.int32).to(self.device, non_blocking=True)
+        audio = torch.empty(len(picks), seg, dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib().hg_segment_gather(self.pool.data_ptr(), starts.data_ptr(), valid.data_ptr(), len(picks),
+                                                seg, audio.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                   "hg_segment_gather")
         mel = mel_spectrogram(audio, *self.mel_args, self.fmax, center=False)
         mel_loss = mel_spectrogram(audio, *self.mel_args, self.fmax_loss, center=False)
         return mel, audio, mel_loss

@@ -147,6 +147,12 @@ int hg_ncl_to_nlc(const float* x, int batch, int c, int t, int c_pad, void* out,
                   float act_slope, void* stream);
 int hg_nlc_to_ncl(const void* x, int batch, int t, int c, float* out, void* stream);
 
+/* hg_segment_gather — batched form of MelDataset.__getitem__'s crop / right zero-pad (src/meldataset.py:141-150):
+ * out[b][i] = i < valid[b] ? pool[start[b] + i] : 0.  pool fp32 (all utterances concatenated, resident in HBM),
+ * start int64 [B] (utterance offset + the drawn audio_start), valid int32 [B] (min(len, seg)), out fp32 [B][seg]. */
+int hg_segment_gather(const float* pool, const long long* start, const int* valid, int batch, int seg,
+                      float* out, void* stream);
+
 /* hg_conv_post_tanh_fwd — conv_post + tanh (src/models.py:113-114).  x bf16 [B][T][C] already
  * holds leaky_relu(., 0.01) (models.py:112, fused into the producer's epilogue).  w fp32 [C][k]
  * (folded weight of the single output channel), y fp32 [B][T] == the reference's [B,1,T].

@@ -215,6 +215,41 @@ def stage_pairs(b, frames, debug=0):
                 del x, o1
 
 
+def stage_melperf():
+    """cfg5 sweep: fused mel kernel throughput vs the 1344 B/frame HBM roofline, and vs torchaudio on the GPU."""
+    import torchaudio
+    ref = torchaudio.transforms.MelSpectrogram(sample_rate=22050, n_fft=1024, win_length=1024, hop_length=256,
+                                               f_min=0, f_max=8000, n_mels=80, center=False).cuda()
+    for t in (8192, 262144):
+        for b in (1, 4, 16, 64, 256):
+            if b * t > 256 * 262144 // 4:
+                continue
+            y = (torch.rand(b, t, device="cuda") * 1.9 - 0.95)
+            def ours():
+                return H.mel_spectrogram(y, 1024, 80, 22050, 256, 1024, 0, 8000)
+            def theirs():
+                yp = F.pad(y.unsqueeze(1), (384, 384), mode="reflect").squeeze(1)
+                return torch.log(torch.clamp(ref(yp), min=1e-5))
+            res = {}
+            for name, fn in (("ours", ours), ("torchaudio", theirs)):
+                for _ in range(3):
+                    out = fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n = 20
+                e0.record()
+                for _ in range(n):
+                    out = fn()
+                e1.record()
+                torch.cuda.synchronize()
+                res[name] = e0.elapsed_time(e1) / n
+            frames = out.shape[0] * out.shape[2]
+            emit(stage="melperf", b=b, t=t, frames=frames, ms=round(res["ours"], 4),
+                 frames_per_s=round(frames / res["ours"] * 1e3), gbs=round(frames * 1344 / res["ours"] / 1e6, 1),
+                 torchaudio_ms=round(res["torchaudio"], 4))
+    H.meldataset.flush_range_warnings()
+
+
 def stage_disc(b, t):
     """Timing of the discriminator forwards (both inputs), CUDA events."""
     torch.manual_seed(1234)
@@ -247,6 +282,8 @@ if __name__ == "__main__":
         stage_conv(int(sys.argv[2]))
     elif st == "gen":
         stage_gen(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]))
+    elif st == "melperf":
+        stage_melperf()
     elif st == "disc":
         stage_disc(int(sys.argv[2]), int(sys.argv[3]))
     elif st == "pairs":
