@@ -18,6 +18,7 @@ There is no CPU path and no fallback: CPU tensors raise.
 """
 from __future__ import annotations
 
+import os
 import warnings
 from ctypes import byref, c_int
 from typing import Dict, List, Optional, Tuple
@@ -309,6 +310,7 @@ class _GeneratorEngine:
         self.post_b = torch.zeros(1, dtype=torch.float32, device=device)
         self.post_key = None
         self.ws: Dict[Tuple[int, int], Dict[str, torch.Tensor]] = {}
+        self.graphs: Dict[tuple, tuple] = {}
 
     def refresh(self) -> None:
         self.pre.refresh()
@@ -349,22 +351,56 @@ class _GeneratorEngine:
         for n in names:
             ws[n] = bf(biggest)
         ws["y"] = torch.empty(batch, 1, t, dtype=torch.float32, device=dev)
-        if len(self.ws) >= 4:  # bound the cache: workspaces for config 2 are ~10 GB
-            self.ws.pop(next(iter(self.ws)))
+        if len(self.ws) >= 8:  # bound the cache: workspaces for config 2 are ~10 GB
+            old = next(iter(self.ws))
+            self.ws.pop(old)
+            for gk in [k for k in self.graphs if k[:2] == old]:
+                self.graphs.pop(gk)      # a captured graph owns pointers into that workspace
         self.ws[key] = ws
         return ws
+
+    # Small workloads are launch-bound (64 launches per V1 forward): replay them as one CUDA graph.
+    GRAPH_MAX_SAMPLES = 1 << 21
 
     def forward(self, x: torch.Tensor, time_convs: bool = False) -> torch.Tensor:
         """time_convs=True brackets the tensor-core conv launches (everything between the input transposition
         and conv_post) with CUDA events on the launching stream -> self.last_conv_events (bench.py roofline)."""
-        L = _lib.lib()
-        gen = self.gen
-        self.refresh()
+        self.refresh()   # weight (re)packing stays outside any graph: it writes the same buffers in place
         b, c, frames = x.shape
-        ws = self.workspace(b, frames)
         xin = x.contiguous()
         if xin.dtype != torch.float32:
             xin = xin.float()
+        t_out = frames
+        for pc in self.ups:
+            t_out *= pc.stride
+        use_graph = (not time_convs and b * t_out <= self.GRAPH_MAX_SAMPLES
+                     and not os.environ.get("HG_DISABLE_GRAPHS") and not torch.cuda.is_current_stream_capturing())
+        if not use_graph:
+            return self._launch(xin, time_convs)
+        key = (b, frames, _FUSE_PAIRS)
+        entry = self.graphs.get(key)
+        if entry is None:
+            static_in = torch.empty_like(xin)
+            static_in.copy_(xin)
+            self._launch(static_in, False)          # eager warm-up: one-time kernel attribute setup, workspaces
+            torch.cuda.current_stream().synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._launch(static_in, False)
+            entry = (graph, static_in, out)
+            if len(self.graphs) >= 8:
+                self.graphs.pop(next(iter(self.graphs)))
+            self.graphs[key] = entry
+        graph, static_in, out = entry
+        static_in.copy_(xin)
+        graph.replay()
+        return out
+
+    def _launch(self, xin: torch.Tensor, time_convs: bool) -> torch.Tensor:
+        L = _lib.lib()
+        gen = self.gen
+        b, c, frames = xin.shape
+        ws = self.workspace(b, frames)
         _lib.check(L.hg_ncl_to_nlc(xin.data_ptr(), b, c, frames, self.pre.cin_p, ws["mel"].data_ptr(), 0, 0.0,
                                    _stream()), "hg_ncl_to_nlc")
         if time_convs:
