@@ -170,7 +170,34 @@ __global__ void segment_gather_kernel(const float* __restrict__ pool, const long
     out[static_cast<size_t>(b) * seg + i] = i < nv ? pool[s0 + i] : 0.f;
 }
 
+// mode 0: sum |a - b|     (feature_loss / mel L1, src/models.py:251-257)
+// mode 1: sum (c - a)^2   (LSGAN terms, src/models.py:260-282; c = 1 for "real", 0 for "generated")
+__global__ void __launch_bounds__(256)
+loss_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, int mode, float c,
+                float* __restrict__ out) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x) {
+    const float d = mode == 0 ? a[i] - b[i] : c - a[i];
+    acc += mode == 0 ? fabsf(d) : d * d;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
 }  // namespace
+
+extern "C" int hg_loss_sum(const float* a, const float* b, long long n, int mode, float c, float* out_acc,
+                           void* stream) {
+  HG_REQUIRE(a && out_acc && n > 0 && (mode == 0 ? b != nullptr : mode == 1), "hg_loss_sum: bad arguments");
+  long long blocks = (n + 256 * 8 - 1) / (256 * 8);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  loss_sum_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, n, mode, c,
+                                                                                              out_acc);
+  HG_CHECK_CUDA(cudaGetLastError());
+  g_hg_launches.fetch_add(1, std::memory_order_relaxed);
+  return HG_OK;
+}
 
 extern "C" int hg_segment_gather(const float* pool, const long long* start, const int* valid, int batch,
                                  int seg, float* out, void* stream) {

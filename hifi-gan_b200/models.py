@@ -776,12 +776,26 @@ class MultiScaleDiscriminator(torch.nn.Module):
         return y_d_rs, y_d_gs, fmap_rs, fmap_gs
 
 
+def _device_mean(a: torch.Tensor, b: Optional[torch.Tensor], mode: int, c: float) -> Optional[torch.Tensor]:
+    """mean |a-b| (mode 0) or mean (c-a)^2 (mode 1) through hg_loss_sum; None when the kernel path does not
+    apply (CPU tensors or tensors that carry autograd history — backward is not built)."""
+    if not a.is_cuda or a.requires_grad or (b is not None and (b.requires_grad or not b.is_cuda)):
+        return None
+    a32 = a.detach().contiguous().float()
+    b32 = None if b is None else b.detach().contiguous().float()
+    acc = torch.zeros(1, dtype=torch.float32, device=a.device)
+    _lib.check(_lib.lib().hg_loss_sum(a32.data_ptr(), 0 if b32 is None else b32.data_ptr(), a32.numel(), mode, c,
+                                      acc.data_ptr(), _stream()), "hg_loss_sum")
+    return acc[0] / a32.numel()
+
+
 def feature_loss(fmap_r, fmap_g):
     """2 * sum of mean |r - g| over all feature maps; reference src/models.py:251-257."""
     total = 0
     for maps_r, maps_g in zip(fmap_r, fmap_g):
         for r, g in zip(maps_r, maps_g):
-            total = total + torch.mean(torch.abs(r - g))
+            m = _device_mean(r, g, 0, 0.0)
+            total = total + (m if m is not None else torch.mean(torch.abs(r - g)))
     return total * 2
 
 
@@ -790,8 +804,12 @@ def discriminator_loss(disc_real_outputs, disc_generated_outputs):
     The 2*N scalars cross to the host in ONE transfer instead of the reference's 2*N `.item()` syncs."""
     total, parts = 0, []
     for dr, dg in zip(disc_real_outputs, disc_generated_outputs):
-        r_loss = torch.mean((1 - dr) ** 2)
-        g_loss = torch.mean(dg ** 2)
+        r_loss = _device_mean(dr, None, 1, 1.0)
+        g_loss = _device_mean(dg, None, 1, 0.0)
+        if r_loss is None:
+            r_loss = torch.mean((1 - dr) ** 2)
+        if g_loss is None:
+            g_loss = torch.mean(dg ** 2)
         total = total + (r_loss + g_loss)
         parts += [r_loss.detach(), g_loss.detach()]
     host = torch.stack(parts).tolist() if parts else []
@@ -800,7 +818,10 @@ def discriminator_loss(disc_real_outputs, disc_generated_outputs):
 
 def generator_loss(disc_outputs):
     """LSGAN generator loss; returns (sum, [per-sub-discriminator tensors]); reference :274-282."""
-    gen_losses = [torch.mean((1 - dg) ** 2) for dg in disc_outputs]
+    gen_losses = []
+    for dg in disc_outputs:
+        l = _device_mean(dg, None, 1, 1.0)
+        gen_losses.append(l if l is not None else torch.mean((1 - dg) ** 2))
     total = 0
     for l in gen_losses:
         total = total + l

@@ -147,6 +147,11 @@ int hg_ncl_to_nlc(const float* x, int batch, int c, int t, int c_pad, void* out,
                   float act_slope, void* stream);
 int hg_nlc_to_ncl(const void* x, int batch, int t, int c, float* out, void* stream);
 
+/* hg_loss_sum — the reductions behind feature_loss / discriminator_loss / generator_loss (src/models.py:251-282)
+ * and the mel L1: mode 0 accumulates sum |a[i] - b[i]|, mode 1 accumulates sum (c - a[i])^2 into *out_acc (fp32,
+ * atomicAdd: zero it first; the caller divides by n for the mean).  a, b fp32 device arrays of n elements. */
+int hg_loss_sum(const float* a, const float* b, long long n, int mode, float c, float* out_acc, void* stream);
+
 /* hg_segment_gather — batched form of MelDataset.__getitem__'s crop / right zero-pad (src/meldataset.py:141-150):
  * out[b][i] = i < valid[b] ? pool[start[b] + i] : 0.  pool fp32 (all utterances concatenated, resident in HBM),
  * start int64 [B] (utterance offset + the drawn audio_start), valid int32 [B] (min(len, seg)), out fp32 [B][seg]. */

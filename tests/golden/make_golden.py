@@ -130,6 +130,37 @@ def main():
     np.savez_compressed(os.path.join(HERE, "disc_seed1234.npz"), **d)
     print("disc", d["mpd_feature_loss"], d["msd_feature_loss"], d["mpd_disc_loss"], d["msd_gen_loss"])
 
+    # 6. forward half of the UPSTREAM training step, reference modules, B = 2, no optimizer update:
+    #    G forward, mel of the generated audio, D-step losses, G-step losses (msd is called twice, so the
+    #    spectral-norm scale runs 4 power iterations, as in a real step)
+    torch.manual_seed(1234)
+    hh = env.AttrDict(O.config("v1"))
+    G = models.Generator(hh).train()
+    mpd = models.MultiPeriodDiscriminator().train()
+    msd = models.MultiScaleDiscriminator().train()
+    ya = O.synthetic_audio(2, 8192, seed=5)
+    with torch.no_grad():
+        x = meldataset.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, 8000)
+        y_mel = meldataset.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, None)
+        y = ya.unsqueeze(1)
+        y_g_hat = G(x)
+        y_g_hat_mel = meldataset.mel_spectrogram(y_g_hat.squeeze(1), 1024, 80, 22050, 256, 1024, 0, None)
+        y_df_r, y_df_g, _, _ = mpd(y, y_g_hat)
+        loss_disc_f, _, _ = models.discriminator_loss(y_df_r, y_df_g)
+        y_ds_r, y_ds_g, _, _ = msd(y, y_g_hat)
+        loss_disc_s, _, _ = models.discriminator_loss(y_ds_r, y_ds_g)
+        loss_mel = torch.nn.functional.l1_loss(y_mel, y_g_hat_mel) * 45
+        _, y_df_g, fmap_f_r, fmap_f_g = mpd(y, y_g_hat)
+        _, y_ds_g, fmap_s_r, fmap_s_g = msd(y, y_g_hat)
+        t = {"audio": ya.numpy(), "y_g_hat": y_g_hat.numpy(),
+             "loss_disc_f": float(loss_disc_f), "loss_disc_s": float(loss_disc_s), "loss_mel": float(loss_mel),
+             "loss_fm_f": float(models.feature_loss(fmap_f_r, fmap_f_g)),
+             "loss_fm_s": float(models.feature_loss(fmap_s_r, fmap_s_g)),
+             "loss_gen_f": float(models.generator_loss(y_df_g)[0]),
+             "loss_gen_s": float(models.generator_loss(y_ds_g)[0])}
+    np.savez_compressed(os.path.join(HERE, "train_fwd_seed1234.npz"), **t)
+    print("train fwd", {k: v for k, v in t.items() if k.startswith("loss")})
+
     # 5. per-layer known answers for the conv primitives at odd sizes (torch ops the reference calls)
     g = torch.Generator().manual_seed(5)
     x = torch.randn(2, 6, 37, generator=g)

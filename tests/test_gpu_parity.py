@@ -474,3 +474,35 @@ def test_discriminator_fmaps_vs_oracle(H, O):
                 assert fr.shape == fg.shape
                 scale = fr.abs().max().item() + 1e-6
                 assert (fg.cpu() - fr).abs().max().item() < 4e-2 * scale
+
+
+def test_training_step_forward_losses_vs_reference_golden(H, O):
+    """Forward half of the UPSTREAM training step (G, mel of the generated audio, both D passes, all seven loss
+    terms) vs the REFERENCE's values (tests/golden/train_fwd_seed1234.npz).  Tolerance: 3 % relative on every
+    loss (bf16 operands; the adversarial terms are sums over 8 sub-discriminators of O(1) values)."""
+    from hifigan_b200.train import step_losses
+    z = load_npz("train_fwd_seed1234.npz")
+    h = H.AttrDict(O.config("v1"))
+    torch.manual_seed(1234)
+    G = H.Generator(h).cuda().train()
+    mpd = H.MultiPeriodDiscriminator().cuda().train()
+    msd = H.MultiScaleDiscriminator().cuda().train()
+    audio = torch.from_numpy(z["audio"]).cuda()
+    x = H.mel_spectrogram(audio, 1024, 80, 22050, 256, 1024, 0, 8000)
+    y_mel = H.mel_spectrogram(audio, 1024, 80, 22050, 256, 1024, 0, None)
+    out = step_losses(G, mpd, msd, x, audio.unsqueeze(1), y_mel, h)
+    ref_wave = torch.from_numpy(z["y_g_hat"])
+    assert (out["y_g_hat"].cpu() - ref_wave).abs().max().item() < WAVE_MAX_ABS
+    for k in ("loss_disc_f", "loss_disc_s", "loss_mel", "loss_fm_f", "loss_fm_s", "loss_gen_f", "loss_gen_s"):
+        ref = float(z[k])
+        assert abs(out[k].item() - ref) < 3e-2 * abs(ref), (k, out[k].item(), ref)
+
+
+def test_loss_sum_kernel(H):
+    from hifigan_b200 import _lib
+    g = torch.Generator().manual_seed(4)
+    a, b = torch.randn(3, 1000, 37, generator=g).cuda(), torch.randn(3, 1000, 37, generator=g).cuda()
+    assert torch.allclose(H.feature_loss([[a]], [[b]]), 2 * (a - b).abs().mean(), rtol=1e-5)
+    l, r, gg = H.discriminator_loss([a], [b])
+    assert torch.allclose(l, ((1 - a) ** 2).mean() + (b ** 2).mean(), rtol=1e-5) and isinstance(r[0], float)
+    assert torch.allclose(H.generator_loss([a])[0], ((1 - a) ** 2).mean(), rtol=1e-5)
