@@ -74,6 +74,7 @@ _SIGNATURES = {
     "hg_avgpool_4_2_2_fwd": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "hg_disc_export_fmap": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hg_resblock_pair_supported": (c_int, [c_int, c_int, c_int]),
+    "hg_resblock_single_supported": (c_int, [c_int, c_int, c_int]),
     "hg_resblock_pair_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                      c_int, c_float, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_float,
                                      c_void_p]),

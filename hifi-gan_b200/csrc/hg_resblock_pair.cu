@@ -41,6 +41,7 @@ constexpr int kMaxXSlots = 4;
 struct PairArgs {
   int batch, t, c;
   int ktaps, dil1;
+  int single;           // 1: ResBlock2 step — ONE conv: y = conv1(lrelu(x)) + b1 + x (no conv2 / intermediate)
   int subs;             // 128-row sub-tiles per pipeline item (1, 2 or 4): one barrier hand-off covers all
   int r_out;            // output rows per item = subs*128 - (k-1)
   int pad1, pad2;       // (k-1)*d1/2, (k-1)/2
@@ -76,7 +77,7 @@ __device__ __forceinline__ uint32_t lrelu_bf16x2(uint32_t w, __nv_bfloat162 slop
 }
 
 // C = channels = UMMA N = K-chunk width: 64 -> SWIZZLE_128B rows of 128 B, 32 -> SWIZZLE_64B rows of 64 B.
-template <int C>
+template <int C, bool kSingle>
 __global__ void __launch_bounds__(pair_threads(C), 1)
 resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
                      const __grid_constant__ CUtensorMap tm_w2, const PairArgs p) {
@@ -96,7 +97,7 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   uint8_t* t1_buf = x_buf + p.x_slots * p.x_slot_bytes;
   uint8_t* w1_buf = t1_buf + 2 * p.t1_slot_bytes;
   uint8_t* w2_buf = w1_buf + p.w_bytes;
-  PairBarriers* bars = reinterpret_cast<PairBarriers*>(w2_buf + p.w_bytes);
+  PairBarriers* bars = reinterpret_cast<PairBarriers*>(w1_buf + (kSingle ? 1 : 2) * p.w_bytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -149,9 +150,9 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   if (warp == 0) {
     // ============================ TMA producer ============================
     if (lane == 0) {
-      hg::mbar_arrive_expect_tx(&bars->w_full, 2 * p.w_bytes);
+      hg::mbar_arrive_expect_tx(&bars->w_full, (kSingle ? 1 : 2) * p.w_bytes);
       hg::tma_load_3d(w1_buf, &tm_w1, &bars->w_full, 0, 0, 0);
-      hg::tma_load_3d(w2_buf, &tm_w2, &bars->w_full, 0, 0, 0);
+      if (!kSingle) hg::tma_load_3d(w2_buf, &tm_w2, &bars->w_full, 0, 0, 0);
       const uint32_t box_bytes = static_cast<uint32_t>(p.x_box_rows) * kRowBytes;
       int tt = blockIdx.x % p.tiles_t, b = blockIdx.x / p.tiles_t;
       const int tt_step = gridDim.x % p.tiles_t, b_step = gridDim.x / p.tiles_t;
@@ -222,10 +223,14 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       }
       __syncwarp();
     };
-    if (n_local > 0) conv1(0);
-    for (int i = 0; i < n_local; ++i) {
-      if (i + 1 < n_local) conv1(i + 1);
-      conv2(i);
+    if (kSingle) {
+      for (int i = 0; i < n_local; ++i) conv1(i);
+    } else {
+      if (n_local > 0) conv1(0);
+      for (int i = 0; i < n_local; ++i) {
+        if (i + 1 < n_local) conv1(i + 1);
+        conv2(i);
+      }
     }
   } else if (warp < 2 + kXformWarps) {
     // ============================ transform: in-place leaky_relu ==========
@@ -267,7 +272,7 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       const uint32_t swz = (C == 64) ? (row & 7) : ((row >> 1) & 3);
       int tt = blockIdx.x % p.tiles_t;   // time-tile index of the current item, advanced without divisions
       const int tt_step = gridDim.x % p.tiles_t;
-      for (int i = 0; i < n_local; ++i) {
+      for (int i = 0; i < (kSingle ? 0 : n_local); ++i) {
         const uint32_t a = i & 1u, ph = (i >> 1) & 1u;
         hg::mbar_wait(&bars->acc1_full[a], ph);
         hg::mbar_wait(&bars->t1_empty[a], ph ^ 1u);
@@ -311,7 +316,11 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       }
     } else {
       // ---- E2: y = (acc2 + b2 + x + res1 + res2) * scale  ->  global
-      const float* bias = bars->b2;
+      // single-conv mode: this role drains conv1's accumulators directly (bias b1, no intermediate)
+      const float* bias = kSingle ? bars->b1 : bars->b2;
+      uint64_t* full_bar = kSingle ? bars->acc1_full : bars->acc2_full;
+      uint64_t* empty_bar = kSingle ? bars->acc1_empty : bars->acc2_empty;
+      const uint32_t acc_base = kSingle ? 0u : 2 * acc_cols;
       // unit = (item, sub-tile m); residual rows are fetched one unit ahead so their (L2) latency hides.
       // The (time tile, batch, sub-tile) of the NEXT unit is advanced incrementally: integer divisions per unit
       // were the single largest cost of this warp role (clock64 traces).
@@ -354,18 +363,18 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
           }
         }
         if (m == 0) {
-          hg::mbar_wait(&bars->acc2_full[a], ph);
+          hg::mbar_wait(&full_bar[a], ph);
           hg::tc_fence_after();
         }
 #pragma unroll
         for (int g = 0; g < kG; ++g) {
           uint32_t raw[16];
-          hg::tmem_ld_32x16(tmem_base + lane_base + 2 * acc_cols + a * acc_cols + m * C + col0 + g * 16, raw);
+          hg::tmem_ld_32x16(tmem_base + lane_base + acc_base + a * acc_cols + m * C + col0 + g * 16, raw);
           hg::tmem_ld_wait();
           if (g == kG - 1 && m == S - 1) {
             hg::tc_fence_before();
             __syncwarp();
-            if (lane == 0) hg::mbar_arrive(&bars->acc2_empty[a]);
+            if (lane == 0) hg::mbar_arrive(&empty_bar[a]);
           }
           if (valid) {
             float v[16];
@@ -410,27 +419,27 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 
 int g_sms = 0, g_smem = 0;
 
-template <int C>
+template <int C, bool kSingle>
 int launch_pair(const CUtensorMap& tx, const CUtensorMap& tw1, const CUtensorMap& tw2, const PairArgs& p,
                 size_t smem_bytes, int grid, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    HG_CHECK_CUDA(cudaFuncSetAttribute(resblock_pair_kernel<C>,
+    HG_CHECK_CUDA(cudaFuncSetAttribute(resblock_pair_kernel<C, kSingle>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem));
     configured = true;
   }
-  resblock_pair_kernel<C><<<grid, pair_threads(C), smem_bytes, st>>>(tx, tw1, tw2, p);
+  resblock_pair_kernel<C, kSingle><<<grid, pair_threads(C), smem_bytes, st>>>(tx, tw1, tw2, p);
   HG_CHECK_CUDA(cudaGetLastError());
   return HG_OK;
 }
 
-size_t pair_smem_bytes(int c, int ktaps, int dil1, int subs, int x_slots, PairArgs* out) {
+size_t pair_smem_bytes(int c, int ktaps, int dil1, int subs, int x_slots, int single, PairArgs* out) {
   const uint32_t row = static_cast<uint32_t>(c) * 2;
   const uint32_t a_rows = subs * kM + (ktaps - 1) * dil1;
   const uint32_t boxes = (a_rows + 255) / 256;
   const uint32_t box_rows = ((a_rows + boxes - 1) / boxes + 15) & ~15u;   // 16-row multiples keep every box
   const uint32_t x_slot = (boxes * box_rows * row + 1023u) & ~1023u;      // 1024-byte aligned in smem
-  const uint32_t t1_slot = ((subs * kM + ktaps - 1) * row + 1023u) & ~1023u;
+  const uint32_t t1_slot = single ? 0u : ((subs * kM + ktaps - 1) * row + 1023u) & ~1023u;
   const uint32_t w_bytes = static_cast<uint32_t>(ktaps) * c * row;
   if (box_rows > 256) return ~static_cast<size_t>(0);
   if (out) {
@@ -438,13 +447,13 @@ size_t pair_smem_bytes(int c, int ktaps, int dil1, int subs, int x_slots, PairAr
     out->x_slot_bytes = x_slot; out->t1_slot_bytes = t1_slot; out->w_bytes = w_bytes;
   }
   return 1024 + static_cast<size_t>(x_slots) * x_slot + 2 * static_cast<size_t>(t1_slot) +
-         2 * static_cast<size_t>(w_bytes) + sizeof(PairBarriers);
+         (single ? 1 : 2) * static_cast<size_t>(w_bytes) + sizeof(PairBarriers);
 }
 
 // Largest sub-tile count whose TMEM (4*subs*C columns <= 512) and shared memory (>= 2 x slots) fit.
-int pick_subs(int c, int ktaps, int dil1) {
+int pick_subs(int c, int ktaps, int dil1, int single) {
   for (int subs = 512 / (4 * c); subs >= 1; subs >>= 1)
-    if (pair_smem_bytes(c, ktaps, dil1, subs, 2, nullptr) <= static_cast<size_t>(g_smem)) return subs;
+    if (pair_smem_bytes(c, ktaps, dil1, subs, 2, single, nullptr) <= static_cast<size_t>(g_smem)) return subs;
   return 0;
 }
 
@@ -459,7 +468,13 @@ extern "C" int hg_resblock_pair_supported(int c, int ktaps, int dil1) {
     cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&g_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   }
-  return pick_subs(c, ktaps, dil1) > 0 ? 1 : 0;
+  return pick_subs(c, ktaps, dil1, 0) > 0 ? 1 : 0;
+}
+
+extern "C" int hg_resblock_single_supported(int c, int ktaps, int dil1) {
+  if (!hg_resblock_pair_supported(c, 1, 1) && !g_smem) return 0;   // also initialises the device limits
+  if (!(c == 32 || c == 64) || ktaps < 1 || !(ktaps & 1) || dil1 < 1 || ktaps > 65) return 0;
+  return pick_subs(c, ktaps, dil1, 1) > 0 ? 1 : 0;
 }
 
 extern "C" int hg_resblock_pair_fwd(const void* x, const void* w1_packed, const float* b1,
@@ -467,25 +482,27 @@ extern "C" int hg_resblock_pair_fwd(const void* x, const void* w1_packed, const 
                                     int ktaps, int dil1, float in_slope, const void* res1,
                                     const void* res2, float scale, void* out_raw, void* out_act,
                                     float out_slope, void* stream) {
-  HG_REQUIRE(x && w1_packed && w2_packed && b1 && b2, "hg_resblock_pair_fwd: null input");
+  const int single = w2_packed == nullptr;   // ResBlock2 step: one conv + residual
+  HG_REQUIRE(x && w1_packed && b1 && (single || b2), "hg_resblock_pair_fwd: null input");
   HG_REQUIRE(out_raw || out_act, "hg_resblock_pair_fwd: no output requested");
   HG_REQUIRE(batch > 0 && t > 0, "hg_resblock_pair_fwd: empty batch/time");
-  HG_REQUIRE(hg_resblock_pair_supported(c, ktaps, dil1),
+  HG_REQUIRE(hg_resblock_pair_supported(c, ktaps, dil1) || (single && hg_resblock_single_supported(c, ktaps, dil1)),
              "hg_resblock_pair_fwd: unsupported shape c=%d k=%d d=%d (use hg_conv1d_fwd)", c, ktaps, dil1);
   PairArgs p{};
   p.batch = batch; p.t = t; p.c = c; p.ktaps = ktaps; p.dil1 = dil1;
-  const int subs = pick_subs(c, ktaps, dil1);
-  p.r_out = subs * kM + 1 - ktaps;
+  const int subs = pick_subs(c, ktaps, dil1, single);
+  p.single = single;
+  p.r_out = single ? subs * kM : subs * kM + 1 - ktaps;
   p.pad1 = (ktaps - 1) * dil1 / 2;
-  p.pad2 = (ktaps - 1) / 2;
+  p.pad2 = single ? 0 : (ktaps - 1) / 2;
   p.tiles_t = (t + p.r_out - 1) / p.r_out;
   p.num_tiles = batch * p.tiles_t;
   int slots = kMaxXSlots;
-  while (slots > 2 && pair_smem_bytes(c, ktaps, dil1, subs, slots, nullptr) > static_cast<size_t>(g_smem)) --slots;
+  while (slots > 2 && pair_smem_bytes(c, ktaps, dil1, subs, slots, single, nullptr) > static_cast<size_t>(g_smem)) --slots;
   p.x_slots = slots;
-  const size_t smem_bytes = pair_smem_bytes(c, ktaps, dil1, subs, slots, &p);
+  const size_t smem_bytes = pair_smem_bytes(c, ktaps, dil1, subs, slots, single, &p);
   p.x = static_cast<const __nv_bfloat16*>(x);
-  p.b1 = b1; p.b2 = b2;
+  p.b1 = b1; p.b2 = single ? b1 : b2;
   p.res1 = static_cast<const __nv_bfloat16*>(res1);
   p.res2 = static_cast<const __nv_bfloat16*>(res2);
   p.scale = scale; p.in_slope = in_slope; p.out_slope = out_slope;
@@ -500,13 +517,17 @@ extern "C" int hg_resblock_pair_fwd(const void* x, const void* w1_packed, const 
   rc = hg_encode_tmap_bf16_3d(&tw1, w1_packed, c, c, ktaps, static_cast<uint64_t>(c) * 2,
                               static_cast<uint64_t>(c) * c * 2, c, c, ktaps, swz);
   if (rc) return rc;
-  rc = hg_encode_tmap_bf16_3d(&tw2, w2_packed, c, c, ktaps, static_cast<uint64_t>(c) * 2,
+  rc = hg_encode_tmap_bf16_3d(&tw2, single ? w1_packed : w2_packed, c, c, ktaps, static_cast<uint64_t>(c) * 2,
                               static_cast<uint64_t>(c) * c * 2, c, c, ktaps, swz);
   if (rc) return rc;
   const int grid = p.num_tiles < g_sms ? p.num_tiles : g_sms;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  rc = (c == 64) ? launch_pair<64>(tx, tw1, tw2, p, smem_bytes, grid, st)
-                 : launch_pair<32>(tx, tw1, tw2, p, smem_bytes, grid, st);
+  if (single)
+    rc = (c == 64) ? launch_pair<64, true>(tx, tw1, tw2, p, smem_bytes, grid, st)
+                   : launch_pair<32, true>(tx, tw1, tw2, p, smem_bytes, grid, st);
+  else
+    rc = (c == 64) ? launch_pair<64, false>(tx, tw1, tw2, p, smem_bytes, grid, st)
+                   : launch_pair<32, false>(tx, tw1, tw2, p, smem_bytes, grid, st);
   if (rc) return rc;
   g_hg_launches.fetch_add(1, std::memory_order_relaxed);
   return HG_OK;

@@ -155,8 +155,9 @@ def _pair(L, x, pc1: _PackedConv, pc2: _PackedConv, batch: int, t: int, *, res=(
           out_raw=None, out_act=None, slope=LRELU_SLOPE) -> None:
     """One fused ResBlock1 step: conv2(lrelu(conv1(lrelu(x)) + b1)) + b2 + x (+ res) — hg_resblock_pair_fwd."""
     p = [0 if r is None else r.data_ptr() for r in res]
-    _lib.check(L.hg_resblock_pair_fwd(x.data_ptr(), pc1.w.data_ptr(), pc1.bias.data_ptr(), pc2.w.data_ptr(),
-                                      pc2.bias.data_ptr(), batch, t, pc1.cin_p, pc1.taps, pc1.dil, LRELU_SLOPE,
+    w2, b2 = (0, 0) if pc2 is None else (pc2.w.data_ptr(), pc2.bias.data_ptr())   # None: one ResBlock2 step
+    _lib.check(L.hg_resblock_pair_fwd(x.data_ptr(), pc1.w.data_ptr(), pc1.bias.data_ptr(), w2,
+                                      b2, batch, t, pc1.cin_p, pc1.taps, pc1.dil, LRELU_SLOPE,
                                       p[0], p[1], scale, 0 if out_raw is None else out_raw.data_ptr(),
                                       0 if out_act is None else out_act.data_ptr(), slope, _stream()),
                "hg_resblock_pair_fwd")
@@ -170,10 +171,15 @@ def _pair_ok(L, pc1: _PackedConv, pc2: _PackedConv) -> bool:
                 and pc2.dil == 1 and L.hg_resblock_pair_supported(pc1.cin_p, pc1.taps, pc1.dil))
 
 
+def _single_ok(L, pc: _PackedConv) -> bool:
+    return bool(_FUSE_PAIRS and pc.cin_p == pc.cout_p and L.hg_resblock_single_supported(pc.cin_p, pc.taps, pc.dil))
+
+
 def _block_plan(L, block: "nn.Module", packs: List[_PackedConv]) -> List[bool]:
-    """Per ResBlock step: True when it runs as ONE fused pair launch."""
+    """Per ResBlock step: True when it runs as ONE fused launch (conv-lrelu-conv-residual for ResBlock1,
+    lrelu-conv-residual for ResBlock2)."""
     if not isinstance(block, ResBlock1):
-        return [False] * len(packs)
+        return [_single_ok(L, pc) for pc in packs]
     return [_pair_ok(L, packs[2 * i], packs[2 * i + 1]) for i in range(len(packs) // 2)]
 
 
@@ -193,7 +199,7 @@ def _resblock_chain(L, block: "nn.Module", packs: List[_PackedConv], batch: int,
         nr, na = ping[i & 1]
         want_act = (not last) and (not fused[i + 1])  # only an unfused consumer needs the activated copy
         if fused[i]:
-            pc1, pc2 = packs[2 * i], packs[2 * i + 1]
+            pc1, pc2 = (packs[2 * i], packs[2 * i + 1]) if two_conv else (packs[i], None)
             if last:
                 final(dict(pair=(pc1, pc2), x=cur_raw))
             else:

@@ -110,8 +110,12 @@ int hg_conv1d_general_fwd(const void* x, const void* w_packed, const float* bias
  * Both convolutions use "same" zero padding ((k-1)*d/2).  The intermediate t1 stays in shared memory;
  * HBM traffic is one read of x and one write per requested output.  out_* must not alias x.
  * hg_resblock_pair_supported(c, ktaps, dil1) tells whether the shape fits (c in {32,64}, both filter
- * banks resident in shared memory); otherwise the caller composes two hg_conv1d_fwd calls. */
+ * banks resident in shared memory); otherwise the caller composes two hg_conv1d_fwd calls.
+ * With w2_packed == NULL (b2 ignored) the same kernel runs ONE ResBlock2 step (src/models.py:64-67):
+ *   v = (conv1d(leaky_relu(x, in_slope), w1, dilation=dil1) + b1 + x + res1 + res2) * scale
+ * (hg_resblock_single_supported). */
 int hg_resblock_pair_supported(int c, int ktaps, int dil1);
+int hg_resblock_single_supported(int c, int ktaps, int dil1);
 int hg_resblock_pair_fwd(const void* x, const void* w1_packed, const float* b1, const void* w2_packed,
                          const float* b2, int batch, int t, int c, int ktaps, int dil1, float in_slope,
                          const void* res1, const void* res2, float scale, void* out_raw, void* out_act,

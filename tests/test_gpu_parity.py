@@ -135,10 +135,40 @@ def test_resblock_pair_vs_torch_fp32(H, c, k, d, b, t):
     assert (out_raw.float() - ref).abs().mean().item() < 2e-3
 
 
-def test_fused_and_unfused_generator_paths_agree(H, O):
+@pytest.mark.parametrize("c,k,d", [(64, 3, 1), (64, 7, 12), (64, 5, 6), (32, 3, 2), (32, 7, 12), (32, 5, 2)])
+@pytest.mark.parametrize("b,t", [(2, 700), (1, 130), (3, 1)])
+def test_resblock_single_vs_torch_fp32(H, c, k, d, b, t):
+    """hg_resblock_pair_fwd with w2 == NULL: one ResBlock2 step (lrelu -> dilated conv -> + x) vs fp32 torch."""
+    from hifigan_b200 import _lib
+    L = _lib.lib()
+    assert L.hg_resblock_single_supported(c, k, d) == 1
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(c * 1000 + k * 10 + d)
+    x = torch.randn(b, t, c, generator=g).to(dev).bfloat16()
+    w1 = (torch.randn(c, c, k, generator=g) / (c * k) ** 0.5).to(dev)
+    b1 = torch.randn(c, generator=g).to(dev)
+    r1 = torch.randn(b, t, c, generator=g).to(dev).bfloat16()
+    st = torch.cuda.current_stream().cuda_stream
+    wp1 = torch.empty(k, c, c, dtype=torch.bfloat16, device=dev)
+    _lib.check(L.hg_pack_conv1d_weight(w1.data_ptr(), 0, c, c, k, c, wp1.data_ptr(), st))
+    out_raw = torch.full((b, t, c), 7.0, dtype=torch.bfloat16, device=dev)
+    out_act = torch.full((b, t, c), 7.0, dtype=torch.bfloat16, device=dev)
+    _lib.check(L.hg_resblock_pair_fwd(x.data_ptr(), wp1.data_ptr(), b1.data_ptr(), 0, 0, b, t, c, k, d, 0.1,
+                                      r1.data_ptr(), 0, 0.5, out_raw.data_ptr(), out_act.data_ptr(), 0.1, st))
+    torch.cuda.synchronize()
+    xa = F.leaky_relu(x.float(), 0.1).bfloat16().float().transpose(1, 2)
+    y = F.conv1d(xa, wp1.float().permute(1, 2, 0).contiguous(), b1, dilation=d, padding=(k - 1) * d // 2)
+    ref = (y.transpose(1, 2) + x.float() + r1.float()) * 0.5
+    tol = 2.0 ** -8 * ref.abs() + 2e-3
+    assert bool(((out_raw.float() - ref).abs() <= tol).all())
+    assert bool(((out_act.float() - F.leaky_relu(ref, 0.1)).abs() <= tol).all())
+
+
+@pytest.mark.parametrize("ver", ["v1", "v3"])
+def test_fused_and_unfused_generator_paths_agree(H, O, ver):
     """The Generator through fused ResBlock pairs vs the same Generator through two-launch convs."""
     from hifigan_b200 import models
-    h = H.AttrDict(O.config("v1"))
+    h = H.AttrDict(O.config(ver))
     torch.manual_seed(1234)
     G = H.Generator(h).cuda().eval()
     x = torch.randn(2, 80, 40, device="cuda")
