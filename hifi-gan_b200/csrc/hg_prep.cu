@@ -113,11 +113,15 @@ __global__ void nlc_to_ncl_kernel(const __nv_bfloat16* __restrict__ x, int t, in
 }
 
 // conv_post + tanh: y[b,t] = tanh(bias + sum_{j,c} x[b, t + j - k/2, c] * w[c][j]).
-// One thread per output sample; the (TT + k - 1) x C input window is staged in shared memory with
-// a 16-byte row pad so the 128-bit row reads of a quarter-warp hit distinct banks.
-constexpr int kPostTile = 256;
+// Each thread produces kPostPer consecutive samples so that one shared-memory read of a weight vector feeds
+// kPostPer FMAs (one-output-per-thread was bound by the LDS issue rate, 0.76 ms at config 2).  The
+// (tile + k - 1) x C input window is staged in shared memory with a 16-byte row pad so the 128-bit row reads of
+// a quarter-warp hit distinct banks.
+constexpr int kPostThreads = 128;
+constexpr int kPostPer = 4;
+constexpr int kPostTile = kPostThreads * kPostPer;
 
-__global__ void __launch_bounds__(kPostTile)
+__global__ void __launch_bounds__(kPostThreads)
 conv_post_tanh_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                       const float* __restrict__ bias, int t, int c, int k, float* __restrict__ y) {
   extern __shared__ __align__(16) uint8_t sm[];
@@ -142,22 +146,30 @@ conv_post_tanh_kernel(const __nv_bfloat16* __restrict__ x, const float* __restri
     *reinterpret_cast<uint4*>(xs + r * pitch + vq * 16) = val;
   }
   __syncthreads();
-  const int tt = t0 + threadIdx.x;
-  if (tt >= t) return;
-  float acc = bias ? bias[0] : 0.f;
+  // thread owns outputs tid, tid + 128, tid + 256, tid + 384 of the tile: lanes of a warp read adjacent staged
+  // rows (conflict-free with the 16-byte pad) and every weight vector read from shared memory feeds 4 outputs
+  float acc[kPostPer];
+#pragma unroll
+  for (int o = 0; o < kPostPer; ++o) acc[o] = bias ? bias[0] : 0.f;
   for (int j = 0; j < k; ++j) {
-    const uint8_t* row = xs + (threadIdx.x + j) * pitch;
-    const float* wj = ws + j * c;
     for (int vq = 0; vq < vec_per_row; ++vq) {
-      const uint4 r = *reinterpret_cast<const uint4*>(row + vq * 16);
-      const float2 a = hg::unpack_bf16x2(r.x), bb = hg::unpack_bf16x2(r.y),
-                   cc2 = hg::unpack_bf16x2(r.z), d = hg::unpack_bf16x2(r.w);
-      const float* wq = wj + vq * 8;
-      acc += a.x * wq[0] + a.y * wq[1] + bb.x * wq[2] + bb.y * wq[3] + cc2.x * wq[4] +
-             cc2.y * wq[5] + d.x * wq[6] + d.y * wq[7];
+      const float4 w0 = *reinterpret_cast<const float4*>(ws + j * c + vq * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(ws + j * c + vq * 8 + 4);
+#pragma unroll
+      for (int o = 0; o < kPostPer; ++o) {
+        const uint4 rv = *reinterpret_cast<const uint4*>(xs + (threadIdx.x + o * kPostThreads + j) * pitch + vq * 16);
+        const float2 a0 = hg::unpack_bf16x2(rv.x), a1 = hg::unpack_bf16x2(rv.y), a2 = hg::unpack_bf16x2(rv.z),
+                     a3 = hg::unpack_bf16x2(rv.w);
+        acc[o] += a0.x * w0.x + a0.y * w0.y + a1.x * w0.z + a1.y * w0.w + a2.x * w1.x + a2.y * w1.y +
+                  a3.x * w1.z + a3.y * w1.w;
+      }
     }
   }
-  y[static_cast<size_t>(b) * t + tt] = tanhf(acc);
+#pragma unroll
+  for (int o = 0; o < kPostPer; ++o) {
+    const int tt = t0 + threadIdx.x + o * kPostThreads;
+    if (tt < t) y[static_cast<size_t>(b) * t + tt] = tanhf(acc[o]);
+  }
 }
 
 // out[b][i] = i < valid[b] ? pool[start[b] + i] : 0   (MelDataset crop / right zero-pad, meldataset.py:141-150)
@@ -276,16 +288,16 @@ extern "C" int hg_nlc_to_ncl(const void* x, int batch, int t, int c, float* out,
 extern "C" int hg_conv_post_tanh_fwd(const void* x, const float* w, const float* bias, int batch,
                                      int t, int c, int k, float* y, void* stream) {
   HG_REQUIRE(x && w && y, "hg_conv_post_tanh_fwd: null pointer");
-  HG_REQUIRE(batch > 0 && t > 0 && c > 0 && c % 8 == 0 && k > 0 && (k & 1),
-             "hg_conv_post_tanh_fwd: bad shape (c %% 8 == 0, odd k required)");
+  HG_REQUIRE(batch > 0 && t > 0 && c > 0 && c % 8 == 0 && k > 0 && (k & 1) && k <= 15,
+             "hg_conv_post_tanh_fwd: bad shape (c %% 8 == 0, odd k <= 15 required)");
   HG_REQUIRE(batch <= 65535, "hg_conv_post_tanh_fwd: batch too large");
   const size_t smem = ((k * c * 4 + 15) & ~15) + static_cast<size_t>(kPostTile + k - 1) * (c * 2 + 16);
   HG_REQUIRE(smem <= 200 * 1024, "hg_conv_post_tanh_fwd: window does not fit shared memory");
-  if (smem > 48 * 1024)
-    HG_CHECK_CUDA(cudaFuncSetAttribute(conv_post_tanh_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((t + kPostTile - 1) / kPostTile, batch);
-  conv_post_tanh_kernel<<<grid, kPostTile, smem, static_cast<cudaStream_t>(stream)>>>(
+  if (smem > 48 * 1024)
+    HG_CHECK_CUDA(cudaFuncSetAttribute(conv_post_tanh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+  conv_post_tanh_kernel<<<grid, kPostThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), w, bias, t, c, k, y);
   HG_CHECK_CUDA(cudaGetLastError());
   g_hg_launches.fetch_add(1, std::memory_order_relaxed);

@@ -317,6 +317,7 @@ class _GeneratorEngine:
         self.post_key = None
         self.ws: Dict[Tuple[int, int], Dict[str, torch.Tensor]] = {}
         self.graphs: Dict[tuple, tuple] = {}
+        self.graph_seen = set()
 
     def refresh(self) -> None:
         self.pre.refresh()
@@ -388,16 +389,28 @@ class _GeneratorEngine:
         if entry is None:
             static_in = torch.empty_like(xin)
             static_in.copy_(xin)
-            self._launch(static_in, False)          # eager warm-up: one-time kernel attribute setup, workspaces
-            torch.cuda.current_stream().synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                out = self._launch(static_in, False)
-            entry = (graph, static_in, out)
+            out = self._launch(static_in, False)    # eager run: one-time kernel loading / attribute setup, workspaces
+            torch.cuda.synchronize()
+            # capture on the SECOND call of a shape: the first call of a process can still be loading kernel
+            # images lazily, which is not allowed while a stream is capturing
+            if key not in self.graph_seen:
+                self.graph_seen.add(key)
+                return out
+            try:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    out = self._launch(static_in, False)
+                entry = (graph, static_in, out)
+            except RuntimeError as e:               # stay correct: this shape keeps running eagerly
+                warnings.warn(f"hifigan_b200: CUDA graph capture failed for shape {key}, running eagerly ({e})")
+                torch.cuda.synchronize()
+                entry = (None, None, None)
             if len(self.graphs) >= 8:
                 self.graphs.pop(next(iter(self.graphs)))
             self.graphs[key] = entry
         graph, static_in, out = entry
+        if graph is None:
+            return self._launch(xin, False)
         static_in.copy_(xin)
         graph.replay()
         return out

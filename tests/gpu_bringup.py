@@ -215,6 +215,30 @@ def stage_pairs(b, frames, debug=0):
                 del x, o1
 
 
+def stage_post(b, t):
+    L = _lib.lib()
+    dev = torch.device("cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    x = torch.randn(b, t, 32, device=dev).bfloat16()
+    w = torch.randn(32, 7, device=dev) * 0.1
+    bias = torch.zeros(1, device=dev)
+    y = torch.empty(b, t, device=dev)
+    def run():
+        _lib.check(L.hg_conv_post_tanh_fwd(x.data_ptr(), w.data_ptr(), bias.data_ptr(), b, t, 32, 7, y.data_ptr(), st))
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    ref = torch.tanh(F.conv1d(x.float().transpose(1, 2), w.unsqueeze(0), bias, padding=3))[:, 0]
+    emit(stage="post", b=b, t=t, ms=round(ms, 4), gbs=round(b * t * 68 / ms / 1e6, 1), err=(y - ref).abs().max().item())
+
+
 def stage_melperf():
     """cfg5 sweep: fused mel kernel throughput vs the 1344 B/frame HBM roofline, and vs torchaudio on the GPU."""
     import torchaudio
@@ -282,6 +306,8 @@ if __name__ == "__main__":
         stage_conv(int(sys.argv[2]))
     elif st == "gen":
         stage_gen(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]))
+    elif st == "post":
+        stage_post(int(sys.argv[2]), int(sys.argv[3]))
     elif st == "melperf":
         stage_melperf()
     elif st == "disc":
