@@ -505,8 +505,8 @@ class Generator(torch.nn.Module):
         return eng
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """Returns a view of an engine-owned buffer that the next forward() with the same shape
-        overwrites; `.clone()` it to keep it (the reference allocates a fresh tensor per call)."""
+        """mel [B,80,F] -> waveform [B,1,T], a fresh tensor per call like the reference.  (`self._engine(dev)
+        .forward(x)` returns the engine-owned buffer without the copy: the benchmark's device-resident path.)"""
         _require_cuda(x, "Generator.forward")
         if torch.is_grad_enabled() and self.training and (
                 x.requires_grad or any(p.requires_grad for p in self.parameters())):
@@ -514,7 +514,7 @@ class Generator(torch.nn.Module):
                                       "call under torch.no_grad() or .eval()")
         if x.dim() != 3 or x.shape[1] != self.conv_pre.in_channels:
             raise ValueError(f"expected [B,{self.conv_pre.in_channels},F], got {tuple(x.shape)}")
-        return self._engine(x.device).forward(x)
+        return self._engine(x.device).forward(x).clone()
 
     def _drop_engines(self):
         self.__dict__["_hg_engines"] = {}
