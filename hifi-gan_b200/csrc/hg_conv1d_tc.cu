@@ -24,6 +24,7 @@
 #include "hg_common.cuh"
 
 #include <atomic>
+#include <cstdlib>
 
 extern std::atomic<int64_t> g_hg_launches;
 
@@ -366,6 +367,249 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   if (warp == 1) hg::tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// ==================================================================================================
+// CTA-pair variant (cta_group::2): one 256-row x NT tile per pair.  Each CTA loads the activation box
+// of its own 128 rows and HALF of every weight stage (NT/2 filter rows); the leader issues M = 256
+// MMAs that read both CTAs' shared memory, so per CTA an MMA costs 4 KB (A) + NT*16 B (half of B) of
+// shared-memory bandwidth instead of 4 KB + NT*32 B, and the weight fill traffic per CTA halves too.
+// Used for the dense stride-1 layers whose filter bank does not fit in shared memory (NT >= 128).
+// ==================================================================================================
+struct Barriers2 {
+  uint64_t a_full[kMaxASlots];     // leader's copy is the live one (count 2: leader arm + peer arrive)
+  uint64_t a_empty[kMaxASlots];    // per CTA, released by the leader's multicast commit
+  uint64_t w_full[kMaxStages];
+  uint64_t w_empty[kMaxStages];
+  uint64_t acc_full[2];            // per CTA (multicast commit)
+  uint64_t acc_empty[2];           // leader's copy, count 2 * kEpiWarps (both CTAs' epilogue warps)
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+template <int NT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv1d_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                  const ConvArgs p) {
+  constexpr int KC = 64;
+  constexpr uint32_t kRowBytes = KC * 2;
+  constexpr uint32_t kLayout = 2u;
+  constexpr uint32_t kSbo = 8 * kRowBytes;
+  constexpr uint32_t kTapBytes = (NT / 2) * kRowBytes;   // per CTA: half of the filter rows of one tap
+  constexpr uint32_t kTmemCols = (2 * NT <= 256) ? 256u : 512u;
+  constexpr int kColsPerWarp = NT / 2;
+  constexpr int kGroups16 = kColsPerWarp / 16;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* a_buf = smem;
+  uint8_t* w_buf = smem + p.a_slots * p.a_slot_bytes;
+  Barriers2* bars = reinterpret_cast<Barriers2*>(w_buf + static_cast<uint32_t>(p.stages) * p.w_stage_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = hg::cluster_ctarank();       // 0 = leader (issues the MMAs)
+  const int n_clusters = gridDim.x >> 1;
+  const int cluster_id = blockIdx.x >> 1;
+  // pair tiles: (n tile, pair of time tiles, batch)
+  const int tiles_pt = (p.tiles_t + 1) >> 1;
+  const int num_pt = p.batch * tiles_pt * p.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    hg::tma_prefetch_desc(&tm_x);
+    hg::tma_prefetch_desc(&tm_w);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < kMaxASlots; ++i) {
+        hg::mbar_init(&bars->a_full[i], 2);
+        hg::mbar_init(&bars->a_empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        hg::mbar_init(&bars->acc_full[i], 1);
+        hg::mbar_init(&bars->acc_empty[i], 2 * kEpiWarps);
+      }
+      for (int i = 0; i < kMaxStages; ++i) {
+        hg::mbar_init(&bars->w_full[i], 2);
+        hg::mbar_init(&bars->w_empty[i], 1);
+      }
+      hg::fence_mbar_init();
+    }
+    __syncwarp();
+    hg::tmem_alloc_2sm(&bars->tmem_base, kTmemCols);
+  }
+  hg::tc_fence_before();
+  __syncthreads();
+  hg::cluster_sync_all();     // the peer's barriers must exist before anything is signalled across the pair
+  hg::tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&bars->tmem_base);
+
+  // incremental decode of the cluster's pair tiles
+  auto decode = [&](int pt, int& nt, int& ptt, int& b) {
+    nt = pt % p.tiles_n;
+    const int r = pt / p.tiles_n;
+    ptt = r % tiles_pt;
+    b = r / tiles_pt;
+  };
+
+  if (warp == 0) {
+    // ============================ TMA producer (both CTAs) ================
+    if (lane == 0) {
+      uint32_t a_slot = 0, a_phase = 0, w_slot = 0, w_phase = 0;
+      const uint32_t a_bytes = static_cast<uint32_t>(p.a_rows) * kRowBytes;
+      const uint32_t w_bytes = static_cast<uint32_t>(p.tps) * kTapBytes;
+      for (int pt = cluster_id; pt < num_pt; pt += n_clusters) {
+        int nt, ptt, b;
+        decode(pt, nt, ptt, b);
+        const int t0 = (2 * ptt + static_cast<int>(rank)) * kTileM - p.pad_left;
+        for (int c = 0; c < p.nchunks; ++c) {
+          hg::mbar_wait(&bars->a_empty[a_slot], a_phase ^ 1u);
+          if (rank == 0) hg::mbar_arrive_expect_tx(&bars->a_full[a_slot], 2 * a_bytes);
+          else hg::mbar_arrive_remote(&bars->a_full[a_slot], 0);
+          hg::tma_load_3d_2sm(a_buf + a_slot * p.a_slot_bytes, &tm_x, &bars->a_full[a_slot], c * KC, t0, b);
+          if (++a_slot == static_cast<uint32_t>(p.a_slots)) { a_slot = 0; a_phase ^= 1u; }
+          for (int g = 0; g < p.groups; ++g) {
+            hg::mbar_wait(&bars->w_empty[w_slot], w_phase ^ 1u);
+            if (rank == 0) hg::mbar_arrive_expect_tx(&bars->w_full[w_slot], 2 * w_bytes);
+            else hg::mbar_arrive_remote(&bars->w_full[w_slot], 0);
+            hg::tma_load_3d_2sm(w_buf + w_slot * p.w_stage_bytes, &tm_w, &bars->w_full[w_slot], c * KC,
+                                nt * NT + static_cast<int>(rank) * (NT / 2), g * p.tps);
+            if (++w_slot == static_cast<uint32_t>(p.stages)) { w_slot = 0; w_phase ^= 1u; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ============================ MMA issuer (leader CTA only) ============
+    if (rank == 0) {
+      constexpr uint32_t idesc = hg::umma_idesc_bf16(2 * kTileM, NT);
+      constexpr uint32_t kTapLo = kTapBytes >> 4;
+      const uint32_t desc_hi = hg::umma_desc_hi(kSbo, kLayout);
+      const uint32_t a_tap_step = static_cast<uint32_t>(p.tap_step) * (kRowBytes >> 4);
+      const uint32_t w_lo0 = hg::umma_desc_lo(hg::smem_u32(w_buf));
+      const bool leader = hg::elect_one();
+      uint32_t acc_it = 0, a_slot = 0, a_phase = 0, w_slot = 0, w_phase = 0;
+      for (int pt = cluster_id; pt < num_pt; pt += n_clusters) {
+        const uint32_t acc = acc_it & 1u;
+        hg::mbar_wait(&bars->acc_empty[acc], ((acc_it >> 1) & 1u) ^ 1u);
+        hg::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * NT;
+        uint32_t accumulate = 0;
+        for (int c = 0; c < p.nchunks; ++c) {
+          hg::mbar_wait(&bars->a_full[a_slot], a_phase);
+          hg::tc_fence_after();
+          uint32_t a_lo = hg::umma_desc_lo(hg::smem_u32(a_buf + a_slot * p.a_slot_bytes));
+          int q = 0;
+          for (int g = 0; g < p.groups; ++g) {
+            hg::mbar_wait(&bars->w_full[w_slot], w_phase);
+            hg::tc_fence_after();
+            if (leader) {
+              uint32_t w_lo = w_lo0 + ((w_slot * p.w_stage_bytes) >> 4);
+              const int q_end = min(p.ktaps, q + p.tps);
+              for (int j = q; j < q_end; ++j) {
+#pragma unroll
+                for (int kk = 0; kk < KC / 16; ++kk) {
+                  hg::umma_bf16_ss_lo_2sm(d_tmem, a_lo + kk * 2, w_lo + kk * 2, desc_hi, idesc, accumulate);
+                  accumulate = 1;
+                }
+                a_lo += a_tap_step;
+                w_lo += kTapLo;
+              }
+              hg::umma_commit_2sm(&bars->w_empty[w_slot]);
+            } else {
+              a_lo += a_tap_step * static_cast<uint32_t>(min(p.ktaps, q + p.tps) - q);
+            }
+            accumulate = 1;
+            q += p.tps;
+            __syncwarp();
+            if (++w_slot == static_cast<uint32_t>(p.stages)) { w_slot = 0; w_phase ^= 1u; }
+          }
+          if (leader) hg::umma_commit_2sm(&bars->a_empty[a_slot]);
+          __syncwarp();
+          if (++a_slot == static_cast<uint32_t>(p.a_slots)) { a_slot = 0; a_phase ^= 1u; }
+        }
+        if (leader) hg::umma_commit_2sm(&bars->acc_full[acc]);
+        __syncwarp();
+        ++acc_it;
+      }
+    }
+  } else {
+    // ============================ epilogue (both CTAs, own 128 rows) ======
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    const int row = quarter * 32 + lane;
+    const int col0 = half * kColsPerWarp;
+    uint32_t acc_it = 0;
+    for (int pt = cluster_id; pt < num_pt; pt += n_clusters) {
+      int nt, ptt, b;
+      decode(pt, nt, ptt, b);
+      const int t = (2 * ptt + static_cast<int>(rank)) * kTileM + row;
+      const bool valid = t < p.t;
+      const int ch0 = nt * NT + col0;
+      const size_t off = (static_cast<size_t>(b) * p.t_pitch + (valid ? t : 0)) * p.cout + ch0;
+      hg::U8 rpre[kGroups16];
+      if (p.res0 && valid) {
+#pragma unroll
+        for (int g = 0; g < kGroups16; ++g) rpre[g] = hg::ldg256(p.res0 + off + g * 16);
+      }
+      const uint32_t acc = acc_it & 1u;
+      hg::mbar_wait(&bars->acc_full[acc], (acc_it >> 1) & 1u);
+      hg::tc_fence_after();
+#pragma unroll
+      for (int g = 0; g < kGroups16; ++g) {
+        uint32_t raw[16];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * NT + col0 + g * 16;
+        hg::tmem_ld_32x16(taddr, raw);
+        hg::tmem_ld_wait();
+        if (valid) {
+          float v[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(raw[e]);
+          if (p.bias) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + g * 16 + q * 4));
+              v[4 * q] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
+            }
+          }
+          if (p.res0) hg::add_bf16x16(v, rpre[g]);
+          if (p.res1) hg::add_bf16x16(v, hg::ldg256(p.res1 + off + g * 16));
+          if (p.res2) hg::add_bf16x16(v, hg::ldg256(p.res2 + off + g * 16));
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] *= p.scale;
+          if (p.out_raw) {
+            hg::U8 o;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o.v[i] = hg::pack_bf16x2(v[2 * i], v[2 * i + 1]);
+            hg::stg256(p.out_raw + off + g * 16, o);
+          }
+          if (p.out_act) {
+            hg::U8 o;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              o.v[i] = hg::pack_bf16x2(hg::lrelu(v[2 * i], p.slope), hg::lrelu(v[2 * i + 1], p.slope));
+            hg::stg256(p.out_act + off + g * 16, o);
+          }
+        }
+      }
+      hg::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) hg::mbar_arrive(&bars->acc_empty[acc]);
+        else hg::mbar_arrive_remote(&bars->acc_empty[acc], 0);
+      }
+      ++acc_it;
+    }
+  }
+
+  hg::tc_fence_before();
+  __syncthreads();
+  hg::cluster_sync_all();     // nobody leaves (or frees TMEM) while the peer may still signal / read
+  hg::tc_fence_after();
+  if (warp == 1) hg::tmem_dealloc_2sm(tmem_base, kTmemCols);
+}
+
 int g_num_sms = 0;
 int g_max_smem = 0;
 
@@ -391,6 +635,22 @@ int launch(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const ConvArgs& p, 
   HG_CHECK_CUDA(cudaGetLastError());
   return HG_OK;
 }
+
+template <int NT>
+int launch2(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const ConvArgs& p, size_t smem_bytes, int grid,
+            cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    HG_CHECK_CUDA(cudaFuncSetAttribute(conv1d_tc2_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       g_max_smem));
+    configured = true;
+  }
+  conv1d_tc2_kernel<NT><<<grid, kThreads, smem_bytes, st>>>(tm_x, tm_w, p);   // __cluster_dims__(2,1,1)
+  HG_CHECK_CUDA(cudaGetLastError());
+  return HG_OK;
+}
+
+int g_use_2cta = -1;
 
 // Packed tap order / residue boxes of a (ktaps, stride, dilation, pad_left) convolution.
 struct TapPlan {
@@ -500,6 +760,22 @@ int conv_forward(const void* x, const void* w_packed, const float* bias, int bat
     p.stages = stages;
     w_bytes_total = static_cast<uint32_t>(stages) * p.w_stage_bytes;
   }
+  if (g_use_2cta < 0) g_use_2cta = getenv("HG_DISABLE_2CTA") ? 0 : 1;
+  // CTA-pair path: dense stride-1 layers with streamed weights and wide N tiles (stages 1-2, ups 0-1)
+  const bool pair = g_use_2cta && !p.resident && stride == 1 && !grouped && kc == 64 && n_tile >= 128 &&
+                    (g_num_sms % 2 == 0) && batch * p.tiles_t * p.tiles_n >= g_num_sms;
+  if (pair) {
+    const uint32_t half_tap = tap_bytes / 2;          // each CTA holds half of the filter rows
+    p.tps = half_tap >= 32768 ? 1 : static_cast<int>(32768 / half_tap);
+    if (p.tps > ktaps) p.tps = ktaps;
+    p.groups = (ktaps + p.tps - 1) / p.tps;
+    p.w_stage_bytes = static_cast<uint32_t>(p.tps) * half_tap;
+    int stages = (budget - 2 * static_cast<int>(p.a_slot_bytes)) / static_cast<int>(p.w_stage_bytes);
+    if (stages > 4) stages = 4;
+    HG_REQUIRE(stages >= 2, "conv: not enough shared memory for the weight ring");
+    p.stages = stages;
+    w_bytes_total = static_cast<uint32_t>(stages) * p.w_stage_bytes;
+  }
   int a_slots = (budget - static_cast<int>(w_bytes_total)) / static_cast<int>(p.a_slot_bytes);
   if (a_slots > kMaxASlots) a_slots = kMaxASlots;
   HG_REQUIRE(a_slots >= 2, "conv: not enough shared memory for the activation ring");
@@ -522,13 +798,22 @@ int conv_forward(const void* x, const void* w_packed, const float* bias, int bat
                               static_cast<uint64_t>(t_in_rows) * c_total * 2, kc, a_rows, 1, swz);
   if (rc) return rc;
   rc = hg_encode_tmap_bf16_3d(&tm_w, w_packed, cin_tile, cout, ktaps, static_cast<uint64_t>(cin_tile) * 2,
-                              static_cast<uint64_t>(cout) * cin_tile * 2, kc, n_tile, p.tps, swz);
+                              static_cast<uint64_t>(cout) * cin_tile * 2, kc, pair ? n_tile / 2 : n_tile, p.tps,
+                              swz);
   if (rc) return rc;
 
   const size_t smem_bytes = 1024 + static_cast<size_t>(a_slots) * p.a_slot_bytes + w_bytes_total +
                             sizeof(Barriers);
   const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (pair) {
+    const size_t smem2 = 1024 + static_cast<size_t>(a_slots) * p.a_slot_bytes + w_bytes_total + sizeof(Barriers2);
+    rc = (n_tile == 256) ? launch2<256>(tm_x, tm_w, p, smem2, g_num_sms, st)
+                         : launch2<128>(tm_x, tm_w, p, smem2, g_num_sms, st);
+    if (rc) return rc;
+    g_hg_launches.fetch_add(1, std::memory_order_relaxed);
+    return HG_OK;
+  }
 #define HG_LAUNCH(KC_, NT_) rc = launch<KC_, NT_>(tm_x, tm_w, p, smem_bytes, grid, st)
   if (kc == 64) {
     if (n_tile == 256) HG_LAUNCH(64, 256);

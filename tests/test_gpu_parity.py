@@ -48,6 +48,8 @@ CONV_CASES = [
     (1, 512, 256, 256, 11, 5), (3, 200, 128, 256, 3, 1), (2, 256, 32, 32, 3, 1), (2, 256, 32, 32, 11, 5),
     (2, 256, 32, 64, 7, 3), (1, 100, 128, 512, 7, 1), (1, 1, 64, 64, 3, 1), (2, 129, 64, 32, 5, 12),
     (1, 2048, 128, 128, 7, 12),
+    # large enough (>= 148 tiles, streamed weights, N >= 128) to take the CTA-pair (cta_group::2) kernel
+    (8, 4224, 128, 128, 7, 3), (4, 8192, 256, 256, 3, 1), (2, 10000, 256, 512, 11, 5), (5, 4000, 128, 256, 5, 1),
 ]
 
 
