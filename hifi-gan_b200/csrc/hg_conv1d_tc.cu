@@ -313,6 +313,20 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 #pragma unroll
         for (int g = 0; g < kGroups16; ++g) rpre[g] = hg::ldg256(p.res0 + off + g * 16);
       }
+      // the MRF-final launch adds two more tensors: fetch them up front as well when the registers allow
+      // (loading them at the point of use exposed their latency: +0.3 .. +1.2 ms on those launches)
+      constexpr bool kPreAll = kGroups16 <= 4;
+      hg::U8 rpre1[kPreAll ? kGroups16 : 1], rpre2[kPreAll ? kGroups16 : 1];
+      if (kPreAll && valid) {
+        if (p.res1) {
+#pragma unroll
+          for (int g = 0; g < kGroups16; ++g) rpre1[kPreAll ? g : 0] = hg::ldg256(p.res1 + off + g * 16);
+        }
+        if (p.res2) {
+#pragma unroll
+          for (int g = 0; g < kGroups16; ++g) rpre2[kPreAll ? g : 0] = hg::ldg256(p.res2 + off + g * 16);
+        }
+      }
       const uint32_t acc = acc_it & 1u;
       hg::mbar_wait(&bars->acc_full[acc], (acc_it >> 1) & 1u);
       hg::tc_fence_after();
@@ -335,8 +349,8 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             }
           }
           if (p.res0) hg::add_bf16x16(v, rpre[g]);
-          if (p.res1) hg::add_bf16x16(v, hg::ldg256(p.res1 + off + g * 16));
-          if (p.res2) hg::add_bf16x16(v, hg::ldg256(p.res2 + off + g * 16));
+          if (p.res1) hg::add_bf16x16(v, kPreAll ? rpre1[kPreAll ? g : 0] : hg::ldg256(p.res1 + off + g * 16));
+          if (p.res2) hg::add_bf16x16(v, kPreAll ? rpre2[kPreAll ? g : 0] : hg::ldg256(p.res2 + off + g * 16));
 #pragma unroll
           for (int e = 0; e < 16; ++e) v[e] *= p.scale;
           if (p.out_raw) {
@@ -553,6 +567,20 @@ conv1d_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
         for (int g = 0; g < kGroups16; ++g) rpre[g] = hg::ldg256(p.res0 + off + g * 16);
       }
+      // the MRF-final launch adds two more tensors: fetch them up front as well when the registers allow
+      // (loading them at the point of use exposed their latency: +0.3 .. +1.2 ms on those launches)
+      constexpr bool kPreAll = kGroups16 <= 4;
+      hg::U8 rpre1[kPreAll ? kGroups16 : 1], rpre2[kPreAll ? kGroups16 : 1];
+      if (kPreAll && valid) {
+        if (p.res1) {
+#pragma unroll
+          for (int g = 0; g < kGroups16; ++g) rpre1[kPreAll ? g : 0] = hg::ldg256(p.res1 + off + g * 16);
+        }
+        if (p.res2) {
+#pragma unroll
+          for (int g = 0; g < kGroups16; ++g) rpre2[kPreAll ? g : 0] = hg::ldg256(p.res2 + off + g * 16);
+        }
+      }
       const uint32_t acc = acc_it & 1u;
       hg::mbar_wait(&bars->acc_full[acc], (acc_it >> 1) & 1u);
       hg::tc_fence_after();
@@ -574,8 +602,8 @@ conv1d_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             }
           }
           if (p.res0) hg::add_bf16x16(v, rpre[g]);
-          if (p.res1) hg::add_bf16x16(v, hg::ldg256(p.res1 + off + g * 16));
-          if (p.res2) hg::add_bf16x16(v, hg::ldg256(p.res2 + off + g * 16));
+          if (p.res1) hg::add_bf16x16(v, kPreAll ? rpre1[kPreAll ? g : 0] : hg::ldg256(p.res1 + off + g * 16));
+          if (p.res2) hg::add_bf16x16(v, kPreAll ? rpre2[kPreAll ? g : 0] : hg::ldg256(p.res2 + off + g * 16));
 #pragma unroll
           for (int e = 0; e < 16; ++e) v[e] *= p.scale;
           if (p.out_raw) {

@@ -362,6 +362,18 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             for (int g = 0; g < kG; ++g) rnext[g] = hg::ldg256(p.x + off_next + g * 16);
           }
         }
+        // MRF-final launch: the two extra addends of this unit, issued before the accumulator wait
+        // (C = 64 runs 704 threads under an 80-register cap: it keeps loading them at the point of use)
+        constexpr bool kPreRes = (C == 32);
+        hg::U8 r1[kPreRes ? kG : 1], r2[kPreRes ? kG : 1];
+        if (kPreRes && valid && p.res1) {
+#pragma unroll
+          for (int g = 0; g < kG; ++g) r1[kPreRes ? g : 0] = hg::ldg256(p.res1 + off + g * 16);
+        }
+        if (kPreRes && valid && p.res2) {
+#pragma unroll
+          for (int g = 0; g < kG; ++g) r2[kPreRes ? g : 0] = hg::ldg256(p.res2 + off + g * 16);
+        }
         if (m == 0) {
           hg::mbar_wait(&full_bar[a], ph);
           hg::tc_fence_after();
@@ -387,8 +399,8 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
               v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + bq.w;
             }
             hg::add_bf16x16(v, rcur[g]);
-            if (p.res1) hg::add_bf16x16(v, hg::ldg256(p.res1 + off + g * 16));
-            if (p.res2) hg::add_bf16x16(v, hg::ldg256(p.res2 + off + g * 16));
+            if (p.res1) hg::add_bf16x16(v, kPreRes ? r1[kPreRes ? g : 0] : hg::ldg256(p.res1 + off + g * 16));
+            if (p.res2) hg::add_bf16x16(v, kPreRes ? r2[kPreRes ? g : 0] : hg::ldg256(p.res2 + off + g * 16));
 #pragma unroll
             for (int e = 0; e < 16; ++e) v[e] *= p.scale;
             if (p.out_raw) {
