@@ -123,9 +123,10 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------- CPU baseline (oracle)
 def cpu_generator_baseline(version: str, frames: int, batch: int, steps: int, warmup: int):
     """The oracle port (torch CPU fp32 = the very ops the reference's CPU path runs) on a bounded sample."""
-    from oracle import hifigan_oracle as O
+    from oracle import hifigan_oracle as O   # the timed CPU implementation (allowed here: cpu_baseline leg)
     import hifigan_b200 as H
-    h = O.config(version)
+    from hifigan_b200.configs import load_config
+    h = load_config(version)
     torch.manual_seed(1234)
     G = H.Generator(H.AttrDict(h))  # parameter container only; never run on the CPU
     G.remove_weight_norm()
@@ -174,7 +175,7 @@ def run_reference(args, rank, world):
 def run_ours(args, rank, world, local_rank):
     import hifigan_b200 as H
     from hifigan_b200 import _lib
-    from oracle import hifigan_oracle as O  # configs + the cpu_baseline leg only
+    from hifigan_b200.configs import load_config
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — hifigan_b200 has no CPU path")
@@ -182,7 +183,7 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     wl = WORKLOADS[args.workload]
     ver, batch, frames = wl["version"], wl["batch"], wl["frames"]
-    h = H.AttrDict(O.config(ver))
+    h = load_config(ver)
     torch.manual_seed(1234)
     G = H.Generator(h).to(dev).eval()
     G.remove_weight_norm()

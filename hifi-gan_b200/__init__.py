@@ -1,5 +1,6 @@
 """hifigan_b200 — B200-native (sm_100a) HiFi-GAN vocoder hot path behind the reference's module API."""
 from . import _lib  # noqa: F401
+from .configs import load_config  # noqa: F401
 from .env import AttrDict, build_env  # noqa: F401
 from .meldataset import MAX_WAV_VALUE, SegmentSampler, mel_spectrogram  # noqa: F401
 from .models import (LRELU_SLOPE, DiscriminatorP, DiscriminatorS, Generator,  # noqa: F401

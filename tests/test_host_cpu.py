@@ -201,3 +201,12 @@ def test_reference_style_top_level_imports():
     env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "hifi-gan_b200", "compat") + os.pathsep + ROOT)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd="/tmp")
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr
+
+
+def test_shipped_configs_match_upstream_values():
+    """config_v1/v2/v3.json (deleted by the fork, restated here) carry the keys Generator consumes."""
+    for v in ("v1", "v2", "v3"):
+        h, ref = H.load_config(v), O.config(v)
+        assert all(h[k] == ref[k] for k in ref)
+        H.Generator(h)
+    assert H.load_config("v3").resblock == "2" and H.load_config("v1").upsample_initial_channel == 512
