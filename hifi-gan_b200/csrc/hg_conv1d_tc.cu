@@ -69,6 +69,13 @@ struct ConvArgs {
   __nv_bfloat16* out_raw;
   __nv_bfloat16* out_act;
   float slope;
+  // backward-pass epilogue terms (hg_conv1d_dgrad): v = (acc + bias + fm_coef * sgn(fm_g - fm_r)) * lrelu'(mask) + res...
+  const __nv_bfloat16* mask;     // activation whose sign selects 1 / mask_slope (leaky_relu backward)
+  float mask_slope;
+  const __nv_bfloat16* fm_r;     // feature-matching L1 term (src/models.py:251-257): d|r - g|/dg = sgn(g - r)
+  const __nv_bfloat16* fm_g;
+  float fm_coef;
+  int group_mod;                 // grouped: N tile nt reads input channel block (nt % group_mod)
 };
 
 struct Barriers {
@@ -181,7 +188,7 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       for (TileIter it(p); it.tile < p.num_tiles; it.next()) {
         const int nt = it.nt, b = it.b;
         const int t0 = it.tt * kTileM;
-        const int chan0 = p.grouped ? nt * p.cin : 0;
+        const int chan0 = p.grouped ? (nt % p.group_mod) * p.cin : 0;
         for (int c = 0; c < p.nchunks; ++c) {
           int in_stage = 0;   // position of the next packed tap inside its weight stage (no modulo per tap)
           for (int bx = 0; bx < p.nboxes; ++bx) {
@@ -346,6 +353,24 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             for (int q = 0; q < 4; ++q) {
               const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + g * 16 + q * 4));
               v[4 * q] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
+            }
+          }
+          if (p.fm_g) {
+            const hg::U8 fg = hg::ldg256(p.fm_g + off + g * 16), fr = hg::ldg256(p.fm_r + off + g * 16);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float2 a = hg::unpack_bf16x2(fg.v[i]), r = hg::unpack_bf16x2(fr.v[i]);
+              v[2 * i] += p.fm_coef * ((a.x > r.x) ? 1.f : (a.x < r.x) ? -1.f : 0.f);
+              v[2 * i + 1] += p.fm_coef * ((a.y > r.y) ? 1.f : (a.y < r.y) ? -1.f : 0.f);
+            }
+          }
+          if (p.mask) {
+            const hg::U8 mk = hg::ldg256(p.mask + off + g * 16);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float2 a = hg::unpack_bf16x2(mk.v[i]);
+              if (!(a.x > 0.f)) v[2 * i] *= p.mask_slope;
+              if (!(a.y > 0.f)) v[2 * i + 1] *= p.mask_slope;
             }
           }
           if (p.res0) hg::add_bf16x16(v, rpre[g]);
@@ -601,6 +626,24 @@ conv1d_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               v[4 * q] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
             }
           }
+          if (p.fm_g) {
+            const hg::U8 fg = hg::ldg256(p.fm_g + off + g * 16), fr = hg::ldg256(p.fm_r + off + g * 16);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float2 a = hg::unpack_bf16x2(fg.v[i]), r = hg::unpack_bf16x2(fr.v[i]);
+              v[2 * i] += p.fm_coef * ((a.x > r.x) ? 1.f : (a.x < r.x) ? -1.f : 0.f);
+              v[2 * i + 1] += p.fm_coef * ((a.y > r.y) ? 1.f : (a.y < r.y) ? -1.f : 0.f);
+            }
+          }
+          if (p.mask) {
+            const hg::U8 mk = hg::ldg256(p.mask + off + g * 16);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float2 a = hg::unpack_bf16x2(mk.v[i]);
+              if (!(a.x > 0.f)) v[2 * i] *= p.mask_slope;
+              if (!(a.y > 0.f)) v[2 * i + 1] *= p.mask_slope;
+            }
+          }
           if (p.res0) hg::add_bf16x16(v, rpre[g]);
           if (p.res1) hg::add_bf16x16(v, kPreAll ? rpre1[kPreAll ? g : 0] : hg::ldg256(p.res1 + off + g * 16));
           if (p.res2) hg::add_bf16x16(v, kPreAll ? rpre2[kPreAll ? g : 0] : hg::ldg256(p.res2 + off + g * 16));
@@ -723,11 +766,21 @@ int make_tap_plan(int ktaps, int stride, int dilation, int pad_left, TapPlan* tp
   return 0;
 }
 
+struct ConvExtra {
+  const void* mask = nullptr;
+  float mask_slope = 1.f;
+  const void* fm_r = nullptr;
+  const void* fm_g = nullptr;
+  float fm_coef = 0.f;
+  int group_mod = 0;      // 0: one input channel block per N tile (forward grouped convs)
+  int t_in_valid = -1;    // stride 1 only: input rows >= this are read as zero (TMA bound); -1 = t_in_rows
+};
+
 int conv_forward(const void* x, const void* w_packed, const float* bias, int batch, int t_in_rows,
                  int c_total, int t_out, int t_out_rows, int cin_tile, int cout, int n_tile, int grouped, int ktaps,
                  int stride, int dilation, int pad_left, const void* res0, const void* res1,
                  const void* res2, float scale, void* out_raw, void* out_act, float act_slope,
-                 void* stream) {
+                 void* stream, const ConvExtra& ex = ConvExtra()) {
   HG_REQUIRE(x && w_packed, "conv: null input");
   HG_REQUIRE(out_raw || out_act, "conv: no output requested");
   HG_REQUIRE(batch > 0 && t_out > 0 && t_in_rows > 0, "conv: empty batch/time");
@@ -817,11 +870,20 @@ int conv_forward(const void* x, const void* w_packed, const float* bias, int bat
   p.out_raw = static_cast<__nv_bfloat16*>(out_raw);
   p.out_act = static_cast<__nv_bfloat16*>(out_act);
   p.slope = act_slope;
+  p.mask = static_cast<const __nv_bfloat16*>(ex.mask);
+  p.mask_slope = ex.mask_slope;
+  p.fm_r = static_cast<const __nv_bfloat16*>(ex.fm_r);
+  p.fm_g = static_cast<const __nv_bfloat16*>(ex.fm_g);
+  p.fm_coef = ex.fm_coef;
+  p.group_mod = ex.group_mod > 0 ? ex.group_mod : p.tiles_n;
+  HG_REQUIRE(!p.fm_g || p.fm_r, "conv: fm_g without fm_r");
+  HG_REQUIRE(ex.t_in_valid < 0 || (stride == 1 && ex.t_in_valid <= t_in_rows), "conv: bad input bound");
+  const int t_in_bound = ex.t_in_valid >= 0 ? ex.t_in_valid : t_in_rows / stride;
 
   CUtensorMap tm_x, tm_w;
   const int swz = kc * 2;
   // activations through the strided view [B][T_in/stride][stride*C_total]
-  rc = hg_encode_tmap_bf16_3d(&tm_x, x, static_cast<uint64_t>(stride) * c_total, t_in_rows / stride, batch,
+  rc = hg_encode_tmap_bf16_3d(&tm_x, x, static_cast<uint64_t>(stride) * c_total, t_in_bound, batch,
                               static_cast<uint64_t>(stride) * c_total * 2,
                               static_cast<uint64_t>(t_in_rows) * c_total * 2, kc, a_rows, 1, swz);
   if (rc) return rc;
@@ -901,4 +963,37 @@ extern "C" int hg_conv1d_general_fwd(const void* x, const void* w_packed, const 
                       ktaps,
                       stride, 1, pad_left, nullptr, nullptr, nullptr, 1.f, out_raw, out_act, act_slope,
                       stream);
+}
+
+// hg_conv1d_dgrad — data gradient of a conv layer, run on the same implicit-GEMM kernel: the gradient of a
+// stride-1 dilated conv is a conv with flipped taps and transposed filters (hg_pack_dgrad_weight), the gradient
+// of a strided conv (or the forward of its transpose) is its polyphase form (hg_pack_convtr1d_weight on the
+// conv weight).  The epilogue applies the leaky_relu backward mask of the layer input, the feature-matching L1
+// term and up to two gradient addends (residual path / MRF branch sum):
+//   out[b,t,n] = ((sum_{j,c} dy[b, t + j*dil - pad_left, blk(n) + c] * w[j][n][c] + fm_coef * sgn(fm_g - fm_r))
+//                 * (mask_src > 0 ? 1 : mask_slope) + res0 + res1) * scale
+extern "C" int hg_conv1d_dgrad(const void* dy, const void* w_packed, int batch, int t_dy_valid, int t_dy_rows,
+                               int c_dy_total, int t_out, int t_out_rows, int groups, int n_tile, int cout, int ktaps,
+                               int dilation, int pad_left, const void* mask_src, float mask_slope,
+                               const void* fm_r, const void* fm_g, float fm_coef, const void* res0, const void* res1,
+                               float scale, void* out, void* stream) {
+  HG_REQUIRE(groups >= 1 && c_dy_total % groups == 0, "hg_conv1d_dgrad: bad groups");
+  HG_REQUIRE(ktaps > 0 && dilation > 0 && 128 + (ktaps - 1) * dilation <= 256,
+             "hg_conv1d_dgrad: halo too large for one TMA box (taps=%d dilation=%d)", ktaps, dilation);
+  ConvExtra ex;
+  ex.mask = mask_src; ex.mask_slope = mask_slope;
+  ex.fm_r = fm_r; ex.fm_g = fm_g; ex.fm_coef = fm_coef;
+  ex.t_in_valid = t_dy_valid;
+  const int cin_tile = c_dy_total / groups;
+  if (groups == 1) {
+    if (n_tile <= 0) n_tile = (cout % 256 == 0) ? 256 : (cout % 128 == 0) ? 128 : (cout % 64 == 0) ? 64 : 32;
+    return conv_forward(dy, w_packed, nullptr, batch, t_dy_rows, c_dy_total, t_out, t_out_rows, cin_tile, cout,
+                        n_tile, 0, ktaps, 1, dilation, pad_left, res0, res1, nullptr, scale, out, nullptr, 1.f,
+                        stream, ex);
+  }
+  HG_REQUIRE(n_tile > 0, "hg_conv1d_dgrad: grouped layers need an explicit N tile");
+  ex.group_mod = groups;
+  return conv_forward(dy, w_packed, nullptr, batch, t_dy_rows, c_dy_total, t_out, t_out_rows, cin_tile, cout,
+                      n_tile, 1, ktaps, 1, dilation, pad_left, res0, res1, nullptr, scale, out, nullptr, 1.f,
+                      stream, ex);
 }

@@ -374,6 +374,94 @@ extern "C" int hg_mel_fwd(const hg_mel_plan* plan, const float* y, int batch, in
 }
 
 // ---------------------------------------------------------------------------------------------
+// mel_spectrogram backward (the generated-mel L1 term of the generator loss, UPSTREAM train.py: F.l1_loss(y_mel,
+// y_g_hat_mel) * 45 through src/meldataset.py:78-83).  One block per frame: recompute the windowed frame's
+// 513-bin spectrum with a direct DFT (training segments are 32 frames per item: 2 MFLOP per frame is nothing),
+// push dL/dlogmel back through log-clamp, the CSR filterbank and |X|^2, take the adjoint DFT, window, and
+// scatter-add into dy with the reflect padding folded back.
+namespace {
+
+__global__ void __launch_bounds__(256)
+mel_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dmel, int t, int frames, int hop, int pad,
+               int num_mels, const float* __restrict__ window, const int* __restrict__ mel_start,
+               const int* __restrict__ mel_off, const float* __restrict__ mel_w, float* __restrict__ dy) {
+  __shared__ float xw[kNfft];
+  __shared__ float2 tw[kNfft];
+  __shared__ float re[kHalf + 1], im[kHalf + 1], dp[kHalf + 1];
+  __shared__ float dm[128];
+  const int f = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const float* yb = y + static_cast<size_t>(b) * t;
+  for (int n = tid; n < kNfft; n += 256) {
+    int i = f * hop + n - pad;
+    if (i < 0) i = -i;
+    if (i >= t) i = 2 * (t - 1) - i;
+    xw[n] = yb[i] * window[n];
+    float sn, cs;
+    sincospif(static_cast<float>(n) * (2.0f / kNfft), &sn, &cs);
+    tw[n] = make_float2(cs, sn);
+  }
+  for (int k = tid; k <= kHalf; k += 256) dp[k] = 0.f;
+  __syncthreads();
+  for (int k = tid; k <= kHalf; k += 256) {
+    float ar = 0.f, ai = 0.f;
+    for (int n = 0; n < kNfft; ++n) {
+      const float2 c = tw[(k * n) & (kNfft - 1)];
+      ar += xw[n] * c.x;
+      ai -= xw[n] * c.y;
+    }
+    re[k] = ar; im[k] = ai;
+  }
+  __syncthreads();
+  if (tid < num_mels) {
+    const int k0 = mel_start[tid], o0 = mel_off[tid], cnt = mel_off[tid + 1] - o0;
+    float m = 0.f;
+    for (int i = 0; i < cnt; ++i) m += mel_w[o0 + i] * (re[k0 + i] * re[k0 + i] + im[k0 + i] * im[k0 + i]);
+    const float g = dmel[(static_cast<size_t>(b) * num_mels + tid) * frames + f];
+    dm[tid] = m > 1e-5f ? g / m : 0.f;      // clamp(min=1e-5) passes no gradient below the floor
+  }
+  __syncthreads();
+  if (tid < num_mels) {
+    const int k0 = mel_start[tid], o0 = mel_off[tid], cnt = mel_off[tid + 1] - o0;
+    for (int i = 0; i < cnt; ++i) atomicAdd(&dp[k0 + i], mel_w[o0 + i] * dm[tid]);
+  }
+  __syncthreads();
+  for (int k = tid; k <= kHalf; k += 256) {
+    const float g = 2.f * dp[k];
+    re[k] *= g; im[k] *= g;                 // dL/dRe, dL/dIm
+  }
+  __syncthreads();
+  for (int n = tid; n < kNfft; n += 256) {
+    float a = 0.f;
+    for (int k = 0; k <= kHalf; ++k) {
+      const float2 c = tw[(k * n) & (kNfft - 1)];
+      a += re[k] * c.x - im[k] * c.y;
+    }
+    int i = f * hop + n - pad;
+    if (i < 0) i = -i;
+    if (i >= t) i = 2 * (t - 1) - i;
+    atomicAdd(dy + static_cast<size_t>(b) * t + i, a * window[n]);
+  }
+}
+
+}  // namespace
+
+extern "C" int hg_mel_bwd(const hg_mel_plan* plan, const float* y, const float* dmel, int batch, int t, float* dy,
+                          void* stream) {
+  HG_REQUIRE(plan && y && dmel && dy, "hg_mel_bwd: null pointer");
+  HG_REQUIRE(plan->window, "hg_mel_bwd: plan has no device tables");
+  HG_REQUIRE(batch > 0 && batch <= 65535 && t > plan->pad && plan->num_mels <= 128, "hg_mel_bwd: bad arguments");
+  const int frames = hg_mel_num_frames(plan, t);
+  HG_REQUIRE(frames > 0, "hg_mel_bwd: input too short for one frame");
+  dim3 grid(frames, batch);
+  mel_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, dmel, t, frames, plan->hop, plan->pad,
+                                                                      plan->num_mels, plan->window, plan->mel_start,
+                                                                      plan->mel_off, plan->mel_w, dy);
+  HG_CHECK_CUDA(cudaGetLastError());
+  g_hg_launches.fetch_add(1, std::memory_order_relaxed);
+  return HG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // CPU emulation of the kernel's arithmetic (same phase functions, threads serialised).  Test-only
 // entry point: lets the CPU test-suite pin the FFT / un-pack / CSR-mel logic without a GPU.
 // y, out are HOST pointers here.

@@ -1,0 +1,584 @@
+// hg_train.cu — the bandwidth-bound pieces of the training step (UPSTREAM train.py restated in SURVEY.md §3.3;
+// every op below is what torch autograd / torch.optim would run for the reference's src/models.py modules):
+//   * dgrad weight packing (tap flip + filter transpose), bias gradients (column sums)
+//   * conv_post + tanh backward (src/models.py:112-114), the Cin = 1 / Cout = 1 discriminator ends' backward
+//     (src/models.py:134,141,146-151,196,204), AvgPool1d(4,2,2) backward (:227-230)
+//   * loss gradients (src/models.py:251-282 + the mel L1), L1 sums over internal bf16 feature maps
+//   * unpacking of hg_conv1d_wgrad results to the parameter layout, weight_norm backward
+//     (torch._weight_norm_interface_backward; reparametrisation at src/models.py:16-31,81,86-88,96,132-140)
+//   * AdamW (torch.optim.AdamW semantics, decoupled weight decay)
+#include "hg_common.cuh"
+
+#include <atomic>
+
+#include "../../include/hifigan_b200.h"
+
+extern std::atomic<int64_t> g_hg_launches;
+
+namespace {
+
+inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+inline void count() { g_hg_launches.fetch_add(1, std::memory_order_relaxed); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float s = 0.f;
+  for (int i = 0; i < nw; ++i) s += red[i];
+  __syncthreads();
+  return s;
+}
+__device__ __forceinline__ float sgn(float d) { return d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f); }
+
+// bf16 [k][n][c] -> bf16 [k][c][n] with the taps reversed: the filter bank of the data gradient
+__global__ void pack_dgrad_kernel(const __nv_bfloat16* __restrict__ w, int k, int n, int c,
+                                  __nv_bfloat16* __restrict__ out) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const int j = blockIdx.z;
+  const int c0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int i = ty; i < 32; i += 8)
+    if (n0 + i < n && c0 + tx < c) tile[i][tx] = w[(static_cast<size_t>(j) * n + n0 + i) * c + c0 + tx];
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8)
+    if (c0 + i < c && n0 + tx < n)
+      out[(static_cast<size_t>(k - 1 - j) * c + c0 + i) * n + n0 + tx] = tile[tx][i];
+}
+
+// out[c] (+)= sum over (b, t < t_valid) of x[b][t][c];  x bf16 [B][t_rows][C]
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ x, int t_valid, int t_rows, int c, int rows_per_block,
+              float* __restrict__ out) {
+  // thread = (row lane, 8-channel vector); block covers rows_per_block rows of one batch item
+  const int vecs = c / 8;
+  const int b = blockIdx.y;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(t_valid, r0 + rows_per_block);
+  const int lanes = blockDim.x / vecs;           // rows processed in parallel (vecs <= 256)
+  const int vq = threadIdx.x % vecs, rl = threadIdx.x / vecs;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (rl < lanes) {
+    for (int r = r0 + rl; r < r1; r += lanes) {
+      const uint4 v = *reinterpret_cast<const uint4*>(x + (static_cast<size_t>(b) * t_rows + r) * c + vq * 8);
+      const float2 a0 = hg::unpack_bf16x2(v.x), a1 = hg::unpack_bf16x2(v.y), a2 = hg::unpack_bf16x2(v.z),
+                   a3 = hg::unpack_bf16x2(v.w);
+      acc[0] += a0.x; acc[1] += a0.y; acc[2] += a1.x; acc[3] += a1.y;
+      acc[4] += a2.x; acc[5] += a2.y; acc[6] += a3.x; acc[7] += a3.y;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (acc[e] != 0.f) atomicAdd(out + vq * 8 + e, acc[e]);
+  }
+}
+
+// conv_post + tanh backward, data half: dpre = dy * (1 - y^2);
+// dx[b,t,c] = lrelu'(x[b,t,c]; slope) * sum_j dpre[b, t - j + pad] * w[c][j]     (x = the activated conv_post input)
+__global__ void __launch_bounds__(256)
+conv_post_bwd_dx_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                        const float* __restrict__ y, const float* __restrict__ dy, int t, int c, int k,
+                        float slope, __nv_bfloat16* __restrict__ dx, float* __restrict__ dpre_out) {
+  extern __shared__ float smf[];
+  float* ws = smf;                 // [c][k]
+  float* dp = smf + c * k;         // [256 + k - 1]
+  const int b = blockIdx.y, t0 = blockIdx.x * 256, pad = k / 2;
+  for (int i = threadIdx.x; i < c * k; i += blockDim.x) ws[i] = w[i];
+  for (int i = threadIdx.x; i < 256 + k - 1; i += blockDim.x) {
+    const int tt = t0 + i - (k - 1 - pad);
+    float v = 0.f;
+    if (tt >= 0 && tt < t) {
+      const float yy = y[static_cast<size_t>(b) * t + tt];
+      v = dy[static_cast<size_t>(b) * t + tt] * (1.f - yy * yy);
+    }
+    dp[i] = v;
+  }
+  __syncthreads();
+  const int tt = t0 + threadIdx.x;
+  if (tt >= t) return;
+  if (dpre_out) dpre_out[static_cast<size_t>(b) * t + tt] = dp[threadIdx.x + (k - 1 - pad)];
+  const __nv_bfloat16* xr = x + (static_cast<size_t>(b) * t + tt) * c;
+  __nv_bfloat16* dr = dx + (static_cast<size_t>(b) * t + tt) * c;
+  for (int c0 = 0; c0 < c; c0 += 8) {
+    const uint4 xv = *reinterpret_cast<const uint4*>(xr + c0);
+    const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      float g2[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int cc = c0 + 2 * h + e;
+        float a = 0.f;
+        // input position tt feeds output tt - j + pad through tap j
+        for (int j = 0; j < k; ++j) a += dp[threadIdx.x + (k - 1 - pad) - j + pad] * ws[cc * k + j];
+        g2[e] = a;
+      }
+      const float2 xs = hg::unpack_bf16x2(xw[h]);
+      if (!(xs.x > 0.f)) g2[0] *= slope;
+      if (!(xs.y > 0.f)) g2[1] *= slope;
+      ow[h] = hg::pack_bf16x2(g2[0], g2[1]);
+    }
+    *reinterpret_cast<uint4*>(dr + c0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
+}
+
+// weight half: dw[c][j] += sum_{b,t} dpre[b,t] * x[b, t + j - pad, c];  db += sum dpre
+__global__ void __launch_bounds__(256)
+conv_post_bwd_dw_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ dpre, int t, int c, int k,
+                        int tile, float* __restrict__ dw, float* __restrict__ db) {
+  extern __shared__ float smf[];
+  float* dp = smf;                                   // [tile]
+  __shared__ float red[32];
+  const int b = blockIdx.y, t0 = blockIdx.x * tile, pad = k / 2;
+  float bsum = 0.f;
+  for (int i = threadIdx.x; i < tile; i += blockDim.x) {
+    const int tt = t0 + i;
+    const float v = tt < t ? dpre[static_cast<size_t>(b) * t + tt] : 0.f;
+    dp[i] = v;
+    bsum += v;
+  }
+  __syncthreads();
+  bsum = block_sum(bsum, red);
+  if (threadIdx.x == 0 && db) atomicAdd(db, bsum);
+  for (int idx = threadIdx.x; idx < c * k; idx += blockDim.x) {
+    const int j = idx / c, cc = idx % c;             // adjacent threads read adjacent channels
+    float a = 0.f;
+    for (int i = 0; i < tile; ++i) {
+      const int ti = t0 + i + j - pad;
+      if (ti >= 0 && ti < t) a += dp[i] * __bfloat162float(x[(static_cast<size_t>(b) * t + ti) * c + cc]);
+    }
+    atomicAdd(dw + cc * k + j, a);
+  }
+}
+
+// discriminator conv_post (Cout = 1) backward.
+// data half: dx[s,h,c] = (sum_j dl[s, h - j + pad] * w[c][j] + fm_coef * sgn(fm_g - fm_r)) * lrelu'(x[s,h,c])
+__global__ void __launch_bounds__(256)
+disc_last_bwd_dx_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                        const float* __restrict__ dl, int h, int h_rows, int c, int k, float slope,
+                        const __nv_bfloat16* __restrict__ fm_r, float fm_coef, __nv_bfloat16* __restrict__ dx) {
+  const int s = blockIdx.y, ho = blockIdx.x, pad = k / 2;
+  float d[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int o = ho - j + pad;
+    d[j] = (j < k && o >= 0 && o < h) ? dl[static_cast<size_t>(s) * h + o] : 0.f;
+  }
+  const size_t off = (static_cast<size_t>(s) * h_rows + ho) * c;
+  for (int cc = threadIdx.x; cc < c; cc += blockDim.x) {
+    float a = 0.f;
+    for (int j = 0; j < k; ++j) a += d[j] * w[cc * k + j];
+    const float xv = __bfloat162float(x[off + cc]);
+    if (fm_r) a += fm_coef * sgn(xv - __bfloat162float(fm_r[off + cc]));
+    if (!(xv > 0.f)) a *= slope;
+    dx[off + cc] = __float2bfloat16(a);
+  }
+}
+// weight half: dw[c][j] += sum_{s,h} dl[s,h] * x[s, h + j - pad, c]; db += sum dl.  One block per channel slab.
+__global__ void __launch_bounds__(256)
+disc_last_bwd_dw_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ dl, int nseq, int h,
+                        int h_rows, int c, int k, float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float red[32];
+  const int cc = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pad = k / 2;
+  const int s0 = blockIdx.y, sstep = gridDim.y;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float bsum = 0.f;
+  for (int s = s0; s < nseq; s += sstep) {
+    for (int ho = 0; ho < h; ++ho) {
+      const float d = dl[static_cast<size_t>(s) * h + ho];
+      bsum += d;
+      if (cc < c) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int hi = ho + j - pad;
+          if (j < k && hi >= 0 && hi < h)
+            acc[j] += d * __bfloat162float(x[(static_cast<size_t>(s) * h_rows + hi) * c + cc]);
+        }
+      }
+    }
+  }
+  if (cc < c)
+    for (int j = 0; j < k; ++j) atomicAdd(dw + cc * k + j, acc[j]);
+  if (blockIdx.x == 0 && db) {
+    // every thread accumulated the same bsum; take one
+    (void)red;
+    if (threadIdx.x == 0) atomicAdd(db, bsum);
+  }
+}
+
+// discriminator first conv (Cin = 1) backward.  dpre bf16 [S][h_rows][cout] is the gradient at the conv output
+// (leaky_relu mask already applied by the producer).  One thread = one output position.
+//   dw[co][j] += sum dpre[s,ho,co] * yin(s, ho*stride + j - pad);  db[co] += sum dpre
+//   dy[b, i]  += sum_{co,j} dpre[s,ho,co] * w[co][j]   (reflect-padded tail folded back, src/models.py:146-151)
+__global__ void __launch_bounds__(128)
+disc_first_bwd_kernel(const float* __restrict__ y, const float* __restrict__ w, const __nv_bfloat16* __restrict__ dpre,
+                      int t, int period, int h_in, int h_out, int h_rows, int k, int stride, int pad, int cout,
+                      float* __restrict__ dw, float* __restrict__ db, float* __restrict__ dy) {
+  extern __shared__ float smf[];
+  float* ws = smf;                    // [k][cout]
+  float* acc_w = smf + k * cout;      // [k][cout] block partial sums
+  float* acc_b = acc_w + k * cout;    // [cout]
+  for (int i = threadIdx.x; i < k * cout; i += blockDim.x) {
+    const int j = i / cout, co = i % cout;
+    ws[i] = w[co * k + j];
+    acc_w[i] = 0.f;
+  }
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) acc_b[i] = 0.f;
+  __syncthreads();
+  const int seq = blockIdx.y;
+  const int b = seq / period, wcol = seq % period;
+  const int ho = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = ho < h_out;
+  float xin[16];
+  int xidx[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float v = 0.f;
+    int idx = -1;
+    if (live && j < k) {
+      const int hh = ho * stride + j - pad;
+      if (hh >= 0 && hh < h_in) {
+        int i = hh * period + wcol;
+        if (i >= t) i = 2 * (t - 1) - i;
+        idx = i;
+        v = y[static_cast<size_t>(b) * t + i];
+      }
+    }
+    xin[j] = v; xidx[j] = idx;
+  }
+  float gy[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) gy[j] = 0.f;
+  const __nv_bfloat16* drow = dpre + (static_cast<size_t>(seq) * h_rows + (live ? ho : 0)) * cout;
+  const int lane = threadIdx.x & 31;
+  for (int co = 0; co < cout; ++co) {
+    const float d = live ? __bfloat162float(drow[co]) : 0.f;
+    if (dw) {
+      const float bs = warp_sum(d);
+      if (lane == 0) atomicAdd(acc_b + co, bs);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (j < k) {
+          const float s = warp_sum(d * xin[j]);
+          if (lane == 0) atomicAdd(acc_w + j * cout + co, s);
+        }
+      }
+    }
+    if (dy) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j < k) gy[j] += d * ws[j * cout + co];
+    }
+  }
+  if (dy && live) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < k && xidx[j] >= 0) atomicAdd(dy + static_cast<size_t>(b) * t + xidx[j], gy[j]);
+  }
+  if (dw) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < k * cout; i += blockDim.x) {
+      const int j = i / cout, co = i % cout;
+      atomicAdd(dw + co * k + j, acc_w[i]);
+    }
+    for (int i = threadIdx.x; i < cout; i += blockDim.x) atomicAdd(db + i, acc_b[i]);
+  }
+}
+
+// AvgPool1d(4,2,2) backward: din[b][i] += 0.25 * sum_{o: 2o-2+j = i} dout[b][o]
+__global__ void avgpool_bwd_kernel(const float* __restrict__ dout, int t, int t_out, float* __restrict__ din) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= t) return;
+  float a = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int e = i + 2 - j;
+    if (e >= 0 && (e & 1) == 0 && (e >> 1) < t_out) a += dout[static_cast<size_t>(b) * t_out + (e >> 1)];
+  }
+  din[static_cast<size_t>(b) * t + i] += 0.25f * a;
+}
+
+// mode 0: out = coef * sgn(a - b); mode 1: out = coef * (a - c); mode 2: out = coef * (a - c) + coef2 * sgn(a - b)
+__global__ void loss_grad_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, int mode,
+                                 float c, float coef, float coef2, float* __restrict__ out) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x) {
+    const float av = a[i];
+    float g;
+    if (mode == 0) g = coef * sgn(av - b[i]);
+    else if (mode == 1) g = coef * (av - c);
+    else g = coef * (av - c) + coef2 * sgn(av - b[i]);
+    out[i] = g;
+  }
+}
+
+// sum |a - b| over bf16 arrays (feature maps in their internal layout; zero padding rows contribute nothing)
+__global__ void __launch_bounds__(256)
+l1_sum_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, long long n8,
+                   float* __restrict__ out) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n8; i += 256LL * gridDim.x) {
+    const uint4 av = reinterpret_cast<const uint4*>(a)[i], bv = reinterpret_cast<const uint4*>(b)[i];
+    const uint32_t aw[4] = {av.x, av.y, av.z, av.w}, bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const float2 x = hg::unpack_bf16x2(aw[h]), y = hg::unpack_bf16x2(bw[h]);
+      acc += fabsf(x.x - y.x) + fabsf(x.y - y.y);
+    }
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
+struct UnpackArgs {
+  int mode;          // 0: Conv1d, 1: ConvTranspose1d (polyphase)
+  int d0, d1, k;     // parameter shape [d0][d1][k]  (conv: cout, cin/groups; convtr: cin, cout)
+  int rows_p;        // rows of the packed tensor per tap (cout_p, or stride * cout_p)
+  int cin_tile;      // inner dimension of the packed tensor
+  int cout_g, merge; // conv: output channels per group, groups merged per tile
+  int stride, padding, shift_min, cout_p;   // convtr
+  int pos[64];       // conv: packed position of original tap j
+};
+
+// packed fp32 [taps][rows_p][cin_tile] -> dense parameter-layout gradient [d0][d1][k]
+__global__ void unpack_wgrad_kernel(const float* __restrict__ p, const UnpackArgs a, float* __restrict__ dw) {
+  const long long n = static_cast<long long>(a.d0) * a.d1 * a.k;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x) {
+    const int j = static_cast<int>(i % a.k);
+    const int i1 = static_cast<int>((i / a.k) % a.d1);
+    const int i0 = static_cast<int>(i / (static_cast<long long>(a.k) * a.d1));
+    float v;
+    if (a.mode == 0) {
+      const int slot = (i0 / a.cout_g) % a.merge;
+      v = p[(static_cast<size_t>(a.pos[j]) * a.rows_p + i0) * a.cin_tile + slot * a.d1 + i1];
+    } else {
+      const int ph = (((j - a.padding) % a.stride) + a.stride) % a.stride;
+      const int s = (ph + a.padding - j) / a.stride - a.shift_min;
+      v = p[(static_cast<size_t>(s) * a.rows_p + ph * a.cout_p + i1) * a.cin_tile + i0];
+    }
+    dw[i] = v;
+  }
+}
+
+// weight_norm backward (dim 0): w = g * v / ||v||;  dg = <dw, v> / ||v||;  dv = g/||v|| * (dw - v * <dw,v>/||v||^2)
+// one block per dim-0 index; dv, dg are ACCUMULATED into (+=) when accumulate != 0
+__global__ void __launch_bounds__(256)
+weight_norm_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ v, const float* __restrict__ g,
+                       int rest, int accumulate, float* __restrict__ dv, float* __restrict__ dg) {
+  __shared__ float red[32];
+  const int r = blockIdx.x;
+  const float* vr = v + static_cast<size_t>(r) * rest;
+  const float* dr = dw + static_cast<size_t>(r) * rest;
+  float ss = 0.f, dot = 0.f;
+  for (int i = threadIdx.x; i < rest; i += blockDim.x) {
+    ss += vr[i] * vr[i];
+    dot += vr[i] * dr[i];
+  }
+  ss = block_sum(ss, red);
+  dot = block_sum(dot, red);
+  const float nrm = sqrtf(ss);
+  const float inv = nrm > 0.f ? 1.f / nrm : 0.f;
+  const float gg = g[r];
+  float* o = dv + static_cast<size_t>(r) * rest;
+  for (int i = threadIdx.x; i < rest; i += blockDim.x) {
+    const float val = gg * inv * (dr[i] - vr[i] * dot * inv * inv);
+    o[i] = accumulate ? o[i] + val : val;
+  }
+  if (threadIdx.x == 0) dg[r] = accumulate ? dg[r] + dot * inv : dot * inv;
+}
+
+// torch.optim.AdamW step on one flat fp32 tensor
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
+                             float bc1, float bc2_sqrt, float gscale) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x) {
+    const float gi = g[i] * gscale;
+    float pi = p[i] * (1.f - lr * wd);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    pi -= (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
+    p[i] = pi;
+  }
+}
+
+int blocks_for(long long n, int per = 256) {
+  long long b = (n + per - 1) / per;
+  if (b > 148 * 16) b = 148 * 16;
+  return b < 1 ? 1 : static_cast<int>(b);
+}
+
+}  // namespace
+
+extern "C" int hg_pack_dgrad_weight(const void* w_packed, int ktaps, int n, int c, void* out, void* stream) {
+  HG_REQUIRE(w_packed && out && ktaps > 0 && n > 0 && c > 0 && ktaps <= 65535, "hg_pack_dgrad_weight: bad arguments");
+  dim3 grid((c + 31) / 32, (n + 31) / 32, ktaps), block(32, 8);
+  pack_dgrad_kernel<<<grid, block, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(w_packed), ktaps, n, c,
+                                                    static_cast<__nv_bfloat16*>(out));
+  HG_CHECK_CUDA(cudaGetLastError());
+  count();
+  return HG_OK;
+}
+
+extern "C" int hg_colsum_bf16(const void* x, int batch, int t_valid, int t_rows, int c, int accumulate, float* out,
+                              void* stream) {
+  HG_REQUIRE(x && out && batch > 0 && batch <= 65535 && t_valid > 0 && t_rows >= t_valid, "hg_colsum_bf16: bad sizes");
+  HG_REQUIRE(c % 8 == 0 && c / 8 <= 256, "hg_colsum_bf16: c must be a multiple of 8, at most 2048");
+  if (!accumulate) HG_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * c, S(stream)));
+  const int rows_per_block = 256;
+  dim3 grid((t_valid + rows_per_block - 1) / rows_per_block, batch);
+  colsum_kernel<<<grid, 256, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(x), t_valid, t_rows, c, rows_per_block,
+                                              out);
+  HG_CHECK_CUDA(cudaGetLastError());
+  count();
+  return HG_OK;
+}
+
+extern "C" int hg_conv_post_tanh_bwd(const void* x, const float* w, const float* y, const float* dy, int batch, int t,
+                                     int c, int k, float in_slope, void* dx, float* dpre_ws, float* dw, float* db,
+                                     void* stream) {
+  HG_REQUIRE(x && w && y && dy && dx && dpre_ws, "hg_conv_post_tanh_bwd: null pointer");
+  HG_REQUIRE(batch > 0 && batch <= 65535 && t > 0 && c % 8 == 0 && (k & 1) && k <= 15, "hg_conv_post_tanh_bwd: bad shape");
+  dim3 grid((t + 255) / 256, batch);
+  const size_t smem = (static_cast<size_t>(c) * k + 256 + k) * sizeof(float);
+  conv_post_bwd_dx_kernel<<<grid, 256, smem, S(stream)>>>(static_cast<const __nv_bfloat16*>(x), w, y, dy, t, c, k,
+                                                          in_slope, static_cast<__nv_bfloat16*>(dx), dpre_ws);
+  HG_CHECK_CUDA(cudaGetLastError());
+  count();
+  if (dw) {
+    const int tile = 1024;
+    dim3 g2((t + tile - 1) / tile, batch);
+    conv_post_bwd_dw_kernel<<<g2, 256, tile * sizeof(float), S(stream)>>>(static_cast<const __nv_bfloat16*>(x),
+                                                                          dpre_ws, t, c, k, tile, dw, db);
+    HG_CHECK_CUDA(cudaGetLastError());
+    count();
+  }
+  return HG_OK;
+}
+
+extern "C" int hg_disc_last_conv_bwd(const void* x, const float* w, const float* dlogit, int nseq, int h, int h_rows,
+                                     int c, int k, float slope, const void* fm_r, float fm_coef, void* dx, float* dw,
+                                     float* db, void* stream) {
+  HG_REQUIRE(x && w && dlogit, "hg_disc_last_conv_bwd: null pointer");
+  HG_REQUIRE(nseq > 0 && nseq <= 65535 && h > 0 && h_rows >= h && k <= 8 && (k & 1), "hg_disc_last_conv_bwd: bad shape");
+  if (dx) {
+    dim3 grid(h, nseq);
+    disc_last_bwd_dx_kernel<<<grid, 256, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(x), w, dlogit, h, h_rows, c,
+                                                         k, slope, static_cast<const __nv_bfloat16*>(fm_r), fm_coef,
+                                                         static_cast<__nv_bfloat16*>(dx));
+    HG_CHECK_CUDA(cudaGetLastError());
+    count();
+  }
+  if (dw) {
+    dim3 grid((c + 255) / 256, nseq < 32 ? nseq : 32);
+    disc_last_bwd_dw_kernel<<<grid, 256, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(x), dlogit, nseq, h, h_rows,
+                                                         c, k, dw, db);
+    HG_CHECK_CUDA(cudaGetLastError());
+    count();
+  }
+  return HG_OK;
+}
+
+extern "C" int hg_disc_first_conv_bwd(const float* y, const float* w, const void* dpre, int batch, int t, int period,
+                                      int k, int stride, int pad, int cout, int h_rows, float* dw, float* db,
+                                      float* dy, void* stream) {
+  HG_REQUIRE(y && w && dpre && (dw || dy), "hg_disc_first_conv_bwd: null pointer");
+  HG_REQUIRE(!dw || db, "hg_disc_first_conv_bwd: dw needs db");
+  HG_REQUIRE(batch > 0 && t > 1 && period >= 1 && k >= 1 && k <= 16 && stride >= 1 && cout > 0,
+             "hg_disc_first_conv_bwd: bad shape");
+  const int t_pad = (t + period - 1) / period * period;
+  const int h_in = t_pad / period;
+  const int h_out = (h_in + 2 * pad - k) / stride + 1;
+  HG_REQUIRE(h_out > 0 && h_rows >= h_out && batch * period <= 65535, "hg_disc_first_conv_bwd: bad geometry");
+  dim3 grid((h_out + 127) / 128, batch * period);
+  const size_t smem = (static_cast<size_t>(2 * k + 1) * cout) * sizeof(float);
+  disc_first_bwd_kernel<<<grid, 128, smem, S(stream)>>>(y, w, static_cast<const __nv_bfloat16*>(dpre), t, period, h_in,
+                                                        h_out, h_rows, k, stride, pad, cout, dw, db, dy);
+  HG_CHECK_CUDA(cudaGetLastError());
+  count();
+  return HG_OK;
+}
+
+extern "C" int hg_avgpool_4_2_2_bwd(const float* dout, int batch, int t, float* din, void* stream) {
+  HG_REQUIRE(dout && din && batch > 0 && batch <= 65535 && t > 0, "hg_avgpool_4_2_2_bwd: bad arguments");
+  dim3 grid((t + 255) / 256, batch);
+  avgpool_bwd_kernel<<<grid, 256, 0, S(stream)>>>(dout, t, t / 2 + 1, din);
+  HG_CHECK_CUDA(cudaGetLastError());
+  count();
+  return HG_OK;
+}
+
+extern "C" int hg_loss_grad(const float* a, const float* b, long long n, int mode, float c, float coef, float coef2,
+                            float* out, void* stream) {
+  HG_REQUIRE(a && out && n > 0 && mode >= 0 && mode <= 2 && (mode == 1 || b), "hg_loss_grad: bad arguments");
+  loss_grad_kernel<<<blocks_for(n), 256, 0, S(stream)>>>(a, b, n, mode, c, coef, coef2, out);
+  HG_CHECK_CUDA(cudaGetLastError());
+  count();
+  return HG_OK;
+}
+
+extern "C" int hg_l1_sum_bf16(const void* a, const void* b, long long n, float* out_acc, void* stream) {
+  HG_REQUIRE(a && b && out_acc && n > 0 && n % 8 == 0, "hg_l1_sum_bf16: n must be a positive multiple of 8");
+  l1_sum_bf16_kernel<<<blocks_for(n / 8), 256, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(a),
+                                                              static_cast<const __nv_bfloat16*>(b), n / 8, out_acc);
+  HG_CHECK_CUDA(cudaGetLastError());
+  count();
+  return HG_OK;
+}
+
+extern "C" int hg_unpack_wgrad_conv(const float* dw_packed, int cout, int cin_g, int k, int rows_p, int cin_tile,
+                                    int cout_g, int merge, const int* host_tap_order, float* dw, void* stream) {
+  HG_REQUIRE(dw_packed && dw && k > 0 && k <= 64 && cout > 0 && cin_g > 0 && merge >= 1 && cout_g >= 1,
+             "hg_unpack_wgrad_conv: bad arguments");
+  UnpackArgs a{};
+  a.mode = 0; a.d0 = cout; a.d1 = cin_g; a.k = k; a.rows_p = rows_p; a.cin_tile = cin_tile;
+  a.cout_g = cout_g; a.merge = merge;
+  for (int q = 0; q < k; ++q) a.pos[host_tap_order ? host_tap_order[q] : q] = q;
+  unpack_wgrad_kernel<<<blocks_for(static_cast<long long>(cout) * cin_g * k), 256, 0, S(stream)>>>(dw_packed, a, dw);
+  HG_CHECK_CUDA(cudaGetLastError());
+  count();
+  return HG_OK;
+}
+
+extern "C" int hg_unpack_wgrad_convtr(const float* dw_packed, int cin, int cout, int k, int stride, int padding,
+                                      int cin_p, int cout_p, float* dw, void* stream) {
+  HG_REQUIRE(dw_packed && dw && k > 0 && cin > 0 && cout > 0 && stride > 0, "hg_unpack_wgrad_convtr: bad arguments");
+  int nshift = 0, smin = 0;
+  int rc = hg_convtr1d_geometry(k, stride, padding, &nshift, &smin);
+  if (rc) return rc;
+  UnpackArgs a{};
+  a.mode = 1; a.d0 = cin; a.d1 = cout; a.k = k; a.rows_p = stride * cout_p; a.cin_tile = cin_p;
+  a.stride = stride; a.padding = padding; a.shift_min = smin; a.cout_p = cout_p;
+  unpack_wgrad_kernel<<<blocks_for(static_cast<long long>(cin) * cout * k), 256, 0, S(stream)>>>(dw_packed, a, dw);
+  HG_CHECK_CUDA(cudaGetLastError());
+  count();
+  return HG_OK;
+}
+
+extern "C" int hg_weight_norm_bwd(const float* dw, const float* v, const float* g, int dim0, int rest, int accumulate,
+                                  float* dv, float* dg, void* stream) {
+  HG_REQUIRE(dw && v && g && dv && dg && dim0 > 0 && rest > 0, "hg_weight_norm_bwd: bad arguments");
+  weight_norm_bwd_kernel<<<dim0, 256, 0, S(stream)>>>(dw, v, g, rest, accumulate, dv, dg);
+  HG_CHECK_CUDA(cudaGetLastError());
+  count();
+  return HG_OK;
+}
+
+extern "C" int hg_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                             float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream) {
+  HG_REQUIRE(p && g && m && v && n > 0 && step >= 1, "hg_adamw_step: bad arguments");
+  const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
+  const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
+  adamw_kernel<<<blocks_for(n, 1024), 256, 0, S(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1,
+                                                           sqrtf(bc2), grad_scale);
+  HG_CHECK_CUDA(cudaGetLastError());
+  count();
+  return HG_OK;
+}

@@ -1,28 +1,44 @@
-"""Forward half of the UPSTREAM training step (jik876/hifi-gan train.py; the fork deleted the file but ships every
-function it calls — SURVEY.md §3.3), composed from the CUDA-backed modules of this package.
+"""The UPSTREAM training step (jik876/hifi-gan train.py; the fork deleted the file but ships every function it
+calls — SURVEY.md §3.3) on hand-written sm_100a kernels: forward, backward, AdamW and the data-parallel gradient
+all-reduce.  No torch autograd runs here: every gradient is produced by a kernel of libhifigan_b200.so
+(include/hifigan_b200.h, "Training step" section) and the chain rule is spelled out below.
 
-Only the forward graph and the loss values exist so far: the backward kernels (dgrad / wgrad of every conv, mel
-backward, weight-norm backward), AdamW and the data-parallel gradient all-reduce are not built.
+    y_g_hat = G(x);  y_g_hat_mel = mel(y_g_hat)
+    D step:  loss_disc = sum_d [mean((1 - d(y))^2) + mean(d(y_g_hat.detach())^2)]   over MPD + MSD; AdamW(D)
+    G step:  loss_gen  = 45 * L1(y_mel, y_g_hat_mel) + sum_d [2 * sum_l mean|fmap_r - fmap_g| + mean((1 - d(y_g_hat))^2)]
+             back through the UPDATED discriminators into G; AdamW(G)
+
+Numerics (declared): bf16 operands and bf16-stored activations / activation gradients, fp32 accumulation,
+fp32 parameter gradients, fp32 master weights and optimizer state.
 """
 from __future__ import annotations
 
-from typing import Dict
+from ctypes import byref, c_int
+from typing import Dict, List, Optional, Tuple
 
 import torch
+import torch.nn as nn
 
 from . import _lib
-from .meldataset import mel_spectrogram
-from .models import _device_mean, discriminator_loss, feature_loss, generator_loss
+from .meldataset import mel_spectrogram, torch_mels
+from .models import (LRELU_SLOPE, DiscriminatorP, DiscriminatorS, Generator, MultiPeriodDiscriminator,
+                     MultiScaleDiscriminator, ResBlock1, _DiscLayer, _PackedConv, _conv, _device_mean,
+                     _effective_weight, _g_v, _pad_ch, _round_up, _stream, discriminator_loss, feature_loss,
+                     generator_loss)
+
+
+def _p(x) -> int:
+    """device pointer of a tensor / raw int pointer / None"""
+    if x is None:
+        return 0
+    if isinstance(x, int):
+        return x
+    return x.data_ptr()
 
 
 def step_losses(generator, mpd, msd, x: torch.Tensor, y: torch.Tensor, y_mel: torch.Tensor, h) -> Dict[str, torch.Tensor]:
     """One training step's loss values, call for call as the reference computes them (no optimizer update):
-
-        y_g_hat = generator(x);  y_g_hat_mel = mel_spectrogram(y_g_hat.squeeze(1), ..., h.fmax_for_loss)
-        D step:  mpd(y, y_g_hat.detach()), msd(...)  ->  loss_disc_f, loss_disc_s
-        G step:  45 * L1(y_mel, y_g_hat_mel), mpd / msd again  ->  feature and generator losses
-
-    x [B,80,F] mel, y [B,1,T] audio, y_mel [B,80,F] loss-mel (all on the GPU).  msd is evaluated twice, so a
+    the forward half of `TrainStep.step`, through the public module API.  msd is evaluated twice, so a
     train-mode spectral-norm scale advances 4 power iterations per step exactly like the reference."""
     with torch.no_grad():
         y_g_hat = generator(x).clone()
@@ -42,3 +58,782 @@ def step_losses(generator, mpd, msd, x: torch.Tensor, y: torch.Tensor, y_mel: to
         out["loss_gen_all"] = (out["loss_gen_s"] + out["loss_gen_f"] + out["loss_fm_s"] + out["loss_fm_f"]
                                + out["loss_mel"])
     return out
+
+
+# ------------------------------------------------------------------------------------------------ flat params
+class FlatParams:
+    """All parameters of a module re-pointed into ONE fp32 buffer (plus flat gradient and AdamW state buffers):
+    the optimizer step is one kernel launch and the data-parallel all-reduce one NCCL call per network.
+    state_dict() / load_state_dict() keep working — they copy through the views."""
+
+    def __init__(self, module: nn.Module, device):
+        self.module = module
+        ps = [p for p in module.parameters()]
+        self.sizes = [p.numel() for p in ps]
+        n = sum(self.sizes)
+        # 16-byte aligned offsets so kernels may use vector accesses on any view
+        self.offsets, off = [], 0
+        for s in self.sizes:
+            self.offsets.append(off)
+            off += (s + 3) // 4 * 4
+        self.numel = off
+        self.p = torch.zeros(off, dtype=torch.float32, device=device)
+        self.g = torch.zeros(off, dtype=torch.float32, device=device)
+        self.m = torch.zeros(off, dtype=torch.float32, device=device)
+        self.v = torch.zeros(off, dtype=torch.float32, device=device)
+        self.step_count = 0
+        with torch.no_grad():
+            for p, o, s in zip(ps, self.offsets, self.sizes):
+                view = self.p[o:o + s].view(p.shape)
+                view.copy_(p.detach().to(device=device, dtype=torch.float32))
+                p.data = view
+                p.grad = self.g[o:o + s].view(p.shape)
+        self.params = ps
+
+    def adamw(self, lr: float, betas=(0.8, 0.99), eps: float = 1e-8, weight_decay: float = 0.01,
+              grad_scale: float = 1.0) -> None:
+        """torch.optim.AdamW(lr, betas) semantics (UPSTREAM train.py: AdamW(h.learning_rate, [adam_b1, adam_b2]))."""
+        self.step_count += 1
+        _lib.check(_lib.lib().hg_adamw_step(self.p.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                            self.numel, lr, betas[0], betas[1], eps, weight_decay, self.step_count,
+                                            grad_scale, _stream()), "hg_adamw_step")
+
+
+# ------------------------------------------------------------------------------------------------ generator
+class _GenLayerGrad:
+    """Backward-side state of one packed Generator conv: dgrad filter bank, packed fp32 weight gradient, bias
+    gradient (padded), and the route back to the weight_norm parameters."""
+
+    def __init__(self, pc: _PackedConv, device, need_dgrad: bool = True):
+        self.pc = pc
+        rows = pc.w.shape[1]
+        self.rows = rows
+        self.wd = torch.empty(pc.taps, pc.cin_p, rows, dtype=torch.bfloat16, device=device) if need_dgrad else None
+        self.dwp = torch.zeros(pc.taps, rows, pc.cin_p, dtype=torch.float32, device=device)
+        self.db = torch.zeros(rows, dtype=torch.float32, device=device)
+        self.dgrad_pad = (pc.taps - 1) * pc.dil - pc.pad_left
+
+    def pack(self, L) -> None:
+        if self.wd is not None:
+            pc = self.pc
+            _lib.check(L.hg_pack_dgrad_weight(pc.w.data_ptr(), pc.taps, self.rows, pc.cin_p, self.wd.data_ptr(),
+                                              _stream()), "hg_pack_dgrad_weight")
+
+    def wgrad(self, L, x, dy, batch: int, t: int) -> None:
+        """x bf16 [B][t][cin_p] (the forward input), dy bf16 [B][t][rows] -> dwp, db"""
+        pc = self.pc
+        _lib.check(L.hg_conv1d_wgrad(_p(x), _p(dy), batch, t, pc.cin_p, t, t, 1, self.rows, pc.taps, 1, pc.dil,
+                                     pc.pad_left, self.dwp.data_ptr(), 0, _stream()), "hg_conv1d_wgrad")
+
+    def bias_grad(self, L, dy, batch: int, t: int, c: int) -> None:
+        _lib.check(L.hg_colsum_bf16(_p(dy), batch, t, t, c, 0, self.db.data_ptr(), _stream()), "hg_colsum_bf16")
+
+    def dgrad(self, L, dy, batch: int, t: int, out, mask=None, slope: float = LRELU_SLOPE, res0=None, res1=None,
+              scale: float = 1.0) -> None:
+        pc = self.pc
+        _lib.check(L.hg_conv1d_dgrad(_p(dy), self.wd.data_ptr(), batch, t, t, self.rows, t, t, 1, 0, pc.cin_p,
+                                     pc.taps, pc.dil, self.dgrad_pad, _p(mask), slope, 0, 0, 0.0, _p(res0), _p(res1),
+                                     scale, _p(out), _stream()), "hg_conv1d_dgrad")
+
+    def to_param_grads(self, L, scratch: torch.Tensor) -> None:
+        """packed dW -> (weight_g.grad, weight_v.grad) or weight.grad; bias.grad"""
+        pc = self.pc
+        m = pc.module
+        g, v = _g_v(m)
+        st = _stream()
+        if pc.kind == "conv":
+            d0, d1, k = pc.cout, pc.cin, pc.taps
+            _lib.check(L.hg_unpack_wgrad_conv(self.dwp.data_ptr(), d0, d1, k, self.rows, pc.cin_p, d0, 1, None,
+                                              scratch.data_ptr(), st), "hg_unpack_wgrad_conv")
+            if m.bias is not None:
+                m.bias.grad.copy_(self.db[: pc.cout])
+        else:
+            k = m.kernel_size[0]
+            d0, d1 = pc.cin, pc.cout
+            _lib.check(L.hg_unpack_wgrad_convtr(self.dwp.data_ptr(), d0, d1, k, pc.stride, m.padding[0], pc.cin_p,
+                                                pc.cout_p, scratch.data_ptr(), st), "hg_unpack_wgrad_convtr")
+            if m.bias is not None:
+                m.bias.grad.copy_(self.db[: pc.cout])
+        _route_weight_grad(L, m, scratch, d0, d1 * k)
+
+
+def _route_weight_grad(L, m: nn.Module, dw: torch.Tensor, d0: int, rest: int, accumulate: bool = False) -> None:
+    """dw fp32 (dense, parameter layout, first d0*rest elements of `dw`) -> the module's parameter gradients."""
+    g, v = _g_v(m)
+    if g is not None:
+        _lib.check(L.hg_weight_norm_bwd(dw.data_ptr(), v.data_ptr(), g.data_ptr(), d0, rest, 1 if accumulate else 0,
+                                        v.grad.data_ptr(), g.grad.data_ptr(), _stream()), "hg_weight_norm_bwd")
+    else:
+        src = dw[: d0 * rest].view(v.shape)
+        if accumulate:
+            v.grad.add_(src)
+        else:
+            v.grad.copy_(src)
+
+
+class GeneratorTrainer:
+    """Training-mode forward (every conv input kept in HBM) and hand-written backward of one Generator."""
+
+    def __init__(self, gen: Generator, device):
+        self.gen, self.device = gen, device
+        self.flat = FlatParams(gen, device)
+        gen._drop_engines()
+        self.eng = gen._engine(device)
+        e = self.eng
+        self.g_pre = _GenLayerGrad(e.pre, device, need_dgrad=False)
+        self.g_ups = [_GenLayerGrad(pc, device) for pc in e.ups]
+        self.g_blocks = [[_GenLayerGrad(pc, device) for pc in blk] for blk in e.blocks]
+        nmax = max(gl.dwp.numel() for gl in [self.g_pre] + self.g_ups + [x for b in self.g_blocks for x in b])
+        self.scratch = torch.empty(nmax, dtype=torch.float32, device=device)
+        post = gen.conv_post
+        self.post_dw = torch.zeros(e.post_cin_p, post.kernel_size[0], dtype=torch.float32, device=device)
+        self.post_db = torch.zeros(1, dtype=torch.float32, device=device)
+        self.ws: Dict[Tuple[int, int], dict] = {}
+        self.two_conv = isinstance(gen.resblocks[0], ResBlock1)
+        if gen.num_kernels > 3:
+            raise NotImplementedError("training path supports up to 3 MRF branches (V1/V2/V3)")
+
+    def invalidate(self) -> None:
+        """parameters were updated in place through raw pointers (AdamW kernel): force a re-pack"""
+        e = self.eng
+        for pc in [e.pre] + e.ups + [x for b in e.blocks for x in b]:
+            pc.key = None
+        e.post_key = None
+
+    def _workspace(self, b: int, frames: int) -> dict:
+        ws = self.ws.get((b, frames))
+        if ws is not None:
+            return ws
+        e, gen, dev = self.eng, self.gen, self.device
+        bf = lambda *shape: torch.empty(*shape, dtype=torch.bfloat16, device=dev)
+        nk = gen.num_kernels
+        ws = {"mel": bf(b, frames, e.pre.cin_p), "pre_act": bf(b, frames, e.pre.cout_p), "stages": []}
+        t = frames
+        for i, up in enumerate(e.ups):
+            t_in = t
+            t *= up.stride
+            c = up.cout_p
+            steps = len(e.blocks[i * nk]) // (2 if self.two_conv else 1)
+            mk = lambda: bf(b, t, c)
+            st = {"t_in": t_in, "t": t, "c": c, "steps": steps, "x_raw": mk(), "xa0": mk(), "stage_act": mk(),
+                  "raw": [mk(), mk()], "r": [mk() for _ in range(max(1, nk - 1))],
+                  # saved conv inputs: xa[j][s] for s >= 1 (s = 0 is the shared xa0), t1[j][s]
+                  "xa": [[None] + [mk() for _ in range(steps - 1)] for _ in range(nk)],
+                  "t1": [[mk() for _ in range(steps)] for _ in range(nk)] if self.two_conv else None,
+                  # gradient buffers
+                  "g0": mk(), "gp": [mk(), mk()], "gt1": mk(), "gb": [mk(), mk()]}
+            ws["stages"].append(st)
+        ws["y"] = torch.empty(b, 1, t, dtype=torch.float32, device=dev)
+        ws["dpre"] = torch.empty(b, t, dtype=torch.float32, device=dev)
+        ws["g_pre"] = bf(b, frames, e.pre.cout_p)
+        ws["t_out"] = t
+        if len(self.ws) >= 4:
+            self.ws.pop(next(iter(self.ws)))
+        self.ws[(b, frames)] = ws
+        return ws
+
+    # ---- forward -------------------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """mel fp32 [B,80,F] -> waveform fp32 [B,1,T] (engine-owned buffer), keeping what backward needs."""
+        L = _lib.lib()
+        e, gen = self.eng, self.gen
+        e.refresh()
+        for gl in self.g_ups + [x_ for blk in self.g_blocks for x_ in blk]:
+            gl.pack(L)
+        b, c, frames = x.shape
+        xin = x.contiguous().float()
+        ws = self._workspace(b, frames)
+        self.cur = ws
+        _lib.check(L.hg_ncl_to_nlc(xin.data_ptr(), b, c, frames, e.pre.cin_p, ws["mel"].data_ptr(), 0, 0.0, _stream()),
+                   "hg_ncl_to_nlc")
+        _conv(L, ws["mel"], e.pre, b, frames, out_act=ws["pre_act"])
+        cur, t = ws["pre_act"], frames
+        nk = gen.num_kernels
+        for i, up in enumerate(e.ups):
+            st = ws["stages"][i]
+            _conv(L, cur, up, b, t, out_raw=st["x_raw"], out_act=st["xa0"])
+            t = st["t"]
+            last_stage = i == len(e.ups) - 1
+            out_slope = 0.01 if last_stage else LRELU_SLOPE
+            for j in range(nk):
+                packs = e.blocks[i * nk + j]
+                cur_raw, cur_act = st["x_raw"], st["xa0"]
+                for s in range(st["steps"]):
+                    last = s == st["steps"] - 1
+                    if self.two_conv:
+                        _conv(L, cur_act, packs[2 * s], b, t, out_act=st["t1"][j][s])
+                        src, pc = st["t1"][j][s], packs[2 * s + 1]
+                    else:
+                        src, pc = cur_act, packs[s]
+                    if not last:
+                        nr, na = st["raw"][s & 1], st["xa"][j][s + 1]
+                        _conv(L, src, pc, b, t, res=(cur_raw, None, None), out_raw=nr, out_act=na)
+                        cur_raw, cur_act = nr, na
+                    elif j < nk - 1:
+                        _conv(L, src, pc, b, t, res=(cur_raw, None, None), out_raw=st["r"][j])
+                    else:
+                        others = tuple(st["r"][q] for q in range(nk - 1)) + (None,) * (3 - nk)
+                        _conv(L, src, pc, b, t, res=(cur_raw,) + others[:2], scale=1.0 / nk,
+                              out_act=st["stage_act"], slope=out_slope)
+            cur = st["stage_act"]
+        post = gen.conv_post
+        _lib.check(L.hg_conv_post_tanh_fwd(cur.data_ptr(), e.post_w.data_ptr(), e.post_b.data_ptr(), b, t,
+                                           e.post_cin_p, post.kernel_size[0], ws["y"].data_ptr(), _stream()),
+                   "hg_conv_post_tanh_fwd")
+        return ws["y"]
+
+    # ---- backward ------------------------------------------------------------------------------------------
+    def backward(self, dy: torch.Tensor) -> None:
+        """dy fp32 [B,T] (or [B,1,T]): gradient at the waveform of the LAST forward -> every parameter's .grad."""
+        L = _lib.lib()
+        e, gen, ws = self.eng, self.gen, self.cur
+        b, frames = ws["mel"].shape[0], ws["mel"].shape[1]
+        nk = gen.num_kernels
+        dy = dy.reshape(b, -1).contiguous().float()
+        t = ws["t_out"]
+        post = gen.conv_post
+        stages = ws["stages"]
+        last = stages[-1]
+        self.post_dw.zero_()
+        self.post_db.zero_()
+        # conv_post + tanh; the kernel also applies the slope-0.01 leaky_relu mask of the last stage
+        _lib.check(L.hg_conv_post_tanh_bwd(last["stage_act"].data_ptr(), e.post_w.data_ptr(), ws["y"].data_ptr(),
+                                           dy.data_ptr(), b, t, e.post_cin_p, post.kernel_size[0], 0.01,
+                                           last["g0"].data_ptr(), ws["dpre"].data_ptr(), self.post_dw.data_ptr(),
+                                           self.post_db.data_ptr(), _stream()), "hg_conv_post_tanh_bwd")
+        first_scale = 1.0 / nk      # d(mean of branches)/d(branch): folded into the first consumer of g0 below
+        for i in reversed(range(len(e.ups))):
+            st = stages[i]
+            t, c = st["t"], st["c"]
+            g0 = st["g0"]
+            if i == len(e.ups) - 1:
+                # conv_post's dx is not yet divided by nk: do it once, in place, with the cheapest kernel at hand
+                g0.mul_(first_scale)
+            prev = None
+            for j in range(nk):
+                gl = self.g_blocks[i * nk + j]
+                g = g0
+                for s in reversed(range(st["steps"])):
+                    xa = st["xa0"] if s == 0 else st["xa"][j][s]
+                    out = st["gb"][j & 1] if s == 0 else st["gp"][s & 1]
+                    res1 = prev if s == 0 else None
+                    if self.two_conv:
+                        c1, c2 = gl[2 * s], gl[2 * s + 1]
+                        t1 = st["t1"][j][s]
+                        c2.bias_grad(L, g, b, t, c)
+                        c2.wgrad(L, t1, g, b, t)
+                        c2.dgrad(L, g, b, t, st["gt1"], mask=t1)
+                        c1.bias_grad(L, st["gt1"], b, t, c)
+                        c1.wgrad(L, xa, st["gt1"], b, t)
+                        c1.dgrad(L, st["gt1"], b, t, out, mask=xa, res0=g, res1=res1)
+                    else:
+                        cc = gl[s]
+                        cc.bias_grad(L, g, b, t, c)
+                        cc.wgrad(L, xa, g, b, t)
+                        cc.dgrad(L, g, b, t, out, mask=xa, res0=g, res1=res1)
+                    g = out
+                prev = g
+            dx_raw = prev                                  # gradient at the upsampler's output [B][t][c]
+            up = self.g_ups[i]
+            t_in = st["t_in"]
+            up_in = ws["pre_act"] if i == 0 else stages[i - 1]["stage_act"]
+            _lib.check(L.hg_colsum_bf16(dx_raw.data_ptr(), b, t, t, c, 0, up.db.data_ptr(), _stream()), "hg_colsum_bf16")
+            up.wgrad(L, up_in, dx_raw, b, t_in)            # dy viewed as [B][t_in][stride * c]
+            if i > 0:
+                up.dgrad(L, dx_raw, b, t_in, stages[i - 1]["g0"], mask=up_in, scale=1.0 / nk)
+            else:
+                up.dgrad(L, dx_raw, b, t_in, ws["g_pre"], mask=up_in)
+                self.g_pre.bias_grad(L, ws["g_pre"], b, frames, e.pre.cout_p)
+                self.g_pre.wgrad(L, ws["mel"], ws["g_pre"], b, frames)
+        # parameter gradients
+        for gl in [self.g_pre] + self.g_ups + [x for blk in self.g_blocks for x in blk]:
+            gl.to_param_grads(L, self.scratch)
+        cin = post.in_channels
+        k = post.kernel_size[0]
+        dw = self.post_dw[:cin].contiguous()
+        _route_weight_grad(L, post, dw, 1, cin * k)
+        post.bias.grad.copy_(self.post_db)
+
+
+# ------------------------------------------------------------------------------------------------ discriminators
+class _DiscBwdLayer:
+    """Data-gradient side of one wide discriminator conv: the polyphase / flipped filter bank and its launch."""
+
+    def __init__(self, layer: _DiscLayer, device):
+        self.layer = layer
+        s, k, pad = layer.stride, layer.k, layer.pad
+        L = _lib.lib()
+        nshift, smin = c_int(), c_int()
+        _lib.check(L.hg_convtr1d_geometry(k, s, pad, byref(nshift), byref(smin)))
+        self.nshift, self.smin = nshift.value, smin.value
+        self.pad_left = -self.smin
+        cin, cout = layer.cin, layer.cout
+        self.grouped = layer.groups > 1
+        if not self.grouped:
+            self.cout_tile = cout
+            self.w = torch.empty(self.nshift, s * cin, cout, dtype=torch.bfloat16, device=device)
+            self.idx = None
+        else:
+            cin_g, cout_g, merge = cin // layer.groups, cout // layer.groups, layer.merge
+            ct = cout_g * merge
+            self.cout_tile = ct
+            m_idx = torch.arange(self.nshift).view(-1, 1, 1, 1)
+            rho = torch.arange(s).view(1, -1, 1, 1)
+            ci = torch.arange(cin).view(1, 1, -1, 1)
+            cc = torch.arange(ct).view(1, 1, 1, -1)
+            g = ci // cin_g
+            co = (g // merge) * ct + cc
+            j = rho + pad - s * (m_idx + self.smin)
+            valid = (co // cout_g == g) & (j >= 0) & (j < k)
+            src = (co * cin_g + (ci % cin_g)) * k + j
+            zero_slot = cout * cin_g * k
+            self.idx = torch.where(valid, src, torch.full_like(src, zero_slot)).reshape(-1).to(device)
+            self.w = torch.empty(self.nshift, s * cin, ct, dtype=torch.bfloat16, device=device)
+
+    def pack(self, w_eff: torch.Tensor, w_fwd_packed: torch.Tensor) -> None:
+        """w_eff fp32 [cout][cin/groups][k] (effective weight), w_fwd_packed the forward's bf16 pack"""
+        layer = self.layer
+        L = _lib.lib()
+        if self.grouped:
+            flat = torch.cat([w_eff.reshape(-1), w_eff.new_zeros(1)])
+            self.w.view(-1).copy_(flat[self.idx])
+        elif layer.stride == 1:
+            _lib.check(L.hg_pack_dgrad_weight(w_fwd_packed.data_ptr(), layer.k, layer.cout, layer.cin,
+                                              self.w.data_ptr(), _stream()), "hg_pack_dgrad_weight")
+        else:
+            w32 = w_eff.contiguous()
+            _lib.check(L.hg_pack_convtr1d_weight(w32.data_ptr(), 0, layer.cout, layer.cin, layer.k, layer.stride,
+                                                 layer.pad, self.w.data_ptr(), _stream()), "hg_pack_convtr1d_weight")
+
+    def dgrad(self, L, dy, nseq: int, t_dy_valid: int, t_dy_rows: int, rows_in: int, act_g, act_r, fm_coef: float,
+              out, st) -> None:
+        """out[nseq][rows_in][cin] = (conv^T(dy) + fm_coef * sgn(act_g - act_r)) * lrelu'(act_g)"""
+        layer = self.layer
+        s = layer.stride
+        vrows = rows_in // s
+        _lib.check(L.hg_conv1d_dgrad(_p(dy), self.w.data_ptr(), nseq, t_dy_valid, t_dy_rows, layer.cout, vrows, vrows,
+                                     layer.groups_eff if self.grouped else 1,
+                                     layer.cin_tile if self.grouped else 0, s * layer.cin, self.nshift, 1,
+                                     self.pad_left, _p(act_g), LRELU_SLOPE, _p(act_r),
+                                     _p(act_g) if act_r is not None else 0, fm_coef, 0, 0, 1.0, _p(out), st),
+                   "hg_conv1d_dgrad")
+
+
+class _SubDiscTrainer:
+    """One DiscriminatorP / DiscriminatorS: batched (real ++ generated) forward with saved activations, losses on
+    the internal layout, and the hand-written backward."""
+
+    def __init__(self, disc: nn.Module, device):
+        self.disc, self.device = disc, device
+        self.period = getattr(disc, "period", 1)
+        convs = list(disc.convs)
+        self.mods = convs + [disc.conv_post]
+        m0 = convs[0]
+        self.first = (m0.kernel_size[0], m0.stride[0], m0.padding[0], m0.out_channels)
+        groups = lambda m: getattr(m, "groups", 1)
+        self.mids = [_DiscLayer(m.in_channels, m.out_channels, m.kernel_size[0], m.stride[0], m.padding[0], groups(m))
+                     for m in convs[1:]]
+        self.bwd = [_DiscBwdLayer(l, device) for l in self.mids]
+        self.kpost = disc.conv_post.kernel_size[0]
+        self.spectral = hasattr(m0, "weight_orig")
+        self.ws = {}
+        nmax = max(l.k * l.cout * l.cin_tile for l in self.mids)
+        self.dwp = torch.zeros(nmax, dtype=torch.float32, device=device)
+        self.scratch = torch.empty(max(m.weight_v.numel() if hasattr(m, "weight_v") and not self.spectral
+                                       else m.weight_orig.numel() if self.spectral else m.weight.numel()
+                                       for m in self.mods), dtype=torch.float32, device=device)
+        self.db = torch.zeros(1024, dtype=torch.float32, device=device)
+
+    # ---- weights -------------------------------------------------------------------------------------------
+    def _weights(self):
+        """effective fp32 weights + GEMM packs of every layer (one spectral-norm power iteration per call in
+        train mode, exactly like one reference forward)."""
+        ws = {"eff": [], "fwd": [], "sn": []}
+        for li, m in enumerate(self.mods):
+            w = _effective_weight(m)
+            w = w.reshape(w.shape[0], w.shape[1], -1).contiguous()     # Conv2d (k,1) kernels -> [cout][cin/g][k]
+            ws["eff"].append(w)
+            if hasattr(m, "weight_orig"):
+                # u, v as this call left them: the backward of THIS call's weights needs them (the next call moves on)
+                u, v = m.weight_u.clone(), m.weight_v.clone()
+                ws["sn"].append((u, v, torch.dot(u, torch.mv(m.weight_orig.detach().flatten(1), v))))
+            else:
+                ws["sn"].append(None)
+            if 1 <= li <= len(self.mids):
+                layer = self.mids[li - 1]
+                ws["fwd"].append(layer.pack(w))
+            else:
+                ws["fwd"].append(None)
+        return ws
+
+    def _geometry(self, nb: int, t: int):
+        key = (nb, t)
+        g = self.ws.get(key)
+        if g is not None:
+            return g
+        dev, period = self.device, self.period
+        k0, s0, p0, c0 = self.first
+        h = (t + period - 1) // period
+        if h * period - t >= t:
+            raise RuntimeError("reflect padding needs n_pad < t (reference F.pad behaviour)")
+        hh = (h + 2 * p0 - k0) // s0 + 1
+        geo = [(hh, _round_up(hh, self.mids[0].stride), c0)]
+        for li, layer in enumerate(self.mids):
+            hh = (hh + 2 * layer.pad - layer.k) // layer.stride + 1
+            nxt = self.mids[li + 1].stride if li + 1 < len(self.mids) else 1
+            geo.append((hh, _round_up(hh, nxt), layer.cout))
+        nseq = nb * period
+        g = {"geo": geo, "nseq": nseq,
+             "act": [torch.zeros(nseq, r, c, dtype=torch.bfloat16, device=dev) for _, r, c in geo],
+             "grad": [torch.zeros(nseq, r, c, dtype=torch.bfloat16, device=dev) for _, r, c in geo],
+             "logit": torch.empty(nseq, geo[-1][0], dtype=torch.float32, device=dev),
+             "dlogit": torch.empty(nseq, geo[-1][0], dtype=torch.float32, device=dev)}
+        if len(self.ws) >= 4:
+            self.ws.pop(next(iter(self.ws)))
+        self.ws[key] = g
+        return g
+
+    # ---- forward -------------------------------------------------------------------------------------------
+    def forward(self, ycat: torch.Tensor, nreal: int):
+        """ycat fp32 [2B, T]: rows [0, nreal) real, the rest generated.  Weight-norm sub-discriminators run the
+        whole batch through each layer once; the spectral-norm one runs the two halves with their own weights,
+        because the reference's d(y) and d(y_hat) calls each advance the power iteration (models.py:236-244)."""
+        L = _lib.lib()
+        nb, t = ycat.shape
+        G = self._geometry(nb, t)
+        period = self.period
+        parts = [(0, nb)] if not self.spectral else [(0, nreal), (nreal, nb - nreal)]
+        self.parts = []
+        st = _stream()
+        k0, s0, p0, c0 = self.first
+        for b0, bn in parts:
+            W = self._weights()
+            self.parts.append((b0, bn, W))
+            seq0, nseq = b0 * period, bn * period
+            w0 = W["eff"][0].reshape(c0, k0).contiguous()
+            W["w0"] = w0
+            b0_bias = self.mods[0].bias.detach().float().contiguous()
+            act = G["act"][0]
+            h, rows, _ = G["geo"][0]
+            _lib.check(L.hg_disc_first_conv_fwd(ycat[b0:].data_ptr(), w0.data_ptr(), b0_bias.data_ptr(), bn, t, period,
+                                                k0, s0, p0, c0, rows, act[seq0:].data_ptr(), LRELU_SLOPE, st),
+                       "hg_disc_first_conv_fwd")
+            for li, layer in enumerate(self.mids):
+                m = self.mods[1 + li]
+                bias = m.bias.detach().float().contiguous()
+                out = G["act"][1 + li]
+                h_out, rows_out, _ = G["geo"][1 + li]
+                _lib.check(L.hg_conv1d_general_fwd(act[seq0:].data_ptr(), W["fwd"][1 + li].data_ptr(), bias.data_ptr(),
+                                                   nseq, rows, layer.cin, h_out, rows_out, layer.groups_eff,
+                                                   layer.cout, layer.k, layer.stride, layer.pad,
+                                                   out[seq0:].data_ptr(), LRELU_SLOPE, 0, st), "hg_conv1d_general_fwd")
+                act, h, rows = out, h_out, rows_out
+            c_last = G["geo"][-1][2]
+            wp = W["eff"][-1].reshape(c_last, self.kpost).contiguous()
+            W["wp"] = wp
+            bp = self.mods[-1].bias.detach().float().contiguous()
+            _lib.check(L.hg_disc_last_conv_fwd(act[seq0:].data_ptr(), wp.data_ptr(), bp.data_ptr(), nseq, h, rows,
+                                               c_last, self.kpost, G["logit"][seq0:].data_ptr(), st),
+                       "hg_disc_last_conv_fwd")
+        self.G, self.nb, self.nreal, self.t, self.ycat = G, nb, nreal, t, ycat
+        return G
+
+    # ---- losses (on the internal layouts; means are permutation-invariant) -------------------------------------
+    def numel_fmaps(self, nb_half: int) -> List[int]:
+        """element counts of the reference's feature maps for a batch of nb_half items"""
+        return [nb_half * self.period * h * c for h, _, c in self.G["geo"]] + [nb_half * self.period * self.G["geo"][-1][0]]
+
+    def loss_terms(self, acc: torch.Tensor, slot: int) -> None:
+        """acc[slot + 0] += sum (1 - logit_r)^2, [1] += sum logit_g^2, [2] += sum (1 - logit_g)^2,
+        acc[slot + 3 + l] += sum |fmap_r[l] - fmap_g[l]| (l = 0..n_layers, the last one the logits)"""
+        L = _lib.lib()
+        G, period, st = self.G, self.period, _stream()
+        nr = self.nreal * period
+        ng = (self.nb - self.nreal) * period
+        h = G["geo"][-1][0]
+        lr, lg = G["logit"][:nr], G["logit"][nr:]
+        _lib.check(L.hg_loss_sum(lr.data_ptr(), 0, nr * h, 1, 1.0, acc[slot:].data_ptr(), st))
+        _lib.check(L.hg_loss_sum(lg.data_ptr(), 0, ng * h, 1, 0.0, acc[slot + 1:].data_ptr(), st))
+        _lib.check(L.hg_loss_sum(lg.data_ptr(), 0, ng * h, 1, 1.0, acc[slot + 2:].data_ptr(), st))
+        if nr == ng:
+            for l, a in enumerate(G["act"]):
+                n = a[:nr].numel()
+                _lib.check(L.hg_l1_sum_bf16(a.data_ptr(), a[nr:].data_ptr(), n, acc[slot + 3 + l:].data_ptr(), st))
+            _lib.check(L.hg_loss_sum(lr.data_ptr(), lg.data_ptr(), nr * h, 0, 0.0,
+                                     acc[slot + 3 + len(G["act"]):].data_ptr(), st))
+
+    # ---- backward ------------------------------------------------------------------------------------------
+    def backward_d(self) -> None:
+        """discriminator step: d loss_disc / d parameters, both halves (full dgrad + wgrad)."""
+        L = _lib.lib()
+        G, period, st = self.G, self.period, _stream()
+        nr = self.nreal * period
+        ntot = self.nb * period
+        h = G["geo"][-1][0]
+        lr, lg = G["logit"][:nr], G["logit"][nr:]
+        # d/dlogit of mean((1 - lr)^2) + mean(lg^2)
+        _lib.check(L.hg_loss_grad(lr.data_ptr(), 0, nr * h, 1, 1.0, 2.0 / (nr * h), 0.0, G["dlogit"].data_ptr(), st))
+        _lib.check(L.hg_loss_grad(lg.data_ptr(), 0, (ntot - nr) * h, 1, 0.0, 2.0 / ((ntot - nr) * h), 0.0,
+                                  G["dlogit"][nr:].data_ptr(), st))
+        first_part = True
+        for b0, bn, W in self.parts:
+            seq0, nseq = b0 * period, bn * period
+            for bl, w_eff, w_f in zip(self.bwd, W["eff"][1:-1], W["fwd"][1:-1]):
+                bl.pack(w_eff, w_f)
+            self._backward_part(L, G, W, b0, bn, want_wgrad=True, fm=False, dy_audio=None, accumulate=not first_part)
+            first_part = False
+
+    def backward_g(self, dy_audio: torch.Tensor, nfm: List[float]) -> None:
+        """generator step: d (loss_gen + loss_fm) / d y_g_hat accumulated into dy_audio fp32 [B][T] (generated half
+        only, no weight gradients).  nfm[l] = 2 / numel(fmap l) (feature_loss doubles the sum of means)."""
+        L = _lib.lib()
+        G, period, st = self.G, self.period, _stream()
+        nr = self.nreal * period
+        ng = (self.nb - self.nreal) * period
+        h = G["geo"][-1][0]
+        lr, lg = G["logit"][:nr], G["logit"][nr:]
+        # d/dlg of mean((1 - lg)^2) + 2 * mean|lr - lg|
+        _lib.check(L.hg_loss_grad(lg.data_ptr(), lr.data_ptr(), ng * h, 2, 1.0, 2.0 / (ng * h), nfm[-1],
+                                  G["dlogit"][nr:].data_ptr(), st))
+        b0, bn, W = self.parts[-1] if self.spectral else (self.nreal, self.nb - self.nreal, self.parts[0][2])
+        for bl, w_eff, w_f in zip(self.bwd, W["eff"][1:-1], W["fwd"][1:-1]):
+            bl.pack(w_eff, w_f)
+        self._backward_part(L, G, W, self.nreal, self.nb - self.nreal, want_wgrad=False, fm=True,
+                            dy_audio=dy_audio, accumulate=False, nfm=nfm)
+
+    def _backward_part(self, L, G, W, b0: int, bn: int, want_wgrad: bool, fm: bool, dy_audio, accumulate: bool,
+                       nfm: Optional[List[float]] = None) -> None:
+        period, st = self.period, _stream()
+        seq0, nseq = b0 * period, bn * period
+        nr = self.nreal * period
+        geo = G["geo"]
+        nl = len(self.mids)
+        h_last, rows_last, c_last = geo[-1]
+        act_last = G["act"][-1]
+        post = self.mods[-1]
+        dwq = dbq = 0
+        if want_wgrad:
+            self.scratch[: c_last * self.kpost].zero_()
+            self.db.zero_()
+            dwq, dbq = self.scratch.data_ptr(), self.db.data_ptr()
+        # fm_r for the generated half is the real half of the same buffer (seq - nr)
+        fm_r_last = act_last[seq0 - nr:].data_ptr() if fm else 0
+        _lib.check(L.hg_disc_last_conv_bwd(act_last[seq0:].data_ptr(), W["wp"].data_ptr(), G["dlogit"][seq0:].data_ptr(),
+                                           nseq, h_last, rows_last, c_last, self.kpost, LRELU_SLOPE, fm_r_last,
+                                           nfm[nl] if fm else 0.0, G["grad"][-1][seq0:].data_ptr(), dwq, dbq, st),
+                   "hg_disc_last_conv_bwd")
+        if want_wgrad:
+            self._route(L, post, self.scratch, 1, c_last * self.kpost, W, len(self.mods) - 1, accumulate)
+            self._bias(post, self.db[:1], accumulate)
+        for li in reversed(range(nl)):
+            layer = self.mids[li]
+            m = self.mods[1 + li]
+            h_out, rows_out, _ = geo[1 + li]
+            h_in, rows_in, c_in = geo[li]
+            d_out = G["grad"][1 + li][seq0:]
+            a_in = G["act"][li]
+            if want_wgrad:
+                _lib.check(L.hg_colsum_bf16(d_out.data_ptr(), nseq, h_out, rows_out, layer.cout, 0, self.db.data_ptr(),
+                                            st), "hg_colsum_bf16")
+                self._bias(m, self.db[: layer.cout], accumulate)
+                _lib.check(L.hg_conv1d_wgrad(a_in[seq0:].data_ptr(), d_out.data_ptr(), nseq, rows_in, layer.cin, h_out,
+                                             rows_out, layer.groups_eff, layer.cout, layer.k, layer.stride, 1,
+                                             layer.pad, self.dwp.data_ptr(), 0, st), "hg_conv1d_wgrad")
+                cin_g = layer.cin // layer.groups
+                order = (c_int * layer.k)(*layer.order)
+                _lib.check(L.hg_unpack_wgrad_conv(self.dwp.data_ptr(), layer.cout, cin_g, layer.k, layer.cout,
+                                                  layer.cin_tile, layer.cout // layer.groups, layer.merge, order,
+                                                  self.scratch.data_ptr(), st), "hg_unpack_wgrad_conv")
+                self._route(L, m, self.scratch, layer.cout, cin_g * layer.k, W, 1 + li, accumulate)
+            self.bwd[li].dgrad(L, d_out, nseq, h_out, rows_out, rows_in, a_in[seq0:],
+                               a_in[seq0 - nr:] if fm else None, nfm[li] if fm else 0.0, G["grad"][li][seq0:], st)
+        # first conv (Cin = 1)
+        k0, s0, p0, c0 = self.first
+        m0 = self.mods[0]
+        dw0 = db0 = 0
+        if want_wgrad:
+            self.scratch[: c0 * k0].zero_()
+            self.db.zero_()
+            dw0, db0 = self.scratch.data_ptr(), self.db.data_ptr()
+        _lib.check(L.hg_disc_first_conv_bwd(self.ycat[b0:].data_ptr(), W["w0"].data_ptr(), G["grad"][0][seq0:].data_ptr(),
+                                            bn, self.t, period, k0, s0, p0, c0, geo[0][1], dw0, db0,
+                                            _p(dy_audio), st), "hg_disc_first_conv_bwd")
+        if want_wgrad:
+            self._route(L, m0, self.scratch, c0, k0, W, 0, accumulate)
+            self._bias(m0, self.db[:c0], accumulate)
+
+    @staticmethod
+    def _bias(m: nn.Module, db: torch.Tensor, accumulate: bool) -> None:
+        if accumulate:
+            m.bias.grad.add_(db)
+        else:
+            m.bias.grad.copy_(db)
+
+    def _route(self, L, m: nn.Module, dw: torch.Tensor, d0: int, rest: int, W, li: int, accumulate: bool) -> None:
+        if hasattr(m, "weight_orig"):
+            # spectral norm: w = W / sigma with sigma = u^T W v (u, v constants): dW = (dw - <dw, w> u v^T) / sigma
+            w_eff = W["eff"][li].reshape(d0, rest)
+            wo = m.weight_orig
+            u, v, sigma = W["sn"][li]
+            d = dw[: d0 * rest].view(d0, rest)
+            gr = (d - (d * w_eff).sum() * torch.outer(u, v)) / sigma
+            if accumulate:
+                wo.grad.add_(gr.view(wo.shape))
+            else:
+                wo.grad.copy_(gr.view(wo.shape))
+        else:
+            _route_weight_grad(L, m, dw, d0, rest, accumulate)
+
+
+class DiscriminatorTrainer:
+    """MultiPeriodDiscriminator + MultiScaleDiscriminator of one training step."""
+
+    def __init__(self, mpd: MultiPeriodDiscriminator, msd: MultiScaleDiscriminator, device):
+        self.mpd, self.msd, self.device = mpd, msd, device
+        holder = nn.ModuleList([mpd, msd])        # optimizer order of the reference: chain(msd, mpd) — order is free
+        self.flat = FlatParams(holder, device)
+        for d in list(mpd.discriminators) + list(msd.discriminators):
+            d.__dict__.pop("_hg_wcache", None)
+        self.subs_p = [_SubDiscTrainer(d, device) for d in mpd.discriminators]
+        self.subs_s = [_SubDiscTrainer(d, device) for d in msd.discriminators]
+        self.subs = self.subs_p + self.subs_s
+        self.nslots = 12
+        self.acc = torch.zeros(len(self.subs) * self.nslots, dtype=torch.float32, device=device)
+        self.pooled: List[torch.Tensor] = []
+
+    def forward(self, y: torch.Tensor, y_hat: torch.Tensor) -> None:
+        """y, y_hat fp32 [B,1,T] (or [B,T]).  Runs every sub-discriminator on (y ++ y_hat) and accumulates the raw
+        loss sums (self.acc)."""
+        L = _lib.lib()
+        b = y.shape[0]
+        ycat = torch.cat([y.reshape(b, -1), y_hat.reshape(b, -1)], 0).contiguous().float()
+        self.b, self.t = b, ycat.shape[1]
+        self.acc.zero_()
+        self.pooled = [ycat]
+        cur = ycat
+        for i in range(1, len(self.subs_s)):
+            t = cur.shape[1]
+            nxt = torch.empty(2 * b, t // 2 + 1, dtype=torch.float32, device=self.device)
+            _lib.check(L.hg_avgpool_4_2_2_fwd(cur.data_ptr(), 2 * b, t, nxt.data_ptr(), _stream()), "hg_avgpool_4_2_2_fwd")
+            self.pooled.append(nxt)
+            cur = nxt
+        for i, sd in enumerate(self.subs):
+            inp = ycat if i < len(self.subs_p) else self.pooled[i - len(self.subs_p)]
+            sd.forward(inp, b)
+            sd.loss_terms(self.acc, i * self.nslots)
+
+    def losses(self) -> Dict[str, torch.Tensor]:
+        """loss values from the accumulated sums (device tensors, no host sync)."""
+        a = self.acc.view(len(self.subs), self.nslots)
+        out = {}
+        np_ = len(self.subs_p)
+        nlog = torch.tensor([sd.numel_fmaps(self.b)[-1] for sd in self.subs], dtype=torch.float32, device=self.device)
+        d_terms = (a[:, 0] + a[:, 1]) / nlog
+        g_terms = a[:, 2] / nlog
+        out["loss_disc_f"], out["loss_disc_s"] = d_terms[:np_].sum(), d_terms[np_:].sum()
+        out["loss_gen_f"], out["loss_gen_s"] = g_terms[:np_].sum(), g_terms[np_:].sum()
+        fm = []
+        for i, sd in enumerate(self.subs):
+            n = torch.tensor(sd.numel_fmaps(self.b), dtype=torch.float32, device=self.device)
+            fm.append((a[i, 3:3 + n.numel()] / n).sum() * 2)
+        out["loss_fm_f"], out["loss_fm_s"] = torch.stack(fm[:np_]).sum(), torch.stack(fm[np_:]).sum()
+        return out
+
+    def backward_d(self) -> None:
+        for sd in self.subs:
+            sd.backward_d()
+
+    def backward_g(self, dy_audio: torch.Tensor) -> None:
+        """adds d(loss_gen + loss_fm)/d y_hat into dy_audio fp32 [B][T]."""
+        L = _lib.lib()
+        b = self.b
+        for sd in self.subs_p:
+            sd.backward_g(dy_audio, [2.0 / n for n in sd.numel_fmaps(b)])
+        # MSD: scale i sees the (i times) pooled signal; chain the pooling backward from the coarsest scale up
+        grads = [dy_audio] + [torch.zeros(b, p.shape[1], dtype=torch.float32, device=self.device)
+                              for p in self.pooled[1:]]
+        for i, sd in enumerate(self.subs_s):
+            sd.backward_g(grads[i], [2.0 / n for n in sd.numel_fmaps(b)])
+        for i in reversed(range(1, len(grads))):
+            _lib.check(L.hg_avgpool_4_2_2_bwd(grads[i].data_ptr(), b, grads[i - 1].shape[1], grads[i - 1].data_ptr(),
+                                              _stream()), "hg_avgpool_4_2_2_bwd")
+
+
+# ------------------------------------------------------------------------------------------------ the step
+class TrainStep:
+    """One process's share of the UPSTREAM train loop body.  With torch.distributed initialised (NCCL, one process
+    per GPU) the flat gradient buffers are all-reduced (sum) after each backward and AdamW divides by world size —
+    identical to DistributedDataParallel's gradient averaging."""
+
+    def __init__(self, generator: Generator, mpd: MultiPeriodDiscriminator, msd: MultiScaleDiscriminator, h,
+                 device=None, process_group=None):
+        device = torch.device(device if device is not None else "cuda")
+        self.h, self.device = h, device
+        generator.to(device); mpd.to(device); msd.to(device)
+        generator.train(); mpd.train(); msd.train()
+        self.G = GeneratorTrainer(generator, device)
+        self.D = DiscriminatorTrainer(mpd, msd, device)
+        self.lr = h.learning_rate
+        self.betas = (h.adam_b1, h.adam_b2)
+        self.pg = process_group
+        self.world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(process_group)
+
+    def _allreduce(self, flat: FlatParams) -> None:
+        if self.world > 1:
+            torch.distributed.all_reduce(flat.g, group=self.pg)
+
+    def _mel(self, y2d: torch.Tensor) -> torch.Tensor:
+        h = self.h
+        return mel_spectrogram(y2d, h.n_fft, h.num_mels, h.sampling_rate, h.hop_size, h.win_size, h.fmin,
+                               h.fmax_for_loss)
+
+    def step(self, x: torch.Tensor, y: torch.Tensor, y_mel: torch.Tensor, update: bool = True) -> Dict[str, torch.Tensor]:
+        """x [B,80,F] input mel, y [B,1,T] audio, y_mel [B,80,F] loss mel.  Returns the loss tensors (device)."""
+        L = _lib.lib()
+        h = self.h
+        b = x.shape[0]
+        st = _stream()
+        y2 = y.reshape(b, -1).contiguous().float()
+        y_g = self.G.forward(x)                                # [B,1,T]
+        y_g2 = y_g.view(b, -1)
+        out: Dict[str, torch.Tensor] = {}
+        # ---- discriminator step
+        self.D.forward(y2, y_g2)
+        dl = self.D.losses()
+        out["loss_disc_f"], out["loss_disc_s"] = dl["loss_disc_f"], dl["loss_disc_s"]
+        out["loss_disc_all"] = dl["loss_disc_f"] + dl["loss_disc_s"]
+        self.D.backward_d()
+        self._allreduce(self.D.flat)
+        if update:
+            self.D.flat.adamw(self.lr, self.betas, grad_scale=1.0 / self.world)
+        # ---- generator step (through the updated discriminators)
+        mel_g = self._mel(y_g2)
+        n_mel = mel_g.numel()
+        acc = torch.zeros(1, dtype=torch.float32, device=self.device)
+        ym = y_mel.contiguous().float()
+        _lib.check(L.hg_loss_sum(ym.data_ptr(), mel_g.data_ptr(), n_mel, 0, 0.0, acc.data_ptr(), st), "hg_loss_sum")
+        out["loss_mel"] = acc[0] / n_mel * 45
+        dmel = torch.empty_like(mel_g)
+        _lib.check(L.hg_loss_grad(mel_g.data_ptr(), ym.data_ptr(), n_mel, 0, 0.0, 45.0 / n_mel, 0.0, dmel.data_ptr(), st),
+                   "hg_loss_grad")
+        dy = torch.zeros(b, y_g2.shape[1], dtype=torch.float32, device=self.device)
+        key = f'{str(y_g2.device)}_{h.n_fft}_{h.num_mels}_{h.sampling_rate}_{h.hop_size}_{h.win_size}_{h.fmin}_{h.fmax_for_loss}_False'
+        plan = torch_mels[key]
+        _lib.check(L.hg_mel_bwd(plan.handle, y_g2.data_ptr(), dmel.data_ptr(), b, y_g2.shape[1], dy.data_ptr(), st),
+                   "hg_mel_bwd")
+        self.D.forward(y2, y_g2)
+        gl = self.D.losses()
+        for k in ("loss_gen_f", "loss_gen_s", "loss_fm_f", "loss_fm_s"):
+            out[k] = gl[k]
+        out["loss_gen_all"] = gl["loss_gen_s"] + gl["loss_gen_f"] + gl["loss_fm_s"] + gl["loss_fm_f"] + out["loss_mel"]
+        self.D.backward_g(dy)
+        self.dy_audio = dy
+        self.G.backward(dy)
+        self._allreduce(self.G.flat)
+        if update:
+            self.G.flat.adamw(self.lr, self.betas, grad_scale=1.0 / self.world)
+            self.G.invalidate()
+        out["y_g_hat"] = y_g
+        return out

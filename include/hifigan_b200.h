@@ -189,11 +189,98 @@ int hg_mel_num_frames(const hg_mel_plan* plan, int t);
 int hg_mel_fwd(const hg_mel_plan* plan, const float* y, int batch, int t, float* out,
                float* minmax, void* stream);
 
+/* hg_mel_bwd — backward of hg_mel_fwd: dmel fp32 [B][num_mels][frames] (gradient at the log-mel output) ->
+ * dy fp32 [B][T] ADDED to (zero it first).  y is the forward input; the spectrum is recomputed. */
+int hg_mel_bwd(const hg_mel_plan* plan, const float* y, const float* dmel, int batch, int t, float* dy,
+               void* stream);
+
 /* Test hook: runs the mel kernel's per-thread phase functions on the HOST (threads serialised) so
  * the FFT / un-pack / CSR-mel arithmetic can be pinned without a GPU.  host_y, host_out are HOST
  * pointers; works on a plan created without a device. */
 int hg_mel_emulate_host(const hg_mel_plan* plan, const float* host_y, int batch, int t,
                         float* host_out);
+
+/* ==========================================================================================
+ * Training step (UPSTREAM train.py restated in SURVEY.md §3.3; the reference runs these through torch autograd
+ * and torch.optim.AdamW).  Gradients between kernels are bf16 [B][T][C] like the activations; parameter
+ * gradients are fp32.
+ * ========================================================================================== */
+
+/* hg_pack_dgrad_weight: bf16 [ktaps][n][c] -> bf16 [ktaps][c][n] with the taps reversed — the filter bank with
+ * which hg_conv1d_dgrad computes the data gradient of a stride-1 (dilated) conv, pad_left' = (k-1)*dil - pad_left. */
+int hg_pack_dgrad_weight(const void* w_packed, int ktaps, int n, int c, void* out, void* stream);
+
+/* hg_conv1d_dgrad — data gradient on the tcgen05 implicit-GEMM kernel (replaces convolution_backward's input
+ * half for src/models.py:35-42,63-68,104,153-158,208-214):
+ *   out[b,t,n] = ((sum_{j,c} dy[b, t + j*dil - pad_left, blk(n) + c] * w[j][n][c] + fm_coef * sgn(fm_g - fm_r))
+ *                 * (mask_src[b,t,n] > 0 ? 1 : mask_slope) + res0 + res1) * scale
+ * dy bf16 [B][t_dy_rows][c_dy_total], rows >= t_dy_valid read as zero; w_packed bf16 [ktaps][cout][c_dy_total/groups];
+ * mask_src / fm_r / fm_g / res* / out bf16 [B][t_out_rows][cout] (optional except out).  mask_src is the layer
+ * input as the forward stored it (leaky_relu'd: its sign is the sign of the pre-activation); fm_* add the
+ * feature-matching L1 gradient (src/models.py:251-257).  groups > 1: N tile nt (width n_tile) reads dy channel
+ * block nt % groups — the polyphase (phase-major) output of a strided grouped conv's gradient. */
+int hg_conv1d_dgrad(const void* dy, const void* w_packed, int batch, int t_dy_valid, int t_dy_rows, int c_dy_total,
+                    int t_out, int t_out_rows, int groups, int n_tile, int cout, int ktaps, int dilation, int pad_left,
+                    const void* mask_src, float mask_slope, const void* fm_r, const void* fm_g, float fm_coef,
+                    const void* res0, const void* res1, float scale, void* out, void* stream);
+
+/* hg_conv1d_wgrad — weight gradient as a tcgen05 implicit GEMM contracting over time (MN-major operands):
+ *   dw[q][co][ci] (+)= sum_{b, t < t_out} dy[b,t,co] * xv[b, t + row(q), col(q) + blk(co) + ci]
+ * in the packed layout of the forward weight (tap order of hg_conv1d_tap_order, [ktaps][cout][c_total/groups]).
+ * x bf16 [B][t_in_rows][c_total] is the forward input (same zero-padding-rows contract as hg_conv1d_general_fwd),
+ * dy bf16 [B][t_out_rows][cout].  c_total/groups must be 32, 64 or a multiple of 128; cout/groups one of
+ * 32/64/128/256 when groups > 1.  accumulate == 0 zeroes dw first.  Partial sums are added with fp32 atomics. */
+int hg_conv1d_wgrad(const void* x, const void* dy, int batch, int t_in_rows, int c_total, int t_out, int t_out_rows,
+                    int groups, int cout, int ktaps, int stride, int dilation, int pad_left, float* dw_packed,
+                    int accumulate, void* stream);
+
+/* Packed weight gradient -> parameter layout.  conv: dw fp32 [cout][cin_g][k] from [k][rows_p][cin_tile]
+ * (host_tap_order = hg_conv1d_tap_order or NULL for identity; merge = groups merged per block-diagonal tile,
+ * cout_g = output channels per original group).  convtr: dw fp32 [cin][cout][k] from the polyphase
+ * [nshift][stride*cout_p][cin_p]. */
+int hg_unpack_wgrad_conv(const float* dw_packed, int cout, int cin_g, int k, int rows_p, int cin_tile, int cout_g,
+                         int merge, const int* host_tap_order, float* dw, void* stream);
+int hg_unpack_wgrad_convtr(const float* dw_packed, int cin, int cout, int k, int stride, int padding, int cin_p,
+                           int cout_p, float* dw, void* stream);
+
+/* hg_weight_norm_bwd — backward of w = g * v / ||v|| (norm over all dims but 0): dw, v fp32 [dim0][rest],
+ * g fp32 [dim0] -> dv, dg (added to the existing values when accumulate != 0). */
+int hg_weight_norm_bwd(const float* dw, const float* v, const float* g, int dim0, int rest, int accumulate,
+                       float* dv, float* dg, void* stream);
+
+/* hg_colsum_bf16 — bias gradient: out[c] (+)= sum_{b, t < t_valid} x[b][t][c]; x bf16 [B][t_rows][C]. */
+int hg_colsum_bf16(const void* x, int batch, int t_valid, int t_rows, int c, int accumulate, float* out, void* stream);
+
+/* hg_conv_post_tanh_bwd — backward of hg_conv_post_tanh_fwd.  x bf16 [B][T][C] (the activated input), y fp32 [B][T]
+ * (the forward output), dy fp32 [B][T] -> dx bf16 [B][T][C] = gradient at the PRE-activation of x (the
+ * leaky_relu(., in_slope) mask taken from x's sign), dw fp32 [C][k] and db fp32 [1] (both ADDED to; may be NULL).
+ * dpre_ws fp32 [B][T] receives dy * (1 - y^2). */
+int hg_conv_post_tanh_bwd(const void* x, const float* w, const float* y, const float* dy, int batch, int t, int c,
+                          int k, float in_slope, void* dx, float* dpre_ws, float* dw, float* db, void* stream);
+
+/* Discriminator ends, backward.  hg_disc_last_conv_bwd: dx bf16 [S][h_rows][C] = (conv^T(dlogit) + fm_coef *
+ * sgn(x - fm_r)) * lrelu'(x) (x = the last wide layer's activated output, fm_r optional), dw fp32 [C][k] / db
+ * ADDED to (NULL to skip; dx may be NULL too).  hg_disc_first_conv_bwd: dpre bf16 [B*period][h_rows][cout] is the
+ * gradient at the first conv's output (mask applied) -> dw fp32 [cout][k], db fp32 [cout] (ADDED to; NULL to skip)
+ * and / or dy fp32 [B][T] (ADDED to: the gradient reaching the audio, reflect-padded tail folded back).
+ * hg_avgpool_4_2_2_bwd: din fp32 [B][T] += backward of AvgPool1d(4,2,2) from dout fp32 [B][T/2+1]. */
+int hg_disc_last_conv_bwd(const void* x, const float* w, const float* dlogit, int nseq, int h, int h_rows, int c,
+                          int k, float slope, const void* fm_r, float fm_coef, void* dx, float* dw, float* db,
+                          void* stream);
+int hg_disc_first_conv_bwd(const float* y, const float* w, const void* dpre, int batch, int t, int period, int k,
+                           int stride, int pad, int cout, int h_rows, float* dw, float* db, float* dy, void* stream);
+int hg_avgpool_4_2_2_bwd(const float* dout, int batch, int t, float* din, void* stream);
+
+/* Loss gradients (src/models.py:251-282 and the mel L1): mode 0 out = coef * sgn(a - b); mode 1 out = coef * (a - c);
+ * mode 2 out = coef * (a - c) + coef2 * sgn(a - b).  hg_l1_sum_bf16: *out_acc += sum |a - b| over bf16 arrays. */
+int hg_loss_grad(const float* a, const float* b, long long n, int mode, float c, float coef, float coef2, float* out,
+                 void* stream);
+int hg_l1_sum_bf16(const void* a, const void* b, long long n, float* out_acc, void* stream);
+
+/* hg_adamw_step — torch.optim.AdamW on one flat fp32 tensor (decoupled weight decay, bias correction by `step`,
+ * gradients multiplied by grad_scale first: 1/world_size after a sum all-reduce). */
+int hg_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int step, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -106,9 +106,10 @@ def spectral_norm_step(w: Tensor, u: Tensor, v: Tensor, n_iter: int = 1, eps: fl
     """One train-mode forward of torch.nn.utils.spectral_norm (dim=0, n_power_iterations=1, eps=1e-12):
     v <- normalize(W^T u); u <- normalize(W v); sigma = u . (W v).  Returns (W / sigma, u, v)."""
     wm = w.flatten(1)
-    for _ in range(n_iter):
-        v = F.normalize(torch.mv(wm.t(), u), dim=0, eps=eps)
-        u = F.normalize(torch.mv(wm, v), dim=0, eps=eps)
+    with torch.no_grad():   # torch runs the power iteration outside autograd: u, v are constants of sigma
+        for _ in range(n_iter):
+            v = F.normalize(torch.mv(wm.t(), u), dim=0, eps=eps)
+            u = F.normalize(torch.mv(wm, v), dim=0, eps=eps)
     sigma = torch.dot(u, torch.mv(wm, v))
     return w / sigma, u, v
 

@@ -1,0 +1,107 @@
+"""Bring-up driver for the training step (not a pytest): runs TrainStep for two steps from the seeded weights and
+prints, per parameter, our gradient norm vs the reference's (tests/golden/train_step_seed1234.npz), cosines for
+the gradients stored in full, dL/dy_g_hat agreement, losses; optionally timing.
+    python tests/gpu_bringup_train.py [parity|time B]
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import hifigan_b200 as H  # noqa: E402
+from hifigan_b200 import _lib  # noqa: E402
+from hifigan_b200.train import TrainStep  # noqa: E402
+
+CFG = dict(resblock="1", upsample_rates=[8, 8, 2, 2], upsample_kernel_sizes=[16, 16, 4, 4],
+           upsample_initial_channel=512, resblock_kernel_sizes=[3, 7, 11],
+           resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5], [1, 3, 5]], segment_size=8192, num_mels=80, n_fft=1024,
+           hop_size=256, win_size=1024, sampling_rate=22050, fmin=0, fmax=8000, fmax_for_loss=None,
+           learning_rate=2e-4, adam_b1=0.8, adam_b2=0.99)
+
+
+def build():
+    h = H.AttrDict(CFG)
+    torch.manual_seed(1234)
+    G = H.Generator(h)
+    mpd = H.MultiPeriodDiscriminator()
+    msd = H.MultiScaleDiscriminator()
+    return h, TrainStep(G, mpd, msd, h, "cuda"), (G, mpd, msd)
+
+
+def parity():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "train_step_seed1234.npz"))
+    h, ts, (G, mpd, msd) = build()
+    ya = torch.from_numpy(z["audio"]).cuda()
+    x = H.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, 8000)
+    y_mel = H.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, None)
+    for step in (1, 2):
+        out = ts.step(x, ya.unsqueeze(1), y_mel)
+        torch.cuda.synchronize()
+        for k in ("loss_disc_f", "loss_disc_s", "loss_mel", "loss_fm_f", "loss_fm_s", "loss_gen_f", "loss_gen_s"):
+            ref = float(z[f"step{step}_{k}"])
+            print(f"step{step} {k:12s} ours {out[k].item():.5f} ref {ref:.5f} rel {abs(out[k].item() - ref) / abs(ref):.2e}")
+        if step == 1:
+            dy = ts.dy_audio.cpu()
+            ref = torch.from_numpy(z["dy_g_hat"]).reshape(dy.shape)
+            cos = torch.nn.functional.cosine_similarity(dy.flatten(), ref.flatten(), dim=0).item()
+            print(f"dy_g_hat: norm ours {dy.norm():.4e} ref {ref.norm():.4e} cos {cos:.5f}")
+            for name, net in (("g", G), ("mpd", mpd), ("msd", msd)):
+                keys = [str(k) for k in z[f"{name}_keys"]]
+                norms = z[f"{name}_grad_norm"]
+                named = dict(net.named_parameters())
+                worst = []
+                for k, n in zip(keys, norms):
+                    got = named[k].grad.norm().item()
+                    worst.append((abs(got - n) / (n + 1e-12), k, got, n))
+                worst.sort(reverse=True)
+                print(f"{name}: {len(keys)} tensors; worst norm mismatches:")
+                for w in worst[:8]:
+                    print(f"   rel {w[0]:.3e}  {w[1]:45s} ours {w[2]:.4e} ref {w[3]:.4e}")
+                med = sorted(w[0] for w in worst)[len(worst) // 2]
+                print(f"   median rel {med:.3e}")
+            for key in z.files:
+                if "_grad::" in key:
+                    name, k = key.split("_grad::")
+                    net = {"g": G, "mpd": mpd, "msd": msd}[name]
+                    got = dict(net.named_parameters())[k].grad.cpu().flatten()
+                    ref = torch.from_numpy(z[key]).flatten()
+                    cos = torch.nn.functional.cosine_similarity(got, ref, dim=0).item()
+                    print(f"   full {key:55s} cos {cos:.5f} relL2 {(got - ref).norm() / ref.norm():.3e}")
+
+
+def timing(b):
+    h, ts, _ = build()
+    from oracle import hifigan_oracle as O
+    ya = O.synthetic_audio(b, 8192, seed=3).cuda()
+    x = H.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, 8000)
+    y_mel = H.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, None)
+    y = ya.unsqueeze(1)
+    for _ in range(3):
+        ts.step(x, y, y_mel)
+    torch.cuda.synchronize()
+    n0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    ev0.record()
+    iters = 5
+    for _ in range(iters):
+        out = ts.step(x, y, y_mel)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / iters
+    print(json.dumps({"batch": b, "ms_per_step": ms, "segments_per_s": b / ms * 1e3, "wall_ms": (time.time() - t0) / iters * 1e3,
+                      "launches_per_step": (_lib.launch_count() - n0) / iters,
+                      "loss_gen_all": out["loss_gen_all"].item(), "loss_disc_all": out["loss_disc_all"].item()}))
+
+
+if __name__ == "__main__":
+    mode = sys.argv[1] if len(sys.argv) > 1 else "parity"
+    if mode == "parity":
+        parity()
+    else:
+        timing(int(sys.argv[2]) if len(sys.argv) > 2 else 16)

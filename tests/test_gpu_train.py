@@ -1,0 +1,292 @@
+"""Backward-pass kernels against torch autograd in fp32 on the same bf16-rounded operands.
+
+Tolerances: the tensor-core kernels multiply exact bf16 operands and accumulate in fp32, so weight gradients (fp32
+outputs) agree to accumulation-order noise (rel 2e-3 of the tensor's max); data gradients are stored in bf16
+(|err| <= 2^-8 |ref| + eps).
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def H():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    import hifigan_b200
+    hifigan_b200._lib.lib()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return hifigan_b200
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+WGRAD_CASES = [
+    # b, t_in, cin, cout, k, stride, dil, pad, groups
+    (2, 300, 256, 256, 11, 1, 5, 25, 1),     # wide, N = 256
+    (3, 257, 128, 128, 7, 1, 3, 9, 1),       # wide, N = 128
+    (2, 1000, 64, 64, 11, 1, 5, 25, 1),      # narrow SW128: 2 taps per M tile
+    (2, 1000, 64, 64, 3, 1, 1, 1, 1),
+    (2, 2000, 32, 32, 7, 1, 3, 9, 1),        # narrow SW64: 4 taps per M tile
+    (2, 500, 32, 32, 11, 1, 1, 5, 1),
+    (1, 64, 512, 2048, 3, 1, 1, 1, 1),       # polyphase ups0 shape (cout = 8 * 256)
+    (2, 90, 128, 512, 7, 1, 1, 3, 1),        # conv_pre shape (cin 80 padded to 128)
+    (3, 300, 32, 128, 5, 3, 1, 2, 1),        # DiscriminatorP strided layers
+    (2, 911, 128, 512, 5, 3, 1, 2, 1),
+    (2, 100, 512, 1024, 5, 3, 1, 2, 1),
+    (4, 51, 1024, 1024, 5, 1, 1, 2, 1),
+    (2, 1000, 128, 128, 41, 2, 1, 20, 4),    # DiscriminatorS grouped / strided layers
+    (2, 600, 128, 256, 41, 2, 1, 20, 16),
+    (1, 700, 256, 512, 41, 4, 1, 20, 16),
+    (1, 515, 512, 1024, 41, 4, 1, 20, 16),
+    (1, 130, 1024, 1024, 41, 1, 1, 20, 16),
+    (1, 1, 64, 64, 3, 1, 1, 1, 1),           # single time step
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES)
+def test_wgrad_vs_torch_autograd(H, case):
+    from hifigan_b200 import _lib
+    from hifigan_b200.models import _DiscLayer, _round_up
+    L = _lib.lib()
+    b, t, cin, cout, k, s, d, pad, g = case
+    dev = torch.device("cuda")
+    gen = torch.Generator().manual_seed(sum(case))
+    rows = _round_up(t, s)
+    x = torch.zeros(b, rows, cin, dtype=torch.bfloat16, device=dev)
+    x[:, :t] = torch.randn(b, t, cin, generator=gen).to(dev).bfloat16()
+    t_out = (t + 2 * pad - d * (k - 1) - 1) // s + 1
+    rows_out = t_out + 3
+    dy = torch.randn(b, rows_out, cout, generator=gen).to(dev).bfloat16()   # pitch rows hold garbage on purpose
+    layer = _DiscLayer(cin, cout, k, s, pad, g)
+    dwp = torch.full((k, cout, layer.cin_tile), 3.0, dtype=torch.float32, device=dev)
+    _lib.check(L.hg_conv1d_wgrad(x.data_ptr(), dy.data_ptr(), b, rows, cin, t_out, rows_out, layer.groups_eff, cout,
+                                 k, s, d, pad, dwp.data_ptr(), 0, _st()), "hg_conv1d_wgrad")
+    # accumulate = 1 adds a second copy
+    _lib.check(L.hg_conv1d_wgrad(x.data_ptr(), dy.data_ptr(), b, rows, cin, t_out, rows_out, layer.groups_eff, cout,
+                                 k, s, d, pad, dwp.data_ptr(), 1, _st()), "hg_conv1d_wgrad")
+    dw = torch.empty(cout, cin // g, k, dtype=torch.float32, device=dev)
+    from ctypes import c_int
+    order = (c_int * k)(*layer.order)
+    _lib.check(L.hg_unpack_wgrad_conv(dwp.data_ptr(), cout, cin // g, k, cout, layer.cin_tile, cout // g, layer.merge,
+                                      order, dw.data_ptr(), _st()), "hg_unpack_wgrad_conv")
+    torch.cuda.synchronize()
+    w = torch.zeros(cout, cin // g, k, device=dev, requires_grad=True)
+    y = F.conv1d(x[:, :t].float().transpose(1, 2), w, None, stride=s, padding=pad, dilation=d, groups=g)
+    assert y.shape[2] == t_out
+    y.backward(dy[:, :t_out].float().transpose(1, 2))
+    ref = 2 * w.grad
+    err = (dw - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item() + 1e-5, (err, ref.abs().max().item())
+
+
+DGRAD_CASES = [
+    # b, t, cin, cout, k, dil  (stride-1 "same" convs of the Generator)
+    (2, 300, 256, 256, 11, 5), (3, 257, 128, 128, 7, 3), (2, 1000, 64, 64, 3, 1), (2, 777, 32, 32, 7, 5),
+    (2, 129, 128, 512, 7, 1), (8, 4224, 128, 128, 7, 3),
+]
+
+
+@pytest.mark.parametrize("case", DGRAD_CASES)
+def test_dgrad_stride1_vs_torch_autograd(H, case):
+    """dx = (conv^T(dy) * lrelu'(x_in)) + res, with the mask taken from the stored activated input."""
+    from hifigan_b200 import _lib
+    L = _lib.lib()
+    b, t, cin, cout, k, d = case
+    dev = torch.device("cuda")
+    gen = torch.Generator().manual_seed(sum(case))
+    pad = (k - 1) * d // 2
+    w = (torch.randn(cout, cin, k, generator=gen) / (cin * k) ** 0.5).to(dev)
+    wp = torch.empty(k, cout, cin, dtype=torch.bfloat16, device=dev)
+    _lib.check(L.hg_pack_conv1d_weight(w.data_ptr(), 0, cout, cin, k, cin, wp.data_ptr(), _st()))
+    wd = torch.empty(k, cin, cout, dtype=torch.bfloat16, device=dev)
+    _lib.check(L.hg_pack_dgrad_weight(wp.data_ptr(), k, cout, cin, wd.data_ptr(), _st()))
+    x_pre = torch.randn(b, t, cin, generator=gen).to(dev)
+    x_act = F.leaky_relu(x_pre, 0.1).bfloat16()                 # what the forward stored
+    dy = torch.randn(b, t + 2, cout, generator=gen).to(dev).bfloat16()
+    res = torch.randn(b, t, cin, generator=gen).to(dev).bfloat16()
+    out = torch.empty(b, t, cin, dtype=torch.bfloat16, device=dev)
+    _lib.check(L.hg_conv1d_dgrad(dy.data_ptr(), wd.data_ptr(), b, t, t + 2, cout, t, t, 1, 0, cin, k, d,
+                                 (k - 1) * d - pad, x_act.data_ptr(), 0.1, 0, 0, 0.0, res.data_ptr(), 0, 0.5,
+                                 out.data_ptr(), _st()), "hg_conv1d_dgrad")
+    torch.cuda.synchronize()
+    wr = wp.float().permute(1, 2, 0).contiguous()
+    xin = x_act.float().transpose(1, 2).requires_grad_(True)
+    y = F.conv1d(xin, wr, None, dilation=d, padding=pad)
+    y.backward(dy[:, :t].float().transpose(1, 2))
+    mask = torch.where(x_act.float() > 0, 1.0, 0.1)
+    ref = (xin.grad.transpose(1, 2) * mask + res.float()) * 0.5
+    assert bool(((out.float() - ref).abs() <= 2.0 ** -7 * ref.abs() + 2e-3).all())
+
+
+STRIDED_DGRAD_CASES = [
+    # b, t_in, cin, cout, k, stride, pad, groups
+    (3, 300, 32, 128, 5, 3, 2, 1),
+    (2, 911, 128, 512, 5, 3, 2, 1),
+    (2, 100, 512, 1024, 5, 3, 2, 1),
+    (2, 51, 1024, 1024, 5, 1, 2, 1),
+    (2, 1000, 128, 128, 41, 2, 20, 4),
+    (2, 600, 128, 256, 41, 2, 20, 16),
+    (1, 700, 256, 512, 41, 4, 20, 16),
+    (1, 515, 512, 1024, 41, 4, 20, 16),
+    (1, 130, 1024, 1024, 41, 1, 20, 16),
+]
+
+
+@pytest.mark.parametrize("case", STRIDED_DGRAD_CASES)
+def test_dgrad_strided_grouped_vs_torch_autograd(H, case):
+    """Discriminator layers: polyphase data gradient with the feature-matching term and the leaky_relu mask."""
+    from hifigan_b200 import _lib
+    from hifigan_b200.models import _DiscLayer, _round_up
+    from hifigan_b200.train import _DiscBwdLayer
+    L = _lib.lib()
+    b, t, cin, cout, k, s, pad, g = case
+    dev = torch.device("cuda")
+    gen = torch.Generator().manual_seed(sum(case))
+    rows = _round_up(t, s)
+    layer = _DiscLayer(cin, cout, k, s, pad, g)
+    w = (torch.randn(cout, cin // g, k, generator=gen) / (cin // g * k) ** 0.5).to(dev).bfloat16().float()
+    t_out = (t + 2 * pad - k) // s + 1
+    rows_out = t_out + 2
+    dy = torch.randn(b, rows_out, cout, generator=gen).to(dev).bfloat16()
+    act_g = torch.zeros(b, rows, cin, dtype=torch.bfloat16, device=dev)
+    act_g[:, :t] = F.leaky_relu(torch.randn(b, t, cin, generator=gen), 0.1).to(dev).bfloat16()
+    act_r = torch.zeros_like(act_g)
+    act_r[:, :t] = F.leaky_relu(torch.randn(b, t, cin, generator=gen), 0.1).to(dev).bfloat16()
+    bl = _DiscBwdLayer(layer, dev)
+    bl.pack(w, layer.pack(w))
+    out = torch.zeros(b, rows, cin, dtype=torch.bfloat16, device=dev)
+    fm_coef = 0.37
+    bl.dgrad(L, dy, b, t_out, rows_out, rows, act_g, act_r, fm_coef, out, _st())
+    torch.cuda.synchronize()
+    xin = act_g[:, :t].float().transpose(1, 2).requires_grad_(True)
+    y = F.conv1d(xin, w, None, stride=s, padding=pad, groups=g)
+    y.backward(dy[:, :t_out].float().transpose(1, 2))
+    ag, ar = act_g[:, :t].float(), act_r[:, :t].float()
+    ref = (xin.grad.transpose(1, 2) + fm_coef * torch.sign(ag - ar)) * torch.where(ag > 0, 1.0, 0.1)
+    got = out[:, :t].float()
+    assert bool(((got - ref).abs() <= 2.0 ** -7 * ref.abs() + 3e-3).all()), (got - ref).abs().max().item()
+
+
+def test_small_backward_kernels_vs_torch(H):
+    from hifigan_b200 import _lib
+    L = _lib.lib()
+    dev = torch.device("cuda")
+    gen = torch.Generator().manual_seed(5)
+    # column sums (bias gradients)
+    x = torch.randn(3, 50, 64, generator=gen).to(dev).bfloat16()
+    out = torch.empty(64, device=dev)
+    _lib.check(L.hg_colsum_bf16(x.data_ptr(), 3, 47, 50, 64, 0, out.data_ptr(), _st()))
+    assert torch.allclose(out, x[:, :47].float().sum((0, 1)), atol=1e-3)
+    # conv_post + tanh backward
+    b, t, c, k = 2, 700, 32, 7
+    xr = torch.randn(b, t, c, generator=gen).to(dev)
+    xa = F.leaky_relu(xr, 0.01).bfloat16()
+    w = (torch.randn(1, c, k, generator=gen) * 0.1).to(dev)
+    bias = torch.randn(1, generator=gen).to(dev)
+    dy = torch.randn(b, t, generator=gen).to(dev)
+    xin = xa.float().transpose(1, 2).requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    br = bias.clone().requires_grad_(True)
+    y = torch.tanh(F.conv1d(xin, wr, br, padding=3)).squeeze(1)
+    y.backward(dy)
+    dx = torch.empty(b, t, c, dtype=torch.bfloat16, device=dev)
+    dpre = torch.empty(b, t, device=dev)
+    dw = torch.zeros(c, k, device=dev)
+    db = torch.zeros(1, device=dev)
+    _lib.check(L.hg_conv_post_tanh_bwd(xa.data_ptr(), w[0].contiguous().data_ptr(), y.detach().contiguous().data_ptr(),
+                                       dy.data_ptr(), b, t, c, k, 0.01, dx.data_ptr(), dpre.data_ptr(), dw.data_ptr(),
+                                       db.data_ptr(), _st()))
+    torch.cuda.synchronize()
+    ref_dx = xin.grad.transpose(1, 2) * torch.where(xa.float() > 0, 1.0, 0.01)
+    assert bool(((dx.float() - ref_dx).abs() <= 2.0 ** -7 * ref_dx.abs() + 1e-4).all())
+    assert torch.allclose(dw, wr.grad[0], rtol=1e-3, atol=1e-3)
+    assert torch.allclose(db, br.grad, rtol=1e-3, atol=1e-3)
+    # avg-pool backward
+    xin = torch.randn(3, 4097, generator=gen).to(dev).requires_grad_(True)
+    yo = F.avg_pool1d(xin.unsqueeze(1), 4, 2, 2).squeeze(1)
+    do = torch.randn(yo.shape, generator=gen).to(dev)
+    yo.backward(do)
+    din = torch.zeros(3, 4097, device=dev)
+    _lib.check(L.hg_avgpool_4_2_2_bwd(do.data_ptr(), 3, 4097, din.data_ptr(), _st()))
+    assert torch.allclose(din, xin.grad, atol=1e-6)
+    # weight-norm backward
+    v = torch.randn(40, 30, 7, generator=gen).to(dev)
+    g = torch.rand(40, 1, 1, generator=gen).to(dev) + 0.5
+    vv, gg = v.clone().requires_grad_(True), g.clone().requires_grad_(True)
+    wn = torch._weight_norm(vv, gg, 0)
+    dwn = torch.randn(40, 30, 7, generator=gen).to(dev)
+    wn.backward(dwn)
+    dv, dg = torch.empty_like(v), torch.empty(40, device=dev)
+    _lib.check(L.hg_weight_norm_bwd(dwn.data_ptr(), v.data_ptr(), g.data_ptr(), 40, 210, 0, dv.data_ptr(),
+                                    dg.data_ptr(), _st()))
+    assert torch.allclose(dv, vv.grad, rtol=1e-4, atol=1e-5) and torch.allclose(dg, gg.grad.flatten(), rtol=1e-4, atol=1e-5)
+    # AdamW, three steps
+    p = torch.randn(1000, generator=gen).to(dev)
+    ref_p = p.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([ref_p], lr=2e-4, betas=(0.8, 0.99))
+    m, vv2 = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 4):
+        gr = torch.randn(1000, generator=gen).to(dev)
+        ref_p.grad = gr.clone()
+        opt.step()
+        _lib.check(L.hg_adamw_step(p.data_ptr(), gr.data_ptr(), m.data_ptr(), vv2.data_ptr(), 1000, 2e-4, 0.8, 0.99,
+                                   1e-8, 0.01, step, 1.0, _st()))
+    assert torch.allclose(p, ref_p.detach(), rtol=1e-5, atol=1e-6)
+
+
+def test_disc_end_backward_kernels_vs_torch(H):
+    from hifigan_b200 import _lib
+    L = _lib.lib()
+    dev = torch.device("cuda")
+    gen = torch.Generator().manual_seed(9)
+    # last conv (Cout = 1): data + weight gradient with the feature-matching term
+    s_, h, rows, c, k = 6, 51, 52, 1024, 3
+    x = torch.zeros(s_, rows, c, dtype=torch.bfloat16, device=dev)
+    x[:, :h] = F.leaky_relu(torch.randn(s_, h, c, generator=gen), 0.1).to(dev).bfloat16()
+    fr = torch.zeros_like(x)
+    fr[:, :h] = F.leaky_relu(torch.randn(s_, h, c, generator=gen), 0.1).to(dev).bfloat16()
+    w = (torch.randn(1, c, k, generator=gen) * 0.05).to(dev)
+    dl = torch.randn(s_, h, generator=gen).to(dev)
+    xin = x[:, :h].float().transpose(1, 2).requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    br = torch.zeros(1, device=dev, requires_grad=True)
+    F.conv1d(xin, wr, br, padding=1).squeeze(1).backward(dl)
+    dx = torch.zeros_like(x)
+    dw, db = torch.zeros(c, k, device=dev), torch.zeros(1, device=dev)
+    _lib.check(L.hg_disc_last_conv_bwd(x.data_ptr(), w[0].contiguous().data_ptr(), dl.data_ptr(), s_, h, rows, c, k,
+                                       0.1, fr.data_ptr(), 0.25, dx.data_ptr(), dw.data_ptr(), db.data_ptr(), _st()))
+    torch.cuda.synchronize()
+    xa, ra = x[:, :h].float(), fr[:, :h].float()
+    ref = (xin.grad.transpose(1, 2) + 0.25 * torch.sign(xa - ra)) * torch.where(xa > 0, 1.0, 0.1)
+    assert bool(((dx[:, :h].float() - ref).abs() <= 2.0 ** -7 * ref.abs() + 1e-4).all())
+    assert torch.allclose(dw, wr.grad[0], rtol=1e-3, atol=1e-3) and torch.allclose(db, br.grad, rtol=1e-3, atol=1e-3)
+    # first conv (Cin = 1) with the period view and reflect pad
+    for period, k0, s0, p0, c0, t in [(3, 5, 3, 2, 32, 1000), (1, 15, 1, 7, 128, 777), (7, 5, 3, 2, 32, 8192)]:
+        b = 2
+        y = torch.randn(b, t, generator=gen).to(dev)
+        w0 = torch.randn(c0, k0, generator=gen).to(dev)
+        yy = y.clone().requires_grad_(True)
+        ww = w0.clone().requires_grad_(True)
+        bb = torch.zeros(c0, device=dev, requires_grad=True)
+        sig = yy.unsqueeze(1)
+        if t % period:
+            sig = F.pad(sig, (0, period - t % period), "reflect")
+        hh = sig.shape[-1] // period
+        o = F.conv2d(sig.view(b, 1, hh, period), ww.view(c0, 1, k0, 1), bb, stride=(s0, 1), padding=(p0, 0))
+        h_out = o.shape[2]
+        dpre = torch.randn(b * period, h_out + 1, c0, generator=gen).to(dev).bfloat16()
+        o.backward(dpre[:, :h_out].float().view(b, period, h_out, c0).permute(0, 3, 2, 1))
+        dw0, db0, dyy = torch.zeros(c0, k0, device=dev), torch.zeros(c0, device=dev), torch.zeros(b, t, device=dev)
+        _lib.check(L.hg_disc_first_conv_bwd(y.data_ptr(), w0.data_ptr(), dpre.data_ptr(), b, t, period, k0, s0, p0, c0,
+                                            h_out + 1, dw0.data_ptr(), db0.data_ptr(), dyy.data_ptr(), _st()))
+        torch.cuda.synchronize()
+        assert torch.allclose(dw0, ww.grad, rtol=2e-3, atol=2e-2), (dw0 - ww.grad).abs().max()
+        assert torch.allclose(db0, bb.grad, rtol=2e-3, atol=2e-2)
+        assert torch.allclose(dyy, yy.grad, rtol=2e-3, atol=2e-3), (dyy - yy.grad).abs().max()

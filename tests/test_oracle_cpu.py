@@ -161,3 +161,43 @@ def test_crop_or_pad_rule():
     a = torch.arange(10.0).unsqueeze(0)
     assert O.crop_or_pad_segment(a, 4, 3).tolist() == [[3.0, 4.0, 5.0, 6.0]]
     assert O.crop_or_pad_segment(a, 12, 0).tolist() == [list(range(10)) + [0.0, 0.0]]
+
+
+def test_training_step_oracle_vs_reference_golden():
+    """oracle/train_oracle.py (autograd over the oracle's restated forward + torch AdamW) against the REFERENCE's
+    own modules run through the same two steps (tests/golden/train_step_seed1234.npz): losses of both steps,
+    dL/dy_g_hat, every parameter-gradient norm and the stored full gradients.  fp32 on both sides: 2e-3 relative
+    (the two differ only in op ordering: weight-norm fold, reflect pad / view order, mel via rfft)."""
+    import hifigan_b200 as H
+    from oracle import hifigan_oracle as O
+    from oracle import train_oracle as TO
+    z = load_npz("train_step_seed1234.npz")
+    h = H.AttrDict(O.config("v1"))
+    torch.manual_seed(1234)
+    G = H.Generator(h)
+    mpd = H.MultiPeriodDiscriminator()
+    msd = H.MultiScaleDiscriminator()
+    sd_g, sd_p, sd_s = (TO.leaf_params(m.state_dict()) for m in (G, mpd, msd))
+    ya = torch.from_numpy(z["audio"])
+    x = O.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, 8000)
+    y_mel = O.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, None)
+    optims = TO.make_optimizers(sd_g, sd_p, sd_s, h)
+    for step in (1, 2):
+        losses, gg, gp, gs, y_g, dy_g = TO.train_step(sd_g, sd_p, sd_s, h, x, ya.unsqueeze(1), y_mel, optims=optims)
+        for k in ("loss_disc_f", "loss_disc_s", "loss_mel", "loss_fm_f", "loss_fm_s", "loss_gen_f", "loss_gen_s"):
+            ref = float(z[f"step{step}_{k}"])
+            assert abs(losses[k] - ref) <= 2e-3 * abs(ref), (step, k, losses[k], ref)
+        if step == 1:
+            ref_dy = torch.from_numpy(z["dy_g_hat"])
+            assert (dy_g - ref_dy).norm() <= 2e-3 * ref_dy.norm()
+            for name, grads in (("g", gg), ("mpd", gp), ("msd", gs)):
+                keys = [str(k) for k in z[f"{name}_keys"]]
+                norms = z[f"{name}_grad_norm"]
+                for k, n in zip(keys, norms):
+                    assert abs(float(grads[k].norm()) - n) <= 2e-3 * n + 1e-7, (name, k, float(grads[k].norm()), n)
+            for key in z.files:
+                if "_grad::" in key:
+                    name, k = key.split("_grad::")
+                    got = {"g": gg, "mpd": gp, "msd": gs}[name][k]
+                    ref = torch.from_numpy(z[key])
+                    assert (got - ref).norm() <= 2e-3 * ref.norm() + 1e-7, key
