@@ -290,3 +290,113 @@ def test_disc_end_backward_kernels_vs_torch(H):
         assert torch.allclose(dw0, ww.grad, rtol=2e-3, atol=2e-2), (dw0 - ww.grad).abs().max()
         assert torch.allclose(db0, bb.grad, rtol=2e-3, atol=2e-2)
         assert torch.allclose(dyy, yy.grad, rtol=2e-3, atol=2e-3), (dyy - yy.grad).abs().max()
+
+
+# ------------------------------------------------------------------------------------------ the full step
+def _seeded_step(H):
+    from oracle import hifigan_oracle as O
+    from hifigan_b200.train import TrainStep
+    h = H.AttrDict(O.config("v1"))
+    torch.manual_seed(1234)
+    G = H.Generator(h)
+    mpd = H.MultiPeriodDiscriminator()
+    msd = H.MultiScaleDiscriminator()
+    sds = [{k: v.detach().clone() for k, v in m.state_dict().items()} for m in (G, mpd, msd)]
+    return h, TrainStep(G, mpd, msd, h, "cuda"), (G, mpd, msd), sds
+
+
+LOSS_KEYS = ("loss_disc_f", "loss_disc_s", "loss_mel", "loss_fm_f", "loss_fm_s", "loss_gen_f", "loss_gen_s")
+
+
+def test_train_step_vs_reference_golden(H):
+    """Two full UPSTREAM steps (G fwd, D step + AdamW, G step through the updated D + AdamW) against the
+    REFERENCE's own modules (tests/golden/train_step_seed1234.npz, torch autograd + torch.optim.AdamW, CPU fp32).
+    Tolerances for the declared bf16-operand / fp32-accumulate numerics: losses 2e-2 relative
+    (measured 3e-4), every parameter-gradient norm 5e-2 relative (measured <= 2.9e-2), gradients stored in full:
+    cosine >= 0.999 and rel-L2 <= 5e-2, dL/dy_g_hat cosine >= 0.998.  Step-2 losses pin both AdamW updates."""
+    from conftest import load_npz
+    z = load_npz("train_step_seed1234.npz")
+    h, ts, (G, mpd, msd), _ = _seeded_step(H)
+    ya = torch.from_numpy(z["audio"]).cuda()
+    x = H.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, 8000)
+    y_mel = H.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, None)
+    for step in (1, 2):
+        out = ts.step(x, ya.unsqueeze(1), y_mel)
+        for k in LOSS_KEYS:
+            ref = float(z[f"step{step}_{k}"])
+            assert abs(out[k].item() - ref) <= 2e-2 * abs(ref), (step, k, out[k].item(), ref)
+        if step > 1:
+            continue
+        dy, ref = ts.dy_audio.cpu().flatten(), torch.from_numpy(z["dy_g_hat"]).flatten()
+        assert F.cosine_similarity(dy, ref, dim=0).item() >= 0.998
+        for name, net in (("g", G), ("mpd", mpd), ("msd", msd)):
+            named = dict(net.named_parameters())
+            for k, n in zip([str(k) for k in z[f"{name}_keys"]], z[f"{name}_grad_norm"]):
+                got = named[k].grad.norm().item()
+                assert abs(got - n) <= 5e-2 * n + 1e-9, (name, k, got, n)
+        for key in z.files:
+            if "_grad::" not in key:
+                continue
+            name, k = key.split("_grad::")
+            got = dict({"g": G, "mpd": mpd, "msd": msd}[name].named_parameters())[k].grad.cpu().flatten()
+            ref = torch.from_numpy(z[key]).flatten()
+            assert F.cosine_similarity(got, ref, dim=0).item() >= 0.999, key
+            assert (got - ref).norm() <= 5e-2 * ref.norm(), key
+
+
+def test_train_step_every_gradient_vs_oracle(H):
+    """Every one of the 388 parameter gradients of one step against autograd over the CPU oracle
+    (oracle/train_oracle.py, pinned to the reference by tests/test_oracle_cpu.py), batch of 3 ragged-content
+    segments: per-tensor cosine >= 0.995 and rel-L2 <= 0.1 (bf16 activation gradients; the worst tensors are the
+    bias gradients of the 32-channel stage, sums over 8192 x B bf16 values)."""
+    from oracle import hifigan_oracle as O
+    from oracle import train_oracle as TO
+    h, ts, (G, mpd, msd), sds = _seeded_step(H)
+    ya = O.synthetic_audio(3, 8192, seed=11)
+    ya[2, 5000:] = 0.0                                  # a zero-padded tail, as MelDataset pads short files
+    x_ref = O.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, 8000)
+    y_mel_ref = O.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, None)
+    sd_g, sd_p, sd_s = (TO.leaf_params(sd) for sd in sds)
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    losses, gg, gp, gs, y_g, dy_g = TO.train_step(sd_g, sd_p, sd_s, h, x_ref, ya.unsqueeze(1), y_mel_ref)
+    yc = ya.cuda()
+    out = ts.step(H.mel_spectrogram(yc, 1024, 80, 22050, 256, 1024, 0, 8000), yc.unsqueeze(1),
+                  H.mel_spectrogram(yc, 1024, 80, 22050, 256, 1024, 0, None))
+    for k in LOSS_KEYS:
+        assert abs(out[k].item() - losses[k]) <= 2e-2 * abs(losses[k]), (k, out[k].item(), losses[k])
+    worst = (1.0, "")
+    for net, grads in ((G, gg), (mpd, gp), (msd, gs)):
+        for k, p in net.named_parameters():
+            got, ref = p.grad.cpu().flatten(), grads[k].flatten()
+            cos = F.cosine_similarity(got, ref, dim=0).item()
+            rel = ((got - ref).norm() / (ref.norm() + 1e-12)).item()
+            worst = min(worst, (cos, k))
+            assert cos >= 0.995 and rel <= 0.1, (k, cos, rel)
+    print("worst cosine", worst)
+
+
+def test_train_step_v3_and_no_update(H):
+    """ResBlock2 generator (V3) through the same step; update=False leaves every parameter untouched."""
+    from oracle import hifigan_oracle as O
+    from oracle import train_oracle as TO
+    from hifigan_b200.train import TrainStep
+    h = H.AttrDict(O.config("v3"))
+    torch.manual_seed(7)
+    G, mpd, msd = H.Generator(h), H.MultiPeriodDiscriminator(), H.MultiScaleDiscriminator()
+    sds = [{k: v.detach().clone() for k, v in m.state_dict().items()} for m in (G, mpd, msd)]
+    ts = TrainStep(G, mpd, msd, h, "cuda")
+    ya = O.synthetic_audio(2, 8192, seed=2)
+    sd_g, sd_p, sd_s = (TO.leaf_params(sd) for sd in sds)
+    losses, gg, _, _, _, _ = TO.train_step(sd_g, sd_p, sd_s, h, O.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, 8000),
+                                           ya.unsqueeze(1), O.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, None),
+                                           update=False)
+    yc = ya.cuda()
+    before = ts.G.flat.p.clone(), ts.D.flat.p.clone()
+    out = ts.step(H.mel_spectrogram(yc, 1024, 80, 22050, 256, 1024, 0, 8000), yc.unsqueeze(1),
+                  H.mel_spectrogram(yc, 1024, 80, 22050, 256, 1024, 0, None), update=False)
+    assert torch.equal(before[0], ts.G.flat.p) and torch.equal(before[1], ts.D.flat.p)
+    for k in LOSS_KEYS:
+        assert abs(out[k].item() - losses[k]) <= 2e-2 * abs(losses[k]), (k, out[k].item(), losses[k])
+    for k, p in G.named_parameters():
+        got, ref = p.grad.cpu().flatten(), gg[k].flatten()
+        assert F.cosine_similarity(got, ref, dim=0).item() >= 0.995, k
