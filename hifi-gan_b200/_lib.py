@@ -97,6 +97,8 @@ _SIGNATURES = {
     "hg_unpack_wgrad_conv": (c_int, [c_void_p] + [c_int] * 7 + [POINTER(c_int), c_void_p, c_void_p]),
     "hg_unpack_wgrad_convtr": (c_int, [c_void_p] + [c_int] * 7 + [c_void_p, c_void_p]),
     "hg_weight_norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "hg_fold_weight_norm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "hg_pack_disc_weight": (c_int, [c_void_p] + [c_int] * 7 + [c_void_p, c_void_p, c_void_p]),
     "hg_colsum_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hg_conv_post_tanh_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -108,7 +110,7 @@ _SIGNATURES = {
                              c_void_p]),
     "hg_l1_sum_bf16": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_void_p, c_void_p]),
     "hg_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_float, c_float, c_float,
-                              c_float, c_float, c_int, c_float, c_void_p]),
+                              c_float, c_float, c_int, c_void_p, c_float, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -52,10 +52,12 @@ __global__ void pack_dgrad_kernel(const __nv_bfloat16* __restrict__ w, int k, in
 }
 
 // out[c] (+)= sum over (b, t < t_valid) of x[b][t][c];  x bf16 [B][t_rows][C]
+// thread = (row lane, 8-channel vector); a block reduces its rows in registers, then across row lanes through
+// shared memory, and issues ONE atomic per channel.
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __nv_bfloat16* __restrict__ x, int t_valid, int t_rows, int c, int rows_per_block,
               float* __restrict__ out) {
-  // thread = (row lane, 8-channel vector); block covers rows_per_block rows of one batch item
+  extern __shared__ float part[];                // [lanes][c]
   const int vecs = c / 8;
   const int b = blockIdx.y;
   const int r0 = blockIdx.x * rows_per_block;
@@ -72,8 +74,13 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, int t_valid, int t_rows, int 
       acc[4] += a2.x; acc[5] += a2.y; acc[6] += a3.x; acc[7] += a3.y;
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e)
-      if (acc[e] != 0.f) atomicAdd(out + vq * 8 + e, acc[e]);
+    for (int e = 0; e < 8; ++e) part[rl * c + vq * 8 + e] = acc[e];
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float sum = 0.f;
+    for (int l = 0; l < lanes; ++l) sum += part[l * c + ch];
+    atomicAdd(out + ch, sum);
   }
 }
 
@@ -213,81 +220,117 @@ disc_last_bwd_dw_kernel(const __nv_bfloat16* __restrict__ x, const float* __rest
 }
 
 // discriminator first conv (Cin = 1) backward.  dpre bf16 [S][h_rows][cout] is the gradient at the conv output
-// (leaky_relu mask already applied by the producer).  One thread = one output position.
+// (leaky_relu mask already applied by the producer).
 //   dw[co][j] += sum dpre[s,ho,co] * yin(s, ho*stride + j - pad);  db[co] += sum dpre
 //   dy[b, i]  += sum_{co,j} dpre[s,ho,co] * w[co][j]   (reflect-padded tail folded back, src/models.py:146-151)
-__global__ void __launch_bounds__(128)
+// A block walks kFirstChunk output positions of one sequence in tiles of 128: the dpre tile and the k input
+// samples of every position are staged in shared memory; the weight gradient is a [cout x 128] x [128 x (k+1)]
+// product accumulated in registers across tiles (column k is the bias), the audio gradient one thread pair per
+// position.  One atomic per output per block.
+constexpr int kFirstTile = 128;
+constexpr int kFirstChunk = 2048;
+constexpr int kFirstK = 16;
+
+__global__ void __launch_bounds__(256)
 disc_first_bwd_kernel(const float* __restrict__ y, const float* __restrict__ w, const __nv_bfloat16* __restrict__ dpre,
                       int t, int period, int h_in, int h_out, int h_rows, int k, int stride, int pad, int cout,
                       float* __restrict__ dw, float* __restrict__ db, float* __restrict__ dy) {
-  extern __shared__ float smf[];
-  float* ws = smf;                    // [k][cout]
-  float* acc_w = smf + k * cout;      // [k][cout] block partial sums
-  float* acc_b = acc_w + k * cout;    // [cout]
-  for (int i = threadIdx.x; i < k * cout; i += blockDim.x) {
+  extern __shared__ __align__(16) uint8_t smb[];
+  const int pitch = cout + 2;                                   // odd word pitch: column reads are conflict-free
+  float* ws = reinterpret_cast<float*>(smb);                    // [k][cout]
+  float* xin = ws + k * cout;                                   // [tile][kFirstK + 1]  (last column = 1: bias)
+  int* xidx = reinterpret_cast<int*>(xin + kFirstTile * (kFirstK + 1));   // [tile][kFirstK]
+  __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(xidx + kFirstTile * kFirstK);   // [tile][pitch]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < k * cout; i += 256) {
     const int j = i / cout, co = i % cout;
     ws[i] = w[co * k + j];
-    acc_w[i] = 0.f;
   }
-  for (int i = threadIdx.x; i < cout; i += blockDim.x) acc_b[i] = 0.f;
-  __syncthreads();
   const int seq = blockIdx.y;
   const int b = seq / period, wcol = seq % period;
-  const int ho = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = ho < h_out;
-  float xin[16];
-  int xidx[16];
+  const int p0 = blockIdx.x * kFirstChunk;
+  const int p1 = min(h_out, p0 + kFirstChunk);
+  const int n_out = (k + 1) * cout;                             // weight + bias gradient entries
+  float acc[8];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    float v = 0.f;
-    int idx = -1;
-    if (live && j < k) {
-      const int hh = ho * stride + j - pad;
-      if (hh >= 0 && hh < h_in) {
-        int i = hh * period + wcol;
-        if (i >= t) i = 2 * (t - 1) - i;
-        idx = i;
-        v = y[static_cast<size_t>(b) * t + i];
-      }
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int q0 = p0; q0 < p1; q0 += kFirstTile) {
+    __syncthreads();
+    // stage dpre rows (zero past the end) and the input samples of each position
+    const int vec_per_row = cout / 2;                           // bf16x2 words
+    for (int i = tid; i < kFirstTile * vec_per_row; i += 256) {
+      const int r = i / vec_per_row, v = i % vec_per_row;
+      const int ho = q0 + r;
+      uint32_t val = 0;
+      if (ho < p1) val = reinterpret_cast<const uint32_t*>(dpre + (static_cast<size_t>(seq) * h_rows + ho) * cout)[v];
+      reinterpret_cast<uint32_t*>(dp + r * pitch)[v] = val;
     }
-    xin[j] = v; xidx[j] = idx;
-  }
-  float gy[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) gy[j] = 0.f;
-  const __nv_bfloat16* drow = dpre + (static_cast<size_t>(seq) * h_rows + (live ? ho : 0)) * cout;
-  const int lane = threadIdx.x & 31;
-  for (int co = 0; co < cout; ++co) {
-    const float d = live ? __bfloat162float(drow[co]) : 0.f;
+    for (int i = tid; i < kFirstTile * (kFirstK + 1); i += 256) {
+      const int r = i / (kFirstK + 1), j = i % (kFirstK + 1);
+      const int ho = q0 + r;
+      float v = 0.f;
+      int idx = -1;
+      if (j == kFirstK) {
+        v = 1.f;
+      } else if (j < k && ho < p1) {
+        const int hh = ho * stride + j - pad;
+        if (hh >= 0 && hh < h_in) {
+          int ii = hh * period + wcol;
+          if (ii >= t) ii = 2 * (t - 1) - ii;
+          idx = ii;
+          v = y[static_cast<size_t>(b) * t + ii];
+        }
+      }
+      xin[i] = v;
+      if (j < kFirstK) xidx[r * kFirstK + j] = idx;
+    }
+    __syncthreads();
     if (dw) {
-      const float bs = warp_sum(d);
-      if (lane == 0) atomicAdd(acc_b + co, bs);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if (j < k) {
-          const float s = warp_sum(d * xin[j]);
-          if (lane == 0) atomicAdd(acc_w + j * cout + co, s);
+      for (int i = 0; i < 8; ++i) {
+        const int o = tid + 256 * i;
+        if (o < n_out) {
+          const int j = o / cout, co = o % cout;
+          const int col = j == k ? kFirstK : j;
+          float a = 0.f;
+          for (int r = 0; r < kFirstTile; ++r) a += __bfloat162float(dp[r * pitch + co]) * xin[r * (kFirstK + 1) + col];
+          acc[i] += a;
         }
       }
     }
     if (dy) {
+      const int r = tid & (kFirstTile - 1), half = tid >> 7;   // two threads per position, half of the channels each
+      if (q0 + r < p1) {
+        float gy[kFirstK];
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (j < k) gy[j] += d * ws[j * cout + co];
+        for (int j = 0; j < kFirstK; ++j) gy[j] = 0.f;
+        const int c0 = half * (cout / 2), c1 = c0 + cout / 2;
+        for (int co = c0; co < c1; ++co) {
+          const float d = __bfloat162float(dp[r * pitch + co]);
+#pragma unroll
+          for (int j = 0; j < kFirstK; ++j)
+            if (j < k) gy[j] += d * ws[j * cout + co];
+        }
+#pragma unroll
+        for (int j = 0; j < kFirstK; ++j) {
+          if (j < k) {
+            const int idx = xidx[r * kFirstK + j];
+            if (idx >= 0) atomicAdd(dy + static_cast<size_t>(b) * t + idx, gy[j]);
+          }
+        }
+      }
     }
-  }
-  if (dy && live) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (j < k && xidx[j] >= 0) atomicAdd(dy + static_cast<size_t>(b) * t + xidx[j], gy[j]);
   }
   if (dw) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < k * cout; i += blockDim.x) {
-      const int j = i / cout, co = i % cout;
-      atomicAdd(dw + co * k + j, acc_w[i]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int o = tid + 256 * i;
+      if (o < n_out) {
+        const int j = o / cout, co = o % cout;
+        if (j == k) atomicAdd(db + co, acc[i]);
+        else atomicAdd(dw + co * k + j, acc[i]);
+      }
     }
-    for (int i = threadIdx.x; i < cout; i += blockDim.x) atomicAdd(db + i, acc_b[i]);
   }
 }
 
@@ -397,7 +440,12 @@ weight_norm_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ v
 // torch.optim.AdamW step on one flat fp32 tensor
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
-                             float bc1, float bc2_sqrt, float gscale) {
+                             float bc1, float bc2_sqrt, float gscale, const int* __restrict__ dev_step) {
+  if (dev_step) {   // step counter kept on the device so a captured CUDA graph advances it
+    const float st = static_cast<float>(*dev_step);
+    bc1 = 1.f - powf(b1, st);
+    bc2_sqrt = sqrtf(1.f - powf(b2, st));
+  }
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x) {
     const float gi = g[i] * gscale;
     float pi = p[i] * (1.f - lr * wd);
@@ -406,6 +454,61 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
     m[i] = mi; v[i] = vi;
     pi -= (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
     p[i] = pi;
+  }
+}
+
+// w_eff[r][:] = g[r] * v[r][:] / ||v[r]||   (weight_norm fold, fp32; g == NULL copies)
+__global__ void __launch_bounds__(256)
+fold_weight_kernel(const float* __restrict__ v, const float* __restrict__ g, int rest, float* __restrict__ out) {
+  __shared__ float red[32];
+  const int r = blockIdx.x;
+  const float* vr = v + static_cast<size_t>(r) * rest;
+  float scale = 1.f;
+  if (g) {
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < rest; i += blockDim.x) ss += vr[i] * vr[i];
+    ss = block_sum(ss, red);
+    scale = ss > 0.f ? g[r] / sqrtf(ss) : 0.f;
+  }
+  for (int i = threadIdx.x; i < rest; i += blockDim.x) out[static_cast<size_t>(r) * rest + i] = vr[i] * scale;
+}
+
+struct DiscPackArgs {
+  int cout, cin_g, k, merge, cout_g, cin_tile;      // forward pack
+  int cin, groups, stride, pad, nshift, shift_min, cout_tile;   // dgrad pack
+  int order[64];
+};
+
+// forward pack: fp32 [cout][cin_g][k] -> bf16 [q][cout][cin_tile] (taps in kernel order, groups merged block-diagonally)
+__global__ void pack_disc_fwd_kernel(const float* __restrict__ w, const DiscPackArgs a, __nv_bfloat16* __restrict__ out) {
+  const long long n = static_cast<long long>(a.k) * a.cout * a.cin_tile;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x) {
+    const int ct = static_cast<int>(i % a.cin_tile);
+    const int co = static_cast<int>((i / a.cin_tile) % a.cout);
+    const int q = static_cast<int>(i / (static_cast<long long>(a.cin_tile) * a.cout));
+    const int slot = ct / a.cin_g, own = (co / a.cout_g) % a.merge;
+    float v = 0.f;
+    if (slot == own) v = w[(static_cast<size_t>(co) * a.cin_g + (ct - slot * a.cin_g)) * a.k + a.order[q]];
+    out[i] = __float2bfloat16(v);
+  }
+}
+
+// dgrad (polyphase) pack: fp32 [cout][cin_g][k] -> bf16 [m][rho * cin + ci][cc], cc = dy channel inside the
+// (merged) group tile of ci;  j = rho + pad - stride * (m + shift_min)
+__global__ void pack_disc_dgrad_kernel(const float* __restrict__ w, const DiscPackArgs a, __nv_bfloat16* __restrict__ out) {
+  const long long n = static_cast<long long>(a.nshift) * a.stride * a.cin * a.cout_tile;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x) {
+    const int cc = static_cast<int>(i % a.cout_tile);
+    long long r = i / a.cout_tile;
+    const int ci = static_cast<int>(r % a.cin); r /= a.cin;
+    const int rho = static_cast<int>(r % a.stride);
+    const int m = static_cast<int>(r / a.stride);
+    const int g = ci / a.cin_g;
+    const int co = (g / a.merge) * a.cout_tile + cc;
+    const int j = rho + a.pad - a.stride * (m + a.shift_min);
+    float v = 0.f;
+    if (co / a.cout_g == g && j >= 0 && j < a.k) v = w[(static_cast<size_t>(co) * a.cin_g + (ci - g * a.cin_g)) * a.k + j];
+    out[i] = __float2bfloat16(v);
   }
 }
 
@@ -432,9 +535,12 @@ extern "C" int hg_colsum_bf16(const void* x, int batch, int t_valid, int t_rows,
   HG_REQUIRE(x && out && batch > 0 && batch <= 65535 && t_valid > 0 && t_rows >= t_valid, "hg_colsum_bf16: bad sizes");
   HG_REQUIRE(c % 8 == 0 && c / 8 <= 256, "hg_colsum_bf16: c must be a multiple of 8, at most 2048");
   if (!accumulate) HG_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * c, S(stream)));
-  const int rows_per_block = 256;
+  // enough blocks to fill the machine, few enough that the per-channel atomics stay cheap
+  int rows_per_block = static_cast<int>((static_cast<long long>(batch) * t_valid + 591) / 592);
+  if (rows_per_block < 64) rows_per_block = 64;
   dim3 grid((t_valid + rows_per_block - 1) / rows_per_block, batch);
-  colsum_kernel<<<grid, 256, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(x), t_valid, t_rows, c, rows_per_block,
+  const size_t smem = static_cast<size_t>(256 / (c / 8)) * c * sizeof(float);
+  colsum_kernel<<<grid, 256, smem, S(stream)>>>(static_cast<const __nv_bfloat16*>(x), t_valid, t_rows, c, rows_per_block,
                                               out);
   HG_CHECK_CUDA(cudaGetLastError());
   count();
@@ -491,15 +597,23 @@ extern "C" int hg_disc_first_conv_bwd(const float* y, const float* w, const void
                                       float* dy, void* stream) {
   HG_REQUIRE(y && w && dpre && (dw || dy), "hg_disc_first_conv_bwd: null pointer");
   HG_REQUIRE(!dw || db, "hg_disc_first_conv_bwd: dw needs db");
-  HG_REQUIRE(batch > 0 && t > 1 && period >= 1 && k >= 1 && k <= 16 && stride >= 1 && cout > 0,
+  HG_REQUIRE(batch > 0 && t > 1 && period >= 1 && k >= 1 && k <= kFirstK && stride >= 1 && cout > 0 && cout % 2 == 0,
              "hg_disc_first_conv_bwd: bad shape");
+  HG_REQUIRE((k + 1) * cout <= 8 * 256, "hg_disc_first_conv_bwd: (k + 1) * cout = %d exceeds 2048", (k + 1) * cout);
   const int t_pad = (t + period - 1) / period * period;
   const int h_in = t_pad / period;
   const int h_out = (h_in + 2 * pad - k) / stride + 1;
   HG_REQUIRE(h_out > 0 && h_rows >= h_out && batch * period <= 65535, "hg_disc_first_conv_bwd: bad geometry");
-  dim3 grid((h_out + 127) / 128, batch * period);
-  const size_t smem = (static_cast<size_t>(2 * k + 1) * cout) * sizeof(float);
-  disc_first_bwd_kernel<<<grid, 128, smem, S(stream)>>>(y, w, static_cast<const __nv_bfloat16*>(dpre), t, period, h_in,
+  dim3 grid((h_out + kFirstChunk - 1) / kFirstChunk, batch * period);
+  const size_t smem = static_cast<size_t>(k) * cout * 4 + kFirstTile * (kFirstK + 1) * 4 + kFirstTile * kFirstK * 4 +
+                      static_cast<size_t>(kFirstTile) * (cout + 2) * 2;
+  static bool configured = false;
+  if (!configured) {
+    HG_CHECK_CUDA(cudaFuncSetAttribute(disc_first_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    configured = true;
+  }
+  HG_REQUIRE(smem <= 96 * 1024, "hg_disc_first_conv_bwd: tile does not fit shared memory");
+  disc_first_bwd_kernel<<<grid, 256, smem, S(stream)>>>(y, w, static_cast<const __nv_bfloat16*>(dpre), t, period, h_in,
                                                         h_out, h_rows, k, stride, pad, cout, dw, db, dy);
   HG_CHECK_CUDA(cudaGetLastError());
   count();
@@ -572,13 +686,51 @@ extern "C" int hg_weight_norm_bwd(const float* dw, const float* v, const float* 
 }
 
 extern "C" int hg_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
-                             float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream) {
-  HG_REQUIRE(p && g && m && v && n > 0 && step >= 1, "hg_adamw_step: bad arguments");
+                             float beta2, float eps, float weight_decay, int step, const int* dev_step,
+                             float grad_scale, void* stream) {
+  HG_REQUIRE(p && g && m && v && n > 0 && (step >= 1 || dev_step), "hg_adamw_step: bad arguments");
+  if (step < 1) step = 1;
   const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
   const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
   adamw_kernel<<<blocks_for(n, 1024), 256, 0, S(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1,
-                                                           sqrtf(bc2), grad_scale);
+                                                           sqrtf(bc2), grad_scale, dev_step);
   HG_CHECK_CUDA(cudaGetLastError());
   count();
+  return HG_OK;
+}
+
+extern "C" int hg_fold_weight_norm(const float* v, const float* g, int dim0, int rest, float* w_eff, void* stream) {
+  HG_REQUIRE(v && w_eff && dim0 > 0 && rest > 0, "hg_fold_weight_norm: bad arguments");
+  fold_weight_kernel<<<dim0, 256, 0, S(stream)>>>(v, g, rest, w_eff);
+  HG_CHECK_CUDA(cudaGetLastError());
+  count();
+  return HG_OK;
+}
+
+extern "C" int hg_pack_disc_weight(const float* w_eff, int cout, int cin, int groups, int merge, int k, int stride,
+                                   int pad, void* w_fwd, void* w_dgrad, void* stream) {
+  HG_REQUIRE(w_eff && (w_fwd || w_dgrad), "hg_pack_disc_weight: null pointer");
+  HG_REQUIRE(cout > 0 && cin > 0 && groups >= 1 && merge >= 1 && groups % merge == 0 && k >= 1 && k <= 64 && stride >= 1,
+             "hg_pack_disc_weight: bad arguments");
+  DiscPackArgs a{};
+  a.cout = cout; a.cin = cin; a.groups = groups; a.merge = merge; a.k = k; a.stride = stride; a.pad = pad;
+  a.cin_g = cin / groups; a.cout_g = cout / groups;
+  a.cin_tile = a.cin_g * merge; a.cout_tile = a.cout_g * merge;
+  int rc = hg_conv1d_tap_order(k, stride, pad, a.order);
+  if (rc) return rc;
+  rc = hg_convtr1d_geometry(k, stride, pad, &a.nshift, &a.shift_min);
+  if (rc) return rc;
+  if (w_fwd) {
+    pack_disc_fwd_kernel<<<blocks_for(static_cast<long long>(k) * cout * a.cin_tile), 256, 0, S(stream)>>>(
+        w_eff, a, static_cast<__nv_bfloat16*>(w_fwd));
+    HG_CHECK_CUDA(cudaGetLastError());
+    count();
+  }
+  if (w_dgrad) {
+    pack_disc_dgrad_kernel<<<blocks_for(static_cast<long long>(a.nshift) * stride * cin * a.cout_tile), 256, 0,
+                             S(stream)>>>(w_eff, a, static_cast<__nv_bfloat16*>(w_dgrad));
+    HG_CHECK_CUDA(cudaGetLastError());
+    count();
+  }
   return HG_OK;
 }

@@ -81,7 +81,7 @@ class FlatParams:
         self.g = torch.zeros(off, dtype=torch.float32, device=device)
         self.m = torch.zeros(off, dtype=torch.float32, device=device)
         self.v = torch.zeros(off, dtype=torch.float32, device=device)
-        self.step_count = 0
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=device)   # AdamW step counter (graph-capturable)
         with torch.no_grad():
             for p, o, s in zip(ps, self.offsets, self.sizes):
                 view = self.p[o:o + s].view(p.shape)
@@ -93,10 +93,10 @@ class FlatParams:
     def adamw(self, lr: float, betas=(0.8, 0.99), eps: float = 1e-8, weight_decay: float = 0.01,
               grad_scale: float = 1.0) -> None:
         """torch.optim.AdamW(lr, betas) semantics (UPSTREAM train.py: AdamW(h.learning_rate, [adam_b1, adam_b2]))."""
-        self.step_count += 1
+        self.step_dev.add_(1)
         _lib.check(_lib.lib().hg_adamw_step(self.p.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
-                                            self.numel, lr, betas[0], betas[1], eps, weight_decay, self.step_count,
-                                            grad_scale, _stream()), "hg_adamw_step")
+                                            self.numel, lr, betas[0], betas[1], eps, weight_decay, 0,
+                                            self.step_dev.data_ptr(), grad_scale, _stream()), "hg_adamw_step")
 
 
 # ------------------------------------------------------------------------------------------------ generator
@@ -367,43 +367,16 @@ class _DiscBwdLayer:
         _lib.check(L.hg_convtr1d_geometry(k, s, pad, byref(nshift), byref(smin)))
         self.nshift, self.smin = nshift.value, smin.value
         self.pad_left = -self.smin
-        cin, cout = layer.cin, layer.cout
         self.grouped = layer.groups > 1
-        if not self.grouped:
-            self.cout_tile = cout
-            self.w = torch.empty(self.nshift, s * cin, cout, dtype=torch.bfloat16, device=device)
-            self.idx = None
-        else:
-            cin_g, cout_g, merge = cin // layer.groups, cout // layer.groups, layer.merge
-            ct = cout_g * merge
-            self.cout_tile = ct
-            m_idx = torch.arange(self.nshift).view(-1, 1, 1, 1)
-            rho = torch.arange(s).view(1, -1, 1, 1)
-            ci = torch.arange(cin).view(1, 1, -1, 1)
-            cc = torch.arange(ct).view(1, 1, 1, -1)
-            g = ci // cin_g
-            co = (g // merge) * ct + cc
-            j = rho + pad - s * (m_idx + self.smin)
-            valid = (co // cout_g == g) & (j >= 0) & (j < k)
-            src = (co * cin_g + (ci % cin_g)) * k + j
-            zero_slot = cout * cin_g * k
-            self.idx = torch.where(valid, src, torch.full_like(src, zero_slot)).reshape(-1).to(device)
-            self.w = torch.empty(self.nshift, s * cin, ct, dtype=torch.bfloat16, device=device)
+        self.cout_tile = (layer.cout // layer.groups) * layer.merge
+        self.w = torch.empty(self.nshift, s * layer.cin, self.cout_tile, dtype=torch.bfloat16, device=device)
 
-    def pack(self, w_eff: torch.Tensor, w_fwd_packed: torch.Tensor) -> None:
-        """w_eff fp32 [cout][cin/groups][k] (effective weight), w_fwd_packed the forward's bf16 pack"""
+    def pack(self, w_eff: torch.Tensor, w_fwd_packed=None) -> None:
+        """w_eff fp32 [cout][cin/groups][k] (effective weight) -> the data-gradient filter bank (hg_pack_disc_weight)"""
         layer = self.layer
-        L = _lib.lib()
-        if self.grouped:
-            flat = torch.cat([w_eff.reshape(-1), w_eff.new_zeros(1)])
-            self.w.view(-1).copy_(flat[self.idx])
-        elif layer.stride == 1:
-            _lib.check(L.hg_pack_dgrad_weight(w_fwd_packed.data_ptr(), layer.k, layer.cout, layer.cin,
-                                              self.w.data_ptr(), _stream()), "hg_pack_dgrad_weight")
-        else:
-            w32 = w_eff.contiguous()
-            _lib.check(L.hg_pack_convtr1d_weight(w32.data_ptr(), 0, layer.cout, layer.cin, layer.k, layer.stride,
-                                                 layer.pad, self.w.data_ptr(), _stream()), "hg_pack_convtr1d_weight")
+        _lib.check(_lib.lib().hg_pack_disc_weight(w_eff.data_ptr(), layer.cout, layer.cin, layer.groups, layer.merge,
+                                                  layer.k, layer.stride, layer.pad, 0, self.w.data_ptr(), _stream()),
+                   "hg_pack_disc_weight")
 
     def dgrad(self, L, dy, nseq: int, t_dy_valid: int, t_dy_rows: int, rows_in: int, act_g, act_r, fm_coef: float,
               out, st) -> None:
@@ -443,27 +416,47 @@ class _SubDiscTrainer:
                                        else m.weight_orig.numel() if self.spectral else m.weight.numel()
                                        for m in self.mods), dtype=torch.float32, device=device)
         self.db = torch.zeros(1024, dtype=torch.float32, device=device)
+        self.wbufs = {}
 
     # ---- weights -------------------------------------------------------------------------------------------
-    def _weights(self):
-        """effective fp32 weights + GEMM packs of every layer (one spectral-norm power iteration per call in
-        train mode, exactly like one reference forward)."""
-        ws = {"eff": [], "fwd": [], "sn": []}
+    def _weights(self, part: int):
+        """effective fp32 weights + forward GEMM packs of every layer, into per-part persistent buffers.
+        weight_norm layers: hg_fold_weight_norm + hg_pack_disc_weight.  spectral_norm layers: one power iteration
+        per call in train mode (torch ops on the u / v buffers, exactly like one reference forward)."""
+        L = _lib.lib()
+        st = _stream()
+        bufs = self.wbufs.get(part)
+        if bufs is None:
+            bufs = {"eff": [], "fwd": []}
+            for li, m in enumerate(self.mods):
+                _, v = _g_v(m) if not hasattr(m, "weight_orig") else (None, m.weight_orig)
+                bufs["eff"].append(torch.empty(v.shape[0], v.shape[1], v.shape[2] if v.dim() > 2 else 1,
+                                               dtype=torch.float32, device=self.device))
+                if 1 <= li <= len(self.mids):
+                    layer = self.mids[li - 1]
+                    bufs["fwd"].append(torch.empty(layer.k, layer.cout, layer.cin_tile, dtype=torch.bfloat16,
+                                                   device=self.device))
+                else:
+                    bufs["fwd"].append(None)
+            self.wbufs[part] = bufs
+        ws = {"eff": bufs["eff"], "fwd": bufs["fwd"], "sn": []}
         for li, m in enumerate(self.mods):
-            w = _effective_weight(m)
-            w = w.reshape(w.shape[0], w.shape[1], -1).contiguous()     # Conv2d (k,1) kernels -> [cout][cin/g][k]
-            ws["eff"].append(w)
+            eff = bufs["eff"][li]
             if hasattr(m, "weight_orig"):
+                eff.view(-1).copy_(_effective_weight(m).reshape(-1))
                 # u, v as this call left them: the backward of THIS call's weights needs them (the next call moves on)
                 u, v = m.weight_u.clone(), m.weight_v.clone()
                 ws["sn"].append((u, v, torch.dot(u, torch.mv(m.weight_orig.detach().flatten(1), v))))
             else:
+                g, v = _g_v(m)
+                _lib.check(L.hg_fold_weight_norm(v.data_ptr(), 0 if g is None else g.data_ptr(), v.shape[0],
+                                                 v.numel() // v.shape[0], eff.data_ptr(), st), "hg_fold_weight_norm")
                 ws["sn"].append(None)
             if 1 <= li <= len(self.mids):
                 layer = self.mids[li - 1]
-                ws["fwd"].append(layer.pack(w))
-            else:
-                ws["fwd"].append(None)
+                _lib.check(L.hg_pack_disc_weight(eff.data_ptr(), layer.cout, layer.cin, layer.groups, layer.merge,
+                                                 layer.k, layer.stride, layer.pad, bufs["fwd"][li].data_ptr(), 0, st),
+                           "hg_pack_disc_weight")
         return ws
 
     def _geometry(self, nb: int, t: int):
@@ -506,13 +499,13 @@ class _SubDiscTrainer:
         self.parts = []
         st = _stream()
         k0, s0, p0, c0 = self.first
-        for b0, bn in parts:
-            W = self._weights()
+        for pi, (b0, bn) in enumerate(parts):
+            W = self._weights(pi)
             self.parts.append((b0, bn, W))
             seq0, nseq = b0 * period, bn * period
             w0 = W["eff"][0].reshape(c0, k0).contiguous()
             W["w0"] = w0
-            b0_bias = self.mods[0].bias.detach().float().contiguous()
+            b0_bias = self.mods[0].bias
             act = G["act"][0]
             h, rows, _ = G["geo"][0]
             _lib.check(L.hg_disc_first_conv_fwd(ycat[b0:].data_ptr(), w0.data_ptr(), b0_bias.data_ptr(), bn, t, period,
@@ -520,7 +513,7 @@ class _SubDiscTrainer:
                        "hg_disc_first_conv_fwd")
             for li, layer in enumerate(self.mids):
                 m = self.mods[1 + li]
-                bias = m.bias.detach().float().contiguous()
+                bias = m.bias
                 out = G["act"][1 + li]
                 h_out, rows_out, _ = G["geo"][1 + li]
                 _lib.check(L.hg_conv1d_general_fwd(act[seq0:].data_ptr(), W["fwd"][1 + li].data_ptr(), bias.data_ptr(),
@@ -531,7 +524,7 @@ class _SubDiscTrainer:
             c_last = G["geo"][-1][2]
             wp = W["eff"][-1].reshape(c_last, self.kpost).contiguous()
             W["wp"] = wp
-            bp = self.mods[-1].bias.detach().float().contiguous()
+            bp = self.mods[-1].bias
             _lib.check(L.hg_disc_last_conv_fwd(act[seq0:].data_ptr(), wp.data_ptr(), bp.data_ptr(), nseq, h, rows,
                                                c_last, self.kpost, G["logit"][seq0:].data_ptr(), st),
                        "hg_disc_last_conv_fwd")
@@ -700,6 +693,7 @@ class DiscriminatorTrainer:
         self.nslots = 12
         self.acc = torch.zeros(len(self.subs) * self.nslots, dtype=torch.float32, device=device)
         self.pooled: List[torch.Tensor] = []
+        self._inv_counts: Dict[Tuple[int, int], torch.Tensor] = {}
 
     def forward(self, y: torch.Tensor, y_hat: torch.Tensor) -> None:
         """y, y_hat fp32 [B,1,T] (or [B,T]).  Runs every sub-discriminator on (y ++ y_hat) and accumulates the raw
@@ -727,16 +721,21 @@ class DiscriminatorTrainer:
         a = self.acc.view(len(self.subs), self.nslots)
         out = {}
         np_ = len(self.subs_p)
-        nlog = torch.tensor([sd.numel_fmaps(self.b)[-1] for sd in self.subs], dtype=torch.float32, device=self.device)
-        d_terms = (a[:, 0] + a[:, 1]) / nlog
-        g_terms = a[:, 2] / nlog
-        out["loss_disc_f"], out["loss_disc_s"] = d_terms[:np_].sum(), d_terms[np_:].sum()
-        out["loss_gen_f"], out["loss_gen_s"] = g_terms[:np_].sum(), g_terms[np_:].sum()
-        fm = []
-        for i, sd in enumerate(self.subs):
-            n = torch.tensor(sd.numel_fmaps(self.b), dtype=torch.float32, device=self.device)
-            fm.append((a[i, 3:3 + n.numel()] / n).sum() * 2)
-        out["loss_fm_f"], out["loss_fm_s"] = torch.stack(fm[:np_]).sum(), torch.stack(fm[np_:]).sum()
+        key = (self.b, self.t)
+        inv = self._inv_counts.get(key)
+        if inv is None:
+            # 1 / numel of every loss term, laid out like self.acc (slots 0-2: logits, 3..: feature maps, x2)
+            host = torch.zeros(len(self.subs), self.nslots)
+            for i, sd in enumerate(self.subs):
+                n = sd.numel_fmaps(self.b)
+                host[i, 0:3] = 1.0 / n[-1]
+                host[i, 3:3 + len(n)] = 2.0 / torch.tensor(n, dtype=torch.float64)
+            inv = host.to(self.device)
+            self._inv_counts[key] = inv
+        terms = a * inv
+        out["loss_disc_f"], out["loss_disc_s"] = terms[:np_, 0:2].sum(), terms[np_:, 0:2].sum()
+        out["loss_gen_f"], out["loss_gen_s"] = terms[:np_, 2].sum(), terms[np_:, 2].sum()
+        out["loss_fm_f"], out["loss_fm_s"] = terms[:np_, 3:].sum(), terms[np_:, 3:].sum()
         return out
 
     def backward_d(self) -> None:
@@ -784,10 +783,28 @@ class TrainStep:
         if self.world > 1:
             torch.distributed.all_reduce(flat.g, group=self.pg)
 
-    def _mel(self, y2d: torch.Tensor) -> torch.Tensor:
+    def _mel_plan(self):
+        """the loss-mel plan (fmax_for_loss), created through the public function's cache"""
         h = self.h
-        return mel_spectrogram(y2d, h.n_fft, h.num_mels, h.sampling_rate, h.hop_size, h.win_size, h.fmin,
-                               h.fmax_for_loss)
+        dev = self.G.flat.p.device          # the resolved device ("cuda:0"), as mel_spectrogram spells its cache key
+        key = (f'{str(dev)}_{h.n_fft}_{h.num_mels}_{h.sampling_rate}_{h.hop_size}_{h.win_size}_{h.fmin}_'
+               f'{h.fmax_for_loss}_False')
+        plan = torch_mels.get(key)
+        if plan is None:
+            mel_spectrogram(torch.zeros(1, h.segment_size, device=self.device), h.n_fft, h.num_mels, h.sampling_rate,
+                            h.hop_size, h.win_size, h.fmin, h.fmax_for_loss)
+            plan = torch_mels[key]
+        return plan
+
+    def _mel(self, y2d: torch.Tensor) -> torch.Tensor:
+        """log-mel of the generated audio: the kernel behind mel_spectrogram, without the public function's lazy
+        range-warning bookkeeping (event queries are not allowed while a CUDA graph is capturing; the generator
+        output is tanh-bounded anyway)."""
+        plan = self._mel_plan()
+        b, t = y2d.shape
+        out = torch.empty(b, self.h.num_mels, plan.frames(t), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib().hg_mel_fwd(plan.handle, y2d.data_ptr(), b, t, out.data_ptr(), 0, _stream()), "hg_mel_fwd")
+        return out
 
     def step(self, x: torch.Tensor, y: torch.Tensor, y_mel: torch.Tensor, update: bool = True) -> Dict[str, torch.Tensor]:
         """x [B,80,F] input mel, y [B,1,T] audio, y_mel [B,80,F] loss mel.  Returns the loss tensors (device)."""
@@ -819,8 +836,7 @@ class TrainStep:
         _lib.check(L.hg_loss_grad(mel_g.data_ptr(), ym.data_ptr(), n_mel, 0, 0.0, 45.0 / n_mel, 0.0, dmel.data_ptr(), st),
                    "hg_loss_grad")
         dy = torch.zeros(b, y_g2.shape[1], dtype=torch.float32, device=self.device)
-        key = f'{str(y_g2.device)}_{h.n_fft}_{h.num_mels}_{h.sampling_rate}_{h.hop_size}_{h.win_size}_{h.fmin}_{h.fmax_for_loss}_False'
-        plan = torch_mels[key]
+        plan = self._mel_plan()
         _lib.check(L.hg_mel_bwd(plan.handle, y_g2.data_ptr(), dmel.data_ptr(), b, y_g2.shape[1], dy.data_ptr(), st),
                    "hg_mel_bwd")
         self.D.forward(y2, y_g2)
@@ -836,4 +852,37 @@ class TrainStep:
             self.G.flat.adamw(self.lr, self.betas, grad_scale=1.0 / self.world)
             self.G.invalidate()
         out["y_g_hat"] = y_g
+        return out
+
+    # ---- CUDA-graph replay ---------------------------------------------------------------------------------------
+    def step_graphed(self, x: torch.Tensor, y: torch.Tensor, y_mel: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """`step` replayed as ONE CUDA graph (about 3000 launches per step are otherwise host-bound at batch 16).
+        The first call of a shape runs eagerly (it is a real step and loads every kernel); the second call captures
+        and replays; later calls copy the inputs into the captured buffers and replay.  The returned loss tensors are
+        the graph's static outputs: read them before the next call.  Falls back to eager when capture fails."""
+        key = (tuple(x.shape), tuple(y.shape), float(self.lr), self.world)
+        graphs = self.__dict__.setdefault("_graphs", {})
+        entry = graphs.get(key)
+        if entry is None:
+            graphs[key] = "seen"
+            return self.step(x, y, y_mel)
+        if entry == "seen":
+            sx, sy, sm = x.clone(), y.clone(), y_mel.clone()
+            torch.cuda.synchronize()
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    out = self.step(sx, sy, sm)
+                entry = (g, sx, sy, sm, out)
+            except Exception as e:  # noqa: BLE001
+                import warnings
+                warnings.warn(f"hifigan_b200: CUDA graph capture of the training step failed, running eagerly ({e})")
+                torch.cuda.synchronize()
+                entry = "eager"
+            graphs[key] = entry
+        if entry == "eager":
+            return self.step(x, y, y_mel)
+        g, sx, sy, sm, out = entry
+        sx.copy_(x); sy.copy_(y); sm.copy_(y_mel)
+        g.replay()
         return out

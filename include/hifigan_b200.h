@@ -248,6 +248,16 @@ int hg_unpack_wgrad_convtr(const float* dw_packed, int cin, int cout, int k, int
 int hg_weight_norm_bwd(const float* dw, const float* v, const float* g, int dim0, int rest, int accumulate,
                        float* dv, float* dg, void* stream);
 
+/* Discriminator weight preparation (replaces torch.nn.utils.weight_norm's per-forward recompute for
+ * src/models.py:132-141,194-204).  hg_fold_weight_norm: w_eff fp32 [dim0][rest] = g * v / ||v|| (g == NULL copies).
+ * hg_pack_disc_weight: w_eff fp32 [cout][cin/groups][k] -> w_fwd bf16 [k][cout][cin_tile] (taps in
+ * hg_conv1d_tap_order order, `merge` adjacent groups merged into one block-diagonal tile) for
+ * hg_conv1d_general_fwd, and / or w_dgrad bf16 [nshift][stride*cin][cout_tile] (polyphase data-gradient filter
+ * bank, geometry of hg_convtr1d_geometry(k, stride, pad)) for hg_conv1d_dgrad. */
+int hg_fold_weight_norm(const float* v, const float* g, int dim0, int rest, float* w_eff, void* stream);
+int hg_pack_disc_weight(const float* w_eff, int cout, int cin, int groups, int merge, int k, int stride, int pad,
+                        void* w_fwd, void* w_dgrad, void* stream);
+
 /* hg_colsum_bf16 — bias gradient: out[c] (+)= sum_{b, t < t_valid} x[b][t][c]; x bf16 [B][t_rows][C]. */
 int hg_colsum_bf16(const void* x, int batch, int t_valid, int t_rows, int c, int accumulate, float* out, void* stream);
 
@@ -278,9 +288,10 @@ int hg_loss_grad(const float* a, const float* b, long long n, int mode, float c,
 int hg_l1_sum_bf16(const void* a, const void* b, long long n, float* out_acc, void* stream);
 
 /* hg_adamw_step — torch.optim.AdamW on one flat fp32 tensor (decoupled weight decay, bias correction by `step`,
+ * or by the device-resident counter *dev_step when non-NULL so that a captured CUDA graph advances it;
  * gradients multiplied by grad_scale first: 1/world_size after a sum all-reduce). */
 int hg_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                  float eps, float weight_decay, int step, float grad_scale, void* stream);
+                  float eps, float weight_decay, int step, const int* dev_step, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

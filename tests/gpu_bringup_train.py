@@ -81,8 +81,9 @@ def timing(b):
     x = H.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, 8000)
     y_mel = H.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, None)
     y = ya.unsqueeze(1)
+    fn = ts.step if os.environ.get("HG_TRAIN_EAGER") else ts.step_graphed
     for _ in range(3):
-        ts.step(x, y, y_mel)
+        fn(x, y, y_mel)
     torch.cuda.synchronize()
     n0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -90,18 +91,37 @@ def timing(b):
     ev0.record()
     iters = 5
     for _ in range(iters):
-        out = ts.step(x, y, y_mel)
+        out = fn(x, y, y_mel)
     ev1.record()
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1) / iters
     print(json.dumps({"batch": b, "ms_per_step": ms, "segments_per_s": b / ms * 1e3, "wall_ms": (time.time() - t0) / iters * 1e3,
-                      "launches_per_step": (_lib.launch_count() - n0) / iters,
+                      "launches_per_step": (_lib.launch_count() - n0) / iters, "graphed": fn is not ts.step,
                       "loss_gen_all": out["loss_gen_all"].item(), "loss_disc_all": out["loss_disc_all"].item()}))
+
+
+def profile(b):
+    """one step between cudaProfilerStart/Stop (ncu --profile-from-start off)"""
+    h, ts, _ = build()
+    from oracle import hifigan_oracle as O
+    ya = O.synthetic_audio(b, 8192, seed=3).cuda()
+    x = H.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, 8000)
+    y_mel = H.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, None)
+    y = ya.unsqueeze(1)
+    for _ in range(2):
+        ts.step(x, y, y_mel)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    ts.step(x, y, y_mel)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
 
 
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "parity"
     if mode == "parity":
         parity()
+    elif mode == "profile":
+        profile(int(sys.argv[2]) if len(sys.argv) > 2 else 16)
     else:
         timing(int(sys.argv[2]) if len(sys.argv) > 2 else 16)
