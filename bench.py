@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the hifigan_b200 hot path (contract: see DESIGN.md §Measurement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|v3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|v3|train]
 
 A "step" is one Generator forward over one batch of synthetic mels.  Default workload = BASELINE.json
 configs[1]: V1 Generator, batch 64 x [80 x 1024-frame] mels (16 777 216 output samples per step) per GPU.
@@ -15,6 +15,11 @@ Output: ONE JSON line on rank 0.
                D2H of the waveform inside the timed region
   roofline     tensor-core roofline of the dominant kernels (tcgen05 conv launches, 62 per V1 step)
   cpu_baseline the oracle port (torch CPU fp32, all host threads) on a bounded sample, rank 0, N == 1 only
+  train        (default workload only) the second half of BASELINE.json's metric, "V1 train segments/s": a short
+               run of the full training step (BASELINE configs[2]: batch 16 x 8192-sample segments per GPU, G + MPD +
+               MSD forward/backward, two AdamW updates; gradient all-reduce over NCCL when N > 1)
+
+--workload train makes the training step the primary metric of the line (same keys).
 """
 from __future__ import annotations
 
@@ -40,6 +45,11 @@ WORKLOADS = {
     "v3": dict(version="v3", batch=64, frames=1024, name="V3 Generator inference, batch 64 x 80x1024 mels"),
 }
 SR = 22050
+TRAIN = dict(version="v1", batch=16, segment=8192,
+             name="V1 full training step (G + MPD + MSD, mel-L1/feature/adversarial losses, 2 x AdamW), "
+                  "batch 16 x 8192-sample segments per GPU")
+# minimal algorithmic work of one step = 3 F_G + 9 F_D MACs per segment, x2 FLOP/MAC
+TRAIN_FLOP_PER_SEGMENT = 214.668e9
 
 
 # ------------------------------------------------------------------------------------------------ helpers
@@ -151,11 +161,162 @@ def cpu_generator_baseline(version: str, frames: int, batch: int, steps: int, wa
             "ms_per_step": mean * 1e3, "xrt": samples / mean / SR}
 
 
+
+# --------------------------------------------------------------------------------------------- training step
+def cpu_train_baseline(batch: int, steps: int, warmup: int):
+    """The training oracle (torch CPU fp32 autograd + torch AdamW over the restated forward = the ops the
+    reference's CPU path runs) on a bounded sample of the training workload."""
+    from oracle import hifigan_oracle as O          # allowed here: cpu_baseline / --impl reference legs
+    from oracle import train_oracle as TO
+    import hifigan_b200 as H
+    from hifigan_b200.configs import load_config
+    h = load_config("v1")
+    torch.manual_seed(1234)
+    G, mpd, msd = H.Generator(h), H.MultiPeriodDiscriminator(), H.MultiScaleDiscriminator()  # parameter containers
+    sds = [TO.leaf_params({k: v.detach().clone() for k, v in m.state_dict().items()}) for m in (G, mpd, msd)]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ya = O.synthetic_audio(batch, 8192, seed=3)
+    x = O.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, 8000)
+    y_mel = O.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, None)
+    optims = TO.make_optimizers(*sds, h)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        TO.train_step(*sds, h, x, ya.unsqueeze(1), y_mel, optims=optims)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    mean = sum(times) / len(times)
+    return {"value": batch / mean, "unit": "segments/s", "cores": cores, "kind": "port",
+            "sample": f"V1 full training step on {batch} x 8192-sample segments per step, fp32 torch-CPU oracle "
+                      f"(autograd + AdamW), {len(times)} timed steps", "ms_per_step": mean * 1e3}
+
+
+def measure_train(dev, rank, world, steps: int, warmup: int, batch: int = TRAIN["batch"]):
+    """Time the full training step.  Returns a dict with device-resident and end-to-end numbers (max over ranks)."""
+    import hifigan_b200 as H
+    from hifigan_b200 import _lib
+    from hifigan_b200.configs import load_config
+    from hifigan_b200.train import TrainStep
+    h = load_config("v1")
+    torch.manual_seed(1234)                                   # same replicated initial weights on every rank
+    ts = TrainStep(H.Generator(h), H.MultiPeriodDiscriminator(), H.MultiScaleDiscriminator(), h, dev)
+    g = torch.Generator().manual_seed(100 + rank)             # every rank its own shard of the global batch
+    seg = TRAIN["segment"]
+    t_ax = torch.arange(seg, dtype=torch.float32) / SR
+    f0 = 80 + 320 * torch.rand(batch, 1, generator=g)
+    host_y = (0.5 * torch.sin(2 * torch.pi * f0 * t_ax) + 0.1 * torch.randn(batch, seg, generator=g)).clamp(-0.95, 0.95)
+    host_y = host_y.pin_memory()
+    y = host_y.to(dev)
+    x = H.mel_spectrogram(y, h.n_fft, h.num_mels, h.sampling_rate, h.hop_size, h.win_size, h.fmin, h.fmax)
+    y_mel = H.mel_spectrogram(y, h.n_fft, h.num_mels, h.sampling_rate, h.hop_size, h.win_size, h.fmin, h.fmax_for_loss)
+    host_x, host_ymel = x.cpu().pin_memory(), y_mel.cpu().pin_memory()
+    y3 = y.unsqueeze(1)
+    fn = ts.step if (world > 1 or os.environ.get("HG_TRAIN_EAGER")) else ts.step_graphed
+
+    def barrier():
+        if _dist_on():
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(warmup, 3)):
+        fn(x, y3, y_mel)
+    barrier()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = fn(x, y3, y_mel)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    launches = _lib.launch_count() - n0
+    # end to end: the step's three inputs come from pinned host memory, the logged losses go back to the host
+    host_loss = torch.empty(2, dtype=torch.float32).pin_memory()
+    f0e, f1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0e.record()
+    for _ in range(steps):
+        xd = host_x.to(dev, non_blocking=True)
+        yd = host_y.to(dev, non_blocking=True).unsqueeze(1)
+        md = host_ymel.to(dev, non_blocking=True)
+        out = fn(xd, yd, md)
+        host_loss.copy_(torch.stack([out["loss_gen_all"], out["loss_disc_all"]]), non_blocking=True)
+    f1e.record()
+    barrier()
+    e2e_ms = f0e.elapsed_time(f1e) / steps
+    graphed = ts.graph_active
+    # a graph replay launches the captured kernels without passing through the C-ABI counter: report the number
+    # of library kernels recorded when the step was captured
+    per_step = ts.launches_per_step if graphed else launches / steps
+    return {"ms": max_over_ranks(ms), "e2e_ms": max_over_ranks(e2e_ms), "batch": batch,
+            "segments": sum_over_ranks(float(batch)), "launches_per_step": per_step, "graphed": graphed,
+            "h2d": (host_x.numel() + host_y.numel() + host_ymel.numel()) * 4, "d2h": 8,
+            "losses": [float(v) for v in host_loss.tolist()]}
+
+
+def train_summary(r, world):
+    peaks = measured_peaks()
+    sps = r["segments"] / (r["ms"] * 1e-3)
+    achieved = sps * TRAIN_FLOP_PER_SEGMENT / 1e12 / world      # per GPU
+    return {"metric": "V1 train segments/s", "value": sps, "unit": "segments/s", "ms_per_step": r["ms"],
+            "per_gpu_batch": r["batch"], "global_batch": int(r["segments"]),
+            "e2e": {"value": r["segments"] / (r["e2e_ms"] * 1e-3), "unit": "segments/s", "ms_per_step": r["e2e_ms"],
+                    "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
+            "cuda_graph": r["graphed"], "kernel_launches_per_step": r["launches_per_step"],
+            "parallelism": f"data-parallel x{world}" + (", NCCL all-reduce of the flat G and D gradient buffers"
+                                                        if world > 1 else ""),
+            "roofline": {"bound": "tensor", "kernel": "whole step (conv fwd / dgrad / wgrad tcgen05 launches + the rest)",
+                         "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["tflops"], "traffic": None,
+                         "algorithmic_flop_per_segment": TRAIN_FLOP_PER_SEGMENT, "peak_source": peaks["source"]},
+            "losses_last_step": {"loss_gen_all": r["losses"][0], "loss_disc_all": r["losses"][1]}}
+
+
+def run_train(args, rank, world, local_rank):
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    r = measure_train(dev, rank, world, args.steps, args.warmup)
+    clocks = sampler.stop()
+    if rank != 0:
+        return
+    t = train_summary(r, world)
+    line = {"metric": t["metric"], "value": t["value"], "unit": t["unit"], "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": t["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": TRAIN["name"], "per_gpu_batch": r["batch"], "global_batch": t["global_batch"],
+                       "segment_size": TRAIN["segment"], "weights": "random init, seed 1234",
+                       "numerics": "bf16 operands / activations / activation gradients, fp32 accumulate, fp32 "
+                                   "parameter gradients, master weights and AdamW state",
+                       "l2": "one step touches > 1.5 GB of activations, gradients, weights and optimizer state per "
+                             "GPU (> 126 MB L2); no flush needed",
+                       "cuda_graph": t["cuda_graph"], "parallelism": t["parallelism"]},
+            "clocks": clocks, "e2e": t["e2e"],
+            "gpu_launches": int(t["kernel_launches_per_step"] * args.steps), "roofline": t["roofline"],
+            "losses_last_step": t["losses_last_step"]}
+    if world == 1 and not args.no_cpu_baseline:
+        cb = cpu_train_baseline(2, 2, 1)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line), flush=True)
+
 # ------------------------------------------------------------------------------------------------- arms
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path (oracle port; the reference itself is
     Python over torch and cannot travel to the GPU box) on the box's host cores.  Rank 0 only."""
     if rank != 0:
+        return
+    if args.workload == "train":
+        r = cpu_train_baseline(2, max(1, args.steps), max(0, min(args.warmup, 1)))
+        line = {"impl": "reference", "metric": "V1 train segments/s", "value": r["value"], "unit": "segments/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": TRAIN["name"], "sample": r["sample"]},
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
         return
     wl = WORKLOADS[args.workload]
     batch = 2 if wl["batch"] > 2 else wl["batch"]
@@ -237,6 +398,16 @@ def run_ours(args, rank, world, local_rank):
     ms = max_over_ranks(ms)
     e2e_ms = max_over_ranks(e2e_ms)
     total_samples = sum_over_ranks(float(samples))
+    train = None
+    if args.workload == "cfg2" and not profile_mode and not args.no_train:
+        # second half of BASELINE.json's metric: a short run of the full training step on the same GPUs
+        del eng, x
+        G._drop_engines()
+        torch.cuda.empty_cache()
+        try:
+            train = train_summary(measure_train(dev, rank, world, max(5, min(args.steps, 20)), 3), world)
+        except Exception as e:  # noqa: BLE001  (the headline number must survive a failure of the secondary one)
+            train = {"error": f"{type(e).__name__}: {e}"}
     if rank != 0:
         return
     peaks = measured_peaks()
@@ -266,6 +437,8 @@ def run_ours(args, rank, world, local_rank):
                      "avg_launch_ms": conv_ms / n_conv, "flop_per_launch_avg": conv_flops / n_conv,
                      "peak_source": peaks["source"]},
     }
+    if train is not None:
+        line["train"] = train
     if profile_mode:
         line["invalid"] = "HG_BENCH_PROFILE run (short warm-up, no e2e): not a bench value"
     if world == 1 and not args.no_cpu_baseline and not profile_mode:
@@ -280,8 +453,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + ["train"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step summary of the default line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -294,7 +468,10 @@ def main():
         torch.cuda.set_device(local_rank)
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(args, rank, world, local_rank)
+        if args.workload == "train":
+            run_train(args, rank, world, local_rank)
+        else:
+            run_ours(args, rank, world, local_rank)
     finally:
         if _dist_on():
             torch.distributed.barrier()

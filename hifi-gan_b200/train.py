@@ -99,6 +99,26 @@ class FlatParams:
                                             self.step_dev.data_ptr(), grad_scale, _stream()), "hg_adamw_step")
 
 
+def allreduce_gradients(flat: FlatParams, group=None) -> float:
+    """Data-parallel exchange step: SUM all-reduce of one network's flat gradient buffer over the process group
+    (NCCL over NVLink on the GPUs; gloo in the CPU tests).  Returns the factor the optimizer must apply to the summed
+    gradients (1 / world size) — the same averaging DistributedDataParallel performs for the reference."""
+    if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        return 1.0
+    world = torch.distributed.get_world_size(group)
+    if world > 1:
+        torch.distributed.all_reduce(flat.g, op=torch.distributed.ReduceOp.SUM, group=group)
+    return 1.0 / world
+
+
+def shard_batch(global_batch: int, rank: int, world: int) -> Tuple[int, int]:
+    """[lo, hi) rows of the global batch owned by `rank` (BASELINE configs[3]: global batch 128 over 2/4/8 GPUs)."""
+    if global_batch % world:
+        raise ValueError(f"global batch {global_batch} does not divide over {world} ranks")
+    per = global_batch // world
+    return rank * per, (rank + 1) * per
+
+
 # ------------------------------------------------------------------------------------------------ generator
 class _GenLayerGrad:
     """Backward-side state of one packed Generator conv: dgrad filter bank, packed fp32 weight gradient, bias
@@ -780,8 +800,7 @@ class TrainStep:
             self.world = torch.distributed.get_world_size(process_group)
 
     def _allreduce(self, flat: FlatParams) -> None:
-        if self.world > 1:
-            torch.distributed.all_reduce(flat.g, group=self.pg)
+        allreduce_gradients(flat, self.pg)
 
     def _mel_plan(self):
         """the loss-mel plan (fmax_for_loss), created through the public function's cache"""
@@ -812,6 +831,7 @@ class TrainStep:
         h = self.h
         b = x.shape[0]
         st = _stream()
+        launches0 = _lib.launch_count()
         y2 = y.reshape(b, -1).contiguous().float()
         y_g = self.G.forward(x)                                # [B,1,T]
         y_g2 = y_g.view(b, -1)
@@ -852,7 +872,12 @@ class TrainStep:
             self.G.flat.adamw(self.lr, self.betas, grad_scale=1.0 / self.world)
             self.G.invalidate()
         out["y_g_hat"] = y_g
+        self.launches_per_step = _lib.launch_count() - launches0   # library kernels issued (or captured) per step
         return out
+
+    @property
+    def graph_active(self) -> bool:
+        return any(isinstance(v, tuple) for v in self.__dict__.get("_graphs", {}).values())
 
     # ---- CUDA-graph replay ---------------------------------------------------------------------------------------
     def step_graphed(self, x: torch.Tensor, y: torch.Tensor, y_mel: torch.Tensor) -> Dict[str, torch.Tensor]:
