@@ -67,7 +67,7 @@ _SIGNATURES = {
                               c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_float, c_void_p]),
     "hg_conv1d_tap_order": (c_int, [c_int, c_int, c_int, POINTER(c_int)]),
     "hg_conv1d_general_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                                      c_int, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p]),
+                                      c_int, c_int, c_int, c_void_p, c_float, c_void_p, c_int, c_int, c_void_p]),
     "hg_disc_first_conv_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                        c_int, c_void_p, c_float, c_void_p]),
     "hg_disc_last_conv_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
@@ -92,7 +92,7 @@ _SIGNATURES = {
     "hg_mel_emulate_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "hg_pack_dgrad_weight": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hg_conv1d_dgrad": (c_int, [c_void_p, c_void_p] + [c_int] * 12 + [c_void_p, c_float, c_void_p, c_void_p, c_float,
-                                c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
+                                c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "hg_conv1d_wgrad": (c_int, [c_void_p, c_void_p] + [c_int] * 11 + [c_void_p, c_int, c_void_p]),
     "hg_unpack_wgrad_conv": (c_int, [c_void_p] + [c_int] * 7 + [POINTER(c_int), c_void_p, c_void_p]),
     "hg_unpack_wgrad_convtr": (c_int, [c_void_p] + [c_int] * 7 + [c_void_p, c_void_p]),

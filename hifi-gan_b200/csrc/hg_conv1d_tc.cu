@@ -76,6 +76,10 @@ struct ConvArgs {
   const __nv_bfloat16* fm_g;
   float fm_coef;
   int group_mod;                 // grouped: N tile nt reads input channel block (nt % group_mod)
+  // "flat" sequences: many short sequences laid end to end on the time axis (pitch rows each, zero rows between
+  // them standing in for the conv padding).  Output element (row t, N tile nt) is stored only when
+  // (t % seq_pitch) * seq_mul + (nt * NT) / seq_div < seq_valid, so the gap rows stay zero.  seq_pitch == 0: off.
+  int seq_pitch, seq_valid, seq_mul, seq_div;
 };
 
 struct Barriers {
@@ -311,7 +315,8 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     for (TileIter it(p); it.tile < p.num_tiles; it.next()) {
       const int nt = it.nt, b = it.b;
       const int t = it.tt * kTileM + row;
-      const bool valid = t < p.t;
+      bool valid = t < p.t;
+      if (p.seq_pitch) valid = valid && ((t % p.seq_pitch) * p.seq_mul + (nt * NT) / p.seq_div < p.seq_valid);
       const int ch0 = nt * NT + col0;
       const size_t off = (static_cast<size_t>(b) * p.t_pitch + (valid ? t : 0)) * p.cout + ch0;
       // residual prefetch: issued before the accumulator wait so its latency hides under the MMAs
@@ -584,7 +589,8 @@ conv1d_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       int nt, ptt, b;
       decode(pt, nt, ptt, b);
       const int t = (2 * ptt + static_cast<int>(rank)) * kTileM + row;
-      const bool valid = t < p.t;
+      bool valid = t < p.t;
+      if (p.seq_pitch) valid = valid && ((t % p.seq_pitch) * p.seq_mul + (nt * NT) / p.seq_div < p.seq_valid);
       const int ch0 = nt * NT + col0;
       const size_t off = (static_cast<size_t>(b) * p.t_pitch + (valid ? t : 0)) * p.cout + ch0;
       hg::U8 rpre[kGroups16];
@@ -774,6 +780,7 @@ struct ConvExtra {
   float fm_coef = 0.f;
   int group_mod = 0;      // 0: one input channel block per N tile (forward grouped convs)
   int t_in_valid = -1;    // stride 1 only: input rows >= this are read as zero (TMA bound); -1 = t_in_rows
+  int seq_pitch = 0, seq_valid = 0, seq_mul = 1, seq_div = 1 << 30;
 };
 
 int conv_forward(const void* x, const void* w_packed, const float* bias, int batch, int t_in_rows,
@@ -876,6 +883,9 @@ int conv_forward(const void* x, const void* w_packed, const float* bias, int bat
   p.fm_g = static_cast<const __nv_bfloat16*>(ex.fm_g);
   p.fm_coef = ex.fm_coef;
   p.group_mod = ex.group_mod > 0 ? ex.group_mod : p.tiles_n;
+  p.seq_pitch = ex.seq_pitch; p.seq_valid = ex.seq_valid; p.seq_mul = ex.seq_mul;
+  p.seq_div = ex.seq_div > 0 ? ex.seq_div : (1 << 30);
+  HG_REQUIRE(ex.seq_pitch >= 0 && (ex.seq_pitch == 0 || batch == 1), "conv: flat sequences need batch == 1");
   HG_REQUIRE(!p.fm_g || p.fm_r, "conv: fm_g without fm_r");
   HG_REQUIRE(ex.t_in_valid < 0 || (stride == 1 && ex.t_in_valid <= t_in_rows), "conv: bad input bound");
   const int t_in_bound = ex.t_in_valid >= 0 ? ex.t_in_valid : t_in_rows / stride;
@@ -949,20 +959,22 @@ extern "C" int hg_conv1d_general_fwd(const void* x, const void* w_packed, const 
                                      int t_in_rows, int c_total, int t_out, int t_out_rows, int groups,
                                      int cout, int ktaps,
                                      int stride, int pad_left, void* out_act, float act_slope,
-                                     void* out_raw, void* stream) {
+                                     void* out_raw, int seq_pitch, int seq_valid, void* stream) {
   HG_REQUIRE(groups >= 1 && c_total % groups == 0 && cout % groups == 0, "hg_conv1d_general_fwd: bad groups");
   const int cin_tile = c_total / groups, n_tile_g = cout / groups;
+  ConvExtra ex;
+  ex.seq_pitch = seq_pitch; ex.seq_valid = seq_valid;
   if (groups == 1) {
     const int n_tile = (cout % 256 == 0) ? 256 : (cout % 128 == 0) ? 128 : (cout % 64 == 0) ? 64 : 32;
     return conv_forward(x, w_packed, bias, batch, t_in_rows, c_total, t_out, t_out_rows, c_total, cout, n_tile, 0,
                         ktaps,
                         stride, 1, pad_left, nullptr, nullptr, nullptr, 1.f, out_raw, out_act, act_slope,
-                        stream);
+                        stream, ex);
   }
   return conv_forward(x, w_packed, bias, batch, t_in_rows, c_total, t_out, t_out_rows, cin_tile, cout, n_tile_g, 1,
                       ktaps,
                       stride, 1, pad_left, nullptr, nullptr, nullptr, 1.f, out_raw, out_act, act_slope,
-                      stream);
+                      stream, ex);
 }
 
 // hg_conv1d_dgrad — data gradient of a conv layer, run on the same implicit-GEMM kernel: the gradient of a
@@ -976,7 +988,8 @@ extern "C" int hg_conv1d_dgrad(const void* dy, const void* w_packed, int batch, 
                                int c_dy_total, int t_out, int t_out_rows, int groups, int n_tile, int cout, int ktaps,
                                int dilation, int pad_left, const void* mask_src, float mask_slope,
                                const void* fm_r, const void* fm_g, float fm_coef, const void* res0, const void* res1,
-                               float scale, void* out, void* stream) {
+                               float scale, void* out, int seq_pitch, int seq_valid, int seq_mul, int seq_div,
+                               void* stream) {
   HG_REQUIRE(groups >= 1 && c_dy_total % groups == 0, "hg_conv1d_dgrad: bad groups");
   HG_REQUIRE(ktaps > 0 && dilation > 0 && 128 + (ktaps - 1) * dilation <= 256,
              "hg_conv1d_dgrad: halo too large for one TMA box (taps=%d dilation=%d)", ktaps, dilation);
@@ -984,6 +997,7 @@ extern "C" int hg_conv1d_dgrad(const void* dy, const void* w_packed, int batch, 
   ex.mask = mask_src; ex.mask_slope = mask_slope;
   ex.fm_r = fm_r; ex.fm_g = fm_g; ex.fm_coef = fm_coef;
   ex.t_in_valid = t_dy_valid;
+  ex.seq_pitch = seq_pitch; ex.seq_valid = seq_valid; ex.seq_mul = seq_mul > 0 ? seq_mul : 1; ex.seq_div = seq_div;
   const int cin_tile = c_dy_total / groups;
   if (groups == 1) {
     if (n_tile <= 0) n_tile = (cout % 256 == 0) ? 256 : (cout % 128 == 0) ? 128 : (cout % 64 == 0) ? 64 : 32;

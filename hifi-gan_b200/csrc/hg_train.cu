@@ -228,7 +228,7 @@ disc_last_bwd_dw_kernel(const __nv_bfloat16* __restrict__ x, const float* __rest
 // product accumulated in registers across tiles (column k is the bias), the audio gradient one thread pair per
 // position.  One atomic per output per block.
 constexpr int kFirstTile = 128;
-constexpr int kFirstChunk = 2048;
+constexpr int kFirstChunk = 1024;
 constexpr int kFirstK = 16;
 
 __global__ void __launch_bounds__(256)
@@ -240,7 +240,8 @@ disc_first_bwd_kernel(const float* __restrict__ y, const float* __restrict__ w, 
   float* ws = reinterpret_cast<float*>(smb);                    // [k][cout]
   float* xin = ws + k * cout;                                   // [tile][kFirstK + 1]  (last column = 1: bias)
   int* xidx = reinterpret_cast<int*>(xin + kFirstTile * (kFirstK + 1));   // [tile][kFirstK]
-  __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(xidx + kFirstTile * kFirstK);   // [tile][pitch]
+  float* gsm = reinterpret_cast<float*>(xidx + kFirstTile * kFirstK);          // [2][tile][kFirstK] tap sums
+  __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(gsm + 2 * kFirstTile * kFirstK);   // [tile][pitch]
   const int tid = threadIdx.x;
   for (int i = tid; i < k * cout; i += 256) {
     const int j = i / cout, co = i % cout;
@@ -286,24 +287,32 @@ disc_first_bwd_kernel(const float* __restrict__ y, const float* __restrict__ w, 
     }
     __syncthreads();
     if (dw) {
+      // 8 independent accumulators per thread, row loop outside: the shared-memory loads of consecutive rows
+      // pipeline instead of forming one dependent load -> FMA chain per output
+      int dco[8], dcol[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int o = tid + 256 * i;
-        if (o < n_out) {
-          const int j = o / cout, co = o % cout;
-          const int col = j == k ? kFirstK : j;
-          float a = 0.f;
-          for (int r = 0; r < kFirstTile; ++r) a += __bfloat162float(dp[r * pitch + co]) * xin[r * (kFirstK + 1) + col];
-          acc[i] += a;
-        }
+        const int o = min(tid + 256 * i, n_out - 1);
+        const int j = o / cout;
+        dco[i] = o % cout;
+        dcol[i] = j == k ? kFirstK : j;
+      }
+#pragma unroll 4
+      for (int r = 0; r < kFirstTile; ++r) {
+        const __nv_bfloat16* dr = dp + r * pitch;
+        const float* xr = xin + r * (kFirstK + 1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += __bfloat162float(dr[dco[i]]) * xr[dcol[i]];
       }
     }
     if (dy) {
-      const int r = tid & (kFirstTile - 1), half = tid >> 7;   // two threads per position, half of the channels each
-      if (q0 + r < p1) {
-        float gy[kFirstK];
+      // phase A: per output position, G[j] = sum_co dpre[co] * w[co][j] (two threads per position, half of the
+      // channels each); phase B: every INPUT row of the tile gathers its taps from G -> one atomic per input row
+      const int r = tid & (kFirstTile - 1), half = tid >> 7;
+      float gy[kFirstK];
 #pragma unroll
-        for (int j = 0; j < kFirstK; ++j) gy[j] = 0.f;
+      for (int j = 0; j < kFirstK; ++j) gy[j] = 0.f;
+      if (q0 + r < p1) {
         const int c0 = half * (cout / 2), c1 = c0 + cout / 2;
         for (int co = c0; co < c1; ++co) {
           const float d = __bfloat162float(dp[r * pitch + co]);
@@ -311,13 +320,25 @@ disc_first_bwd_kernel(const float* __restrict__ y, const float* __restrict__ w, 
           for (int j = 0; j < kFirstK; ++j)
             if (j < k) gy[j] += d * ws[j * cout + co];
         }
+      }
 #pragma unroll
-        for (int j = 0; j < kFirstK; ++j) {
-          if (j < k) {
-            const int idx = xidx[r * kFirstK + j];
-            if (idx >= 0) atomicAdd(dy + static_cast<size_t>(b) * t + idx, gy[j]);
-          }
+      for (int j = 0; j < kFirstK; ++j) gsm[(half * kFirstTile + r) * kFirstK + j] = gy[j];
+      __syncthreads();
+      const int n_in = (kFirstTile - 1) * stride + k;
+      for (int e = tid; e < n_in; e += 256) {
+        const int hh = q0 * stride - pad + e;
+        if (hh < 0 || hh >= h_in) continue;
+        float a = 0.f;
+        for (int j = 0; j < k; ++j) {
+          const int num = hh + pad - j;
+          if (num < 0 || num % stride) continue;
+          const int ho = num / stride;
+          if (ho < q0 || ho >= p1 || ho >= q0 + kFirstTile) continue;
+          a += gsm[(ho - q0) * kFirstK + j] + gsm[(kFirstTile + ho - q0) * kFirstK + j];
         }
+        int ii = hh * period + wcol;
+        if (ii >= t) ii = 2 * (t - 1) - ii;
+        atomicAdd(dy + static_cast<size_t>(b) * t + ii, a);
       }
     }
   }
@@ -606,7 +627,7 @@ extern "C" int hg_disc_first_conv_bwd(const float* y, const float* w, const void
   HG_REQUIRE(h_out > 0 && h_rows >= h_out && batch * period <= 65535, "hg_disc_first_conv_bwd: bad geometry");
   dim3 grid((h_out + kFirstChunk - 1) / kFirstChunk, batch * period);
   const size_t smem = static_cast<size_t>(k) * cout * 4 + kFirstTile * (kFirstK + 1) * 4 + kFirstTile * kFirstK * 4 +
-                      static_cast<size_t>(kFirstTile) * (cout + 2) * 2;
+                      2 * kFirstTile * kFirstK * 4 + static_cast<size_t>(kFirstTile) * (cout + 2) * 2;
   static bool configured = false;
   if (!configured) {
     HG_CHECK_CUDA(cudaFuncSetAttribute(disc_first_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));

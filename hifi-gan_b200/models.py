@@ -673,7 +673,7 @@ def _disc_forward(L, owner: nn.Module, y: torch.Tensor, period: int, first, mids
         out, h_out, rows_out, _ = ws[1 + li]
         _lib.check(L.hg_conv1d_general_fwd(act.data_ptr(), w.data_ptr(), bias.data_ptr(), nseq, rows, layer.cin, h_out,
                                            rows_out, layer.groups_eff, layer.cout, layer.k, layer.stride, layer.pad,
-                                           out.data_ptr(), LRELU_SLOPE, 0, st), "hg_conv1d_general_fwd")
+                                           out.data_ptr(), LRELU_SLOPE, 0, 0, 0, st), "hg_conv1d_general_fwd")
         act, h, rows = out, h_out, rows_out
     mp, kp, c_last = mods[-1], last[0], ws[-1][3]
     wp, bp = _disc_weights(owner, len(mods) - 1, mp, lambda: (_effective_weight(mp).reshape(c_last, kp).contiguous(),

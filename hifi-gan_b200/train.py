@@ -153,7 +153,7 @@ class _GenLayerGrad:
         pc = self.pc
         _lib.check(L.hg_conv1d_dgrad(_p(dy), self.wd.data_ptr(), batch, t, t, self.rows, t, t, 1, 0, pc.cin_p,
                                      pc.taps, pc.dil, self.dgrad_pad, _p(mask), slope, 0, 0, 0.0, _p(res0), _p(res1),
-                                     scale, _p(out), _stream()), "hg_conv1d_dgrad")
+                                     scale, _p(out), 0, 0, 1, 0, _stream()), "hg_conv1d_dgrad")
 
     def to_param_grads(self, L, scratch: torch.Tensor) -> None:
         """packed dW -> (weight_g.grad, weight_v.grad) or weight.grad; bias.grad"""
@@ -399,16 +399,22 @@ class _DiscBwdLayer:
                    "hg_pack_disc_weight")
 
     def dgrad(self, L, dy, nseq: int, t_dy_valid: int, t_dy_rows: int, rows_in: int, act_g, act_r, fm_coef: float,
-              out, st) -> None:
-        """out[nseq][rows_in][cin] = (conv^T(dy) + fm_coef * sgn(act_g - act_r)) * lrelu'(act_g)"""
+              out, st, flat_h_in: Optional[int] = None) -> None:
+        """out[nseq][rows_in][cin] = (conv^T(dy) + fm_coef * sgn(act_g - act_r)) * lrelu'(act_g).
+        flat_h_in given: the nseq sequences are laid end to end (pitch t_dy_rows output rows / rows_in input rows
+        each, zero gap rows) and run as ONE long sequence; only positions < flat_h_in of each are stored."""
         layer = self.layer
         s = layer.stride
         vrows = rows_in // s
-        _lib.check(L.hg_conv1d_dgrad(_p(dy), self.w.data_ptr(), nseq, t_dy_valid, t_dy_rows, layer.cout, vrows, vrows,
+        batch, t_valid, t_rows, t_out, seq = nseq, t_dy_valid, t_dy_rows, vrows, (0, 0, 1, 0)
+        if flat_h_in is not None:
+            batch, t_valid, t_rows, t_out = 1, nseq * t_dy_rows, nseq * t_dy_rows, nseq * vrows
+            seq = (vrows, flat_h_in, s, layer.cin)
+        _lib.check(L.hg_conv1d_dgrad(_p(dy), self.w.data_ptr(), batch, t_valid, t_rows, layer.cout, t_out, t_out,
                                      layer.groups_eff if self.grouped else 1,
                                      layer.cin_tile if self.grouped else 0, s * layer.cin, self.nshift, 1,
                                      self.pad_left, _p(act_g), LRELU_SLOPE, _p(act_r),
-                                     _p(act_g) if act_r is not None else 0, fm_coef, 0, 0, 1.0, _p(out), st),
+                                     _p(act_g) if act_r is not None else 0, fm_coef, 0, 0, 1.0, _p(out), *seq, st),
                    "hg_conv1d_dgrad")
 
 
@@ -490,11 +496,12 @@ class _SubDiscTrainer:
         if h * period - t >= t:
             raise RuntimeError("reflect padding needs n_pad < t (reference F.pad behaviour)")
         hh = (h + 2 * p0 - k0) // s0 + 1
-        geo = [(hh, _round_up(hh, self.mids[0].stride), c0)]
-        for li, layer in enumerate(self.mids):
+        hs, cs = [hh], [c0]
+        for layer in self.mids:
             hh = (hh + 2 * layer.pad - layer.k) // layer.stride + 1
-            nxt = self.mids[li + 1].stride if li + 1 < len(self.mids) else 1
-            geo.append((hh, _round_up(hh, nxt), layer.cout))
+            hs.append(hh)
+            cs.append(layer.cout)
+        geo = [(h_, p_, c_) for h_, p_, c_ in zip(hs, self._flat_pitches(hs), cs)]
         nseq = nb * period
         g = {"geo": geo, "nseq": nseq,
              "act": [torch.zeros(nseq, r, c, dtype=torch.bfloat16, device=dev) for _, r, c in geo],
@@ -505,6 +512,36 @@ class _SubDiscTrainer:
             self.ws.pop(next(iter(self.ws)))
         self.ws[key] = g
         return g
+
+    def _flat_pitches(self, hs: List[int]) -> List[int]:
+        """Rows per sequence of every activation buffer when the sequences of a layer are laid end to end and run as
+        ONE long sequence (the late layers have 10..51 rows per sequence; 128-row tiles would be mostly empty
+        otherwise).  Buffer l feeds layer l (stride s_l) whose output is buffer l+1, so pitch_l = s_l * pitch_{l+1};
+        the zero rows between two sequences must cover the padding every conv / data-gradient tap reaches into."""
+        def chain(p_last):
+            ps = [p_last]
+            for layer in reversed(self.mids):
+                ps.insert(0, ps[0] * layer.stride)
+            return ps
+
+        def ok(ps):
+            for li, (layer, bl) in enumerate(zip(self.mids, self.bwd)):
+                h_in, p_in, h_out, p_out, s = hs[li], ps[li], hs[li + 1], ps[li + 1], layer.stride
+                if p_in - h_in < layer.pad:                                   # left padding of the next sequence
+                    return False
+                if (h_out - 1) * s + layer.k - 1 - layer.pad > p_in - 1:        # right reach of the last output
+                    return False
+                smax = bl.smin + bl.nshift - 1
+                if p_out - h_out < -bl.smin:                                   # data gradient: taps before row 0
+                    return False
+                if (h_in + s - 1) // s - 1 + smax > p_out - 1:                  # ... and past the last row
+                    return False
+            return True
+
+        p_last = hs[-1] + 1
+        while not ok(chain(p_last)):
+            p_last += 1
+        return chain(p_last)
 
     # ---- forward -------------------------------------------------------------------------------------------
     def forward(self, ycat: torch.Tensor, nreal: int):
@@ -537,9 +574,10 @@ class _SubDiscTrainer:
                 out = G["act"][1 + li]
                 h_out, rows_out, _ = G["geo"][1 + li]
                 _lib.check(L.hg_conv1d_general_fwd(act[seq0:].data_ptr(), W["fwd"][1 + li].data_ptr(), bias.data_ptr(),
-                                                   nseq, rows, layer.cin, h_out, rows_out, layer.groups_eff,
-                                                   layer.cout, layer.k, layer.stride, layer.pad,
-                                                   out[seq0:].data_ptr(), LRELU_SLOPE, 0, st), "hg_conv1d_general_fwd")
+                                                   1, nseq * rows, layer.cin, nseq * rows_out, nseq * rows_out,
+                                                   layer.groups_eff, layer.cout, layer.k, layer.stride, layer.pad,
+                                                   out[seq0:].data_ptr(), LRELU_SLOPE, 0, rows_out, h_out, st),
+                           "hg_conv1d_general_fwd")
                 act, h, rows = out, h_out, rows_out
             c_last = G["geo"][-1][2]
             wp = W["eff"][-1].reshape(c_last, self.kpost).contiguous()
@@ -649,9 +687,9 @@ class _SubDiscTrainer:
                 _lib.check(L.hg_colsum_bf16(d_out.data_ptr(), nseq, h_out, rows_out, layer.cout, 0, self.db.data_ptr(),
                                             st), "hg_colsum_bf16")
                 self._bias(m, self.db[: layer.cout], accumulate)
-                _lib.check(L.hg_conv1d_wgrad(a_in[seq0:].data_ptr(), d_out.data_ptr(), nseq, rows_in, layer.cin, h_out,
-                                             rows_out, layer.groups_eff, layer.cout, layer.k, layer.stride, 1,
-                                             layer.pad, self.dwp.data_ptr(), 0, st), "hg_conv1d_wgrad")
+                _lib.check(L.hg_conv1d_wgrad(a_in[seq0:].data_ptr(), d_out.data_ptr(), 1, nseq * rows_in, layer.cin,
+                                             nseq * rows_out, nseq * rows_out, layer.groups_eff, layer.cout, layer.k,
+                                             layer.stride, 1, layer.pad, self.dwp.data_ptr(), 0, st), "hg_conv1d_wgrad")
                 cin_g = layer.cin // layer.groups
                 order = (c_int * layer.k)(*layer.order)
                 _lib.check(L.hg_unpack_wgrad_conv(self.dwp.data_ptr(), layer.cout, cin_g, layer.k, layer.cout,
@@ -659,7 +697,8 @@ class _SubDiscTrainer:
                                                   self.scratch.data_ptr(), st), "hg_unpack_wgrad_conv")
                 self._route(L, m, self.scratch, layer.cout, cin_g * layer.k, W, 1 + li, accumulate)
             self.bwd[li].dgrad(L, d_out, nseq, h_out, rows_out, rows_in, a_in[seq0:],
-                               a_in[seq0 - nr:] if fm else None, nfm[li] if fm else 0.0, G["grad"][li][seq0:], st)
+                               a_in[seq0 - nr:] if fm else None, nfm[li] if fm else 0.0, G["grad"][li][seq0:], st,
+                               flat_h_in=h_in)
         # first conv (Cin = 1)
         k0, s0, p0, c0 = self.first
         m0 = self.mods[0]

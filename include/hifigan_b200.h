@@ -92,12 +92,16 @@ int hg_conv1d_fwd(const void* x, const void* w_packed, const float* bias, int ba
  * [ktaps][cout][c_total/groups] with the taps in the order given by hg_conv1d_tap_order (identity for stride 1).
  * Per-group widths must be multiples of 32 (cin) and one of 32/64/128/256 (cout): callers merge narrower
  * groups into block-diagonal ones.  out_act / out_raw bf16 [B][t_out_rows][cout] (rows >= t_out are left
- * untouched so a zero-initialised buffer keeps its zero padding), either may be NULL. */
+ * untouched so a zero-initialised buffer keeps its zero padding), either may be NULL.
+ * Flat sequences (seq_pitch > 0, batch == 1): many short sequences laid end to end on the time axis, seq_pitch
+ * output rows each (seq_pitch * stride input rows), the first seq_valid of them real; the zero rows between two
+ * sequences stand in for the conv padding, and rows >= seq_valid of every sequence are never written.  The late
+ * discriminator layers (10..51 rows per sequence, hundreds of sequences) fill 128-row tiles this way. */
 int hg_conv1d_tap_order(int ktaps, int stride, int pad_left, int* host_order);
 int hg_conv1d_general_fwd(const void* x, const void* w_packed, const float* bias, int batch, int t_in_rows,
                           int c_total, int t_out, int t_out_rows, int groups, int cout, int ktaps, int stride,
                           int pad_left,
-                          void* out_act, float act_slope, void* out_raw, void* stream);
+                          void* out_act, float act_slope, void* out_raw, int seq_pitch, int seq_valid, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * hg_resblock_pair_fwd — one fused ResBlock1 step (src/models.py:36-41) for the narrow stages:
@@ -218,11 +222,15 @@ int hg_pack_dgrad_weight(const void* w_packed, int ktaps, int n, int c, void* ou
  * mask_src / fm_r / fm_g / res* / out bf16 [B][t_out_rows][cout] (optional except out).  mask_src is the layer
  * input as the forward stored it (leaky_relu'd: its sign is the sign of the pre-activation); fm_* add the
  * feature-matching L1 gradient (src/models.py:251-257).  groups > 1: N tile nt (width n_tile) reads dy channel
- * block nt % groups — the polyphase (phase-major) output of a strided grouped conv's gradient. */
+ * block nt % groups — the polyphase (phase-major) output of a strided grouped conv's gradient.
+ * Flat sequences (seq_pitch > 0, batch == 1, see hg_conv1d_general_fwd): output element (row t, channel n) is stored
+ * only when (t % seq_pitch) * seq_mul + n / seq_div < seq_valid — for a polyphase gradient seq_mul = stride and
+ * seq_div = the layer's input channel count, i.e. the input position the element stands for must be real. */
 int hg_conv1d_dgrad(const void* dy, const void* w_packed, int batch, int t_dy_valid, int t_dy_rows, int c_dy_total,
                     int t_out, int t_out_rows, int groups, int n_tile, int cout, int ktaps, int dilation, int pad_left,
                     const void* mask_src, float mask_slope, const void* fm_r, const void* fm_g, float fm_coef,
-                    const void* res0, const void* res1, float scale, void* out, void* stream);
+                    const void* res0, const void* res1, float scale, void* out, int seq_pitch, int seq_valid,
+                    int seq_mul, int seq_div, void* stream);
 
 /* hg_conv1d_wgrad — weight gradient as a tcgen05 implicit GEMM contracting over time (MN-major operands):
  *   dw[q][co][ci] (+)= sum_{b, t < t_out} dy[b,t,co] * xv[b, t + row(q), col(q) + blk(co) + ci]

@@ -406,7 +406,7 @@ def test_general_conv_vs_torch(H, case):
     rows_out = t_out + 5
     out = torch.full((b, rows_out, cout), 7.0, dtype=torch.bfloat16, device=dev)
     _lib.check(L.hg_conv1d_general_fwd(x.data_ptr(), wp.data_ptr(), bias.data_ptr(), b, rows, cin, t_out, rows_out,
-                                       layer.groups_eff, cout, k, s, pad, out.data_ptr(), 0.1, 0,
+                                       layer.groups_eff, cout, k, s, pad, out.data_ptr(), 0.1, 0, 0, 0,
                                        torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     ref = F.leaky_relu(F.conv1d(x[:, :t].float().transpose(1, 2), w, bias, stride=s, padding=pad, groups=g), 0.1)

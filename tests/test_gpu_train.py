@@ -114,7 +114,7 @@ def test_dgrad_stride1_vs_torch_autograd(H, case):
     out = torch.empty(b, t, cin, dtype=torch.bfloat16, device=dev)
     _lib.check(L.hg_conv1d_dgrad(dy.data_ptr(), wd.data_ptr(), b, t, t + 2, cout, t, t, 1, 0, cin, k, d,
                                  (k - 1) * d - pad, x_act.data_ptr(), 0.1, 0, 0, 0.0, res.data_ptr(), 0, 0.5,
-                                 out.data_ptr(), _st()), "hg_conv1d_dgrad")
+                                 out.data_ptr(), 0, 0, 1, 0, _st()), "hg_conv1d_dgrad")
     torch.cuda.synchronize()
     wr = wp.float().permute(1, 2, 0).contiguous()
     xin = x_act.float().transpose(1, 2).requires_grad_(True)
