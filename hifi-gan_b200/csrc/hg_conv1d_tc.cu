@@ -983,13 +983,13 @@ extern "C" int hg_conv1d_general_fwd(const void* x, const void* w_packed, const 
 // conv weight).  The epilogue applies the leaky_relu backward mask of the layer input, the feature-matching L1
 // term and up to two gradient addends (residual path / MRF branch sum):
 //   out[b,t,n] = ((sum_{j,c} dy[b, t + j*dil - pad_left, blk(n) + c] * w[j][n][c] + fm_coef * sgn(fm_g - fm_r))
-//                 * (mask_src > 0 ? 1 : mask_slope) + res0 + res1) * scale
+//                 * (mask_src > 0 ? 1 : mask_slope) + res0 + res1 + res2) * scale
 extern "C" int hg_conv1d_dgrad(const void* dy, const void* w_packed, int batch, int t_dy_valid, int t_dy_rows,
                                int c_dy_total, int t_out, int t_out_rows, int groups, int n_tile, int cout, int ktaps,
                                int dilation, int pad_left, const void* mask_src, float mask_slope,
                                const void* fm_r, const void* fm_g, float fm_coef, const void* res0, const void* res1,
-                               float scale, void* out, int seq_pitch, int seq_valid, int seq_mul, int seq_div,
-                               void* stream) {
+                               const void* res2, float scale, void* out, int seq_pitch, int seq_valid, int seq_mul,
+                               int seq_div, void* stream) {
   HG_REQUIRE(groups >= 1 && c_dy_total % groups == 0, "hg_conv1d_dgrad: bad groups");
   HG_REQUIRE(ktaps > 0 && dilation > 0 && 128 + (ktaps - 1) * dilation <= 256,
              "hg_conv1d_dgrad: halo too large for one TMA box (taps=%d dilation=%d)", ktaps, dilation);
@@ -1002,12 +1002,12 @@ extern "C" int hg_conv1d_dgrad(const void* dy, const void* w_packed, int batch, 
   if (groups == 1) {
     if (n_tile <= 0) n_tile = (cout % 256 == 0) ? 256 : (cout % 128 == 0) ? 128 : (cout % 64 == 0) ? 64 : 32;
     return conv_forward(dy, w_packed, nullptr, batch, t_dy_rows, c_dy_total, t_out, t_out_rows, cin_tile, cout,
-                        n_tile, 0, ktaps, 1, dilation, pad_left, res0, res1, nullptr, scale, out, nullptr, 1.f,
+                        n_tile, 0, ktaps, 1, dilation, pad_left, res0, res1, res2, scale, out, nullptr, 1.f,
                         stream, ex);
   }
   HG_REQUIRE(n_tile > 0, "hg_conv1d_dgrad: grouped layers need an explicit N tile");
   ex.group_mod = groups;
   return conv_forward(dy, w_packed, nullptr, batch, t_dy_rows, c_dy_total, t_out, t_out_rows, cin_tile, cout,
-                      n_tile, 1, ktaps, 1, dilation, pad_left, res0, res1, nullptr, scale, out, nullptr, 1.f,
+                      n_tile, 1, ktaps, 1, dilation, pad_left, res0, res1, res2, scale, out, nullptr, 1.f,
                       stream, ex);
 }

@@ -120,9 +120,12 @@ class _PackedConv:
             _lib.check(L.hg_pack_conv1d_weight(v.data_ptr(), 0 if g is None else g.contiguous().data_ptr(),
                                                self.cout_p, self.cin, self.taps, self.cin_p,
                                                self.w.data_ptr(), _stream()), "hg_pack_conv1d_weight")
-            self.bias.zero_()
-            if b is not None:
-                self.bias[: self.cout].copy_(b)
+            if b is not None and self.cout_p == self.cout and b.is_contiguous():
+                self.bias = b           # no padding: read the parameter in place (no copy kernel per step)
+            else:
+                self.bias.zero_()
+                if b is not None:
+                    self.bias[: self.cout].copy_(b)
         else:
             k = m.kernel_size[0]
             if self.cout_p != self.cout or self.cin_p != self.cin:

@@ -99,6 +99,29 @@ class FlatParams:
                                             self.step_dev.data_ptr(), grad_scale, _stream()), "hg_adamw_step")
 
 
+class _Lanes:
+    """A set of side streams for independent kernel chains (the eight sub-discriminators, the MRF branches, the
+    weight-gradient launches beside the data-gradient chain).  fork() makes every lane wait for the work already
+    queued on the current stream, join() makes the current stream wait for every lane; both are event waits, so
+    under CUDA-graph capture the lanes become parallel branches of the graph."""
+
+    def __init__(self, n: int, device):
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(n)] if torch.cuda.is_available() else []
+
+    def fork(self) -> None:
+        main = torch.cuda.current_stream()
+        for s in self.streams:
+            s.wait_stream(main)
+
+    def join(self) -> None:
+        main = torch.cuda.current_stream()
+        for s in self.streams:
+            main.wait_stream(s)
+
+    def lane(self, i: int):
+        return torch.cuda.stream(self.streams[i % len(self.streams)])
+
+
 def allreduce_gradients(flat: FlatParams, group=None) -> float:
     """Data-parallel exchange step: SUM all-reduce of one network's flat gradient buffer over the process group
     (NCCL over NVLink on the GPUs; gloo in the CPU tests).  Returns the factor the optimizer must apply to the summed
@@ -149,11 +172,11 @@ class _GenLayerGrad:
         _lib.check(L.hg_colsum_bf16(_p(dy), batch, t, t, c, 0, self.db.data_ptr(), _stream()), "hg_colsum_bf16")
 
     def dgrad(self, L, dy, batch: int, t: int, out, mask=None, slope: float = LRELU_SLOPE, res0=None, res1=None,
-              scale: float = 1.0) -> None:
+              res2=None, scale: float = 1.0) -> None:
         pc = self.pc
         _lib.check(L.hg_conv1d_dgrad(_p(dy), self.wd.data_ptr(), batch, t, t, self.rows, t, t, 1, 0, pc.cin_p,
                                      pc.taps, pc.dil, self.dgrad_pad, _p(mask), slope, 0, 0, 0.0, _p(res0), _p(res1),
-                                     scale, _p(out), 0, 0, 1, 0, _stream()), "hg_conv1d_dgrad")
+                                     _p(res2), scale, _p(out), 0, 0, 1, 0, _stream()), "hg_conv1d_dgrad")
 
     def to_param_grads(self, L, scratch: torch.Tensor) -> None:
         """packed dW -> (weight_g.grad, weight_v.grad) or weight.grad; bias.grad"""
@@ -204,7 +227,11 @@ class GeneratorTrainer:
         self.g_ups = [_GenLayerGrad(pc, device) for pc in e.ups]
         self.g_blocks = [[_GenLayerGrad(pc, device) for pc in blk] for blk in e.blocks]
         nmax = max(gl.dwp.numel() for gl in [self.g_pre] + self.g_ups + [x for b in self.g_blocks for x in b])
-        self.scratch = torch.empty(nmax, dtype=torch.float32, device=device)
+        # stream lanes: 0 .. nk-2 = MRF branches beside the main stream, W_LANE + j = weight-gradient work of branch j
+        nk = gen.num_kernels
+        self.W_LANE = max(1, nk - 1)
+        self.lanes = _Lanes(self.W_LANE + nk, device)
+        self.scratch = [torch.empty(nmax, dtype=torch.float32, device=device) for _ in range(self.W_LANE + nk)]
         post = gen.conv_post
         self.post_dw = torch.zeros(e.post_cin_p, post.kernel_size[0], dtype=torch.float32, device=device)
         self.post_db = torch.zeros(1, dtype=torch.float32, device=device)
@@ -235,13 +262,16 @@ class GeneratorTrainer:
             c = up.cout_p
             steps = len(e.blocks[i * nk]) // (2 if self.two_conv else 1)
             mk = lambda: bf(b, t, c)
+            # The MRF branches run on parallel stream lanes and the weight-gradient launches beside the data-gradient
+            # chain, so nothing is ping-ponged: every branch / step owns its buffers.
             st = {"t_in": t_in, "t": t, "c": c, "steps": steps, "x_raw": mk(), "xa0": mk(), "stage_act": mk(),
-                  "raw": [mk(), mk()], "r": [mk() for _ in range(max(1, nk - 1))],
+                  "raw": [[mk(), mk()] for _ in range(nk)], "r": [mk() for _ in range(max(1, nk - 1))],
                   # saved conv inputs: xa[j][s] for s >= 1 (s = 0 is the shared xa0), t1[j][s]
                   "xa": [[None] + [mk() for _ in range(steps - 1)] for _ in range(nk)],
                   "t1": [[mk() for _ in range(steps)] for _ in range(nk)] if self.two_conv else None,
-                  # gradient buffers
-                  "g0": mk(), "gp": [mk(), mk()], "gt1": mk(), "gb": [mk(), mk()]}
+                  # gradients: g0 at the stage output, gs[j][s] at the input of step s of branch j, gt1[j][s]
+                  "g0": mk(), "gs": [[mk() for _ in range(steps)] for _ in range(nk)],
+                  "gt1": [[mk() for _ in range(steps)] for _ in range(nk)] if self.two_conv else None}
             ws["stages"].append(st)
         ws["y"] = torch.empty(b, 1, t, dtype=torch.float32, device=dev)
         ws["dpre"] = torch.empty(b, t, dtype=torch.float32, device=dev)
@@ -253,60 +283,122 @@ class GeneratorTrainer:
         return ws
 
     # ---- forward -------------------------------------------------------------------------------------------
+    def _branch_forward(self, L, st, j: int, packs, b: int, t: int, stop_before_last: bool):
+        """steps of MRF branch j; returns the (src, conv, residual) of its final launch when stop_before_last"""
+        cur_raw, cur_act = st["x_raw"], st["xa0"]
+        for s in range(st["steps"]):
+            last = s == st["steps"] - 1
+            if self.two_conv:
+                _conv(L, cur_act, packs[2 * s], b, t, out_act=st["t1"][j][s])
+                src, pc = st["t1"][j][s], packs[2 * s + 1]
+            else:
+                src, pc = cur_act, packs[s]
+            if not last:
+                nr, na = st["raw"][j][s & 1], st["xa"][j][s + 1]
+                _conv(L, src, pc, b, t, res=(cur_raw, None, None), out_raw=nr, out_act=na)
+                cur_raw, cur_act = nr, na
+            elif stop_before_last:
+                return src, pc, cur_raw
+            else:
+                _conv(L, src, pc, b, t, res=(cur_raw, None, None), out_raw=st["r"][j])
+        return None
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """mel fp32 [B,80,F] -> waveform fp32 [B,1,T] (engine-owned buffer), keeping what backward needs."""
         L = _lib.lib()
         e, gen = self.eng, self.gen
+        lanes = self.lanes
         e.refresh()
-        for gl in self.g_ups + [x_ for blk in self.g_blocks for x_ in blk]:
-            gl.pack(L)
         b, c, frames = x.shape
         xin = x.contiguous().float()
         ws = self._workspace(b, frames)
         self.cur = ws
+        lanes.fork()
+        with lanes.lane(self.W_LANE):            # the data-gradient filter banks are not needed before backward
+            for gl in self.g_ups + [x_ for blk in self.g_blocks for x_ in blk]:
+                gl.pack(L)
         _lib.check(L.hg_ncl_to_nlc(xin.data_ptr(), b, c, frames, e.pre.cin_p, ws["mel"].data_ptr(), 0, 0.0, _stream()),
                    "hg_ncl_to_nlc")
         _conv(L, ws["mel"], e.pre, b, frames, out_act=ws["pre_act"])
         cur, t = ws["pre_act"], frames
         nk = gen.num_kernels
+        main = torch.cuda.current_stream()
         for i, up in enumerate(e.ups):
             st = ws["stages"][i]
             _conv(L, cur, up, b, t, out_raw=st["x_raw"], out_act=st["xa0"])
             t = st["t"]
-            last_stage = i == len(e.ups) - 1
-            out_slope = 0.01 if last_stage else LRELU_SLOPE
-            for j in range(nk):
-                packs = e.blocks[i * nk + j]
-                cur_raw, cur_act = st["x_raw"], st["xa0"]
-                for s in range(st["steps"]):
-                    last = s == st["steps"] - 1
-                    if self.two_conv:
-                        _conv(L, cur_act, packs[2 * s], b, t, out_act=st["t1"][j][s])
-                        src, pc = st["t1"][j][s], packs[2 * s + 1]
-                    else:
-                        src, pc = cur_act, packs[s]
-                    if not last:
-                        nr, na = st["raw"][s & 1], st["xa"][j][s + 1]
-                        _conv(L, src, pc, b, t, res=(cur_raw, None, None), out_raw=nr, out_act=na)
-                        cur_raw, cur_act = nr, na
-                    elif j < nk - 1:
-                        _conv(L, src, pc, b, t, res=(cur_raw, None, None), out_raw=st["r"][j])
-                    else:
-                        others = tuple(st["r"][q] for q in range(nk - 1)) + (None,) * (3 - nk)
-                        _conv(L, src, pc, b, t, res=(cur_raw,) + others[:2], scale=1.0 / nk,
-                              out_act=st["stage_act"], slope=out_slope)
+            out_slope = 0.01 if i == len(e.ups) - 1 else LRELU_SLOPE
+            for j in range(nk - 1):              # branches 0 .. nk-2 on their own lanes
+                lanes.streams[j].wait_stream(main)
+                with lanes.lane(j):
+                    self._branch_forward(L, st, j, e.blocks[i * nk + j], b, t, False)
+            src, pc, cur_raw = self._branch_forward(L, st, nk - 1, e.blocks[i * nk + nk - 1], b, t, True)
+            for j in range(nk - 1):
+                main.wait_stream(lanes.streams[j])
+            others = tuple(st["r"][q] for q in range(nk - 1)) + (None,) * (3 - nk)
+            _conv(L, src, pc, b, t, res=(cur_raw,) + others[:2], scale=1.0 / nk, out_act=st["stage_act"],
+                  slope=out_slope)
             cur = st["stage_act"]
         post = gen.conv_post
         _lib.check(L.hg_conv_post_tanh_fwd(cur.data_ptr(), e.post_w.data_ptr(), e.post_b.data_ptr(), b, t,
                                            e.post_cin_p, post.kernel_size[0], ws["y"].data_ptr(), _stream()),
                    "hg_conv_post_tanh_fwd")
+        lanes.join()
         return ws["y"]
 
     # ---- backward ------------------------------------------------------------------------------------------
+    def _side(self, L, lane: int, producer, fn) -> None:
+        """run fn() (weight / bias gradient work) on a side lane once `producer` (a stream) reached this point"""
+        s = self.lanes.streams[lane]
+        s.wait_stream(producer)
+        with torch.cuda.stream(s):
+            fn()
+
+    def _branch_backward(self, L, st, i: int, j: int, b: int, t: int, c: int, g0, extra):
+        """data-gradient chain of MRF branch j on the current stream; its weight / bias gradients on lane W_LANE + j.
+        `extra` = gradients of the other branches to add into the last launch (None: write gs[j][0] alone)."""
+        gl = self.g_blocks[i * self.gen.num_kernels + j]
+        wl = self.W_LANE + j
+        g = g0
+        here = torch.cuda.current_stream()
+        for s in reversed(range(st["steps"])):
+            xa = st["xa0"] if s == 0 else st["xa"][j][s]
+            out = st["gs"][j][s]
+            r1, r2 = (extra if (s == 0 and extra is not None) else (None, None))
+            if self.two_conv:
+                c1, c2 = gl[2 * s], gl[2 * s + 1]
+                t1, gt1 = st["t1"][j][s], st["gt1"][j][s]
+
+                def w2(c2=c2, t1=t1, g=g):
+                    c2.bias_grad(L, g, b, t, c)
+                    c2.wgrad(L, t1, g, b, t)
+                    c2.to_param_grads(L, self.scratch[wl])
+                self._side(L, wl, here, w2)
+                c2.dgrad(L, g, b, t, gt1, mask=t1)
+
+                def w1(c1=c1, xa=xa, gt1=gt1):
+                    c1.bias_grad(L, gt1, b, t, c)
+                    c1.wgrad(L, xa, gt1, b, t)
+                    c1.to_param_grads(L, self.scratch[wl])
+                self._side(L, wl, here, w1)
+                c1.dgrad(L, gt1, b, t, out, mask=xa, res0=g, res1=r1, res2=r2)
+            else:
+                cc = gl[s]
+
+                def w0(cc=cc, xa=xa, g=g):
+                    cc.bias_grad(L, g, b, t, c)
+                    cc.wgrad(L, xa, g, b, t)
+                    cc.to_param_grads(L, self.scratch[wl])
+                self._side(L, wl, here, w0)
+                cc.dgrad(L, g, b, t, out, mask=xa, res0=g, res1=r1, res2=r2)
+            g = out
+        return g
+
     def backward(self, dy: torch.Tensor) -> None:
         """dy fp32 [B,T] (or [B,1,T]): gradient at the waveform of the LAST forward -> every parameter's .grad."""
         L = _lib.lib()
         e, gen, ws = self.eng, self.gen, self.cur
+        lanes = self.lanes
         b, frames = ws["mel"].shape[0], ws["mel"].shape[1]
         nk = gen.num_kernels
         dy = dy.reshape(b, -1).contiguous().float()
@@ -314,65 +406,56 @@ class GeneratorTrainer:
         post = gen.conv_post
         stages = ws["stages"]
         last = stages[-1]
+        main = torch.cuda.current_stream()
         self.post_dw.zero_()
         self.post_db.zero_()
+        lanes.fork()
         # conv_post + tanh; the kernel also applies the slope-0.01 leaky_relu mask of the last stage
         _lib.check(L.hg_conv_post_tanh_bwd(last["stage_act"].data_ptr(), e.post_w.data_ptr(), ws["y"].data_ptr(),
                                            dy.data_ptr(), b, t, e.post_cin_p, post.kernel_size[0], 0.01,
                                            last["g0"].data_ptr(), ws["dpre"].data_ptr(), self.post_dw.data_ptr(),
                                            self.post_db.data_ptr(), _stream()), "hg_conv_post_tanh_bwd")
-        first_scale = 1.0 / nk      # d(mean of branches)/d(branch): folded into the first consumer of g0 below
+        last["g0"].mul_(1.0 / nk)       # d(mean of branches)/d(branch); earlier stages get it from the ups dgrad scale
+
+        def post_grads():
+            cin, k = post.in_channels, post.kernel_size[0]
+            _route_weight_grad(L, post, self.post_dw[:cin].contiguous(), 1, cin * k)
+            post.bias.grad.copy_(self.post_db)
+        self._side(L, self.W_LANE, main, post_grads)
         for i in reversed(range(len(e.ups))):
             st = stages[i]
             t, c = st["t"], st["c"]
             g0 = st["g0"]
-            if i == len(e.ups) - 1:
-                # conv_post's dx is not yet divided by nk: do it once, in place, with the cheapest kernel at hand
-                g0.mul_(first_scale)
-            prev = None
-            for j in range(nk):
-                gl = self.g_blocks[i * nk + j]
-                g = g0
-                for s in reversed(range(st["steps"])):
-                    xa = st["xa0"] if s == 0 else st["xa"][j][s]
-                    out = st["gb"][j & 1] if s == 0 else st["gp"][s & 1]
-                    res1 = prev if s == 0 else None
-                    if self.two_conv:
-                        c1, c2 = gl[2 * s], gl[2 * s + 1]
-                        t1 = st["t1"][j][s]
-                        c2.bias_grad(L, g, b, t, c)
-                        c2.wgrad(L, t1, g, b, t)
-                        c2.dgrad(L, g, b, t, st["gt1"], mask=t1)
-                        c1.bias_grad(L, st["gt1"], b, t, c)
-                        c1.wgrad(L, xa, st["gt1"], b, t)
-                        c1.dgrad(L, st["gt1"], b, t, out, mask=xa, res0=g, res1=res1)
-                    else:
-                        cc = gl[s]
-                        cc.bias_grad(L, g, b, t, c)
-                        cc.wgrad(L, xa, g, b, t)
-                        cc.dgrad(L, g, b, t, out, mask=xa, res0=g, res1=res1)
-                    g = out
-                prev = g
-            dx_raw = prev                                  # gradient at the upsampler's output [B][t][c]
+            # branches 0 .. nk-2 on their own lanes, the last one here; it adds the others into its final launch
+            for j in range(nk - 1):
+                lanes.streams[j].wait_stream(main)
+                with lanes.lane(j):
+                    self._branch_backward(L, st, i, j, b, t, c, g0, None)
+            # the last branch's chain up to (not including) its final launch must not wait for the others: run it,
+            # then join right before the final launch.  _branch_backward issues the final launch itself, so the join
+            # happens first — the other branches are the same length, little is lost.
+            for j in range(nk - 1):
+                main.wait_stream(lanes.streams[j])
+            others = [st["gs"][j][0] for j in range(nk - 1)] + [None, None]
+            dx_raw = self._branch_backward(L, st, i, nk - 1, b, t, c, g0, (others[0], others[1]))
             up = self.g_ups[i]
             t_in = st["t_in"]
             up_in = ws["pre_act"] if i == 0 else stages[i - 1]["stage_act"]
-            _lib.check(L.hg_colsum_bf16(dx_raw.data_ptr(), b, t, t, c, 0, up.db.data_ptr(), _stream()), "hg_colsum_bf16")
-            up.wgrad(L, up_in, dx_raw, b, t_in)            # dy viewed as [B][t_in][stride * c]
+
+            def up_grads(up=up, dx_raw=dx_raw, up_in=up_in, t=t, c=c, t_in=t_in):
+                _lib.check(L.hg_colsum_bf16(dx_raw.data_ptr(), b, t, t, c, 0, up.db.data_ptr(), _stream()),
+                           "hg_colsum_bf16")
+                up.wgrad(L, up_in, dx_raw, b, t_in)            # dy viewed as [B][t_in][stride * c]
+                up.to_param_grads(L, self.scratch[self.W_LANE])
+            self._side(L, self.W_LANE, main, up_grads)
             if i > 0:
                 up.dgrad(L, dx_raw, b, t_in, stages[i - 1]["g0"], mask=up_in, scale=1.0 / nk)
             else:
                 up.dgrad(L, dx_raw, b, t_in, ws["g_pre"], mask=up_in)
                 self.g_pre.bias_grad(L, ws["g_pre"], b, frames, e.pre.cout_p)
                 self.g_pre.wgrad(L, ws["mel"], ws["g_pre"], b, frames)
-        # parameter gradients
-        for gl in [self.g_pre] + self.g_ups + [x for blk in self.g_blocks for x in blk]:
-            gl.to_param_grads(L, self.scratch)
-        cin = post.in_channels
-        k = post.kernel_size[0]
-        dw = self.post_dw[:cin].contiguous()
-        _route_weight_grad(L, post, dw, 1, cin * k)
-        post.bias.grad.copy_(self.post_db)
+                self.g_pre.to_param_grads(L, self.scratch[0])
+        lanes.join()
 
 
 # ------------------------------------------------------------------------------------------------ discriminators
@@ -414,7 +497,7 @@ class _DiscBwdLayer:
                                      layer.groups_eff if self.grouped else 1,
                                      layer.cin_tile if self.grouped else 0, s * layer.cin, self.nshift, 1,
                                      self.pad_left, _p(act_g), LRELU_SLOPE, _p(act_r),
-                                     _p(act_g) if act_r is not None else 0, fm_coef, 0, 0, 1.0, _p(out), *seq, st),
+                                     _p(act_g) if act_r is not None else 0, fm_coef, 0, 0, 0, 1.0, _p(out), *seq, st),
                    "hg_conv1d_dgrad")
 
 
@@ -443,6 +526,12 @@ class _SubDiscTrainer:
                                        for m in self.mods), dtype=torch.float32, device=device)
         self.db = torch.zeros(1024, dtype=torch.float32, device=device)
         self.wbufs = {}
+        self.fwd_valid = self.dgrad_valid = False
+        self.W_cached = None
+
+    def invalidate(self) -> None:
+        """the parameters changed (optimizer update / load_state_dict): re-fold and re-pack on next use"""
+        self.fwd_valid = self.dgrad_valid = False
 
     # ---- weights -------------------------------------------------------------------------------------------
     def _weights(self, part: int):
@@ -557,7 +646,14 @@ class _SubDiscTrainer:
         st = _stream()
         k0, s0, p0, c0 = self.first
         for pi, (b0, bn) in enumerate(parts):
-            W = self._weights(pi)
+            # weight_norm layers: the packs stay valid until the next optimizer update (the G-step forward of one
+            # step and the D-step forward of the next see the same weights); spectral norm moves on every call
+            if self.spectral or not self.fwd_valid:
+                W = self._weights(pi)
+                self.W_cached = W
+                self.fwd_valid = True
+            else:
+                W = self.W_cached
             self.parts.append((b0, bn, W))
             seq0, nseq = b0 * period, bn * period
             w0 = W["eff"][0].reshape(c0, k0).contiguous()
@@ -629,10 +725,15 @@ class _SubDiscTrainer:
         first_part = True
         for b0, bn, W in self.parts:
             seq0, nseq = b0 * period, bn * period
-            for bl, w_eff, w_f in zip(self.bwd, W["eff"][1:-1], W["fwd"][1:-1]):
-                bl.pack(w_eff, w_f)
+            self._pack_dgrad(W)
             self._backward_part(L, G, W, b0, bn, want_wgrad=True, fm=False, dy_audio=None, accumulate=not first_part)
             first_part = False
+
+    def _pack_dgrad(self, W) -> None:
+        if self.spectral or not self.dgrad_valid:
+            for bl, w_eff in zip(self.bwd, W["eff"][1:-1]):
+                bl.pack(w_eff)
+            self.dgrad_valid = True
 
     def backward_g(self, dy_audio: torch.Tensor, nfm: List[float]) -> None:
         """generator step: d (loss_gen + loss_fm) / d y_g_hat accumulated into dy_audio fp32 [B][T] (generated half
@@ -647,8 +748,7 @@ class _SubDiscTrainer:
         _lib.check(L.hg_loss_grad(lg.data_ptr(), lr.data_ptr(), ng * h, 2, 1.0, 2.0 / (ng * h), nfm[-1],
                                   G["dlogit"][nr:].data_ptr(), st))
         b0, bn, W = self.parts[-1] if self.spectral else (self.nreal, self.nb - self.nreal, self.parts[0][2])
-        for bl, w_eff, w_f in zip(self.bwd, W["eff"][1:-1], W["fwd"][1:-1]):
-            bl.pack(w_eff, w_f)
+        self._pack_dgrad(W)
         self._backward_part(L, G, W, self.nreal, self.nb - self.nreal, want_wgrad=False, fm=True,
                             dy_audio=dy_audio, accumulate=False, nfm=nfm)
 
@@ -753,6 +853,7 @@ class DiscriminatorTrainer:
         self.acc = torch.zeros(len(self.subs) * self.nslots, dtype=torch.float32, device=device)
         self.pooled: List[torch.Tensor] = []
         self._inv_counts: Dict[Tuple[int, int], torch.Tensor] = {}
+        self.lanes = _Lanes(len(self.subs), device)      # one stream per sub-discriminator: they are independent
 
     def forward(self, y: torch.Tensor, y_hat: torch.Tensor) -> None:
         """y, y_hat fp32 [B,1,T] (or [B,T]).  Runs every sub-discriminator on (y ++ y_hat) and accumulates the raw
@@ -770,10 +871,13 @@ class DiscriminatorTrainer:
             _lib.check(L.hg_avgpool_4_2_2_fwd(cur.data_ptr(), 2 * b, t, nxt.data_ptr(), _stream()), "hg_avgpool_4_2_2_fwd")
             self.pooled.append(nxt)
             cur = nxt
+        self.lanes.fork()
         for i, sd in enumerate(self.subs):
             inp = ycat if i < len(self.subs_p) else self.pooled[i - len(self.subs_p)]
-            sd.forward(inp, b)
-            sd.loss_terms(self.acc, i * self.nslots)
+            with self.lanes.lane(i):
+                sd.forward(inp, b)
+                sd.loss_terms(self.acc, i * self.nslots)
+        self.lanes.join()
 
     def losses(self) -> Dict[str, torch.Tensor]:
         """loss values from the accumulated sums (device tensors, no host sync)."""
@@ -798,20 +902,29 @@ class DiscriminatorTrainer:
         return out
 
     def backward_d(self) -> None:
-        for sd in self.subs:
-            sd.backward_d()
+        self.lanes.fork()
+        for i, sd in enumerate(self.subs):
+            with self.lanes.lane(i):
+                sd.backward_d()
+        self.lanes.join()
 
     def backward_g(self, dy_audio: torch.Tensor) -> None:
         """adds d(loss_gen + loss_fm)/d y_hat into dy_audio fp32 [B][T]."""
         L = _lib.lib()
         b = self.b
-        for sd in self.subs_p:
-            sd.backward_g(dy_audio, [2.0 / n for n in sd.numel_fmaps(b)])
         # MSD: scale i sees the (i times) pooled signal; chain the pooling backward from the coarsest scale up
         grads = [dy_audio] + [torch.zeros(b, p.shape[1], dtype=torch.float32, device=self.device)
                               for p in self.pooled[1:]]
+        self.lanes.fork()
+        # every lane ADDS into its audio-gradient buffer with atomics, so the period discriminators and scale 0 may
+        # share dy_audio
+        for i, sd in enumerate(self.subs_p):
+            with self.lanes.lane(i):
+                sd.backward_g(dy_audio, [2.0 / n for n in sd.numel_fmaps(b)])
         for i, sd in enumerate(self.subs_s):
-            sd.backward_g(grads[i], [2.0 / n for n in sd.numel_fmaps(b)])
+            with self.lanes.lane(len(self.subs_p) + i):
+                sd.backward_g(grads[i], [2.0 / n for n in sd.numel_fmaps(b)])
+        self.lanes.join()
         for i in reversed(range(1, len(grads))):
             _lib.check(L.hg_avgpool_4_2_2_bwd(grads[i].data_ptr(), b, grads[i - 1].shape[1], grads[i - 1].data_ptr(),
                                               _stream()), "hg_avgpool_4_2_2_bwd")
@@ -884,6 +997,8 @@ class TrainStep:
         self._allreduce(self.D.flat)
         if update:
             self.D.flat.adamw(self.lr, self.betas, grad_scale=1.0 / self.world)
+            for sd in self.D.subs:
+                sd.invalidate()
         # ---- generator step (through the updated discriminators)
         mel_g = self._mel(y_g2)
         n_mel = mel_g.numel()

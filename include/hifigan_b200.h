@@ -217,7 +217,7 @@ int hg_pack_dgrad_weight(const void* w_packed, int ktaps, int n, int c, void* ou
 /* hg_conv1d_dgrad — data gradient on the tcgen05 implicit-GEMM kernel (replaces convolution_backward's input
  * half for src/models.py:35-42,63-68,104,153-158,208-214):
  *   out[b,t,n] = ((sum_{j,c} dy[b, t + j*dil - pad_left, blk(n) + c] * w[j][n][c] + fm_coef * sgn(fm_g - fm_r))
- *                 * (mask_src[b,t,n] > 0 ? 1 : mask_slope) + res0 + res1) * scale
+ *                 * (mask_src[b,t,n] > 0 ? 1 : mask_slope) + res0 + res1 + res2) * scale
  * dy bf16 [B][t_dy_rows][c_dy_total], rows >= t_dy_valid read as zero; w_packed bf16 [ktaps][cout][c_dy_total/groups];
  * mask_src / fm_r / fm_g / res* / out bf16 [B][t_out_rows][cout] (optional except out).  mask_src is the layer
  * input as the forward stored it (leaky_relu'd: its sign is the sign of the pre-activation); fm_* add the
@@ -229,8 +229,8 @@ int hg_pack_dgrad_weight(const void* w_packed, int ktaps, int n, int c, void* ou
 int hg_conv1d_dgrad(const void* dy, const void* w_packed, int batch, int t_dy_valid, int t_dy_rows, int c_dy_total,
                     int t_out, int t_out_rows, int groups, int n_tile, int cout, int ktaps, int dilation, int pad_left,
                     const void* mask_src, float mask_slope, const void* fm_r, const void* fm_g, float fm_coef,
-                    const void* res0, const void* res1, float scale, void* out, int seq_pitch, int seq_valid,
-                    int seq_mul, int seq_div, void* stream);
+                    const void* res0, const void* res1, const void* res2, float scale, void* out, int seq_pitch,
+                    int seq_valid, int seq_mul, int seq_div, void* stream);
 
 /* hg_conv1d_wgrad — weight gradient as a tcgen05 implicit GEMM contracting over time (MN-major operands):
  *   dw[q][co][ci] (+)= sum_{b, t < t_out} dy[b,t,co] * xv[b, t + row(q), col(q) + blk(co) + ci]

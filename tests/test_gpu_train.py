@@ -113,7 +113,7 @@ def test_dgrad_stride1_vs_torch_autograd(H, case):
     res = torch.randn(b, t, cin, generator=gen).to(dev).bfloat16()
     out = torch.empty(b, t, cin, dtype=torch.bfloat16, device=dev)
     _lib.check(L.hg_conv1d_dgrad(dy.data_ptr(), wd.data_ptr(), b, t, t + 2, cout, t, t, 1, 0, cin, k, d,
-                                 (k - 1) * d - pad, x_act.data_ptr(), 0.1, 0, 0, 0.0, res.data_ptr(), 0, 0.5,
+                                 (k - 1) * d - pad, x_act.data_ptr(), 0.1, 0, 0, 0.0, res.data_ptr(), 0, 0, 0.5,
                                  out.data_ptr(), 0, 0, 1, 0, _st()), "hg_conv1d_dgrad")
     torch.cuda.synchronize()
     wr = wp.float().permute(1, 2, 0).contiguous()
