@@ -533,6 +533,98 @@ __global__ void pack_disc_dgrad_kernel(const float* __restrict__ w, const DiscPa
   }
 }
 
+// ---- spectral norm (torch.nn.utils.spectral_norm, dim 0, one power iteration, eps 1e-12; src/models.py:194) ----
+// K1: t[j] += sum_{i in row chunk} W[i][j] * u[i]            (W^T u, rows split over blockIdx.y, t zeroed before)
+__global__ void __launch_bounds__(256)
+sn_wtu_kernel(const float* __restrict__ w, const float* __restrict__ u, int rows, int cols, int rows_per_block,
+              float* __restrict__ t) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= cols) return;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float a = 0.f;
+  for (int i = r0; i < r1; ++i) a += w[static_cast<size_t>(i) * cols + j] * u[i];
+  atomicAdd(t + j, a);
+}
+// K2: v = normalize(t) (or the stored v when !iterate);  s[i] = sum_j W[i][j] * v[j]   (one warp per row)
+__global__ void __launch_bounds__(256)
+sn_wv_kernel(const float* __restrict__ w, const float* __restrict__ t, float* __restrict__ v, float* __restrict__ v_copy,
+             int rows, int cols, int iterate, float eps, float* __restrict__ s) {
+  __shared__ float red[32];
+  float inv = 1.f;
+  if (iterate) {
+    float ss = 0.f;
+    for (int j = threadIdx.x; j < cols; j += 256) ss += t[j] * t[j];
+    ss = block_sum(ss, red);
+    inv = 1.f / fmaxf(sqrtf(ss), eps);
+  }
+  const float* src = iterate ? t : v;
+  if (blockIdx.x == 0) {
+    for (int j = threadIdx.x; j < cols; j += 256) {
+      const float val = src[j] * inv;
+      if (v_copy) v_copy[j] = val;
+      if (iterate) v[j] = val;     // in-place buffer update, as torch does in train mode
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = blockIdx.x * 8 + warp; i < rows; i += gridDim.x * 8) {
+    const float* wr = w + static_cast<size_t>(i) * cols;
+    float a = 0.f;
+    for (int j = lane; j < cols; j += 32) a += wr[j] * src[j];
+    a = warp_sum(a) * inv;
+    if (lane == 0) s[i] = a;
+  }
+}
+// K3: u = normalize(s) (or the stored u), sigma = u . s, w_eff = W / sigma
+__global__ void __launch_bounds__(256)
+sn_scale_kernel(const float* __restrict__ w, const float* __restrict__ s, float* __restrict__ u,
+                float* __restrict__ u_copy, int rows, long long n, int iterate, float eps, float* __restrict__ w_eff,
+                float* __restrict__ sigma_out) {
+  __shared__ float red[32];
+  float sigma;
+  if (iterate) {
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < rows; i += 256) ss += s[i] * s[i];
+    ss = block_sum(ss, red);
+    const float inv = 1.f / fmaxf(sqrtf(ss), eps);
+    sigma = ss * inv;
+    if (blockIdx.x == 0)
+      for (int i = threadIdx.x; i < rows; i += 256) {
+        const float val = s[i] * inv;
+        u[i] = val;
+        if (u_copy) u_copy[i] = val;
+      }
+  } else {
+    float d = 0.f;
+    for (int i = threadIdx.x; i < rows; i += 256) d += u[i] * s[i];
+    sigma = block_sum(d, red);
+    if (blockIdx.x == 0 && u_copy)
+      for (int i = threadIdx.x; i < rows; i += 256) u_copy[i] = u[i];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && sigma_out) *sigma_out = sigma;
+  const float inv_sigma = 1.f / sigma;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x) w_eff[i] = w[i] * inv_sigma;
+}
+// backward: dot = <dw_eff, w_eff>;  dW[i][j] (+)= (dw_eff[i][j] - dot * u[i] * v[j]) / sigma
+__global__ void __launch_bounds__(256)
+sn_bwd_dot_kernel(const float* __restrict__ d, const float* __restrict__ w_eff, long long n, float* __restrict__ dot) {
+  __shared__ float red[32];
+  float a = 0.f;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x) a += d[i] * w_eff[i];
+  a = block_sum(a, red);
+  if (threadIdx.x == 0) atomicAdd(dot, a);
+}
+__global__ void __launch_bounds__(256)
+sn_bwd_apply_kernel(const float* __restrict__ d, const float* __restrict__ u, const float* __restrict__ v,
+                    const float* __restrict__ sigma, const float* __restrict__ dot, int cols, long long n,
+                    int accumulate, float* __restrict__ out) {
+  const float inv = 1.f / *sigma, dt = *dot;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x) {
+    const int r = static_cast<int>(i / cols), c = static_cast<int>(i - static_cast<long long>(r) * cols);
+    const float val = (d[i] - dt * u[r] * v[c]) * inv;
+    out[i] = accumulate ? out[i] + val : val;
+  }
+}
+
 int blocks_for(long long n, int per = 256) {
   long long b = (n + per - 1) / per;
   if (b > 148 * 16) b = 148 * 16;
@@ -753,5 +845,46 @@ extern "C" int hg_pack_disc_weight(const float* w_eff, int cout, int cin, int gr
     HG_CHECK_CUDA(cudaGetLastError());
     count();
   }
+  return HG_OK;
+}
+
+extern "C" int hg_spectral_norm_fwd(const float* w, float* u, float* v, int rows, int cols, int iterate, float* w_eff,
+                                    float* sigma_out, float* u_copy, float* v_copy, float* ws, void* stream) {
+  HG_REQUIRE(w && u && v && w_eff && ws && rows > 0 && cols > 0, "hg_spectral_norm_fwd: bad arguments");
+  float* t = ws;            // [cols]
+  float* sv = ws + cols;    // [rows]
+  const float eps = 1e-12f;
+  if (iterate) {
+    HG_CHECK_CUDA(cudaMemsetAsync(t, 0, sizeof(float) * cols, S(stream)));
+    const int rpb = 64;
+    dim3 g1((cols + 255) / 256, (rows + rpb - 1) / rpb);
+    sn_wtu_kernel<<<g1, 256, 0, S(stream)>>>(w, u, rows, cols, rpb, t);
+    HG_CHECK_CUDA(cudaGetLastError());
+    count();
+  }
+  const int g2 = (rows + 7) / 8 < 592 ? (rows + 7) / 8 : 592;
+  sn_wv_kernel<<<g2, 256, 0, S(stream)>>>(w, t, v, v_copy, rows, cols, iterate, eps, sv);
+  HG_CHECK_CUDA(cudaGetLastError());
+  count();
+  const long long n = static_cast<long long>(rows) * cols;
+  sn_scale_kernel<<<blocks_for(n, 1024), 256, 0, S(stream)>>>(w, sv, u, u_copy, rows, n, iterate, eps, w_eff, sigma_out);
+  HG_CHECK_CUDA(cudaGetLastError());
+  count();
+  return HG_OK;
+}
+
+extern "C" int hg_spectral_norm_bwd(const float* dw_eff, const float* w_eff, const float* u, const float* v,
+                                    const float* sigma, int rows, int cols, int accumulate, float* dw_orig, float* ws,
+                                    void* stream) {
+  HG_REQUIRE(dw_eff && w_eff && u && v && sigma && dw_orig && ws && rows > 0 && cols > 0,
+             "hg_spectral_norm_bwd: bad arguments");
+  const long long n = static_cast<long long>(rows) * cols;
+  HG_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(float), S(stream)));
+  sn_bwd_dot_kernel<<<blocks_for(n, 2048), 256, 0, S(stream)>>>(dw_eff, w_eff, n, ws);
+  HG_CHECK_CUDA(cudaGetLastError());
+  count();
+  sn_bwd_apply_kernel<<<blocks_for(n, 1024), 256, 0, S(stream)>>>(dw_eff, u, v, sigma, ws, cols, n, accumulate, dw_orig);
+  HG_CHECK_CUDA(cudaGetLastError());
+  count();
   return HG_OK;
 }

@@ -558,10 +558,20 @@ class _SubDiscTrainer:
         for li, m in enumerate(self.mods):
             eff = bufs["eff"][li]
             if hasattr(m, "weight_orig"):
-                eff.view(-1).copy_(_effective_weight(m).reshape(-1))
-                # u, v as this call left them: the backward of THIS call's weights needs them (the next call moves on)
-                u, v = m.weight_u.clone(), m.weight_v.clone()
-                ws["sn"].append((u, v, torch.dot(u, torch.mv(m.weight_orig.detach().flatten(1), v))))
+                wo = m.weight_orig
+                rows, cols = wo.shape[0], wo.numel() // wo.shape[0]
+                snb = bufs.setdefault("sn", {}).get(li)
+                if snb is None:
+                    f32 = lambda n: torch.empty(n, dtype=torch.float32, device=self.device)
+                    snb = (f32(rows), f32(cols), f32(1), f32(rows + cols + 4))     # u, v, sigma of this call; workspace
+                    bufs["sn"][li] = snb
+                # one power iteration per call in train mode, u / v buffers updated in place (hg_spectral_norm_fwd);
+                # the copies are what the backward of THIS call's weights needs (the next call moves u, v on)
+                _lib.check(L.hg_spectral_norm_fwd(wo.data_ptr(), m.weight_u.data_ptr(), m.weight_v.data_ptr(), rows,
+                                                  cols, 1 if m.training else 0, eff.data_ptr(), snb[2].data_ptr(),
+                                                  snb[0].data_ptr(), snb[1].data_ptr(), snb[3].data_ptr(), st),
+                           "hg_spectral_norm_fwd")
+                ws["sn"].append(snb)
             else:
                 g, v = _g_v(m)
                 _lib.check(L.hg_fold_weight_norm(v.data_ptr(), 0 if g is None else g.data_ptr(), v.shape[0],
@@ -824,15 +834,11 @@ class _SubDiscTrainer:
     def _route(self, L, m: nn.Module, dw: torch.Tensor, d0: int, rest: int, W, li: int, accumulate: bool) -> None:
         if hasattr(m, "weight_orig"):
             # spectral norm: w = W / sigma with sigma = u^T W v (u, v constants): dW = (dw - <dw, w> u v^T) / sigma
-            w_eff = W["eff"][li].reshape(d0, rest)
-            wo = m.weight_orig
-            u, v, sigma = W["sn"][li]
-            d = dw[: d0 * rest].view(d0, rest)
-            gr = (d - (d * w_eff).sum() * torch.outer(u, v)) / sigma
-            if accumulate:
-                wo.grad.add_(gr.view(wo.shape))
-            else:
-                wo.grad.copy_(gr.view(wo.shape))
+            u, v, sigma, snws = W["sn"][li]
+            _lib.check(L.hg_spectral_norm_bwd(dw.data_ptr(), W["eff"][li].data_ptr(), u.data_ptr(), v.data_ptr(),
+                                              sigma.data_ptr(), d0, rest, 1 if accumulate else 0,
+                                              m.weight_orig.grad.data_ptr(), snws.data_ptr(), _stream()),
+                       "hg_spectral_norm_bwd")
         else:
             _route_weight_grad(L, m, dw, d0, rest, accumulate)
 

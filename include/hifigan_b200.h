@@ -266,6 +266,18 @@ int hg_fold_weight_norm(const float* v, const float* g, int dim0, int rest, floa
 int hg_pack_disc_weight(const float* w_eff, int cout, int cin, int groups, int merge, int k, int stride, int pad,
                         void* w_fwd, void* w_dgrad, void* stream);
 
+/* Spectral norm (torch.nn.utils.spectral_norm as used by MultiScaleDiscriminator's first scale, src/models.py:194,
+ * 222; dim 0, eps 1e-12).  hg_spectral_norm_fwd: w fp32 [rows][cols]; with iterate != 0 (train mode) one power
+ * iteration v <- normalize(W^T u), u <- normalize(W v) updates the u / v buffers IN PLACE like torch; then
+ * sigma = u . (W v), w_eff = W / sigma.  u_copy / v_copy (optional) receive the vectors this call used (the next
+ * call moves them on; the backward of THIS call needs them), sigma_out fp32 [1] the scalar.  ws: >= rows + cols
+ * floats.  hg_spectral_norm_bwd: dw_orig (+)= (dw_eff - <dw_eff, w_eff> u v^T) / sigma (u, v constants of sigma, as
+ * torch computes them under no_grad).  ws: >= 1 float. */
+int hg_spectral_norm_fwd(const float* w, float* u, float* v, int rows, int cols, int iterate, float* w_eff,
+                         float* sigma_out, float* u_copy, float* v_copy, float* ws, void* stream);
+int hg_spectral_norm_bwd(const float* dw_eff, const float* w_eff, const float* u, const float* v, const float* sigma,
+                         int rows, int cols, int accumulate, float* dw_orig, float* ws, void* stream);
+
 /* hg_colsum_bf16 — bias gradient: out[c] (+)= sum_{b, t < t_valid} x[b][t][c]; x bf16 [B][t_rows][C]. */
 int hg_colsum_bf16(const void* x, int batch, int t_valid, int t_rows, int c, int accumulate, float* out, void* stream);
 

@@ -117,10 +117,37 @@ def profile(b):
     torch.cuda.profiler.stop()
 
 
+def trace(b):
+    """torch.profiler (CUPTI) kernel timeline of two graph replays -> gpurun_out/train_trace.json (kernels only)"""
+    from torch.profiler import ProfilerActivity, profile as tprofile
+    h, ts, _ = build()
+    from oracle import hifigan_oracle as O
+    ya = O.synthetic_audio(b, 8192, seed=3).cuda()
+    x = H.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, 8000)
+    y_mel = H.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, None)
+    y = ya.unsqueeze(1)
+    for _ in range(4):
+        ts.step_graphed(x, y, y_mel)
+    torch.cuda.synchronize()
+    with tprofile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        for _ in range(2):
+            ts.step_graphed(x, y, y_mel)
+        torch.cuda.synchronize()
+    ev = []
+    for e in prof.events():
+        if e.device_type == torch.autograd.DeviceType.CUDA:
+            ev.append({"name": e.name[:80], "start": e.time_range.start, "dur": e.time_range.elapsed_us()})
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    prof.export_chrome_trace(os.path.join(ROOT, "gpurun_out", "train_trace_full.json"))
+    print("events", len(ev))
+
+
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "parity"
     if mode == "parity":
         parity()
+    elif mode == "trace":
+        trace(int(sys.argv[2]) if len(sys.argv) > 2 else 16)
     elif mode == "profile":
         profile(int(sys.argv[2]) if len(sys.argv) > 2 else 16)
     else:

@@ -421,3 +421,42 @@ def test_graphed_step_matches_eager(H):
         res.append({k: out[k].item() for k in LOSS_KEYS})
     for k in LOSS_KEYS:
         assert abs(res[0][k] - res[1][k]) <= 1e-3 * abs(res[0][k]) + 1e-5, (k, res[0][k], res[1][k])
+
+
+def test_spectral_norm_kernels_vs_torch(H):
+    """hg_spectral_norm_fwd / _bwd against torch.nn.utils.spectral_norm itself (train-mode forward = one power
+    iteration updating u / v in place; autograd through W / sigma with u, v constant)."""
+    from hifigan_b200 import _lib
+    L = _lib.lib()
+    dev = torch.device("cuda")
+    for shape in [(128, 1, 15), (1024, 64, 41), (1, 1024, 3), (256, 8, 41)]:
+        torch.manual_seed(sum(shape))
+        m = torch.nn.utils.spectral_norm(torch.nn.Conv1d(shape[1], shape[0], shape[2])).to(dev).train()
+        w = m.weight_orig.detach().clone()
+        u, v = m.weight_u.detach().clone(), m.weight_v.detach().clone()
+        rows, cols = shape[0], shape[1] * shape[2]
+        for it in range(2):                       # two consecutive calls: the state must carry over
+            x = torch.randn(2, shape[1], 50, device=dev)
+            y = m(x)                              # runs the power iteration, builds m.weight
+            d = torch.randn_like(m.weight)
+            m.weight_orig.grad = None
+            (m.weight * d).sum().backward()
+            eff = torch.empty(rows, cols, device=dev)
+            sig, uc, vc = torch.empty(1, device=dev), torch.empty(rows, device=dev), torch.empty(cols, device=dev)
+            ws = torch.empty(rows + cols + 4, device=dev)
+            _lib.check(L.hg_spectral_norm_fwd(w.data_ptr(), u.data_ptr(), v.data_ptr(), rows, cols, 1, eff.data_ptr(),
+                                              sig.data_ptr(), uc.data_ptr(), vc.data_ptr(), ws.data_ptr(), _st()))
+            assert torch.allclose(eff.view_as(m.weight), m.weight.detach(), rtol=1e-4, atol=1e-6)
+            assert torch.allclose(u, m.weight_u, rtol=1e-4, atol=1e-6) and torch.allclose(v, m.weight_v, rtol=1e-4, atol=1e-6)
+            out = torch.full((rows, cols), 1.0, device=dev)
+            _lib.check(L.hg_spectral_norm_bwd(d.contiguous().data_ptr(), eff.data_ptr(), uc.data_ptr(), vc.data_ptr(),
+                                              sig.data_ptr(), rows, cols, 1, out.data_ptr(), ws.data_ptr(), _st()))
+            ref = m.weight_orig.grad.reshape(rows, cols) + 1.0
+            assert torch.allclose(out, ref, rtol=1e-3, atol=1e-5), (out - ref).abs().max()
+        # eval mode: stored u, v, no update
+        u0 = u.clone()
+        _lib.check(L.hg_spectral_norm_fwd(w.data_ptr(), u.data_ptr(), v.data_ptr(), rows, cols, 0, eff.data_ptr(),
+                                          sig.data_ptr(), 0, 0, ws.data_ptr(), _st()))
+        m.eval()
+        m(x)
+        assert torch.equal(u, u0) and torch.allclose(eff.view_as(m.weight), m.weight.detach(), rtol=1e-4, atol=1e-6)
