@@ -10,6 +10,7 @@
 #include "hg_common.cuh"
 
 #include <atomic>
+#include <cstdlib>
 
 #include "../../include/hifigan_b200.h"
 
@@ -230,31 +231,38 @@ disc_last_bwd_dw_kernel(const __nv_bfloat16* __restrict__ x, const float* __rest
 constexpr int kFirstTile = 128;
 constexpr int kFirstChunk = 1024;
 constexpr int kFirstK = 16;
+constexpr int kXPitch = 20;   // floats per staged input row (16-byte multiple)
 
 __global__ void __launch_bounds__(256)
 disc_first_bwd_kernel(const float* __restrict__ y, const float* __restrict__ w, const __nv_bfloat16* __restrict__ dpre,
                       int t, int period, int h_in, int h_out, int h_rows, int k, int stride, int pad, int cout,
-                      float* __restrict__ dw, float* __restrict__ db, float* __restrict__ dy) {
+                      float* __restrict__ dw, float* __restrict__ db, float* __restrict__ dy, int dbg) {
   extern __shared__ __align__(16) uint8_t smb[];
   const int pitch = cout + 2;                                   // odd word pitch: column reads are conflict-free
-  float* ws = reinterpret_cast<float*>(smb);                    // [k][cout]
-  float* xin = ws + k * cout;                                   // [tile][kFirstK + 1]  (last column = 1: bias)
-  int* xidx = reinterpret_cast<int*>(xin + kFirstTile * (kFirstK + 1));   // [tile][kFirstK]
+  float* ws = reinterpret_cast<float*>(smb);                    // [kFirstK][cout], zero for taps >= k
+  float* xin = ws + kFirstK * cout;                             // [tile][kXPitch]: taps, then 1 (bias) at column k
+  int* xidx = reinterpret_cast<int*>(xin + kFirstTile * kXPitch);   // [tile][kFirstK]
   float* gsm = reinterpret_cast<float*>(xidx + kFirstTile * kFirstK);          // [2][tile][kFirstK] tap sums
   __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(gsm + 2 * kFirstTile * kFirstK);   // [tile][pitch]
   const int tid = threadIdx.x;
-  for (int i = tid; i < k * cout; i += 256) {
-    const int j = i / cout, co = i % cout;
-    ws[i] = w[co * k + j];
+  if (dy) {
+    for (int i = tid; i < kFirstK * cout; i += 256) {
+      const int j = i / cout, co = i % cout;
+      ws[i] = j < k ? w[co * k + j] : 0.f;
+    }
   }
   const int seq = blockIdx.y;
   const int b = seq / period, wcol = seq % period;
   const int p0 = blockIdx.x * kFirstChunk;
   const int p1 = min(h_out, p0 + kFirstChunk);
-  const int n_out = (k + 1) * cout;                             // weight + bias gradient entries
-  float acc[8];
+  // weight-gradient register tile: thread = (4 channels, 4 columns of [taps | bias], row group)
+  const int cgs = cout / 4;
+  const int cg = tid % cgs, jg = (tid / cgs) & 3, rh = tid / cout, rgroups = 256 / cout;
+  float acc[4][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
   for (int q0 = p0; q0 < p1; q0 += kFirstTile) {
     __syncthreads();
     // stage dpre rows (zero past the end) and the input samples of each position
@@ -266,13 +274,13 @@ disc_first_bwd_kernel(const float* __restrict__ y, const float* __restrict__ w, 
       if (ho < p1) val = reinterpret_cast<const uint32_t*>(dpre + (static_cast<size_t>(seq) * h_rows + ho) * cout)[v];
       reinterpret_cast<uint32_t*>(dp + r * pitch)[v] = val;
     }
-    for (int i = tid; i < kFirstTile * (kFirstK + 1); i += 256) {
-      const int r = i / (kFirstK + 1), j = i % (kFirstK + 1);
+    for (int i = tid; i < kFirstTile * kFirstK; i += 256) {
+      const int r = i / kFirstK, j = i % kFirstK;
       const int ho = q0 + r;
       float v = 0.f;
       int idx = -1;
-      if (j == kFirstK) {
-        v = 1.f;
+      if (j == k) {
+        v = ho < p1 ? 1.f : 0.f;
       } else if (j < k && ho < p1) {
         const int hh = ho * stride + j - pad;
         if (hh >= 0 && hh < h_in) {
@@ -282,27 +290,22 @@ disc_first_bwd_kernel(const float* __restrict__ y, const float* __restrict__ w, 
           v = y[static_cast<size_t>(b) * t + ii];
         }
       }
-      xin[i] = v;
-      if (j < kFirstK) xidx[r * kFirstK + j] = idx;
+      xin[r * kXPitch + j] = v;
+      xidx[i] = idx;
     }
     __syncthreads();
-    if (dw) {
-      // 8 independent accumulators per thread, row loop outside: the shared-memory loads of consecutive rows
-      // pipeline instead of forming one dependent load -> FMA chain per output
-      int dco[8], dcol[8];
+    if (dw && rh < rgroups) {
+      // [4 channels] x [4 columns] outer products per staged row: 6 shared-memory loads feed 16 FMAs
+      for (int r = rh; r < kFirstTile; r += rgroups) {
+        const uint32_t* dr = reinterpret_cast<const uint32_t*>(dp + r * pitch) + cg * 2;
+        const float2 d01 = hg::unpack_bf16x2(dr[0]), d23 = hg::unpack_bf16x2(dr[1]);
+        const float4 xv = *reinterpret_cast<const float4*>(xin + r * kXPitch + jg * 4);
+        const float dv[4] = {d01.x, d01.y, d23.x, d23.y};
+        const float xc[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int o = min(tid + 256 * i, n_out - 1);
-        const int j = o / cout;
-        dco[i] = o % cout;
-        dcol[i] = j == k ? kFirstK : j;
-      }
-#pragma unroll 4
-      for (int r = 0; r < kFirstTile; ++r) {
-        const __nv_bfloat16* dr = dp + r * pitch;
-        const float* xr = xin + r * (kFirstK + 1);
+        for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += __bfloat162float(dr[dco[i]]) * xr[dcol[i]];
+          for (int c = 0; c < 4; ++c) acc[a][c] += dv[a] * xc[c];
       }
     }
     if (dy) {
@@ -312,20 +315,22 @@ disc_first_bwd_kernel(const float* __restrict__ y, const float* __restrict__ w, 
       float gy[kFirstK];
 #pragma unroll
       for (int j = 0; j < kFirstK; ++j) gy[j] = 0.f;
-      if (q0 + r < p1) {
+      if (q0 + r < p1 && !(dbg & 1)) {
         const int c0 = half * (cout / 2), c1 = c0 + cout / 2;
+        const __nv_bfloat16* drow = dp + r * pitch;
+#pragma unroll 2
         for (int co = c0; co < c1; ++co) {
-          const float d = __bfloat162float(dp[r * pitch + co]);
+          const float d = __bfloat162float(drow[co]);
+          const float* wc = ws + co;
 #pragma unroll
-          for (int j = 0; j < kFirstK; ++j)
-            if (j < k) gy[j] += d * ws[j * cout + co];
+          for (int j = 0; j < kFirstK; ++j) gy[j] += d * wc[j * cout];   // taps >= k hold zero weights: no predicate
         }
       }
 #pragma unroll
       for (int j = 0; j < kFirstK; ++j) gsm[(half * kFirstTile + r) * kFirstK + j] = gy[j];
       __syncthreads();
       const int n_in = (kFirstTile - 1) * stride + k;
-      for (int e = tid; e < n_in; e += 256) {
+      for (int e = tid; e < n_in && !(dbg & 2); e += 256) {
         const int hh = q0 * stride - pad + e;
         if (hh < 0 || hh >= h_in) continue;
         float a = 0.f;
@@ -342,14 +347,15 @@ disc_first_bwd_kernel(const float* __restrict__ y, const float* __restrict__ w, 
       }
     }
   }
-  if (dw) {
+  if (dw && rh < rgroups) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int o = tid + 256 * i;
-      if (o < n_out) {
-        const int j = o / cout, co = o % cout;
-        if (j == k) atomicAdd(db + co, acc[i]);
-        else atomicAdd(dw + co * k + j, acc[i]);
+    for (int a = 0; a < 4; ++a) {
+      const int co = cg * 4 + a;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int j = jg * 4 + c;
+        if (j < k) atomicAdd(dw + co * k + j, acc[a][c]);
+        else if (j == k) atomicAdd(db + co, acc[a][c]);
       }
     }
   }
@@ -712,13 +718,13 @@ extern "C" int hg_disc_first_conv_bwd(const float* y, const float* w, const void
   HG_REQUIRE(!dw || db, "hg_disc_first_conv_bwd: dw needs db");
   HG_REQUIRE(batch > 0 && t > 1 && period >= 1 && k >= 1 && k <= kFirstK && stride >= 1 && cout > 0 && cout % 2 == 0,
              "hg_disc_first_conv_bwd: bad shape");
-  HG_REQUIRE((k + 1) * cout <= 8 * 256, "hg_disc_first_conv_bwd: (k + 1) * cout = %d exceeds 2048", (k + 1) * cout);
+  HG_REQUIRE(cout % 4 == 0 && 256 % cout == 0 && cout >= 4, "hg_disc_first_conv_bwd: cout must divide 256 (got %d)", cout);
   const int t_pad = (t + period - 1) / period * period;
   const int h_in = t_pad / period;
   const int h_out = (h_in + 2 * pad - k) / stride + 1;
   HG_REQUIRE(h_out > 0 && h_rows >= h_out && batch * period <= 65535, "hg_disc_first_conv_bwd: bad geometry");
   dim3 grid((h_out + kFirstChunk - 1) / kFirstChunk, batch * period);
-  const size_t smem = static_cast<size_t>(k) * cout * 4 + kFirstTile * (kFirstK + 1) * 4 + kFirstTile * kFirstK * 4 +
+  const size_t smem = static_cast<size_t>(kFirstK) * cout * 4 + kFirstTile * kXPitch * 4 + kFirstTile * kFirstK * 4 +
                       2 * kFirstTile * kFirstK * 4 + static_cast<size_t>(kFirstTile) * (cout + 2) * 2;
   static bool configured = false;
   if (!configured) {
@@ -727,7 +733,8 @@ extern "C" int hg_disc_first_conv_bwd(const float* y, const float* w, const void
   }
   HG_REQUIRE(smem <= 96 * 1024, "hg_disc_first_conv_bwd: tile does not fit shared memory");
   disc_first_bwd_kernel<<<grid, 256, smem, S(stream)>>>(y, w, static_cast<const __nv_bfloat16*>(dpre), t, period, h_in,
-                                                        h_out, h_rows, k, stride, pad, cout, dw, db, dy);
+                                                        h_out, h_rows, k, stride, pad, cout, dw, db, dy,
+                                                        getenv("HG_FIRST_DBG") ? atoi(getenv("HG_FIRST_DBG")) : 0);
   HG_CHECK_CUDA(cudaGetLastError());
   count();
   return HG_OK;

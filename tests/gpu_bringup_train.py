@@ -117,6 +117,33 @@ def profile(b):
     torch.cuda.profiler.stop()
 
 
+def firstbwd():
+    """micro-benchmark of hg_disc_first_conv_bwd in its two modes at the MSD scale-1 shape"""
+    L = _lib.lib()
+    dev = torch.device("cuda")
+    for (b, t, period, k, s, pad, cout) in [(16, 8192, 1, 15, 1, 7, 128), (32, 8192, 1, 15, 1, 7, 128), (16, 8192, 2, 5, 3, 2, 32)]:
+        y = torch.randn(b, t, device=dev)
+        w = torch.randn(cout, k, device=dev)
+        h_in = (t + period - 1) // period
+        h_out = (h_in + 2 * pad - k) // s + 1
+        dpre = torch.randn(b * period, h_out, cout, device=dev).bfloat16()
+        dw, db, dy = torch.zeros(cout, k, device=dev), torch.zeros(cout, device=dev), torch.zeros(b, t, device=dev)
+        st = torch.cuda.current_stream().cuda_stream
+        for mode in ("dw", "dy"):
+            args = (dw.data_ptr(), db.data_ptr(), 0) if mode == "dw" else (0, 0, dy.data_ptr())
+            for _ in range(3):
+                _lib.check(L.hg_disc_first_conv_bwd(y.data_ptr(), w.data_ptr(), dpre.data_ptr(), b, t, period, k, s, pad,
+                                                    cout, h_out, *args, st))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                _lib.check(L.hg_disc_first_conv_bwd(y.data_ptr(), w.data_ptr(), dpre.data_ptr(), b, t, period, k, s, pad,
+                                                    cout, h_out, *args, st))
+            e1.record()
+            torch.cuda.synchronize()
+            print(f"first_bwd b={b} period={period} cout={cout} mode={mode}: {e0.elapsed_time(e1) / 10 * 1e3:.1f} us")
+
+
 def trace(b):
     """torch.profiler (CUPTI) kernel timeline of two graph replays -> gpurun_out/train_trace.json (kernels only)"""
     from torch.profiler import ProfilerActivity, profile as tprofile
@@ -146,6 +173,8 @@ if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "parity"
     if mode == "parity":
         parity()
+    elif mode == "firstbwd":
+        firstbwd()
     elif mode == "trace":
         trace(int(sys.argv[2]) if len(sys.argv) > 2 else 16)
     elif mode == "profile":
