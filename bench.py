@@ -213,7 +213,8 @@ def measure_train(dev, rank, world, steps: int, warmup: int, batch: int = TRAIN[
     y_mel = H.mel_spectrogram(y, h.n_fft, h.num_mels, h.sampling_rate, h.hop_size, h.win_size, h.fmin, h.fmax_for_loss)
     host_x, host_ymel = x.cpu().pin_memory(), y_mel.cpu().pin_memory()
     y3 = y.unsqueeze(1)
-    fn = ts.step if (world > 1 or os.environ.get("HG_TRAIN_EAGER")) else ts.step_graphed
+    # the whole step (the NCCL all-reduces included when N > 1) replays as one CUDA graph; eager on request
+    fn = ts.step if os.environ.get("HG_TRAIN_EAGER") else ts.step_graphed
 
     def barrier():
         if _dist_on():

@@ -1056,7 +1056,8 @@ class TrainStep:
             torch.cuda.synchronize()
             try:
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                # thread_local: the NCCL watchdog thread of a data-parallel run may touch the CUDA API meanwhile
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
                     out = self.step(sx, sy, sm)
                 entry = (g, sx, sy, sm, out)
             except Exception as e:  # noqa: BLE001
