@@ -97,6 +97,10 @@ _SIGNATURES = {
     "hg_conv1d_wgrad": (c_int, [c_void_p, c_void_p] + [c_int] * 11 + [c_void_p, c_int, c_void_p]),
     "hg_unpack_wgrad_conv": (c_int, [c_void_p] + [c_int] * 7 + [POINTER(c_int), c_void_p, c_void_p]),
     "hg_unpack_wgrad_convtr": (c_int, [c_void_p] + [c_int] * 7 + [c_void_p, c_void_p]),
+    "hg_wgrad_finish_conv": (c_int, [c_void_p] + [c_int] * 7 + [POINTER(c_int), c_void_p, c_void_p, c_int, c_void_p,
+                                                                  c_void_p, c_void_p]),
+    "hg_wgrad_finish_convtr": (c_int, [c_void_p] + [c_int] * 7 + [c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                                                    c_void_p]),
     "hg_weight_norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "hg_fold_weight_norm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "hg_pack_disc_weight": (c_int, [c_void_p] + [c_int] * 7 + [c_void_p, c_void_p, c_void_p]),

@@ -437,6 +437,51 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ p, const UnpackArg
   }
 }
 
+__device__ __forceinline__ float packed_dw(const float* __restrict__ p, const UnpackArgs& a, int i0, int i1, int j) {
+  if (a.mode == 0) {
+    const int slot = (i0 / a.cout_g) % a.merge;
+    return p[(static_cast<size_t>(a.pos[j]) * a.rows_p + i0) * a.cin_tile + slot * a.d1 + i1];
+  }
+  const int ph = (((j - a.padding) % a.stride) + a.stride) % a.stride;
+  const int s = (ph + a.padding - j) / a.stride - a.shift_min;
+  return p[(static_cast<size_t>(s) * a.rows_p + ph * a.cout_p + i1) * a.cin_tile + i0];
+}
+
+// packed weight gradient -> parameter gradients in ONE pass (unpack + weight_norm backward): one block per dim-0
+// index.  g == NULL: plain weight, dv (+)= dw.  Results are ADDED to dv / dg when accumulate != 0.
+__global__ void __launch_bounds__(256)
+wgrad_finish_kernel(const float* __restrict__ p, const UnpackArgs a, const float* __restrict__ v,
+                    const float* __restrict__ g, int accumulate, float* __restrict__ dv, float* __restrict__ dg) {
+  __shared__ float red[32];
+  const int r = blockIdx.x;
+  const int rest = a.d1 * a.k;
+  const float* vr = v + static_cast<size_t>(r) * rest;
+  float* o = dv + static_cast<size_t>(r) * rest;
+  if (!g) {
+    for (int i = threadIdx.x; i < rest; i += blockDim.x) {
+      const float d = packed_dw(p, a, r, i / a.k, i % a.k);
+      o[i] = accumulate ? o[i] + d : d;
+    }
+    return;
+  }
+  float ss = 0.f, dot = 0.f;
+  for (int i = threadIdx.x; i < rest; i += blockDim.x) {
+    const float vv = vr[i];
+    ss += vv * vv;
+    dot += vv * packed_dw(p, a, r, i / a.k, i % a.k);
+  }
+  ss = block_sum(ss, red);
+  dot = block_sum(dot, red);
+  const float nrm = sqrtf(ss);
+  const float inv = nrm > 0.f ? 1.f / nrm : 0.f;
+  const float gg = g[r];
+  for (int i = threadIdx.x; i < rest; i += blockDim.x) {
+    const float val = gg * inv * (packed_dw(p, a, r, i / a.k, i % a.k) - vr[i] * dot * inv * inv);
+    o[i] = accumulate ? o[i] + val : val;
+  }
+  if (threadIdx.x == 0) dg[r] = accumulate ? dg[r] + dot * inv : dot * inv;
+}
+
 // weight_norm backward (dim 0): w = g * v / ||v||;  dg = <dw, v> / ||v||;  dv = g/||v|| * (dw - v * <dw,v>/||v||^2)
 // one block per dim-0 index; dv, dg are ACCUMULATED into (+=) when accumulate != 0
 __global__ void __launch_bounds__(256)
@@ -891,6 +936,40 @@ extern "C" int hg_spectral_norm_bwd(const float* dw_eff, const float* w_eff, con
   HG_CHECK_CUDA(cudaGetLastError());
   count();
   sn_bwd_apply_kernel<<<blocks_for(n, 1024), 256, 0, S(stream)>>>(dw_eff, u, v, sigma, ws, cols, n, accumulate, dw_orig);
+  HG_CHECK_CUDA(cudaGetLastError());
+  count();
+  return HG_OK;
+}
+
+// hg_wgrad_finish_*: hg_unpack_wgrad_* + hg_weight_norm_bwd fused (one launch per layer).  v, g: the module's
+// weight_v / weight_g (g == NULL: plain `weight`, dv receives the unpacked gradient).
+extern "C" int hg_wgrad_finish_conv(const float* dw_packed, int cout, int cin_g, int k, int rows_p, int cin_tile,
+                                    int cout_g, int merge, const int* host_tap_order, const float* v, const float* g,
+                                    int accumulate, float* dv, float* dg, void* stream) {
+  HG_REQUIRE(dw_packed && v && dv && (!g || dg) && k > 0 && k <= 64 && cout > 0 && cin_g > 0 && merge >= 1 && cout_g >= 1,
+             "hg_wgrad_finish_conv: bad arguments");
+  UnpackArgs a{};
+  a.mode = 0; a.d0 = cout; a.d1 = cin_g; a.k = k; a.rows_p = rows_p; a.cin_tile = cin_tile;
+  a.cout_g = cout_g; a.merge = merge;
+  for (int q = 0; q < k; ++q) a.pos[host_tap_order ? host_tap_order[q] : q] = q;
+  wgrad_finish_kernel<<<cout, 256, 0, S(stream)>>>(dw_packed, a, v, g, accumulate, dv, dg);
+  HG_CHECK_CUDA(cudaGetLastError());
+  count();
+  return HG_OK;
+}
+
+extern "C" int hg_wgrad_finish_convtr(const float* dw_packed, int cin, int cout, int k, int stride, int padding,
+                                      int cin_p, int cout_p, const float* v, const float* g, int accumulate,
+                                      float* dv, float* dg, void* stream) {
+  HG_REQUIRE(dw_packed && v && dv && (!g || dg) && k > 0 && cin > 0 && cout > 0 && stride > 0,
+             "hg_wgrad_finish_convtr: bad arguments");
+  int nshift = 0, smin = 0;
+  int rc = hg_convtr1d_geometry(k, stride, padding, &nshift, &smin);
+  if (rc) return rc;
+  UnpackArgs a{};
+  a.mode = 1; a.d0 = cin; a.d1 = cout; a.k = k; a.rows_p = stride * cout_p; a.cin_tile = cin_p;
+  a.stride = stride; a.padding = padding; a.shift_min = smin; a.cout_p = cout_p;
+  wgrad_finish_kernel<<<cin, 256, 0, S(stream)>>>(dw_packed, a, v, g, accumulate, dv, dg);
   HG_CHECK_CUDA(cudaGetLastError());
   count();
   return HG_OK;

@@ -144,16 +144,19 @@ def shard_batch(global_batch: int, rank: int, world: int) -> Tuple[int, int]:
 
 # ------------------------------------------------------------------------------------------------ generator
 class _GenLayerGrad:
-    """Backward-side state of one packed Generator conv: dgrad filter bank, packed fp32 weight gradient, bias
-    gradient (padded), and the route back to the weight_norm parameters."""
+    """Backward-side state of one packed Generator conv: dgrad filter bank, packed fp32 weight gradient (a view
+    into the trainer's flat buffer, zeroed once per backward), and the route back to the weight_norm parameters.
+    Every kernel here ACCUMULATES: GeneratorTrainer.backward zeroes the flat packed-gradient buffer and the flat
+    parameter-gradient buffer first, so no per-layer memset / copy nodes are needed."""
 
     def __init__(self, pc: _PackedConv, device, need_dgrad: bool = True):
         self.pc = pc
         rows = pc.w.shape[1]
         self.rows = rows
         self.wd = torch.empty(pc.taps, pc.cin_p, rows, dtype=torch.bfloat16, device=device) if need_dgrad else None
-        self.dwp = torch.zeros(pc.taps, rows, pc.cin_p, dtype=torch.float32, device=device)
-        self.db = torch.zeros(rows, dtype=torch.float32, device=device)
+        self.dwp_numel = pc.taps * rows * pc.cin_p
+        self.dwp = None                                   # assigned by GeneratorTrainer (view into one flat buffer)
+        self.db = None                                    # padded bias gradient, only when cout_p != cout
         self.dgrad_pad = (pc.taps - 1) * pc.dil - pc.pad_left
 
     def pack(self, L) -> None:
@@ -163,13 +166,23 @@ class _GenLayerGrad:
                                               _stream()), "hg_pack_dgrad_weight")
 
     def wgrad(self, L, x, dy, batch: int, t: int) -> None:
-        """x bf16 [B][t][cin_p] (the forward input), dy bf16 [B][t][rows] -> dwp, db"""
+        """x bf16 [B][t][cin_p] (the forward input), dy bf16 [B][t][rows] -> dwp (+=)"""
         pc = self.pc
         _lib.check(L.hg_conv1d_wgrad(_p(x), _p(dy), batch, t, pc.cin_p, t, t, 1, self.rows, pc.taps, 1, pc.dil,
-                                     pc.pad_left, self.dwp.data_ptr(), 0, _stream()), "hg_conv1d_wgrad")
+                                     pc.pad_left, self.dwp.data_ptr(), 1, _stream()), "hg_conv1d_wgrad")
 
     def bias_grad(self, L, dy, batch: int, t: int, c: int) -> None:
-        _lib.check(L.hg_colsum_bf16(_p(dy), batch, t, t, c, 0, self.db.data_ptr(), _stream()), "hg_colsum_bf16")
+        """bias.grad (+)= column sums of dy [B][t][c]; written in place when the layer has no channel padding"""
+        b = self.pc.module.bias
+        if b is None:
+            return
+        if c == self.pc.cout:
+            _lib.check(L.hg_colsum_bf16(_p(dy), batch, t, t, c, 1, b.grad.data_ptr(), _stream()), "hg_colsum_bf16")
+        else:
+            if self.db is None:
+                self.db = torch.zeros(c, dtype=torch.float32, device=dy.device)
+            _lib.check(L.hg_colsum_bf16(_p(dy), batch, t, t, c, 0, self.db.data_ptr(), _stream()), "hg_colsum_bf16")
+            b.grad.add_(self.db[: self.pc.cout])
 
     def dgrad(self, L, dy, batch: int, t: int, out, mask=None, slope: float = LRELU_SLOPE, res0=None, res1=None,
               res2=None, scale: float = 1.0) -> None:
@@ -178,26 +191,20 @@ class _GenLayerGrad:
                                      pc.taps, pc.dil, self.dgrad_pad, _p(mask), slope, 0, 0, 0.0, _p(res0), _p(res1),
                                      _p(res2), scale, _p(out), 0, 0, 1, 0, _stream()), "hg_conv1d_dgrad")
 
-    def to_param_grads(self, L, scratch: torch.Tensor) -> None:
-        """packed dW -> (weight_g.grad, weight_v.grad) or weight.grad; bias.grad"""
+    def to_param_grads(self, L, scratch=None) -> None:
+        """packed dW -> (weight_g.grad, weight_v.grad) or weight.grad, one fused launch (hg_wgrad_finish_*)"""
         pc = self.pc
         m = pc.module
         g, v = _g_v(m)
-        st = _stream()
+        gp, dgp = (0, 0) if g is None else (g.data_ptr(), g.grad.data_ptr())
         if pc.kind == "conv":
-            d0, d1, k = pc.cout, pc.cin, pc.taps
-            _lib.check(L.hg_unpack_wgrad_conv(self.dwp.data_ptr(), d0, d1, k, self.rows, pc.cin_p, d0, 1, None,
-                                              scratch.data_ptr(), st), "hg_unpack_wgrad_conv")
-            if m.bias is not None:
-                m.bias.grad.copy_(self.db[: pc.cout])
+            _lib.check(L.hg_wgrad_finish_conv(self.dwp.data_ptr(), pc.cout, pc.cin, pc.taps, self.rows, pc.cin_p,
+                                              pc.cout, 1, None, v.data_ptr(), gp, 1, v.grad.data_ptr(), dgp,
+                                              _stream()), "hg_wgrad_finish_conv")
         else:
-            k = m.kernel_size[0]
-            d0, d1 = pc.cin, pc.cout
-            _lib.check(L.hg_unpack_wgrad_convtr(self.dwp.data_ptr(), d0, d1, k, pc.stride, m.padding[0], pc.cin_p,
-                                                pc.cout_p, scratch.data_ptr(), st), "hg_unpack_wgrad_convtr")
-            if m.bias is not None:
-                m.bias.grad.copy_(self.db[: pc.cout])
-        _route_weight_grad(L, m, scratch, d0, d1 * k)
+            _lib.check(L.hg_wgrad_finish_convtr(self.dwp.data_ptr(), pc.cin, pc.cout, m.kernel_size[0], pc.stride,
+                                                m.padding[0], pc.cin_p, pc.cout_p, v.data_ptr(), gp, 1,
+                                                v.grad.data_ptr(), dgp, _stream()), "hg_wgrad_finish_convtr")
 
 
 def _route_weight_grad(L, m: nn.Module, dw: torch.Tensor, d0: int, rest: int, accumulate: bool = False) -> None:
@@ -226,7 +233,13 @@ class GeneratorTrainer:
         self.g_pre = _GenLayerGrad(e.pre, device, need_dgrad=False)
         self.g_ups = [_GenLayerGrad(pc, device) for pc in e.ups]
         self.g_blocks = [[_GenLayerGrad(pc, device) for pc in blk] for blk in e.blocks]
-        nmax = max(gl.dwp.numel() for gl in [self.g_pre] + self.g_ups + [x for b in self.g_blocks for x in b])
+        layers = [self.g_pre] + self.g_ups + [x for b in self.g_blocks for x in b]
+        self.dwp_flat = torch.zeros(sum(gl.dwp_numel for gl in layers), dtype=torch.float32, device=device)
+        off = 0
+        for gl in layers:
+            gl.dwp = self.dwp_flat[off:off + gl.dwp_numel]
+            off += gl.dwp_numel
+        nmax = max(gl.dwp_numel for gl in layers)
         # stream lanes: 0 .. nk-2 = MRF branches beside the main stream, W_LANE + j = weight-gradient work of branch j
         nk = gen.num_kernels
         self.W_LANE = max(1, nk - 1)
@@ -409,6 +422,8 @@ class GeneratorTrainer:
         main = torch.cuda.current_stream()
         self.post_dw.zero_()
         self.post_db.zero_()
+        self.dwp_flat.zero_()          # every wgrad / finish / bias kernel below accumulates
+        self.flat.g.zero_()
         lanes.fork()
         # conv_post + tanh; the kernel also applies the slope-0.01 leaky_relu mask of the last stage
         _lib.check(L.hg_conv_post_tanh_bwd(last["stage_act"].data_ptr(), e.post_w.data_ptr(), ws["y"].data_ptr(),
@@ -420,7 +435,7 @@ class GeneratorTrainer:
         def post_grads():
             cin, k = post.in_channels, post.kernel_size[0]
             _route_weight_grad(L, post, self.post_dw[:cin].contiguous(), 1, cin * k)
-            post.bias.grad.copy_(self.post_db)
+            post.bias.grad.copy_(self.post_db)      # flat.g was zeroed: plain stores here
         self._side(L, self.W_LANE, main, post_grads)
         for i in reversed(range(len(e.ups))):
             st = stages[i]
@@ -443,8 +458,7 @@ class GeneratorTrainer:
             up_in = ws["pre_act"] if i == 0 else stages[i - 1]["stage_act"]
 
             def up_grads(up=up, dx_raw=dx_raw, up_in=up_in, t=t, c=c, t_in=t_in):
-                _lib.check(L.hg_colsum_bf16(dx_raw.data_ptr(), b, t, t, c, 0, up.db.data_ptr(), _stream()),
-                           "hg_colsum_bf16")
+                up.bias_grad(L, dx_raw, b, t, c)               # dx_raw as [B][t][c]: phases fold into the rows
                 up.wgrad(L, up_in, dx_raw, b, t_in)            # dy viewed as [B][t_in][stride * c]
                 up.to_param_grads(L, self.scratch[self.W_LANE])
             self._side(L, self.W_LANE, main, up_grads)
@@ -784,8 +798,8 @@ class _SubDiscTrainer:
                                            nfm[nl] if fm else 0.0, G["grad"][-1][seq0:].data_ptr(), dwq, dbq, st),
                    "hg_disc_last_conv_bwd")
         if want_wgrad:
-            self._route(L, post, self.scratch, 1, c_last * self.kpost, W, len(self.mods) - 1, accumulate)
-            self._bias(post, self.db[:1], accumulate)
+            self._route(L, post, self.scratch, 1, c_last * self.kpost, W, len(self.mods) - 1, True)
+            self._bias(post, self.db[:1], True)
         for li in reversed(range(nl)):
             layer = self.mids[li]
             m = self.mods[1 + li]
@@ -794,18 +808,25 @@ class _SubDiscTrainer:
             d_out = G["grad"][1 + li][seq0:]
             a_in = G["act"][li]
             if want_wgrad:
-                _lib.check(L.hg_colsum_bf16(d_out.data_ptr(), nseq, h_out, rows_out, layer.cout, 0, self.db.data_ptr(),
-                                            st), "hg_colsum_bf16")
-                self._bias(m, self.db[: layer.cout], accumulate)
+                # bias.grad += column sums, in place (the flat gradient buffer was zeroed at the start of backward_d)
+                _lib.check(L.hg_colsum_bf16(d_out.data_ptr(), nseq, h_out, rows_out, layer.cout, 1,
+                                            m.bias.grad.data_ptr(), st), "hg_colsum_bf16")
                 _lib.check(L.hg_conv1d_wgrad(a_in[seq0:].data_ptr(), d_out.data_ptr(), 1, nseq * rows_in, layer.cin,
                                              nseq * rows_out, nseq * rows_out, layer.groups_eff, layer.cout, layer.k,
                                              layer.stride, 1, layer.pad, self.dwp.data_ptr(), 0, st), "hg_conv1d_wgrad")
                 cin_g = layer.cin // layer.groups
                 order = (c_int * layer.k)(*layer.order)
-                _lib.check(L.hg_unpack_wgrad_conv(self.dwp.data_ptr(), layer.cout, cin_g, layer.k, layer.cout,
-                                                  layer.cin_tile, layer.cout // layer.groups, layer.merge, order,
-                                                  self.scratch.data_ptr(), st), "hg_unpack_wgrad_conv")
-                self._route(L, m, self.scratch, layer.cout, cin_g * layer.k, W, 1 + li, accumulate)
+                if hasattr(m, "weight_orig"):
+                    _lib.check(L.hg_unpack_wgrad_conv(self.dwp.data_ptr(), layer.cout, cin_g, layer.k, layer.cout,
+                                                      layer.cin_tile, layer.cout // layer.groups, layer.merge, order,
+                                                      self.scratch.data_ptr(), st), "hg_unpack_wgrad_conv")
+                    self._route(L, m, self.scratch, layer.cout, cin_g * layer.k, W, 1 + li, True)
+                else:
+                    g, v = _g_v(m)          # unpack + weight_norm backward in one launch, accumulating
+                    _lib.check(L.hg_wgrad_finish_conv(self.dwp.data_ptr(), layer.cout, cin_g, layer.k, layer.cout,
+                                                      layer.cin_tile, layer.cout // layer.groups, layer.merge, order,
+                                                      v.data_ptr(), g.data_ptr(), 1, v.grad.data_ptr(),
+                                                      g.grad.data_ptr(), st), "hg_wgrad_finish_conv")
             self.bwd[li].dgrad(L, d_out, nseq, h_out, rows_out, rows_in, a_in[seq0:],
                                a_in[seq0 - nr:] if fm else None, nfm[li] if fm else 0.0, G["grad"][li][seq0:], st,
                                flat_h_in=h_in)
@@ -821,8 +842,8 @@ class _SubDiscTrainer:
                                             bn, self.t, period, k0, s0, p0, c0, geo[0][1], dw0, db0,
                                             _p(dy_audio), st), "hg_disc_first_conv_bwd")
         if want_wgrad:
-            self._route(L, m0, self.scratch, c0, k0, W, 0, accumulate)
-            self._bias(m0, self.db[:c0], accumulate)
+            self._route(L, m0, self.scratch, c0, k0, W, 0, True)
+            self._bias(m0, self.db[:c0], True)
 
     @staticmethod
     def _bias(m: nn.Module, db: torch.Tensor, accumulate: bool) -> None:
@@ -908,6 +929,7 @@ class DiscriminatorTrainer:
         return out
 
     def backward_d(self) -> None:
+        self.flat.g.zero_()                 # every parameter-gradient kernel of the sub-discriminators accumulates
         self.lanes.fork()
         for i, sd in enumerate(self.subs):
             with self.lanes.lane(i):

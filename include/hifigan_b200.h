@@ -251,6 +251,16 @@ int hg_unpack_wgrad_conv(const float* dw_packed, int cout, int cin_g, int k, int
 int hg_unpack_wgrad_convtr(const float* dw_packed, int cin, int cout, int k, int stride, int padding, int cin_p,
                            int cout_p, float* dw, void* stream);
 
+/* hg_wgrad_finish_conv / _convtr — hg_unpack_wgrad_* and hg_weight_norm_bwd in ONE launch per layer: packed
+ * weight gradient -> (weight_v.grad, weight_g.grad), or -> weight.grad when g == NULL.  Added to the existing
+ * values when accumulate != 0. */
+int hg_wgrad_finish_conv(const float* dw_packed, int cout, int cin_g, int k, int rows_p, int cin_tile, int cout_g,
+                         int merge, const int* host_tap_order, const float* v, const float* g, int accumulate,
+                         float* dv, float* dg, void* stream);
+int hg_wgrad_finish_convtr(const float* dw_packed, int cin, int cout, int k, int stride, int padding, int cin_p,
+                           int cout_p, const float* v, const float* g, int accumulate, float* dv, float* dg,
+                           void* stream);
+
 /* hg_weight_norm_bwd — backward of w = g * v / ||v|| (norm over all dims but 0): dw, v fp32 [dim0][rest],
  * g fp32 [dim0] -> dv, dg (added to the existing values when accumulate != 0). */
 int hg_weight_norm_bwd(const float* dw, const float* v, const float* g, int dim0, int rest, int accumulate,
