@@ -532,6 +532,10 @@ class _SubDiscTrainer:
         self.bwd = [_DiscBwdLayer(l, device) for l in self.mids]
         self.kpost = disc.conv_post.kernel_size[0]
         self.spectral = hasattr(m0, "weight_orig")
+        # the spectral-norm scale runs its real / generated halves as two parts with their own sigma (and their own
+        # data-gradient filter banks), on two lanes; lane 0 is the parameter-gradient lane of this sub-discriminator
+        self.bwd_parts = [self.bwd] + ([[_DiscBwdLayer(l, device) for l in self.mids]] if self.spectral else [])
+        self.lanes = _Lanes(2, device)
         self.ws = {}
         nmax = max(l.k * l.cout * l.cin_tile for l in self.mids)
         self.dwp = torch.zeros(nmax, dtype=torch.float32, device=device)
@@ -669,16 +673,38 @@ class _SubDiscTrainer:
         self.parts = []
         st = _stream()
         k0, s0, p0, c0 = self.first
-        for pi, (b0, bn) in enumerate(parts):
+        Ws = []
+        for pi in range(len(parts)):
             # weight_norm layers: the packs stay valid until the next optimizer update (the G-step forward of one
-            # step and the D-step forward of the next see the same weights); spectral norm moves on every call
+            # step and the D-step forward of the next see the same weights); spectral norm moves on every call, and
+            # its second part's power iteration continues from the first's
             if self.spectral or not self.fwd_valid:
                 W = self._weights(pi)
                 self.W_cached = W
                 self.fwd_valid = True
             else:
                 W = self.W_cached
+            Ws.append(W)
+        here = torch.cuda.current_stream()
+        for pi, (b0, bn) in enumerate(parts):
+            W = Ws[pi]
             self.parts.append((b0, bn, W))
+            if pi == 1:
+                self.lanes.streams[1].wait_stream(here)
+                with torch.cuda.stream(self.lanes.streams[1]):
+                    self._forward_part(L, G, W, ycat, b0, bn, t)
+            else:
+                self._forward_part(L, G, W, ycat, b0, bn, t)
+        if len(parts) > 1:
+            here.wait_stream(self.lanes.streams[1])
+        self.G, self.nb, self.nreal, self.t, self.ycat = G, nb, nreal, t, ycat
+        return G
+
+    def _forward_part(self, L, G, W, ycat, b0: int, bn: int, t: int) -> None:
+        period = self.period
+        st = _stream()
+        k0, s0, p0, c0 = self.first
+        if True:
             seq0, nseq = b0 * period, bn * period
             w0 = W["eff"][0].reshape(c0, k0).contiguous()
             W["w0"] = w0
@@ -706,8 +732,6 @@ class _SubDiscTrainer:
             _lib.check(L.hg_disc_last_conv_fwd(act[seq0:].data_ptr(), wp.data_ptr(), bp.data_ptr(), nseq, h, rows,
                                                c_last, self.kpost, G["logit"][seq0:].data_ptr(), st),
                        "hg_disc_last_conv_fwd")
-        self.G, self.nb, self.nreal, self.t, self.ycat = G, nb, nreal, t, ycat
-        return G
 
     # ---- losses (on the internal layouts; means are permutation-invariant) -------------------------------------
     def numel_fmaps(self, nb_half: int) -> List[int]:
@@ -746,16 +770,24 @@ class _SubDiscTrainer:
         _lib.check(L.hg_loss_grad(lr.data_ptr(), 0, nr * h, 1, 1.0, 2.0 / (nr * h), 0.0, G["dlogit"].data_ptr(), st))
         _lib.check(L.hg_loss_grad(lg.data_ptr(), 0, (ntot - nr) * h, 1, 0.0, 2.0 / ((ntot - nr) * h), 0.0,
                                   G["dlogit"][nr:].data_ptr(), st))
-        first_part = True
-        for b0, bn, W in self.parts:
-            seq0, nseq = b0 * period, bn * period
-            self._pack_dgrad(W)
-            self._backward_part(L, G, W, b0, bn, want_wgrad=True, fm=False, dy_audio=None, accumulate=not first_part)
-            first_part = False
+        here = torch.cuda.current_stream()
+        for pi, (b0, bn, W) in enumerate(self.parts):
+            self._pack_dgrad(W, pi)
+        self.lanes.fork()     # both lanes join the capture here (a join of a never-forked stream would invalidate it)
+        for pi, (b0, bn, W) in enumerate(self.parts):
+            if pi == 1:                       # spectral norm: the generated half's chain on the second lane
+                self.lanes.streams[1].wait_stream(here)
+                with torch.cuda.stream(self.lanes.streams[1]):
+                    self._backward_part(L, G, W, b0, bn, want_wgrad=True, fm=False, dy_audio=None, accumulate=True,
+                                        part=pi)
+            else:
+                self._backward_part(L, G, W, b0, bn, want_wgrad=True, fm=False, dy_audio=None, accumulate=True,
+                                    part=pi)
+        self.lanes.join()
 
-    def _pack_dgrad(self, W) -> None:
+    def _pack_dgrad(self, W, part: int = 0) -> None:
         if self.spectral or not self.dgrad_valid:
-            for bl, w_eff in zip(self.bwd, W["eff"][1:-1]):
+            for bl, w_eff in zip(self.bwd_parts[part], W["eff"][1:-1]):
                 bl.pack(w_eff)
             self.dgrad_valid = True
 
@@ -772,34 +804,49 @@ class _SubDiscTrainer:
         _lib.check(L.hg_loss_grad(lg.data_ptr(), lr.data_ptr(), ng * h, 2, 1.0, 2.0 / (ng * h), nfm[-1],
                                   G["dlogit"][nr:].data_ptr(), st))
         b0, bn, W = self.parts[-1] if self.spectral else (self.nreal, self.nb - self.nreal, self.parts[0][2])
-        self._pack_dgrad(W)
+        part = len(self.parts) - 1
+        self._pack_dgrad(W, part)
         self._backward_part(L, G, W, self.nreal, self.nb - self.nreal, want_wgrad=False, fm=True,
-                            dy_audio=dy_audio, accumulate=False, nfm=nfm)
+                            dy_audio=dy_audio, accumulate=False, nfm=nfm, part=part)
 
     def _backward_part(self, L, G, W, b0: int, bn: int, want_wgrad: bool, fm: bool, dy_audio, accumulate: bool,
-                       nfm: Optional[List[float]] = None) -> None:
-        period, st = self.period, _stream()
+                       nfm: Optional[List[float]] = None, part: int = 0) -> None:
+        """The data-gradient chain runs on the current stream; all parameter-gradient work (bias sums, wgrad,
+        finish) goes to this sub-discriminator's w-lane, which also serialises the use of the shared scratch."""
+        period = self.period
         seq0, nseq = b0 * period, bn * period
         nr = self.nreal * period
         geo = G["geo"]
         nl = len(self.mids)
+        bwd = self.bwd_parts[part]
         h_last, rows_last, c_last = geo[-1]
         act_last = G["act"][-1]
         post = self.mods[-1]
-        dwq = dbq = 0
-        if want_wgrad:
-            self.scratch[: c_last * self.kpost].zero_()
-            self.db.zero_()
-            dwq, dbq = self.scratch.data_ptr(), self.db.data_ptr()
+        here = torch.cuda.current_stream()
+        wlane = self.lanes.streams[0]
+
+        def side(fn):
+            wlane.wait_stream(here)
+            with torch.cuda.stream(wlane):
+                fn()
+
         # fm_r for the generated half is the real half of the same buffer (seq - nr)
         fm_r_last = act_last[seq0 - nr:].data_ptr() if fm else 0
         _lib.check(L.hg_disc_last_conv_bwd(act_last[seq0:].data_ptr(), W["wp"].data_ptr(), G["dlogit"][seq0:].data_ptr(),
                                            nseq, h_last, rows_last, c_last, self.kpost, LRELU_SLOPE, fm_r_last,
-                                           nfm[nl] if fm else 0.0, G["grad"][-1][seq0:].data_ptr(), dwq, dbq, st),
+                                           nfm[nl] if fm else 0.0, G["grad"][-1][seq0:].data_ptr(), 0, 0, _stream()),
                    "hg_disc_last_conv_bwd")
         if want_wgrad:
-            self._route(L, post, self.scratch, 1, c_last * self.kpost, W, len(self.mods) - 1, True)
-            self._bias(post, self.db[:1], True)
+            def post_grads():
+                self.scratch[: c_last * self.kpost].zero_()
+                self.db.zero_()
+                _lib.check(L.hg_disc_last_conv_bwd(act_last[seq0:].data_ptr(), W["wp"].data_ptr(),
+                                                   G["dlogit"][seq0:].data_ptr(), nseq, h_last, rows_last, c_last,
+                                                   self.kpost, LRELU_SLOPE, 0, 0.0, 0, self.scratch.data_ptr(),
+                                                   self.db.data_ptr(), _stream()), "hg_disc_last_conv_bwd")
+                self._route(L, post, self.scratch, 1, c_last * self.kpost, W, len(self.mods) - 1, True)
+                self._bias(post, self.db[:1], True)
+            side(post_grads)
         for li in reversed(range(nl)):
             layer = self.mids[li]
             m = self.mods[1 + li]
@@ -808,42 +855,51 @@ class _SubDiscTrainer:
             d_out = G["grad"][1 + li][seq0:]
             a_in = G["act"][li]
             if want_wgrad:
-                # bias.grad += column sums, in place (the flat gradient buffer was zeroed at the start of backward_d)
-                _lib.check(L.hg_colsum_bf16(d_out.data_ptr(), nseq, h_out, rows_out, layer.cout, 1,
-                                            m.bias.grad.data_ptr(), st), "hg_colsum_bf16")
-                _lib.check(L.hg_conv1d_wgrad(a_in[seq0:].data_ptr(), d_out.data_ptr(), 1, nseq * rows_in, layer.cin,
-                                             nseq * rows_out, nseq * rows_out, layer.groups_eff, layer.cout, layer.k,
-                                             layer.stride, 1, layer.pad, self.dwp.data_ptr(), 0, st), "hg_conv1d_wgrad")
-                cin_g = layer.cin // layer.groups
-                order = (c_int * layer.k)(*layer.order)
-                if hasattr(m, "weight_orig"):
-                    _lib.check(L.hg_unpack_wgrad_conv(self.dwp.data_ptr(), layer.cout, cin_g, layer.k, layer.cout,
-                                                      layer.cin_tile, layer.cout // layer.groups, layer.merge, order,
-                                                      self.scratch.data_ptr(), st), "hg_unpack_wgrad_conv")
-                    self._route(L, m, self.scratch, layer.cout, cin_g * layer.k, W, 1 + li, True)
-                else:
-                    g, v = _g_v(m)          # unpack + weight_norm backward in one launch, accumulating
-                    _lib.check(L.hg_wgrad_finish_conv(self.dwp.data_ptr(), layer.cout, cin_g, layer.k, layer.cout,
-                                                      layer.cin_tile, layer.cout // layer.groups, layer.merge, order,
-                                                      v.data_ptr(), g.data_ptr(), 1, v.grad.data_ptr(),
-                                                      g.grad.data_ptr(), st), "hg_wgrad_finish_conv")
-            self.bwd[li].dgrad(L, d_out, nseq, h_out, rows_out, rows_in, a_in[seq0:],
-                               a_in[seq0 - nr:] if fm else None, nfm[li] if fm else 0.0, G["grad"][li][seq0:], st,
-                               flat_h_in=h_in)
+                def layer_grads(layer=layer, m=m, li=li, h_out=h_out, rows_out=rows_out, rows_in=rows_in, d_out=d_out,
+                                a_in=a_in):
+                    st = _stream()
+                    # bias.grad += column sums, in place (the flat gradient buffer was zeroed in backward_d)
+                    _lib.check(L.hg_colsum_bf16(d_out.data_ptr(), nseq, h_out, rows_out, layer.cout, 1,
+                                                m.bias.grad.data_ptr(), st), "hg_colsum_bf16")
+                    _lib.check(L.hg_conv1d_wgrad(a_in[seq0:].data_ptr(), d_out.data_ptr(), 1, nseq * rows_in, layer.cin,
+                                                 nseq * rows_out, nseq * rows_out, layer.groups_eff, layer.cout,
+                                                 layer.k, layer.stride, 1, layer.pad, self.dwp.data_ptr(), 0, st),
+                               "hg_conv1d_wgrad")
+                    cin_g = layer.cin // layer.groups
+                    order = (c_int * layer.k)(*layer.order)
+                    if hasattr(m, "weight_orig"):
+                        _lib.check(L.hg_unpack_wgrad_conv(self.dwp.data_ptr(), layer.cout, cin_g, layer.k, layer.cout,
+                                                          layer.cin_tile, layer.cout // layer.groups, layer.merge,
+                                                          order, self.scratch.data_ptr(), st), "hg_unpack_wgrad_conv")
+                        self._route(L, m, self.scratch, layer.cout, cin_g * layer.k, W, 1 + li, True)
+                    else:
+                        g, v = _g_v(m)          # unpack + weight_norm backward in one launch, accumulating
+                        _lib.check(L.hg_wgrad_finish_conv(self.dwp.data_ptr(), layer.cout, cin_g, layer.k, layer.cout,
+                                                          layer.cin_tile, layer.cout // layer.groups, layer.merge,
+                                                          order, v.data_ptr(), g.data_ptr(), 1, v.grad.data_ptr(),
+                                                          g.grad.data_ptr(), st), "hg_wgrad_finish_conv")
+                side(layer_grads)
+            bwd[li].dgrad(L, d_out, nseq, h_out, rows_out, rows_in, a_in[seq0:],
+                          a_in[seq0 - nr:] if fm else None, nfm[li] if fm else 0.0, G["grad"][li][seq0:], _stream(),
+                          flat_h_in=h_in)
         # first conv (Cin = 1)
         k0, s0, p0, c0 = self.first
         m0 = self.mods[0]
-        dw0 = db0 = 0
         if want_wgrad:
-            self.scratch[: c0 * k0].zero_()
-            self.db.zero_()
-            dw0, db0 = self.scratch.data_ptr(), self.db.data_ptr()
-        _lib.check(L.hg_disc_first_conv_bwd(self.ycat[b0:].data_ptr(), W["w0"].data_ptr(), G["grad"][0][seq0:].data_ptr(),
-                                            bn, self.t, period, k0, s0, p0, c0, geo[0][1], dw0, db0,
-                                            _p(dy_audio), st), "hg_disc_first_conv_bwd")
-        if want_wgrad:
-            self._route(L, m0, self.scratch, c0, k0, W, 0, True)
-            self._bias(m0, self.db[:c0], True)
+            def first_grads():
+                self.scratch[: c0 * k0].zero_()
+                self.db.zero_()
+                _lib.check(L.hg_disc_first_conv_bwd(self.ycat[b0:].data_ptr(), W["w0"].data_ptr(),
+                                                    G["grad"][0][seq0:].data_ptr(), bn, self.t, period, k0, s0, p0, c0,
+                                                    geo[0][1], self.scratch.data_ptr(), self.db.data_ptr(), 0,
+                                                    _stream()), "hg_disc_first_conv_bwd")
+                self._route(L, m0, self.scratch, c0, k0, W, 0, True)
+                self._bias(m0, self.db[:c0], True)
+            side(first_grads)
+        if dy_audio is not None:
+            _lib.check(L.hg_disc_first_conv_bwd(self.ycat[b0:].data_ptr(), W["w0"].data_ptr(),
+                                                G["grad"][0][seq0:].data_ptr(), bn, self.t, period, k0, s0, p0, c0,
+                                                geo[0][1], 0, 0, _p(dy_audio), _stream()), "hg_disc_first_conv_bwd")
 
     @staticmethod
     def _bias(m: nn.Module, db: torch.Tensor, accumulate: bool) -> None:
@@ -1087,6 +1143,11 @@ class TrainStep:
                 warnings.warn(f"hifigan_b200: CUDA graph capture of the training step failed, running eagerly ({e})")
                 torch.cuda.synchronize()
                 entry = "eager"
+                # the aborted capture ran the host side of a step (flags, caches) without executing any kernel:
+                # drop every cached pack so the eager path rebuilds them
+                self.G.invalidate()
+                for sd in self.D.subs:
+                    sd.invalidate()
             graphs[key] = entry
         if entry == "eager":
             return self.step(x, y, y_mel)

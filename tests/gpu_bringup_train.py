@@ -117,6 +117,37 @@ def profile(b):
     torch.cuda.profiler.stop()
 
 
+def convfloor():
+    """per-launch cost of the tcgen05 conv / wgrad kernels on small problems (back-to-back launches on one stream)"""
+    L = _lib.lib()
+    dev = torch.device("cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for (b, t, c, k, d) in [(1, 128, 64, 3, 1), (1, 128, 256, 3, 1), (16, 256, 256, 11, 5), (16, 2048, 128, 7, 3),
+                            (16, 4096, 64, 11, 5), (16, 8192, 32, 11, 5), (16, 8192, 32, 3, 1)]:
+        x = torch.randn(b, t, c, device=dev).bfloat16()
+        w = torch.randn(k, c, c, device=dev).bfloat16()
+        out = torch.empty_like(x)
+        dwp = torch.zeros(k, c, c, device=dev)
+        pad = (k - 1) * d // 2
+        res = {}
+        for name, fn in (("fwd", lambda: L.hg_conv1d_fwd(x.data_ptr(), w.data_ptr(), 0, b, t, c, c, k, d, pad, 0, 0, 0, 1.0,
+                                                         out.data_ptr(), 0, 0.1, st)),
+                         ("wgrad", lambda: L.hg_conv1d_wgrad(x.data_ptr(), out.data_ptr(), b, t, c, t, t, 1, c, k, 1, d, pad,
+                                                             dwp.data_ptr(), 1, st))):
+            for _ in range(5):
+                _lib.check(fn())
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(200):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            res[name] = e0.elapsed_time(e1) / 200 * 1e3
+        flop = 2.0 * b * t * c * c * k
+        print(f"b={b} t={t} c={c} k={k}: fwd {res['fwd']:.1f} us ({flop / res['fwd'] / 1e6:.0f} TFLOP/s)  "
+              f"wgrad {res['wgrad']:.1f} us ({flop / res['wgrad'] / 1e6:.0f} TFLOP/s)")
+
+
 def firstbwd():
     """micro-benchmark of hg_disc_first_conv_bwd in its two modes at the MSD scale-1 shape"""
     L = _lib.lib()
@@ -173,6 +204,8 @@ if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "parity"
     if mode == "parity":
         parity()
+    elif mode == "convfloor":
+        convfloor()
     elif mode == "firstbwd":
         firstbwd()
     elif mode == "trace":
