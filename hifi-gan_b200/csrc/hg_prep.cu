@@ -197,7 +197,24 @@ loss_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, long l
   if (threadIdx.x == 0) atomicAdd(out, acc);
 }
 
+// out[i] = (int16) trunc(x[i] * scale): the `audio * MAX_WAV_VALUE -> astype('int16')` of the reference's drivers
+// (src/inference.py:57-58, src/inference_e2e.py:51-52) on the device, so the D2H copy moves 2 bytes per sample
+__global__ void float_to_int16_kernel(const float* __restrict__ x, long long n, float scale, int16_t* __restrict__ out) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x)
+    out[i] = static_cast<int16_t>(static_cast<int>(x[i] * scale));
+}
+
 }  // namespace
+
+extern "C" int hg_float_to_int16(const float* x, long long n, float scale, int16_t* out, void* stream) {
+  HG_REQUIRE(x && out && n > 0, "hg_float_to_int16: bad arguments");
+  long long blocks = (n + 256 * 4 - 1) / (256 * 4);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  float_to_int16_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, scale, out);
+  HG_CHECK_CUDA(cudaGetLastError());
+  g_hg_launches.fetch_add(1, std::memory_order_relaxed);
+  return HG_OK;
+}
 
 extern "C" int hg_loss_sum(const float* a, const float* b, long long n, int mode, float c, float* out_acc,
                            void* stream) {

@@ -155,6 +155,10 @@ int hg_ncl_to_nlc(const float* x, int batch, int c, int t, int c_pad, void* out,
                   float act_slope, void* stream);
 int hg_nlc_to_ncl(const void* x, int batch, int t, int c, float* out, void* stream);
 
+/* hg_float_to_int16 — out[i] = (int16) trunc(x[i] * scale): the `audio * MAX_WAV_VALUE` -> `astype('int16')` of the
+ * reference's inference drivers (src/inference.py:57-58, src/inference_e2e.py:51-52) on the device. */
+int hg_float_to_int16(const float* x, long long n, float scale, int16_t* out, void* stream);
+
 /* hg_loss_sum — the reductions behind feature_loss / discriminator_loss / generator_loss (src/models.py:251-282)
  * and the mel L1: mode 0 accumulates sum |a[i] - b[i]|, mode 1 accumulates sum (c - a[i])^2 into *out_acc (fp32,
  * atomicAdd: zero it first; the caller divides by n for the mean).  a, b fp32 device arrays of n elements. */

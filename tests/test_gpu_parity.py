@@ -538,3 +538,39 @@ def test_loss_sum_kernel(H):
     l, r, gg = H.discriminator_loss([a], [b])
     assert torch.allclose(l, ((1 - a) ** 2).mean() + (b ** 2).mean(), rtol=1e-5) and isinstance(r[0], float)
     assert torch.allclose(H.generator_loss([a])[0], ((1 - a) ** 2).mean(), rtol=1e-5)
+
+
+def test_inference_e2e_driver_matches_per_file_reference_schedule(H, O, tmp_path):
+    """hifigan_b200.inference: the batched, length-bucketed mel -> wav driver writes the same int16
+    samples as the reference's per-file schedule (src/inference_e2e.py:45-56: generator(x) -> * 32768 -> astype
+    int16), with the reference's output names; checkpoint + config.json layout as src/inference.py:74-80."""
+    import json
+    from scipy.io.wavfile import read
+    from hifigan_b200 import inference as drv
+    cfg = dict(O.config("v3"))
+    cfg["seed"] = 1234
+    h = H.AttrDict(cfg)
+    torch.manual_seed(3)
+    G = H.Generator(h)
+    cp = tmp_path / "cp"
+    cp.mkdir()
+    torch.save({"generator": G.state_dict()}, cp / "g_00000001")
+    (cp / "config.json").write_text(json.dumps(cfg))
+    mels = tmp_path / "mels"
+    mels.mkdir()
+    g = torch.Generator().manual_seed(0)
+    frames = {"u0": 40, "u1": 33, "u2": 40, "u3": 40, "u4": 33}
+    data = {k: torch.randn(1, 80, f, generator=g) for k, f in frames.items()}
+    for k, v in data.items():
+        np.save(mels / f"{k}.npy", v.numpy())
+    out = tmp_path / "out"
+    drv.main(["e2e", "--checkpoint_file", str(cp / "g_00000001"), "--input_mels_dir", str(mels), "--output_dir", str(out),
+              "--max_batch", "2"])
+    Gd = G.cuda().eval()
+    Gd.remove_weight_norm()
+    for k, v in data.items():
+        sr, wav = read(out / f"{k}_generated_e2e.wav")
+        with torch.no_grad():
+            ref = (Gd(v.cuda()).squeeze() * 32768.0).cpu().numpy().astype("int16")
+        assert sr == h.sampling_rate and wav.dtype == np.int16 and wav.shape == ref.shape
+        assert np.array_equal(wav, ref), k

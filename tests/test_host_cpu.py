@@ -210,3 +210,14 @@ def test_shipped_configs_match_upstream_values():
         assert all(h[k] == ref[k] for k in ref)
         H.Generator(h)
     assert H.load_config("v3").resblock == "2" and H.load_config("v1").upsample_initial_channel == 512
+
+
+def test_inference_driver_buckets_by_exact_length():
+    """hifigan_b200.inference: only equal-length mels share a batch (zero padding at every layer of the Generator
+    makes ragged batching change edge samples), order of first appearance is kept, batches are capped."""
+    from hifigan_b200.inference import bucket_by_length
+    items = [("a", torch.zeros(80, 10)), ("b", torch.zeros(80, 7)), ("c", torch.zeros(80, 10)),
+             ("d", torch.zeros(80, 10)), ("e", torch.zeros(80, 7))]
+    got = [[n for n, _ in b] for b in bucket_by_length(items, 2)]
+    assert got == [["a", "c"], ["d"], ["b", "e"]]
+    assert bucket_by_length([], 4) == []
