@@ -120,7 +120,7 @@ _SIGNATURES = {
                              c_void_p]),
     "hg_l1_sum_bf16": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_void_p, c_void_p]),
     "hg_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_float, c_float, c_float,
-                              c_float, c_float, c_int, c_void_p, c_float, c_void_p]),
+                              c_float, c_float, c_int, c_void_p, c_void_p, c_float, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -10,7 +10,6 @@
 #include "hg_common.cuh"
 
 #include <atomic>
-#include <cstdlib>
 
 #include "../../include/hifigan_b200.h"
 
@@ -236,7 +235,7 @@ constexpr int kXPitch = 20;   // floats per staged input row (16-byte multiple)
 __global__ void __launch_bounds__(256)
 disc_first_bwd_kernel(const float* __restrict__ y, const float* __restrict__ w, const __nv_bfloat16* __restrict__ dpre,
                       int t, int period, int h_in, int h_out, int h_rows, int k, int stride, int pad, int cout,
-                      float* __restrict__ dw, float* __restrict__ db, float* __restrict__ dy, int dbg) {
+                      float* __restrict__ dw, float* __restrict__ db, float* __restrict__ dy) {
   extern __shared__ __align__(16) uint8_t smb[];
   const int pitch = cout + 2;                                   // odd word pitch: column reads are conflict-free
   float* ws = reinterpret_cast<float*>(smb);                    // [kFirstK][cout], zero for taps >= k
@@ -315,7 +314,7 @@ disc_first_bwd_kernel(const float* __restrict__ y, const float* __restrict__ w, 
       float gy[kFirstK];
 #pragma unroll
       for (int j = 0; j < kFirstK; ++j) gy[j] = 0.f;
-      if (q0 + r < p1 && !(dbg & 1)) {
+      if (q0 + r < p1) {
         const int c0 = half * (cout / 2), c1 = c0 + cout / 2;
         const __nv_bfloat16* drow = dp + r * pitch;
 #pragma unroll 2
@@ -330,7 +329,7 @@ disc_first_bwd_kernel(const float* __restrict__ y, const float* __restrict__ w, 
       for (int j = 0; j < kFirstK; ++j) gsm[(half * kFirstTile + r) * kFirstK + j] = gy[j];
       __syncthreads();
       const int n_in = (kFirstTile - 1) * stride + k;
-      for (int e = tid; e < n_in && !(dbg & 2); e += 256) {
+      for (int e = tid; e < n_in; e += 256) {
         const int hh = q0 * stride - pad + e;
         if (hh < 0 || hh >= h_in) continue;
         float a = 0.f;
@@ -512,12 +511,14 @@ weight_norm_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ v
 // torch.optim.AdamW step on one flat fp32 tensor
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
-                             float bc1, float bc2_sqrt, float gscale, const int* __restrict__ dev_step) {
+                             float bc1, float bc2_sqrt, float gscale, const int* __restrict__ dev_step,
+                             const float* __restrict__ dev_lr) {
   if (dev_step) {   // step counter kept on the device so a captured CUDA graph advances it
     const float st = static_cast<float>(*dev_step);
     bc1 = 1.f - powf(b1, st);
     bc2_sqrt = sqrtf(1.f - powf(b2, st));
   }
+  if (dev_lr) lr = *dev_lr;   // learning-rate schedule without re-capturing the graph
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x) {
     const float gi = g[i] * gscale;
     float pi = p[i] * (1.f - lr * wd);
@@ -778,8 +779,7 @@ extern "C" int hg_disc_first_conv_bwd(const float* y, const float* w, const void
   }
   HG_REQUIRE(smem <= 96 * 1024, "hg_disc_first_conv_bwd: tile does not fit shared memory");
   disc_first_bwd_kernel<<<grid, 256, smem, S(stream)>>>(y, w, static_cast<const __nv_bfloat16*>(dpre), t, period, h_in,
-                                                        h_out, h_rows, k, stride, pad, cout, dw, db, dy,
-                                                        getenv("HG_FIRST_DBG") ? atoi(getenv("HG_FIRST_DBG")) : 0);
+                                                        h_out, h_rows, k, stride, pad, cout, dw, db, dy);
   HG_CHECK_CUDA(cudaGetLastError());
   count();
   return HG_OK;
@@ -852,13 +852,13 @@ extern "C" int hg_weight_norm_bwd(const float* dw, const float* v, const float* 
 
 extern "C" int hg_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
                              float beta2, float eps, float weight_decay, int step, const int* dev_step,
-                             float grad_scale, void* stream) {
+                             const float* dev_lr, float grad_scale, void* stream) {
   HG_REQUIRE(p && g && m && v && n > 0 && (step >= 1 || dev_step), "hg_adamw_step: bad arguments");
   if (step < 1) step = 1;
   const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
   const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
   adamw_kernel<<<blocks_for(n, 1024), 256, 0, S(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1,
-                                                           sqrtf(bc2), grad_scale, dev_step);
+                                                           sqrtf(bc2), grad_scale, dev_step, dev_lr);
   HG_CHECK_CUDA(cudaGetLastError());
   count();
   return HG_OK;

@@ -144,6 +144,18 @@ def spectral_de_normalize_torch(magnitudes):
     return dynamic_range_decompression_torch(magnitudes)
 
 
+def get_dataset_filelist(a):
+    """reference meldataset.py:88-96: `name|text` list files -> wav paths under a.input_wavs_dir."""
+    import os
+    with open(a.input_training_file, 'r', encoding='utf-8') as fi:
+        training_files = [os.path.join(a.input_wavs_dir, x.split('|')[0] + '.wav')
+                          for x in fi.read().split('\n') if len(x) > 0]
+    with open(a.input_validation_file, 'r', encoding='utf-8') as fi:
+        validation_files = [os.path.join(a.input_wavs_dir, x.split('|')[0] + '.wav')
+                            for x in fi.read().split('\n') if len(x) > 0]
+    return training_files, validation_files
+
+
 class SegmentSampler:
     """Batched GPU form of MelDataset.__getitem__'s crop/pad rule (reference meldataset.py:141-150):
     utterances live in one resident device pool; a batch is B (utterance, start) pairs drawn with the

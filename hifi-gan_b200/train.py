@@ -82,6 +82,8 @@ class FlatParams:
         self.m = torch.zeros(off, dtype=torch.float32, device=device)
         self.v = torch.zeros(off, dtype=torch.float32, device=device)
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=device)   # AdamW step counter (graph-capturable)
+        self.lr_dev = torch.zeros(1, dtype=torch.float32, device=device)   # learning rate, read by the kernel
+        self._lr_host = None
         with torch.no_grad():
             for p, o, s in zip(ps, self.offsets, self.sizes):
                 view = self.p[o:o + s].view(p.shape)
@@ -96,7 +98,15 @@ class FlatParams:
         self.step_dev.add_(1)
         _lib.check(_lib.lib().hg_adamw_step(self.p.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                             self.numel, lr, betas[0], betas[1], eps, weight_decay, 0,
-                                            self.step_dev.data_ptr(), grad_scale, _stream()), "hg_adamw_step")
+                                            self.step_dev.data_ptr(), self.lr_dev.data_ptr(), grad_scale, _stream()),
+                   "hg_adamw_step")
+
+    def set_lr(self, lr: float) -> None:
+        """the learning rate lives in device memory so that a captured step follows a schedule without re-capture;
+        call OUTSIDE graph capture (TrainStep does, before every step)"""
+        if lr != self._lr_host:
+            self.lr_dev.fill_(lr)
+            self._lr_host = lr
 
 
 class _Lanes:
@@ -191,7 +201,7 @@ class _GenLayerGrad:
                                      pc.taps, pc.dil, self.dgrad_pad, _p(mask), slope, 0, 0, 0.0, _p(res0), _p(res1),
                                      _p(res2), scale, _p(out), 0, 0, 1, 0, _stream()), "hg_conv1d_dgrad")
 
-    def to_param_grads(self, L, scratch=None) -> None:
+    def to_param_grads(self, L) -> None:
         """packed dW -> (weight_g.grad, weight_v.grad) or weight.grad, one fused launch (hg_wgrad_finish_*)"""
         pc = self.pc
         m = pc.module
@@ -239,12 +249,10 @@ class GeneratorTrainer:
         for gl in layers:
             gl.dwp = self.dwp_flat[off:off + gl.dwp_numel]
             off += gl.dwp_numel
-        nmax = max(gl.dwp_numel for gl in layers)
         # stream lanes: 0 .. nk-2 = MRF branches beside the main stream, W_LANE + j = weight-gradient work of branch j
         nk = gen.num_kernels
         self.W_LANE = max(1, nk - 1)
         self.lanes = _Lanes(self.W_LANE + nk, device)
-        self.scratch = [torch.empty(nmax, dtype=torch.float32, device=device) for _ in range(self.W_LANE + nk)]
         post = gen.conv_post
         self.post_dw = torch.zeros(e.post_cin_p, post.kernel_size[0], dtype=torch.float32, device=device)
         self.post_db = torch.zeros(1, dtype=torch.float32, device=device)
@@ -255,10 +263,11 @@ class GeneratorTrainer:
 
     def invalidate(self) -> None:
         """parameters were updated in place through raw pointers (AdamW kernel): force a re-pack"""
-        e = self.eng
-        for pc in [e.pre] + e.ups + [x for b in e.blocks for x in b]:
-            pc.key = None
-        e.post_key = None
+        engines = [self.eng] + [e for e in self.gen.__dict__.get("_hg_engines", {}).values() if e is not self.eng]
+        for e in engines:      # the module API (`generator(x)` in eval / validation) may hold engines of its own
+            for pc in [e.pre] + e.ups + [x for b in e.blocks for x in b]:
+                pc.key = None
+            e.post_key = None
 
     def _workspace(self, b: int, frames: int) -> dict:
         ws = self.ws.get((b, frames))
@@ -385,14 +394,14 @@ class GeneratorTrainer:
                 def w2(c2=c2, t1=t1, g=g):
                     c2.bias_grad(L, g, b, t, c)
                     c2.wgrad(L, t1, g, b, t)
-                    c2.to_param_grads(L, self.scratch[wl])
+                    c2.to_param_grads(L)
                 self._side(L, wl, here, w2)
                 c2.dgrad(L, g, b, t, gt1, mask=t1)
 
                 def w1(c1=c1, xa=xa, gt1=gt1):
                     c1.bias_grad(L, gt1, b, t, c)
                     c1.wgrad(L, xa, gt1, b, t)
-                    c1.to_param_grads(L, self.scratch[wl])
+                    c1.to_param_grads(L)
                 self._side(L, wl, here, w1)
                 c1.dgrad(L, gt1, b, t, out, mask=xa, res0=g, res1=r1, res2=r2)
             else:
@@ -401,7 +410,7 @@ class GeneratorTrainer:
                 def w0(cc=cc, xa=xa, g=g):
                     cc.bias_grad(L, g, b, t, c)
                     cc.wgrad(L, xa, g, b, t)
-                    cc.to_param_grads(L, self.scratch[wl])
+                    cc.to_param_grads(L)
                 self._side(L, wl, here, w0)
                 cc.dgrad(L, g, b, t, out, mask=xa, res0=g, res1=r1, res2=r2)
             g = out
@@ -460,7 +469,7 @@ class GeneratorTrainer:
             def up_grads(up=up, dx_raw=dx_raw, up_in=up_in, t=t, c=c, t_in=t_in):
                 up.bias_grad(L, dx_raw, b, t, c)               # dx_raw as [B][t][c]: phases fold into the rows
                 up.wgrad(L, up_in, dx_raw, b, t_in)            # dy viewed as [B][t_in][stride * c]
-                up.to_param_grads(L, self.scratch[self.W_LANE])
+                up.to_param_grads(L)
             self._side(L, self.W_LANE, main, up_grads)
             if i > 0:
                 up.dgrad(L, dx_raw, b, t_in, stages[i - 1]["g0"], mask=up_in, scale=1.0 / nk)
@@ -468,7 +477,7 @@ class GeneratorTrainer:
                 up.dgrad(L, dx_raw, b, t_in, ws["g_pre"], mask=up_in)
                 self.g_pre.bias_grad(L, ws["g_pre"], b, frames, e.pre.cout_p)
                 self.g_pre.wgrad(L, ws["mel"], ws["g_pre"], b, frames)
-                self.g_pre.to_param_grads(L, self.scratch[0])
+                self.g_pre.to_param_grads(L)
         lanes.join()
 
 
@@ -550,6 +559,7 @@ class _SubDiscTrainer:
     def invalidate(self) -> None:
         """the parameters changed (optimizer update / load_state_dict): re-fold and re-pack on next use"""
         self.fwd_valid = self.dgrad_valid = False
+        self.disc.__dict__.pop("_hg_wcache", None)      # the module API's own pack cache (inference-side forward)
 
     # ---- weights -------------------------------------------------------------------------------------------
     def _weights(self, part: int):
@@ -671,8 +681,6 @@ class _SubDiscTrainer:
         period = self.period
         parts = [(0, nb)] if not self.spectral else [(0, nreal), (nreal, nb - nreal)]
         self.parts = []
-        st = _stream()
-        k0, s0, p0, c0 = self.first
         Ws = []
         for pi in range(len(parts)):
             # weight_norm layers: the packs stay valid until the next optimizer update (the G-step forward of one
@@ -704,34 +712,33 @@ class _SubDiscTrainer:
         period = self.period
         st = _stream()
         k0, s0, p0, c0 = self.first
-        if True:
-            seq0, nseq = b0 * period, bn * period
-            w0 = W["eff"][0].reshape(c0, k0).contiguous()
-            W["w0"] = w0
-            b0_bias = self.mods[0].bias
-            act = G["act"][0]
-            h, rows, _ = G["geo"][0]
-            _lib.check(L.hg_disc_first_conv_fwd(ycat[b0:].data_ptr(), w0.data_ptr(), b0_bias.data_ptr(), bn, t, period,
-                                                k0, s0, p0, c0, rows, act[seq0:].data_ptr(), LRELU_SLOPE, st),
-                       "hg_disc_first_conv_fwd")
-            for li, layer in enumerate(self.mids):
-                m = self.mods[1 + li]
-                bias = m.bias
-                out = G["act"][1 + li]
-                h_out, rows_out, _ = G["geo"][1 + li]
-                _lib.check(L.hg_conv1d_general_fwd(act[seq0:].data_ptr(), W["fwd"][1 + li].data_ptr(), bias.data_ptr(),
-                                                   1, nseq * rows, layer.cin, nseq * rows_out, nseq * rows_out,
-                                                   layer.groups_eff, layer.cout, layer.k, layer.stride, layer.pad,
-                                                   out[seq0:].data_ptr(), LRELU_SLOPE, 0, rows_out, h_out, st),
-                           "hg_conv1d_general_fwd")
-                act, h, rows = out, h_out, rows_out
-            c_last = G["geo"][-1][2]
-            wp = W["eff"][-1].reshape(c_last, self.kpost).contiguous()
-            W["wp"] = wp
-            bp = self.mods[-1].bias
-            _lib.check(L.hg_disc_last_conv_fwd(act[seq0:].data_ptr(), wp.data_ptr(), bp.data_ptr(), nseq, h, rows,
-                                               c_last, self.kpost, G["logit"][seq0:].data_ptr(), st),
-                       "hg_disc_last_conv_fwd")
+        seq0, nseq = b0 * period, bn * period
+        w0 = W["eff"][0].reshape(c0, k0).contiguous()
+        W["w0"] = w0
+        b0_bias = self.mods[0].bias
+        act = G["act"][0]
+        h, rows, _ = G["geo"][0]
+        _lib.check(L.hg_disc_first_conv_fwd(ycat[b0:].data_ptr(), w0.data_ptr(), b0_bias.data_ptr(), bn, t, period,
+                                            k0, s0, p0, c0, rows, act[seq0:].data_ptr(), LRELU_SLOPE, st),
+                   "hg_disc_first_conv_fwd")
+        for li, layer in enumerate(self.mids):
+            m = self.mods[1 + li]
+            bias = m.bias
+            out = G["act"][1 + li]
+            h_out, rows_out, _ = G["geo"][1 + li]
+            _lib.check(L.hg_conv1d_general_fwd(act[seq0:].data_ptr(), W["fwd"][1 + li].data_ptr(), bias.data_ptr(),
+                                               1, nseq * rows, layer.cin, nseq * rows_out, nseq * rows_out,
+                                               layer.groups_eff, layer.cout, layer.k, layer.stride, layer.pad,
+                                               out[seq0:].data_ptr(), LRELU_SLOPE, 0, rows_out, h_out, st),
+                       "hg_conv1d_general_fwd")
+            act, h, rows = out, h_out, rows_out
+        c_last = G["geo"][-1][2]
+        wp = W["eff"][-1].reshape(c_last, self.kpost).contiguous()
+        W["wp"] = wp
+        bp = self.mods[-1].bias
+        _lib.check(L.hg_disc_last_conv_fwd(act[seq0:].data_ptr(), wp.data_ptr(), bp.data_ptr(), nseq, h, rows,
+                                           c_last, self.kpost, G["logit"][seq0:].data_ptr(), st),
+                   "hg_disc_last_conv_fwd")
 
     # ---- losses (on the internal layouts; means are permutation-invariant) -------------------------------------
     def numel_fmaps(self, nb_half: int) -> List[int]:
@@ -1067,6 +1074,9 @@ class TrainStep:
         h = self.h
         b = x.shape[0]
         st = _stream()
+        if not torch.cuda.is_current_stream_capturing():
+            self.G.flat.set_lr(self.lr)
+            self.D.flat.set_lr(self.lr)
         launches0 = _lib.launch_count()
         y2 = y.reshape(b, -1).contiguous().float()
         y_g = self.G.forward(x)                                # [B,1,T]
@@ -1123,7 +1133,9 @@ class TrainStep:
         The first call of a shape runs eagerly (it is a real step and loads every kernel); the second call captures
         and replays; later calls copy the inputs into the captured buffers and replay.  The returned loss tensors are
         the graph's static outputs: read them before the next call.  Falls back to eager when capture fails."""
-        key = (tuple(x.shape), tuple(y.shape), float(self.lr), self.world)
+        self.G.flat.set_lr(self.lr)
+        self.D.flat.set_lr(self.lr)
+        key = (tuple(x.shape), tuple(y.shape), self.world)
         graphs = self.__dict__.setdefault("_graphs", {})
         entry = graphs.get(key)
         if entry is None:

@@ -322,10 +322,12 @@ int hg_loss_grad(const float* a, const float* b, long long n, int mode, float c,
 int hg_l1_sum_bf16(const void* a, const void* b, long long n, float* out_acc, void* stream);
 
 /* hg_adamw_step — torch.optim.AdamW on one flat fp32 tensor (decoupled weight decay, bias correction by `step`,
- * or by the device-resident counter *dev_step when non-NULL so that a captured CUDA graph advances it;
- * gradients multiplied by grad_scale first: 1/world_size after a sum all-reduce). */
+ * or by the device-resident counter *dev_step when non-NULL so that a captured CUDA graph advances it; *dev_lr,
+ * when non-NULL, overrides lr the same way (learning-rate schedules without re-capture); gradients multiplied by
+ * grad_scale first: 1/world_size after a sum all-reduce). */
 int hg_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                  float eps, float weight_decay, int step, const int* dev_step, float grad_scale, void* stream);
+                  float eps, float weight_decay, int step, const int* dev_step, const float* dev_lr, float grad_scale,
+                  void* stream);
 
 #ifdef __cplusplus
 }

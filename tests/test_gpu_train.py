@@ -237,7 +237,7 @@ def test_small_backward_kernels_vs_torch(H):
         ref_p.grad = gr.clone()
         opt.step()
         _lib.check(L.hg_adamw_step(p.data_ptr(), gr.data_ptr(), m.data_ptr(), vv2.data_ptr(), 1000, 2e-4, 0.8, 0.99,
-                                   1e-8, 0.01, step, 0, 1.0, _st()))
+                                   1e-8, 0.01, step, 0, 0, 1.0, _st()))
     assert torch.allclose(p, ref_p.detach(), rtol=1e-5, atol=1e-6)
 
 
@@ -460,3 +460,43 @@ def test_spectral_norm_kernels_vs_torch(H):
         m.eval()
         m(x)
         assert torch.equal(u, u0) and torch.allclose(eff.view_as(m.weight), m.weight.detach(), rtol=1e-4, atol=1e-6)
+
+
+def test_train_driver_checkpoints_and_resumes(H, tmp_path):
+    """hifigan_b200.train_loop (UPSTREAM train.py's command line): trains on a tiny synthetic wav
+    set, writes g_* / do_* files in the reference's format at the configured cadence, validates, and a second run
+    resumes from the newest pair (steps, epoch, optimizer moments) and continues."""
+    import json
+    from scipy.io.wavfile import write
+    from hifigan_b200 import train_loop
+    from oracle import hifigan_oracle as O
+    cfg = dict(H.load_config("v1"))
+    cfg.update(batch_size=2, seed=1234, num_gpus=0)
+    (tmp_path / "config_v1.json").write_text(json.dumps(cfg))
+    wavs = tmp_path / "wavs"
+    wavs.mkdir()
+    audio = O.synthetic_audio(5, 12000, seed=9)
+    names = [f"utt{i}" for i in range(5)]
+    for n, a in zip(names, audio):
+        write(wavs / f"{n}.wav", 22050, (a.numpy() * 32767).astype(np.int16))
+    (tmp_path / "training.txt").write_text("\n".join(f"{n}|text" for n in names[:4]))
+    (tmp_path / "validation.txt").write_text(f"{names[4]}|text")
+    cp = tmp_path / "cp"
+    argv = ["--input_wavs_dir", str(wavs), "--input_training_file", str(tmp_path / "training.txt"),
+            "--input_validation_file", str(tmp_path / "validation.txt"), "--checkpoint_path", str(cp),
+            "--config", str(tmp_path / "config_v1.json"), "--stdout_interval", "1", "--checkpoint_interval", "2",
+            "--validation_interval", "3", "--summary_interval", "1000"]
+    r1 = train_loop.main(argv + ["--training_epochs", "2"])
+    assert r1["final_steps"] == 4 and (cp / "g_00000002").exists() and (cp / "do_00000002").exists()
+    assert (cp / "config.json").exists() and np.isfinite(r1["val_mel_error"]) and np.isfinite(r1["loss_gen_all"])
+    do = torch.load(cp / "do_00000002", map_location="cpu")
+    assert set(do) == {"mpd", "msd", "optim_g", "optim_d", "steps", "epoch"} and do["steps"] == 2
+    # the optimizer state is torch.optim.AdamW's format, parameter order chain(msd, mpd) as UPSTREAM
+    msd, mpd = H.MultiScaleDiscriminator(), H.MultiPeriodDiscriminator()
+    opt = torch.optim.AdamW(list(msd.parameters()) + list(mpd.parameters()), 2e-4, betas=[0.8, 0.99])
+    opt.load_state_dict(do["optim_d"])
+    assert float(opt.state_dict()["state"][0]["step"]) == 3.0     # three D updates before the save at steps == 2
+    g = torch.load(cp / "g_00000002", map_location="cpu")
+    assert set(g) == {"generator"} and "conv_pre.weight_g" in g["generator"]
+    r2 = train_loop.main(argv + ["--training_epochs", "3"])
+    assert r2["final_steps"] == 3 + 2 * 2 and (cp / "g_00000004").exists()

@@ -221,3 +221,35 @@ def test_inference_driver_buckets_by_exact_length():
     got = [[n for n, _ in b] for b in bucket_by_length(items, 2)]
     assert got == [["a", "c"], ["d"], ["b", "e"]]
     assert bucket_by_length([], 4) == []
+
+
+def test_optimizer_state_roundtrip_with_torch_adamw():
+    """train_loop.optimizer_state_dict writes torch.optim.AdamW's own state_dict format (UPSTREAM do_* files): a torch
+    optimizer loads it, and a state_dict produced BY torch (after two real steps) loads back into the flat buffers."""
+    import torch.nn as nn
+    from hifigan_b200.train import FlatParams
+    from hifigan_b200.train_loop import load_optimizer_state_dict, optimizer_state_dict
+    torch.manual_seed(0)
+    net = nn.Sequential(nn.Conv1d(3, 4, 3), nn.Conv1d(4, 2, 5))
+    params = list(net.parameters())
+    opt = torch.optim.AdamW(params, 2e-4, betas=[0.8, 0.99])
+    for _ in range(2):
+        for p in params:
+            p.grad = torch.randn_like(p)
+        opt.step()
+    ref = opt.state_dict()
+    flat = FlatParams(net, "cpu")
+    order = list(reversed(params))                      # any order: UPSTREAM's D optimizer is chain(msd, mpd)
+    opt2 = torch.optim.AdamW(order, 2e-4, betas=[0.8, 0.99])
+    for p in order:
+        p.grad = torch.zeros_like(p)
+    opt2.step()
+    load_optimizer_state_dict(flat, params, ref)
+    assert int(flat.step_dev.item()) == 2
+    sd = optimizer_state_dict(flat, order, 2e-4, (0.8, 0.99))
+    opt2.load_state_dict(sd)                            # torch accepts the format
+    for j, p in enumerate(order):
+        i = params.index(p) if False else [k for k, q in enumerate(params) if q is p][0]
+        assert torch.equal(opt2.state_dict()["state"][j]["exp_avg"], ref["state"][i]["exp_avg"])
+        assert torch.equal(opt2.state_dict()["state"][j]["exp_avg_sq"], ref["state"][i]["exp_avg_sq"])
+        assert float(opt2.state_dict()["state"][j]["step"]) == 2.0
