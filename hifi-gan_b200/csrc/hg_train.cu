@@ -186,36 +186,59 @@ disc_last_bwd_dx_kernel(const __nv_bfloat16* __restrict__ x, const float* __rest
     dx[off + cc] = __float2bfloat16(a);
   }
 }
-// weight half: dw[c][j] += sum_{s,h} dl[s,h] * x[s, h + j - pad, c]; db += sum dl.  One block per channel slab.
+// weight half: dw[c][j] += sum_{s,h} dl[s,h] * x[s, h + j - pad, c]; db += sum dl.
+// Thread = (channel pair, row lane): a block covers 256 channels with two row lanes, blockIdx.y strides over the
+// flat (sequence, position) list, so every thread sees a short chain of independent loads; the two lanes meet in
+// shared memory and issue one atomic per (channel, tap).
 __global__ void __launch_bounds__(256)
 disc_last_bwd_dw_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ dl, int nseq, int h,
                         int h_rows, int c, int k, float* __restrict__ dw, float* __restrict__ db) {
-  __shared__ float red[32];
-  const int cc = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float part[128][17];
+  const int cp = threadIdx.x & 127, lane = threadIdx.x >> 7;
+  const int c0 = blockIdx.x * 256 + cp * 2;
   const int pad = k / 2;
-  const int s0 = blockIdx.y, sstep = gridDim.y;
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  float bsum = 0.f;
-  for (int s = s0; s < nseq; s += sstep) {
-    for (int ho = 0; ho < h; ++ho) {
-      const float d = dl[static_cast<size_t>(s) * h + ho];
-      bsum += d;
-      if (cc < c) {
+  const int total = nseq * h;
+  const int q0 = blockIdx.y * 2 + lane, qstep = gridDim.y * 2;
+  float acc[8][2];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int hi = ho + j - pad;
-          if (j < k && hi >= 0 && hi < h)
-            acc[j] += d * __bfloat162float(x[(static_cast<size_t>(s) * h_rows + hi) * c + cc]);
+  for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0.f;
+  float bsum = 0.f;
+  const bool live = c0 < c;
+  for (int q = q0; q < total; q += qstep) {
+    const int s = q / h, ho = q - s * h;
+    const float d = dl[q];
+    bsum += d;
+    if (live) {
+      const __nv_bfloat16* xs = x + static_cast<size_t>(s) * h_rows * c + c0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int hi = ho + j - pad;
+        if (j < k && hi >= 0 && hi < h) {
+          const float2 v = hg::unpack_bf16x2(*reinterpret_cast<const uint32_t*>(xs + static_cast<size_t>(hi) * c));
+          acc[j][0] += d * v.x;
+          acc[j][1] += d * v.y;
         }
       }
     }
   }
-  if (cc < c)
-    for (int j = 0; j < k; ++j) atomicAdd(dw + cc * k + j, acc[j]);
-  if (blockIdx.x == 0 && db) {
-    // every thread accumulated the same bsum; take one
-    (void)red;
-    if (threadIdx.x == 0) atomicAdd(db, bsum);
+  if (lane == 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { part[cp][2 * j] = acc[j][0]; part[cp][2 * j + 1] = acc[j][1]; }
+    part[cp][16] = bsum;
+  }
+  __syncthreads();
+  if (lane == 0) {
+    if (live) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < k) {
+          atomicAdd(dw + static_cast<size_t>(c0) * k + j, acc[j][0] + part[cp][2 * j]);
+          atomicAdd(dw + static_cast<size_t>(c0 + 1) * k + j, acc[j][1] + part[cp][2 * j + 1]);
+        }
+      }
+    }
+    // every channel pair of a lane accumulated the same bsum; one thread of the first channel block reports it
+    if (blockIdx.x == 0 && cp == 0 && db) atomicAdd(db, bsum + part[0][16]);
   }
 }
 
@@ -553,21 +576,30 @@ struct DiscPackArgs {
 };
 
 // forward pack: fp32 [cout][cin_g][k] -> bf16 [q][cout][cin_tile] (taps in kernel order, groups merged block-diagonally)
-__global__ void pack_disc_fwd_kernel(const float* __restrict__ w, const DiscPackArgs a, __nv_bfloat16* __restrict__ out) {
-  const long long n = static_cast<long long>(a.k) * a.cout * a.cin_tile;
-  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x) {
-    const int ct = static_cast<int>(i % a.cin_tile);
-    const int co = static_cast<int>((i / a.cin_tile) % a.cout);
-    const int q = static_cast<int>(i / (static_cast<long long>(a.cin_tile) * a.cout));
-    const int slot = ct / a.cin_g, own = (co / a.cout_g) % a.merge;
-    float v = 0.f;
-    if (slot == own) v = w[(static_cast<size_t>(co) * a.cin_g + (ct - slot * a.cin_g)) * a.k + a.order[q]];
-    out[i] = __float2bfloat16(v);
+// One block per output channel: its [cin_g][k] row is read once, coalesced, into shared memory; every tap plane is
+// then written as one contiguous run of cin_tile bf16 values (two per thread).
+__global__ void __launch_bounds__(256)
+pack_disc_fwd_kernel(const float* __restrict__ w, const DiscPackArgs a, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ float row[];
+  const int co = blockIdx.x;
+  const int n = a.cin_g * a.k;
+  const float* wr = w + static_cast<size_t>(co) * n;
+  for (int i = threadIdx.x; i < n; i += 256) row[i] = wr[i];
+  __syncthreads();
+  const int lo = ((co / a.cout_g) % a.merge) * a.cin_g;       // this channel's slot inside the merged group tile
+  const int half = a.cin_tile >> 1;
+  for (int idx = threadIdx.x; idx < a.k * half; idx += 256) {
+    const int q = idx / half, ct = (idx - q * half) * 2;
+    const int cl = ct - lo, tap = a.order[q];
+    const float v0 = (cl >= 0 && cl < a.cin_g) ? row[cl * a.k + tap] : 0.f;
+    const float v1 = (cl + 1 >= 0 && cl + 1 < a.cin_g) ? row[(cl + 1) * a.k + tap] : 0.f;
+    *reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(q) * a.cout + co) * a.cin_tile + ct) = hg::pack_bf16x2(v0, v1);
   }
 }
 
 // dgrad (polyphase) pack: fp32 [cout][cin_g][k] -> bf16 [m][rho * cin + ci][cc], cc = dy channel inside the
 // (merged) group tile of ci;  j = rho + pad - stride * (m + shift_min)
+// Generic form (one thread per output element); used when a layer's shape does not tile.
 __global__ void pack_disc_dgrad_kernel(const float* __restrict__ w, const DiscPackArgs a, __nv_bfloat16* __restrict__ out) {
   const long long n = static_cast<long long>(a.nshift) * a.stride * a.cin * a.cout_tile;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x) {
@@ -582,6 +614,38 @@ __global__ void pack_disc_dgrad_kernel(const float* __restrict__ w, const DiscPa
     float v = 0.f;
     if (co / a.cout_g == g && j >= 0 && j < a.k) v = w[(static_cast<size_t>(co) * a.cin_g + (ci - g * a.cin_g)) * a.k + j];
     out[i] = __float2bfloat16(v);
+  }
+}
+// Tiled form: a block owns [tci input channels of one group] x [32 dy channels].  The 32 source runs (tci * k
+// contiguous floats each) are read coalesced into shared memory (odd pitch); every (shift, phase) plane is then
+// written as 64-byte runs along cc, two bf16 per thread, conflict-free.
+__global__ void __launch_bounds__(256)
+pack_disc_dgrad_tiled_kernel(const float* __restrict__ w, const DiscPackArgs a, int tci, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ float sm[];                               // [32][tci * k + 1]
+  const int ci0 = blockIdx.x * tci, cc0 = blockIdx.y * 32;
+  const int g = ci0 / a.cin_g, cil0 = ci0 - g * a.cin_g;
+  const int co_base = (g / a.merge) * a.cout_tile + cc0;
+  const int run = tci * a.k, pitch = run + 1;
+  for (int idx = threadIdx.x; idx < 32 * run; idx += 256) {
+    const int ccl = idx / run, r = idx - ccl * run;
+    const int co = co_base + ccl;
+    sm[ccl * pitch + r] = (co / a.cout_g == g) ? w[(static_cast<size_t>(co) * a.cin_g + cil0) * a.k + r] : 0.f;
+  }
+  __syncthreads();
+  const int planes = a.nshift * a.stride;
+  for (int idx = threadIdx.x; idx < planes * tci * 16; idx += 256) {
+    const int cc2 = (idx & 15) * 2;
+    const int t = idx >> 4;
+    const int ms = t / tci, cil = t - ms * tci;
+    const int m = ms / a.stride, rho = ms - m * a.stride;
+    const int j = rho + a.pad - a.stride * (m + a.shift_min);
+    float v0 = 0.f, v1 = 0.f;
+    if (j >= 0 && j < a.k) {
+      v0 = sm[cc2 * pitch + cil * a.k + j];
+      v1 = sm[(cc2 + 1) * pitch + cil * a.k + j];
+    }
+    *reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(ms) * a.cin + ci0 + cil) * a.cout_tile + cc0 + cc2) =
+        hg::pack_bf16x2(v0, v1);
   }
 }
 
@@ -748,7 +812,11 @@ extern "C" int hg_disc_last_conv_bwd(const void* x, const float* w, const float*
     count();
   }
   if (dw) {
-    dim3 grid((c + 255) / 256, nseq < 32 ? nseq : 32);
+    HG_REQUIRE(c % 2 == 0, "hg_disc_last_conv_bwd: channel count must be even");
+    const int total = nseq * h;
+    int chunks = (total + 31) / 32;          // ~16 positions per thread
+    if (chunks > 256) chunks = 256;
+    dim3 grid((c + 255) / 256, chunks < 1 ? 1 : chunks);
     disc_last_bwd_dw_kernel<<<grid, 256, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(x), dlogit, nseq, h, h_rows,
                                                          c, k, dw, db);
     HG_CHECK_CUDA(cudaGetLastError());
@@ -886,14 +954,24 @@ extern "C" int hg_pack_disc_weight(const float* w_eff, int cout, int cin, int gr
   rc = hg_convtr1d_geometry(k, stride, pad, &a.nshift, &a.shift_min);
   if (rc) return rc;
   if (w_fwd) {
-    pack_disc_fwd_kernel<<<blocks_for(static_cast<long long>(k) * cout * a.cin_tile), 256, 0, S(stream)>>>(
-        w_eff, a, static_cast<__nv_bfloat16*>(w_fwd));
+    const size_t smem = static_cast<size_t>(a.cin_g) * k * sizeof(float);
+    HG_REQUIRE(smem <= 48 * 1024 && a.cin_tile % 2 == 0, "hg_pack_disc_weight: filter row does not fit (cin/groups * k = %d)",
+               a.cin_g * k);
+    pack_disc_fwd_kernel<<<cout, 256, smem, S(stream)>>>(w_eff, a, static_cast<__nv_bfloat16*>(w_fwd));
     HG_CHECK_CUDA(cudaGetLastError());
     count();
   }
   if (w_dgrad) {
-    pack_disc_dgrad_kernel<<<blocks_for(static_cast<long long>(a.nshift) * stride * cin * a.cout_tile), 256, 0,
-                             S(stream)>>>(w_eff, a, static_cast<__nv_bfloat16*>(w_dgrad));
+    int tci = k <= 10 ? 32 : 8;
+    while (tci > 2 && (a.cin_g % tci || cin % tci)) tci >>= 1;
+    const size_t smem = 32 * (static_cast<size_t>(tci) * k + 1) * sizeof(float);
+    if (a.cin_g % tci == 0 && cin % tci == 0 && a.cout_tile % 32 == 0 && smem <= 48 * 1024) {
+      dim3 grid(cin / tci, a.cout_tile / 32);
+      pack_disc_dgrad_tiled_kernel<<<grid, 256, smem, S(stream)>>>(w_eff, a, tci, static_cast<__nv_bfloat16*>(w_dgrad));
+    } else {
+      pack_disc_dgrad_kernel<<<blocks_for(static_cast<long long>(a.nshift) * stride * cin * a.cout_tile), 256, 0,
+                               S(stream)>>>(w_eff, a, static_cast<__nv_bfloat16*>(w_dgrad));
+    }
     HG_CHECK_CUDA(cudaGetLastError());
     count();
   }

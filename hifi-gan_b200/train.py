@@ -101,6 +101,30 @@ class FlatParams:
                                             self.step_dev.data_ptr(), self.lr_dev.data_ptr(), grad_scale, _stream()),
                    "hg_adamw_step")
 
+    def bump_step(self) -> None:
+        """advance the device-side AdamW step counter once per optimizer step (before any adamw_slice of that step)"""
+        self.step_dev.add_(1)
+
+    def adamw_slice(self, lo: int, hi: int, lr: float, betas=(0.8, 0.99), eps: float = 1e-8,
+                    weight_decay: float = 0.01, grad_scale: float = 1.0) -> None:
+        """the same update on elements [lo, hi) of the flat buffers only (after bump_step): lets independent parts of
+        a network update on their own stream lanes as soon as their gradients are complete"""
+        o = 4 * lo
+        _lib.check(_lib.lib().hg_adamw_step(self.p.data_ptr() + o, self.g.data_ptr() + o, self.m.data_ptr() + o,
+                                            self.v.data_ptr() + o, hi - lo, lr, betas[0], betas[1], eps, weight_decay,
+                                            0, self.step_dev.data_ptr(), self.lr_dev.data_ptr(), grad_scale, _stream()),
+                   "hg_adamw_step")
+
+    def span_of(self, module: nn.Module) -> Tuple[int, int]:
+        """[lo, hi) of the flat buffers covered by `module`'s parameters (they must be contiguous in the buffer)"""
+        ids = {id(q) for q in module.parameters()}
+        idx = [i for i, q in enumerate(self.params) if id(q) in ids]
+        if not idx or idx != list(range(idx[0], idx[-1] + 1)):
+            raise RuntimeError("FlatParams.span_of: the module's parameters are not one contiguous run")
+        lo = self.offsets[idx[0]]
+        hi = self.offsets[idx[-1] + 1] if idx[-1] + 1 < len(self.params) else self.numel
+        return lo, hi
+
     def set_lr(self, lr: float) -> None:
         """the learning rate lives in device memory so that a captured step follows a schedule without re-capture;
         call OUTSIDE graph capture (TrainStep does, before every step)"""
@@ -694,6 +718,13 @@ class _SubDiscTrainer:
                 W = self.W_cached
             Ws.append(W)
         here = torch.cuda.current_stream()
+        # the data-gradient filter banks of these weights are packed on the w-lane, beside the forward chain; the
+        # backward waits for that lane before its first data-gradient launch
+        wlane = self.lanes.streams[0]
+        wlane.wait_stream(here)
+        with torch.cuda.stream(wlane):
+            for pi in range(len(parts)):
+                self._pack_dgrad(Ws[pi], pi)
         for pi, (b0, bn) in enumerate(parts):
             W = Ws[pi]
             self.parts.append((b0, bn, W))
@@ -778,8 +809,7 @@ class _SubDiscTrainer:
         _lib.check(L.hg_loss_grad(lg.data_ptr(), 0, (ntot - nr) * h, 1, 0.0, 2.0 / ((ntot - nr) * h), 0.0,
                                   G["dlogit"][nr:].data_ptr(), st))
         here = torch.cuda.current_stream()
-        for pi, (b0, bn, W) in enumerate(self.parts):
-            self._pack_dgrad(W, pi)
+        here.wait_stream(self.lanes.streams[0])     # data-gradient packs (queued by forward on the w-lane)
         self.lanes.fork()     # both lanes join the capture here (a join of a never-forked stream would invalidate it)
         for pi, (b0, bn, W) in enumerate(self.parts):
             if pi == 1:                       # spectral norm: the generated half's chain on the second lane
@@ -812,7 +842,7 @@ class _SubDiscTrainer:
                                   G["dlogit"][nr:].data_ptr(), st))
         b0, bn, W = self.parts[-1] if self.spectral else (self.nreal, self.nb - self.nreal, self.parts[0][2])
         part = len(self.parts) - 1
-        self._pack_dgrad(W, part)
+        torch.cuda.current_stream().wait_stream(self.lanes.streams[0])    # data-gradient packs (see forward)
         self._backward_part(L, G, W, self.nreal, self.nb - self.nreal, want_wgrad=False, fm=True,
                             dy_audio=dy_audio, accumulate=False, nfm=nfm, part=part)
 
@@ -940,19 +970,23 @@ class DiscriminatorTrainer:
         self.subs_s = [_SubDiscTrainer(d, device) for d in msd.discriminators]
         self.subs = self.subs_p + self.subs_s
         self.nslots = 12
-        self.acc = torch.zeros(len(self.subs) * self.nslots, dtype=torch.float32, device=device)
+        # raw loss sums of the discriminator-step forward / of the generator-step forward
+        self.acc_d = torch.zeros(len(self.subs) * self.nslots, dtype=torch.float32, device=device)
+        self.acc_g = torch.zeros_like(self.acc_d)
         self.pooled: List[torch.Tensor] = []
         self._inv_counts: Dict[Tuple[int, int], torch.Tensor] = {}
         self.lanes = _Lanes(len(self.subs), device)      # one stream per sub-discriminator: they are independent
+        self.spans = [self.flat.span_of(d) for d in list(mpd.discriminators) + list(msd.discriminators)]
+        if self.spans[0][0] != 0 or self.spans[-1][1] != self.flat.numel or any(
+                a[1] != b[0] for a, b in zip(self.spans, self.spans[1:])):
+            raise RuntimeError("DiscriminatorTrainer: sub-discriminator parameter spans do not tile the flat buffer")
 
-    def forward(self, y: torch.Tensor, y_hat: torch.Tensor) -> None:
-        """y, y_hat fp32 [B,1,T] (or [B,T]).  Runs every sub-discriminator on (y ++ y_hat) and accumulates the raw
-        loss sums (self.acc)."""
+    def _inputs(self, y: torch.Tensor, y_hat: torch.Tensor) -> int:
+        """(real ++ generated) audio and its AvgPool1d(4,2,2) pyramid for the scale discriminators"""
         L = _lib.lib()
         b = y.shape[0]
         ycat = torch.cat([y.reshape(b, -1), y_hat.reshape(b, -1)], 0).contiguous().float()
         self.b, self.t = b, ycat.shape[1]
-        self.acc.zero_()
         self.pooled = [ycat]
         cur = ycat
         for i in range(1, len(self.subs_s)):
@@ -961,17 +995,58 @@ class DiscriminatorTrainer:
             _lib.check(L.hg_avgpool_4_2_2_fwd(cur.data_ptr(), 2 * b, t, nxt.data_ptr(), _stream()), "hg_avgpool_4_2_2_fwd")
             self.pooled.append(nxt)
             cur = nxt
+        return b
+
+    def _input_of(self, i: int) -> torch.Tensor:
+        return self.pooled[0] if i < len(self.subs_p) else self.pooled[i - len(self.subs_p)]
+
+    def run_phases(self, y: torch.Tensor, y_hat: torch.Tensor, dy_audio: torch.Tensor, update: bool, lr: float, betas,
+                   world: int = 1, allreduce=None) -> Tuple[Dict[str, torch.Tensor], Dict[str, torch.Tensor]]:
+        """The discriminator step and the discriminator half of the generator step of ONE training step, with every
+        sub-discriminator running its whole chain on its own lane:
+            forward -> loss sums -> backward (parameter gradients) -> AdamW on its own slice of the flat buffers
+            -> forward with the updated weights -> loss sums -> data gradient into dy_audio.
+        The lanes only meet at the end (and, data-parallel, around the gradient all-reduce), so a short chain (a period
+        discriminator) is already in its generator-step forward while the longest one (the spectral-norm scale) is
+        still in its backward.  Same arithmetic as forward / backward_d / adamw / forward / backward_g in sequence.
+        Returns (discriminator-step losses, generator-step losses); dy_audio fp32 [B][T] is ADDED to."""
+        L = _lib.lib()
+        b = self._inputs(y, y_hat)
+        self.acc_d.zero_()
+        self.acc_g.zero_()
+        self.flat.g.zero_()                 # every parameter-gradient kernel of the sub-discriminators accumulates
+        if update:
+            self.flat.bump_step()
+        grads = [dy_audio] + [torch.zeros(b, p.shape[1], dtype=torch.float32, device=self.device)
+                              for p in self.pooled[1:]]
+        np_ = len(self.subs_p)
         self.lanes.fork()
         for i, sd in enumerate(self.subs):
-            inp = ycat if i < len(self.subs_p) else self.pooled[i - len(self.subs_p)]
             with self.lanes.lane(i):
-                sd.forward(inp, b)
-                sd.loss_terms(self.acc, i * self.nslots)
+                sd.forward(self._input_of(i), b)
+                sd.loss_terms(self.acc_d, i * self.nslots)
+                sd.backward_d()
+        if world > 1:
+            self.lanes.join()
+            allreduce(self.flat)
+            self.lanes.fork()
+        for i, sd in enumerate(self.subs):
+            with self.lanes.lane(i):
+                if update:
+                    self.flat.adamw_slice(self.spans[i][0], self.spans[i][1], lr, betas, grad_scale=1.0 / world)
+                    sd.invalidate()
+                sd.forward(self._input_of(i), b)
+                sd.loss_terms(self.acc_g, i * self.nslots)
+                sd.backward_g(grads[0] if i < np_ else grads[i - np_], [2.0 / n for n in sd.numel_fmaps(b)])
         self.lanes.join()
+        for i in reversed(range(1, len(grads))):
+            _lib.check(L.hg_avgpool_4_2_2_bwd(grads[i].data_ptr(), b, grads[i - 1].shape[1], grads[i - 1].data_ptr(),
+                                              _stream()), "hg_avgpool_4_2_2_bwd")
+        return self.losses(self.acc_d), self.losses(self.acc_g)
 
-    def losses(self) -> Dict[str, torch.Tensor]:
-        """loss values from the accumulated sums (device tensors, no host sync)."""
-        a = self.acc.view(len(self.subs), self.nslots)
+    def losses(self, acc: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """loss values from the accumulated sums of one forward (device tensors, no host sync)."""
+        a = acc.view(len(self.subs), self.nslots)
         out = {}
         np_ = len(self.subs_p)
         key = (self.b, self.t)
@@ -991,35 +1066,6 @@ class DiscriminatorTrainer:
         out["loss_fm_f"], out["loss_fm_s"] = terms[:np_, 3:].sum(), terms[np_:, 3:].sum()
         return out
 
-    def backward_d(self) -> None:
-        self.flat.g.zero_()                 # every parameter-gradient kernel of the sub-discriminators accumulates
-        self.lanes.fork()
-        for i, sd in enumerate(self.subs):
-            with self.lanes.lane(i):
-                sd.backward_d()
-        self.lanes.join()
-
-    def backward_g(self, dy_audio: torch.Tensor) -> None:
-        """adds d(loss_gen + loss_fm)/d y_hat into dy_audio fp32 [B][T]."""
-        L = _lib.lib()
-        b = self.b
-        # MSD: scale i sees the (i times) pooled signal; chain the pooling backward from the coarsest scale up
-        grads = [dy_audio] + [torch.zeros(b, p.shape[1], dtype=torch.float32, device=self.device)
-                              for p in self.pooled[1:]]
-        self.lanes.fork()
-        # every lane ADDS into its audio-gradient buffer with atomics, so the period discriminators and scale 0 may
-        # share dy_audio
-        for i, sd in enumerate(self.subs_p):
-            with self.lanes.lane(i):
-                sd.backward_g(dy_audio, [2.0 / n for n in sd.numel_fmaps(b)])
-        for i, sd in enumerate(self.subs_s):
-            with self.lanes.lane(len(self.subs_p) + i):
-                sd.backward_g(grads[i], [2.0 / n for n in sd.numel_fmaps(b)])
-        self.lanes.join()
-        for i in reversed(range(1, len(grads))):
-            _lib.check(L.hg_avgpool_4_2_2_bwd(grads[i].data_ptr(), b, grads[i - 1].shape[1], grads[i - 1].data_ptr(),
-                                              _stream()), "hg_avgpool_4_2_2_bwd")
-
 
 # ------------------------------------------------------------------------------------------------ the step
 class TrainStep:
@@ -1038,6 +1084,7 @@ class TrainStep:
         self.lr = h.learning_rate
         self.betas = (h.adam_b1, h.adam_b2)
         self.pg = process_group
+        self.mel_lane = torch.cuda.Stream(device=device)
         self.world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
@@ -1058,16 +1105,6 @@ class TrainStep:
             plan = torch_mels[key]
         return plan
 
-    def _mel(self, y2d: torch.Tensor) -> torch.Tensor:
-        """log-mel of the generated audio: the kernel behind mel_spectrogram, without the public function's lazy
-        range-warning bookkeeping (event queries are not allowed while a CUDA graph is capturing; the generator
-        output is tanh-bounded anyway)."""
-        plan = self._mel_plan()
-        b, t = y2d.shape
-        out = torch.empty(b, self.h.num_mels, plan.frames(t), dtype=torch.float32, device=self.device)
-        _lib.check(_lib.lib().hg_mel_fwd(plan.handle, y2d.data_ptr(), b, t, out.data_ptr(), 0, _stream()), "hg_mel_fwd")
-        return out
-
     def step(self, x: torch.Tensor, y: torch.Tensor, y_mel: torch.Tensor, update: bool = True) -> Dict[str, torch.Tensor]:
         """x [B,80,F] input mel, y [B,1,T] audio, y_mel [B,80,F] loss mel.  Returns the loss tensors (device)."""
         L = _lib.lib()
@@ -1082,37 +1119,34 @@ class TrainStep:
         y_g = self.G.forward(x)                                # [B,1,T]
         y_g2 = y_g.view(b, -1)
         out: Dict[str, torch.Tensor] = {}
-        # ---- discriminator step
-        self.D.forward(y2, y_g2)
-        dl = self.D.losses()
-        out["loss_disc_f"], out["loss_disc_s"] = dl["loss_disc_f"], dl["loss_disc_s"]
-        out["loss_disc_all"] = dl["loss_disc_f"] + dl["loss_disc_s"]
-        self.D.backward_d()
-        self._allreduce(self.D.flat)
-        if update:
-            self.D.flat.adamw(self.lr, self.betas, grad_scale=1.0 / self.world)
-            for sd in self.D.subs:
-                sd.invalidate()
-        # ---- generator step (through the updated discriminators)
-        mel_g = self._mel(y_g2)
+        # ---- mel loss of the generated audio and its gradient: its own lane, beside the discriminator work
+        plan = self._mel_plan()
+        n_frames = plan.frames(y_g2.shape[1])
+        mel_g = torch.empty(b, h.num_mels, n_frames, dtype=torch.float32, device=self.device)
         n_mel = mel_g.numel()
         acc = torch.zeros(1, dtype=torch.float32, device=self.device)
         ym = y_mel.contiguous().float()
-        _lib.check(L.hg_loss_sum(ym.data_ptr(), mel_g.data_ptr(), n_mel, 0, 0.0, acc.data_ptr(), st), "hg_loss_sum")
-        out["loss_mel"] = acc[0] / n_mel * 45
         dmel = torch.empty_like(mel_g)
-        _lib.check(L.hg_loss_grad(mel_g.data_ptr(), ym.data_ptr(), n_mel, 0, 0.0, 45.0 / n_mel, 0.0, dmel.data_ptr(), st),
-                   "hg_loss_grad")
-        dy = torch.zeros(b, y_g2.shape[1], dtype=torch.float32, device=self.device)
-        plan = self._mel_plan()
-        _lib.check(L.hg_mel_bwd(plan.handle, y_g2.data_ptr(), dmel.data_ptr(), b, y_g2.shape[1], dy.data_ptr(), st),
-                   "hg_mel_bwd")
-        self.D.forward(y2, y_g2)
-        gl = self.D.losses()
+        dy = torch.zeros(b, y_g2.shape[1], dtype=torch.float32, device=self.device)   # every producer ADDS into it
+        here = torch.cuda.current_stream()
+        self.mel_lane.wait_stream(here)
+        with torch.cuda.stream(self.mel_lane):
+            ms = _stream()
+            _lib.check(L.hg_mel_fwd(plan.handle, y_g2.data_ptr(), b, y_g2.shape[1], mel_g.data_ptr(), 0, ms), "hg_mel_fwd")
+            _lib.check(L.hg_loss_sum(ym.data_ptr(), mel_g.data_ptr(), n_mel, 0, 0.0, acc.data_ptr(), ms), "hg_loss_sum")
+            _lib.check(L.hg_loss_grad(mel_g.data_ptr(), ym.data_ptr(), n_mel, 0, 0.0, 45.0 / n_mel, 0.0, dmel.data_ptr(),
+                                      ms), "hg_loss_grad")
+            _lib.check(L.hg_mel_bwd(plan.handle, y_g2.data_ptr(), dmel.data_ptr(), b, y_g2.shape[1], dy.data_ptr(), ms),
+                       "hg_mel_bwd")
+        # ---- discriminator step, then the generator step's pass through the updated discriminators
+        dl, gl = self.D.run_phases(y2, y_g2, dy, update, self.lr, self.betas, self.world, self._allreduce)
+        here.wait_stream(self.mel_lane)
+        out["loss_mel"] = acc[0] / n_mel * 45
+        out["loss_disc_f"], out["loss_disc_s"] = dl["loss_disc_f"], dl["loss_disc_s"]
+        out["loss_disc_all"] = dl["loss_disc_f"] + dl["loss_disc_s"]
         for k in ("loss_gen_f", "loss_gen_s", "loss_fm_f", "loss_fm_s"):
             out[k] = gl[k]
         out["loss_gen_all"] = gl["loss_gen_s"] + gl["loss_gen_f"] + gl["loss_fm_s"] + gl["loss_fm_f"] + out["loss_mel"]
-        self.D.backward_g(dy)
         self.dy_audio = dy
         self.G.backward(dy)
         self._allreduce(self.G.flat)

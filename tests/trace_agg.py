@@ -8,16 +8,22 @@ import sys
 def main(path, top=3):
     ev = json.load(open(path))
     ev.sort(key=lambda e: e["ts"])
-    ad = [i for i, e in enumerate(ev) if "adamw" in e["n"]]
-    step = ev[ad[1] + 1:ad[3] + 1]
+    # one step = the kernels between two generator AdamW launches (the generator's update is the last kernel of a
+    # step, on the main stream; the sub-discriminators update slice by slice on their own lanes)
+    main = [e for e in ev if "adamw" in e["n"]][-1]["s"]
+    ad = [i for i, e in enumerate(ev) if "adamw" in e["n"] and e["s"] == main]
+    step = ev[ad[0] + 1:ad[1] + 1]
     t0 = step[0]["ts"]
     t1 = max(e["ts"] + e["dur"] for e in step)
     print(f"step span {(t1 - t0) / 1e3:.2f} ms, {len(step)} kernels, summed durations {sum(e['dur'] for e in step) / 1e3:.2f} ms")
-    for label, name in [("G fwd end", "conv_post_tanh_kernel"), ("D bwd start", "loss_grad_kernel"), ("adamw D", "adamw_kernel"),
+    for label, name in [("G fwd end", "conv_post_tanh_kernel"), ("D bwd start", "loss_grad_kernel"), ("first adamw D", "adamw_kernel"),
                         ("mel_bwd", "mel_bwd_kernel"), ("G bwd start", "conv_post_bwd_dx")]:
         x = next((e["ts"] for e in step if name in e["n"]), None)
         if x is not None:
             print(f"  {label:14s} at {(x - t0) / 1e3:6.2f} ms")
+    dad = [e for e in step if "adamw" in e["n"] and e["s"] != main]
+    if dad:
+        print(f"  last adamw D   at {(dad[-1]['ts'] - t0) / 1e3:6.2f} ms")
     streams = collections.defaultdict(list)
     for e in step:
         streams[e["s"]].append(e)
