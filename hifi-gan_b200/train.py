@@ -354,21 +354,28 @@ class GeneratorTrainer:
         L = _lib.lib()
         e, gen = self.eng, self.gen
         lanes = self.lanes
-        e.refresh()
         b, c, frames = x.shape
         xin = x.contiguous().float()
         ws = self._workspace(b, frames)
         self.cur = ws
+        main = torch.cuda.current_stream()
         lanes.fork()
-        with lanes.lane(self.W_LANE):            # the data-gradient filter banks are not needed before backward
-            for gl in self.g_ups + [x_ for blk in self.g_blocks for x_ in blk]:
-                gl.pack(L)
+        # after an optimizer update every filter bank is re-folded and re-packed (~80 small launches): spread them over
+        # the lanes while the main stream packs conv_pre / conv_post and runs the first conv
+        for idx, pc in enumerate(e.ups + [x_ for blk in e.blocks for x_ in blk]):
+            with lanes.lane(idx):
+                pc.refresh()
+        e.refresh()                              # what is left: conv_pre, conv_post
         _lib.check(L.hg_ncl_to_nlc(xin.data_ptr(), b, c, frames, e.pre.cin_p, ws["mel"].data_ptr(), 0, 0.0, _stream()),
                    "hg_ncl_to_nlc")
         _conv(L, ws["mel"], e.pre, b, frames, out_act=ws["pre_act"])
+        lanes.join()
+        lanes.streams[self.W_LANE].wait_stream(main)
+        with lanes.lane(self.W_LANE):            # the data-gradient filter banks are not needed before backward
+            for gl in self.g_ups + [x_ for blk in self.g_blocks for x_ in blk]:
+                gl.pack(L)
         cur, t = ws["pre_act"], frames
         nk = gen.num_kernels
-        main = torch.cuda.current_stream()
         for i, up in enumerate(e.ups):
             st = ws["stages"][i]
             _conv(L, cur, up, b, t, out_raw=st["x_raw"], out_act=st["xa0"])
@@ -569,6 +576,7 @@ class _SubDiscTrainer:
         # data-gradient filter banks), on two lanes; lane 0 is the parameter-gradient lane of this sub-discriminator
         self.bwd_parts = [self.bwd] + ([[_DiscBwdLayer(l, device) for l in self.mids]] if self.spectral else [])
         self.lanes = _Lanes(2, device)
+        self.prep = _Lanes(4, device)          # weight preparation: independent layers side by side
         self.ws = {}
         nmax = max(l.k * l.cout * l.cin_tile for l in self.mids)
         self.dwp = torch.zeros(nmax, dtype=torch.float32, device=device)
@@ -586,12 +594,10 @@ class _SubDiscTrainer:
         self.disc.__dict__.pop("_hg_wcache", None)      # the module API's own pack cache (inference-side forward)
 
     # ---- weights -------------------------------------------------------------------------------------------
-    def _weights(self, part: int):
+    def _weights(self, part: int, only_buffers: bool = False):
         """effective fp32 weights + forward GEMM packs of every layer, into per-part persistent buffers.
         weight_norm layers: hg_fold_weight_norm + hg_pack_disc_weight.  spectral_norm layers: one power iteration
         per call in train mode (torch ops on the u / v buffers, exactly like one reference forward)."""
-        L = _lib.lib()
-        st = _stream()
         bufs = self.wbufs.get(part)
         if bufs is None:
             bufs = {"eff": [], "fwd": []}
@@ -606,35 +612,43 @@ class _SubDiscTrainer:
                 else:
                     bufs["fwd"].append(None)
             self.wbufs[part] = bufs
-        ws = {"eff": bufs["eff"], "fwd": bufs["fwd"], "sn": []}
-        for li, m in enumerate(self.mods):
-            eff = bufs["eff"][li]
-            if hasattr(m, "weight_orig"):
-                wo = m.weight_orig
-                rows, cols = wo.shape[0], wo.numel() // wo.shape[0]
-                snb = bufs.setdefault("sn", {}).get(li)
-                if snb is None:
-                    f32 = lambda n: torch.empty(n, dtype=torch.float32, device=self.device)
-                    snb = (f32(rows), f32(cols), f32(1), f32(rows + cols + 4))     # u, v, sigma of this call; workspace
-                    bufs["sn"][li] = snb
-                # one power iteration per call in train mode, u / v buffers updated in place (hg_spectral_norm_fwd);
-                # the copies are what the backward of THIS call's weights needs (the next call moves u, v on)
-                _lib.check(L.hg_spectral_norm_fwd(wo.data_ptr(), m.weight_u.data_ptr(), m.weight_v.data_ptr(), rows,
-                                                  cols, 1 if m.training else 0, eff.data_ptr(), snb[2].data_ptr(),
-                                                  snb[0].data_ptr(), snb[1].data_ptr(), snb[3].data_ptr(), st),
-                           "hg_spectral_norm_fwd")
-                ws["sn"].append(snb)
-            else:
-                g, v = _g_v(m)
-                _lib.check(L.hg_fold_weight_norm(v.data_ptr(), 0 if g is None else g.data_ptr(), v.shape[0],
-                                                 v.numel() // v.shape[0], eff.data_ptr(), st), "hg_fold_weight_norm")
-                ws["sn"].append(None)
-            if 1 <= li <= len(self.mids):
-                layer = self.mids[li - 1]
-                _lib.check(L.hg_pack_disc_weight(eff.data_ptr(), layer.cout, layer.cin, layer.groups, layer.merge,
-                                                 layer.k, layer.stride, layer.pad, bufs["fwd"][li].data_ptr(), 0, st),
-                           "hg_pack_disc_weight")
+        ws = {"eff": bufs["eff"], "fwd": bufs["fwd"], "sn": [None] * len(self.mods)}
+        if only_buffers:
+            return ws
+        for li in range(len(self.mods)):
+            self._weights_layer(ws, bufs, li)
         return ws
+
+    def _weights_layer(self, ws, bufs, li: int) -> None:
+        """fold (weight norm) or power-iterate (spectral norm) layer li and pack its forward filter bank"""
+        L = _lib.lib()
+        st = _stream()
+        m = self.mods[li]
+        eff = bufs["eff"][li]
+        if hasattr(m, "weight_orig"):
+            wo = m.weight_orig
+            rows, cols = wo.shape[0], wo.numel() // wo.shape[0]
+            snb = bufs.setdefault("sn", {}).get(li)
+            if snb is None:
+                f32 = lambda n: torch.empty(n, dtype=torch.float32, device=self.device)
+                snb = (f32(rows), f32(cols), f32(1), f32(rows + cols + 4))     # u, v, sigma of this call; workspace
+                bufs["sn"][li] = snb
+            # one power iteration per call in train mode, u / v buffers updated in place (hg_spectral_norm_fwd);
+            # the copies are what the backward of THIS call's weights needs (the next call moves u, v on)
+            _lib.check(L.hg_spectral_norm_fwd(wo.data_ptr(), m.weight_u.data_ptr(), m.weight_v.data_ptr(), rows,
+                                              cols, 1 if m.training else 0, eff.data_ptr(), snb[2].data_ptr(),
+                                              snb[0].data_ptr(), snb[1].data_ptr(), snb[3].data_ptr(), st),
+                       "hg_spectral_norm_fwd")
+            ws["sn"][li] = snb
+        else:
+            g, v = _g_v(m)
+            _lib.check(L.hg_fold_weight_norm(v.data_ptr(), 0 if g is None else g.data_ptr(), v.shape[0],
+                                             v.numel() // v.shape[0], eff.data_ptr(), st), "hg_fold_weight_norm")
+        if 1 <= li <= len(self.mids):
+            layer = self.mids[li - 1]
+            _lib.check(L.hg_pack_disc_weight(eff.data_ptr(), layer.cout, layer.cin, layer.groups, layer.merge,
+                                             layer.k, layer.stride, layer.pad, bufs["fwd"][li].data_ptr(), 0, st),
+                       "hg_pack_disc_weight")
 
     def _geometry(self, nb: int, t: int):
         key = (nb, t)
@@ -705,18 +719,22 @@ class _SubDiscTrainer:
         period = self.period
         parts = [(0, nb)] if not self.spectral else [(0, nreal), (nreal, nb - nreal)]
         self.parts = []
-        Ws = []
-        for pi in range(len(parts)):
-            # weight_norm layers: the packs stay valid until the next optimizer update (the G-step forward of one
-            # step and the D-step forward of the next see the same weights); spectral norm moves on every call, and
-            # its second part's power iteration continues from the first's
-            if self.spectral or not self.fwd_valid:
-                W = self._weights(pi)
-                self.W_cached = W
-                self.fwd_valid = True
-            else:
-                W = self.W_cached
-            Ws.append(W)
+        # weight_norm layers: the packs stay valid until the next optimizer update (the G-step forward of one step
+        # and the D-step forward of the next see the same weights); spectral norm moves on every call, and its
+        # second part's power iteration continues from the first's.  The layers are independent of each other, so
+        # their fold / power-iteration / pack chains are spread over the prep lanes (part 0 before part 1 per layer).
+        if self.spectral or not self.fwd_valid:
+            Ws = [self._weights(pi, only_buffers=True) for pi in range(len(parts))]
+            self.prep.fork()
+            for li in range(len(self.mods)):
+                with self.prep.lane(li):
+                    for pi, W in enumerate(Ws):
+                        self._weights_layer(W, self.wbufs[pi], li)
+            self.prep.join()
+            self.W_cached = Ws[-1]
+            self.fwd_valid = True
+        else:
+            Ws = [self.W_cached]
         here = torch.cuda.current_stream()
         # the data-gradient filter banks of these weights are packed on the w-lane, beside the forward chain; the
         # backward waits for that lane before its first data-gradient launch
