@@ -369,16 +369,25 @@ disc_first_bwd_kernel(const float* __restrict__ y, const float* __restrict__ w, 
       }
     }
   }
-  if (dw && rh < rgroups) {
+  if (dw) {
+    // the row groups of the block meet in shared memory (the staging buffers are free now): one atomic per
+    // (channel, tap | bias) per block instead of one per row group — the atomics were the cost of this kernel
+    __syncthreads();
+    float* red = reinterpret_cast<float*>(smb);                 // [rgroups][cout][kFirstK]
+    if (rh < rgroups) {
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int co = cg * 4 + a;
+      for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int j = jg * 4 + c;
-        if (j < k) atomicAdd(dw + co * k + j, acc[a][c]);
-        else if (j == k) atomicAdd(db + co, acc[a][c]);
-      }
+        for (int c = 0; c < 4; ++c) red[(rh * cout + cg * 4 + a) * kFirstK + jg * 4 + c] = acc[a][c];
+    }
+    __syncthreads();
+    for (int i = tid; i < cout * kFirstK; i += 256) {
+      const int co = i / kFirstK, j = i % kFirstK;
+      if (j > k) continue;
+      float v = 0.f;
+      for (int g = 0; g < rgroups; ++g) v += red[g * cout * kFirstK + i];
+      if (j < k) atomicAdd(dw + co * k + j, v);
+      else atomicAdd(db + co, v);
     }
   }
 }
