@@ -139,8 +139,14 @@ class _Lanes:
     queued on the current stream, join() makes the current stream wait for every lane; both are event waits, so
     under CUDA-graph capture the lanes become parallel branches of the graph."""
 
-    def __init__(self, n: int, device):
-        self.streams = [torch.cuda.Stream(device=device) for _ in range(n)] if torch.cuda.is_available() else []
+    def __init__(self, n: int, device, priorities=None):
+        """priorities[i]: CUDA stream priority of lane i (-1 = high, 0 = default / low).  The chains a step waits for
+        (forward, data gradients) run on high-priority lanes, parameter-gradient and packing work on low-priority
+        ones: when both have thread blocks pending, the critical chain's blocks are placed first.  Captured into the
+        step's CUDA graph as kernel-node priorities."""
+        pr = priorities if priorities is not None else [0] * n
+        self.streams = ([torch.cuda.Stream(device=device, priority=pr[i]) for i in range(n)]
+                        if torch.cuda.is_available() else [])
 
     def fork(self) -> None:
         main = torch.cuda.current_stream()
@@ -276,7 +282,7 @@ class GeneratorTrainer:
         # stream lanes: 0 .. nk-2 = MRF branches beside the main stream, W_LANE + j = weight-gradient work of branch j
         nk = gen.num_kernels
         self.W_LANE = max(1, nk - 1)
-        self.lanes = _Lanes(self.W_LANE + nk, device)
+        self.lanes = _Lanes(self.W_LANE + nk, device, [-1] * self.W_LANE + [0] * nk)
         post = gen.conv_post
         self.post_dw = torch.zeros(e.post_cin_p, post.kernel_size[0], dtype=torch.float32, device=device)
         self.post_db = torch.zeros(1, dtype=torch.float32, device=device)
@@ -575,8 +581,8 @@ class _SubDiscTrainer:
         # the spectral-norm scale runs its real / generated halves as two parts with their own sigma (and their own
         # data-gradient filter banks), on two lanes; lane 0 is the parameter-gradient lane of this sub-discriminator
         self.bwd_parts = [self.bwd] + ([[_DiscBwdLayer(l, device) for l in self.mids]] if self.spectral else [])
-        self.lanes = _Lanes(2, device)
-        self.prep = _Lanes(4, device)          # weight preparation: independent layers side by side
+        self.lanes = _Lanes(2, device, [0, -1])      # 0: parameter-gradient lane, 1: second data-gradient chain
+        self.prep = _Lanes(4, device, [-1] * 4)      # weight preparation: independent layers side by side
         self.ws = {}
         nmax = max(l.k * l.cout * l.cin_tile for l in self.mids)
         self.dwp = torch.zeros(nmax, dtype=torch.float32, device=device)
@@ -993,7 +999,7 @@ class DiscriminatorTrainer:
         self.acc_g = torch.zeros_like(self.acc_d)
         self.pooled: List[torch.Tensor] = []
         self._inv_counts: Dict[Tuple[int, int], torch.Tensor] = {}
-        self.lanes = _Lanes(len(self.subs), device)      # one stream per sub-discriminator: they are independent
+        self.lanes = _Lanes(len(self.subs), device, [-1] * len(self.subs))   # one per sub-discriminator
         self.spans = [self.flat.span_of(d) for d in list(mpd.discriminators) + list(msd.discriminators)]
         if self.spans[0][0] != 0 or self.spans[-1][1] != self.flat.numel or any(
                 a[1] != b[0] for a, b in zip(self.spans, self.spans[1:])):
@@ -1103,6 +1109,7 @@ class TrainStep:
         self.betas = (h.adam_b1, h.adam_b2)
         self.pg = process_group
         self.mel_lane = torch.cuda.Stream(device=device)
+        self.capture_stream = torch.cuda.Stream(device=device, priority=-1)
         self.world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
@@ -1199,7 +1206,9 @@ class TrainStep:
             try:
                 g = torch.cuda.CUDAGraph()
                 # thread_local: the NCCL watchdog thread of a data-parallel run may touch the CUDA API meanwhile
-                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                # captured on a high-priority stream: the main chain (generator forward / data gradients) outranks
+                # the parameter-gradient lanes
+                with torch.cuda.graph(g, stream=self.capture_stream, capture_error_mode="thread_local"):
                     out = self.step(sx, sy, sm)
                 entry = (g, sx, sy, sm, out)
             except Exception as e:  # noqa: BLE001
