@@ -131,6 +131,21 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------- CPU baseline (oracle)
+def measured_traffic(workload: str, n_conv: int):
+    """DRAM bytes (read + write) per conv launch, averaged over the step's conv launches, from the committed ncu
+    capture of this same workload (profiles/r01_traffic.json; never measured under the timed run).  None when no
+    capture of this workload / launch count is on file."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+    except (OSError, ValueError):
+        return None
+    if d.get("workload") != workload or d.get("conv_launches") != n_conv:
+        return None
+    return d["per_launch_avg_bytes"]
+
+
 def cpu_generator_baseline(version: str, frames: int, batch: int, steps: int, warmup: int):
     """The oracle port (torch CPU fp32 = the very ops the reference's CPU path runs) on a bounded sample."""
     from oracle import hifigan_oracle as O   # the timed CPU implementation (allowed here: cpu_baseline leg)
@@ -434,7 +449,7 @@ def run_ours(args, rank, world, local_rank):
         "roofline": {"bound": "tensor", "kernel": "conv1d_tc_kernel + resblock_pair_kernel (tcgen05 implicit GEMM)",
                      "launches_per_step": n_conv,
                      "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["tflops"], "traffic": None,
+                     "frac": achieved / peaks["tflops"], "traffic": measured_traffic(args.workload, n_conv),
                      "avg_launch_ms": conv_ms / n_conv, "flop_per_launch_avg": conv_flops / n_conv,
                      "peak_source": peaks["source"]},
     }

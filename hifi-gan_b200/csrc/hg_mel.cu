@@ -28,12 +28,13 @@ struct hg_mel_plan {
   float* window;     // [n_fft]
   float2* tw512;     // [512]  exp(-2*pi*i*m/512)
   float2* tw1024;    // [513]  exp(-2*pi*i*k/1024)
+  float2* tw_n;      // [n_fft] (cos, sin)(2*pi*n/n_fft): the direct-DFT path of every other n_fft
   int* mel_start;    // [num_mels] first rFFT bin with a non-zero weight
   int* mel_off;      // [num_mels+1] CSR offsets into mel_w
   float* mel_w;      // [nnz]
   // host copies (CPU emulation for tests, and geometry queries)
   std::vector<float> h_window;
-  std::vector<float2> h_tw512, h_tw1024;
+  std::vector<float2> h_tw512, h_tw1024, h_tw_n;
   std::vector<int> h_mel_start, h_mel_off;
   std::vector<float> h_mel_w;
 };
@@ -235,6 +236,68 @@ __global__ void __launch_bounds__(kMelThreads) mel_kernel(const MelArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Any other n_fft (the reference's other callers pass n_fft = a layer's kernel size at sr 16000,
+// src/speech_distillation/lightning_model.py:513-522, custom_layers.py:138-161): one block per frame, direct DFT
+// over a shared-memory twiddle table.  O(n_fft^2 / 2) per frame — a general-purpose path, not the tuned one.
+// Per-bin and per-mel phases are __host__ __device__ so hg_mel_emulate_host runs the same arithmetic.
+__host__ __device__ inline float dft_bin_power(int k, int n_fft, const float* xw, const float2* tw) {
+  float ar = 0.f, ai = 0.f;
+  int idx = 0;                                  // (k * n) mod n_fft, advanced incrementally
+  for (int n = 0; n < n_fft; ++n) {
+    const float2 c = tw[idx];
+    ar += xw[n] * c.x;
+    ai -= xw[n] * c.y;
+    idx += k;
+    if (idx >= n_fft) idx -= n_fft;
+  }
+  return ar * ar + ai * ai;
+}
+__host__ __device__ inline float mel_bin_log(int m, const float* power, const int* mel_start, const int* mel_off,
+                                             const float* mel_w) {
+  const int k0 = mel_start[m], o0 = mel_off[m], cnt = mel_off[m + 1] - o0;
+  float acc = 0.f;
+  for (int i = 0; i < cnt; ++i) acc += mel_w[o0 + i] * power[k0 + i];
+  return logf(fmaxf(acc, 1e-5f));
+}
+
+__global__ void __launch_bounds__(256)
+mel_dft_kernel(const float* __restrict__ y, int t, int frames, int n_fft, int hop, int pad, int num_mels,
+               const float* __restrict__ window, const float2* __restrict__ twiddle, const int* __restrict__ mel_start,
+               const int* __restrict__ mel_off, const float* __restrict__ mel_w, float* __restrict__ out,
+               float* __restrict__ minmax) {
+  extern __shared__ __align__(16) uint8_t smg[];
+  float2* tw = reinterpret_cast<float2*>(smg);                  // [n_fft]
+  float* xw = reinterpret_cast<float*>(tw + n_fft);             // [n_fft]
+  float* power = xw + n_fft;                                    // [n_fft / 2 + 1]
+  const int f = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const float* yb = y + static_cast<size_t>(b) * t;
+  float vmin = INFINITY, vmax = -INFINITY;
+  for (int n = tid; n < n_fft; n += 256) {
+    const float v = yb[reflect_index(f * hop + n - pad, t)];
+    vmin = fminf(vmin, v);
+    vmax = fmaxf(vmax, v);
+    xw[n] = v * window[n];
+    tw[n] = twiddle[n];
+  }
+  if (minmax) {
+    for (int o = 16; o > 0; o >>= 1) {
+      vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+      vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    }
+    if ((tid & 31) == 0) {
+      if (vmin < *reinterpret_cast<volatile float*>(minmax)) atomic_min_f32(minmax, vmin);
+      if (vmax > *reinterpret_cast<volatile float*>(minmax + 1)) atomic_max_f32(minmax + 1, vmax);
+    }
+  }
+  __syncthreads();
+  const int nbins = n_fft / 2 + 1;
+  for (int k = tid; k < nbins; k += 256) power[k] = dft_bin_power(k, n_fft, xw, tw);
+  __syncthreads();
+  for (int m = tid; m < num_mels; m += 256)
+    out[(static_cast<size_t>(b) * num_mels + m) * frames + f] = mel_bin_log(m, power, mel_start, mel_off, mel_w);
+}
+
 double hz_to_mel_htk(double f) { return 2595.0 * std::log10(1.0 + f / 700.0); }
 double mel_to_hz_htk(double m) { return 700.0 * (std::pow(10.0, m / 2595.0) - 1.0); }
 
@@ -251,7 +314,8 @@ extern "C" int hg_mel_plan_create(hg_mel_plan** out_plan, int n_fft, int num_mel
                                   int hop_size, int win_size, double fmin, double fmax,
                                   void* stream) {
   HG_REQUIRE(out_plan, "hg_mel_plan_create: null out_plan");
-  HG_REQUIRE(n_fft == kNfft, "hg_mel_plan_create: only n_fft == 1024 is implemented (got %d)", n_fft);
+  HG_REQUIRE(n_fft >= 16 && n_fft <= 4096 && n_fft % 2 == 0,
+             "hg_mel_plan_create: n_fft must be even and within [16, 4096] (got %d)", n_fft);
   HG_REQUIRE(num_mels > 0 && num_mels <= 128, "hg_mel_plan_create: num_mels out of range");
   HG_REQUIRE(win_size > 0 && win_size <= n_fft, "hg_mel_plan_create: win_size must be <= n_fft");
   HG_REQUIRE(hop_size > 0 && hop_size <= n_fft, "hg_mel_plan_create: bad hop_size");
@@ -275,6 +339,13 @@ extern "C" int hg_mel_plan_create(hg_mel_plan** out_plan, int n_fft, int num_mel
   for (int k = 0; k <= kHalf; ++k)
     p->h_tw1024[k] = make_float2(static_cast<float>(std::cos(two_pi * k / kNfft)),
                                  static_cast<float>(-std::sin(two_pi * k / kNfft)));
+
+  if (n_fft != kNfft) {
+    p->h_tw_n.resize(n_fft);
+    for (int n = 0; n < n_fft; ++n)
+      p->h_tw_n[n] = make_float2(static_cast<float>(std::cos(two_pi * n / n_fft)),
+                                 static_cast<float>(std::sin(two_pi * n / n_fft)));
+  }
 
   // HTK triangles, norm=None (torchaudio.functional.melscale_fbanks), as CSR per mel bin
   const int n_freqs = n_fft / 2 + 1;
@@ -313,7 +384,7 @@ extern "C" int hg_mel_plan_create(hg_mel_plan** out_plan, int n_fft, int num_mel
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     // host-only plan (CPU emulation in tests); device tables stay null
     (void)cudaGetLastError();
-    p->window = nullptr; p->tw512 = nullptr; p->tw1024 = nullptr;
+    p->window = nullptr; p->tw512 = nullptr; p->tw1024 = nullptr; p->tw_n = nullptr;
     p->mel_start = nullptr; p->mel_off = nullptr; p->mel_w = nullptr;
     *out_plan = p;
     return HG_OK;
@@ -325,6 +396,8 @@ extern "C" int hg_mel_plan_create(hg_mel_plan** out_plan, int n_fft, int num_mel
   HG_UP(window, h_window, float)
   HG_UP(tw512, h_tw512, float2)
   HG_UP(tw1024, h_tw1024, float2)
+  p->tw_n = nullptr;
+  if (!p->h_tw_n.empty()) { HG_UP(tw_n, h_tw_n, float2) }
   HG_UP(mel_start, h_mel_start, int)
   HG_UP(mel_off, h_mel_off, int)
   HG_UP(mel_w, h_mel_w, float)
@@ -339,6 +412,7 @@ extern "C" int hg_mel_plan_destroy(hg_mel_plan* p) {
   if (p->window) cudaFree(p->window);
   if (p->tw512) cudaFree(p->tw512);
   if (p->tw1024) cudaFree(p->tw1024);
+  if (p->tw_n) cudaFree(p->tw_n);
   if (p->mel_start) cudaFree(p->mel_start);
   if (p->mel_off) cudaFree(p->mel_off);
   if (p->mel_w) cudaFree(p->mel_w);
@@ -354,6 +428,22 @@ extern "C" int hg_mel_fwd(const hg_mel_plan* plan, const float* y, int batch, in
   HG_REQUIRE(t > plan->pad, "hg_mel_fwd: reflect padding %d needs more than %d samples", plan->pad, t);
   const int frames = hg_mel_num_frames(plan, t);
   HG_REQUIRE(frames > 0, "hg_mel_fwd: input too short for one frame");
+  if (plan->n_fft != kNfft) {
+    const size_t smem = static_cast<size_t>(plan->n_fft) * (sizeof(float2) + sizeof(float)) +
+                        (plan->n_fft / 2 + 1) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+      HG_CHECK_CUDA(cudaFuncSetAttribute(mel_dft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      configured = true;
+    }
+    dim3 grid(frames, batch);
+    mel_dft_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        y, t, frames, plan->n_fft, plan->hop, plan->pad, plan->num_mels, plan->window, plan->tw_n, plan->mel_start,
+        plan->mel_off, plan->mel_w, out, minmax);
+    HG_CHECK_CUDA(cudaGetLastError());
+    g_hg_launches.fetch_add(1, std::memory_order_relaxed);
+    return HG_OK;
+  }
   MelArgs a{};
   a.y = y; a.out = out; a.minmax = minmax;
   a.batch = batch; a.t = t; a.frames = frames; a.hop = plan->hop; a.pad = plan->pad;
@@ -449,6 +539,8 @@ extern "C" int hg_mel_bwd(const hg_mel_plan* plan, const float* y, const float* 
                           void* stream) {
   HG_REQUIRE(plan && y && dmel && dy, "hg_mel_bwd: null pointer");
   HG_REQUIRE(plan->window, "hg_mel_bwd: plan has no device tables");
+  HG_REQUIRE(plan->n_fft == kNfft, "hg_mel_bwd: only n_fft == 1024 (the training configs) is implemented (got %d)",
+             plan->n_fft);
   HG_REQUIRE(batch > 0 && batch <= 65535 && t > plan->pad && plan->num_mels <= 128, "hg_mel_bwd: bad arguments");
   const int frames = hg_mel_num_frames(plan, t);
   HG_REQUIRE(frames > 0, "hg_mel_bwd: input too short for one frame");
@@ -470,6 +562,21 @@ extern "C" int hg_mel_emulate_host(const hg_mel_plan* plan, const float* host_y,
   HG_REQUIRE(plan && host_y && host_out, "hg_mel_emulate_host: null pointer");
   const int frames = hg_mel_num_frames(plan, t);
   HG_REQUIRE(frames > 0 && t > plan->pad, "hg_mel_emulate_host: input too short");
+  if (plan->n_fft != kNfft) {
+    const int n_fft = plan->n_fft, nbins = n_fft / 2 + 1;
+    std::vector<float> xw(n_fft), pw(nbins);
+    for (int b = 0; b < batch; ++b)
+      for (int f = 0; f < frames; ++f) {
+        for (int n = 0; n < n_fft; ++n)
+          xw[n] = host_y[static_cast<size_t>(b) * t + reflect_index(f * plan->hop - plan->pad + n, t)] *
+                  plan->h_window[n];
+        for (int k = 0; k < nbins; ++k) pw[k] = dft_bin_power(k, n_fft, xw.data(), plan->h_tw_n.data());
+        for (int m = 0; m < plan->num_mels; ++m)
+          host_out[(static_cast<size_t>(b) * plan->num_mels + m) * frames + f] =
+              mel_bin_log(m, pw.data(), plan->h_mel_start.data(), plan->h_mel_off.data(), plan->h_mel_w.data());
+      }
+    return HG_OK;
+  }
   std::vector<float> smp(plan->n_fft);
   std::vector<cpx> z0(kPadLen), z1(kPadLen);
   std::vector<float> power(kHalf + 1);

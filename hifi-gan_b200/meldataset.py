@@ -163,9 +163,13 @@ class SegmentSampler:
     (input mel with fmax, loss mel with fmax_loss, meldataset.py:152-154,174-176)."""
 
     def __init__(self, utterances, segment_length, n_fft, num_mels, hop_size, win_size, sampling_rate, fmin,
-                 fmax, fmax_loss=None, seed=1234, device="cuda"):
+                 fmax, fmax_loss=None, seed=1234, device="cuda", mels=None):
+        """mels: fine-tuning mode (reference meldataset.py:155-172) — one precomputed [num_mels, F_i] (or
+        [1, num_mels, F_i]) mel per utterance, e.g. an acoustic model's teacher-forced output loaded from `.npy`; the
+        input mel of a batch is then cropped from these instead of being computed from the audio."""
         self.device = torch.device(device)
         self.segment_length = segment_length
+        self.hop_size = hop_size
         self.mel_args = (n_fft, num_mels, sampling_rate, hop_size, win_size, fmin)
         self.fmax, self.fmax_loss = fmax, fmax_loss
         self.lengths = [int(u.numel()) for u in utterances]
@@ -174,6 +178,17 @@ class SegmentSampler:
             self.offsets.append(self.offsets[-1] + n)
         self.pool = torch.cat([u.reshape(-1).float() for u in utterances]).to(self.device)
         self.rng = random.Random(seed)
+        self.fine_tuning = mels is not None
+        if self.fine_tuning:
+            if len(mels) != len(utterances):
+                raise ValueError("SegmentSampler: one mel per utterance is required in fine-tuning mode")
+            ms = [torch.as_tensor(m).float().reshape(-1, torch.as_tensor(m).shape[-1]) for m in mels]
+            self.mel_frames = [int(m.shape[1]) for m in ms]
+            self.mel_offsets = [0]
+            for f in self.mel_frames:
+                self.mel_offsets.append(self.mel_offsets[-1] + f)
+            self.mel_pool = torch.cat(ms, dim=1).to(self.device)          # [num_mels, sum F_i]
+            self.frames_per_seg = math.ceil(segment_length / hop_size)
 
     def draw(self, indices):
         """(pool offset, valid length) per item, following the reference's inclusive randint rule."""
@@ -184,15 +199,46 @@ class SegmentSampler:
             picks.append((self.offsets[i] + start, min(n, seg)))
         return picks
 
-    def batch(self, indices):
-        picks = self.draw(indices)
+    def draw_fine_tuning(self, indices):
+        """(audio pool offset, valid samples, mel pool column, valid frames) per item — reference meldataset.py:163-172:
+        utterances of at least one segment draw `mel_start = random.randint(0, F - frames_per_seg - 1)` and crop the
+        audio at `mel_start * hop`; shorter ones are right-padded with zeros (mel and audio)."""
+        seg, fps, hop, picks = self.segment_length, self.frames_per_seg, self.hop_size, []
+        for i in indices:
+            n, f = self.lengths[i], self.mel_frames[i]
+            if n >= seg:
+                mel_start = self.rng.randint(0, f - fps - 1)
+                a0 = mel_start * hop
+                picks.append((self.offsets[i] + a0, max(0, min(n - a0, fps * hop, seg)), self.mel_offsets[i] + mel_start,
+                              min(fps, f - mel_start)))
+            else:
+                picks.append((self.offsets[i], n, self.mel_offsets[i], min(fps, f)))
+        return picks
+
+    def _gather_audio(self, starts, valid):
         seg = self.segment_length
-        starts = torch.tensor([p[0] for p in picks], dtype=torch.int64).to(self.device, non_blocking=True)
-        valid = torch.tensor([p[1] for p in picks], dtype=torch.int32).to(self.device, non_blocking=True)
-        audio = torch.empty(len(picks), seg, dtype=torch.float32, device=self.device)
-        _lib.check(_lib.lib().hg_segment_gather(self.pool.data_ptr(), starts.data_ptr(), valid.data_ptr(), len(picks),
+        starts = torch.tensor(starts, dtype=torch.int64).to(self.device, non_blocking=True)
+        valid = torch.tensor(valid, dtype=torch.int32).to(self.device, non_blocking=True)
+        audio = torch.empty(starts.numel(), seg, dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib().hg_segment_gather(self.pool.data_ptr(), starts.data_ptr(), valid.data_ptr(), starts.numel(),
                                                 seg, audio.data_ptr(), torch.cuda.current_stream().cuda_stream),
                    "hg_segment_gather")
-        mel = mel_spectrogram(audio, *self.mel_args, self.fmax, center=False)
+        return audio
+
+    def batch(self, indices):
+        if self.fine_tuning:
+            picks = self.draw_fine_tuning(indices)
+            audio = self._gather_audio([p[0] for p in picks], [p[1] for p in picks])
+            fps = self.frames_per_seg
+            col0 = torch.tensor([p[2] for p in picks], dtype=torch.int64, device=self.device)
+            nval = torch.tensor([p[3] for p in picks], dtype=torch.int64, device=self.device)
+            ar = torch.arange(fps, device=self.device)
+            cols = (col0[:, None] + ar[None, :]).clamp_(max=self.mel_pool.shape[1] - 1)      # [B, fps]
+            mel = self.mel_pool[:, cols].permute(1, 0, 2) * (ar[None, :] < nval[:, None])[:, None, :]   # zero padding
+            mel = mel.contiguous()
+        else:
+            picks = self.draw(indices)
+            audio = self._gather_audio([p[0] for p in picks], [p[1] for p in picks])
+            mel = mel_spectrogram(audio, *self.mel_args, self.fmax, center=False)
         mel_loss = mel_spectrogram(audio, *self.mel_args, self.fmax_loss, center=False)
         return mel, audio, mel_loss

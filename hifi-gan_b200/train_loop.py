@@ -16,7 +16,7 @@ files written here load into torch optimizers.  Resume = newest `g_` / `do_` pai
 What differs from UPSTREAM, deliberately: the DataLoader workers computing mels on the CPU are replaced by the
 GPU-resident `SegmentSampler` (the kernels have no CPU path); audio is peak-normalised per utterance to 0.95 (the
 UPSTREAM rule — this fork's `[1, L]` call of librosa.util.normalize normalises per SAMPLE, SURVEY §8a row S);
-fine-tuning from `.npy` mels is not implemented; TensorBoard scalars are written only if tensorboard is installed.
+TensorBoard scalars are written only if tensorboard is installed.
 """
 from __future__ import annotations
 
@@ -128,10 +128,15 @@ def train(rank: int, a, h) -> Dict[str, float]:
     training_files, validation_files = get_dataset_filelist(a)
     random.seed(1234)                                                # MelDataset.__init__ (meldataset.py:104-106)
     random.shuffle(training_files)
-    utts = [normalize_peak(read_wav(f, h.sampling_rate) / MAX_WAV_VALUE) for f in training_files]   # quirk :128 kept
+    # meldataset.py:126-130: `/ MAX_WAV_VALUE` (quirk kept), then peak normalisation unless fine-tuning
+    prep = (lambda a_: a_) if a.fine_tuning else normalize_peak
+    utts = [prep(read_wav(f, h.sampling_rate) / MAX_WAV_VALUE) for f in training_files]
+    npy = lambda f: np.load(os.path.join(a.input_mels_dir, os.path.splitext(os.path.split(f)[-1])[0] + '.npy'))
     sampler = SegmentSampler(utts, h.segment_size, h.n_fft, h.num_mels, h.hop_size, h.win_size, h.sampling_rate, h.fmin,
-                             h.fmax, h.fmax_for_loss, seed=1234, device=device)
-    val = [normalize_peak(read_wav(f, h.sampling_rate) / MAX_WAV_VALUE) for f in validation_files] if rank == 0 else []
+                             h.fmax, h.fmax_for_loss, seed=1234, device=device,
+                             mels=[npy(f) for f in training_files] if a.fine_tuning else None)   # meldataset.py:155-161
+    val = [prep(read_wav(f, h.sampling_rate) / MAX_WAV_VALUE) for f in validation_files] if rank == 0 else []
+    val_mels = [torch.from_numpy(npy(f)).float() for f in validation_files] if (rank == 0 and a.fine_tuning) else None
     sw = None
     if rank == 0:
         try:
@@ -176,7 +181,7 @@ def train(rank: int, a, h) -> Dict[str, float]:
                     sw.add_scalar("training/mel_spec_error", out["loss_mel"].item() / 45, steps)
                 if steps % a.validation_interval == 0 and val:
                     ts.G.invalidate()       # the module API must re-pack: the last AdamW update ran inside the graph
-                    last["val_mel_error"] = validate(generator, val, h, device)
+                    last["val_mel_error"] = validate(generator, val, h, device, val_mels)
                     print('Steps : {:d}, Validation Mel-Spec. Error : {:4.3f}'.format(steps, last["val_mel_error"]))
                     if sw is not None:
                         sw.add_scalar("validation/mel_spec_error", last["val_mel_error"], steps)
@@ -189,16 +194,23 @@ def train(rank: int, a, h) -> Dict[str, float]:
 
 
 @torch.no_grad()
-def validate(generator: Generator, utterances: List[torch.Tensor], h, device) -> float:
-    """UPSTREAM validation: mean over files of L1(mel(y), mel(G(mel_in(y)))) on whole utterances (split=False)."""
+def validate(generator: Generator, utterances: List[torch.Tensor], h, device, mels=None) -> float:
+    """UPSTREAM validation: mean over files of L1(mel(y), mel(G(x))) on whole utterances (split=False), x = mel_in(y)
+    or, fine-tuning, the utterance's precomputed mel."""
     generator.eval()
     err = 0.0
-    for y in utterances:
+    mel = lambda a_, fmax: mel_spectrogram(a_, h.n_fft, h.num_mels, h.sampling_rate, h.hop_size, h.win_size, h.fmin, fmax)
+    for i, y in enumerate(utterances):
         y = y.to(device).reshape(1, -1)
         frames = y.shape[1] // h.hop_size
+        if mels is not None:
+            x = mels[i].to(device).reshape(1, h.num_mels, -1)
+            frames = min(frames, x.shape[2])
+            x = x[:, :, :frames].contiguous()
         y = y[:, : frames * h.hop_size]
-        mel = lambda a_, fmax: mel_spectrogram(a_, h.n_fft, h.num_mels, h.sampling_rate, h.hop_size, h.win_size, h.fmin, fmax)
-        y_g_hat = generator(mel(y, h.fmax))
+        if mels is None:
+            x = mel(y, h.fmax)
+        y_g_hat = generator(x)
         err += torch.nn.functional.l1_loss(mel(y, h.fmax_for_loss), mel(y_g_hat.squeeze(1), h.fmax_for_loss)).item()
     return err / max(1, len(utterances))
 
@@ -220,8 +232,6 @@ def main(argv=None) -> Dict[str, float]:
     parser.add_argument('--validation_interval', default=1000, type=int)
     parser.add_argument('--fine_tuning', default=False, type=bool)
     a = parser.parse_args(argv)
-    if a.fine_tuning:
-        raise NotImplementedError("fine-tuning from .npy mels (reference meldataset.py:155-172) is not implemented")
     with open(a.config) as f:
         h = AttrDict(json.loads(f.read()))
     build_env(a.config, 'config.json', a.checkpoint_path)

@@ -353,6 +353,18 @@ def crop_or_pad_segment(audio: Tensor, segment_length: int, audio_start: int) ->
     return F.pad(audio, (0, segment_length - audio.size(1)), "constant")
 
 
+def finetune_crop_or_pad(mel: Tensor, audio: Tensor, segment_length: int, hop_size: int, mel_start: int):
+    """Fine-tuning branch of MelDataset.__getitem__ (src/meldataset.py:155-172): mel [1,M,F] loaded from .npy,
+    audio [1,L].  L >= seg: frames [mel_start, mel_start + fps) with mel_start drawn by
+    random.randint(0, F - fps - 1) and the audio cropped at mel_start * hop; else both right zero-padded."""
+    fps = math.ceil(segment_length / hop_size)
+    if audio.size(1) >= segment_length:
+        return (mel[:, :, mel_start:mel_start + fps],
+                audio[:, mel_start * hop_size:(mel_start + fps) * hop_size])
+    return (F.pad(mel, (0, fps - mel.size(2)), "constant"),
+            F.pad(audio, (0, segment_length - audio.size(1)), "constant"))
+
+
 # --------------------------------------------------------------------------------------------------
 # synthetic inputs shared by tests / bench (SURVEY.md §8d)
 # --------------------------------------------------------------------------------------------------

@@ -354,6 +354,20 @@ def test_mel_range_warning_is_lazy_but_kept(H, capsys):
     assert "max value is" in capsys.readouterr().out
 
 
+@pytest.mark.parametrize("case", range(4))
+def test_mel_other_shapes_vs_reference_golden(H, case):
+    """mel_spectrogram at the shapes of the reference's other callers (n_fft != 1024, 16 kHz, fmax None,
+    win < n_fft, fmin > 0) — the direct-DFT kernel against outputs of the reference's own function."""
+    from test_oracle_cpu import mel_close
+    z = load_npz("mel_other.npz")
+    n_fft, nm, sr, hop, win, fmin, fmax = [int(v) for v in z["cases"][case]]
+    y = torch.from_numpy(z["y"]).cuda()
+    got = H.mel_spectrogram(y, n_fft, nm, sr, hop, win, fmin, None if fmax < 0 else fmax)
+    ref = z[f"mel_{case}"]
+    assert tuple(got.shape) == ref.shape
+    mel_close(got.cpu().double().numpy(), ref, 2e-4)
+
+
 def test_segment_sampler_batch(H, O):
     from hifigan_b200.meldataset import SegmentSampler
     utts = [O.synthetic_audio(1, n, seed=n)[0] for n in (30000, 5000, 8192, 12345)]
@@ -366,6 +380,29 @@ def test_segment_sampler_batch(H, O):
         start = ref_rng.randint(0, u.numel() - 8192) if u.numel() >= 8192 else 0
         want = O.crop_or_pad_segment(u.unsqueeze(0), 8192, start)[0]
         assert torch.equal(audio[i].cpu(), want)
+    ref = O.mel_spectrogram(audio.cpu().double(), 1024, 80, 22050, 256, 1024, 0, None)
+    assert (mel_loss.cpu().double() - ref).abs().max().item() < 1e-3
+
+
+def test_segment_sampler_fine_tuning_batch(H, O):
+    """fine-tuning mode (meldataset.py:155-172): input mels cropped from precomputed per-utterance mels at the drawn
+    frame, audio cropped at frame * hop, short utterances zero-padded — bit-exact against the oracle's restatement."""
+    import random
+    from hifigan_b200.meldataset import SegmentSampler
+    lens = (30000, 5000, 8192, 12345)
+    utts = [O.synthetic_audio(1, n, seed=n)[0] for n in lens]
+    g = torch.Generator().manual_seed(3)
+    mels = [torch.randn(1, 80, n // 256 + 1, generator=g) for n in lens]
+    s = SegmentSampler(utts, 8192, 1024, 80, 256, 1024, 22050, 0, 8000, fmax_loss=None, seed=99,
+                       mels=[m.numpy() for m in mels])
+    ref_rng = random.Random(99)
+    mel, audio, mel_loss = s.batch([0, 1, 2, 3])
+    assert audio.shape == (4, 8192) and mel.shape == (4, 80, 32) and mel_loss.shape == (4, 80, 32)
+    for i, (u, m) in enumerate(zip(utts, mels)):
+        start = ref_rng.randint(0, m.shape[2] - 32 - 1) if u.numel() >= 8192 else 0
+        wm, wa = O.finetune_crop_or_pad(m, u.unsqueeze(0), 8192, 256, start)
+        wa = torch.nn.functional.pad(wa, (0, 8192 - wa.shape[1]))       # a crop that runs past the end (see draw rule)
+        assert torch.equal(audio[i].cpu(), wa[0]) and torch.equal(mel[i].cpu(), wm[0])
     ref = O.mel_spectrogram(audio.cpu().double(), 1024, 80, 22050, 256, 1024, 0, None)
     assert (mel_loss.cpu().double() - ref).abs().max().item() < 1e-3
 

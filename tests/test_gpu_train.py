@@ -500,3 +500,14 @@ def test_train_driver_checkpoints_and_resumes(H, tmp_path):
     assert set(g) == {"generator"} and "conv_pre.weight_g" in g["generator"]
     r2 = train_loop.main(argv + ["--training_epochs", "3"])
     assert r2["final_steps"] == 3 + 2 * 2 and (cp / "g_00000004").exists()
+    # fine-tuning mode (UPSTREAM --fine_tuning True: input mels from <input_mels_dir>/<name>.npy, no peak normalisation)
+    mels = tmp_path / "mels"
+    mels.mkdir()
+    for n, a in zip(names, audio):
+        m = O.mel_spectrogram(a.unsqueeze(0) / 32768.0 * 32767 / 32768.0, 1024, 80, 22050, 256, 1024, 0, 8000)
+        np.save(mels / f"{n}.npy", m.numpy().astype(np.float32))
+    cp_ft = tmp_path / "cp_ft"
+    argv_ft = [x if x != str(cp) else str(cp_ft) for x in argv] + ["--fine_tuning", "True", "--input_mels_dir", str(mels)]
+    r3 = train_loop.main(argv_ft + ["--training_epochs", "2"])
+    assert r3["final_steps"] == 4 and (cp_ft / "g_00000002").exists()
+    assert np.isfinite(r3["val_mel_error"]) and np.isfinite(r3["loss_gen_all"])

@@ -174,8 +174,32 @@ def test_mel_kernel_arithmetic_on_host_vs_reference(name, fmax):
 def test_mel_plan_rejects_unsupported():
     L = _lib.lib()
     plan = ctypes.c_void_p()
-    assert L.hg_mel_plan_create(ctypes.byref(plan), 512, 80, 22050, 128, 512, 0.0, 8000.0, None) != 0
-    assert b"n_fft == 1024" in L.hg_last_error()
+    assert L.hg_mel_plan_create(ctypes.byref(plan), 511, 80, 22050, 128, 511, 0.0, 8000.0, None) != 0
+    assert b"n_fft must be even" in L.hg_last_error()
+    assert L.hg_mel_plan_create(ctypes.byref(plan), 512, 80, 22050, 128, 600, 0.0, 8000.0, None) != 0
+    assert b"win_size" in L.hg_last_error()
+
+
+@pytest.mark.parametrize("case", range(4))
+def test_mel_other_shapes_emulation_vs_reference_golden(case):
+    """n_fft other than 1024 (SURVEY §8f-4: the reference's Lightning-side callers) runs the direct-DFT kernel;
+    its arithmetic, executed on the host, against outputs of the reference's own mel_spectrogram
+    (tests/golden/make_golden_mel_other.py)."""
+    from test_oracle_cpu import mel_close
+    z = load_npz("mel_other.npz")
+    n_fft, nm, sr, hop, win, fmin, fmax = [int(v) for v in z["cases"][case]]
+    L = _lib.lib()
+    plan = ctypes.c_void_p()
+    assert L.hg_mel_plan_create(ctypes.byref(plan), n_fft, nm, sr, hop, win, float(fmin), float(fmax), None) == 0
+    y = np.ascontiguousarray(z["y"])
+    b, t = y.shape
+    frames = L.hg_mel_num_frames(plan, t)
+    out = np.zeros((b, nm, frames), np.float32)
+    assert L.hg_mel_emulate_host(plan, y.ctypes.data, b, t, out.ctypes.data) == 0
+    L.hg_mel_plan_destroy(plan)
+    ref = z[f"mel_{case}"]
+    assert out.shape == ref.shape
+    mel_close(out.astype(np.float64), ref, 2e-4)
 
 
 def test_segment_sampler_draw_rule_matches_reference():
@@ -188,6 +212,27 @@ def test_segment_sampler_draw_rule_matches_reference():
     picks = s.draw([0, 1, 2, 0])
     ref = random.Random(1234)
     want = [(0 + ref.randint(0, 12), 8), (20, 5), (25 + ref.randint(0, 0), 8), (0 + ref.randint(0, 12), 8)]
+    assert picks == want
+
+
+def test_segment_sampler_fine_tuning_draw_rule_matches_reference():
+    """fine-tuning branch (meldataset.py:163-172): mel_start = random.randint(0, F - fps - 1), audio cropped at
+    mel_start * hop; short utterances keep offset 0 and are padded."""
+    import random
+    from hifigan_b200.meldataset import SegmentSampler
+    s = SegmentSampler.__new__(SegmentSampler)
+    s.segment_length, s.hop_size, s.frames_per_seg = 8, 2, 4
+    s.lengths, s.offsets = [20, 5, 8], [0, 20, 25, 33]
+    s.mel_frames, s.mel_offsets = [10, 3, 5], [0, 10, 13, 18]
+    s.rng = random.Random(7)
+    picks = s.draw_fine_tuning([0, 1, 2, 0])
+    ref = random.Random(7)
+    m0 = ref.randint(0, 10 - 4 - 1)
+    want = [(0 + 2 * m0, 8, 0 + m0, 4), (20, 5, 10, 3)]
+    m2 = ref.randint(0, 5 - 4 - 1)
+    want.append((25 + 2 * m2, 8, 13 + m2, 4))
+    m3 = ref.randint(0, 10 - 4 - 1)
+    want.append((0 + 2 * m3, 8, 0 + m3, 4))
     assert picks == want
 
 

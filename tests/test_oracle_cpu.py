@@ -70,6 +70,17 @@ def test_mel_vs_reference(name, fmax):
     mel_close(got32.numpy(), ref, 2e-4)
 
 
+@pytest.mark.parametrize("case", range(4))
+def test_mel_other_shapes_vs_reference(case):
+    """the oracle's restatement at the shapes of the reference's other callers (n_fft != 1024, 16 kHz, fmax None,
+    win < n_fft, fmin > 0) against outputs of the reference's own mel_spectrogram"""
+    z = load_npz("mel_other.npz")
+    n_fft, nm, sr, hop, win, fmin, fmax = [int(v) for v in z["cases"][case]]
+    got = O.mel_spectrogram(torch.from_numpy(z["y"]).double(), n_fft, nm, sr, hop, win, fmin, None if fmax < 0 else fmax)
+    assert got.shape == z[f"mel_{case}"].shape
+    mel_close(got.numpy(), z[f"mel_{case}"], 1e-4)
+
+
 def test_mel_silence_hits_the_clamp():
     z = load_npz("mel.npz")
     got = O.mel_spectrogram(torch.from_numpy(z["special"][:1]).double(), 1024, 80, 22050, 256, 1024, 0, 8000)
