@@ -182,7 +182,10 @@ int hg_conv_post_tanh_fwd(const void* x, const float* w, const float* bias, int 
  * periodic Hann window, rFFT(n_fft), |X|^2, HTK mel filterbank (un-normalised triangles), and
  * log(clamp(., 1e-5)) in ONE kernel.  The plan owns the immutable tables (window, twiddles, sparse
  * filterbank), keyed like the reference's cache key (meldataset.py:57).
- * Supported: n_fft == 1024, win_size <= n_fft, hop_size | anything, num_mels <= 128.
+ * n_fft == 1024 (every HiFi-GAN config) runs the fused radix-8 FFT kernel; any other even n_fft in [16, 4096]
+ * (the reference's other callers: src/speech_distillation/lightning_model.py:513-522 pass 16 kHz / fmax None /
+ * n_fft = a layer's kernel size) runs a general direct-DFT kernel, one block per frame.
+ * win_size <= n_fft, hop_size <= n_fft, num_mels <= 128.
  */
 typedef struct hg_mel_plan hg_mel_plan;
 int hg_mel_plan_create(hg_mel_plan** out_plan, int n_fft, int num_mels, int sampling_rate,
@@ -198,7 +201,8 @@ int hg_mel_fwd(const hg_mel_plan* plan, const float* y, int batch, int t, float*
                float* minmax, void* stream);
 
 /* hg_mel_bwd — backward of hg_mel_fwd: dmel fp32 [B][num_mels][frames] (gradient at the log-mel output) ->
- * dy fp32 [B][T] ADDED to (zero it first).  y is the forward input; the spectrum is recomputed. */
+ * dy fp32 [B][T] ADDED to (zero it first).  y is the forward input; the spectrum is recomputed.
+ * n_fft == 1024 only (the training configs). */
 int hg_mel_bwd(const hg_mel_plan* plan, const float* y, const float* dmel, int batch, int t, float* dy,
                void* stream);
 
