@@ -800,7 +800,7 @@ class _SubDiscTrainer:
         """element counts of the reference's feature maps for a batch of nb_half items"""
         return [nb_half * self.period * h * c for h, _, c in self.G["geo"]] + [nb_half * self.period * self.G["geo"][-1][0]]
 
-    def loss_terms(self, acc: torch.Tensor, slot: int) -> None:
+    def loss_terms(self, acc: torch.Tensor, slot: int, fm: bool = True) -> None:
         """acc[slot + 0] += sum (1 - logit_r)^2, [1] += sum logit_g^2, [2] += sum (1 - logit_g)^2,
         acc[slot + 3 + l] += sum |fmap_r[l] - fmap_g[l]| (l = 0..n_layers, the last one the logits)"""
         L = _lib.lib()
@@ -812,7 +812,7 @@ class _SubDiscTrainer:
         _lib.check(L.hg_loss_sum(lr.data_ptr(), 0, nr * h, 1, 1.0, acc[slot:].data_ptr(), st))
         _lib.check(L.hg_loss_sum(lg.data_ptr(), 0, ng * h, 1, 0.0, acc[slot + 1:].data_ptr(), st))
         _lib.check(L.hg_loss_sum(lg.data_ptr(), 0, ng * h, 1, 1.0, acc[slot + 2:].data_ptr(), st))
-        if nr == ng:
+        if fm and nr == ng:      # feature-matching sums: only the generator step reads them
             for l, a in enumerate(G["act"]):
                 n = a[:nr].numel()
                 _lib.check(L.hg_l1_sum_bf16(a.data_ptr(), a[nr:].data_ptr(), n, acc[slot + 3 + l:].data_ptr(), st))
@@ -1048,7 +1048,7 @@ class DiscriminatorTrainer:
         for i, sd in enumerate(self.subs):
             with self.lanes.lane(i):
                 sd.forward(self._input_of(i), b)
-                sd.loss_terms(self.acc_d, i * self.nslots)
+                sd.loss_terms(self.acc_d, i * self.nslots, fm=False)
                 sd.backward_d()
         if world > 1:
             self.lanes.join()

@@ -298,3 +298,22 @@ def test_optimizer_state_roundtrip_with_torch_adamw():
         assert torch.equal(opt2.state_dict()["state"][j]["exp_avg"], ref["state"][i]["exp_avg"])
         assert torch.equal(opt2.state_dict()["state"][j]["exp_avg_sq"], ref["state"][i]["exp_avg_sq"])
         assert float(opt2.state_dict()["state"][j]["step"]) == 2.0
+
+
+def test_flat_param_spans_of_the_sub_discriminators_tile_the_buffer():
+    """Each sub-discriminator updates its own slice of the flat parameter / gradient / moment buffers on its own lane
+    (DiscriminatorTrainer.run_phases): the slices must be contiguous, 16-byte aligned and cover the buffer exactly."""
+    from hifigan_b200.train import FlatParams
+    mpd, msd = H.MultiPeriodDiscriminator(), H.MultiScaleDiscriminator()
+    flat = FlatParams(torch.nn.ModuleList([mpd, msd]), "cpu")
+    spans = [flat.span_of(d) for d in list(mpd.discriminators) + list(msd.discriminators)]
+    assert spans[0][0] == 0 and spans[-1][1] == flat.numel
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:])) and all(lo % 4 == 0 for lo, _ in spans)
+    for d, (lo, hi) in zip(list(mpd.discriminators) + list(msd.discriminators), spans):
+        n = sum((p.numel() + 3) // 4 * 4 for p in d.parameters())
+        assert hi - lo == n
+        for p in d.parameters():                      # every parameter is a view into its slice
+            off = (p.data_ptr() - flat.p.data_ptr()) // 4
+            assert lo <= off and off + p.numel() <= hi
+    with pytest.raises(RuntimeError):
+        flat.span_of(torch.nn.ModuleList([mpd.discriminators[0], msd.discriminators[1]]))
