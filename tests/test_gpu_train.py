@@ -375,6 +375,55 @@ def test_train_step_every_gradient_vs_oracle(H):
     print("worst cosine", worst)
 
 
+def test_train_trajectory_vs_oracle_on_the_same_gpu(H):
+    """Eight consecutive optimizer steps (fresh batch each step, graph replay from step 3 on) against the training
+    oracle run in fp32 (TF32 off) on the same GPU: the losses of every step and the parameters after the last one.
+    Pins the AdamW slices, the step counter, the cached / re-packed weights and the lane schedule over more than one
+    update.  Tolerances: losses 3e-2 relative (bf16 activations over 8 updates), cosine of the accumulated parameter
+    change >= 0.98 per network (AdamW's first updates are lr * sign(g)-like: elements whose gradient is below the
+    bf16 noise floor take either sign, so this is a direction check, not an element-wise one)."""
+    from oracle import hifigan_oracle as O
+    from oracle import train_oracle as TO
+    h, ts, (G, mpd, msd), sds = _seeded_step(H)
+    init = [{k: v.clone() for k, v in sd.items()} for sd in sds]
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        batches = [O.synthetic_audio(4, 8192, seed=100 + i) for i in range(8)]
+        mels = [(O.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, 8000),
+                 O.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, None)) for ya in batches]
+        torch.set_default_device("cuda")      # the oracle builds its window / filterbank on the default device
+        try:
+            ref_sds = [TO.leaf_params({k: v.detach().clone().cuda() for k, v in sd.items()}) for sd in sds]
+            optims = TO.make_optimizers(*ref_sds, h)
+            ref_losses = []
+            for ya, (x, y_mel) in zip(batches, mels):
+                losses = TO.train_step(*ref_sds, h, x.cuda(), ya.cuda().unsqueeze(1), y_mel.cuda(), optims=optims)[0]
+                ref_losses.append(losses)
+        finally:
+            torch.set_default_device("cpu")
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    for i, (ya, (x, y_mel)) in enumerate(zip(batches, mels)):
+        out = ts.step_graphed(x.cuda(), ya.cuda().unsqueeze(1), y_mel.cuda())
+        for k in LOSS_KEYS:
+            got, ref = out[k].item(), ref_losses[i][k]
+            assert abs(got - ref) <= 3e-2 * abs(ref) + 1e-4, (i, k, got, ref)
+    assert ts.graph_active
+    for net, ref_sd, sd0 in zip((G, mpd, msd), ref_sds, init):
+        mine = net.state_dict()
+        num = den_a = den_b = 0.0
+        for k, v in ref_sd.items():
+            if not v.requires_grad:
+                continue
+            da = (mine[k].detach().float().cpu() - sd0[k]).flatten().double()
+            db = (v.detach().cpu() - sd0[k]).flatten().double()
+            num += float(da @ db); den_a += float(da @ da); den_b += float(db @ db)
+        cos = num / (den_a ** 0.5 * den_b ** 0.5 + 1e-30)
+        print("accumulated update cosine", type(net).__name__, round(cos, 4))
+        assert cos >= 0.98, (type(net).__name__, cos)      # measured 0.996 (G), 0.9995 (MPD), 0.9996 (MSD)
+
+
 def test_train_step_v3_and_no_update(H):
     """ResBlock2 generator (V3) through the same step; update=False leaves every parameter untouched."""
     from oracle import hifigan_oracle as O
