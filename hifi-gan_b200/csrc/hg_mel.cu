@@ -43,8 +43,8 @@ namespace {
 
 constexpr int kNfft = 1024;
 constexpr int kHalf = 512;
-constexpr int kFramesPerBlock = 8;
-constexpr int kGroups = 4;
+constexpr int kFramesPerBlock = 16;
+constexpr int kGroups = 8;
 constexpr int kGroupThreads = 64;
 constexpr int kMelThreads = kGroups * kGroupThreads;
 constexpr int kPadLen = kHalf + kHalf / 16;  // PADI(511) + 1 = 543 -> 544
@@ -172,62 +172,131 @@ struct MelArgs {
   const int* mel_off;
   const float* mel_w;
   int stage_len;  // samples staged per block = (kFramesPerBlock-1)*hop + n_fft
+  int nnz;        // entries of mel_w
 };
+
+// shared-memory layout of mel_kernel (bytes, every region 16-byte aligned)
+struct MelSmem {
+  uint32_t win, tw512, tw1024, melw, melidx, meloff, buf0, buf1, outs, total;
+};
+__host__ __device__ inline MelSmem mel_smem_layout(int stage_len, int num_mels, int nnz) {
+  auto up = [](uint32_t v) { return (v + 15u) & ~15u; };
+  MelSmem l;
+  uint32_t o = up(static_cast<uint32_t>(stage_len) * 4u);
+  l.win = o;    o += kNfft * 4u;
+  l.tw512 = o;  o += kHalf * 8u;
+  l.tw1024 = o; o += up((kHalf + 1) * 8u);
+  l.melw = o;   o += up(static_cast<uint32_t>(nnz > 0 ? nnz : 1) * 4u);
+  l.melidx = o; o += up(static_cast<uint32_t>(num_mels) * 4u);            // mel_start
+  l.meloff = o; o += up(static_cast<uint32_t>(num_mels + 1) * 4u);        // mel_off
+  l.buf0 = o;   o += kGroups * kPadLen * 8u;
+  l.buf1 = o;   o += kGroups * kPadLen * 8u;
+  l.outs = o;   o += static_cast<uint32_t>(num_mels) * kFramesPerBlock * 4u;
+  l.total = o;
+  return l;
+}
+// asynchronous global -> shared copies (LDGSTS): every copy of the block prologue is in flight at once, so the
+// prologue costs one memory round trip instead of one per dependent load / store pair (ncu source view: the
+// staging stores waiting on their loads, and the barrier behind them, were ~25 % of this kernel's stall samples)
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(hg::smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(hg::smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// nbytes (a multiple of 4) from a 16-byte aligned global table into a 16-byte aligned shared region
+__device__ __forceinline__ void cp_async_table(void* dst_smem, const void* src, int nbytes, int tid, int nthreads) {
+  const int n16 = nbytes >> 4;
+  for (int i = tid; i < n16; i += nthreads)
+    cp_async16(static_cast<uint8_t*>(dst_smem) + 16 * i, static_cast<const uint8_t*>(src) + 16 * i);
+  for (int i = n16 * 4 + tid; i < (nbytes >> 2); i += nthreads)
+    cp_async4(static_cast<uint8_t*>(dst_smem) + 4 * i, static_cast<const uint8_t*>(src) + 4 * i);
+}
+// the two warps of a frame group meet on their own named barrier: groups drift apart freely
+__device__ __forceinline__ void group_sync(int g) {
+  asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(kGroupThreads) : "memory");
+}
 
 __global__ void __launch_bounds__(kMelThreads) mel_kernel(const MelArgs a) {
   extern __shared__ __align__(16) uint8_t sm[];
+  const MelSmem L = mel_smem_layout(a.stage_len, a.num_mels, a.nnz);
   float* stage = reinterpret_cast<float*>(sm);                                 // [stage_len]
-  cpx* buf0 = reinterpret_cast<cpx*>(sm + ((a.stage_len * 4 + 15) & ~15));     // [groups][kPadLen]
-  cpx* buf1 = buf0 + kGroups * kPadLen;                                        // [groups][kPadLen]
-  float* outs = reinterpret_cast<float*>(buf1 + kGroups * kPadLen);            // [num_mels][8]
+  float* s_win = reinterpret_cast<float*>(sm + L.win);                         // tables: read ~18 KB per frame
+  float2* s_tw512 = reinterpret_cast<float2*>(sm + L.tw512);                   //   from L1 / L2 otherwise
+  float2* s_tw1024 = reinterpret_cast<float2*>(sm + L.tw1024);
+  float* s_melw = reinterpret_cast<float*>(sm + L.melw);
+  int* s_start = reinterpret_cast<int*>(sm + L.melidx);
+  int* s_off = reinterpret_cast<int*>(sm + L.meloff);
+  cpx* buf0 = reinterpret_cast<cpx*>(sm + L.buf0);                             // [groups][kPadLen]
+  cpx* buf1 = reinterpret_cast<cpx*>(sm + L.buf1);                             // [groups][kPadLen]
+  float* outs = reinterpret_cast<float*>(sm + L.outs);                         // [num_mels][frames per block]
 
   const int b = blockIdx.y;
   const int f0 = blockIdx.x * kFramesPerBlock;
   const int tid = threadIdx.x;
   const float* yb = a.y + static_cast<size_t>(b) * a.t;
   const int base = f0 * a.hop - a.pad;
-  float vmin = INFINITY, vmax = -INFINITY;
-  for (int i = tid; i < a.stage_len; i += kMelThreads) {
-    // samples past the last frame of this batch item are never used; clamp keeps the index legal
-    int src = reflect_index(base + i, a.t);
-    src = src < 0 ? 0 : (src >= a.t ? a.t - 1 : src);
-    const float v = yb[src];
-    stage[i] = v;
-    vmin = fminf(vmin, v);
-    vmax = fmaxf(vmax, v);
+  // samples actually used by this block's frames (the last block of an item may hold fewer than 16 frames)
+  const int nfr = min(kFramesPerBlock, a.frames - f0);
+  const int used = (nfr - 1) * a.hop + kNfft;
+  const bool interior = base >= 0 && base + used <= a.t && ((a.t | base) & 3) == 0 &&
+                        (reinterpret_cast<uintptr_t>(a.y) & 15) == 0;
+  if (interior) {
+    // no reflection, 16-byte aligned: straight vector copies
+    const int n16 = used >> 2;
+    for (int i = tid; i < n16; i += kMelThreads) cp_async16(stage + 4 * i, yb + base + 4 * i);
+    for (int i = n16 * 4 + tid; i < used; i += kMelThreads) cp_async4(stage + i, yb + base + i);
+  } else {
+    for (int i = tid; i < used; i += kMelThreads) cp_async4(stage + i, yb + reflect_index(base + i, a.t));
   }
+  cp_async_table(s_win, a.window, kNfft * 4, tid, kMelThreads);
+  cp_async_table(s_tw512, a.tw512, kHalf * 8, tid, kMelThreads);
+  cp_async_table(s_tw1024, a.tw1024, (kHalf + 1) * 8, tid, kMelThreads);
+  cp_async_table(s_melw, a.mel_w, a.nnz * 4, tid, kMelThreads);
+  cp_async_table(s_start, a.mel_start, a.num_mels * 4, tid, kMelThreads);
+  cp_async_table(s_off, a.mel_off, (a.num_mels + 1) * 4, tid, kMelThreads);
+  cp_async_wait_all();
+  __syncthreads();
   if (a.minmax) {
+    float vmin = INFINITY, vmax = -INFINITY;
+    for (int i = tid; i < used; i += kMelThreads) {
+      const float v = stage[i];
+      vmin = fminf(vmin, v);
+      vmax = fmaxf(vmax, v);
+    }
     for (int o = 16; o > 0; o >>= 1) {
       vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
       vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
     }
     // almost every warp loses against the running extrema: peek first (a stale read only costs one
-    // redundant atomic), otherwise 2 x 8 same-address atomics per block serialise in L2
+    // redundant atomic), otherwise 2 x 16 same-address atomics per block serialise in L2
     if ((tid & 31) == 0) {
       if (vmin < *reinterpret_cast<volatile float*>(a.minmax)) atomic_min_f32(a.minmax, vmin);
       if (vmax > *reinterpret_cast<volatile float*>(a.minmax + 1)) atomic_max_f32(a.minmax + 1, vmax);
     }
   }
-  __syncthreads();
 
   const int g = tid / kGroupThreads, j = tid % kGroupThreads;
   cpx* z0 = buf0 + g * kPadLen;
   cpx* z1 = buf1 + g * kPadLen;
   for (int it = 0; it < kFramesPerBlock / kGroups; ++it) {
     const int fl = it * kGroups + g;  // frame within the block
+    if (fl >= nfr) break;             // group-uniform: the whole group leaves together
     const float* smp = stage + fl * a.hop;
-    fft_pass<true>(j, 1, nullptr, z0, smp, a.window, a.tw512);
-    __syncthreads();
-    fft_pass<false>(j, 8, z0, z1, nullptr, nullptr, a.tw512);
-    __syncthreads();
-    fft_pass<false>(j, 64, z1, z0, nullptr, nullptr, a.tw512);
-    __syncthreads();
+    fft_pass<true>(j, 1, nullptr, z0, smp, s_win, s_tw512);
+    group_sync(g);
+    fft_pass<false>(j, 8, z0, z1, nullptr, nullptr, s_tw512);
+    group_sync(g);
+    fft_pass<false>(j, 64, z1, z0, nullptr, nullptr, s_tw512);
+    group_sync(g);
     float* power = reinterpret_cast<float*>(z1);  // 513 floats fit in the 544-cpx scratch
-    unpack_power(j, z0, power, a.tw1024);
-    __syncthreads();
-    mel_project(j, a.num_mels, power, a.mel_start, a.mel_off, a.mel_w, outs + fl, kFramesPerBlock);
-    __syncthreads();
+    unpack_power(j, z0, power, s_tw1024);
+    group_sync(g);
+    mel_project(j, a.num_mels, power, s_start, s_off, s_melw, outs + fl, kFramesPerBlock);
+    group_sync(g);
   }
+  __syncthreads();
   // outs[m][fl] -> out[b][m][f0 + fl]
   float* ob = a.out + static_cast<size_t>(b) * a.num_mels * a.frames;
   for (int i = tid; i < a.num_mels * kFramesPerBlock; i += kMelThreads) {
@@ -451,11 +520,14 @@ extern "C" int hg_mel_fwd(const hg_mel_plan* plan, const float* y, int batch, in
   a.window = plan->window; a.tw512 = plan->tw512; a.tw1024 = plan->tw1024;
   a.mel_start = plan->mel_start; a.mel_off = plan->mel_off; a.mel_w = plan->mel_w;
   a.stage_len = (kFramesPerBlock - 1) * plan->hop + plan->n_fft;
-  const size_t smem = ((a.stage_len * 4 + 15) & ~15) + 2 * kGroups * kPadLen * sizeof(cpx) +
-                      static_cast<size_t>(plan->num_mels) * kFramesPerBlock * sizeof(float);
-  if (smem > 48 * 1024)
-    HG_CHECK_CUDA(cudaFuncSetAttribute(mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
+  a.nnz = plan->nnz;
+  const size_t smem = mel_smem_layout(a.stage_len, plan->num_mels, plan->nnz).total;
+  HG_REQUIRE(smem <= 227 * 1024, "hg_mel_fwd: hop_size %d needs %zu bytes of shared memory", plan->hop, smem);
+  static size_t configured = 0;
+  if (smem > configured) {
+    HG_CHECK_CUDA(cudaFuncSetAttribute(mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
   dim3 grid((frames + kFramesPerBlock - 1) / kFramesPerBlock, batch);
   mel_kernel<<<grid, kMelThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
   HG_CHECK_CUDA(cudaGetLastError());
