@@ -4,6 +4,8 @@ and the reference-generated golden fixtures.  Tolerances are stated where they a
 Declared numerics of the tensor-core path: bf16 operands and bf16-stored activations, fp32 accumulation.
 Measured noise floor on random-init weights (profiles/r01_bringup.md): waveform SNR 41-43 dB vs fp32.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -611,3 +613,16 @@ def test_inference_e2e_driver_matches_per_file_reference_schedule(H, O, tmp_path
             ref = (Gd(v.cuda()).squeeze() * 32768.0).cpu().numpy().astype("int16")
         assert sr == h.sampling_rate and wav.dtype == np.int16 and wav.shape == ref.shape
         assert np.array_equal(wav, ref), k
+
+
+def test_randomised_shapes_sweep():
+    """tests/gpu_fuzz.py, fixed seed: batch sizes, frame counts, audio lengths, (n_fft, hop, win) and training batch
+    sizes the fixed cases above do not hit — generators, discriminators (logits + all feature maps), mel and one
+    full training step (losses + every gradient) against the oracle, with the fixed tests' tolerances."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "gpu_fuzz.py"), "0", "8"], capture_output=True,
+                         text=True, cwd=root, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert "failures: 0" in out.stdout
