@@ -162,15 +162,19 @@ class _Lanes:
         return torch.cuda.stream(self.streams[i % len(self.streams)])
 
 
-def allreduce_gradients(flat: FlatParams, group=None) -> float:
-    """Data-parallel exchange step: SUM all-reduce of one network's flat gradient buffer over the process group
-    (NCCL over NVLink on the GPUs; gloo in the CPU tests).  Returns the factor the optimizer must apply to the summed
-    gradients (1 / world size) — the same averaging DistributedDataParallel performs for the reference."""
+def allreduce_gradients(flat: FlatParams, group=None, span: Optional[Tuple[int, int]] = None) -> float:
+    """Data-parallel exchange step: SUM all-reduce of one network's flat gradient buffer (or of elements [lo, hi) of it)
+    over the process group (NCCL over NVLink on the GPUs; gloo in the CPU tests).  Returns the factor the optimizer
+    must apply to the summed gradients (1 / world size) — the same averaging DistributedDataParallel performs for the
+    reference.  Every rank must issue these calls in the same order; NCCL runs them in that order on its own stream,
+    after the work already queued on the CALLER's current stream, and the caller's stream then waits for the result —
+    so slices issued from different lanes overlap with the lanes still computing."""
     if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
         return 1.0
     world = torch.distributed.get_world_size(group)
     if world > 1:
-        torch.distributed.all_reduce(flat.g, op=torch.distributed.ReduceOp.SUM, group=group)
+        g = flat.g if span is None else flat.g[span[0]:span[1]]
+        torch.distributed.all_reduce(g, op=torch.distributed.ReduceOp.SUM, group=group)
     return 1.0 / world
 
 
@@ -1030,9 +1034,9 @@ class DiscriminatorTrainer:
         sub-discriminator running its whole chain on its own lane:
             forward -> loss sums -> backward (parameter gradients) -> AdamW on its own slice of the flat buffers
             -> forward with the updated weights -> loss sums -> data gradient into dy_audio.
-        The lanes only meet at the end (and, data-parallel, around the gradient all-reduce), so a short chain (a period
-        discriminator) is already in its generator-step forward while the longest one (the spectral-norm scale) is
-        still in its backward.  Same arithmetic as forward / backward_d / adamw / forward / backward_g in sequence.
+        The lanes only meet at the end, so a short chain (a period discriminator) is already in its generator-step
+        forward while the longest one (the spectral-norm scale) is still in its backward; data-parallel, each lane
+        all-reduces its own gradient slice between its backward and its AdamW.  Same arithmetic as forward / backward_d / adamw / forward / backward_g in sequence.
         Returns (discriminator-step losses, generator-step losses); dy_audio fp32 [B][T] is ADDED to."""
         L = _lib.lib()
         b = self._inputs(y, y_hat)
@@ -1050,10 +1054,10 @@ class DiscriminatorTrainer:
                 sd.forward(self._input_of(i), b)
                 sd.loss_terms(self.acc_d, i * self.nslots, fm=False)
                 sd.backward_d()
-        if world > 1:
-            self.lanes.join()
-            allreduce(self.flat)
-            self.lanes.fork()
+                if world > 1:
+                    # this sub-discriminator's slice of the gradient buffer, exchanged as soon as its backward is
+                    # done: the collectives run in lane order on NCCL's stream while the later lanes still compute
+                    allreduce(self.flat, self.spans[i])
         for i, sd in enumerate(self.subs):
             with self.lanes.lane(i):
                 if update:
@@ -1114,8 +1118,8 @@ class TrainStep:
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
 
-    def _allreduce(self, flat: FlatParams) -> None:
-        allreduce_gradients(flat, self.pg)
+    def _allreduce(self, flat: FlatParams, span: Optional[Tuple[int, int]] = None) -> None:
+        allreduce_gradients(flat, self.pg, span)
 
     def _mel_plan(self):
         """the loss-mel plan (fmax_for_loss), created through the public function's cache"""

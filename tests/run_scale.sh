@@ -1,6 +1,6 @@
 #!/bin/bash
 # scaling evidence on one multi-GPU box: training step at N = 4, 8 and the default line (inference + train summary) at N = 8
-#   gpurun --gpus 8 --timeout 900 -- 'bash tests/run_scale.sh'
+#   gpurun --gpus 8 --timeout 900 -- 'bash tests/run_scale.sh [train-only]'
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 run() {  # N, log, extra args
@@ -11,4 +11,4 @@ run() {  # N, log, extra args
 }
 run 4 bench_train_4gpu.log --workload train --steps 20 --warmup 3
 run 8 bench_train_8gpu.log --workload train --steps 20 --warmup 3
-run 8 bench_default_8gpu.log --steps 10 --warmup 3
+[ "$1" = "train-only" ] || run 8 bench_default_8gpu.log --steps 10 --warmup 3

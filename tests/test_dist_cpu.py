@@ -68,7 +68,12 @@ def _dp_worker(rank, world, port, q):
     local = data[lo:hi].sum()
     for p in net.parameters():
         p.grad.fill_(float(local))          # stands in for this rank's summed per-sample gradients
-    scale = allreduce_gradients(flat)
+    # exchanged slice by slice, as the sub-discriminator lanes do (DiscriminatorTrainer.run_phases): the two convs'
+    # spans tile the buffer, so the result must equal one all-reduce of the whole buffer
+    spans = [flat.span_of(m) for m in net]
+    assert spans[0][0] == 0 and spans[0][1] == spans[1][0] and spans[1][1] == flat.numel
+    for sp in spans:
+        scale = allreduce_gradients(flat, span=sp)
     mean = (flat.g * scale)
     flat.p.sub_(0.1 * mean)
     q.put((rank, lo, hi, float(mean[0]), float(scale), flat.p.clone()))
