@@ -307,6 +307,20 @@ __device__ __forceinline__ void add_bf16x16(float (&v)[16], const U8& r) {
 }
 
 
+
+// cudaFuncSetAttribute is per DEVICE: launchers remember, per device ordinal, whether (or with which size) they
+// already raised a kernel's dynamic shared-memory limit.  One process may drive several GPUs.
+struct PerDeviceOnce {
+  size_t done[64] = {};
+  // true when `want` exceeds what was configured on the current device so far (and records it)
+  bool need(size_t want = 1) {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    if (done[d] >= want) return false;
+    done[d] = want;
+    return true;
+  }
+};
 }  // namespace hg
 
 // host-side: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda needed)

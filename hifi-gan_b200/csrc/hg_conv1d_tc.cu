@@ -702,12 +702,10 @@ int device_props() {
 template <int KC, int NT>
 int launch(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const ConvArgs& p, size_t smem_bytes,
            int grid, cudaStream_t st) {
-  static bool configured = false;  // per instantiation
-  if (!configured) {
+  static hg::PerDeviceOnce once;  // per instantiation
+  if (once.need())
     HG_CHECK_CUDA(cudaFuncSetAttribute(conv1d_tc_kernel<KC, NT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
-    configured = true;
-  }
   conv1d_tc_kernel<KC, NT><<<grid, kThreads, smem_bytes, st>>>(tm_x, tm_w, p);
   HG_CHECK_CUDA(cudaGetLastError());
   return HG_OK;
@@ -716,12 +714,10 @@ int launch(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const ConvArgs& p, 
 template <int NT>
 int launch2(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const ConvArgs& p, size_t smem_bytes, int grid,
             cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static hg::PerDeviceOnce once;
+  if (once.need())
     HG_CHECK_CUDA(cudaFuncSetAttribute(conv1d_tc2_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        g_max_smem));
-    configured = true;
-  }
   conv1d_tc2_kernel<NT><<<grid, kThreads, smem_bytes, st>>>(tm_x, tm_w, p);   // __cluster_dims__(2,1,1)
   HG_CHECK_CUDA(cudaGetLastError());
   return HG_OK;

@@ -500,11 +500,9 @@ extern "C" int hg_mel_fwd(const hg_mel_plan* plan, const float* y, int batch, in
   if (plan->n_fft != kNfft) {
     const size_t smem = static_cast<size_t>(plan->n_fft) * (sizeof(float2) + sizeof(float)) +
                         (plan->n_fft / 2 + 1) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static hg::PerDeviceOnce once;
+    if (once.need())
       HG_CHECK_CUDA(cudaFuncSetAttribute(mel_dft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      configured = true;
-    }
     dim3 grid(frames, batch);
     mel_dft_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
         y, t, frames, plan->n_fft, plan->hop, plan->pad, plan->num_mels, plan->window, plan->tw_n, plan->mel_start,
@@ -523,11 +521,9 @@ extern "C" int hg_mel_fwd(const hg_mel_plan* plan, const float* y, int batch, in
   a.nnz = plan->nnz;
   const size_t smem = mel_smem_layout(a.stage_len, plan->num_mels, plan->nnz).total;
   HG_REQUIRE(smem <= 227 * 1024, "hg_mel_fwd: hop_size %d needs %zu bytes of shared memory", plan->hop, smem);
-  static size_t configured = 0;
-  if (smem > configured) {
+  static hg::PerDeviceOnce once;
+  if (once.need(smem))
     HG_CHECK_CUDA(cudaFuncSetAttribute(mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   dim3 grid((frames + kFramesPerBlock - 1) / kFramesPerBlock, batch);
   mel_kernel<<<grid, kMelThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
   HG_CHECK_CUDA(cudaGetLastError());

@@ -434,12 +434,10 @@ int g_sms = 0, g_smem = 0;
 template <int C, bool kSingle>
 int launch_pair(const CUtensorMap& tx, const CUtensorMap& tw1, const CUtensorMap& tw2, const PairArgs& p,
                 size_t smem_bytes, int grid, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static hg::PerDeviceOnce once;
+  if (once.need())
     HG_CHECK_CUDA(cudaFuncSetAttribute(resblock_pair_kernel<C, kSingle>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem));
-    configured = true;
-  }
   resblock_pair_kernel<C, kSingle><<<grid, pair_threads(C), smem_bytes, st>>>(tx, tw1, tw2, p);
   HG_CHECK_CUDA(cudaGetLastError());
   return HG_OK;

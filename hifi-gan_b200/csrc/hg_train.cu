@@ -849,11 +849,9 @@ extern "C" int hg_disc_first_conv_bwd(const float* y, const float* w, const void
   dim3 grid((h_out + kFirstChunk - 1) / kFirstChunk, batch * period);
   const size_t smem = static_cast<size_t>(kFirstK) * cout * 4 + kFirstTile * kXPitch * 4 + kFirstTile * kFirstK * 4 +
                       2 * kFirstTile * kFirstK * 4 + static_cast<size_t>(kFirstTile) * (cout + 2) * 2;
-  static bool configured = false;
-  if (!configured) {
+  static hg::PerDeviceOnce once;
+  if (once.need())
     HG_CHECK_CUDA(cudaFuncSetAttribute(disc_first_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    configured = true;
-  }
   HG_REQUIRE(smem <= 96 * 1024, "hg_disc_first_conv_bwd: tile does not fit shared memory");
   disc_first_bwd_kernel<<<grid, 256, smem, S(stream)>>>(y, w, static_cast<const __nv_bfloat16*>(dpre), t, period, h_in,
                                                         h_out, h_rows, k, stride, pad, cout, dw, db, dy);

@@ -243,12 +243,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 int g_sms = 0, g_smem = 0;
 
 int props() {
-  if (g_sms) return HG_OK;
-  int dev = 0;
-  HG_CHECK_CUDA(cudaGetDevice(&dev));
-  HG_CHECK_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
-  HG_CHECK_CUDA(cudaDeviceGetAttribute(&g_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  HG_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem));
+  if (!g_sms) {
+    int dev = 0;
+    HG_CHECK_CUDA(cudaGetDevice(&dev));
+    HG_CHECK_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+    HG_CHECK_CUDA(cudaDeviceGetAttribute(&g_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  }
+  static hg::PerDeviceOnce once;
+  if (once.need())
+    HG_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem));
   return HG_OK;
 }
 
