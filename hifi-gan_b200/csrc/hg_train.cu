@@ -251,7 +251,7 @@ disc_last_bwd_dw_kernel(const __nv_bfloat16* __restrict__ x, const float* __rest
 // product accumulated in registers across tiles (column k is the bias), the audio gradient one thread pair per
 // position.  One atomic per output per block.
 constexpr int kFirstTile = 128;
-constexpr int kFirstChunk = 1024;
+constexpr int kFirstChunk = 256;    // 2 tiles per block: the MSD launches (16-32 sequences of 8192) fill the GPU (was 1024: 48-128 blocks)
 constexpr int kFirstK = 16;
 constexpr int kXPitch = 20;   // floats per staged input row (16-byte multiple)
 
