@@ -334,9 +334,23 @@ extern "C" int hg_conv1d_wgrad(const void* x, const void* dy, int batch, int t_i
   HG_REQUIRE(stages >= 2, "hg_conv1d_wgrad: not enough shared memory");
   p.stages = stages;
   const int items = p.tiles_n * p.n_cpairs * p.n_tapgroups;
-  int nsplit = (2 * g_sms + items - 1) / items;           // about two waves of CTAs
-  if (nsplit > p.total_chunks) nsplit = p.total_chunks;
-  if (nsplit < 1) nsplit = 1;
+  // Time splits per item.  A CTA costs (its chunks + an epilogue worth about two chunks: TMEM -> red.global of its
+  // tiles) and the grid runs in ceil(CTAs / resident CTAs) rounds, so pick the split that minimises
+  // rounds x (chunks / split + 2) instead of a fixed "about two waves" (which left e.g. the 1024 -> 1024 k = 5 layer
+  // with 384 CTAs = 2.6 rounds of 148).
+  const size_t smem_cta = 1024 + static_cast<size_t>(stages) * p.stage_bytes + sizeof(Bars);
+  const int per_sm = smem_cta * 2 + 2048 <= static_cast<size_t>(228 * 1024) ? 2 : 1;
+  const int resident = g_sms * per_sm;
+  int nsplit = 1;
+  double best = 1e30;
+  const int max_split = p.total_chunks < 4 * g_sms ? p.total_chunks : 4 * g_sms;
+  for (int cand = 1; cand <= max_split; ++cand) {
+    const int ctas = items * cand;
+    if (ctas > 4 * resident && cand > 1) break;
+    const int rounds = (ctas + resident - 1) / resident;
+    const double cost = rounds * (static_cast<double>((p.total_chunks + cand - 1) / cand) + 2.0);
+    if (cost < best - 1e-9) { best = cost; nsplit = cand; }
+  }
   p.nsplit = nsplit;
   p.dw = dw_packed;
 
