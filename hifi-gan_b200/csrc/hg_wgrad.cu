@@ -21,6 +21,8 @@
 // grid = items x splits: item = (N tile / group, channel pair, tap group), split = slice of the time chunks.
 #include "hg_common.cuh"
 
+#include <cstdlib>
+
 #include <atomic>
 
 #include "../../include/hifigan_b200.h"
@@ -340,7 +342,14 @@ extern "C" int hg_conv1d_wgrad(const void* x, const void* dy, int batch, int t_i
   // with 384 CTAs = 2.6 rounds of 148).
   const size_t smem_cta = 1024 + static_cast<size_t>(stages) * p.stage_bytes + sizeof(Bars);
   const int per_sm = smem_cta * 2 + 2048 <= static_cast<size_t>(228 * 1024) ? 2 : 1;
-  const int resident = g_sms * per_sm;
+  // Tuning knobs.  HG_WGRAD_FILL = fraction of the resident CTA slots one round may use, HG_WGRAD_EPI = epilogue cost
+  // in chunks.  Weight-gradient launches run on low-priority lanes BESIDE the data-gradient chain and other
+  // sub-discriminators, so what the step pays for is their SM-time, not their latency: measured on the batch-16 step
+  // (ms/step) fill 1.0: 12.88, 0.75: 12.65, 0.5: 12.54, 0.35: 12.46, 0.25: 12.65 (the fixed two waves before: 13.55).
+  static const double fill = [] { const char* e = std::getenv("HG_WGRAD_FILL"); return e ? std::atof(e) : 0.4; }();
+  static const double epi = [] { const char* e = std::getenv("HG_WGRAD_EPI"); return e ? std::atof(e) : 2.0; }();
+  int resident = static_cast<int>(g_sms * per_sm * fill);
+  if (resident < 1) resident = 1;
   int nsplit = 1;
   double best = 1e30;
   const int max_split = p.total_chunks < 4 * g_sms ? p.total_chunks : 4 * g_sms;
@@ -348,7 +357,7 @@ extern "C" int hg_conv1d_wgrad(const void* x, const void* dy, int batch, int t_i
     const int ctas = items * cand;
     if (ctas > 4 * resident && cand > 1) break;
     const int rounds = (ctas + resident - 1) / resident;
-    const double cost = rounds * (static_cast<double>((p.total_chunks + cand - 1) / cand) + 2.0);
+    const double cost = rounds * (static_cast<double>((p.total_chunks + cand - 1) / cand) + epi);
     if (cost < best - 1e-9) { best = cost; nsplit = cand; }
   }
   p.nsplit = nsplit;
