@@ -483,23 +483,28 @@ __device__ __forceinline__ float packed_dw(const float* __restrict__ p, const Un
 __global__ void __launch_bounds__(256)
 wgrad_finish_kernel(const float* __restrict__ p, const UnpackArgs a, const float* __restrict__ v,
                     const float* __restrict__ g, int accumulate, float* __restrict__ dv, float* __restrict__ dg) {
+  extern __shared__ float sdw[];                 // this row's gradient in parameter order [d1][k]
   __shared__ float red[32];
   const int r = blockIdx.x;
   const int rest = a.d1 * a.k;
   const float* vr = v + static_cast<size_t>(r) * rest;
   float* o = dv + static_cast<size_t>(r) * rest;
+  // gather tap plane by tap plane: the packed layout is contiguous along d1 inside a plane (conv), so the reads
+  // coalesce; the transposing writes go to shared memory (stride k words)
+  for (int idx = threadIdx.x; idx < rest; idx += blockDim.x) {
+    const int j = idx / a.d1, i1 = idx - j * a.d1;
+    sdw[i1 * a.k + j] = packed_dw(p, a, r, i1, j);
+  }
+  __syncthreads();
   if (!g) {
-    for (int i = threadIdx.x; i < rest; i += blockDim.x) {
-      const float d = packed_dw(p, a, r, i / a.k, i % a.k);
-      o[i] = accumulate ? o[i] + d : d;
-    }
+    for (int i = threadIdx.x; i < rest; i += blockDim.x) o[i] = accumulate ? o[i] + sdw[i] : sdw[i];
     return;
   }
   float ss = 0.f, dot = 0.f;
   for (int i = threadIdx.x; i < rest; i += blockDim.x) {
     const float vv = vr[i];
     ss += vv * vv;
-    dot += vv * packed_dw(p, a, r, i / a.k, i % a.k);
+    dot += vv * sdw[i];
   }
   ss = block_sum(ss, red);
   dot = block_sum(dot, red);
@@ -507,7 +512,7 @@ wgrad_finish_kernel(const float* __restrict__ p, const UnpackArgs a, const float
   const float inv = nrm > 0.f ? 1.f / nrm : 0.f;
   const float gg = g[r];
   for (int i = threadIdx.x; i < rest; i += blockDim.x) {
-    const float val = gg * inv * (packed_dw(p, a, r, i / a.k, i % a.k) - vr[i] * dot * inv * inv);
+    const float val = gg * inv * (sdw[i] - vr[i] * dot * inv * inv);
     o[i] = accumulate ? o[i] + val : val;
   }
   if (threadIdx.x == 0) dg[r] = accumulate ? dg[r] + dot * inv : dot * inv;
@@ -1037,7 +1042,8 @@ extern "C" int hg_wgrad_finish_conv(const float* dw_packed, int cout, int cin_g,
   a.mode = 0; a.d0 = cout; a.d1 = cin_g; a.k = k; a.rows_p = rows_p; a.cin_tile = cin_tile;
   a.cout_g = cout_g; a.merge = merge;
   for (int q = 0; q < k; ++q) a.pos[host_tap_order ? host_tap_order[q] : q] = q;
-  wgrad_finish_kernel<<<cout, 256, 0, S(stream)>>>(dw_packed, a, v, g, accumulate, dv, dg);
+  HG_REQUIRE(static_cast<size_t>(cin_g) * k * 4 <= 48 * 1024, "hg_wgrad_finish_conv: row of %d values does not fit", cin_g * k);
+  wgrad_finish_kernel<<<cout, 256, static_cast<size_t>(cin_g) * k * 4, S(stream)>>>(dw_packed, a, v, g, accumulate, dv, dg);
   HG_CHECK_CUDA(cudaGetLastError());
   count();
   return HG_OK;
@@ -1054,7 +1060,8 @@ extern "C" int hg_wgrad_finish_convtr(const float* dw_packed, int cin, int cout,
   UnpackArgs a{};
   a.mode = 1; a.d0 = cin; a.d1 = cout; a.k = k; a.rows_p = stride * cout_p; a.cin_tile = cin_p;
   a.stride = stride; a.padding = padding; a.shift_min = smin; a.cout_p = cout_p;
-  wgrad_finish_kernel<<<cin, 256, 0, S(stream)>>>(dw_packed, a, v, g, accumulate, dv, dg);
+  HG_REQUIRE(static_cast<size_t>(cout) * k * 4 <= 48 * 1024, "hg_wgrad_finish_convtr: row of %d values does not fit", cout * k);
+  wgrad_finish_kernel<<<cin, 256, static_cast<size_t>(cout) * k * 4, S(stream)>>>(dw_packed, a, v, g, accumulate, dv, dg);
   HG_CHECK_CUDA(cudaGetLastError());
   count();
   return HG_OK;
