@@ -1,11 +1,12 @@
 // hg_mel.cu — mel_spectrogram (src/meldataset.py:56-85) as ONE fused kernel:
 //   reflect-pad -> frame x periodic Hann -> rFFT(1024) -> |X|^2 -> HTK mel (sparse) -> log(clamp(.,1e-5))
 // The reference goes through torchaudio.transforms.MelSpectrogram (meldataset.py:59-71): >= 6 library
-// launches and three HBM round trips of the [B,513,F] spectrum.  Here a block of 256 threads owns 8
-// consecutive frames: the 2816-sample input window is staged once in shared memory, each 64-thread
-// group runs a 512-point complex Stockham FFT (radix 8 x 8 x 8) per frame on the even/odd packed
-// samples, un-packs the real spectrum, accumulates the triangular mel filters from a CSR table and the
-// block writes [80][8] outputs with 32-byte contiguous runs.
+// launches and three HBM round trips of the [B,513,F] spectrum.  Here a block of 512 threads owns 16
+// consecutive frames: the 4864-sample input window and the constant tables (window, twiddles, CSR filterbank)
+// are brought into shared memory with one round of cp.async copies, each 64-thread group runs a 512-point
+// complex Stockham FFT (radix 8 x 8 x 8) per frame on the even/odd packed samples (two frames per group, the
+// group's two warps meeting on their own named barrier), un-packs the real spectrum, accumulates the
+// triangular mel filters from the CSR table and the block writes [80][16] outputs with 64-byte contiguous runs.
 //
 // The per-thread phases are __host__ __device__ so tests can run the exact same arithmetic on the CPU
 // (hg_mel_emulate_host below) — there is no GPU in the development container.
