@@ -356,6 +356,21 @@ def test_mel_range_warning_is_lazy_but_kept(H, capsys):
     assert "max value is" in capsys.readouterr().out
 
 
+@pytest.mark.parametrize("hop,win,t,b", [(100, 1024, 9001, 3), (250, 1000, 22050, 2), (255, 1024, 8192, 5),
+                                         (512, 512, 70001, 1), (1024, 1024, 40000, 2), (256, 1024, 8190, 4),
+                                         (64, 1024, 5000, 2)])
+def test_mel_unaligned_hops_and_lengths(H, O, hop, win, t, b):
+    """The fused n_fft = 1024 kernel stages its input with 16-byte cp.async copies when (length, hop) allow and
+    4-byte ones otherwise, and a block's last frames may be missing: hop sizes / lengths on both sides of every one
+    of those conditions against the fp64 oracle (log domain, bins within 60 dB of the frame peak, 2e-4)."""
+    y = O.synthetic_audio(b, t, seed=hop + t)
+    ref = O.mel_spectrogram(y.double(), 1024, 80, 22050, hop, win, 0, 8000)
+    got = H.mel_spectrogram(y.cuda(), 1024, 80, 22050, hop, win, 0, 8000).cpu().double()
+    assert got.shape == ref.shape
+    loud = ref > ref.max(dim=1, keepdim=True).values - 13.8
+    assert (got - ref).abs()[loud].max().item() < 2e-4
+
+
 @pytest.mark.parametrize("case", range(4))
 def test_mel_other_shapes_vs_reference_golden(H, case):
     """mel_spectrogram at the shapes of the reference's other callers (n_fft != 1024, 16 kHz, fmax None,
