@@ -534,72 +534,146 @@ extern "C" int hg_mel_fwd(const hg_mel_plan* plan, const float* y, int batch, in
 
 // ---------------------------------------------------------------------------------------------
 // mel_spectrogram backward (the generated-mel L1 term of the generator loss, UPSTREAM train.py: F.l1_loss(y_mel,
-// y_g_hat_mel) * 45 through src/meldataset.py:78-83).  One block per frame: recompute the windowed frame's
-// 513-bin spectrum with a direct DFT (training segments are 32 frames per item: 2 MFLOP per frame is nothing),
-// push dL/dlogmel back through log-clamp, the CSR filterbank and |X|^2, take the adjoint DFT, window, and
-// scatter-add into dy with the reflect padding folded back.
+// y_g_hat_mel) * 45 through src/meldataset.py:78-83).  One 64-thread group per frame, the forward kernel's own FFT:
+//   recompute Z = FFT512(packed windowed frame), un-pack X[0..512] (kept complex) and |X|^2, the CSR mel sums;
+//   dmel = g / mel above the 1e-5 clamp (0 below), dP[k] = sum_m fb[m][k] dmel[m], G[k] = 2 dP[k] X[k];
+//   the gradient at the windowed samples is S[n] = Re sum_{k=0..512} G[k] e^{+2 pi i k n / 1024}: the real inverse
+//   transform of the Hermitian spectrum H (H[k] = G[k] / 2, H[0] = Re G[0], H[512] = Re G[512]), taken as ONE
+//   512-point complex transform of Zc[k] = (H[k] + conj H[512-k]) + i e^{+2 pi i k / 1024} (H[k] - conj H[512-k])
+//   (S[2m] + i S[2m+1] = sum_k Zc[k] e^{+2 pi i m k / 512}), run through the same forward passes on conj(Zc);
+//   then the window, and a scatter-add into dy with the reflect padding folded back.
+// The phases are __host__ __device__ (hg_mel_bwd_emulate_host runs them with the threads serialised).
 namespace {
 
-__global__ void __launch_bounds__(256)
+// un-pack the real spectrum, keeping X complex: bins k = tid, tid + 64, ... (0..512)
+__host__ __device__ __forceinline__ void unpack_spectrum(int tid, const cpx* __restrict__ z, cpx* __restrict__ X,
+                                                         float* __restrict__ power,
+                                                         const float2* __restrict__ tw1024) {
+  for (int k = tid; k <= kHalf; k += kGroupThreads) {
+    const cpx zk = z[padi(k & (kHalf - 1))];
+    cpx zc = z[padi((kHalf - k) & (kHalf - 1))];
+    zc.y = -zc.y;
+    const cpx e = cpx{0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y)};
+    const cpx d = csub(zk, zc);
+    const cpx o = cpx{0.5f * d.y, -0.5f * d.x};  // (zk - zc) / (2i)
+    const float2 w = tw1024[k];
+    const cpx x = cadd(e, cmul(o, cpx{w.x, w.y}));
+    X[k] = x;
+    power[k] = x.x * x.x + x.y * x.y;
+  }
+}
+// dm[m] = g[m] / mel[m] above the clamp, else 0 (m = tid, tid + 64, ...); also clears dP for the scatter
+__host__ __device__ __forceinline__ void mel_grad(int tid, int num_mels, const float* __restrict__ power,
+                                                  const int* __restrict__ mel_start, const int* __restrict__ mel_off,
+                                                  const float* __restrict__ mel_w, const float* __restrict__ g_col,
+                                                  int g_stride, float* __restrict__ dm, float* __restrict__ dp) {
+  for (int k = tid; k <= kHalf; k += kGroupThreads) dp[k] = 0.f;
+  for (int m = tid; m < num_mels; m += kGroupThreads) {
+    const int s = mel_start[m], o = mel_off[m], n = mel_off[m + 1] - o;
+    float acc = 0.f;
+    for (int i = 0; i < n; ++i) acc += mel_w[o + i] * power[s + i];
+    dm[m] = acc > 1e-5f ? g_col[static_cast<size_t>(m) * g_stride] / acc : 0.f;   // clamp(min=1e-5): no gradient below
+  }
+}
+// dP[k] += fb[m][k] * dm[m]
+template <bool DEVICE>
+__host__ __device__ __forceinline__ void mel_scatter(int tid, int num_mels, const int* __restrict__ mel_start,
+                                                     const int* __restrict__ mel_off, const float* __restrict__ mel_w,
+                                                     const float* __restrict__ dm, float* __restrict__ dp) {
+  for (int m = tid; m < num_mels; m += kGroupThreads) {
+    const int s = mel_start[m], o = mel_off[m], n = mel_off[m + 1] - o;
+    const float d = dm[m];
+    for (int i = 0; i < n; ++i) {
+#ifdef __CUDA_ARCH__
+      atomicAdd(dp + s + i, mel_w[o + i] * d);
+#else
+      dp[s + i] += mel_w[o + i] * d;
+#endif
+    }
+  }
+}
+// conj(Zc)[k] for k = tid, tid + 64, ... (0..511) into the padded FFT buffer
+__host__ __device__ __forceinline__ void build_adjoint_input(int tid, const cpx* __restrict__ X,
+                                                             const float* __restrict__ dp, cpx* __restrict__ out,
+                                                             const float2* __restrict__ tw1024) {
+  auto hk = [&](int k) -> cpx {
+    const float d = dp[k];
+    if (k == 0 || k == kHalf) return cpx{2.f * d * X[k].x, 0.f};
+    return cpx{d * X[k].x, d * X[k].y};
+  };
+  for (int k = tid; k < kHalf; k += kGroupThreads) {
+    const cpx a = hk(k);
+    cpx b = hk(kHalf - k);
+    b.y = -b.y;
+    const cpx sum = cadd(a, b), dif = csub(a, b);
+    const float2 w = tw1024[k];                       // e^{-2 pi i k / 1024}; its conjugate is needed
+    const cpx rot = cmul(dif, cpx{w.x, -w.y});        // e^{+2 pi i k / 1024} (a - b)
+    const cpx zc = cpx{sum.x - rot.y, sum.y + rot.x};  // sum + i * rot
+    out[padi(k)] = cpx{zc.x, -zc.y};
+  }
+}
+// samples 2m, 2m+1 of the frame's gradient from R = FFT512(conj Zc): S[2m] = R[m].x, S[2m+1] = -R[m].y
+template <bool DEVICE>
+__host__ __device__ __forceinline__ void scatter_frame(int tid, const cpx* __restrict__ r, const float* __restrict__ window,
+                                                       int frame_start, int t, float* __restrict__ dy_row) {
+  for (int m = tid; m < kHalf; m += kGroupThreads) {
+    const cpx v = r[padi(m)];
+    const float s0 = v.x * window[2 * m], s1 = -v.y * window[2 * m + 1];
+    const int i0 = reflect_index(frame_start + 2 * m, t), i1 = reflect_index(frame_start + 2 * m + 1, t);
+#ifdef __CUDA_ARCH__
+    atomicAdd(dy_row + i0, s0);
+    atomicAdd(dy_row + i1, s1);
+#else
+    dy_row[i0] += s0;
+    dy_row[i1] += s1;
+#endif
+  }
+}
+
+constexpr int kBwdGroups = 2;                       // frames per block (39 KB of static shared memory)
+
+__global__ void __launch_bounds__(kBwdGroups* kGroupThreads)
 mel_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dmel, int t, int frames, int hop, int pad,
-               int num_mels, const float* __restrict__ window, const int* __restrict__ mel_start,
-               const int* __restrict__ mel_off, const float* __restrict__ mel_w, float* __restrict__ dy) {
-  __shared__ float xw[kNfft];
-  __shared__ float2 tw[kNfft];
-  __shared__ float re[kHalf + 1], im[kHalf + 1], dp[kHalf + 1];
-  __shared__ float dm[128];
-  const int f = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+               int num_mels, const float* __restrict__ window, const float2* __restrict__ tw512,
+               const float2* __restrict__ tw1024, const int* __restrict__ mel_start, const int* __restrict__ mel_off,
+               const float* __restrict__ mel_w, float* __restrict__ dy) {
+  __shared__ float smp[kBwdGroups][kNfft];
+  __shared__ cpx zbuf[kBwdGroups][2][kPadLen];
+  __shared__ cpx xs[kBwdGroups][kHalf + 1];
+  __shared__ float dps[kBwdGroups][kHalf + 1];
+  __shared__ float dms[kBwdGroups][128];
+  const int g = threadIdx.x / kGroupThreads, j = threadIdx.x % kGroupThreads;
+  const int f = blockIdx.x * kBwdGroups + g, b = blockIdx.y;
+  if (f >= frames) return;                          // group-uniform; the groups only meet on their own barriers
   const float* yb = y + static_cast<size_t>(b) * t;
-  for (int n = tid; n < kNfft; n += 256) {
-    int i = f * hop + n - pad;
-    if (i < 0) i = -i;
-    if (i >= t) i = 2 * (t - 1) - i;
-    xw[n] = yb[i] * window[n];
-    float sn, cs;
-    sincospif(static_cast<float>(n) * (2.0f / kNfft), &sn, &cs);
-    tw[n] = make_float2(cs, sn);
-  }
-  for (int k = tid; k <= kHalf; k += 256) dp[k] = 0.f;
-  __syncthreads();
-  for (int k = tid; k <= kHalf; k += 256) {
-    float ar = 0.f, ai = 0.f;
-    for (int n = 0; n < kNfft; ++n) {
-      const float2 c = tw[(k * n) & (kNfft - 1)];
-      ar += xw[n] * c.x;
-      ai -= xw[n] * c.y;
-    }
-    re[k] = ar; im[k] = ai;
-  }
-  __syncthreads();
-  if (tid < num_mels) {
-    const int k0 = mel_start[tid], o0 = mel_off[tid], cnt = mel_off[tid + 1] - o0;
-    float m = 0.f;
-    for (int i = 0; i < cnt; ++i) m += mel_w[o0 + i] * (re[k0 + i] * re[k0 + i] + im[k0 + i] * im[k0 + i]);
-    const float g = dmel[(static_cast<size_t>(b) * num_mels + tid) * frames + f];
-    dm[tid] = m > 1e-5f ? g / m : 0.f;      // clamp(min=1e-5) passes no gradient below the floor
-  }
-  __syncthreads();
-  if (tid < num_mels) {
-    const int k0 = mel_start[tid], o0 = mel_off[tid], cnt = mel_off[tid + 1] - o0;
-    for (int i = 0; i < cnt; ++i) atomicAdd(&dp[k0 + i], mel_w[o0 + i] * dm[tid]);
-  }
-  __syncthreads();
-  for (int k = tid; k <= kHalf; k += 256) {
-    const float g = 2.f * dp[k];
-    re[k] *= g; im[k] *= g;                 // dL/dRe, dL/dIm
-  }
-  __syncthreads();
-  for (int n = tid; n < kNfft; n += 256) {
-    float a = 0.f;
-    for (int k = 0; k <= kHalf; ++k) {
-      const float2 c = tw[(k * n) & (kNfft - 1)];
-      a += re[k] * c.x - im[k] * c.y;
-    }
-    int i = f * hop + n - pad;
-    if (i < 0) i = -i;
-    if (i >= t) i = 2 * (t - 1) - i;
-    atomicAdd(dy + static_cast<size_t>(b) * t + i, a * window[n]);
-  }
+  const int start = f * hop - pad;
+  for (int n = j; n < kNfft; n += kGroupThreads) smp[g][n] = yb[reflect_index(start + n, t)];
+  group_sync(g);
+  cpx* z0 = zbuf[g][0];
+  cpx* z1 = zbuf[g][1];
+  fft_pass<true>(j, 1, nullptr, z0, smp[g], window, tw512);
+  group_sync(g);
+  fft_pass<false>(j, 8, z0, z1, nullptr, nullptr, tw512);
+  group_sync(g);
+  fft_pass<false>(j, 64, z1, z0, nullptr, nullptr, tw512);
+  group_sync(g);
+  float* power = reinterpret_cast<float*>(z1);
+  unpack_spectrum(j, z0, xs[g], power, tw1024);
+  group_sync(g);
+  mel_grad(j, num_mels, power, mel_start, mel_off, mel_w, dmel + static_cast<size_t>(b) * num_mels * frames + f, frames,
+           dms[g], dps[g]);
+  group_sync(g);
+  mel_scatter<true>(j, num_mels, mel_start, mel_off, mel_w, dms[g], dps[g]);
+  group_sync(g);
+  build_adjoint_input(j, xs[g], dps[g], z1, tw1024);
+  group_sync(g);
+  fft_pass<false>(j, 1, z1, z0, nullptr, nullptr, tw512);
+  group_sync(g);
+  fft_pass<false>(j, 8, z0, z1, nullptr, nullptr, tw512);
+  group_sync(g);
+  fft_pass<false>(j, 64, z1, z0, nullptr, nullptr, tw512);
+  group_sync(g);
+  scatter_frame<true>(j, z0, window, start, t, dy + static_cast<size_t>(b) * t);
 }
 
 }  // namespace
@@ -613,12 +687,48 @@ extern "C" int hg_mel_bwd(const hg_mel_plan* plan, const float* y, const float* 
   HG_REQUIRE(batch > 0 && batch <= 65535 && t > plan->pad && plan->num_mels <= 128, "hg_mel_bwd: bad arguments");
   const int frames = hg_mel_num_frames(plan, t);
   HG_REQUIRE(frames > 0, "hg_mel_bwd: input too short for one frame");
-  dim3 grid(frames, batch);
-  mel_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, dmel, t, frames, plan->hop, plan->pad,
-                                                                      plan->num_mels, plan->window, plan->mel_start,
-                                                                      plan->mel_off, plan->mel_w, dy);
+  dim3 grid((frames + kBwdGroups - 1) / kBwdGroups, batch);
+  mel_bwd_kernel<<<grid, kBwdGroups * kGroupThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      y, dmel, t, frames, plan->hop, plan->pad, plan->num_mels, plan->window, plan->tw512, plan->tw1024,
+      plan->mel_start, plan->mel_off, plan->mel_w, dy);
   HG_CHECK_CUDA(cudaGetLastError());
   g_hg_launches.fetch_add(1, std::memory_order_relaxed);
+  return HG_OK;
+}
+
+// Test hook: the backward kernel's phase functions on the HOST (threads serialised).  host_y fp32 [B][T],
+// host_dmel fp32 [B][num_mels][frames], host_dy fp32 [B][T] is ADDED to.
+extern "C" int hg_mel_bwd_emulate_host(const hg_mel_plan* plan, const float* host_y, const float* host_dmel,
+                                       int batch, int t, float* host_dy) {
+  HG_REQUIRE(plan && host_y && host_dmel && host_dy, "hg_mel_bwd_emulate_host: null pointer");
+  HG_REQUIRE(plan->n_fft == kNfft, "hg_mel_bwd_emulate_host: only n_fft == 1024 is implemented");
+  const int frames = hg_mel_num_frames(plan, t);
+  HG_REQUIRE(frames > 0 && t > plan->pad, "hg_mel_bwd_emulate_host: input too short");
+  std::vector<float> smp(plan->n_fft), dp(kHalf + 1), dm(128);
+  std::vector<cpx> z0(kPadLen), z1(kPadLen), X(kHalf + 1);
+  const float* win = plan->h_window.data();
+  const float2 *t512 = plan->h_tw512.data(), *t1024 = plan->h_tw1024.data();
+  const int *ms = plan->h_mel_start.data(), *mo = plan->h_mel_off.data();
+  const float* mw = plan->h_mel_w.data();
+  for (int b = 0; b < batch; ++b)
+    for (int f = 0; f < frames; ++f) {
+      const int start = f * plan->hop - plan->pad;
+      for (int n = 0; n < plan->n_fft; ++n) smp[n] = host_y[static_cast<size_t>(b) * t + reflect_index(start + n, t)];
+      for (int j = 0; j < 64; ++j) fft_pass<true>(j, 1, nullptr, z0.data(), smp.data(), win, t512);
+      for (int j = 0; j < 64; ++j) fft_pass<false>(j, 8, z0.data(), z1.data(), nullptr, nullptr, t512);
+      for (int j = 0; j < 64; ++j) fft_pass<false>(j, 64, z1.data(), z0.data(), nullptr, nullptr, t512);
+      float* power = reinterpret_cast<float*>(z1.data());
+      for (int j = 0; j < 64; ++j) unpack_spectrum(j, z0.data(), X.data(), power, t1024);
+      for (int j = 0; j < 64; ++j)
+        mel_grad(j, plan->num_mels, power, ms, mo, mw, host_dmel + static_cast<size_t>(b) * plan->num_mels * frames + f,
+                 frames, dm.data(), dp.data());
+      for (int j = 0; j < 64; ++j) mel_scatter<false>(j, plan->num_mels, ms, mo, mw, dm.data(), dp.data());
+      for (int j = 0; j < 64; ++j) build_adjoint_input(j, X.data(), dp.data(), z1.data(), t1024);
+      for (int j = 0; j < 64; ++j) fft_pass<false>(j, 1, z1.data(), z0.data(), nullptr, nullptr, t512);
+      for (int j = 0; j < 64; ++j) fft_pass<false>(j, 8, z0.data(), z1.data(), nullptr, nullptr, t512);
+      for (int j = 0; j < 64; ++j) fft_pass<false>(j, 64, z1.data(), z0.data(), nullptr, nullptr, t512);
+      for (int j = 0; j < 64; ++j) scatter_frame<false>(j, z0.data(), win, start, t, host_dy + static_cast<size_t>(b) * t);
+    }
   return HG_OK;
 }
 

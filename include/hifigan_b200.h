@@ -201,10 +201,15 @@ int hg_mel_fwd(const hg_mel_plan* plan, const float* y, int batch, int t, float*
                float* minmax, void* stream);
 
 /* hg_mel_bwd — backward of hg_mel_fwd: dmel fp32 [B][num_mels][frames] (gradient at the log-mel output) ->
- * dy fp32 [B][T] ADDED to (zero it first).  y is the forward input; the spectrum is recomputed.
- * n_fft == 1024 only (the training configs). */
+ * dy fp32 [B][T] ADDED to (zero it first).  y is the forward input; the spectrum is recomputed with the forward
+ * kernel's FFT and the adjoint is one more 512-point transform per frame.  n_fft == 1024 only (the training configs). */
 int hg_mel_bwd(const hg_mel_plan* plan, const float* y, const float* dmel, int batch, int t, float* dy,
                void* stream);
+
+/* Test hook: the backward kernel's phase functions on the HOST (threads serialised).  host_y fp32 [B][T], host_dmel
+ * fp32 [B][num_mels][frames]; host_dy fp32 [B][T] is ADDED to.  n_fft == 1024 only. */
+int hg_mel_bwd_emulate_host(const hg_mel_plan* plan, const float* host_y, const float* host_dmel, int batch, int t,
+                            float* host_dy);
 
 /* Test hook: runs the mel kernel's per-thread phase functions on the HOST (threads serialised) so
  * the FFT / un-pack / CSR-mel arithmetic can be pinned without a GPU.  host_y, host_out are HOST
