@@ -347,3 +347,28 @@ def test_mel_backward_kernel_arithmetic_on_host_vs_autograd(fmax, t):
         err = np.abs(dy[i] - ref[i]).max() / np.abs(ref[i]).max()
         cos = float(np.dot(dy[i], ref[i]) / (np.linalg.norm(dy[i]) * np.linalg.norm(ref[i])))
         assert err < 2e-3 and cos > 0.99999, (i, err, cos)
+
+
+@pytest.mark.parametrize("workload", ["cfg1", "train"])
+def test_bench_reference_arm_contract(workload):
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints ONE JSON line with the contract's
+    keys, runs without a GPU, and — under torchrun-style env with RANK != 0 — exits 0 without work."""
+    import json
+    import subprocess
+    import sys
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", workload, "--steps", "1",
+           "--warmup", "0"]
+    out = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["vs_baseline"] is None and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    other = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, cwd=ROOT, timeout=600, env=env)
+    assert other.returncode == 0 and not [l for l in other.stdout.splitlines() if l.startswith("{")]
