@@ -6,10 +6,12 @@ kernel raises.  Nothing here touches `oracle/`.
 from __future__ import annotations
 
 import ctypes
+import hashlib
 import os
 import shutil
 import subprocess
 import threading
+import time
 from ctypes import POINTER, byref, c_char_p, c_double, c_float, c_int, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -28,30 +30,75 @@ class HgError(RuntimeError):
     pass
 
 
-def _stale() -> bool:
-    if not os.path.exists(LIB_PATH):
-        return True
-    lib_m = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+HASH_PATH = os.path.join(_HERE, "libhifigan_b200.srchash")
+_LOCK_PATH = os.path.join(_HERE, ".build.lock")
+
+
+def _source_hash() -> str:
+    """Content hash of everything the library is compiled from (file times do not survive the copy to a GPU box)."""
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC))
     deps.append(os.path.join(os.path.dirname(_HERE), "include", "hifigan_b200.h"))
-    return any(os.path.getmtime(d) > lib_m for d in deps if os.path.exists(d))
+    for d in deps:
+        if os.path.exists(d):
+            h.update(os.path.basename(d).encode())
+            with open(d, "rb") as f:
+                h.update(f.read())
+    return h.hexdigest()
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
+        return True
+    with open(HASH_PATH) as f:
+        return f.read().strip() != _source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every kernel for sm_100a into hifi-gan_b200/libhifigan_b200.so (in-tree)."""
+    """Compile every kernel for sm_100a into hifi-gan_b200/libhifigan_b200.so (in-tree).  Safe against several
+    processes (torchrun ranks) arriving at once: one compiles into a temporary file under a lock file and renames it
+    into place, the others wait for the lock and find the library fresh."""
     if not force and not _stale():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise HgError("nvcc not found: cannot build libhifigan_b200.so")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise HgError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    deadline = time.time() + 900
+    while True:
+        try:
+            fd = os.open(_LOCK_PATH, os.O_CREAT | os.O_EXCL | os.O_WRONLY)
+            os.close(fd)
+            break
+        except FileExistsError:
+            if time.time() > deadline or time.time() - os.path.getmtime(_LOCK_PATH) > 900:
+                try:
+                    os.unlink(_LOCK_PATH)           # a builder died: take over
+                except FileNotFoundError:
+                    pass
+            time.sleep(0.5)
+    try:
+        if not force and not _stale():              # somebody else built it while this process waited
+            return LIB_PATH
+        tmp = LIB_PATH + f".tmp{os.getpid()}"
+        cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            if os.path.exists(tmp):
+                os.unlink(tmp)
+            raise HgError("nvcc failed:\n" + res.stdout + res.stderr)
+        if verbose:
+            print(res.stderr)
+        os.replace(tmp, LIB_PATH)
+        with open(HASH_PATH + ".tmp", "w") as f:
+            f.write(_source_hash())
+        os.replace(HASH_PATH + ".tmp", HASH_PATH)
+    finally:
+        try:
+            os.unlink(_LOCK_PATH)
+        except FileNotFoundError:
+            pass
     return LIB_PATH
 
 
@@ -128,13 +175,13 @@ EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 
 def lib() -> ctypes.CDLL:
-    """Load (building first if the .so is missing) and return the typed library handle."""
+    """Load (building first if the .so is missing or older than its sources) and return the typed library handle."""
     global _lib
     if _lib is not None:
         return _lib
     with _lock:
         if _lib is None:
-            if not os.path.exists(LIB_PATH):
+            if _stale():                            # missing, or csrc/ / the header changed since it was built
                 build()
             handle = ctypes.CDLL(LIB_PATH)
             for name, (res, args) in _SIGNATURES.items():

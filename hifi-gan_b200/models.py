@@ -102,7 +102,9 @@ class _PackedConv:
     def refresh(self) -> None:
         """(Re)pack when a parameter changed: weight_norm fold + bf16 GEMM layout (hg_pack_*)."""
         key = self._fingerprint()
-        if key == self.key:
+        # (data_ptr, _version) cannot see writes through raw pointers (the AdamW kernel), and a captured graph must
+        # hold the re-pack launches whatever the host cache says: never skip while a stream is capturing
+        if key == self.key and not torch.cuda.is_current_stream_capturing():
             return
         L = _lib.lib()
         m = self.module
@@ -332,7 +334,7 @@ class _GeneratorEngine:
         post = self.gen.conv_post
         g, v = _g_v(post)
         key = tuple((t.data_ptr(), t._version) for t in (g, v, post.bias) if t is not None)
-        if key != self.post_key:
+        if key != self.post_key or torch.cuda.is_current_stream_capturing():
             # single output channel: fold on the device with torch (4 x 224 floats, not a hot path)
             v32 = v.detach().to(self.device, torch.float32)
             w = v32 if g is None else v32 * (g.detach().to(self.device, torch.float32)

@@ -1207,6 +1207,10 @@ class TrainStep:
         if entry == "seen":
             sx, sy, sm = x.clone(), y.clone(), y_mel.clone()
             torch.cuda.synchronize()
+            # The captured step must not depend on host cache state: anything that refreshed the generator's packs
+            # since the last update (a validation `generator(x)` between the eager and the capture step) would make
+            # every refresh a host-side no-op here and the graph would replay G on stale bf16 weights for ever.
+            self.G.invalidate()
             try:
                 g = torch.cuda.CUDAGraph()
                 # thread_local: the NCCL watchdog thread of a data-parallel run may touch the CUDA API meanwhile

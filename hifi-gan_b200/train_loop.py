@@ -95,14 +95,22 @@ def normalize_peak(audio: torch.Tensor) -> torch.Tensor:
     return audio / peak * 0.95 if peak > 0 else audio
 
 
+def normalize_fork(audio: torch.Tensor) -> torch.Tensor:
+    """This fork's literal behaviour (`--normalize fork`): meldataset.py:130 calls librosa.util.normalize on a [1, L]
+    array, whose default axis=0 normalises every SAMPLE by its own magnitude -> +-0.95 (zeros stay zero)."""
+    return torch.sign(audio) * 0.95
+
+
 # ------------------------------------------------------------------------------------------------------ driver
-def train(rank: int, a, h) -> Dict[str, float]:
+def train(rank: int, a, h, local_rank: int = None) -> Dict[str, float]:
+    """rank = global rank (gradient exchange, batch shard, logging); local_rank = the GPU of this process."""
     world = h.num_gpus if h.num_gpus > 1 else 1
+    local_rank = rank if local_rank is None else local_rank
     if world > 1:
         torch.distributed.init_process_group(backend=h.dist_config['dist_backend'], init_method=h.dist_config['dist_url'],
                                              world_size=h.dist_config['world_size'] * h.num_gpus, rank=rank)
     torch.cuda.manual_seed(h.seed)
-    device = torch.device('cuda:{:d}'.format(rank))
+    device = torch.device('cuda:{:d}'.format(local_rank))
     torch.cuda.set_device(device)
     generator, mpd, msd = Generator(h), MultiPeriodDiscriminator(), MultiScaleDiscriminator()
     if rank == 0:
@@ -129,12 +137,14 @@ def train(rank: int, a, h) -> Dict[str, float]:
     random.seed(1234)                                                # MelDataset.__init__ (meldataset.py:104-106)
     random.shuffle(training_files)
     # meldataset.py:126-130: `/ MAX_WAV_VALUE` (quirk kept), then peak normalisation unless fine-tuning
-    prep = (lambda a_: a_) if a.fine_tuning else normalize_peak
+    prep = (lambda a_: a_) if a.fine_tuning else (normalize_fork if getattr(a, "normalize", "peak") == "fork"
+                                                   else normalize_peak)
     utts = [prep(read_wav(f, h.sampling_rate) / MAX_WAV_VALUE) for f in training_files]
     npy = lambda f: np.load(os.path.join(a.input_mels_dir, os.path.splitext(os.path.split(f)[-1])[0] + '.npy'))
     sampler = SegmentSampler(utts, h.segment_size, h.n_fft, h.num_mels, h.hop_size, h.win_size, h.sampling_rate, h.fmin,
-                             h.fmax, h.fmax_for_loss, seed=1234, device=device,
+                             h.fmax, h.fmax_for_loss, seed=1234 + steps, device=device,   # a resumed run draws new crops
                              mels=[npy(f) for f in training_files] if a.fine_tuning else None)   # meldataset.py:155-161
+    del utts                                    # the sampler holds the pool on the device; drop the host copy
     val = [prep(read_wav(f, h.sampling_rate) / MAX_WAV_VALUE) for f in validation_files] if rank == 0 else []
     val_mels = [torch.from_numpy(npy(f)).float() for f in validation_files] if (rank == 0 and a.fine_tuning) else None
     sw = None
@@ -144,7 +154,7 @@ def train(rank: int, a, h) -> Dict[str, float]:
             sw = SummaryWriter(os.path.join(a.checkpoint_path, 'logs'))
         except Exception:  # noqa: BLE001
             sw = None
-    n_items = len(utts)
+    n_items = len(training_files)
     per_rank = h.batch_size                      # UPSTREAM: batch_size is per GPU (h.batch_size / h.num_gpus upstream of DDP)
     batches_per_epoch = max(1, n_items // (per_rank * world))
     last = {}
@@ -231,6 +241,7 @@ def main(argv=None) -> Dict[str, float]:
     parser.add_argument('--summary_interval', default=100, type=int)
     parser.add_argument('--validation_interval', default=1000, type=int)
     parser.add_argument('--fine_tuning', default=False, type=bool)
+    parser.add_argument('--normalize', default='peak', choices=['peak', 'fork'])   # see normalize_fork
     a = parser.parse_args(argv)
     with open(a.config) as f:
         h = AttrDict(json.loads(f.read()))
@@ -239,12 +250,13 @@ def main(argv=None) -> Dict[str, float]:
     if not torch.cuda.is_available():
         raise RuntimeError("hifigan_b200 has no CPU path: a B200 is required")
     h.num_gpus = int(os.environ.get("WORLD_SIZE", "1"))          # one process per GPU, launched by torchrun
-    rank = int(os.environ.get("LOCAL_RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    rank = int(os.environ.get("RANK", str(local_rank)))          # global rank: differs from LOCAL_RANK across nodes
     if h.num_gpus > 1:
         h.dist_config = dict(h.get("dist_config", {}), dist_backend="nccl", dist_url="env://", world_size=1)
         h.batch_size = int(h.batch_size / h.num_gpus)            # UPSTREAM: the configured batch is global
         print('Batch size per GPU :', h.batch_size)
-    return train(rank, a, h)
+    return train(rank, a, h, local_rank)
 
 
 if __name__ == '__main__':

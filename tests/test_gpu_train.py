@@ -501,6 +501,38 @@ def test_graphed_step_matches_eager(H):
         assert abs(res[0][k] - res[1][k]) <= 1e-3 * abs(res[0][k]) + 1e-5, (k, res[0][k], res[1][k])
 
 
+def test_graph_capture_after_module_forward_keeps_repacking(H):
+    """A validation-style `generator(x)` between the eager step and the capture step refreshes the host-side pack
+    cache; the captured graph must still hold the re-pack launches (it would otherwise replay the generator on the
+    bf16 weights of capture time for ever).  Losses after 5 steps and the generator's parameters follow the eager
+    trajectory (1e-3 relative; fp32 atomics make runs non-bit-identical)."""
+    from oracle import hifigan_oracle as O
+    ya = O.synthetic_audio(2, 8192, seed=33).cuda()
+    x = H.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, 8000)
+    y_mel = H.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, None)
+    res, params = [], []
+    for graphed in (False, True):
+        h, ts, (G, _, _), _ = _seeded_step(H)
+        for i in range(5):
+            out = (ts.step_graphed if graphed else ts.step)(x, ya.unsqueeze(1), y_mel)
+            if graphed and i == 0:                      # what train_loop.validate does at steps == 0
+                ts.G.invalidate()
+                G.eval()
+                with torch.no_grad():
+                    G(x)
+                G.train()
+        torch.cuda.synchronize()
+        if graphed:
+            assert ts.graph_active, "capture fell back to eager"
+        res.append({k: out[k].item() for k in LOSS_KEYS})
+        params.append(ts.G.flat.p.clone())
+    for k in LOSS_KEYS:
+        assert abs(res[0][k] - res[1][k]) <= 2e-3 * abs(res[0][k]) + 1e-5, (k, res[0][k], res[1][k])
+    cos = F.cosine_similarity(params[0], params[1], dim=0).item()
+    assert (params[0] - params[1]).norm() <= 2e-3 * params[0].norm(), (params[0] - params[1]).norm().item()
+    assert cos > 0.999999
+
+
 def test_spectral_norm_kernels_vs_torch(H):
     """hg_spectral_norm_fwd / _bwd against torch.nn.utils.spectral_norm itself (train-mode forward = one power
     iteration updating u / v in place; autograd through W / sigma with u, v constant)."""
