@@ -142,7 +142,7 @@ _SIGNATURES = {
     "hg_pack_dgrad_weight": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hg_conv1d_dgrad": (c_int, [c_void_p, c_void_p] + [c_int] * 12 + [c_void_p, c_float, c_void_p, c_void_p, c_float,
                                 c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_int,
-                                c_void_p]),
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "hg_conv1d_wgrad": (c_int, [c_void_p, c_void_p] + [c_int] * 11 + [c_void_p, c_int, c_void_p]),
     "hg_unpack_wgrad_conv": (c_int, [c_void_p] + [c_int] * 7 + [POINTER(c_int), c_void_p, c_void_p]),
     "hg_unpack_wgrad_convtr": (c_int, [c_void_p] + [c_int] * 7 + [c_void_p, c_void_p]),
@@ -159,9 +159,10 @@ _SIGNATURES = {
                                      c_void_p, c_void_p]),
     "hg_colsum_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hg_conv_post_tanh_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
-                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                      c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p]),
     "hg_disc_last_conv_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
-                                      c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                      c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hg_disc_first_conv_bwd": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_void_p] * 4),
     "hg_avgpool_4_2_2_bwd": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "hg_loss_grad": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_float, c_float, c_float, c_void_p,
@@ -188,7 +189,7 @@ def lib() -> ctypes.CDLL:
                 fn = getattr(handle, name)
                 fn.restype = res
                 fn.argtypes = args
-            if handle.hg_abi_version() != 1:
+            if handle.hg_abi_version() != 2:
                 raise HgError("libhifigan_b200.so ABI mismatch")
             _lib = handle
     return _lib

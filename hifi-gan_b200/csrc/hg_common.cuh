@@ -308,6 +308,32 @@ __device__ __forceinline__ void add_bf16x16(float (&v)[16], const U8& r) {
 
 
 
+// Column sums over the 32 lanes of a warp, N (power of two <= 16) columns per lane, in N - 1 + log2(32 / N) shuffles:
+// a halving butterfly — at every step a lane hands the half of its columns it does not keep to its partner.
+// Returns the sum of column `col` (set per lane: the lane bits consumed by the halving steps, most significant
+// first); the 32 / N lanes that differ only in their low bits hold the same column.
+template <int N>
+__device__ __forceinline__ float warp_colsum(float (&v)[N], int lane, int& col) {
+  int off = 16;
+  col = 0;
+#pragma unroll
+  for (int w = N / 2; w >= 1; w >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float send = hi ? v[i] : v[i + w];
+      const float keep = hi ? v[i + w] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+    if (hi) col += w;
+    off >>= 1;
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1)
+    if (o <= off) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+  return v[0];
+}
+
 // cudaFuncSetAttribute is per DEVICE: launchers remember, per device ordinal, whether (or with which size) they
 // already raised a kernel's dynamic shared-memory limit.  One process may drive several GPUs.
 struct PerDeviceOnce {

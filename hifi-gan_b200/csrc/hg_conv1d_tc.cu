@@ -80,7 +80,97 @@ struct ConvArgs {
   // them standing in for the conv padding).  Output element (row t, N tile nt) is stored only when
   // (t % seq_pitch) * seq_mul + (nt * NT) / seq_div < seq_valid, so the gap rows stay zero.  seq_pitch == 0: off.
   int seq_pitch, seq_valid, seq_mul, seq_div;
+  const __nv_bfloat16* pre_add;  // added to the accumulator BEFORE the mask (an incoming feature-map gradient)
+  // Bias gradient of the layer whose OUTPUT this launch differentiates: fp32 column sums of the values the
+  // epilogue is about to round to bf16, folded modulo colsum_mod (a polyphase gradient holds `stride` phases of
+  // every channel) and added to up to three destinations (the last convs of the MRF branches share one gradient).
+  float* colsum[3];
+  int colsum_mod;
 };
+
+// One 16-column group of one accumulator row: everything the epilogue does between the TMEM load and the
+// global stores.  `v` leaves holding the final fp32 values (zero for rows that are not stored).
+__device__ __forceinline__ void epi_group(const ConvArgs& p, bool valid, size_t off, int ch, const uint32_t (&raw)[16],
+                                          const hg::U8* r0, const hg::U8* r1, const hg::U8* r2, float (&v)[16]) {
+  if (!valid) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = 0.f;
+    return;
+  }
+#pragma unroll
+  for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(raw[e]);
+  if (p.bias) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + ch + q * 4));
+      v[4 * q] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
+    }
+  }
+  if (p.fm_g) {
+    const hg::U8 fg = hg::ldg256(p.fm_g + off), fr = hg::ldg256(p.fm_r + off);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 a = hg::unpack_bf16x2(fg.v[i]), r = hg::unpack_bf16x2(fr.v[i]);
+      v[2 * i] += p.fm_coef * ((a.x > r.x) ? 1.f : (a.x < r.x) ? -1.f : 0.f);
+      v[2 * i + 1] += p.fm_coef * ((a.y > r.y) ? 1.f : (a.y < r.y) ? -1.f : 0.f);
+    }
+  }
+  if (p.pre_add) hg::add_bf16x16(v, hg::ldg256(p.pre_add + off));
+  if (p.mask) {
+    const hg::U8 mk = hg::ldg256(p.mask + off);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 a = hg::unpack_bf16x2(mk.v[i]);
+      if (!(a.x > 0.f)) v[2 * i] *= p.mask_slope;
+      if (!(a.y > 0.f)) v[2 * i + 1] *= p.mask_slope;
+    }
+  }
+  if (p.res0) hg::add_bf16x16(v, *r0);
+  if (p.res1) hg::add_bf16x16(v, r1 ? *r1 : hg::ldg256(p.res1 + off));
+  if (p.res2) hg::add_bf16x16(v, r2 ? *r2 : hg::ldg256(p.res2 + off));
+#pragma unroll
+  for (int e = 0; e < 16; ++e) v[e] *= p.scale;
+  if (p.out_raw) {
+    hg::U8 o;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o.v[i] = hg::pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    hg::stg256(p.out_raw + off, o);
+  }
+  if (p.out_act) {
+    hg::U8 o;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      o.v[i] = hg::pack_bf16x2(hg::lrelu(v[2 * i], p.slope), hg::lrelu(v[2 * i + 1], p.slope));
+    hg::stg256(p.out_act + off, o);
+  }
+}
+
+// Column sums of a warp's 32 rows x 16 columns (16 shuffles), added into the CTA's shared-memory partials.
+__device__ __forceinline__ void epi_colsum16(float (&v)[16], int lane, float* csum) {
+  int col;
+  const float sum = hg::warp_colsum<16>(v, lane, col);
+  if (!(lane & 1)) atomicAdd(csum + col, sum);
+}
+
+// epilogue warps only (ids 2 .. 2+kEpiWarps-1): named barrier 1
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
+
+// add the CTA's column sums of N tile `nt` to the bias gradients and clear them (called by all epilogue threads)
+template <int NT>
+__device__ __forceinline__ void epi_colsum_flush(const ConvArgs& p, float* csum, int nt, int epi_tid) {
+  epi_bar_sync();
+  for (int c = epi_tid; c < NT; c += kEpiWarps * 32) {
+    const float sum = csum[c];
+    csum[c] = 0.f;
+    const int gc = (nt * NT + c) % p.colsum_mod;
+    if (sum != 0.f) {
+      atomicAdd(p.colsum[0] + gc, sum);
+      if (p.colsum[1]) atomicAdd(p.colsum[1] + gc, sum);
+      if (p.colsum[2]) atomicAdd(p.colsum[2] + gc, sum);
+    }
+  }
+  epi_bar_sync();
+}
 
 struct Barriers {
   uint64_t a_full[kMaxASlots];
@@ -312,8 +402,20 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const int row = quarter * 32 + lane;
     const int col0 = half * kColsPerWarp;  // first column (within the tile) owned by this warp
     uint32_t acc_it = 0;
+    // bias-gradient column sums: per-CTA fp32 partials in shared memory, flushed when the N tile changes
+    float* csum = reinterpret_cast<float*>(bars + 1);
+    const int epi_tid = threadIdx.x - 64;
+    int cs_nt = -1;
+    if (p.colsum[0]) {
+      for (int c = epi_tid; c < NT; c += kEpiWarps * 32) csum[c] = 0.f;
+      epi_bar_sync();
+    }
     for (TileIter it(p); it.tile < p.num_tiles; it.next()) {
       const int nt = it.nt, b = it.b;
+      if (p.colsum[0] && nt != cs_nt) {
+        if (cs_nt >= 0) epi_colsum_flush<NT>(p, csum, cs_nt, epi_tid);
+        cs_nt = nt;
+      }
       const int t = it.tt * kTileM + row;
       bool valid = t < p.t;
       if (p.seq_pitch) valid = valid && ((t % p.seq_pitch) * p.seq_mul + (nt * NT) / p.seq_div < p.seq_valid);
@@ -349,60 +451,17 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                                col0 + g * 16;
         hg::tmem_ld_32x16(taddr, raw);
         hg::tmem_ld_wait();
-        if (valid) {
-          float v[16];
-#pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(raw[e]);
-          if (p.bias) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + g * 16 + q * 4));
-              v[4 * q] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
-            }
-          }
-          if (p.fm_g) {
-            const hg::U8 fg = hg::ldg256(p.fm_g + off + g * 16), fr = hg::ldg256(p.fm_r + off + g * 16);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float2 a = hg::unpack_bf16x2(fg.v[i]), r = hg::unpack_bf16x2(fr.v[i]);
-              v[2 * i] += p.fm_coef * ((a.x > r.x) ? 1.f : (a.x < r.x) ? -1.f : 0.f);
-              v[2 * i + 1] += p.fm_coef * ((a.y > r.y) ? 1.f : (a.y < r.y) ? -1.f : 0.f);
-            }
-          }
-          if (p.mask) {
-            const hg::U8 mk = hg::ldg256(p.mask + off + g * 16);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float2 a = hg::unpack_bf16x2(mk.v[i]);
-              if (!(a.x > 0.f)) v[2 * i] *= p.mask_slope;
-              if (!(a.y > 0.f)) v[2 * i + 1] *= p.mask_slope;
-            }
-          }
-          if (p.res0) hg::add_bf16x16(v, rpre[g]);
-          if (p.res1) hg::add_bf16x16(v, kPreAll ? rpre1[kPreAll ? g : 0] : hg::ldg256(p.res1 + off + g * 16));
-          if (p.res2) hg::add_bf16x16(v, kPreAll ? rpre2[kPreAll ? g : 0] : hg::ldg256(p.res2 + off + g * 16));
-#pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] *= p.scale;
-          if (p.out_raw) {
-            hg::U8 o;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o.v[i] = hg::pack_bf16x2(v[2 * i], v[2 * i + 1]);
-            hg::stg256(p.out_raw + off + g * 16, o);
-          }
-          if (p.out_act) {
-            hg::U8 o;
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              o.v[i] = hg::pack_bf16x2(hg::lrelu(v[2 * i], p.slope), hg::lrelu(v[2 * i + 1], p.slope));
-            hg::stg256(p.out_act + off + g * 16, o);
-          }
-        }
+        float v[16];
+        epi_group(p, valid, off + g * 16, ch0 + g * 16, raw, &rpre[g], kPreAll ? &rpre1[kPreAll ? g : 0] : nullptr,
+                  kPreAll ? &rpre2[kPreAll ? g : 0] : nullptr, v);
+        if (p.colsum[0]) epi_colsum16(v, lane, csum + col0 + g * 16);
       }
       hg::tc_fence_before();
       __syncwarp();
       if (lane == 0) hg::mbar_arrive(&bars->acc_empty[acc]);
       ++acc_it;
     }
+    if (p.colsum[0] && cs_nt >= 0) epi_colsum_flush<NT>(p, csum, cs_nt, epi_tid);
   }
 
   hg::tc_fence_before();
@@ -585,9 +644,20 @@ conv1d_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const int row = quarter * 32 + lane;
     const int col0 = half * kColsPerWarp;
     uint32_t acc_it = 0;
+    float* csum = reinterpret_cast<float*>(bars + 1);
+    const int epi_tid = threadIdx.x - 64;
+    int cs_nt = -1;
+    if (p.colsum[0]) {
+      for (int c = epi_tid; c < NT; c += kEpiWarps * 32) csum[c] = 0.f;
+      epi_bar_sync();
+    }
     for (int pt = cluster_id; pt < num_pt; pt += n_clusters) {
       int nt, ptt, b;
       decode(pt, nt, ptt, b);
+      if (p.colsum[0] && nt != cs_nt) {
+        if (cs_nt >= 0) epi_colsum_flush<NT>(p, csum, cs_nt, epi_tid);
+        cs_nt = nt;
+      }
       const int t = (2 * ptt + static_cast<int>(rank)) * kTileM + row;
       bool valid = t < p.t;
       if (p.seq_pitch) valid = valid && ((t % p.seq_pitch) * p.seq_mul + (nt * NT) / p.seq_div < p.seq_valid);
@@ -598,8 +668,6 @@ conv1d_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
         for (int g = 0; g < kGroups16; ++g) rpre[g] = hg::ldg256(p.res0 + off + g * 16);
       }
-      // the MRF-final launch adds two more tensors: fetch them up front as well when the registers allow
-      // (loading them at the point of use exposed their latency: +0.3 .. +1.2 ms on those launches)
       constexpr bool kPreAll = kGroups16 <= 4;
       hg::U8 rpre1[kPreAll ? kGroups16 : 1], rpre2[kPreAll ? kGroups16 : 1];
       if (kPreAll && valid) {
@@ -621,54 +689,10 @@ conv1d_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * NT + col0 + g * 16;
         hg::tmem_ld_32x16(taddr, raw);
         hg::tmem_ld_wait();
-        if (valid) {
-          float v[16];
-#pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(raw[e]);
-          if (p.bias) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + g * 16 + q * 4));
-              v[4 * q] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
-            }
-          }
-          if (p.fm_g) {
-            const hg::U8 fg = hg::ldg256(p.fm_g + off + g * 16), fr = hg::ldg256(p.fm_r + off + g * 16);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float2 a = hg::unpack_bf16x2(fg.v[i]), r = hg::unpack_bf16x2(fr.v[i]);
-              v[2 * i] += p.fm_coef * ((a.x > r.x) ? 1.f : (a.x < r.x) ? -1.f : 0.f);
-              v[2 * i + 1] += p.fm_coef * ((a.y > r.y) ? 1.f : (a.y < r.y) ? -1.f : 0.f);
-            }
-          }
-          if (p.mask) {
-            const hg::U8 mk = hg::ldg256(p.mask + off + g * 16);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float2 a = hg::unpack_bf16x2(mk.v[i]);
-              if (!(a.x > 0.f)) v[2 * i] *= p.mask_slope;
-              if (!(a.y > 0.f)) v[2 * i + 1] *= p.mask_slope;
-            }
-          }
-          if (p.res0) hg::add_bf16x16(v, rpre[g]);
-          if (p.res1) hg::add_bf16x16(v, kPreAll ? rpre1[kPreAll ? g : 0] : hg::ldg256(p.res1 + off + g * 16));
-          if (p.res2) hg::add_bf16x16(v, kPreAll ? rpre2[kPreAll ? g : 0] : hg::ldg256(p.res2 + off + g * 16));
-#pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] *= p.scale;
-          if (p.out_raw) {
-            hg::U8 o;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o.v[i] = hg::pack_bf16x2(v[2 * i], v[2 * i + 1]);
-            hg::stg256(p.out_raw + off + g * 16, o);
-          }
-          if (p.out_act) {
-            hg::U8 o;
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              o.v[i] = hg::pack_bf16x2(hg::lrelu(v[2 * i], p.slope), hg::lrelu(v[2 * i + 1], p.slope));
-            hg::stg256(p.out_act + off + g * 16, o);
-          }
-        }
+        float v[16];
+        epi_group(p, valid, off + g * 16, ch0 + g * 16, raw, &rpre[g], kPreAll ? &rpre1[kPreAll ? g : 0] : nullptr,
+                  kPreAll ? &rpre2[kPreAll ? g : 0] : nullptr, v);
+        if (p.colsum[0]) epi_colsum16(v, lane, csum + col0 + g * 16);
       }
       hg::tc_fence_before();
       __syncwarp();
@@ -678,6 +702,7 @@ conv1d_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       }
       ++acc_it;
     }
+    if (p.colsum[0] && cs_nt >= 0) epi_colsum_flush<NT>(p, csum, cs_nt, epi_tid);
   }
 
   hg::tc_fence_before();
@@ -777,6 +802,9 @@ struct ConvExtra {
   int group_mod = 0;      // 0: one input channel block per N tile (forward grouped convs)
   int t_in_valid = -1;    // stride 1 only: input rows >= this are read as zero (TMA bound); -1 = t_in_rows
   int seq_pitch = 0, seq_valid = 0, seq_mul = 1, seq_div = 1 << 30;
+  const void* pre_add = nullptr;
+  float* colsum[3] = {nullptr, nullptr, nullptr};
+  int colsum_mod = 0;     // 0: the launch's output channel count
 };
 
 int conv_forward(const void* x, const void* w_packed, const float* bias, int batch, int t_in_rows,
@@ -822,7 +850,9 @@ int conv_forward(const void* x, const void* w_packed, const float* bias, int bat
   p.num_tiles = batch * p.tiles_t * p.tiles_n;
   p.a_slot_bytes = (static_cast<uint32_t>(a_rows) * kc * 2 + 1023u) & ~1023u;
   const uint32_t tap_bytes = static_cast<uint32_t>(n_tile) * kc * 2;
-  const int budget = g_max_smem - 1024 /*align*/ - static_cast<int>(sizeof(Barriers));
+  // bias-gradient launches keep n_tile fp32 column sums behind the barriers
+  const int colsum_bytes = ex.colsum[0] ? 1024 : 0;
+  const int budget = g_max_smem - 1024 /*align*/ - static_cast<int>(sizeof(Barriers)) - colsum_bytes;
 
   // resident filter bank: needs all taps of all chunks + at least 2 activation slots
   const long long w_all = static_cast<long long>(ktaps) * p.nchunks * tap_bytes;
@@ -880,6 +910,10 @@ int conv_forward(const void* x, const void* w_packed, const float* bias, int bat
   p.fm_coef = ex.fm_coef;
   p.group_mod = ex.group_mod > 0 ? ex.group_mod : p.tiles_n;
   p.seq_pitch = ex.seq_pitch; p.seq_valid = ex.seq_valid; p.seq_mul = ex.seq_mul;
+  p.pre_add = static_cast<const __nv_bfloat16*>(ex.pre_add);
+  for (int i = 0; i < 3; ++i) p.colsum[i] = ex.colsum[i];
+  p.colsum_mod = ex.colsum_mod > 0 ? ex.colsum_mod : cout;
+  HG_REQUIRE(!ex.colsum[1] || ex.colsum[0], "conv: bias-gradient destinations must be filled from slot 0");
   p.seq_div = ex.seq_div > 0 ? ex.seq_div : (1 << 30);
   HG_REQUIRE(ex.seq_pitch >= 0 && (ex.seq_pitch == 0 || batch == 1), "conv: flat sequences need batch == 1");
   HG_REQUIRE(!p.fm_g || p.fm_r, "conv: fm_g without fm_r");
@@ -899,11 +933,12 @@ int conv_forward(const void* x, const void* w_packed, const float* bias, int bat
   if (rc) return rc;
 
   const size_t smem_bytes = 1024 + static_cast<size_t>(a_slots) * p.a_slot_bytes + w_bytes_total +
-                            sizeof(Barriers);
+                            sizeof(Barriers) + colsum_bytes;
   const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (pair) {
-    const size_t smem2 = 1024 + static_cast<size_t>(a_slots) * p.a_slot_bytes + w_bytes_total + sizeof(Barriers2);
+    const size_t smem2 = 1024 + static_cast<size_t>(a_slots) * p.a_slot_bytes + w_bytes_total + sizeof(Barriers2) +
+                         colsum_bytes;
     rc = (n_tile == 256) ? launch2<256>(tm_x, tm_w, p, smem2, g_num_sms, st)
                          : launch2<128>(tm_x, tm_w, p, smem2, g_num_sms, st);
     if (rc) return rc;
@@ -978,14 +1013,16 @@ extern "C" int hg_conv1d_general_fwd(const void* x, const void* w_packed, const 
 // of a strided conv (or the forward of its transpose) is its polyphase form (hg_pack_convtr1d_weight on the
 // conv weight).  The epilogue applies the leaky_relu backward mask of the layer input, the feature-matching L1
 // term and up to two gradient addends (residual path / MRF branch sum):
-//   out[b,t,n] = ((sum_{j,c} dy[b, t + j*dil - pad_left, blk(n) + c] * w[j][n][c] + fm_coef * sgn(fm_g - fm_r))
+//   out[b,t,n] = ((sum_{j,c} dy[b, t + j*dil - pad_left, blk(n) + c] * w[j][n][c] + fm_coef * sgn(fm_g - fm_r) + pre_add)
 //                 * (mask_src > 0 ? 1 : mask_slope) + res0 + res1 + res2) * scale
+//   bias_grad*[n % bias_mod] += sum_{b,t} out[b,t,n]   (fp32, before the bf16 rounding of `out`)
 extern "C" int hg_conv1d_dgrad(const void* dy, const void* w_packed, int batch, int t_dy_valid, int t_dy_rows,
                                int c_dy_total, int t_out, int t_out_rows, int groups, int n_tile, int cout, int ktaps,
                                int dilation, int pad_left, const void* mask_src, float mask_slope,
                                const void* fm_r, const void* fm_g, float fm_coef, const void* res0, const void* res1,
                                const void* res2, float scale, void* out, int seq_pitch, int seq_valid, int seq_mul,
-                               int seq_div, void* stream) {
+                               int seq_div, const void* pre_add, float* bias_grad0, float* bias_grad1,
+                               float* bias_grad2, int bias_mod, void* stream) {
   HG_REQUIRE(groups >= 1 && c_dy_total % groups == 0, "hg_conv1d_dgrad: bad groups");
   HG_REQUIRE(ktaps > 0 && dilation > 0 && 128 + (ktaps - 1) * dilation <= 256,
              "hg_conv1d_dgrad: halo too large for one TMA box (taps=%d dilation=%d)", ktaps, dilation);
@@ -994,6 +1031,8 @@ extern "C" int hg_conv1d_dgrad(const void* dy, const void* w_packed, int batch, 
   ex.fm_r = fm_r; ex.fm_g = fm_g; ex.fm_coef = fm_coef;
   ex.t_in_valid = t_dy_valid;
   ex.seq_pitch = seq_pitch; ex.seq_valid = seq_valid; ex.seq_mul = seq_mul > 0 ? seq_mul : 1; ex.seq_div = seq_div;
+  ex.pre_add = pre_add;
+  ex.colsum[0] = bias_grad0; ex.colsum[1] = bias_grad1; ex.colsum[2] = bias_grad2; ex.colsum_mod = bias_mod;
   const int cin_tile = c_dy_total / groups;
   if (groups == 1) {
     if (n_tile <= 0) n_tile = (cout % 256 == 0) ? 256 : (cout % 128 == 0) ? 128 : (cout % 64 == 0) ? 64 : 32;

@@ -85,16 +85,20 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, int t_valid, int t_rows, int 
 }
 
 // conv_post + tanh backward, data half: dpre = dy * (1 - y^2);
-// dx[b,t,c] = lrelu'(x[b,t,c]; slope) * sum_j dpre[b, t - j + pad] * w[c][j]     (x = the activated conv_post input)
+// dx[b,t,c] = dx_scale * lrelu'(x[b,t,c]; slope) * sum_j dpre[b, t - j + pad] * w[c][j]  (x = the activated conv_post input)
+// bsum*[c] += sum_{b,t} dx[b,t,c] in fp32 (the bias gradient of the convs that produced x's pre-activation)
 __global__ void __launch_bounds__(256)
 conv_post_bwd_dx_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                         const float* __restrict__ y, const float* __restrict__ dy, int t, int c, int k,
-                        float slope, __nv_bfloat16* __restrict__ dx, float* __restrict__ dpre_out) {
+                        float slope, float dx_scale, __nv_bfloat16* __restrict__ dx, float* __restrict__ dpre_out,
+                        float* __restrict__ bsum0, float* __restrict__ bsum1, float* __restrict__ bsum2) {
   extern __shared__ float smf[];
   float* ws = smf;                 // [c][k]
   float* dp = smf + c * k;         // [256 + k - 1]
+  float* cs = dp + 256 + k - 1;    // [c] column sums of the block
   const int b = blockIdx.y, t0 = blockIdx.x * 256, pad = k / 2;
   for (int i = threadIdx.x; i < c * k; i += blockDim.x) ws[i] = w[i];
+  for (int i = threadIdx.x; i < c; i += blockDim.x) cs[i] = 0.f;
   for (int i = threadIdx.x; i < 256 + k - 1; i += blockDim.x) {
     const int tt = t0 + i - (k - 1 - pad);
     float v = 0.f;
@@ -106,31 +110,51 @@ conv_post_bwd_dx_kernel(const __nv_bfloat16* __restrict__ x, const float* __rest
   }
   __syncthreads();
   const int tt = t0 + threadIdx.x;
-  if (tt >= t) return;
-  if (dpre_out) dpre_out[static_cast<size_t>(b) * t + tt] = dp[threadIdx.x + (k - 1 - pad)];
-  const __nv_bfloat16* xr = x + (static_cast<size_t>(b) * t + tt) * c;
-  __nv_bfloat16* dr = dx + (static_cast<size_t>(b) * t + tt) * c;
+  const bool live = tt < t;
+  const int lane = threadIdx.x & 31;
+  if (live && dpre_out) dpre_out[static_cast<size_t>(b) * t + tt] = dp[threadIdx.x + (k - 1 - pad)];
+  const __nv_bfloat16* xr = x + (static_cast<size_t>(b) * t + (live ? tt : 0)) * c;
+  __nv_bfloat16* dr = dx + (static_cast<size_t>(b) * t + (live ? tt : 0)) * c;
   for (int c0 = 0; c0 < c; c0 += 8) {
-    const uint4 xv = *reinterpret_cast<const uint4*>(xr + c0);
-    const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
-    uint32_t ow[4];
+    float g8[8];
+    if (live) {
+      const uint4 xv = *reinterpret_cast<const uint4*>(xr + c0);
+      const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+      uint32_t ow[4];
 #pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      float g2[2];
+      for (int h = 0; h < 4; ++h) {
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int cc = c0 + 2 * h + e;
-        float a = 0.f;
-        // input position tt feeds output tt - j + pad through tap j
-        for (int j = 0; j < k; ++j) a += dp[threadIdx.x + (k - 1 - pad) - j + pad] * ws[cc * k + j];
-        g2[e] = a;
+        for (int e = 0; e < 2; ++e) {
+          const int cc = c0 + 2 * h + e;
+          float a = 0.f;
+          // input position tt feeds output tt - j + pad through tap j
+          for (int j = 0; j < k; ++j) a += dp[threadIdx.x + (k - 1 - pad) - j + pad] * ws[cc * k + j];
+          g8[2 * h + e] = a * dx_scale;
+        }
+        const float2 xs = hg::unpack_bf16x2(xw[h]);
+        if (!(xs.x > 0.f)) g8[2 * h] *= slope;
+        if (!(xs.y > 0.f)) g8[2 * h + 1] *= slope;
+        ow[h] = hg::pack_bf16x2(g8[2 * h], g8[2 * h + 1]);
       }
-      const float2 xs = hg::unpack_bf16x2(xw[h]);
-      if (!(xs.x > 0.f)) g2[0] *= slope;
-      if (!(xs.y > 0.f)) g2[1] *= slope;
-      ow[h] = hg::pack_bf16x2(g2[0], g2[1]);
+      *reinterpret_cast<uint4*>(dr + c0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) g8[e] = 0.f;
     }
-    *reinterpret_cast<uint4*>(dr + c0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    if (bsum0) {
+      int col;
+      const float sum = hg::warp_colsum<8>(g8, lane, col);
+      if (!(lane & 3)) atomicAdd(cs + c0 + col, sum);
+    }
+  }
+  if (bsum0) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+      const float sum = cs[i];
+      atomicAdd(bsum0 + i, sum);
+      if (bsum1) atomicAdd(bsum1 + i, sum);
+      if (bsum2) atomicAdd(bsum2 + i, sum);
+    }
   }
 }
 
@@ -164,26 +188,43 @@ conv_post_bwd_dw_kernel(const __nv_bfloat16* __restrict__ x, const float* __rest
 }
 
 // discriminator conv_post (Cout = 1) backward.
-// data half: dx[s,h,c] = (sum_j dl[s, h - j + pad] * w[c][j] + fm_coef * sgn(fm_g - fm_r)) * lrelu'(x[s,h,c])
+// data half: dx[s,h,c] = (sum_j dl[s, h - j + pad] * w[c][j] + fm_coef * sgn(fm_g - fm_r) + pre_add) * lrelu'(x[s,h,c])
+// A block owns kLastRows positions of one sequence; bsum[c] += sum dx[s,h,c] in fp32 (one atomic per channel per
+// block): the bias gradient of the layer that produced x.
+constexpr int kLastRows = 16;
 __global__ void __launch_bounds__(256)
 disc_last_bwd_dx_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                         const float* __restrict__ dl, int h, int h_rows, int c, int k, float slope,
-                        const __nv_bfloat16* __restrict__ fm_r, float fm_coef, __nv_bfloat16* __restrict__ dx) {
-  const int s = blockIdx.y, ho = blockIdx.x, pad = k / 2;
-  float d[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int o = ho - j + pad;
-    d[j] = (j < k && o >= 0 && o < h) ? dl[static_cast<size_t>(s) * h + o] : 0.f;
+                        const __nv_bfloat16* __restrict__ fm_r, float fm_coef,
+                        const __nv_bfloat16* __restrict__ pre_add, __nv_bfloat16* __restrict__ dx,
+                        float* __restrict__ bsum) {
+  const int s = blockIdx.y, h0 = blockIdx.x * kLastRows, pad = k / 2;
+  const int h1 = min(h, h0 + kLastRows);
+  __shared__ float dls[kLastRows + 8];
+  for (int i = threadIdx.x; i < kLastRows + 8; i += blockDim.x) {
+    const int o = h0 - 4 + i;
+    dls[i] = (o >= 0 && o < h) ? dl[static_cast<size_t>(s) * h + o] : 0.f;
   }
-  const size_t off = (static_cast<size_t>(s) * h_rows + ho) * c;
+  __syncthreads();
   for (int cc = threadIdx.x; cc < c; cc += blockDim.x) {
-    float a = 0.f;
-    for (int j = 0; j < k; ++j) a += d[j] * w[cc * k + j];
-    const float xv = __bfloat162float(x[off + cc]);
-    if (fm_r) a += fm_coef * sgn(xv - __bfloat162float(fm_r[off + cc]));
-    if (!(xv > 0.f)) a *= slope;
-    dx[off + cc] = __float2bfloat16(a);
+    float wk[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wk[j] = j < k ? w[cc * k + j] : 0.f;
+    float csum = 0.f;
+    for (int ho = h0; ho < h1; ++ho) {
+      const size_t off = (static_cast<size_t>(s) * h_rows + ho) * c + cc;
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < 7; ++j)
+        if (j < k) a += dls[ho - h0 + 4 - j + pad] * wk[j];                    // k <= 7, pad = k / 2: index in [1, 22]
+      const float xv = __bfloat162float(x[off]);
+      if (fm_r) a += fm_coef * sgn(xv - __bfloat162float(fm_r[off]));
+      if (pre_add) a += __bfloat162float(pre_add[off]);
+      if (!(xv > 0.f)) a *= slope;
+      dx[off] = __float2bfloat16(a);
+      csum += a;
+    }
+    if (bsum) atomicAdd(bsum + cc, csum);
   }
 }
 // weight half: dw[c][j] += sum_{s,h} dl[s,h] * x[s, h + j - pad, c]; db += sum dl.
@@ -791,14 +832,16 @@ extern "C" int hg_colsum_bf16(const void* x, int batch, int t_valid, int t_rows,
 }
 
 extern "C" int hg_conv_post_tanh_bwd(const void* x, const float* w, const float* y, const float* dy, int batch, int t,
-                                     int c, int k, float in_slope, void* dx, float* dpre_ws, float* dw, float* db,
-                                     void* stream) {
+                                     int c, int k, float in_slope, float dx_scale, void* dx, float* dpre_ws, float* dw,
+                                     float* db, float* bias_grad0, float* bias_grad1, float* bias_grad2, void* stream) {
   HG_REQUIRE(x && w && y && dy && dx && dpre_ws, "hg_conv_post_tanh_bwd: null pointer");
   HG_REQUIRE(batch > 0 && batch <= 65535 && t > 0 && c % 8 == 0 && (k & 1) && k <= 15, "hg_conv_post_tanh_bwd: bad shape");
+  HG_REQUIRE(bias_grad0 || (!bias_grad1 && !bias_grad2), "hg_conv_post_tanh_bwd: fill bias_grad slots from 0");
   dim3 grid((t + 255) / 256, batch);
-  const size_t smem = (static_cast<size_t>(c) * k + 256 + k) * sizeof(float);
+  const size_t smem = (static_cast<size_t>(c) * k + 256 + k + c) * sizeof(float);
   conv_post_bwd_dx_kernel<<<grid, 256, smem, S(stream)>>>(static_cast<const __nv_bfloat16*>(x), w, y, dy, t, c, k,
-                                                          in_slope, static_cast<__nv_bfloat16*>(dx), dpre_ws);
+                                                          in_slope, dx_scale, static_cast<__nv_bfloat16*>(dx), dpre_ws,
+                                                          bias_grad0, bias_grad1, bias_grad2);
   HG_CHECK_CUDA(cudaGetLastError());
   count();
   if (dw) {
@@ -813,15 +856,17 @@ extern "C" int hg_conv_post_tanh_bwd(const void* x, const float* w, const float*
 }
 
 extern "C" int hg_disc_last_conv_bwd(const void* x, const float* w, const float* dlogit, int nseq, int h, int h_rows,
-                                     int c, int k, float slope, const void* fm_r, float fm_coef, void* dx, float* dw,
-                                     float* db, void* stream) {
+                                     int c, int k, float slope, const void* fm_r, float fm_coef, const void* pre_add,
+                                     void* dx, float* dw, float* db, float* bias_grad_in, void* stream) {
   HG_REQUIRE(x && w && dlogit, "hg_disc_last_conv_bwd: null pointer");
-  HG_REQUIRE(nseq > 0 && nseq <= 65535 && h > 0 && h_rows >= h && k <= 8 && (k & 1), "hg_disc_last_conv_bwd: bad shape");
+  HG_REQUIRE(nseq > 0 && nseq <= 65535 && h > 0 && h_rows >= h && k <= 7 && (k & 1), "hg_disc_last_conv_bwd: bad shape");
+  HG_REQUIRE(dx || !bias_grad_in, "hg_disc_last_conv_bwd: bias_grad_in needs dx");
   if (dx) {
-    dim3 grid(h, nseq);
+    dim3 grid((h + kLastRows - 1) / kLastRows, nseq);
     disc_last_bwd_dx_kernel<<<grid, 256, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(x), w, dlogit, h, h_rows, c,
                                                          k, slope, static_cast<const __nv_bfloat16*>(fm_r), fm_coef,
-                                                         static_cast<__nv_bfloat16*>(dx));
+                                                         static_cast<const __nv_bfloat16*>(pre_add),
+                                                         static_cast<__nv_bfloat16*>(dx), bias_grad_in);
     HG_CHECK_CUDA(cudaGetLastError());
     count();
   }

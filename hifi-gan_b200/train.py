@@ -215,10 +215,17 @@ class _GenLayerGrad:
         _lib.check(L.hg_conv1d_wgrad(_p(x), _p(dy), batch, t, pc.cin_p, t, t, 1, self.rows, pc.taps, 1, pc.dil,
                                      pc.pad_left, self.dwp.data_ptr(), 1, _stream()), "hg_conv1d_wgrad")
 
-    def bias_grad(self, L, dy, batch: int, t: int, c: int) -> None:
-        """bias.grad (+)= column sums of dy [B][t][c]; written in place when the layer has no channel padding"""
+    def bias_dst(self, c: int) -> int:
+        """pointer of bias.grad when the producer of this layer's output gradient can add its fp32 column sums
+        straight into it (no channel padding: c output columns == cout), else 0 -> bias_grad() runs afterwards"""
         b = self.pc.module.bias
-        if b is None:
+        return b.grad.data_ptr() if (b is not None and c == self.pc.cout) else 0
+
+    def bias_grad(self, L, dy, batch: int, t: int, c: int) -> None:
+        """bias.grad (+)= column sums of dy [B][t][c] — only for layers with channel padding (V2's 16-channel stage);
+        every other bias gradient comes from the fp32 accumulators of the launch that produced dy (bias_dst)"""
+        b = self.pc.module.bias
+        if b is None or self.bias_dst(c):
             return
         if c == self.pc.cout:
             _lib.check(L.hg_colsum_bf16(_p(dy), batch, t, t, c, 1, b.grad.data_ptr(), _stream()), "hg_colsum_bf16")
@@ -229,11 +236,14 @@ class _GenLayerGrad:
             b.grad.add_(self.db[: self.pc.cout])
 
     def dgrad(self, L, dy, batch: int, t: int, out, mask=None, slope: float = LRELU_SLOPE, res0=None, res1=None,
-              res2=None, scale: float = 1.0) -> None:
+              res2=None, scale: float = 1.0, bias_dsts=()) -> None:
+        """bias_dsts: up to three bias.grad pointers (bias_dst) of the layer(s) whose output gradient `out` is"""
         pc = self.pc
+        bd = [d for d in bias_dsts if d] + [0, 0, 0]
         _lib.check(L.hg_conv1d_dgrad(_p(dy), self.wd.data_ptr(), batch, t, t, self.rows, t, t, 1, 0, pc.cin_p,
                                      pc.taps, pc.dil, self.dgrad_pad, _p(mask), slope, 0, 0, 0.0, _p(res0), _p(res1),
-                                     _p(res2), scale, _p(out), 0, 0, 1, 0, _stream()), "hg_conv1d_dgrad")
+                                     _p(res2), scale, _p(out), 0, 0, 1, 0, 0, bd[0], bd[1], bd[2], 0, _stream()),
+                   "hg_conv1d_dgrad")
 
     def to_param_grads(self, L) -> None:
         """packed dW -> (weight_g.grad, weight_v.grad) or weight.grad, one fused launch (hg_wgrad_finish_*)"""
@@ -417,9 +427,11 @@ class GeneratorTrainer:
         with torch.cuda.stream(s):
             fn()
 
-    def _branch_backward(self, L, st, i: int, j: int, b: int, t: int, c: int, g0, extra):
+    def _branch_backward(self, L, st, i: int, j: int, b: int, t: int, c: int, g0, extra, up_bias: int = 0):
         """data-gradient chain of MRF branch j on the current stream; its weight / bias gradients on lane W_LANE + j.
-        `extra` = gradients of the other branches to add into the last launch (None: write gs[j][0] alone)."""
+        `extra` = gradients of the other branches to add into the last launch (None: write gs[j][0] alone).
+        Every data-gradient launch also sums its fp32 output columns into the bias gradient of the conv that
+        produced the tensor it differentiates (up_bias: the upsampling conv's, for the branch-summing last launch)."""
         gl = self.g_blocks[i * self.gen.num_kernels + j]
         wl = self.W_LANE + j
         g = g0
@@ -428,6 +440,9 @@ class GeneratorTrainer:
             xa = st["xa0"] if s == 0 else st["xa"][j][s]
             out = st["gs"][j][s]
             r1, r2 = (extra if (s == 0 and extra is not None) else (None, None))
+            # `out` is the gradient at the output of the previous step's last conv (s > 0) or of the upsampling conv
+            prev = (gl[2 * s - 1] if self.two_conv else gl[s - 1]) if s > 0 else None
+            out_bias = (prev.bias_dst(c),) if prev is not None else ((up_bias,) if extra is not None else ())
             if self.two_conv:
                 c1, c2 = gl[2 * s], gl[2 * s + 1]
                 t1, gt1 = st["t1"][j][s], st["gt1"][j][s]
@@ -437,14 +452,14 @@ class GeneratorTrainer:
                     c2.wgrad(L, t1, g, b, t)
                     c2.to_param_grads(L)
                 self._side(L, wl, here, w2)
-                c2.dgrad(L, g, b, t, gt1, mask=t1)
+                c2.dgrad(L, g, b, t, gt1, mask=t1, bias_dsts=(c1.bias_dst(c),))
 
                 def w1(c1=c1, xa=xa, gt1=gt1):
                     c1.bias_grad(L, gt1, b, t, c)
                     c1.wgrad(L, xa, gt1, b, t)
                     c1.to_param_grads(L)
                 self._side(L, wl, here, w1)
-                c1.dgrad(L, gt1, b, t, out, mask=xa, res0=g, res1=r1, res2=r2)
+                c1.dgrad(L, gt1, b, t, out, mask=xa, res0=g, res1=r1, res2=r2, bias_dsts=out_bias)
             else:
                 cc = gl[s]
 
@@ -453,9 +468,15 @@ class GeneratorTrainer:
                     cc.wgrad(L, xa, g, b, t)
                     cc.to_param_grads(L)
                 self._side(L, wl, here, w0)
-                cc.dgrad(L, g, b, t, out, mask=xa, res0=g, res1=r1, res2=r2)
+                cc.dgrad(L, g, b, t, out, mask=xa, res0=g, res1=r1, res2=r2, bias_dsts=out_bias)
             g = out
         return g
+
+    def _last_conv_bias_dsts(self, i: int, c: int):
+        """bias.grad pointers of the last conv of every MRF branch of stage i (they share one output gradient, g0)"""
+        nk = self.gen.num_kernels
+        d = [self.g_blocks[i * nk + j][-1].bias_dst(c) for j in range(nk)]
+        return (d + [0, 0, 0])[:3]
 
     def backward(self, dy: torch.Tensor) -> None:
         """dy fp32 [B,T] (or [B,1,T]): gradient at the waveform of the LAST forward -> every parameter's .grad."""
@@ -475,12 +496,15 @@ class GeneratorTrainer:
         self.dwp_flat.zero_()          # every wgrad / finish / bias kernel below accumulates
         self.flat.g.zero_()
         lanes.fork()
-        # conv_post + tanh; the kernel also applies the slope-0.01 leaky_relu mask of the last stage
+        # conv_post + tanh; the kernel also applies the slope-0.01 leaky_relu mask of the last stage, the 1 / nk of
+        # the MRF mean (earlier stages get it from the ups dgrad scale) and sums the bias gradients of the branches'
+        # last convs (they all see this gradient) from its fp32 values
+        bd = self._last_conv_bias_dsts(len(e.ups) - 1, last["c"])
         _lib.check(L.hg_conv_post_tanh_bwd(last["stage_act"].data_ptr(), e.post_w.data_ptr(), ws["y"].data_ptr(),
-                                           dy.data_ptr(), b, t, e.post_cin_p, post.kernel_size[0], 0.01,
+                                           dy.data_ptr(), b, t, e.post_cin_p, post.kernel_size[0], 0.01, 1.0 / nk,
                                            last["g0"].data_ptr(), ws["dpre"].data_ptr(), self.post_dw.data_ptr(),
-                                           self.post_db.data_ptr(), _stream()), "hg_conv_post_tanh_bwd")
-        last["g0"].mul_(1.0 / nk)       # d(mean of branches)/d(branch); earlier stages get it from the ups dgrad scale
+                                           self.post_db.data_ptr(), bd[0], bd[1], bd[2], _stream()),
+                   "hg_conv_post_tanh_bwd")
 
         def post_grads():
             cin, k = post.in_channels, post.kernel_size[0]
@@ -502,8 +526,8 @@ class GeneratorTrainer:
             for j in range(nk - 1):
                 main.wait_stream(lanes.streams[j])
             others = [st["gs"][j][0] for j in range(nk - 1)] + [None, None]
-            dx_raw = self._branch_backward(L, st, i, nk - 1, b, t, c, g0, (others[0], others[1]))
             up = self.g_ups[i]
+            dx_raw = self._branch_backward(L, st, i, nk - 1, b, t, c, g0, (others[0], others[1]), up.bias_dst(c))
             t_in = st["t_in"]
             up_in = ws["pre_act"] if i == 0 else stages[i - 1]["stage_act"]
 
@@ -513,9 +537,10 @@ class GeneratorTrainer:
                 up.to_param_grads(L)
             self._side(L, self.W_LANE, main, up_grads)
             if i > 0:
-                up.dgrad(L, dx_raw, b, t_in, stages[i - 1]["g0"], mask=up_in, scale=1.0 / nk)
+                up.dgrad(L, dx_raw, b, t_in, stages[i - 1]["g0"], mask=up_in, scale=1.0 / nk,
+                         bias_dsts=self._last_conv_bias_dsts(i - 1, stages[i - 1]["c"]))
             else:
-                up.dgrad(L, dx_raw, b, t_in, ws["g_pre"], mask=up_in)
+                up.dgrad(L, dx_raw, b, t_in, ws["g_pre"], mask=up_in, bias_dsts=(self.g_pre.bias_dst(e.pre.cout_p),))
                 self.g_pre.bias_grad(L, ws["g_pre"], b, frames, e.pre.cout_p)
                 self.g_pre.wgrad(L, ws["mel"], ws["g_pre"], b, frames)
                 self.g_pre.to_param_grads(L)
@@ -546,10 +571,11 @@ class _DiscBwdLayer:
                    "hg_pack_disc_weight")
 
     def dgrad(self, L, dy, nseq: int, t_dy_valid: int, t_dy_rows: int, rows_in: int, act_g, act_r, fm_coef: float,
-              out, st, flat_h_in: Optional[int] = None) -> None:
-        """out[nseq][rows_in][cin] = (conv^T(dy) + fm_coef * sgn(act_g - act_r)) * lrelu'(act_g).
+              out, st, flat_h_in: Optional[int] = None, bias_dst: int = 0, pre_add=None) -> None:
+        """out[nseq][rows_in][cin] = (conv^T(dy) + fm_coef * sgn(act_g - act_r) + pre_add) * lrelu'(act_g).
         flat_h_in given: the nseq sequences are laid end to end (pitch t_dy_rows output rows / rows_in input rows
-        each, zero gap rows) and run as ONE long sequence; only positions < flat_h_in of each are stored."""
+        each, zero gap rows) and run as ONE long sequence; only positions < flat_h_in of each are stored.
+        bias_dst: fp32 [cin] bias gradient of the layer that produced act_g, += column sums of `out` (fp32)."""
         layer = self.layer
         s = layer.stride
         vrows = rows_in // s
@@ -561,7 +587,8 @@ class _DiscBwdLayer:
                                      layer.groups_eff if self.grouped else 1,
                                      layer.cin_tile if self.grouped else 0, s * layer.cin, self.nshift, 1,
                                      self.pad_left, _p(act_g), LRELU_SLOPE, _p(act_r),
-                                     _p(act_g) if act_r is not None else 0, fm_coef, 0, 0, 0, 1.0, _p(out), *seq, st),
+                                     _p(act_g) if act_r is not None else 0, fm_coef, 0, 0, 0, 1.0, _p(out), *seq,
+                                     _p(pre_add), bias_dst, 0, 0, layer.cin, st),
                    "hg_conv1d_dgrad")
 
 
@@ -897,18 +924,21 @@ class _SubDiscTrainer:
 
         # fm_r for the generated half is the real half of the same buffer (seq - nr)
         fm_r_last = act_last[seq0 - nr:].data_ptr() if fm else 0
+        # every data-gradient launch of the discriminator step also sums the bias gradient of the layer whose output
+        # it differentiates, in fp32, straight into the flat gradient buffer (zeroed in run_phases)
+        bias_of = (lambda li: self.mods[li].bias.grad.data_ptr()) if want_wgrad else (lambda li: 0)
         _lib.check(L.hg_disc_last_conv_bwd(act_last[seq0:].data_ptr(), W["wp"].data_ptr(), G["dlogit"][seq0:].data_ptr(),
                                            nseq, h_last, rows_last, c_last, self.kpost, LRELU_SLOPE, fm_r_last,
-                                           nfm[nl] if fm else 0.0, G["grad"][-1][seq0:].data_ptr(), 0, 0, _stream()),
-                   "hg_disc_last_conv_bwd")
+                                           nfm[nl] if fm else 0.0, 0, G["grad"][-1][seq0:].data_ptr(), 0, 0,
+                                           bias_of(nl), _stream()), "hg_disc_last_conv_bwd")
         if want_wgrad:
             def post_grads():
                 self.scratch[: c_last * self.kpost].zero_()
                 self.db.zero_()
                 _lib.check(L.hg_disc_last_conv_bwd(act_last[seq0:].data_ptr(), W["wp"].data_ptr(),
                                                    G["dlogit"][seq0:].data_ptr(), nseq, h_last, rows_last, c_last,
-                                                   self.kpost, LRELU_SLOPE, 0, 0.0, 0, self.scratch.data_ptr(),
-                                                   self.db.data_ptr(), _stream()), "hg_disc_last_conv_bwd")
+                                                   self.kpost, LRELU_SLOPE, 0, 0.0, 0, 0, self.scratch.data_ptr(),
+                                                   self.db.data_ptr(), 0, _stream()), "hg_disc_last_conv_bwd")
                 self._route(L, post, self.scratch, 1, c_last * self.kpost, W, len(self.mods) - 1, True)
                 self._bias(post, self.db[:1], True)
             side(post_grads)
@@ -923,9 +953,6 @@ class _SubDiscTrainer:
                 def layer_grads(layer=layer, m=m, li=li, h_out=h_out, rows_out=rows_out, rows_in=rows_in, d_out=d_out,
                                 a_in=a_in):
                     st = _stream()
-                    # bias.grad += column sums, in place (the flat gradient buffer was zeroed in backward_d)
-                    _lib.check(L.hg_colsum_bf16(d_out.data_ptr(), nseq, h_out, rows_out, layer.cout, 1,
-                                                m.bias.grad.data_ptr(), st), "hg_colsum_bf16")
                     _lib.check(L.hg_conv1d_wgrad(a_in[seq0:].data_ptr(), d_out.data_ptr(), 1, nseq * rows_in, layer.cin,
                                                  nseq * rows_out, nseq * rows_out, layer.groups_eff, layer.cout,
                                                  layer.k, layer.stride, 1, layer.pad, self.dwp.data_ptr(), 0, st),
@@ -946,20 +973,20 @@ class _SubDiscTrainer:
                 side(layer_grads)
             bwd[li].dgrad(L, d_out, nseq, h_out, rows_out, rows_in, a_in[seq0:],
                           a_in[seq0 - nr:] if fm else None, nfm[li] if fm else 0.0, G["grad"][li][seq0:], _stream(),
-                          flat_h_in=h_in)
+                          flat_h_in=h_in, bias_dst=bias_of(li))
         # first conv (Cin = 1)
         k0, s0, p0, c0 = self.first
         m0 = self.mods[0]
         if want_wgrad:
             def first_grads():
                 self.scratch[: c0 * k0].zero_()
-                self.db.zero_()
+                # the kernel's own bias column (summed from the bf16 gradient) lands in the db scratch and is not
+                # used: the first conv's bias gradient came from the fp32 sums of the launch that produced grad[0]
                 _lib.check(L.hg_disc_first_conv_bwd(self.ycat[b0:].data_ptr(), W["w0"].data_ptr(),
                                                     G["grad"][0][seq0:].data_ptr(), bn, self.t, period, k0, s0, p0, c0,
                                                     geo[0][1], self.scratch.data_ptr(), self.db.data_ptr(), 0,
                                                     _stream()), "hg_disc_first_conv_bwd")
                 self._route(L, m0, self.scratch, c0, k0, W, 0, True)
-                self._bias(m0, self.db[:c0], True)
             side(first_grads)
         if dy_audio is not None:
             _lib.check(L.hg_disc_first_conv_bwd(self.ycat[b0:].data_ptr(), W["w0"].data_ptr(),

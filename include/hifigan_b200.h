@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HG_ABI_VERSION 1
+#define HG_ABI_VERSION 2
 
 /* Library identity / diagnostics. */
 const char* hg_version(void);
@@ -238,12 +238,21 @@ int hg_pack_dgrad_weight(const void* w_packed, int ktaps, int n, int c, void* ou
  * block nt % groups — the polyphase (phase-major) output of a strided grouped conv's gradient.
  * Flat sequences (seq_pitch > 0, batch == 1, see hg_conv1d_general_fwd): output element (row t, channel n) is stored
  * only when (t % seq_pitch) * seq_mul + n / seq_div < seq_valid — for a polyphase gradient seq_mul = stride and
- * seq_div = the layer's input channel count, i.e. the input position the element stands for must be real. */
+ * seq_div = the layer's input channel count, i.e. the input position the element stands for must be real.
+ *
+ * pre_add (optional, bf16, same layout as out) is added to the accumulator before the mask: a gradient arriving
+ * at the layer's activated input from outside the chain (an exported feature map's gradient under autograd).
+ * bias_grad0..2 (optional, fp32 [bias_mod]): the bias gradient of the layer whose output `out` is the gradient of
+ * — bias_grad*[n % bias_mod] += sum_{b,t} out[b,t,n], summed in fp32 from the accumulators BEFORE `out` is rounded
+ * to bf16 (replaces a separate column-sum pass over the bf16 tensor).  bias_mod = 0: cout; a polyphase gradient
+ * passes the layer's input channel count so the `stride` phases of a channel fold together.  Up to three
+ * destinations receive the same sums (the last convs of the MRF branches share one output gradient). */
 int hg_conv1d_dgrad(const void* dy, const void* w_packed, int batch, int t_dy_valid, int t_dy_rows, int c_dy_total,
                     int t_out, int t_out_rows, int groups, int n_tile, int cout, int ktaps, int dilation, int pad_left,
                     const void* mask_src, float mask_slope, const void* fm_r, const void* fm_g, float fm_coef,
                     const void* res0, const void* res1, const void* res2, float scale, void* out, int seq_pitch,
-                    int seq_valid, int seq_mul, int seq_div, void* stream);
+                    int seq_valid, int seq_mul, int seq_div, const void* pre_add, float* bias_grad0,
+                    float* bias_grad1, float* bias_grad2, int bias_mod, void* stream);
 
 /* hg_conv1d_wgrad — weight gradient as a tcgen05 implicit GEMM contracting over time (MN-major operands):
  *   dw[q][co][ci] (+)= sum_{b, t < t_out} dy[b,t,co] * xv[b, t + row(q), col(q) + blk(co) + ci]
@@ -305,21 +314,24 @@ int hg_spectral_norm_bwd(const float* dw_eff, const float* w_eff, const float* u
 int hg_colsum_bf16(const void* x, int batch, int t_valid, int t_rows, int c, int accumulate, float* out, void* stream);
 
 /* hg_conv_post_tanh_bwd — backward of hg_conv_post_tanh_fwd.  x bf16 [B][T][C] (the activated input), y fp32 [B][T]
- * (the forward output), dy fp32 [B][T] -> dx bf16 [B][T][C] = gradient at the PRE-activation of x (the
- * leaky_relu(., in_slope) mask taken from x's sign), dw fp32 [C][k] and db fp32 [1] (both ADDED to; may be NULL).
- * dpre_ws fp32 [B][T] receives dy * (1 - y^2). */
+ * (the forward output), dy fp32 [B][T] -> dx bf16 [B][T][C] = dx_scale * gradient at the PRE-activation of x (the
+ * leaky_relu(., in_slope) mask taken from x's sign; dx_scale = 1 / num_kernels hands every MRF branch its share,
+ * src/models.py:111), dw fp32 [C][k] and db fp32 [1] (both ADDED to; may be NULL).  dpre_ws fp32 [B][T] receives
+ * dy * (1 - y^2).  bias_grad0..2 (optional, fp32 [C]) += column sums of dx in fp32 (see hg_conv1d_dgrad). */
 int hg_conv_post_tanh_bwd(const void* x, const float* w, const float* y, const float* dy, int batch, int t, int c,
-                          int k, float in_slope, void* dx, float* dpre_ws, float* dw, float* db, void* stream);
+                          int k, float in_slope, float dx_scale, void* dx, float* dpre_ws, float* dw, float* db,
+                          float* bias_grad0, float* bias_grad1, float* bias_grad2, void* stream);
 
 /* Discriminator ends, backward.  hg_disc_last_conv_bwd: dx bf16 [S][h_rows][C] = (conv^T(dlogit) + fm_coef *
- * sgn(x - fm_r)) * lrelu'(x) (x = the last wide layer's activated output, fm_r optional), dw fp32 [C][k] / db
- * ADDED to (NULL to skip; dx may be NULL too).  hg_disc_first_conv_bwd: dpre bf16 [B*period][h_rows][cout] is the
+ * sgn(x - fm_r) + pre_add) * lrelu'(x) (x = the last wide layer's activated output; fm_r, pre_add optional, layout
+ * of x), dw fp32 [C][k] / db ADDED to (NULL to skip; dx may be NULL too); bias_grad_in (optional, fp32 [C]) +=
+ * column sums of dx in fp32 = the bias gradient of the layer that produced x.  hg_disc_first_conv_bwd: dpre bf16 [B*period][h_rows][cout] is the
  * gradient at the first conv's output (mask applied) -> dw fp32 [cout][k], db fp32 [cout] (ADDED to; NULL to skip)
  * and / or dy fp32 [B][T] (ADDED to: the gradient reaching the audio, reflect-padded tail folded back).
  * hg_avgpool_4_2_2_bwd: din fp32 [B][T] += backward of AvgPool1d(4,2,2) from dout fp32 [B][T/2+1]. */
 int hg_disc_last_conv_bwd(const void* x, const float* w, const float* dlogit, int nseq, int h, int h_rows, int c,
-                          int k, float slope, const void* fm_r, float fm_coef, void* dx, float* dw, float* db,
-                          void* stream);
+                          int k, float slope, const void* fm_r, float fm_coef, const void* pre_add, void* dx, float* dw,
+                          float* db, float* bias_grad_in, void* stream);
 int hg_disc_first_conv_bwd(const float* y, const float* w, const void* dpre, int batch, int t, int period, int k,
                            int stride, int pad, int cout, int h_rows, float* dw, float* db, float* dy, void* stream);
 int hg_avgpool_4_2_2_bwd(const float* dout, int batch, int t, float* din, void* stream);

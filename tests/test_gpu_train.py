@@ -112,17 +112,24 @@ def test_dgrad_stride1_vs_torch_autograd(H, case):
     dy = torch.randn(b, t + 2, cout, generator=gen).to(dev).bfloat16()
     res = torch.randn(b, t, cin, generator=gen).to(dev).bfloat16()
     out = torch.empty(b, t, cin, dtype=torch.bfloat16, device=dev)
+    pre = torch.randn(b, t, cin, generator=gen).to(dev).bfloat16()
+    bsum = torch.full((2, cin), 0.25, device=dev)       # two destinations, both ADDED to
     _lib.check(L.hg_conv1d_dgrad(dy.data_ptr(), wd.data_ptr(), b, t, t + 2, cout, t, t, 1, 0, cin, k, d,
                                  (k - 1) * d - pad, x_act.data_ptr(), 0.1, 0, 0, 0.0, res.data_ptr(), 0, 0, 0.5,
-                                 out.data_ptr(), 0, 0, 1, 0, _st()), "hg_conv1d_dgrad")
+                                 out.data_ptr(), 0, 0, 1, 0, pre.data_ptr(), bsum[0].data_ptr(), bsum[1].data_ptr(), 0,
+                                 0, _st()), "hg_conv1d_dgrad")
     torch.cuda.synchronize()
     wr = wp.float().permute(1, 2, 0).contiguous()
     xin = x_act.float().transpose(1, 2).requires_grad_(True)
     y = F.conv1d(xin, wr, None, dilation=d, padding=pad)
     y.backward(dy[:, :t].float().transpose(1, 2))
     mask = torch.where(x_act.float() > 0, 1.0, 0.1)
-    ref = (xin.grad.transpose(1, 2) * mask + res.float()) * 0.5
+    ref = ((xin.grad.transpose(1, 2) + pre.float()) * mask + res.float()) * 0.5
     assert bool(((out.float() - ref).abs() <= 2.0 ** -7 * ref.abs() + 2e-3).all())
+    # the fused bias gradient: fp32 column sums of the un-rounded output, added to every destination
+    cs = ref.sum((0, 1))
+    tol = 1e-3 * ref.abs().sum((0, 1)).max().item() + 1e-3
+    assert (bsum[0] - 0.25 - cs).abs().max().item() <= tol and torch.equal(bsum[0], bsum[1])
 
 
 STRIDED_DGRAD_CASES = [
@@ -163,7 +170,8 @@ def test_dgrad_strided_grouped_vs_torch_autograd(H, case):
     bl.pack(w, layer.pack(w))
     out = torch.zeros(b, rows, cin, dtype=torch.bfloat16, device=dev)
     fm_coef = 0.37
-    bl.dgrad(L, dy, b, t_out, rows_out, rows, act_g, act_r, fm_coef, out, _st())
+    bsum = torch.zeros(cin, device=dev)
+    bl.dgrad(L, dy, b, t_out, rows_out, rows, act_g, act_r, fm_coef, out, _st(), bias_dst=bsum.data_ptr())
     torch.cuda.synchronize()
     xin = act_g[:, :t].float().transpose(1, 2).requires_grad_(True)
     y = F.conv1d(xin, w, None, stride=s, padding=pad, groups=g)
@@ -172,6 +180,9 @@ def test_dgrad_strided_grouped_vs_torch_autograd(H, case):
     ref = (xin.grad.transpose(1, 2) + fm_coef * torch.sign(ag - ar)) * torch.where(ag > 0, 1.0, 0.1)
     got = out[:, :t].float()
     assert bool(((got - ref).abs() <= 2.0 ** -7 * ref.abs() + 3e-3).all()), (got - ref).abs().max().item()
+    if rows == t:       # fused bias gradient: the `stride` phases of a channel fold together (bias_mod = cin)
+        cs = ref.sum((0, 1))
+        assert (bsum - cs).abs().max().item() <= 1e-3 * ref.abs().sum((0, 1)).max().item() + 1e-3
 
 
 def test_small_backward_kernels_vs_torch(H):
@@ -200,12 +211,15 @@ def test_small_backward_kernels_vs_torch(H):
     dpre = torch.empty(b, t, device=dev)
     dw = torch.zeros(c, k, device=dev)
     db = torch.zeros(1, device=dev)
+    bs = torch.zeros(3, c, device=dev)
     _lib.check(L.hg_conv_post_tanh_bwd(xa.data_ptr(), w[0].contiguous().data_ptr(), y.detach().contiguous().data_ptr(),
-                                       dy.data_ptr(), b, t, c, k, 0.01, dx.data_ptr(), dpre.data_ptr(), dw.data_ptr(),
-                                       db.data_ptr(), _st()))
+                                       dy.data_ptr(), b, t, c, k, 0.01, 1.0 / 3, dx.data_ptr(), dpre.data_ptr(),
+                                       dw.data_ptr(), db.data_ptr(), bs[0].data_ptr(), bs[1].data_ptr(),
+                                       bs[2].data_ptr(), _st()))
     torch.cuda.synchronize()
-    ref_dx = xin.grad.transpose(1, 2) * torch.where(xa.float() > 0, 1.0, 0.01)
+    ref_dx = xin.grad.transpose(1, 2) * torch.where(xa.float() > 0, 1.0, 0.01) / 3
     assert bool(((dx.float() - ref_dx).abs() <= 2.0 ** -7 * ref_dx.abs() + 1e-4).all())
+    assert torch.allclose(bs[0], ref_dx.sum((0, 1)), rtol=1e-4, atol=1e-4) and torch.equal(bs[0], bs[2])
     assert torch.allclose(dw, wr.grad[0], rtol=1e-3, atol=1e-3)
     assert torch.allclose(db, br.grad, rtol=1e-3, atol=1e-3)
     # avg-pool backward
@@ -260,12 +274,18 @@ def test_disc_end_backward_kernels_vs_torch(H):
     F.conv1d(xin, wr, br, padding=1).squeeze(1).backward(dl)
     dx = torch.zeros_like(x)
     dw, db = torch.zeros(c, k, device=dev), torch.zeros(1, device=dev)
+    pre = torch.zeros_like(x)
+    pre[:, :h] = torch.randn(s_, h, c, generator=gen).to(dev).bfloat16()
+    bsum = torch.zeros(c, device=dev)
     _lib.check(L.hg_disc_last_conv_bwd(x.data_ptr(), w[0].contiguous().data_ptr(), dl.data_ptr(), s_, h, rows, c, k,
-                                       0.1, fr.data_ptr(), 0.25, dx.data_ptr(), dw.data_ptr(), db.data_ptr(), _st()))
+                                       0.1, fr.data_ptr(), 0.25, pre.data_ptr(), dx.data_ptr(), dw.data_ptr(),
+                                       db.data_ptr(), bsum.data_ptr(), _st()))
     torch.cuda.synchronize()
     xa, ra = x[:, :h].float(), fr[:, :h].float()
-    ref = (xin.grad.transpose(1, 2) + 0.25 * torch.sign(xa - ra)) * torch.where(xa > 0, 1.0, 0.1)
+    ref = (xin.grad.transpose(1, 2) + 0.25 * torch.sign(xa - ra) + pre[:, :h].float()) * torch.where(xa > 0, 1.0, 0.1)
     assert bool(((dx[:, :h].float() - ref).abs() <= 2.0 ** -7 * ref.abs() + 1e-4).all())
+    assert torch.equal(dx[:, h:], torch.zeros_like(dx[:, h:]))          # pitch rows stay untouched
+    assert torch.allclose(bsum, ref.sum((0, 1)), rtol=1e-4, atol=1e-3)
     assert torch.allclose(dw, wr.grad[0], rtol=1e-3, atol=1e-3) and torch.allclose(db, br.grad, rtol=1e-3, atol=1e-3)
     # first conv (Cin = 1) with the period view and reflect pad
     for period, k0, s0, p0, c0, t in [(3, 5, 3, 2, 32, 1000), (1, 15, 1, 7, 128, 777), (7, 5, 3, 2, 32, 8192)]:

@@ -134,7 +134,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/hifigan_b200.h but not exported"
     assert declared == set(_lib.EXPORTED_SYMBOLS)
-    assert _lib.lib().hg_abi_version() == 1
+    assert _lib.lib().hg_abi_version() == 2
 
 
 def test_convtr_geometry():
