@@ -37,10 +37,10 @@ _LOCK_PATH = os.path.join(_HERE, ".build.lock")
 def _source_hash() -> str:
     """Content hash of everything the library is compiled from (file times do not survive the copy to a GPU box)."""
     h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
-    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC))
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
     deps.append(os.path.join(os.path.dirname(_HERE), "include", "hifigan_b200.h"))
     for d in deps:
-        if os.path.exists(d):
+        if os.path.isfile(d):
             h.update(os.path.basename(d).encode())
             with open(d, "rb") as f:
                 h.update(f.read())
