@@ -141,7 +141,39 @@ __global__ void disc_export_fmap_kernel(const __nv_bfloat16* __restrict__ x, int
   }
 }
 
+// fp32 [B][C][H][p] -> bf16 [B*p][h_rows][C] (rows >= H are not written): the inverse of disc_export_fmap_kernel,
+// for a gradient that arrives at an exported feature map
+__global__ void disc_import_fmap_kernel(const float* __restrict__ in, int period, int h, int h_rows, int c,
+                                        __nv_bfloat16* __restrict__ x) {
+  __shared__ float tile[32][33];
+  const int seq = blockIdx.z;
+  const int b = seq / period, wcol = seq % period;
+  const int c0 = blockIdx.x * 32, h0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int i = ty; i < 32; i += 8) {
+    const int cc = c0 + i, hh = h0 + tx;
+    tile[i][tx] = (cc < c && hh < h) ? in[((static_cast<size_t>(b) * c + cc) * h + hh) * period + wcol] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int hh = h0 + i, cc = c0 + tx;
+    if (hh < h && cc < c) x[(static_cast<size_t>(seq) * h_rows + hh) * c + cc] = __float2bfloat16(tile[tx][i]);
+  }
+}
+
 }  // namespace
+
+extern "C" int hg_disc_import_fmap(const float* in, int batch, int period, int h, int h_rows, int c, void* x,
+                                   void* stream) {
+  HG_REQUIRE(x && in && batch > 0 && period > 0 && h > 0 && h_rows >= h && c > 0, "hg_disc_import_fmap: bad arguments");
+  HG_REQUIRE(batch * period <= 65535 && (h + 31) / 32 <= 65535, "hg_disc_import_fmap: grid too large");
+  dim3 grid((c + 31) / 32, (h + 31) / 32, batch * period), block(32, 8);
+  disc_import_fmap_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(in, period, h, h_rows, c,
+                                                                                 static_cast<__nv_bfloat16*>(x));
+  HG_CHECK_CUDA(cudaGetLastError());
+  g_hg_launches.fetch_add(1, std::memory_order_relaxed);
+  return HG_OK;
+}
 
 extern "C" int hg_disc_first_conv_fwd(const float* y, const float* w, const float* bias, int batch, int t,
                                       int period, int k, int stride, int pad, int cout, int h_rows_out,

@@ -27,6 +27,13 @@ from .models import (LRELU_SLOPE, DiscriminatorP, DiscriminatorS, Generator, Mul
                      generator_loss)
 
 
+def _gb(param: torch.Tensor) -> torch.Tensor:
+    """The buffer this library writes `param`'s gradient into (a view of its network's flat gradient buffer, set by
+    FlatParams).  TrainStep binds it as `param.grad` as well; the autograd path (autograd.py) keeps it private and
+    hands copies to torch."""
+    return param._hg_grad
+
+
 def _p(x) -> int:
     """device pointer of a tensor / raw int pointer / None"""
     if x is None:
@@ -66,19 +73,28 @@ class FlatParams:
     the optimizer step is one kernel launch and the data-parallel all-reduce one NCCL call per network.
     state_dict() / load_state_dict() keep working — they copy through the views."""
 
-    def __init__(self, module: nn.Module, device):
+    def __init__(self, module: nn.Module, device, bind: bool = True):
+        """bind=False (the autograd path): only the flat GRADIENT buffer is created and attached to the parameters as
+        `_hg_grad`; parameters, `.grad` and the optimizer state stay torch's."""
         self.module = module
+        self.bound = bind
         ps = [p for p in module.parameters()]
         self.sizes = [p.numel() for p in ps]
-        n = sum(self.sizes)
         # 16-byte aligned offsets so kernels may use vector accesses on any view
         self.offsets, off = [], 0
         for s in self.sizes:
             self.offsets.append(off)
             off += (s + 3) // 4 * 4
         self.numel = off
-        self.p = torch.zeros(off, dtype=torch.float32, device=device)
         self.g = torch.zeros(off, dtype=torch.float32, device=device)
+        self.params = ps
+        if not bind:
+            for p, o, s in zip(ps, self.offsets, self.sizes):
+                if p.device != self.g.device or p.dtype != torch.float32 or not p.is_contiguous():
+                    raise RuntimeError("hifigan_b200: parameters must be contiguous fp32 tensors on the CUDA device")
+                p._hg_grad = self.g[o:o + s].view(p.shape)
+            return
+        self.p = torch.zeros(off, dtype=torch.float32, device=device)
         self.m = torch.zeros(off, dtype=torch.float32, device=device)
         self.v = torch.zeros(off, dtype=torch.float32, device=device)
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=device)   # AdamW step counter (graph-capturable)
@@ -90,7 +106,7 @@ class FlatParams:
                 view.copy_(p.detach().to(device=device, dtype=torch.float32))
                 p.data = view
                 p.grad = self.g[o:o + s].view(p.shape)
-        self.params = ps
+                p._hg_grad = p.grad
 
     def adamw(self, lr: float, betas=(0.8, 0.99), eps: float = 1e-8, weight_decay: float = 0.01,
               grad_scale: float = 1.0) -> None:
@@ -219,7 +235,7 @@ class _GenLayerGrad:
         """pointer of bias.grad when the producer of this layer's output gradient can add its fp32 column sums
         straight into it (no channel padding: c output columns == cout), else 0 -> bias_grad() runs afterwards"""
         b = self.pc.module.bias
-        return b.grad.data_ptr() if (b is not None and c == self.pc.cout) else 0
+        return _gb(b).data_ptr() if (b is not None and c == self.pc.cout) else 0
 
     def bias_grad(self, L, dy, batch: int, t: int, c: int) -> None:
         """bias.grad (+)= column sums of dy [B][t][c] — only for layers with channel padding (V2's 16-channel stage);
@@ -228,12 +244,12 @@ class _GenLayerGrad:
         if b is None or self.bias_dst(c):
             return
         if c == self.pc.cout:
-            _lib.check(L.hg_colsum_bf16(_p(dy), batch, t, t, c, 1, b.grad.data_ptr(), _stream()), "hg_colsum_bf16")
+            _lib.check(L.hg_colsum_bf16(_p(dy), batch, t, t, c, 1, _gb(b).data_ptr(), _stream()), "hg_colsum_bf16")
         else:
             if self.db is None:
                 self.db = torch.zeros(c, dtype=torch.float32, device=dy.device)
             _lib.check(L.hg_colsum_bf16(_p(dy), batch, t, t, c, 0, self.db.data_ptr(), _stream()), "hg_colsum_bf16")
-            b.grad.add_(self.db[: self.pc.cout])
+            _gb(b).add_(self.db[: self.pc.cout])
 
     def dgrad(self, L, dy, batch: int, t: int, out, mask=None, slope: float = LRELU_SLOPE, res0=None, res1=None,
               res2=None, scale: float = 1.0, bias_dsts=()) -> None:
@@ -250,15 +266,15 @@ class _GenLayerGrad:
         pc = self.pc
         m = pc.module
         g, v = _g_v(m)
-        gp, dgp = (0, 0) if g is None else (g.data_ptr(), g.grad.data_ptr())
+        gp, dgp = (0, 0) if g is None else (g.data_ptr(), _gb(g).data_ptr())
         if pc.kind == "conv":
             _lib.check(L.hg_wgrad_finish_conv(self.dwp.data_ptr(), pc.cout, pc.cin, pc.taps, self.rows, pc.cin_p,
-                                              pc.cout, 1, None, v.data_ptr(), gp, 1, v.grad.data_ptr(), dgp,
+                                              pc.cout, 1, None, v.data_ptr(), gp, 1, _gb(v).data_ptr(), dgp,
                                               _stream()), "hg_wgrad_finish_conv")
         else:
             _lib.check(L.hg_wgrad_finish_convtr(self.dwp.data_ptr(), pc.cin, pc.cout, m.kernel_size[0], pc.stride,
                                                 m.padding[0], pc.cin_p, pc.cout_p, v.data_ptr(), gp, 1,
-                                                v.grad.data_ptr(), dgp, _stream()), "hg_wgrad_finish_convtr")
+                                                _gb(v).data_ptr(), dgp, _stream()), "hg_wgrad_finish_convtr")
 
 
 def _route_weight_grad(L, m: nn.Module, dw: torch.Tensor, d0: int, rest: int, accumulate: bool = False) -> None:
@@ -266,13 +282,13 @@ def _route_weight_grad(L, m: nn.Module, dw: torch.Tensor, d0: int, rest: int, ac
     g, v = _g_v(m)
     if g is not None:
         _lib.check(L.hg_weight_norm_bwd(dw.data_ptr(), v.data_ptr(), g.data_ptr(), d0, rest, 1 if accumulate else 0,
-                                        v.grad.data_ptr(), g.grad.data_ptr(), _stream()), "hg_weight_norm_bwd")
+                                        _gb(v).data_ptr(), _gb(g).data_ptr(), _stream()), "hg_weight_norm_bwd")
     else:
         src = dw[: d0 * rest].view(v.shape)
         if accumulate:
-            v.grad.add_(src)
+            _gb(v).add_(src)
         else:
-            v.grad.copy_(src)
+            _gb(v).copy_(src)
 
 
 class GeneratorTrainer:
@@ -509,7 +525,7 @@ class GeneratorTrainer:
         def post_grads():
             cin, k = post.in_channels, post.kernel_size[0]
             _route_weight_grad(L, post, self.post_dw[:cin].contiguous(), 1, cin * k)
-            post.bias.grad.copy_(self.post_db)      # flat.g was zeroed: plain stores here
+            _gb(post.bias).copy_(self.post_db)      # flat.g was zeroed: plain stores here
         self._side(L, self.W_LANE, main, post_grads)
         for i in reversed(range(len(e.ups))):
             st = stages[i]
@@ -926,7 +942,7 @@ class _SubDiscTrainer:
         fm_r_last = act_last[seq0 - nr:].data_ptr() if fm else 0
         # every data-gradient launch of the discriminator step also sums the bias gradient of the layer whose output
         # it differentiates, in fp32, straight into the flat gradient buffer (zeroed in run_phases)
-        bias_of = (lambda li: self.mods[li].bias.grad.data_ptr()) if want_wgrad else (lambda li: 0)
+        bias_of = (lambda li: _gb(self.mods[li].bias).data_ptr()) if want_wgrad else (lambda li: 0)
         _lib.check(L.hg_disc_last_conv_bwd(act_last[seq0:].data_ptr(), W["wp"].data_ptr(), G["dlogit"][seq0:].data_ptr(),
                                            nseq, h_last, rows_last, c_last, self.kpost, LRELU_SLOPE, fm_r_last,
                                            nfm[nl] if fm else 0.0, 0, G["grad"][-1][seq0:].data_ptr(), 0, 0,
@@ -968,8 +984,8 @@ class _SubDiscTrainer:
                         g, v = _g_v(m)          # unpack + weight_norm backward in one launch, accumulating
                         _lib.check(L.hg_wgrad_finish_conv(self.dwp.data_ptr(), layer.cout, cin_g, layer.k, layer.cout,
                                                           layer.cin_tile, layer.cout // layer.groups, layer.merge,
-                                                          order, v.data_ptr(), g.data_ptr(), 1, v.grad.data_ptr(),
-                                                          g.grad.data_ptr(), st), "hg_wgrad_finish_conv")
+                                                          order, v.data_ptr(), g.data_ptr(), 1, _gb(v).data_ptr(),
+                                                          _gb(g).data_ptr(), st), "hg_wgrad_finish_conv")
                 side(layer_grads)
             bwd[li].dgrad(L, d_out, nseq, h_out, rows_out, rows_in, a_in[seq0:],
                           a_in[seq0 - nr:] if fm else None, nfm[li] if fm else 0.0, G["grad"][li][seq0:], _stream(),
@@ -996,9 +1012,9 @@ class _SubDiscTrainer:
     @staticmethod
     def _bias(m: nn.Module, db: torch.Tensor, accumulate: bool) -> None:
         if accumulate:
-            m.bias.grad.add_(db)
+            _gb(m.bias).add_(db)
         else:
-            m.bias.grad.copy_(db)
+            _gb(m.bias).copy_(db)
 
     def _route(self, L, m: nn.Module, dw: torch.Tensor, d0: int, rest: int, W, li: int, accumulate: bool) -> None:
         if hasattr(m, "weight_orig"):
@@ -1006,7 +1022,7 @@ class _SubDiscTrainer:
             u, v, sigma, snws = W["sn"][li]
             _lib.check(L.hg_spectral_norm_bwd(dw.data_ptr(), W["eff"][li].data_ptr(), u.data_ptr(), v.data_ptr(),
                                               sigma.data_ptr(), d0, rest, 1 if accumulate else 0,
-                                              m.weight_orig.grad.data_ptr(), snws.data_ptr(), _stream()),
+                                              _gb(m.weight_orig).data_ptr(), snws.data_ptr(), _stream()),
                        "hg_spectral_norm_bwd")
         else:
             _route_weight_grad(L, m, dw, d0, rest, accumulate)
