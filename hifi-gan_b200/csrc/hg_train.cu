@@ -448,8 +448,11 @@ __global__ void avgpool_bwd_kernel(const float* __restrict__ dout, int t, int t_
 }
 
 // mode 0: out = coef * sgn(a - b); mode 1: out = coef * (a - c); mode 2: out = coef * (a - c) + coef2 * sgn(a - b)
+// scale_dev (optional): a device scalar both coefficients are multiplied with (the incoming gradient of a mean)
 __global__ void loss_grad_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, int mode,
-                                 float c, float coef, float coef2, float* __restrict__ out) {
+                                 float c, float coef, float coef2, const float* __restrict__ scale_dev,
+                                 float* __restrict__ out) {
+  if (scale_dev) { const float sc = *scale_dev; coef *= sc; coef2 *= sc; }
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x) {
     const float av = a[i];
     float g;
@@ -920,9 +923,9 @@ extern "C" int hg_avgpool_4_2_2_bwd(const float* dout, int batch, int t, float* 
 }
 
 extern "C" int hg_loss_grad(const float* a, const float* b, long long n, int mode, float c, float coef, float coef2,
-                            float* out, void* stream) {
+                            const float* scale_dev, float* out, void* stream) {
   HG_REQUIRE(a && out && n > 0 && mode >= 0 && mode <= 2 && (mode == 1 || b), "hg_loss_grad: bad arguments");
-  loss_grad_kernel<<<blocks_for(n), 256, 0, S(stream)>>>(a, b, n, mode, c, coef, coef2, out);
+  loss_grad_kernel<<<blocks_for(n), 256, 0, S(stream)>>>(a, b, n, mode, c, coef, coef2, scale_dev, out);
   HG_CHECK_CUDA(cudaGetLastError());
   count();
   return HG_OK;

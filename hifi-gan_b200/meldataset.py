@@ -101,13 +101,19 @@ def mel_spectrogram(y, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin,
         y2 = y2.float()
     b, t = y2.shape
     frames = plan.frames(t)
-    out = torch.empty(b, num_mels, frames, dtype=torch.float32, device=y.device)
     if len(_pending_range_checks) >= 6:   # never let a ring slot be reused while its check is pending
         flush_range_warnings(block=True)
     minmax, host = plan.next_minmax()
     stream = torch.cuda.current_stream()
-    _lib.check(_lib.lib().hg_mel_fwd(plan.handle, y2.data_ptr(), b, t, out.data_ptr(), minmax.data_ptr(),
-                                     stream.cuda_stream), "hg_mel_fwd")
+    if torch.is_grad_enabled() and y2.requires_grad:
+        # differentiable call (the generated-mel L1 term of the training loss): hg_mel_fwd / hg_mel_bwd as one
+        # autograd.Function
+        from . import autograd
+        out = autograd.mel_forward(y2, plan, minmax.data_ptr())
+    else:
+        out = torch.empty(b, num_mels, frames, dtype=torch.float32, device=y.device)
+        _lib.check(_lib.lib().hg_mel_fwd(plan.handle, y2.data_ptr(), b, t, out.data_ptr(), minmax.data_ptr(),
+                                         stream.cuda_stream), "hg_mel_fwd")
     host.copy_(minmax, non_blocking=True)
     ev = torch.cuda.Event()
     ev.record(stream)

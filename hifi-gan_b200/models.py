@@ -238,6 +238,9 @@ class _StandaloneBlockMixin:
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         _require_cuda(x, type(self).__name__)
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError(f"{type(self).__name__} on its own is an inference surface (call it under "
+                                      "torch.no_grad()); it is differentiable as part of Generator")
         L = _lib.lib()
         b, c, t = x.shape
         packs = self._packs(x.device)
@@ -513,16 +516,18 @@ class Generator(torch.nn.Module):
         """mel [B,80,F] -> waveform [B,1,T], a fresh tensor per call like the reference.  (`self._engine(dev)
         .forward(x)` returns the engine-owned buffer without the copy: the benchmark's device-resident path.)"""
         _require_cuda(x, "Generator.forward")
-        if torch.is_grad_enabled() and self.training and (
-                x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError("Generator backward kernels are not built yet (SURVEY §8 row T); "
-                                      "call under torch.no_grad() or .eval()")
         if x.dim() != 3 or x.shape[1] != self.conv_pre.in_channels:
             raise ValueError(f"expected [B,{self.conv_pre.in_channels},F], got {tuple(x.shape)}")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            # differentiable call (an UPSTREAM-style `loss.backward()` loop): one autograd.Function over the training
+            # forward (every conv input kept) and the hand-written backward — autograd.py
+            from . import autograd
+            return autograd.generator_forward(self, x)
         return self._engine(x.device).forward(x).clone()
 
     def _drop_engines(self):
         self.__dict__["_hg_engines"] = {}
+        self.__dict__.pop("_hg_autograd", None)
 
     def remove_weight_norm(self):
         print('Removing weight norm...')
@@ -698,8 +703,10 @@ def _disc_forward(L, owner: nn.Module, y: torch.Tensor, period: int, first, mids
 
 def _check_disc_input(x: torch.Tensor, what: str) -> None:
     _require_cuda(x, what)
-    if torch.is_grad_enabled() and x.requires_grad:
-        raise NotImplementedError(f"{what}: backward kernels are not built yet (SURVEY §8 row T)")
+
+
+def _disc_wants_grad(x: torch.Tensor, disc: nn.Module) -> bool:
+    return torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in disc.parameters()))
 
 
 class DiscriminatorP(torch.nn.Module):
@@ -716,6 +723,9 @@ class DiscriminatorP(torch.nn.Module):
 
     def forward(self, x):
         _check_disc_input(x, "DiscriminatorP.forward")
+        if _disc_wants_grad(x, self):
+            from . import autograd
+            return autograd.disc_forward(self, x)
         convs = list(self.convs)
         first = (convs[0].kernel_size[0], convs[0].stride[0], convs[0].padding[0], convs[0].out_channels)
         mids = self.__dict__.get("_hg_layers")
@@ -757,6 +767,10 @@ class DiscriminatorS(torch.nn.Module):
 
     def forward(self, x):
         _check_disc_input(x, "DiscriminatorS.forward")
+        if _disc_wants_grad(x, self):
+            from . import autograd
+            out, fmap = autograd.disc_forward(self, x)
+            return out, [f.squeeze(-1) for f in fmap]
         convs = list(self.convs)
         first = (convs[0].kernel_size[0], convs[0].stride[0], convs[0].padding[0], convs[0].out_channels)
         mids = self.__dict__.get("_hg_layers")
@@ -779,6 +793,9 @@ class MultiScaleDiscriminator(torch.nn.Module):
 
     @staticmethod
     def _pool(x: torch.Tensor) -> torch.Tensor:
+        if torch.is_grad_enabled() and x.requires_grad:
+            from . import autograd
+            return autograd.avgpool(x)
         b, c, t = x.shape
         xin = x.reshape(b * c, t).contiguous().float()
         out = torch.empty(b * c, t // 2 + 1, dtype=torch.float32, device=x.device)
@@ -800,11 +817,14 @@ class MultiScaleDiscriminator(torch.nn.Module):
         return y_d_rs, y_d_gs, fmap_rs, fmap_gs
 
 
-def _device_mean(a: torch.Tensor, b: Optional[torch.Tensor], mode: int, c: float) -> Optional[torch.Tensor]:
-    """mean |a-b| (mode 0) or mean (c-a)^2 (mode 1) through hg_loss_sum; None when the kernel path does not
-    apply (CPU tensors or tensors that carry autograd history — backward is not built)."""
-    if not a.is_cuda or a.requires_grad or (b is not None and (b.requires_grad or not b.is_cuda)):
-        return None
+def _device_mean(a: torch.Tensor, b: Optional[torch.Tensor], mode: int, c: float) -> torch.Tensor:
+    """mean |a-b| (mode 0) or mean (c-a)^2 (mode 1) through hg_loss_sum; differentiable (hg_loss_grad) when an
+    argument carries autograd history.  No CPU path."""
+    if not a.is_cuda or (b is not None and not b.is_cuda):
+        raise RuntimeError("hifigan_b200 losses have no CPU path; move the tensors to a B200")
+    if torch.is_grad_enabled() and (a.requires_grad or (b is not None and b.requires_grad)):
+        from . import autograd
+        return autograd.device_mean(a, b, mode, c)
     a32 = a.detach().contiguous().float()
     b32 = None if b is None else b.detach().contiguous().float()
     acc = torch.zeros(1, dtype=torch.float32, device=a.device)
@@ -818,8 +838,7 @@ def feature_loss(fmap_r, fmap_g):
     total = 0
     for maps_r, maps_g in zip(fmap_r, fmap_g):
         for r, g in zip(maps_r, maps_g):
-            m = _device_mean(r, g, 0, 0.0)
-            total = total + (m if m is not None else torch.mean(torch.abs(r - g)))
+            total = total + _device_mean(r, g, 0, 0.0)
     return total * 2
 
 
@@ -830,10 +849,6 @@ def discriminator_loss(disc_real_outputs, disc_generated_outputs):
     for dr, dg in zip(disc_real_outputs, disc_generated_outputs):
         r_loss = _device_mean(dr, None, 1, 1.0)
         g_loss = _device_mean(dg, None, 1, 0.0)
-        if r_loss is None:
-            r_loss = torch.mean((1 - dr) ** 2)
-        if g_loss is None:
-            g_loss = torch.mean(dg ** 2)
         total = total + (r_loss + g_loss)
         parts += [r_loss.detach(), g_loss.detach()]
     host = torch.stack(parts).tolist() if parts else []
@@ -842,10 +857,7 @@ def discriminator_loss(disc_real_outputs, disc_generated_outputs):
 
 def generator_loss(disc_outputs):
     """LSGAN generator loss; returns (sum, [per-sub-discriminator tensors]); reference :274-282."""
-    gen_losses = []
-    for dg in disc_outputs:
-        l = _device_mean(dg, None, 1, 1.0)
-        gen_losses.append(l if l is not None else torch.mean((1 - dg) ** 2))
+    gen_losses = [_device_mean(dg, None, 1, 1.0) for dg in disc_outputs]
     total = 0
     for l in gen_losses:
         total = total + l

@@ -294,13 +294,15 @@ def _route_weight_grad(L, m: nn.Module, dw: torch.Tensor, d0: int, rest: int, ac
 class GeneratorTrainer:
     """Training-mode forward (every conv input kept in HBM) and hand-written backward of one Generator."""
 
-    def __init__(self, gen: Generator, device):
+    def __init__(self, gen: Generator, device, bind: bool = True):
+        """bind=False: the autograd path — gradients go to a private flat buffer, parameters stay torch's, and the
+        gradient at the input mel can be produced (conv_pre gets a data-gradient bank)."""
         self.gen, self.device = gen, device
-        self.flat = FlatParams(gen, device)
+        self.flat = FlatParams(gen, device, bind)
         gen._drop_engines()
         self.eng = gen._engine(device)
         e = self.eng
-        self.g_pre = _GenLayerGrad(e.pre, device, need_dgrad=False)
+        self.g_pre = _GenLayerGrad(e.pre, device, need_dgrad=not bind)
         self.g_ups = [_GenLayerGrad(pc, device) for pc in e.ups]
         self.g_blocks = [[_GenLayerGrad(pc, device) for pc in blk] for blk in e.blocks]
         layers = [self.g_pre] + self.g_ups + [x for b in self.g_blocks for x in b]
@@ -408,7 +410,7 @@ class GeneratorTrainer:
         lanes.join()
         lanes.streams[self.W_LANE].wait_stream(main)
         with lanes.lane(self.W_LANE):            # the data-gradient filter banks are not needed before backward
-            for gl in self.g_ups + [x_ for blk in self.g_blocks for x_ in blk]:
+            for gl in [self.g_pre] + self.g_ups + [x_ for blk in self.g_blocks for x_ in blk]:
                 gl.pack(L)
         cur, t = ws["pre_act"], frames
         nk = gen.num_kernels
@@ -494,8 +496,9 @@ class GeneratorTrainer:
         d = [self.g_blocks[i * nk + j][-1].bias_dst(c) for j in range(nk)]
         return (d + [0, 0, 0])[:3]
 
-    def backward(self, dy: torch.Tensor) -> None:
-        """dy fp32 [B,T] (or [B,1,T]): gradient at the waveform of the LAST forward -> every parameter's .grad."""
+    def backward(self, dy: torch.Tensor, dx_mel: Optional[torch.Tensor] = None) -> None:
+        """dy fp32 [B,T] (or [B,1,T]): gradient at the waveform of the LAST forward -> every parameter's gradient
+        buffer.  dx_mel (optional, fp32 [B, cin_p, F], autograd path): receives the gradient at the input mel."""
         L = _lib.lib()
         e, gen, ws = self.eng, self.gen, self.cur
         lanes = self.lanes
@@ -560,6 +563,13 @@ class GeneratorTrainer:
                 self.g_pre.bias_grad(L, ws["g_pre"], b, frames, e.pre.cout_p)
                 self.g_pre.wgrad(L, ws["mel"], ws["g_pre"], b, frames)
                 self.g_pre.to_param_grads(L)
+                if dx_mel is not None:
+                    gm = ws.get("g_mel")
+                    if gm is None:
+                        gm = ws["g_mel"] = torch.empty_like(ws["mel"])
+                    self.g_pre.dgrad(L, ws["g_pre"], b, frames, gm)
+                    _lib.check(L.hg_nlc_to_ncl(gm.data_ptr(), b, frames, e.pre.cin_p, dx_mel.data_ptr(), _stream()),
+                               "hg_nlc_to_ncl")
         lanes.join()
 
 
@@ -703,8 +713,8 @@ class _SubDiscTrainer:
                                              layer.k, layer.stride, layer.pad, bufs["fwd"][li].data_ptr(), 0, st),
                        "hg_pack_disc_weight")
 
-    def _geometry(self, nb: int, t: int):
-        key = (nb, t)
+    def _geometry(self, nb: int, t: int, slot: int = 0):
+        key = (nb, t, slot)
         g = self.ws.get(key)
         if g is not None:
             return g
@@ -726,7 +736,7 @@ class _SubDiscTrainer:
              "grad": [torch.zeros(nseq, r, c, dtype=torch.bfloat16, device=dev) for _, r, c in geo],
              "logit": torch.empty(nseq, geo[-1][0], dtype=torch.float32, device=dev),
              "dlogit": torch.empty(nseq, geo[-1][0], dtype=torch.float32, device=dev)}
-        if len(self.ws) >= 4:
+        if len(self.ws) >= 8:
             self.ws.pop(next(iter(self.ws)))
         self.ws[key] = g
         return g
@@ -876,8 +886,8 @@ class _SubDiscTrainer:
         h = G["geo"][-1][0]
         lr, lg = G["logit"][:nr], G["logit"][nr:]
         # d/dlogit of mean((1 - lr)^2) + mean(lg^2)
-        _lib.check(L.hg_loss_grad(lr.data_ptr(), 0, nr * h, 1, 1.0, 2.0 / (nr * h), 0.0, G["dlogit"].data_ptr(), st))
-        _lib.check(L.hg_loss_grad(lg.data_ptr(), 0, (ntot - nr) * h, 1, 0.0, 2.0 / ((ntot - nr) * h), 0.0,
+        _lib.check(L.hg_loss_grad(lr.data_ptr(), 0, nr * h, 1, 1.0, 2.0 / (nr * h), 0.0, 0, G["dlogit"].data_ptr(), st))
+        _lib.check(L.hg_loss_grad(lg.data_ptr(), 0, (ntot - nr) * h, 1, 0.0, 2.0 / ((ntot - nr) * h), 0.0, 0,
                                   G["dlogit"][nr:].data_ptr(), st))
         here = torch.cuda.current_stream()
         here.wait_stream(self.lanes.streams[0])     # data-gradient packs (queued by forward on the w-lane)
@@ -893,11 +903,45 @@ class _SubDiscTrainer:
                                     part=pi)
         self.lanes.join()
 
+    def _bwd_bank(self, part: int):
+        """data-gradient filter banks of part / call slot `part` (created on first use)"""
+        while len(self.bwd_parts) <= part:
+            self.bwd_parts.append([_DiscBwdLayer(l, self.device) for l in self.mids])
+        return self.bwd_parts[part]
+
     def _pack_dgrad(self, W, part: int = 0) -> None:
         if self.spectral or not self.dgrad_valid:
-            for bl, w_eff in zip(self.bwd_parts[part], W["eff"][1:-1]):
+            for bl, w_eff in zip(self._bwd_bank(part), W["eff"][1:-1]):
                 bl.pack(w_eff)
             self.dgrad_valid = True
+
+    # ---- one module call under torch autograd (autograd.py): forward with its own activation / weight slot ---------
+    def forward_single(self, x2d: torch.Tensor, slot: int):
+        """x2d fp32 [B, T] -> (G, W) of call slot `slot`: activations, logits, the weights this call used (a train-mode
+        spectral-norm layer advances its power iteration per call, like the reference's hook) and their
+        data-gradient banks.  Everything on the current stream."""
+        L = _lib.lib()
+        nb, t = x2d.shape
+        G = self._geometry(nb, t, slot)
+        W = self._weights(slot)
+        for bl, w_eff in zip(self._bwd_bank(slot), W["eff"][1:-1]):
+            bl.pack(w_eff)
+        self._forward_part(L, G, W, x2d, 0, nb, t)
+        return G, W
+
+    def backward_single(self, G, W, slot: int, x2d: torch.Tensor, dlogit: torch.Tensor, pre_adds, want_wgrad: bool,
+                        dy_audio) -> None:
+        """Backward of forward_single's call: dlogit fp32 [B*period][h] (internal order), pre_adds[l] bf16 gradient at
+        feature map l in the internal layout (or None) -> parameter gradients ADDED into the _gb buffers (want_wgrad)
+        and / or the audio gradient ADDED into dy_audio fp32 [B][T]."""
+        L = _lib.lib()
+        nb, t = x2d.shape
+        self.G, self.nb, self.nreal, self.t, self.ycat = G, nb, nb, t, x2d
+        G["dlogit"].copy_(dlogit)
+        self.lanes.fork()
+        self._backward_part(L, G, W, 0, nb, want_wgrad=want_wgrad, fm=False, dy_audio=dy_audio, accumulate=True,
+                            part=slot, pre_adds=pre_adds)
+        self.lanes.join()
 
     def backward_g(self, dy_audio: torch.Tensor, nfm: List[float]) -> None:
         """generator step: d (loss_gen + loss_fm) / d y_g_hat accumulated into dy_audio fp32 [B][T] (generated half
@@ -909,7 +953,7 @@ class _SubDiscTrainer:
         h = G["geo"][-1][0]
         lr, lg = G["logit"][:nr], G["logit"][nr:]
         # d/dlg of mean((1 - lg)^2) + 2 * mean|lr - lg|
-        _lib.check(L.hg_loss_grad(lg.data_ptr(), lr.data_ptr(), ng * h, 2, 1.0, 2.0 / (ng * h), nfm[-1],
+        _lib.check(L.hg_loss_grad(lg.data_ptr(), lr.data_ptr(), ng * h, 2, 1.0, 2.0 / (ng * h), nfm[-1], 0,
                                   G["dlogit"][nr:].data_ptr(), st))
         b0, bn, W = self.parts[-1] if self.spectral else (self.nreal, self.nb - self.nreal, self.parts[0][2])
         part = len(self.parts) - 1
@@ -918,7 +962,7 @@ class _SubDiscTrainer:
                             dy_audio=dy_audio, accumulate=False, nfm=nfm, part=part)
 
     def _backward_part(self, L, G, W, b0: int, bn: int, want_wgrad: bool, fm: bool, dy_audio, accumulate: bool,
-                       nfm: Optional[List[float]] = None, part: int = 0) -> None:
+                       nfm: Optional[List[float]] = None, part: int = 0, pre_adds=None) -> None:
         """The data-gradient chain runs on the current stream; all parameter-gradient work (bias sums, wgrad,
         finish) goes to this sub-discriminator's w-lane, which also serialises the use of the shared scratch."""
         period = self.period
@@ -926,7 +970,8 @@ class _SubDiscTrainer:
         nr = self.nreal * period
         geo = G["geo"]
         nl = len(self.mids)
-        bwd = self.bwd_parts[part]
+        bwd = self._bwd_bank(part)
+        pre = pre_adds if pre_adds is not None else [None] * (nl + 1)   # incoming feature-map gradients (autograd path)
         h_last, rows_last, c_last = geo[-1]
         act_last = G["act"][-1]
         post = self.mods[-1]
@@ -945,7 +990,7 @@ class _SubDiscTrainer:
         bias_of = (lambda li: _gb(self.mods[li].bias).data_ptr()) if want_wgrad else (lambda li: 0)
         _lib.check(L.hg_disc_last_conv_bwd(act_last[seq0:].data_ptr(), W["wp"].data_ptr(), G["dlogit"][seq0:].data_ptr(),
                                            nseq, h_last, rows_last, c_last, self.kpost, LRELU_SLOPE, fm_r_last,
-                                           nfm[nl] if fm else 0.0, 0, G["grad"][-1][seq0:].data_ptr(), 0, 0,
+                                           nfm[nl] if fm else 0.0, _p(pre[nl]), G["grad"][-1][seq0:].data_ptr(), 0, 0,
                                            bias_of(nl), _stream()), "hg_disc_last_conv_bwd")
         if want_wgrad:
             def post_grads():
@@ -989,7 +1034,7 @@ class _SubDiscTrainer:
                 side(layer_grads)
             bwd[li].dgrad(L, d_out, nseq, h_out, rows_out, rows_in, a_in[seq0:],
                           a_in[seq0 - nr:] if fm else None, nfm[li] if fm else 0.0, G["grad"][li][seq0:], _stream(),
-                          flat_h_in=h_in, bias_dst=bias_of(li))
+                          flat_h_in=h_in, bias_dst=bias_of(li), pre_add=pre[li])
         # first conv (Cin = 1)
         k0, s0, p0, c0 = self.first
         m0 = self.mods[0]
@@ -1206,8 +1251,8 @@ class TrainStep:
             ms = _stream()
             _lib.check(L.hg_mel_fwd(plan.handle, y_g2.data_ptr(), b, y_g2.shape[1], mel_g.data_ptr(), 0, ms), "hg_mel_fwd")
             _lib.check(L.hg_loss_sum(ym.data_ptr(), mel_g.data_ptr(), n_mel, 0, 0.0, acc.data_ptr(), ms), "hg_loss_sum")
-            _lib.check(L.hg_loss_grad(mel_g.data_ptr(), ym.data_ptr(), n_mel, 0, 0.0, 45.0 / n_mel, 0.0, dmel.data_ptr(),
-                                      ms), "hg_loss_grad")
+            _lib.check(L.hg_loss_grad(mel_g.data_ptr(), ym.data_ptr(), n_mel, 0, 0.0, 45.0 / n_mel, 0.0, 0,
+                                      dmel.data_ptr(), ms), "hg_loss_grad")
             _lib.check(L.hg_mel_bwd(plan.handle, y_g2.data_ptr(), dmel.data_ptr(), b, y_g2.shape[1], dy.data_ptr(), ms),
                        "hg_mel_bwd")
         # ---- discriminator step, then the generator step's pass through the updated discriminators

@@ -143,6 +143,10 @@ int hg_disc_last_conv_fwd(const void* x, const float* w, const float* bias, int 
 int hg_avgpool_4_2_2_fwd(const float* x, int batch, int t, float* out, void* stream);
 int hg_disc_export_fmap(const void* x, int batch, int period, int h, int h_rows, int c, float* out,
                         void* stream);
+/* hg_disc_import_fmap — the inverse layout change: fp32 [B][c][H][period] -> bf16 [B*period][h_rows][c] (rows >= H
+ * untouched).  Carries a gradient that arrives at an exported feature map (torch autograd through feature_loss,
+ * src/models.py:251-257) into the data-gradient chain (hg_conv1d_dgrad's pre_add). */
+int hg_disc_import_fmap(const float* in, int batch, int period, int h, int h_rows, int c, void* x, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Layout edges.
@@ -337,9 +341,11 @@ int hg_disc_first_conv_bwd(const float* y, const float* w, const void* dpre, int
 int hg_avgpool_4_2_2_bwd(const float* dout, int batch, int t, float* din, void* stream);
 
 /* Loss gradients (src/models.py:251-282 and the mel L1): mode 0 out = coef * sgn(a - b); mode 1 out = coef * (a - c);
- * mode 2 out = coef * (a - c) + coef2 * sgn(a - b).  hg_l1_sum_bf16: *out_acc += sum |a - b| over bf16 arrays. */
-int hg_loss_grad(const float* a, const float* b, long long n, int mode, float c, float coef, float coef2, float* out,
-                 void* stream);
+ * mode 2 out = coef * (a - c) + coef2 * sgn(a - b).  scale_dev (optional): device scalar multiplied into coef and
+ * coef2 (the gradient arriving at the mean, under torch autograd).  hg_l1_sum_bf16: *out_acc += sum |a - b| over
+ * bf16 arrays. */
+int hg_loss_grad(const float* a, const float* b, long long n, int mode, float c, float coef, float coef2,
+                 const float* scale_dev, float* out, void* stream);
 int hg_l1_sum_bf16(const void* a, const void* b, long long n, float* out_acc, void* stream);
 
 /* hg_adamw_step — torch.optim.AdamW on one flat fp32 tensor (decoupled weight decay, bias correction by `step`,

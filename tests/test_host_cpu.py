@@ -111,18 +111,18 @@ def test_helpers():
     assert H.LRELU_SLOPE == 0.1 and H.MAX_WAV_VALUE == 32768.0
 
 
-def test_losses_match_oracle():
+def test_losses_have_no_cpu_path():
+    """The three loss functions run on hg_loss_sum / hg_loss_grad only: CPU tensors raise instead of silently falling
+    back to torch ops (their values are checked against the oracle on the GPU, tests/test_gpu_parity.py)."""
     g = torch.Generator().manual_seed(0)
-    fr = [[torch.randn(2, 4, 9, generator=g) for _ in range(3)] for _ in range(2)]
-    fg = [[torch.randn(2, 4, 9, generator=g) for _ in range(3)] for _ in range(2)]
-    assert torch.allclose(H.feature_loss(fr, fg), O.feature_loss(fr, fg))
-    dr = [torch.randn(2, 7, generator=g) for _ in range(3)]
-    dg = [torch.randn(2, 7, generator=g) for _ in range(3)]
-    a, b = H.discriminator_loss(dr, dg), O.discriminator_loss(dr, dg)
-    assert torch.allclose(a[0], b[0]) and np.allclose(a[1], b[1]) and np.allclose(a[2], b[2])
-    assert all(isinstance(v, float) for v in a[1] + a[2])
-    ga, gb = H.generator_loss(dg), O.generator_loss(dg)
-    assert torch.allclose(ga[0], gb[0]) and all(torch.is_tensor(t) for t in ga[1])
+    fr = [[torch.randn(2, 4, 9, generator=g)]]
+    dr = [torch.randn(2, 7, generator=g)]
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        H.feature_loss(fr, fr)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        H.discriminator_loss(dr, dr)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        H.generator_loss(dr)
 
 
 # ------------------------------------------------------------------------------------------- C-ABI surface
