@@ -146,66 +146,225 @@ def measured_traffic(workload: str, n_conv: int):
     return d["per_launch_avg_bytes"]
 
 
-def cpu_generator_baseline(version: str, frames: int, batch: int, steps: int, warmup: int):
-    """The oracle port (torch CPU fp32 = the very ops the reference's CPU path runs) on a bounded sample."""
+def _reference_modules():
+    """(models, meldataset, env) of the REFERENCE itself from oracle/_ref (built by oracle/build_ref.py in the build
+    container, shipped with the snapshot), or None -> the oracle port is timed instead (kind "port")."""
+    try:
+        from oracle import build_ref
+        if build_ref.available():
+            return build_ref.load()
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
+def cpu_generator_baseline(version: str, frames: int, batch: int, steps: int, warmup: int, best_of: bool = False):
+    """The reference's CPU implementation of the Generator forward on a bounded sample, all host threads: the
+    reference's own src/models.py (oracle/_ref, kind "reference") when it travelled with the snapshot, else the
+    oracle port (torch CPU fp32 = the very ops the reference's CPU path runs, kind "port").
+    best_of: BASELINE.md / SURVEY §8d cfg1 protocol — report the best of `steps` runs instead of the mean."""
     from oracle import hifigan_oracle as O   # the timed CPU implementation (allowed here: cpu_baseline leg)
-    import hifigan_b200 as H
     from hifigan_b200.configs import load_config
     h = load_config(version)
-    torch.manual_seed(1234)
-    G = H.Generator(H.AttrDict(h))  # parameter container only; never run on the CPU
-    G.remove_weight_norm()
-    sd = {k: v.detach() for k, v in G.state_dict().items()}
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    ref = _reference_modules()
+    torch.manual_seed(1234)
+    if ref is not None:
+        models, _, env = ref
+        G = models.Generator(env.AttrDict(dict(h))).eval()
+        G.remove_weight_norm()                                   # as inference.py:47-48
+        run, kind, what = (lambda x: G(x)), "reference", "the reference's own src/models.py Generator (oracle/_ref)"
+    else:
+        import hifigan_b200 as H
+        Gc = H.Generator(H.AttrDict(h))  # parameter container only; never run on the CPU
+        Gc.remove_weight_norm()
+        sd = {k: v.detach() for k, v in Gc.state_dict().items()}
+        run, kind, what = (lambda x: O.generator_forward(sd, h, x)), "port", "fp32 torch-CPU oracle port"
     torch.manual_seed(0)
     x = torch.randn(batch, 80, frames)
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            O.generator_forward(sd, h, x)
+            run(x)
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
     samples = batch * frames * 256
-    mean = sum(times) / len(times)
-    return {"value": samples / mean, "unit": "samples/s", "cores": cores, "kind": "port",
-            "sample": f"{version} Generator forward on {batch} x 80x{frames} mels per step "
-                      f"({samples} samples), fp32 torch-CPU oracle port, {len(times)} timed steps",
-            "ms_per_step": mean * 1e3, "xrt": samples / mean / SR}
-
+    t = min(times) if best_of else sum(times) / len(times)
+    return {"value": samples / t, "unit": "samples/s", "cores": cores, "kind": kind,
+            "sample": f"{version} Generator forward on {batch} x 80x{frames} mels per step ({samples} samples), fp32 on "
+                      f"the host CPU, {what}, {'best' if best_of else 'mean'} of {len(times)} timed steps after "
+                      f"{warmup} warm-up",
+            "ms_per_step": t * 1e3, "xrt": samples / t / SR}
 
 
 # --------------------------------------------------------------------------------------------- training step
+def _reference_train_step(ref, h, batch):
+    """UPSTREAM train.py's loop body over the REFERENCE's own modules and losses, torch autograd +
+    torch.optim.AdamW on the CPU — the composition tests/golden/make_golden_train.py pins."""
+    import itertools
+    from oracle import hifigan_oracle as O
+    models, meldataset, env = ref
+    hh = env.AttrDict(dict(h))
+    torch.manual_seed(1234)
+    G, mpd, msd = models.Generator(hh).train(), models.MultiPeriodDiscriminator().train(), models.MultiScaleDiscriminator().train()
+    optim_g = torch.optim.AdamW(G.parameters(), hh.learning_rate, betas=[hh.adam_b1, hh.adam_b2])
+    optim_d = torch.optim.AdamW(itertools.chain(msd.parameters(), mpd.parameters()), hh.learning_rate,
+                                betas=[hh.adam_b1, hh.adam_b2])
+    ya = O.synthetic_audio(batch, 8192, seed=3)
+    mel = lambda a, fmax: meldataset.mel_spectrogram(a, hh.n_fft, hh.num_mels, hh.sampling_rate, hh.hop_size,
+                                                     hh.win_size, hh.fmin, fmax)
+    with torch.no_grad():
+        x, y_mel = mel(ya, hh.fmax), mel(ya, hh.fmax_for_loss)
+    y = ya.unsqueeze(1)
+    Fn = torch.nn.functional
+
+    def step():
+        y_g_hat = G(x)
+        y_g_hat_mel = mel(y_g_hat.squeeze(1), hh.fmax_for_loss)
+        optim_d.zero_grad()
+        y_df_r, y_df_g, _, _ = mpd(y, y_g_hat.detach())
+        loss_disc_f, _, _ = models.discriminator_loss(y_df_r, y_df_g)
+        y_ds_r, y_ds_g, _, _ = msd(y, y_g_hat.detach())
+        loss_disc_s, _, _ = models.discriminator_loss(y_ds_r, y_ds_g)
+        (loss_disc_s + loss_disc_f).backward()
+        optim_d.step()
+        optim_g.zero_grad()
+        loss_mel = Fn.l1_loss(y_mel, y_g_hat_mel) * 45
+        _, y_df_g, fmap_f_r, fmap_f_g = mpd(y, y_g_hat)
+        _, y_ds_g, fmap_s_r, fmap_s_g = msd(y, y_g_hat)
+        loss = (models.generator_loss(y_ds_g)[0] + models.generator_loss(y_df_g)[0]
+                + models.feature_loss(fmap_s_r, fmap_s_g) + models.feature_loss(fmap_f_r, fmap_f_g) + loss_mel)
+        loss.backward()
+        optim_g.step()
+    return step
+
+
 def cpu_train_baseline(batch: int, steps: int, warmup: int):
-    """The training oracle (torch CPU fp32 autograd + torch AdamW over the restated forward = the ops the
-    reference's CPU path runs) on a bounded sample of the training workload."""
+    """The reference's CPU implementation of the training step on a bounded sample of the training workload: the
+    reference's own modules under torch autograd + torch.optim.AdamW (oracle/_ref, kind "reference") when they
+    travelled with the snapshot, else the training oracle (kind "port")."""
     from oracle import hifigan_oracle as O          # allowed here: cpu_baseline / --impl reference legs
     from oracle import train_oracle as TO
-    import hifigan_b200 as H
     from hifigan_b200.configs import load_config
     h = load_config("v1")
-    torch.manual_seed(1234)
-    G, mpd, msd = H.Generator(h), H.MultiPeriodDiscriminator(), H.MultiScaleDiscriminator()  # parameter containers
-    sds = [TO.leaf_params({k: v.detach().clone() for k, v in m.state_dict().items()}) for m in (G, mpd, msd)]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    ya = O.synthetic_audio(batch, 8192, seed=3)
-    x = O.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, 8000)
-    y_mel = O.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, None)
-    optims = TO.make_optimizers(*sds, h)
+    ref = _reference_modules()
+    if ref is not None:
+        step, kind, what = _reference_train_step(ref, h, batch), "reference", "the reference's own modules (oracle/_ref)"
+    else:
+        import hifigan_b200 as H
+        torch.manual_seed(1234)
+        G, mpd, msd = H.Generator(h), H.MultiPeriodDiscriminator(), H.MultiScaleDiscriminator()  # parameter containers
+        sds = [TO.leaf_params({k: v.detach().clone() for k, v in m.state_dict().items()}) for m in (G, mpd, msd)]
+        ya = O.synthetic_audio(batch, 8192, seed=3)
+        x = O.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, 8000)
+        y_mel = O.mel_spectrogram(ya, 1024, 80, 22050, 256, 1024, 0, None)
+        optims = TO.make_optimizers(*sds, h)
+        step = lambda: TO.train_step(*sds, h, x, ya.unsqueeze(1), y_mel, optims=optims)
+        kind, what = "port", "fp32 torch-CPU training oracle"
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        TO.train_step(*sds, h, x, ya.unsqueeze(1), y_mel, optims=optims)
+        step()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     mean = sum(times) / len(times)
-    return {"value": batch / mean, "unit": "segments/s", "cores": cores, "kind": "port",
-            "sample": f"V1 full training step on {batch} x 8192-sample segments per step, fp32 torch-CPU oracle "
-                      f"(autograd + AdamW), {len(times)} timed steps", "ms_per_step": mean * 1e3}
+    return {"value": batch / mean, "unit": "segments/s", "cores": cores, "kind": kind,
+            "sample": f"V1 full training step on {batch} x 8192-sample segments per step, fp32 on the host CPU, {what}, "
+                      f"torch autograd + torch.optim.AdamW, {len(times)} timed steps", "ms_per_step": mean * 1e3}
+
+
+KERNEL_CLASSES = (
+    # (class, substrings of the kernel name): tensor-core implicit GEMMs first, then the bandwidth-bound helpers
+    ("conv fwd + dgrad (tcgen05)", ("conv1d_tc_kernel", "conv1d_tc2_kernel", "resblock_pair_kernel")),
+    ("wgrad (tcgen05)", ("wgrad_tc_kernel",)),
+    ("weight prep (fold / pack / spectral norm)", ("pack_", "fold_weight", "sn_")),
+    ("wgrad finish / weight-norm bwd", ("wgrad_finish", "weight_norm_bwd", "unpack_wgrad")),
+    ("cin=1 / cout=1 ends, pooling", ("disc_first", "disc_last", "conv_post", "avgpool", "ncl_to_nlc")),
+    ("losses + mel", ("loss_", "l1_sum", "mel_")),
+    ("AdamW", ("adamw",)),
+    ("bias column sums", ("colsum",)),
+    ("NCCL", ("nccl",)),
+)
+
+
+def train_kernel_classes(fn, args3, flop_tensor: float):
+    """Per-kernel-class time of ONE training step from a CUPTI kernel trace (torch.profiler) of two graph replays
+    taken AFTER the timed region: never a bench value, it only apportions the step.  Serialised kernel time exceeds
+    the step time because the step's stream lanes overlap."""
+    from torch.profiler import ProfilerActivity, profile as tprofile
+    with tprofile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(2):
+            fn(*args3)
+        torch.cuda.synchronize()
+    agg, other = {c: [0, 0.0] for c, _ in KERNEL_CLASSES}, [0, 0.0]
+    for e in prof.events():
+        if e.device_type != torch.autograd.DeviceType.CUDA:
+            continue
+        name = e.name.lower()
+        if name.startswith("memcpy") or name.startswith("memset"):
+            cls = None
+        else:
+            cls = next((c for c, keys in KERNEL_CLASSES if any(k in name for k in keys)), None)
+        slot = agg[cls] if cls is not None else other
+        slot[0] += 1
+        slot[1] += e.time_range.elapsed_us()
+    total = sum(v[1] for v in agg.values()) + other[1]
+    if total <= 0:
+        return None
+    out = {c: {"launches_per_step": v[0] / 2, "ms_per_step": v[1] / 2e3, "share": v[1] / total}
+           for c, v in agg.items() if v[0]}
+    out["other (ATen fill / add / copy, memset)"] = {"launches_per_step": other[0] / 2, "ms_per_step": other[1] / 2e3,
+                                                      "share": other[1] / total}
+    tc_ms = sum(out[c]["ms_per_step"] for c in ("conv fwd + dgrad (tcgen05)", "wgrad (tcgen05)") if c in out)
+    peaks = measured_peaks()
+    return {"source": "CUPTI trace of 2 graph replays after the timed region (serialised kernel time; lanes overlap)",
+            "serialised_ms_per_step": total / 2e3, "classes": out,
+            "tensor_core_kernels": {"ms_per_step": tc_ms, "achieved_tflops": flop_tensor / (tc_ms * 1e-3) / 1e12 if tc_ms else None,
+                                    "frac_of_peak": (flop_tensor / (tc_ms * 1e-3) / 1e12 / peaks["tflops"]) if tc_ms else None},
+            "helper_share": 1.0 - tc_ms / (total / 2e3)}
+
+
+def measure_mel(dev, steps: int):
+    """mel_spectrogram at the 65 536-frame point of BASELINE configs[4]'s sweep (64 x 262 144 samples, n_fft 1024,
+    hop 256, 80 mels): kernel launches through the C-ABI, CUDA events on the launching stream.  Four input / output
+    sets (268 MB + 84 MB) rotate so no iteration finds its input in the 126 MB L2."""
+    import hifigan_b200 as H
+    from hifigan_b200 import _lib
+    b, t = 64, 262144
+    g = torch.Generator().manual_seed(7)
+    ys = [(torch.rand(b, t, generator=g) * 1.9 - 0.95).to(dev) for _ in range(4)]
+    H.mel_spectrogram(ys[0], 1024, 80, SR, 256, 1024, 0, 8000)           # creates / caches the plan
+    plan = H.meldataset.torch_mels[f"{ys[0].device}_1024_80_{SR}_256_1024_0_8000_False"]
+    frames = plan.frames(t)
+    outs = [torch.empty(b, 80, frames, dtype=torch.float32, device=dev) for _ in range(4)]
+    L, st = _lib.lib(), torch.cuda.current_stream().cuda_stream
+    run = lambda i: _lib.check(L.hg_mel_fwd(plan.handle, ys[i % 4].data_ptr(), b, t, outs[i % 4].data_ptr(), 0, st))
+    for i in range(4):
+        run(i)
+    torch.cuda.synchronize()
+    n = max(8, 4 * steps)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        run(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    peaks = measured_peaks()
+    nframes = b * frames
+    gbs = nframes * 1344 / (ms * 1e-3) / 1e9                               # SURVEY §8d: 1 344 algorithmic B / frame
+    return {"metric": "mel_spectrogram frames/s", "value": nframes / (ms * 1e-3), "unit": "frames/s", "ms_per_call": ms,
+            "frames_per_call": nframes, "launches": n,
+            "config": {"workload": "mel_spectrogram, 64 x 262144 samples (65 536 frames), n_fft 1024, hop 256, 80 mels, "
+                                   "fmax 8000", "l2": "4 rotating input/output sets (352 MB) > 126 MB L2"},
+            "roofline": {"bound": "hbm", "kernel": "mel_kernel", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": gbs / peaks["hbm_gbs"], "algorithmic_bytes_per_frame": 1344, "traffic": None}}
 
 
 def measure_train(dev, rank, world, steps: int, warmup: int, batch: int = TRAIN["batch"]):
@@ -265,7 +424,15 @@ def measure_train(dev, rank, world, steps: int, warmup: int, batch: int = TRAIN[
     # a graph replay launches the captured kernels without passing through the C-ABI counter: report the number
     # of library kernels recorded when the step was captured
     per_step = ts.launches_per_step if graphed else launches / steps
-    return {"ms": max_over_ranks(ms), "e2e_ms": max_over_ranks(e2e_ms), "batch": batch,
+    classes = None
+    if rank == 0 and not os.environ.get("HG_BENCH_NO_TRACE"):
+        try:
+            # 3 F_G + 9 F_D MACs per segment run on the tensor-core kernels except the Cin = 1 / Cout = 1 ends (< 1 %)
+            classes = train_kernel_classes(fn, (x, y3, y_mel), batch * TRAIN_FLOP_PER_SEGMENT)
+        except Exception as e:  # noqa: BLE001   (a profiler problem must not cost the measured numbers)
+            classes = {"error": f"{type(e).__name__}: {e}"[:200]}
+    barrier()
+    return {"ms": max_over_ranks(ms), "e2e_ms": max_over_ranks(e2e_ms), "batch": batch, "kernel_classes": classes,
             "segments": sum_over_ranks(float(batch)), "launches_per_step": per_step, "graphed": graphed,
             "h2d": (host_x.numel() + host_y.numel() + host_ymel.numel()) * 4, "d2h": 8,
             "losses": [float(v) for v in host_loss.tolist()]}
@@ -286,7 +453,8 @@ def train_summary(r, world):
                          "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["tflops"], "traffic": None,
                          "algorithmic_flop_per_segment": TRAIN_FLOP_PER_SEGMENT, "peak_source": peaks["source"]},
-            "losses_last_step": {"loss_gen_all": r["losses"][0], "loss_disc_all": r["losses"][1]}}
+            "losses_last_step": {"loss_gen_all": r["losses"][0], "loss_disc_all": r["losses"][1]},
+            "kernel_classes": r.get("kernel_classes")}
 
 
 def run_train(args, rank, world, local_rank):
@@ -311,7 +479,7 @@ def run_train(args, rank, world, local_rank):
                        "cuda_graph": t["cuda_graph"], "parallelism": t["parallelism"]},
             "clocks": clocks, "e2e": t["e2e"],
             "gpu_launches": int(t["kernel_launches_per_step"] * args.steps), "roofline": t["roofline"],
-            "losses_last_step": t["losses_last_step"]}
+            "losses_last_step": t["losses_last_step"], "kernel_classes": t["kernel_classes"]}
     if world == 1 and not args.no_cpu_baseline:
         cb = cpu_train_baseline(2, 2, 1)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -319,8 +487,9 @@ def run_train(args, rank, world, local_rank):
 
 # ------------------------------------------------------------------------------------------------- arms
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference itself is
-    Python over torch and cannot travel to the GPU box) on the box's host cores.  Rank 0 only."""
+    """--impl reference: the reference's CPU implementation of the path on the box's host cores — the reference's own
+    modules from oracle/_ref (kind "reference") when that directory travelled with the snapshot, else the oracle
+    port (kind "port").  Rank 0 only."""
     if rank != 0:
         return
     if args.workload == "train":
@@ -335,9 +504,9 @@ def run_reference(args, rank, world):
         print(json.dumps(line), flush=True)
         return
     wl = WORKLOADS[args.workload]
-    batch = 2 if wl["batch"] > 2 else wl["batch"]
-    frames = min(wl["frames"], 512)
-    r = cpu_generator_baseline(wl["version"], frames, batch, max(1, args.steps), max(0, min(args.warmup, 1)))
+    # a bounded sample of the arm's workload: ONE utterance of the batch at its full length (the batch only repeats
+    # the per-utterance work; ~1 s of 16-core CPU time per step for V1 x 1024 frames)
+    r = cpu_generator_baseline(wl["version"], wl["frames"], 1, max(1, args.steps), max(0, min(args.warmup, 2)))
     line = {"impl": "reference", "metric": "V1 audio samples/sec" if wl["version"] == "v1" else "V3 audio samples/sec",
             "value": r["value"], "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -414,6 +583,13 @@ def run_ours(args, rank, world, local_rank):
     ms = max_over_ranks(ms)
     e2e_ms = max_over_ranks(e2e_ms)
     total_samples = sum_over_ranks(float(samples))
+    mel = None
+    if args.workload == "cfg2" and rank == 0 and not profile_mode:
+        # the third kernel family north_star names: the fused mel front-end, against the HBM roofline
+        try:
+            mel = measure_mel(dev, args.steps)
+        except Exception as e:  # noqa: BLE001
+            mel = {"error": f"{type(e).__name__}: {e}"[:200]}
     train = None
     if args.workload == "cfg2" and not profile_mode and not args.no_train:
         # second half of BASELINE.json's metric: a short run of the full training step on the same GPUs
@@ -455,11 +631,16 @@ def run_ours(args, rank, world, local_rank):
     }
     if train is not None:
         line["train"] = train
+    if mel is not None:
+        line["mel"] = mel
     if profile_mode:
         line["invalid"] = "HG_BENCH_PROFILE run (short warm-up, no e2e): not a bench value"
     if world == 1 and not args.no_cpu_baseline and not profile_mode:
-        cb = cpu_generator_baseline(ver, min(frames, 512), min(batch, 2), 2, 1)
+        # BASELINE.json configs[0] exactly: batch 1 x 80x256 mel, fp32 on the CPU, all host threads,
+        # best of 5 after 1 warm-up
+        cb = cpu_generator_baseline(ver, 256, 1, 5, 1, best_of=True)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline"]["xrt_22050"] = cb["xrt"]
     print(json.dumps(line), flush=True)
 
 
