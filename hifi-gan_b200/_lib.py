@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libhifigan_b200.so")
 SOURCES = ["hg_api.cu", "hg_conv1d_tc.cu", "hg_resblock_pair.cu", "hg_disc.cu", "hg_prep.cu", "hg_mel.cu",
-           "hg_wgrad.cu", "hg_train.cu"]
+           "hg_wgrad.cu", "hg_train.cu", "hg_batched.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -122,6 +122,8 @@ _SIGNATURES = {
     "hg_avgpool_4_2_2_fwd": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "hg_disc_export_fmap": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hg_disc_import_fmap": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "hg_prep_job_size": (c_int, []),
+    "hg_prep_batched": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "hg_resblock_pair_supported": (c_int, [c_int, c_int, c_int]),
     "hg_resblock_single_supported": (c_int, [c_int, c_int, c_int]),
     "hg_resblock_pair_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,

@@ -99,6 +99,32 @@ class _PackedConv:
         b = self.module.bias
         return tuple((t.data_ptr(), t._version) for t in (g, v, b) if t is not None)
 
+    def tensors(self):
+        g, v = _g_v(self.module)
+        return [t for t in (g, v, self.module.bias) if t is not None]
+
+    def batchable(self) -> bool:
+        """parameters the batched pack kernel can read in place: contiguous fp32 on the pack's device"""
+        return all(t.device == self.w.device and t.dtype == torch.float32 and t.is_contiguous() for t in self.tensors())
+
+    def add_pack_job(self, table, phase: str) -> None:
+        """this layer's fold + pack as one job of a batched launch (batched.py / hg_prep_batched)"""
+        from . import batched
+        m = self.module
+        g, v = _g_v(m)
+        if self.bias.data_ptr() in [t.data_ptr() for t in self.tensors()]:     # refresh() may have aliased the parameter
+            self.bias = torch.zeros(self.w.shape[1], dtype=torch.float32, device=self.w.device)
+        if self.kind == "conv":
+            table.add(phase, batched.GEN_CONV, self.cout_p, 0, v, g, m.bias, self.w, self.bias,
+                      ints=(self.cout, self.cin, self.taps, self.cout_p, self.cin_p))
+        else:
+            nshift, smin = c_int(), c_int()
+            _lib.check(_lib.lib().hg_convtr1d_geometry(m.kernel_size[0], self.stride, m.padding[0], byref(nshift),
+                                                       byref(smin)))
+            table.add(phase, batched.GEN_CONVTR, self.cin_p, 0, v, g, m.bias, self.w, self.bias,
+                      ints=(self.cin, self.cout, m.kernel_size[0], self.cin_p, self.cout_p, self.stride, m.padding[0],
+                            nshift.value, smin.value))
+
     def refresh(self) -> None:
         """(Re)pack when a parameter changed: weight_norm fold + bf16 GEMM layout (hg_pack_*)."""
         key = self._fingerprint()
@@ -323,11 +349,52 @@ class _GeneratorEngine:
         self.post_w = torch.zeros(self.post_cin_p, post.kernel_size[0], dtype=torch.float32, device=device)
         self.post_b = torch.zeros(1, dtype=torch.float32, device=device)
         self.post_key = None
+        self.table, self.table_ptrs, self.ver_key = None, None, None
         self.ws: Dict[Tuple[int, int], Dict[str, torch.Tensor]] = {}
         self.graphs: Dict[tuple, tuple] = {}
         self.graph_seen = set()
 
+    def packs(self) -> List[_PackedConv]:
+        return [self.pre] + self.ups + [pc for blk in self.blocks for pc in blk]
+
+    def _post_tensors(self):
+        post = self.gen.conv_post
+        g, v = _g_v(post)
+        return [t for t in (g, v, post.bias) if t is not None]
+
     def refresh(self) -> None:
+        """(Re)derive every filter bank from the parameters when any of them changed: weight_norm fold + bf16 GEMM
+        layout for all layers in ONE launch (hg_prep_batched over a device-resident job table)."""
+        packs = self.packs()
+        tensors = [t for pc in packs for t in pc.tensors()] + self._post_tensors()
+        if not all(pc.batchable() for pc in packs) or not all(
+                t.device == self.device and t.dtype == torch.float32 and t.is_contiguous() for t in self._post_tensors()):
+            return self._refresh_per_layer()            # parameters living elsewhere (a CPU module): staged per layer
+        ptr_key = tuple(t.data_ptr() for t in tensors)
+        ver_key = tuple(t._version for t in tensors)
+        if self.table is None or ptr_key != self.table_ptrs:
+            from . import batched
+            table = batched.JobTable(self.device)
+            for pc in packs:
+                pc.add_pack_job(table, "pack")
+            post = self.gen.conv_post
+            g, v = _g_v(post)
+            table.add("pack", batched.GEN_POST, 1, 0, v, g, post.bias, self.post_w, self.post_b,
+                      ints=(post.in_channels, post.kernel_size[0], self.post_cin_p))
+            self.table, self.table_ptrs, self.ver_key = table.finalize(), ptr_key, None
+        # (data_ptr, _version) cannot see writes through raw pointers (the AdamW kernel: invalidate() clears the key),
+        # and a captured graph must hold the re-pack launch whatever the host cache says
+        if ver_key != self.ver_key or torch.cuda.is_current_stream_capturing():
+            self.table.launch("pack")
+            self.ver_key = ver_key
+
+    def invalidate(self) -> None:
+        self.ver_key = None
+        self.post_key = None
+        for pc in self.packs():
+            pc.key = None
+
+    def _refresh_per_layer(self) -> None:
         self.pre.refresh()
         for pc in self.ups:
             pc.refresh()
@@ -338,7 +405,7 @@ class _GeneratorEngine:
         g, v = _g_v(post)
         key = tuple((t.data_ptr(), t._version) for t in (g, v, post.bias) if t is not None)
         if key != self.post_key or torch.cuda.is_current_stream_capturing():
-            # single output channel: fold on the device with torch (4 x 224 floats, not a hot path)
+            # single output channel, parameters not on this device: fold with torch on the way over
             v32 = v.detach().to(self.device, torch.float32)
             w = v32 if g is None else v32 * (g.detach().to(self.device, torch.float32)
                                              / v32.pow(2).sum(dim=(1, 2), keepdim=True).sqrt())

@@ -225,6 +225,31 @@ class _GenLayerGrad:
             _lib.check(L.hg_pack_dgrad_weight(pc.w.data_ptr(), pc.taps, self.rows, pc.cin_p, self.wd.data_ptr(),
                                               _stream()), "hg_pack_dgrad_weight")
 
+    def add_jobs(self, table) -> None:
+        """this layer's share of the trainer's batched launches: phase "dgrad" = the data-gradient filter bank (tap
+        flip + transpose of the forward bank), phase "finish" = packed dW -> parameter gradients (unpack +
+        weight_norm backward, accumulating)"""
+        from . import batched
+        pc = self.pc
+        if self.wd is not None:
+            tc, tn = (pc.cin_p + 31) // 32, (self.rows + 31) // 32
+            table.add("dgrad", batched.TRANSPOSE_TILE, pc.taps * tc * tn, 32 * 34 * 2, pc.w, dst0=self.wd,
+                      ints=(pc.taps, self.rows, pc.cin_p, tc, tn))
+        m = pc.module
+        g, v = _g_v(m)
+        dg = None if g is None else _gb(g)
+        if pc.kind == "conv":
+            table.add("finish", batched.FINISH_ROW, pc.cout, pc.cin * pc.taps * 4, self.dwp, g, v, _gb(v), dg,
+                      ints=(0, pc.cout, pc.cin, pc.taps, self.rows, pc.cin_p, pc.cout, 1, 0, 0, 0, 0, 1),
+                      tab=range(pc.taps))
+        else:
+            k = m.kernel_size[0]
+            nshift, smin = c_int(), c_int()
+            _lib.check(_lib.lib().hg_convtr1d_geometry(k, pc.stride, m.padding[0], byref(nshift), byref(smin)))
+            table.add("finish", batched.FINISH_ROW, pc.cin, pc.cout * k * 4, self.dwp, g, v, _gb(v), dg,
+                      ints=(1, pc.cin, pc.cout, k, pc.stride * pc.cout_p, pc.cin_p, 0, 1, pc.stride, m.padding[0],
+                            smin.value, pc.cout_p, 1))
+
     def wgrad(self, L, x, dy, batch: int, t: int) -> None:
         """x bf16 [B][t][cin_p] (the forward input), dy bf16 [B][t][rows] -> dwp (+=)"""
         pc = self.pc
@@ -311,6 +336,12 @@ class GeneratorTrainer:
         for gl in layers:
             gl.dwp = self.dwp_flat[off:off + gl.dwp_numel]
             off += gl.dwp_numel
+        # the data-gradient banks of every layer / the finish of every packed weight gradient: one launch each
+        from . import batched
+        self.table = batched.JobTable(device)
+        for gl in layers:
+            gl.add_jobs(self.table)
+        self.table.finalize()
         # stream lanes: 0 .. nk-2 = MRF branches beside the main stream, W_LANE + j = weight-gradient work of branch j
         nk = gen.num_kernels
         self.W_LANE = max(1, nk - 1)
@@ -327,9 +358,7 @@ class GeneratorTrainer:
         """parameters were updated in place through raw pointers (AdamW kernel): force a re-pack"""
         engines = [self.eng] + [e for e in self.gen.__dict__.get("_hg_engines", {}).values() if e is not self.eng]
         for e in engines:      # the module API (`generator(x)` in eval / validation) may hold engines of its own
-            for pc in [e.pre] + e.ups + [x for b in e.blocks for x in b]:
-                pc.key = None
-            e.post_key = None
+            e.invalidate()
 
     def _workspace(self, b: int, frames: int) -> dict:
         ws = self.ws.get((b, frames))
@@ -398,20 +427,15 @@ class GeneratorTrainer:
         self.cur = ws
         main = torch.cuda.current_stream()
         lanes.fork()
-        # after an optimizer update every filter bank is re-folded and re-packed (~80 small launches): spread them over
-        # the lanes while the main stream packs conv_pre / conv_post and runs the first conv
-        for idx, pc in enumerate(e.ups + [x_ for blk in e.blocks for x_ in blk]):
-            with lanes.lane(idx):
-                pc.refresh()
-        e.refresh()                              # what is left: conv_pre, conv_post
+        # after an optimizer update every filter bank is re-folded and re-packed: ONE launch over the engine's job table
+        e.refresh()
         _lib.check(L.hg_ncl_to_nlc(xin.data_ptr(), b, c, frames, e.pre.cin_p, ws["mel"].data_ptr(), 0, 0.0, _stream()),
                    "hg_ncl_to_nlc")
         _conv(L, ws["mel"], e.pre, b, frames, out_act=ws["pre_act"])
         lanes.join()
         lanes.streams[self.W_LANE].wait_stream(main)
         with lanes.lane(self.W_LANE):            # the data-gradient filter banks are not needed before backward
-            for gl in [self.g_pre] + self.g_ups + [x_ for blk in self.g_blocks for x_ in blk]:
-                gl.pack(L)
+            self.table.launch("dgrad")
         cur, t = ws["pre_act"], frames
         nk = gen.num_kernels
         for i, up in enumerate(e.ups):
@@ -468,14 +492,12 @@ class GeneratorTrainer:
                 def w2(c2=c2, t1=t1, g=g):
                     c2.bias_grad(L, g, b, t, c)
                     c2.wgrad(L, t1, g, b, t)
-                    c2.to_param_grads(L)
                 self._side(L, wl, here, w2)
                 c2.dgrad(L, g, b, t, gt1, mask=t1, bias_dsts=(c1.bias_dst(c),))
 
                 def w1(c1=c1, xa=xa, gt1=gt1):
                     c1.bias_grad(L, gt1, b, t, c)
                     c1.wgrad(L, xa, gt1, b, t)
-                    c1.to_param_grads(L)
                 self._side(L, wl, here, w1)
                 c1.dgrad(L, gt1, b, t, out, mask=xa, res0=g, res1=r1, res2=r2, bias_dsts=out_bias)
             else:
@@ -484,7 +506,6 @@ class GeneratorTrainer:
                 def w0(cc=cc, xa=xa, g=g):
                     cc.bias_grad(L, g, b, t, c)
                     cc.wgrad(L, xa, g, b, t)
-                    cc.to_param_grads(L)
                 self._side(L, wl, here, w0)
                 cc.dgrad(L, g, b, t, out, mask=xa, res0=g, res1=r1, res2=r2, bias_dsts=out_bias)
             g = out
@@ -553,7 +574,6 @@ class GeneratorTrainer:
             def up_grads(up=up, dx_raw=dx_raw, up_in=up_in, t=t, c=c, t_in=t_in):
                 up.bias_grad(L, dx_raw, b, t, c)               # dx_raw as [B][t][c]: phases fold into the rows
                 up.wgrad(L, up_in, dx_raw, b, t_in)            # dy viewed as [B][t_in][stride * c]
-                up.to_param_grads(L)
             self._side(L, self.W_LANE, main, up_grads)
             if i > 0:
                 up.dgrad(L, dx_raw, b, t_in, stages[i - 1]["g0"], mask=up_in, scale=1.0 / nk,
@@ -562,7 +582,6 @@ class GeneratorTrainer:
                 up.dgrad(L, dx_raw, b, t_in, ws["g_pre"], mask=up_in, bias_dsts=(self.g_pre.bias_dst(e.pre.cout_p),))
                 self.g_pre.bias_grad(L, ws["g_pre"], b, frames, e.pre.cout_p)
                 self.g_pre.wgrad(L, ws["mel"], ws["g_pre"], b, frames)
-                self.g_pre.to_param_grads(L)
                 if dx_mel is not None:
                     gm = ws.get("g_mel")
                     if gm is None:
@@ -571,6 +590,8 @@ class GeneratorTrainer:
                     _lib.check(L.hg_nlc_to_ncl(gm.data_ptr(), b, frames, e.pre.cin_p, dx_mel.data_ptr(), _stream()),
                                "hg_nlc_to_ncl")
         lanes.join()
+        # every packed weight gradient is complete: unpack + weight_norm backward of ALL layers in one launch
+        self.table.launch("finish")
 
 
 # ------------------------------------------------------------------------------------------------ discriminators
@@ -641,8 +662,15 @@ class _SubDiscTrainer:
         self.lanes = _Lanes(2, device, [0, -1])      # 0: parameter-gradient lane, 1: second data-gradient chain
         self.prep = _Lanes(4, device, [-1] * 4)      # weight preparation: independent layers side by side
         self.ws = {}
-        nmax = max(l.k * l.cout * l.cin_tile for l in self.mids)
-        self.dwp = torch.zeros(nmax, dtype=torch.float32, device=device)
+        # packed fp32 weight gradients, one region per wide layer (zeroed once per backward; the wgrad launches and
+        # the batched finish accumulate)
+        sizes = [l.k * l.cout * l.cin_tile for l in self.mids]
+        self.dwp_flat = torch.zeros(sum(sizes), dtype=torch.float32, device=device)
+        self.dwps, off = [], 0
+        for n in sizes:
+            self.dwps.append(self.dwp_flat[off:off + n])
+            off += n
+        self._tables = {}
         self.scratch = torch.empty(max(m.weight_v.numel() if hasattr(m, "weight_v") and not self.spectral
                                        else m.weight_orig.numel() if self.spectral else m.weight.numel()
                                        for m in self.mods), dtype=torch.float32, device=device)
@@ -682,7 +710,70 @@ class _SubDiscTrainer:
             self._weights_layer(ws, bufs, li)
         return ws
 
-    def _weights_layer(self, ws, bufs, li: int) -> None:
+    def _table(self, part: int):
+        """Job table of part / call slot `part` (batched.py): phase "fwd" = weight_norm fold -> effective fp32 weight +
+        forward bank of every layer (spectral-norm layers: forward bank from the effective weight their power
+        iteration produced), "dgrad" = the polyphase data-gradient banks, "finish" = packed dW -> (weight_g.grad,
+        weight_v.grad) of every wide weight_norm layer.  One launch each instead of one per layer."""
+        t = self._tables.get(part)
+        if t is not None:
+            return t
+        from . import batched
+        L = _lib.lib()
+        bufs = self.wbufs[part]
+        t = batched.JobTable(self.device)
+        nl = len(self.mids)
+        self.untiled = []                         # layers whose data-gradient bank does not tile: packed per layer
+        for li, m in enumerate(self.mods):
+            layer = self.mids[li - 1] if 1 <= li <= nl else None
+            sn = hasattr(m, "weight_orig")
+            if sn and layer is None:
+                continue                          # first / last conv of the spectral-norm scale: eff is all they need
+            g, v = (None, bufs["eff"][li]) if sn else _g_v(m)
+            cout = v.shape[0]
+            cin_g, k = (layer.cin // layer.groups, layer.k) if layer is not None else (v.shape[1], v.numel() // (v.shape[0] * v.shape[1]))
+            ints = (cout, cin_g, k, layer.merge if layer else 1, (layer.cout // layer.groups) if layer else cout,
+                    layer.cin_tile if layer else cin_g)
+            t.add("fwd", batched.DISC_ROW, cout, cin_g * k * 4 if layer is not None else 0, v, g,
+                  dst0=None if sn else bufs["eff"][li], dst1=bufs["fwd"][li] if layer is not None else None,
+                  ints=ints, tab=layer.order if layer is not None else ())
+            if layer is None:
+                continue
+            bl = self._bwd_bank(part)[li - 1]
+            cout_tile = (layer.cout // layer.groups) * layer.merge
+            tci = 32 if layer.k <= 10 else 8
+            while tci > 2 and (cin_g % tci or layer.cin % tci):
+                tci >>= 1
+            smem = 32 * (tci * layer.k + 1) * 4
+            if cin_g % tci == 0 and layer.cin % tci == 0 and cout_tile % 32 == 0 and smem <= 48 * 1024:
+                t.add("dgrad", batched.DISC_DGRAD_TILE, (layer.cin // tci) * (cout_tile // 32), smem, bufs["eff"][li],
+                      dst0=bl.w, ints=(layer.cout, cin_g, layer.k, layer.merge, layer.cout // layer.groups, layer.cin,
+                                       layer.stride, layer.pad, bl.nshift, bl.smin, cout_tile, tci, layer.cin // tci))
+            else:
+                self.untiled.append(li - 1)
+            if not sn:
+                pos = [0] * layer.k
+                for q, j in enumerate(layer.order):
+                    pos[j] = q
+                t.add("finish", batched.FINISH_ROW, layer.cout, cin_g * layer.k * 4, self.dwps[li - 1], g, v, _gb(v),
+                      _gb(g), ints=(0, layer.cout, cin_g, layer.k, layer.cout, layer.cin_tile,
+                                    layer.cout // layer.groups, layer.merge, 0, 0, 0, 0, 1), tab=pos)
+        self._tables[part] = t.finalize()
+        return t
+
+    def _prepare_weights(self, part: int) -> dict:
+        """effective weights + forward banks of part `part` on the current stream: spectral-norm layers run their
+        power iteration (one per call in train mode, like the reference's hook), then ONE batched launch folds /
+        packs every layer"""
+        W = self._weights(part, only_buffers=True)
+        bufs = self.wbufs[part]
+        if self.spectral:
+            for li in range(len(self.mods)):
+                self._weights_layer(W, bufs, li, pack=False)
+        self._table(part).launch("fwd")
+        return W
+
+    def _weights_layer(self, ws, bufs, li: int, pack: bool = True) -> None:
         """fold (weight norm) or power-iterate (spectral norm) layer li and pack its forward filter bank"""
         L = _lib.lib()
         st = _stream()
@@ -707,7 +798,7 @@ class _SubDiscTrainer:
             g, v = _g_v(m)
             _lib.check(L.hg_fold_weight_norm(v.data_ptr(), 0 if g is None else g.data_ptr(), v.shape[0],
                                              v.numel() // v.shape[0], eff.data_ptr(), st), "hg_fold_weight_norm")
-        if 1 <= li <= len(self.mids):
+        if pack and 1 <= li <= len(self.mids):
             layer = self.mids[li - 1]
             _lib.check(L.hg_pack_disc_weight(eff.data_ptr(), layer.cout, layer.cin, layer.groups, layer.merge,
                                              layer.k, layer.stride, layer.pad, bufs["fwd"][li].data_ptr(), 0, st),
@@ -787,13 +878,20 @@ class _SubDiscTrainer:
         # second part's power iteration continues from the first's.  The layers are independent of each other, so
         # their fold / power-iteration / pack chains are spread over the prep lanes (part 0 before part 1 per layer).
         if self.spectral or not self.fwd_valid:
-            Ws = [self._weights(pi, only_buffers=True) for pi in range(len(parts))]
-            self.prep.fork()
-            for li in range(len(self.mods)):
-                with self.prep.lane(li):
-                    for pi, W in enumerate(Ws):
-                        self._weights_layer(W, self.wbufs[pi], li)
-            self.prep.join()
+            if self.spectral:
+                # the power iterations of the layers are independent chains (part 0 before part 1 per layer: the second
+                # call continues from the first's u, v): spread them over the prep lanes, then pack each part
+                Ws = [self._weights(pi, only_buffers=True) for pi in range(len(parts))]
+                self.prep.fork()
+                for li in range(len(self.mods)):
+                    with self.prep.lane(li):
+                        for pi, W in enumerate(Ws):
+                            self._weights_layer(W, self.wbufs[pi], li, pack=False)
+                self.prep.join()
+                for pi in range(len(parts)):
+                    self._table(pi).launch("fwd")
+            else:
+                Ws = [self._prepare_weights(0)]
             self.W_cached = Ws[-1]
             self.fwd_valid = True
         else:
@@ -891,6 +989,8 @@ class _SubDiscTrainer:
                                   G["dlogit"][nr:].data_ptr(), st))
         here = torch.cuda.current_stream()
         here.wait_stream(self.lanes.streams[0])     # data-gradient packs (queued by forward on the w-lane)
+        if not self.spectral:
+            self.dwp_flat.zero_()
         self.lanes.fork()     # both lanes join the capture here (a join of a never-forked stream would invalidate it)
         for pi, (b0, bn, W) in enumerate(self.parts):
             if pi == 1:                       # spectral norm: the generated half's chain on the second lane
@@ -911,8 +1011,11 @@ class _SubDiscTrainer:
 
     def _pack_dgrad(self, W, part: int = 0) -> None:
         if self.spectral or not self.dgrad_valid:
-            for bl, w_eff in zip(self._bwd_bank(part), W["eff"][1:-1]):
-                bl.pack(w_eff)
+            t = self._table(part)
+            if t.has("dgrad"):
+                t.launch("dgrad")
+            for i in self.untiled:
+                self._bwd_bank(part)[i].pack(W["eff"][1 + i])
             self.dgrad_valid = True
 
     # ---- one module call under torch autograd (autograd.py): forward with its own activation / weight slot ---------
@@ -923,9 +1026,12 @@ class _SubDiscTrainer:
         L = _lib.lib()
         nb, t = x2d.shape
         G = self._geometry(nb, t, slot)
-        W = self._weights(slot)
-        for bl, w_eff in zip(self._bwd_bank(slot), W["eff"][1:-1]):
-            bl.pack(w_eff)
+        W = self._prepare_weights(slot)
+        tb = self._table(slot)
+        if tb.has("dgrad"):
+            tb.launch("dgrad")
+        for i in self.untiled:
+            self._bwd_bank(slot)[i].pack(W["eff"][1 + i])
         self._forward_part(L, G, W, x2d, 0, nb, t)
         return G, W
 
@@ -938,6 +1044,8 @@ class _SubDiscTrainer:
         nb, t = x2d.shape
         self.G, self.nb, self.nreal, self.t, self.ycat = G, nb, nb, t, x2d
         G["dlogit"].copy_(dlogit)
+        if want_wgrad and not self.spectral:
+            self.dwp_flat.zero_()
         self.lanes.fork()
         self._backward_part(L, G, W, 0, nb, want_wgrad=want_wgrad, fm=False, dy_audio=dy_audio, accumulate=True,
                             part=slot, pre_adds=pre_adds)
@@ -1014,27 +1122,28 @@ class _SubDiscTrainer:
                 def layer_grads(layer=layer, m=m, li=li, h_out=h_out, rows_out=rows_out, rows_in=rows_in, d_out=d_out,
                                 a_in=a_in):
                     st = _stream()
+                    sn = hasattr(m, "weight_orig")
+                    # weight_norm layers: dwps[li] was zeroed with the whole region (zero_wgrads) and is finished by
+                    # the batched launch below; the spectral-norm scale's two halves each need their own sigma, so
+                    # they start from zero and are routed layer by layer
                     _lib.check(L.hg_conv1d_wgrad(a_in[seq0:].data_ptr(), d_out.data_ptr(), 1, nseq * rows_in, layer.cin,
                                                  nseq * rows_out, nseq * rows_out, layer.groups_eff, layer.cout,
-                                                 layer.k, layer.stride, 1, layer.pad, self.dwp.data_ptr(), 0, st),
-                               "hg_conv1d_wgrad")
-                    cin_g = layer.cin // layer.groups
-                    order = (c_int * layer.k)(*layer.order)
-                    if hasattr(m, "weight_orig"):
-                        _lib.check(L.hg_unpack_wgrad_conv(self.dwp.data_ptr(), layer.cout, cin_g, layer.k, layer.cout,
-                                                          layer.cin_tile, layer.cout // layer.groups, layer.merge,
-                                                          order, self.scratch.data_ptr(), st), "hg_unpack_wgrad_conv")
+                                                 layer.k, layer.stride, 1, layer.pad, self.dwps[li].data_ptr(),
+                                                 0 if sn else 1, st), "hg_conv1d_wgrad")
+                    if sn:
+                        cin_g = layer.cin // layer.groups
+                        order = (c_int * layer.k)(*layer.order)
+                        _lib.check(L.hg_unpack_wgrad_conv(self.dwps[li].data_ptr(), layer.cout, cin_g, layer.k,
+                                                          layer.cout, layer.cin_tile, layer.cout // layer.groups,
+                                                          layer.merge, order, self.scratch.data_ptr(), st),
+                                   "hg_unpack_wgrad_conv")
                         self._route(L, m, self.scratch, layer.cout, cin_g * layer.k, W, 1 + li, True)
-                    else:
-                        g, v = _g_v(m)          # unpack + weight_norm backward in one launch, accumulating
-                        _lib.check(L.hg_wgrad_finish_conv(self.dwp.data_ptr(), layer.cout, cin_g, layer.k, layer.cout,
-                                                          layer.cin_tile, layer.cout // layer.groups, layer.merge,
-                                                          order, v.data_ptr(), g.data_ptr(), 1, _gb(v).data_ptr(),
-                                                          _gb(g).data_ptr(), st), "hg_wgrad_finish_conv")
                 side(layer_grads)
             bwd[li].dgrad(L, d_out, nseq, h_out, rows_out, rows_in, a_in[seq0:],
                           a_in[seq0 - nr:] if fm else None, nfm[li] if fm else 0.0, G["grad"][li][seq0:], _stream(),
                           flat_h_in=h_in, bias_dst=bias_of(li), pre_add=pre[li])
+        if want_wgrad and not self.spectral:
+            side(lambda: self._table(part).launch("finish"))     # every wide layer's unpack + weight_norm backward
         # first conv (Cin = 1)
         k0, s0, p0, c0 = self.first
         m0 = self.mods[0]

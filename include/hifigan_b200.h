@@ -314,6 +314,60 @@ int hg_spectral_norm_fwd(const float* w, float* u, float* v, int rows, int cols,
 int hg_spectral_norm_bwd(const float* dw_eff, const float* w_eff, const float* u, const float* v, const float* sigma,
                          int rows, int cols, int accumulate, float* dw_orig, float* ws, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Batched weight preparation / weight-gradient finishing: ONE launch for many layers.
+ *
+ * The per-layer entry points above (hg_pack_conv1d_weight, hg_pack_convtr1d_weight, hg_pack_dgrad_weight,
+ * hg_fold_weight_norm, hg_pack_disc_weight, hg_wgrad_finish_conv / _convtr) cost one launch per layer and call; a
+ * training step re-derives ~135 filter banks after every optimizer update (the reference's weight_norm hook recomputes
+ * w = g * v / ||v|| on every forward, src/models.py:16-31,56-59,81,86-88,96,132-140,196-204).  hg_prep_batched runs any
+ * mix of those per-layer jobs in one grid: `jobs` is a device array of hg_prep_job, `block_job` a device array of
+ * (job index, block index within the job) int pairs, one per block; blocks [first_block, first_block + nblocks) are
+ * launched with `smem_bytes` of dynamic shared memory (the largest any job in the range needs).  Jobs whose input is
+ * another job's output (a data-gradient bank is packed from the forward bank / the effective weight) go into a later
+ * range = a later launch.  Integer fields by kind (i[..], tab[..]):
+ *   HG_JOB_GEN_CONV        one block per padded output channel.  src0 v fp32 [cout][cin][k], src1 g (NULL: folded weight),
+ *                          src2 bias (optional) -> dst0 bf16 [k][cout_p][cin_p], dst1 bias_out fp32 [cout_p] (optional).
+ *                          i = {cout, cin, k, cout_p, cin_p}
+ *   HG_JOB_GEN_CONVTR      one block per padded input channel.  src0 v fp32 [cin][cout][k], src1 g, src2 bias ->
+ *                          dst0 bf16 [nshift][stride*cout_p][cin_p] (polyphase), dst1 bias_out fp32 [stride*cout_p].
+ *                          i = {cin, cout, k, cin_p, cout_p, stride, padding, nshift, shift_min}
+ *   HG_JOB_GEN_POST        one block.  conv_post folded to fp32: src0 v [1][cin][k], src1 g, src2 bias -> dst0 fp32
+ *                          [cin_p][k], dst1 fp32 [1].  i = {cin, k, cin_p}
+ *   HG_JOB_DISC_ROW        one block per output channel; smem cin_g * k floats.  src0 v fp32 [cout][cin_g][k], src1 g
+ *                          (NULL: src0 is the effective weight) -> dst0 effective weight fp32 (optional), dst1 forward
+ *                          bank bf16 [q][cout][cin_tile] (optional).  i = {cout, cin_g, k, merge, cout_g, cin_tile},
+ *                          tab = tap order (hg_conv1d_tap_order)
+ *   HG_JOB_TRANSPOSE_TILE  one block per 32 x 32 tile; smem 2 176 B.  src0 bf16 [k][n][c] -> dst0 bf16 [k][c][n], taps
+ *                          reversed (hg_pack_dgrad_weight).  i = {k, n, c, tiles_c, tiles_n}; blocks = k*tiles_c*tiles_n
+ *   HG_JOB_DISC_DGRAD_TILE one block per [tci input channels] x [32 dy channels]; smem 32 * (tci*k + 1) floats.  src0
+ *                          effective weight fp32 -> dst0 bf16 [nshift][stride*cin][cout_tile] (hg_pack_disc_weight's
+ *                          w_dgrad).  i = {cout, cin_g, k, merge, cout_g, cin, stride, pad, nshift, shift_min, cout_tile,
+ *                          tci, cin / tci}; blocks = (cin / tci) * (cout_tile / 32)
+ *   HG_JOB_FINISH_ROW      one block per dim-0 index of the parameter; smem d1 * k floats.  src0 packed dW fp32, src1 g
+ *                          (NULL: plain weight), src2 v -> dst0 dv, dst1 dg (hg_wgrad_finish_conv / _convtr).
+ *                          i = {mode (0 conv, 1 convtr), d0, d1, k, rows_p, cin_tile, cout_g, merge, stride, padding,
+ *                          shift_min, cout_p, accumulate}, tab = packed position of tap j (conv)
+ */
+enum {
+  HG_JOB_GEN_CONV = 0, HG_JOB_GEN_CONVTR = 1, HG_JOB_GEN_POST = 2, HG_JOB_DISC_ROW = 3, HG_JOB_TRANSPOSE_TILE = 4,
+  HG_JOB_DISC_DGRAD_TILE = 5, HG_JOB_FINISH_ROW = 6
+};
+typedef struct hg_prep_job {
+  const void* src0;
+  const void* src1;
+  const void* src2;
+  void* dst0;
+  void* dst1;
+  int32_t kind;
+  int32_t i[16];
+  int32_t tab[64];
+  int32_t pad_;
+} hg_prep_job;
+int hg_prep_job_size(void);
+int hg_prep_batched(const hg_prep_job* jobs, const int* block_job, int first_block, int nblocks, int smem_bytes,
+                    void* stream);
+
 /* hg_colsum_bf16 — bias gradient: out[c] (+)= sum_{b, t < t_valid} x[b][t][c]; x bf16 [B][t_rows][C]. */
 int hg_colsum_bf16(const void* x, int batch, int t_valid, int t_rows, int c, int accumulate, float* out, void* stream);
 
