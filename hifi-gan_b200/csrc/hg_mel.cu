@@ -307,6 +307,293 @@ __global__ void __launch_bounds__(kMelThreads) mel_kernel(const MelArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// mel_kernel2 — the forward kernel of round 2: ONE WARP PER TWO FRAMES, the FFT held in registers.
+//
+// The 512-point complex FFT of a frame's even/odd packed samples is split 512 = 32 x 16 (n = 16 n1 + n2,
+// k = k1 + 32 k2):   Z[k1 + 32 k2] = sum_n2 W16^(n2 k2) [ W512^(n2 k1) sum_n1 z[16 n1 + n2] W32^(n1 k1) ]
+//   phase 1  lane = (frame, n2): 32 windowed complex samples straight from global memory (64-bit coalesced loads,
+//            reflect padding by index arithmetic), a 32-point DFT in registers (4 x 8, compile-time twiddles), the
+//            W512 twiddles from a padded shared table, results to the warp's exchange buffer (conflict-free pitch 33)
+//   phase 2  lane = k1: the 16 values of each frame from the exchange buffer, a 16-point DFT in registers (4 x 4),
+//            Z to shared memory in natural order
+//   phase 3  lane = k mod 32: real-FFT un-pack of its 16 (+1) bins from Z[k], Z[512 - k], |X|^2 (only up to the last
+//            bin any mel filter reads), written over the frame's own Z region
+//   phase 4  lane = mel bin mod 32: the CSR triangle sums + log(clamp), staged for 64-byte output runs
+// Warps never meet (__syncwarp between phases); a block is 8 warps = 16 consecutive frames and loops over frame
+// groups, so the constant tables are loaded once per block.  ~2.4x fewer warp-instructions per frame than the
+// radix-8 x 8 x 8 shared-memory kernel above (which stays: the backward kernel is built from its passes), and no
+// block-wide or named barriers on the frame path.
+// The lane phases are __host__ __device__ (hg_mel_emulate_host runs them lane by lane on the CPU).
+constexpr int kExPitch = 33;                              // complex per (frame, n2) row of the exchange buffer
+constexpr int kWarpScratch = 2 * 16 * kExPitch;           // complex per warp (8448 B) >= 2 x 512 (the Z / power view)
+constexpr int kTwPad = kHalf + kHalf / 16;                // padi(511) + 1
+
+// e^{-2 pi i j / 32}, j a compile-time constant after unrolling
+__host__ __device__ __forceinline__ cpx w32(int j) {
+  constexpr float c[9] = {1.f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                          0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f,
+                          0.19509032201612826785f, 0.f};
+  // cos(2 pi j / 32) for j in [0, 32) by symmetry around the quarter turns; sin likewise
+  const int q = j & 31;
+  const int r = q & 7, quad = q >> 3;
+  const float cr = c[r], sr = c[8 - r];                   // cos, sin of the first-quadrant remainder
+  switch (quad) {
+    case 0: return cpx{cr, -sr};
+    case 1: return cpx{-sr, -cr};
+    case 2: return cpx{-cr, sr};
+    default: return cpx{sr, cr};
+  }
+}
+
+// 32-point DFT (forward), v in natural order -> natural order
+__host__ __device__ __forceinline__ void fft32(cpx (&v)[32]) {
+#pragma unroll
+  for (int b = 0; b < 8; ++b) fft4(v[b], v[8 + b], v[16 + b], v[24 + b]);       // over a (n = 8a + b): v[8 ka + b]
+#pragma unroll
+  for (int ka = 1; ka < 4; ++ka)
+#pragma unroll
+    for (int b = 1; b < 8; ++b) v[8 * ka + b] = cmul(v[8 * ka + b], w32(b * ka));
+  cpx o[32];
+#pragma unroll
+  for (int ka = 0; ka < 4; ++ka) {
+    cpx t[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) t[b] = v[8 * ka + b];
+    fft8(t);
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) o[ka + 4 * kb] = t[kb];
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = o[i];
+}
+
+// 16-point DFT (forward), natural order in and out
+__host__ __device__ __forceinline__ void fft16(cpx (&v)[16]) {
+#pragma unroll
+  for (int b = 0; b < 4; ++b) fft4(v[b], v[4 + b], v[8 + b], v[12 + b]);        // n = 4a + b -> v[4 ka + b]
+#pragma unroll
+  for (int ka = 1; ka < 4; ++ka)
+#pragma unroll
+    for (int b = 1; b < 4; ++b) v[4 * ka + b] = cmul(v[4 * ka + b], w32(2 * b * ka));
+  cpx o[16];
+#pragma unroll
+  for (int ka = 0; ka < 4; ++ka) {
+    cpx t0 = v[4 * ka], t1 = v[4 * ka + 1], t2 = v[4 * ka + 2], t3 = v[4 * ka + 3];
+    fft4(t0, t1, t2, t3);
+    o[ka] = t0; o[ka + 4] = t1; o[ka + 8] = t2; o[ka + 12] = t3;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = o[i];
+}
+
+struct Mel2Args {
+  const float* y;
+  float* out;
+  float* minmax;
+  int batch, t, frames, hop, pad, num_mels;
+  const float* window;
+  const float2* tw512;
+  const float2* tw1024;
+  const int* mel_start;
+  const int* mel_off;
+  const float* mel_w;
+  int nnz, max_bin;       // max_bin: the last rFFT bin any mel filter reads
+  int groups_per_item;    // ceil(frames / 16)
+  int total_groups;       // batch * groups_per_item
+};
+
+// phase 1 (lane = 16 * frame + n2): frame samples -> window -> DFT-32 -> W512 twiddle -> exchange buffer.
+// `yb` is the batch item, `start` the (possibly negative) first sample of this lane's frame, `vec` whether the
+// frame is interior and 8-byte aligned (plain 64-bit loads).  Returns the lane's sample extrema through lo / hi.
+__host__ __device__ __forceinline__ void mel2_phase1(int lane, const float* __restrict__ yb, int start, int t, bool vec,
+                                                     const float* __restrict__ window, const float2* __restrict__ tw512p,
+                                                     cpx* __restrict__ ex, float& lo, float& hi) {
+  const int n2 = lane & 15;
+  cpx v[32];
+#pragma unroll
+  for (int n1 = 0; n1 < 32; ++n1) {
+    const int s = 32 * n1 + 2 * n2;
+    float x0, x1;
+    if (vec) {
+      const float2 xv = *reinterpret_cast<const float2*>(yb + start + s);
+      x0 = xv.x; x1 = xv.y;
+    } else {
+      x0 = yb[reflect_index(start + s, t)];
+      x1 = yb[reflect_index(start + s + 1, t)];
+    }
+    lo = fminf(lo, fminf(x0, x1));
+    hi = fmaxf(hi, fmaxf(x0, x1));
+    const float2 w = *reinterpret_cast<const float2*>(window + s);
+    v[n1] = cpx{x0 * w.x, x1 * w.y};
+  }
+  fft32(v);
+  cpx* row = ex + lane * kExPitch;          // (frame * 16 + n2) * pitch
+  row[0] = v[0];
+#pragma unroll
+  for (int k1 = 1; k1 < 32; ++k1) {
+    const float2 w = tw512p[padi(n2 * k1)];
+    row[k1] = cmul(v[k1], cpx{w.x, w.y});
+  }
+}
+// phase 2a (lane = k1): gather the 16 n2 values of both frames; 2b: DFT-16, Z in natural order over the same buffer
+__host__ __device__ __forceinline__ void mel2_phase2_read(int lane, const cpx* __restrict__ ex, cpx (&a)[16], cpx (&b)[16]) {
+#pragma unroll
+  for (int n2 = 0; n2 < 16; ++n2) {
+    a[n2] = ex[n2 * kExPitch + lane];
+    b[n2] = ex[(16 + n2) * kExPitch + lane];
+  }
+}
+__host__ __device__ __forceinline__ void mel2_phase2_write(int lane, cpx (&a)[16], cpx (&b)[16], cpx* __restrict__ z) {
+  fft16(a);
+  fft16(b);
+#pragma unroll
+  for (int k2 = 0; k2 < 16; ++k2) {
+    z[lane + 32 * k2] = a[k2];
+    z[kHalf + lane + 32 * k2] = b[k2];
+  }
+}
+// phase 3a (lane = k mod 32): |X[k]|^2 of the lane's bins k = lane + 32 k2 (k <= max_bin) of one frame's Z;
+// pw[16] is bin 512 (lane 0).  3b: the powers go over the frame's own Z region (as floats).
+__host__ __device__ __forceinline__ void mel2_phase3_compute(int lane, const cpx* __restrict__ z, int max_bin,
+                                                             const float2* __restrict__ tw1024, float (&pw)[17]) {
+#pragma unroll
+  for (int k2 = 0; k2 < 16; ++k2) {
+    const int k = lane + 32 * k2;
+    float p = 0.f;
+    if (k <= max_bin) {
+      const cpx zk = z[k];
+      cpx zc = z[(kHalf - k) & (kHalf - 1)];
+      zc.y = -zc.y;
+      const cpx e = cpx{0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y)};
+      const cpx d = csub(zk, zc);
+      const cpx o = cpx{0.5f * d.y, -0.5f * d.x};  // (zk - zc) / (2i)
+      const float2 w = tw1024[k];
+      const cpx x = cadd(e, cmul(o, cpx{w.x, w.y}));
+      p = x.x * x.x + x.y * x.y;
+    }
+    pw[k2] = p;
+  }
+  pw[16] = 0.f;
+  if (lane == 0 && kHalf <= max_bin) {
+    const cpx z0 = z[0];                           // X[512] = Re Z[0] - Im Z[0]
+    pw[16] = (z0.x - z0.y) * (z0.x - z0.y);
+  }
+}
+__host__ __device__ __forceinline__ void mel2_phase3_write(int lane, const float (&pw)[17], float* __restrict__ power) {
+#pragma unroll
+  for (int k2 = 0; k2 < 16; ++k2) power[lane + 32 * k2] = pw[k2];
+  if (lane == 0) power[kHalf] = pw[16];
+}
+// phase 4 (lane = m mod 32): CSR triangle sums + log(clamp(., 1e-5)) of one frame -> out_col[m * out_stride]
+__host__ __device__ __forceinline__ void mel2_phase4(int lane, int num_mels, const float* __restrict__ power,
+                                                     const int* __restrict__ mel_start, const int* __restrict__ mel_off,
+                                                     const float* __restrict__ mel_w, float* __restrict__ out_col,
+                                                     int out_stride) {
+  for (int m = lane; m < num_mels; m += 32) {
+    const int s = mel_start[m], o = mel_off[m], n = mel_off[m + 1] - o;
+    float acc = 0.f;
+    for (int i = 0; i < n; ++i) acc += mel_w[o + i] * power[s + i];
+    out_col[m * out_stride] = logf(fmaxf(acc, 1e-5f));
+  }
+}
+
+struct Mel2Smem {
+  uint32_t win, tw512, tw1024, melw, melidx, meloff, scratch, outs, total;
+};
+__host__ __device__ inline Mel2Smem mel2_smem_layout(int num_mels, int nnz) {
+  auto up = [](uint32_t v) { return (v + 15u) & ~15u; };
+  Mel2Smem l;
+  uint32_t o = 0;
+  l.win = o;     o += kNfft * 4u;
+  l.tw512 = o;   o += up(kTwPad * 8u);
+  l.tw1024 = o;  o += up((kHalf + 1) * 8u);
+  l.melw = o;    o += up(static_cast<uint32_t>(nnz > 0 ? nnz : 1) * 4u);
+  l.melidx = o;  o += up(static_cast<uint32_t>(num_mels) * 4u);
+  l.meloff = o;  o += up(static_cast<uint32_t>(num_mels + 1) * 4u);
+  l.scratch = o; o += (kMelThreads / 32) * kWarpScratch * 8u;
+  l.outs = o;    o += static_cast<uint32_t>(num_mels) * kFramesPerBlock * 4u;
+  l.total = o;
+  return l;
+}
+
+__global__ void __launch_bounds__(kMelThreads / 2, 2) mel_kernel2(const Mel2Args a) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  constexpr int kThreads2 = kMelThreads / 2;                                   // 8 warps
+  const Mel2Smem L = mel2_smem_layout(a.num_mels, a.nnz);
+  float* s_win = reinterpret_cast<float*>(sm + L.win);
+  float2* s_tw512p = reinterpret_cast<float2*>(sm + L.tw512);                  // padded: entry i at padi(i)
+  float2* s_tw1024 = reinterpret_cast<float2*>(sm + L.tw1024);
+  float* s_melw = reinterpret_cast<float*>(sm + L.melw);
+  int* s_start = reinterpret_cast<int*>(sm + L.melidx);
+  int* s_off = reinterpret_cast<int*>(sm + L.meloff);
+  float* outs = reinterpret_cast<float*>(sm + L.outs);                         // [num_mels][16]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  cpx* scratch = reinterpret_cast<cpx*>(sm + L.scratch) + warp * kWarpScratch;
+
+  cp_async_table(s_win, a.window, kNfft * 4, tid, kThreads2);
+  cp_async_table(s_tw1024, a.tw1024, (kHalf + 1) * 8, tid, kThreads2);
+  cp_async_table(s_melw, a.mel_w, a.nnz * 4, tid, kThreads2);
+  cp_async_table(s_start, a.mel_start, a.num_mels * 4, tid, kThreads2);
+  cp_async_table(s_off, a.mel_off, (a.num_mels + 1) * 4, tid, kThreads2);
+  for (int i = tid; i < kHalf; i += kThreads2) s_tw512p[padi(i)] = a.tw512[i];
+  cp_async_wait_all();
+  __syncthreads();
+
+  float vmin = INFINITY, vmax = -INFINITY;
+  for (int grp = blockIdx.x; grp < a.total_groups; grp += gridDim.x) {
+    const int b = grp / a.groups_per_item;
+    const int f0 = (grp - b * a.groups_per_item) * kFramesPerBlock;
+    const float* yb = a.y + static_cast<size_t>(b) * a.t;
+    const int fl0 = 2 * warp;                           // this warp's two frames within the group
+    const int f = f0 + fl0 + (lane >> 4);
+    const bool live = f < a.frames;                     // half-warp uniform
+    if (f0 + fl0 < a.frames) {                          // warp-uniform: at least the first frame exists
+      const int start = (live ? f : a.frames - 1) * a.hop - a.pad;
+      const bool vec = start >= 0 && start + kNfft <= a.t &&
+                       ((reinterpret_cast<uintptr_t>(yb + start) & 7) == 0);
+      float lo = INFINITY, hi = -INFINITY;
+      mel2_phase1(lane, yb, start, a.t, vec, s_win, s_tw512p, scratch, lo, hi);
+      if (live) { vmin = fminf(vmin, lo); vmax = fmaxf(vmax, hi); }
+      __syncwarp();
+      cpx za[16], zb[16];
+      mel2_phase2_read(lane, scratch, za, zb);
+      __syncwarp();
+      mel2_phase2_write(lane, za, zb, scratch);
+      __syncwarp();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float pw[17];
+        mel2_phase3_compute(lane, scratch + h * kHalf, a.max_bin, s_tw1024, pw);
+        __syncwarp();
+        float* power = reinterpret_cast<float*>(scratch + h * kHalf);
+        mel2_phase3_write(lane, pw, power);
+        __syncwarp();
+        if (f0 + fl0 + h < a.frames)
+          mel2_phase4(lane, a.num_mels, power, s_start, s_off, s_melw, outs + fl0 + h, kFramesPerBlock);
+      }
+    }
+    __syncthreads();
+    // outs[m][fl] -> out[b][m][f0 + fl]
+    float* ob = a.out + static_cast<size_t>(b) * a.num_mels * a.frames;
+    for (int i = tid; i < a.num_mels * kFramesPerBlock; i += kThreads2) {
+      const int m = i / kFramesPerBlock, fl = i % kFramesPerBlock;
+      if (f0 + fl < a.frames) ob[static_cast<size_t>(m) * a.frames + f0 + fl] = outs[i];
+    }
+    __syncthreads();
+  }
+  if (a.minmax) {
+    for (int o = 16; o > 0; o >>= 1) {
+      vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+      vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    }
+    if (lane == 0) {
+      if (vmin < *reinterpret_cast<volatile float*>(a.minmax)) atomic_min_f32(a.minmax, vmin);
+      if (vmax > *reinterpret_cast<volatile float*>(a.minmax + 1)) atomic_max_f32(a.minmax + 1, vmax);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Any other n_fft (the reference's other callers pass n_fft = a layer's kernel size at sr 16000,
 // src/speech_distillation/lightning_model.py:513-522, custom_layers.py:138-161): one block per frame, direct DFT
 // over a shared-memory twiddle table.  O(n_fft^2 / 2) per frame — a general-purpose path, not the tuned one.
@@ -512,6 +799,36 @@ extern "C" int hg_mel_fwd(const hg_mel_plan* plan, const float* y, int batch, in
     g_hg_launches.fetch_add(1, std::memory_order_relaxed);
     return HG_OK;
   }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static const bool use_v1 = getenv("HG_MEL_V1") != nullptr;       // the round-1 kernel, kept for A/B measurements
+  if (!use_v1) {
+    Mel2Args a{};
+    a.y = y; a.out = out; a.minmax = minmax;
+    a.batch = batch; a.t = t; a.frames = frames; a.hop = plan->hop; a.pad = plan->pad;
+    a.num_mels = plan->num_mels;
+    a.window = plan->window; a.tw512 = plan->tw512; a.tw1024 = plan->tw1024;
+    a.mel_start = plan->mel_start; a.mel_off = plan->mel_off; a.mel_w = plan->mel_w;
+    a.nnz = plan->nnz;
+    a.max_bin = 0;
+    for (int m = 0; m < plan->num_mels; ++m) {
+      const int last = plan->h_mel_start[m] + (plan->h_mel_off[m + 1] - plan->h_mel_off[m]) - 1;
+      if (last > a.max_bin) a.max_bin = last;
+    }
+    a.groups_per_item = (frames + kFramesPerBlock - 1) / kFramesPerBlock;
+    a.total_groups = batch * a.groups_per_item;
+    const size_t smem = mel2_smem_layout(plan->num_mels, plan->nnz).total;
+    HG_REQUIRE(smem <= 113 * 1024, "hg_mel_fwd: %zu bytes of shared memory per block", smem);
+    static hg::PerDeviceOnce once2;
+    if (once2.need(smem))
+      HG_CHECK_CUDA(cudaFuncSetAttribute(mel_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = a.total_groups < 2 * sms ? a.total_groups : 2 * sms;   // two resident blocks per SM, looping
+    mel_kernel2<<<grid, kMelThreads / 2, smem, st>>>(a);
+    HG_CHECK_CUDA(cudaGetLastError());
+    g_hg_launches.fetch_add(1, std::memory_order_relaxed);
+    return HG_OK;
+  }
   MelArgs a{};
   a.y = y; a.out = out; a.minmax = minmax;
   a.batch = batch; a.t = t; a.frames = frames; a.hop = plan->hop; a.pad = plan->pad;
@@ -526,7 +843,7 @@ extern "C" int hg_mel_fwd(const hg_mel_plan* plan, const float* y, int batch, in
   if (once.need(smem))
     HG_CHECK_CUDA(cudaFuncSetAttribute(mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((frames + kFramesPerBlock - 1) / kFramesPerBlock, batch);
-  mel_kernel<<<grid, kMelThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  mel_kernel<<<grid, kMelThreads, smem, st>>>(a);
   HG_CHECK_CUDA(cudaGetLastError());
   g_hg_launches.fetch_add(1, std::memory_order_relaxed);
   return HG_OK;
@@ -756,24 +1073,44 @@ extern "C" int hg_mel_emulate_host(const hg_mel_plan* plan, const float* host_y,
       }
     return HG_OK;
   }
-  std::vector<float> smp(plan->n_fft);
-  std::vector<cpx> z0(kPadLen), z1(kPadLen);
-  std::vector<float> power(kHalf + 1);
+  // mel_kernel2's lane phases, the 32 lanes of a warp serialised, two frames at a time
+  std::vector<cpx> scratch(kWarpScratch);
+  std::vector<float2> tw512p(kTwPad);
+  for (int i = 0; i < kHalf; ++i) tw512p[padi(i)] = plan->h_tw512[i];
+  int max_bin = 0;
+  for (int m = 0; m < plan->num_mels; ++m) {
+    const int last = plan->h_mel_start[m] + (plan->h_mel_off[m + 1] - plan->h_mel_off[m]) - 1;
+    if (last > max_bin) max_bin = last;
+  }
+  std::vector<cpx> ra(32 * 16), rb(32 * 16);
+  std::vector<float> pws(32 * 17);
   for (int b = 0; b < batch; ++b)
-    for (int f = 0; f < frames; ++f) {
-      for (int n = 0; n < plan->n_fft; ++n)
-        smp[n] = host_y[static_cast<size_t>(b) * t + reflect_index(f * plan->hop - plan->pad + n, t)];
-      for (int j = 0; j < 64; ++j)
-        fft_pass<true>(j, 1, nullptr, z0.data(), smp.data(), plan->h_window.data(), plan->h_tw512.data());
-      for (int j = 0; j < 64; ++j)
-        fft_pass<false>(j, 8, z0.data(), z1.data(), nullptr, nullptr, plan->h_tw512.data());
-      for (int j = 0; j < 64; ++j)
-        fft_pass<false>(j, 64, z1.data(), z0.data(), nullptr, nullptr, plan->h_tw512.data());
-      for (int j = 0; j < 64; ++j) unpack_power(j, z0.data(), power.data(), plan->h_tw1024.data());
-      float* col = host_out + static_cast<size_t>(b) * plan->num_mels * frames + f;
-      for (int j = 0; j < 64; ++j)
-        mel_project(j, plan->num_mels, power.data(), plan->h_mel_start.data(), plan->h_mel_off.data(),
-                    plan->h_mel_w.data(), col, frames);
+    for (int f0 = 0; f0 < frames; f0 += 2) {
+      const float* yb = host_y + static_cast<size_t>(b) * t;
+      for (int lane = 0; lane < 32; ++lane) {
+        const int f = f0 + (lane >> 4);
+        const int start = (f < frames ? f : frames - 1) * plan->hop - plan->pad;
+        float lo = 0.f, hi = 0.f;
+        mel2_phase1(lane, yb, start, t, false, plan->h_window.data(), tw512p.data(), scratch.data(), lo, hi);
+      }
+      for (int lane = 0; lane < 32; ++lane)
+        mel2_phase2_read(lane, scratch.data(), *reinterpret_cast<cpx(*)[16]>(&ra[lane * 16]),
+                         *reinterpret_cast<cpx(*)[16]>(&rb[lane * 16]));
+      for (int lane = 0; lane < 32; ++lane)
+        mel2_phase2_write(lane, *reinterpret_cast<cpx(*)[16]>(&ra[lane * 16]),
+                          *reinterpret_cast<cpx(*)[16]>(&rb[lane * 16]), scratch.data());
+      for (int h = 0; h < 2 && f0 + h < frames; ++h) {
+        for (int lane = 0; lane < 32; ++lane)
+          mel2_phase3_compute(lane, scratch.data() + h * kHalf, max_bin, plan->h_tw1024.data(),
+                              *reinterpret_cast<float(*)[17]>(&pws[lane * 17]));
+        float* power = reinterpret_cast<float*>(scratch.data() + h * kHalf);
+        for (int lane = 0; lane < 32; ++lane)
+          mel2_phase3_write(lane, *reinterpret_cast<float(*)[17]>(&pws[lane * 17]), power);
+        float* col = host_out + static_cast<size_t>(b) * plan->num_mels * frames + f0 + h;
+        for (int lane = 0; lane < 32; ++lane)
+          mel2_phase4(lane, plan->num_mels, power, plan->h_mel_start.data(), plan->h_mel_off.data(),
+                      plan->h_mel_w.data(), col, frames);
+      }
     }
   return HG_OK;
 }
