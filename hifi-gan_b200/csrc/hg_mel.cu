@@ -327,6 +327,8 @@ __global__ void __launch_bounds__(kMelThreads) mel_kernel(const MelArgs a) {
 constexpr int kExPitch = 33;                              // complex per (frame, n2) row of the exchange buffer
 constexpr int kWarpScratch = 2 * 16 * kExPitch;           // complex per warp (8448 B) >= 2 x 512 (the Z / power view)
 constexpr int kTwPad = kHalf + kHalf / 16;                // padi(511) + 1
+constexpr int kMel2Warps = 8;                             // 8 warps x 2 frames = kFramesPerBlock
+constexpr int kMel2Threads = kMel2Warps * 32;
 
 // e^{-2 pi i j / 32}, j a compile-time constant after unrolling
 __host__ __device__ __forceinline__ cpx w32(int j) {
@@ -510,15 +512,15 @@ __host__ __device__ inline Mel2Smem mel2_smem_layout(int num_mels, int nnz) {
   l.melw = o;    o += up(static_cast<uint32_t>(nnz > 0 ? nnz : 1) * 4u);
   l.melidx = o;  o += up(static_cast<uint32_t>(num_mels) * 4u);
   l.meloff = o;  o += up(static_cast<uint32_t>(num_mels + 1) * 4u);
-  l.scratch = o; o += (kMelThreads / 32) * kWarpScratch * 8u;
+  l.scratch = o; o += kMel2Warps * kWarpScratch * 8u;
   l.outs = o;    o += static_cast<uint32_t>(num_mels) * kFramesPerBlock * 4u;
   l.total = o;
   return l;
 }
 
-__global__ void __launch_bounds__(kMelThreads / 2, 2) mel_kernel2(const Mel2Args a) {
+__global__ void __launch_bounds__(kMel2Threads, 2) mel_kernel2(const Mel2Args a) {
   extern __shared__ __align__(16) uint8_t sm[];
-  constexpr int kThreads2 = kMelThreads / 2;                                   // 8 warps
+  constexpr int kThreads2 = kMel2Threads;
   const Mel2Smem L = mel2_smem_layout(a.num_mels, a.nnz);
   float* s_win = reinterpret_cast<float*>(sm + L.win);
   float2* s_tw512p = reinterpret_cast<float2*>(sm + L.tw512);                  // padded: entry i at padi(i)
@@ -824,7 +826,7 @@ extern "C" int hg_mel_fwd(const hg_mel_plan* plan, const float* y, int batch, in
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = a.total_groups < 2 * sms ? a.total_groups : 2 * sms;   // two resident blocks per SM, looping
-    mel_kernel2<<<grid, kMelThreads / 2, smem, st>>>(a);
+    mel_kernel2<<<grid, kMel2Threads, smem, st>>>(a);
     HG_CHECK_CUDA(cudaGetLastError());
     g_hg_launches.fetch_add(1, std::memory_order_relaxed);
     return HG_OK;
