@@ -123,10 +123,35 @@ def mel_spectrogram(y, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin,
 
 
 def load_wav(full_path):
-    """reference meldataset.py:15-17 (file IO is outside the accelerated path)."""
-    import torchaudio
-    data, sampling_rate = torchaudio.load(full_path, normalize=True)
-    return data, sampling_rate
+    """reference meldataset.py:15-17: (float32 [channels, L] in [-1, 1], sampling_rate), what
+    `torchaudio.load(path, normalize=True)` returns.  File IO is outside the accelerated path; when torchaudio has no
+    audio backend in the environment the same values are read with scipy (16-/32-bit PCM and float wav files)."""
+    try:
+        import torchaudio
+        data, sampling_rate = torchaudio.load(full_path, normalize=True)
+        return data, sampling_rate
+    except Exception:  # noqa: BLE001  (no backend / codec: plain PCM reader)
+        import numpy as np
+        from scipy.io.wavfile import read
+        sampling_rate, data = read(full_path)
+        data = np.asarray(data)
+        if data.dtype == np.int16:
+            data = data.astype(np.float32) / 32768.0
+        elif data.dtype == np.int32:
+            data = data.astype(np.float32) / 2147483648.0
+        elif data.dtype == np.uint8:
+            data = (data.astype(np.float32) - 128.0) / 128.0
+        data = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32))
+        data = data.unsqueeze(0) if data.dim() == 1 else data.t().contiguous()
+        return data, sampling_rate
+
+
+def normalize(audio):
+    """Peak normalisation of an utterance — what UPSTREAM's `librosa.util.normalize(audio)` does on a 1-D array.
+    (This fork calls it on a [1, L] tensor, where librosa's default axis=0 normalises every SAMPLE by its own magnitude;
+    train_loop.normalize_fork reproduces that literal behaviour.  SURVEY.md §8a row S.)"""
+    peak = audio.abs().max()
+    return audio / peak if peak > 0 else audio
 
 
 def save_wav(full_path, data, sampling_rate):
@@ -160,6 +185,96 @@ def get_dataset_filelist(a):
         validation_files = [os.path.join(a.input_wavs_dir, x.split('|')[0] + '.wav')
                             for x in fi.read().split('\n') if len(x) > 0]
     return training_files, validation_files
+
+
+class MelDataset(torch.utils.data.Dataset):
+    """The reference's `MelDataset` (meldataset.py:99-181): same constructor, same per-item rule and the same
+    `(mel, audio, filename, mel_loss)` tuple, with both mel computations on the fused GPU kernel.
+
+    __getitem__ follows the reference line by line — (cached) load, `/ MAX_WAV_VALUE` (the fork's quirk, :128),
+    peak normalisation unless fine-tuning (:129-130), sampling-rate check (:132-134), the inclusive
+    `random.randint(0, len - seg)` crop or right zero-pad (:141-150), input mel with `fmax` / fine-tuning `.npy` mel
+    crop (:152-172), loss mel with `fmax_loss` (:174-176) — using Python's global `random` seeded 1234 at construction
+    (:104) so the draw sequence matches the reference's.  Tensors come back on the CPU (what a DataLoader collates);
+    the mels are computed on `device` (default: the current CUDA device).  For the training loop's batched,
+    GPU-resident form of the same rule see `SegmentSampler`."""
+
+    def __init__(self, training_files, segment_length, n_fft, num_mels, hop_size, win_size, sampling_rate, fmin, fmax,
+                 split=True, shuffle=True, n_cache_reuse=1, device=None, fmax_loss=None, fine_tuning=False,
+                 base_mels_path=None):
+        self.audio_files = training_files
+        random.seed(1234)
+        if shuffle:
+            random.shuffle(self.audio_files)
+        self.segment_length = segment_length
+        self.sampling_rate = sampling_rate
+        self.split = split
+        self.n_fft = n_fft
+        self.num_mels = num_mels
+        self.hop_size = hop_size
+        self.win_size = win_size
+        self.fmin = fmin
+        self.fmax = fmax
+        self.fmax_loss = fmax_loss
+        self.cached_wav = None
+        self.n_cache_reuse = n_cache_reuse
+        self._cache_ref_count = 0
+        self.device = device
+        self.fine_tuning = fine_tuning
+        self.base_mels_path = base_mels_path
+
+    def _mel(self, audio, fmax):
+        dev = torch.device(self.device) if self.device is not None else torch.device("cuda")
+        if dev.type != "cuda":
+            raise RuntimeError("MelDataset: hifigan_b200 has no CPU path; pass a CUDA device (or leave device=None)")
+        return mel_spectrogram(audio.to(dev), self.n_fft, self.num_mels, self.sampling_rate, self.hop_size,
+                               self.win_size, self.fmin, fmax, center=False).cpu()
+
+    def __getitem__(self, index):
+        import os
+        filename = self.audio_files[index]
+        if self._cache_ref_count == 0:
+            audio, sampling_rate = load_wav(filename)
+            audio = audio / MAX_WAV_VALUE
+            if not self.fine_tuning:
+                audio = normalize(audio) * 0.95
+            self.cached_wav = audio
+            if sampling_rate != self.sampling_rate:
+                raise ValueError("{} SR doesn't match target {} SR".format(sampling_rate, self.sampling_rate))
+            self._cache_ref_count = self.n_cache_reuse
+        else:
+            audio = self.cached_wav
+            self._cache_ref_count -= 1
+        audio = torch.as_tensor(audio, dtype=torch.float32).reshape(1, -1)
+        if not self.fine_tuning:
+            if self.split:
+                if audio.size(1) >= self.segment_length:
+                    max_audio_start = audio.size(1) - self.segment_length
+                    audio_start = random.randint(0, max_audio_start)
+                    audio = audio[:, audio_start:audio_start + self.segment_length]
+                else:
+                    audio = torch.nn.functional.pad(audio, (0, self.segment_length - audio.size(1)), 'constant')
+            mel = self._mel(audio, self.fmax)
+        else:
+            import numpy as np
+            mel = torch.from_numpy(np.load(os.path.join(
+                self.base_mels_path, os.path.splitext(os.path.split(filename)[-1])[0] + '.npy')))
+            if len(mel.shape) < 3:
+                mel = mel.unsqueeze(0)
+            if self.split:
+                frames_per_seg = math.ceil(self.segment_length / self.hop_size)
+                if audio.size(1) >= self.segment_length:
+                    mel_start = random.randint(0, mel.size(2) - frames_per_seg - 1)
+                    mel = mel[:, :, mel_start:mel_start + frames_per_seg]
+                    audio = audio[:, mel_start * self.hop_size:(mel_start + frames_per_seg) * self.hop_size]
+                else:
+                    mel = torch.nn.functional.pad(mel, (0, frames_per_seg - mel.size(2)), 'constant')
+                    audio = torch.nn.functional.pad(audio, (0, self.segment_length - audio.size(1)), 'constant')
+        mel_loss = self._mel(audio, self.fmax_loss)
+        return (mel.squeeze(), audio.squeeze(0), filename, mel_loss.squeeze())
+
+    def __len__(self):
+        return len(self.audio_files)
 
 
 class SegmentSampler:

@@ -630,6 +630,110 @@ def test_inference_e2e_driver_matches_per_file_reference_schedule(H, O, tmp_path
         assert np.array_equal(wav, ref), k
 
 
+def _int16_close(wav, ref_float, what):
+    """written int16 samples vs the ORACLE's fp32 waveform under the declared bf16 numerics: max |diff| <= 5e-3 of
+    full scale (SURVEY §8d waveform tolerance) and SNR >= 35 dB against the reference's own `* 32768 -> int16`"""
+    ref = (ref_float * 32768.0).astype("int16")
+    assert wav.dtype == np.int16 and wav.shape == ref.shape, what
+    diff = wav.astype(np.float64) - ref.astype(np.float64)
+    assert np.abs(diff).max() <= 5e-3 * 32768, (what, np.abs(diff).max())
+    sig = ref.astype(np.float64) - ref.astype(np.float64).mean()
+    snr = 10 * np.log10((sig ** 2).sum() / max((diff ** 2).sum(), 1e-9))
+    assert snr >= 35.0, (what, snr)
+
+
+def test_inference_drivers_vs_oracle(H, O, tmp_path):
+    """Both inference drivers against the ORACLE (not this repo's own Generator): `e2e` mode on .npy mels of three
+    different lengths (src/inference_e2e.py:34-57) and `wav` mode on wav files (src/inference.py:37-62), including the
+    reference's quirk of dividing torchaudio's already-normalised floats by 32768 again (inference.py:51-52) — the
+    mel the Generator sees is that of the 32768-times-quieter signal."""
+    import json
+    from scipy.io.wavfile import read, write
+    from hifigan_b200 import inference as drv
+    cfg = dict(O.config("v1"))
+    cfg["seed"] = 1234
+    h = H.AttrDict(cfg)
+    torch.manual_seed(11)
+    G = H.Generator(h)
+    sd = {k: v.detach().clone() for k, v in G.state_dict().items()}
+    cp = tmp_path / "cp"
+    cp.mkdir()
+    torch.save({"generator": G.state_dict()}, cp / "g_00000001")
+    (cp / "config.json").write_text(json.dumps(cfg))
+    # ---- mel -> wav
+    mels = tmp_path / "mels"
+    mels.mkdir()
+    audio = {"a": O.synthetic_audio(1, 9000, seed=1), "b": O.synthetic_audio(1, 5000, seed=2),
+             "c": O.synthetic_audio(1, 9000, seed=3)}
+    data = {k: O.mel_spectrogram(v, 1024, 80, 22050, 256, 1024, 0, 8000) for k, v in audio.items()}
+    for k, v in data.items():
+        np.save(mels / f"{k}.npy", v.numpy())
+    out = tmp_path / "out_e2e"
+    drv.main(["e2e", "--checkpoint_file", str(cp / "g_00000001"), "--input_mels_dir", str(mels), "--output_dir", str(out)])
+    for k, v in data.items():
+        sr, wav = read(out / f"{k}_generated_e2e.wav")
+        with torch.no_grad():
+            ref = O.generator_forward(sd, h, v).squeeze().numpy()
+        assert sr == h.sampling_rate
+        _int16_close(wav, ref, k)
+    # ---- wav -> mel -> wav
+    wavs = tmp_path / "wavs"
+    wavs.mkdir()
+    for k, v in audio.items():
+        write(wavs / f"{k}.wav", 22050, (v[0].numpy() * 32767).astype(np.int16))
+    out = tmp_path / "out_wav"
+    drv.main(["wav", "--checkpoint_file", str(cp / "g_00000001"), "--input_wavs_dir", str(wavs), "--output_dir", str(out)])
+    for k, v in audio.items():
+        sr, wav = read(out / f"{k}_generated.wav")
+        pcm = torch.from_numpy((v[0].numpy() * 32767).astype(np.int16).astype(np.float32) / 32768.0)   # load_wav
+        x = O.mel_spectrogram((pcm / 32768.0).unsqueeze(0), 1024, 80, 22050, 256, 1024, 0, 8000)       # the quirk
+        with torch.no_grad():
+            ref = O.generator_forward(sd, h, x).squeeze().numpy()
+        _int16_close(wav, ref, k + " (wav mode)")
+
+
+def test_meldataset_class_matches_reference_rule(H, O, tmp_path):
+    """`MelDataset` (reference meldataset.py:99-181): constructor signature, the `(mel, audio, filename, mel_loss)`
+    tuple, the seeded shuffle and inclusive randint crop / right zero-pad, both mels against the oracle."""
+    import random
+    from scipy.io.wavfile import write
+    files = []
+    lengths = [20000, 6000, 8192, 12345]
+    for i, n in enumerate(lengths):
+        a = O.synthetic_audio(1, n, seed=40 + i)[0]
+        path = str(tmp_path / f"f{i}.wav")
+        write(path, 22050, (a.numpy() * 32767).astype(np.int16))
+        files.append(path)
+    ds = H.MelDataset(list(files), 8192, 1024, 80, 256, 1024, 22050, 0, 8000, n_cache_reuse=0, shuffle=True,
+                      fmax_loss=None, device="cuda")
+    # the reference's bookkeeping, replayed: seed, shuffle, then one randint per long-enough item
+    random.seed(1234)
+    expect = list(files)
+    random.shuffle(expect)
+    assert ds.audio_files == expect and len(ds) == 4
+    state = random.getstate()
+    items = [ds[i] for i in range(4)]
+    random.setstate(state)
+    from scipy.io.wavfile import read
+    for (mel, audio, name, mel_loss), path in zip(items, expect):
+        _, pcm = read(path)
+        a = torch.from_numpy(pcm.astype(np.float32) / 32768.0) / 32768.0            # load_wav, then the / MAX_WAV_VALUE quirk
+        a = a / a.abs().max() * 0.95                                                  # normalize(audio) * 0.95
+        if a.numel() >= 8192:
+            s0 = random.randint(0, a.numel() - 8192)
+            seg = a[s0:s0 + 8192]
+        else:
+            seg = torch.nn.functional.pad(a, (0, 8192 - a.numel()))
+        assert name == path and audio.shape == (8192,) and mel.shape == (80, 32) and mel_loss.shape == (80, 32)
+        assert torch.allclose(audio, seg, atol=1e-7)
+        for got, fmax in ((mel, 8000), (mel_loss, None)):
+            ref = O.mel_spectrogram(seg.double().unsqueeze(0), 1024, 80, 22050, 256, 1024, 0, fmax)[0]
+            lin_g, lin_r = got.double().exp(), ref.exp()       # fp32 kernel: relative in the power domain, with a
+            assert bool(((lin_g - lin_r).abs() <= 2e-3 * lin_r + 1e-6 * lin_r.max()).all())   # floor 60 dB below the peak
+    with pytest.raises(ValueError, match="SR doesn't match"):
+        H.MelDataset([files[0]], 8192, 1024, 80, 256, 1024, 16000, 0, 8000, shuffle=False)[0]
+
+
 def test_randomised_shapes_sweep():
     """tests/gpu_fuzz.py, fixed seed: batch sizes, frame counts, audio lengths, (n_fft, hop, win) and training batch
     sizes the fixed cases above do not hit — generators, discriminators (logits + all feature maps), mel and one
