@@ -11,7 +11,8 @@ import torch
 
 from . import _lib
 
-GEN_CONV, GEN_CONVTR, GEN_POST, DISC_ROW, TRANSPOSE_TILE, DISC_DGRAD_TILE, FINISH_ROW = range(7)
+(GEN_CONV, GEN_CONVTR, GEN_POST, DISC_ROW, TRANSPOSE_TILE, DISC_DGRAD_TILE, FINISH_ROW, LOSS_SUM, SN_WTU, SN_WV,
+ SN_SCALE) = range(11)
 
 
 class PrepJob(ctypes.Structure):
@@ -55,6 +56,14 @@ class JobTable:
         self._jobs.append(j)
         self._blocks.setdefault(phase, []).extend((idx, b) for b in range(nblocks))
         self._smem[phase] = max(self._smem.get(phase, 0), int(smem))
+
+    def add_loss_sum(self, phase: str, mode: int, a, b, n: int, c: float, out_ptr: int, chunk: int = 16384) -> None:
+        """sum |a - b| (mode 0, fp32; mode 2, bf16: n counts 16-byte groups) or sum (c - a)^2 (mode 1) -> *out_ptr +="""
+        import struct
+        cbits = struct.unpack("<i", struct.pack("<f", float(c)))[0]
+        lo = n & 0xFFFFFFFF
+        lo = lo - (1 << 32) if lo >= (1 << 31) else lo          # the low word travels as a signed int32
+        self.add(phase, LOSS_SUM, (n + chunk - 1) // chunk, 0, a, b, dst0=out_ptr, ints=(mode, lo, n >> 32, chunk, cbits))
 
     def finalize(self) -> "JobTable":
         if ctypes.sizeof(PrepJob) != _lib.lib().hg_prep_job_size():

@@ -33,16 +33,6 @@ struct hg_mel_plan {
   int* mel_start;    // [num_mels] first rFFT bin with a non-zero weight
   int* mel_off;      // [num_mels+1] CSR offsets into mel_w
   float* mel_w;      // [nnz]
-  // lane-balanced form of the same CSR for the warp-per-frame kernel: the nnz (mel, bin, weight) entries in CSR order,
-  // cut into 32 equal runs (one per lane), stored lane-interleaved [per_lane][32]; lb_idx packs bin | flush << 12 |
-  // slot << 13: after an entry with `flush` the lane's running sum is one piece of a mel and goes to part[slot];
-  // mel m is the sum of the pieces lb_ps[m] .. lb_ps[m+1]-1 (in order: deterministic)
-  float* lb_w;
-  int* lb_idx;
-  int* lb_ps;        // [num_mels + 1]
-  int lb_per_lane, lb_slots;
-  std::vector<float> h_lb_w;
-  std::vector<int> h_lb_idx, h_lb_ps;
   // host copies (CPU emulation for tests, and geometry queries)
   std::vector<float> h_window;
   std::vector<float2> h_tw512, h_tw1024, h_tw_n;
@@ -406,13 +396,12 @@ struct Mel2Args {
   const float* window;
   const float2* tw512;
   const float2* tw1024;
-  const float* lb_w;      // lane-balanced mel projection tables (hg_mel_plan)
-  const int* lb_idx;
-  const int* lb_ps;
-  int lb_per_lane, lb_slots;
-  int max_bin;            // the last rFFT bin any mel filter reads
-  int pairs_per_item;     // ceil(frames / 2)
-  int total_pairs;        // batch * pairs_per_item
+  const int* mel_start;
+  const int* mel_off;
+  const float* mel_w;
+  int nnz, max_bin;       // max_bin: the last rFFT bin any mel filter reads
+  int groups_per_item;    // ceil(frames / 16)
+  int total_groups;       // batch * groups_per_item
 };
 
 // phase 1 (lane = 16 * frame + n2): frame samples -> window -> DFT-32 -> W512 twiddle -> exchange buffer.
@@ -497,105 +486,102 @@ __host__ __device__ __forceinline__ void mel2_phase3_write(int lane, const float
   for (int k2 = 0; k2 < 16; ++k2) power[lane + 32 * k2] = pw[k2];
   if (lane == 0) power[kHalf] = pw[16];
 }
-// phase 4a: the lane's run of (bin, weight) entries -> running sums, one piece of a mel per flush -> part[slot];
-// 4b (lane = m mod 32): mel m = its pieces in order, log(clamp(., 1e-5)) -> out_col[m * out_stride]
-__host__ __device__ __forceinline__ void mel2_phase4_pieces(int lane, int per_lane, const float* __restrict__ power,
-                                                            const float* __restrict__ lb_w, const int* __restrict__ lb_idx,
-                                                            float* __restrict__ part) {
-  float sum = 0.f;
-  for (int it = 0; it < per_lane; ++it) {
-    const int idx = lb_idx[it * 32 + lane];
-    sum += lb_w[it * 32 + lane] * power[idx & 0xFFF];
-    if (idx & (1 << 12)) {
-      part[idx >> 13] = sum;
-      sum = 0.f;
-    }
-  }
-}
-__host__ __device__ __forceinline__ void mel2_phase4_log(int lane, int num_mels, const float* __restrict__ part,
-                                                         const int* __restrict__ lb_ps, float* __restrict__ out_col,
-                                                         size_t out_stride) {
+// phase 4 (lane = m mod 32): CSR triangle sums + log(clamp(., 1e-5)) of one frame -> out_col[m * out_stride]
+__host__ __device__ __forceinline__ void mel2_phase4(int lane, int num_mels, const float* __restrict__ power,
+                                                     const int* __restrict__ mel_start, const int* __restrict__ mel_off,
+                                                     const float* __restrict__ mel_w, float* __restrict__ out_col,
+                                                     int out_stride) {
   for (int m = lane; m < num_mels; m += 32) {
+    const int s = mel_start[m], o = mel_off[m], n = mel_off[m + 1] - o;
     float acc = 0.f;
-    for (int q = lb_ps[m]; q < lb_ps[m + 1]; ++q) acc += part[q];
+    for (int i = 0; i < n; ++i) acc += mel_w[o + i] * power[s + i];
     out_col[m * out_stride] = logf(fmaxf(acc, 1e-5f));
   }
 }
 
 struct Mel2Smem {
-  uint32_t win, tw512, tw1024, lbw, lbidx, lbps, scratch, total;
+  uint32_t win, tw512, tw1024, melw, melidx, meloff, scratch, outs, total;
 };
-__host__ __device__ inline Mel2Smem mel2_smem_layout(int num_mels, int per_lane) {
+__host__ __device__ inline Mel2Smem mel2_smem_layout(int num_mels, int nnz) {
   auto up = [](uint32_t v) { return (v + 15u) & ~15u; };
   Mel2Smem l;
   uint32_t o = 0;
   l.win = o;     o += kNfft * 4u;
   l.tw512 = o;   o += up(kTwPad * 8u);
   l.tw1024 = o;  o += up((kHalf + 1) * 8u);
-  l.lbw = o;     o += up(static_cast<uint32_t>(per_lane) * 32u * 4u);
-  l.lbidx = o;   o += up(static_cast<uint32_t>(per_lane) * 32u * 4u);
-  l.lbps = o;    o += up(static_cast<uint32_t>(num_mels + 1) * 4u);
+  l.melw = o;    o += up(static_cast<uint32_t>(nnz > 0 ? nnz : 1) * 4u);
+  l.melidx = o;  o += up(static_cast<uint32_t>(num_mels) * 4u);
+  l.meloff = o;  o += up(static_cast<uint32_t>(num_mels + 1) * 4u);
   l.scratch = o; o += kMel2Warps * kWarpScratch * 8u;
+  l.outs = o;    o += static_cast<uint32_t>(num_mels) * kFramesPerBlock * 4u;
   l.total = o;
   return l;
 }
-constexpr int kPartOff = 520;     // float offset of the mel pieces inside a frame's 1024-float Z / power region
 
 __global__ void __launch_bounds__(kMel2Threads, 2) mel_kernel2(const Mel2Args a) {
   extern __shared__ __align__(16) uint8_t sm[];
-  const Mel2Smem L = mel2_smem_layout(a.num_mels, a.lb_per_lane);
+  constexpr int kThreads2 = kMel2Threads;
+  const Mel2Smem L = mel2_smem_layout(a.num_mels, a.nnz);
   float* s_win = reinterpret_cast<float*>(sm + L.win);
   float2* s_tw512p = reinterpret_cast<float2*>(sm + L.tw512);                  // padded: entry i at padi(i)
   float2* s_tw1024 = reinterpret_cast<float2*>(sm + L.tw1024);
-  float* s_lbw = reinterpret_cast<float*>(sm + L.lbw);
-  int* s_lbidx = reinterpret_cast<int*>(sm + L.lbidx);
-  int* s_lbps = reinterpret_cast<int*>(sm + L.lbps);
+  float* s_melw = reinterpret_cast<float*>(sm + L.melw);
+  int* s_start = reinterpret_cast<int*>(sm + L.melidx);
+  int* s_off = reinterpret_cast<int*>(sm + L.meloff);
+  float* outs = reinterpret_cast<float*>(sm + L.outs);                         // [num_mels][16]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   cpx* scratch = reinterpret_cast<cpx*>(sm + L.scratch) + warp * kWarpScratch;
 
-  cp_async_table(s_win, a.window, kNfft * 4, tid, kMel2Threads);
-  cp_async_table(s_tw1024, a.tw1024, (kHalf + 1) * 8, tid, kMel2Threads);
-  cp_async_table(s_lbw, a.lb_w, a.lb_per_lane * 32 * 4, tid, kMel2Threads);
-  cp_async_table(s_lbidx, a.lb_idx, a.lb_per_lane * 32 * 4, tid, kMel2Threads);
-  cp_async_table(s_lbps, a.lb_ps, (a.num_mels + 1) * 4, tid, kMel2Threads);
-  for (int i = tid; i < kHalf; i += kMel2Threads) s_tw512p[padi(i)] = a.tw512[i];
+  cp_async_table(s_win, a.window, kNfft * 4, tid, kThreads2);
+  cp_async_table(s_tw1024, a.tw1024, (kHalf + 1) * 8, tid, kThreads2);
+  cp_async_table(s_melw, a.mel_w, a.nnz * 4, tid, kThreads2);
+  cp_async_table(s_start, a.mel_start, a.num_mels * 4, tid, kThreads2);
+  cp_async_table(s_off, a.mel_off, (a.num_mels + 1) * 4, tid, kThreads2);
+  for (int i = tid; i < kHalf; i += kThreads2) s_tw512p[padi(i)] = a.tw512[i];
   cp_async_wait_all();
-  __syncthreads();                                      // the only block-wide barrier: warps are independent below
+  __syncthreads();
 
   float vmin = INFINITY, vmax = -INFINITY;
-  const int warps_total = gridDim.x * kMel2Warps;
-  for (int pair = blockIdx.x * kMel2Warps + warp; pair < a.total_pairs; pair += warps_total) {
-    const int b = pair / a.pairs_per_item;
-    const int f0 = (pair - b * a.pairs_per_item) * 2;
+  for (int grp = blockIdx.x; grp < a.total_groups; grp += gridDim.x) {
+    const int b = grp / a.groups_per_item;
+    const int f0 = (grp - b * a.groups_per_item) * kFramesPerBlock;
     const float* yb = a.y + static_cast<size_t>(b) * a.t;
-    const int f = f0 + (lane >> 4);
-    const bool live = f < a.frames;                     // half-warp uniform (an item's last pair may hold one frame)
-    const int start = (live ? f : a.frames - 1) * a.hop - a.pad;
-    const bool vec = start >= 0 && start + kNfft <= a.t && ((reinterpret_cast<uintptr_t>(yb + start) & 7) == 0);
-    float lo = INFINITY, hi = -INFINITY;
-    mel2_phase1(lane, yb, start, a.t, vec, s_win, s_tw512p, scratch, lo, hi);
-    if (live) { vmin = fminf(vmin, lo); vmax = fmaxf(vmax, hi); }
-    __syncwarp();
-    cpx za[16], zb[16];
-    mel2_phase2_read(lane, scratch, za, zb);
-    __syncwarp();
-    mel2_phase2_write(lane, za, zb, scratch);
-    __syncwarp();
-    float* ob = a.out + static_cast<size_t>(b) * a.num_mels * a.frames;
+    const int fl0 = 2 * warp;                           // this warp's two frames within the group
+    const int f = f0 + fl0 + (lane >> 4);
+    const bool live = f < a.frames;                     // half-warp uniform
+    if (f0 + fl0 < a.frames) {                          // warp-uniform: at least the first frame exists
+      const int start = (live ? f : a.frames - 1) * a.hop - a.pad;
+      const bool vec = start >= 0 && start + kNfft <= a.t &&
+                       ((reinterpret_cast<uintptr_t>(yb + start) & 7) == 0);
+      float lo = INFINITY, hi = -INFINITY;
+      mel2_phase1(lane, yb, start, a.t, vec, s_win, s_tw512p, scratch, lo, hi);
+      if (live) { vmin = fminf(vmin, lo); vmax = fmaxf(vmax, hi); }
+      __syncwarp();
+      cpx za[16], zb[16];
+      mel2_phase2_read(lane, scratch, za, zb);
+      __syncwarp();
+      mel2_phase2_write(lane, za, zb, scratch);
+      __syncwarp();
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      float pw[17];
-      mel2_phase3_compute(lane, scratch + h * kHalf, a.max_bin, s_tw1024, pw);
-      __syncwarp();
-      float* power = reinterpret_cast<float*>(scratch + h * kHalf);
-      mel2_phase3_write(lane, pw, power);
-      __syncwarp();
-      mel2_phase4_pieces(lane, a.lb_per_lane, power, s_lbw, s_lbidx, power + kPartOff);
-      __syncwarp();
-      if (f0 + h < a.frames)
-        mel2_phase4_log(lane, a.num_mels, power + kPartOff, s_lbps, ob + f0 + h, static_cast<size_t>(a.frames));
+      for (int h = 0; h < 2; ++h) {
+        float pw[17];
+        mel2_phase3_compute(lane, scratch + h * kHalf, a.max_bin, s_tw1024, pw);
+        __syncwarp();
+        float* power = reinterpret_cast<float*>(scratch + h * kHalf);
+        mel2_phase3_write(lane, pw, power);
+        __syncwarp();
+        if (f0 + fl0 + h < a.frames)
+          mel2_phase4(lane, a.num_mels, power, s_start, s_off, s_melw, outs + fl0 + h, kFramesPerBlock);
+      }
     }
-    __syncwarp();                                       // the next pair's phase 1 overwrites the scratch
+    __syncthreads();
+    // outs[m][fl] -> out[b][m][f0 + fl]
+    float* ob = a.out + static_cast<size_t>(b) * a.num_mels * a.frames;
+    for (int i = tid; i < a.num_mels * kFramesPerBlock; i += kThreads2) {
+      const int m = i / kFramesPerBlock, fl = i % kFramesPerBlock;
+      if (f0 + fl < a.frames) ob[static_cast<size_t>(m) * a.frames + f0 + fl] = outs[i];
+    }
+    __syncthreads();
   }
   if (a.minmax) {
     for (int o = 16; o > 0; o >>= 1) {
@@ -751,33 +737,6 @@ extern "C" int hg_mel_plan_create(hg_mel_plan** out_plan, int n_fft, int num_mel
   }
   p->nnz = static_cast<int>(p->h_mel_w.size());
   if (p->h_mel_w.empty()) p->h_mel_w.push_back(0.f);
-  {
-    // lane-balanced tables (see hg_mel_plan)
-    struct Ent { int m, k; float w; };
-    std::vector<Ent> ents;
-    for (int m = 0; m < num_mels; ++m)
-      for (int i = p->h_mel_off[m]; i < p->h_mel_off[m + 1]; ++i)
-        ents.push_back({m, p->h_mel_start[m] + (i - p->h_mel_off[m]), p->h_mel_w[i]});
-    const int n = static_cast<int>(ents.size());
-    const int per = n > 0 ? (n + 31) / 32 : 1;
-    p->lb_per_lane = per;
-    p->h_lb_w.assign(static_cast<size_t>(per) * 32, 0.f);
-    p->h_lb_idx.assign(static_cast<size_t>(per) * 32, 0);
-    p->h_lb_ps.assign(num_mels + 1, 0);
-    int slot = 0, cur_m = 0;
-    for (int l = 0; l < 32; ++l)
-      for (int it = 0; it < per; ++it) {
-        const int e = l * per + it;
-        if (e >= n) continue;                                  // padding: weight 0, no flush
-        while (cur_m < ents[e].m) p->h_lb_ps[++cur_m] = slot;  // pieces of mels before this one are complete
-        const bool last_of_piece = (it == per - 1) || (e + 1 >= n) || (ents[e + 1].m != ents[e].m);
-        p->h_lb_w[static_cast<size_t>(it) * 32 + l] = ents[e].w;
-        p->h_lb_idx[static_cast<size_t>(it) * 32 + l] = ents[e].k | (last_of_piece ? (1 << 12) : 0) | (slot << 13);
-        if (last_of_piece) ++slot;
-      }
-    while (cur_m < num_mels) p->h_lb_ps[++cur_m] = slot;
-    p->lb_slots = slot;
-  }
 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int ndev = 0;
@@ -786,7 +745,6 @@ extern "C" int hg_mel_plan_create(hg_mel_plan** out_plan, int n_fft, int num_mel
     (void)cudaGetLastError();
     p->window = nullptr; p->tw512 = nullptr; p->tw1024 = nullptr; p->tw_n = nullptr;
     p->mel_start = nullptr; p->mel_off = nullptr; p->mel_w = nullptr;
-    p->lb_w = nullptr; p->lb_idx = nullptr; p->lb_ps = nullptr;
     *out_plan = p;
     return HG_OK;
   }
@@ -802,9 +760,6 @@ extern "C" int hg_mel_plan_create(hg_mel_plan** out_plan, int n_fft, int num_mel
   HG_UP(mel_start, h_mel_start, int)
   HG_UP(mel_off, h_mel_off, int)
   HG_UP(mel_w, h_mel_w, float)
-  HG_UP(lb_w, h_lb_w, float)
-  HG_UP(lb_idx, h_lb_idx, int)
-  HG_UP(lb_ps, h_lb_ps, int)
 #undef HG_UP
   HG_CHECK_CUDA(cudaStreamSynchronize(st));
   *out_plan = p;
@@ -820,9 +775,6 @@ extern "C" int hg_mel_plan_destroy(hg_mel_plan* p) {
   if (p->mel_start) cudaFree(p->mel_start);
   if (p->mel_off) cudaFree(p->mel_off);
   if (p->mel_w) cudaFree(p->mel_w);
-  if (p->lb_w) cudaFree(p->lb_w);
-  if (p->lb_idx) cudaFree(p->lb_idx);
-  if (p->lb_ps) cudaFree(p->lb_ps);
   delete p;
   return HG_OK;
 }
@@ -857,25 +809,23 @@ extern "C" int hg_mel_fwd(const hg_mel_plan* plan, const float* y, int batch, in
     a.batch = batch; a.t = t; a.frames = frames; a.hop = plan->hop; a.pad = plan->pad;
     a.num_mels = plan->num_mels;
     a.window = plan->window; a.tw512 = plan->tw512; a.tw1024 = plan->tw1024;
-    a.lb_w = plan->lb_w; a.lb_idx = plan->lb_idx; a.lb_ps = plan->lb_ps;
-    a.lb_per_lane = plan->lb_per_lane; a.lb_slots = plan->lb_slots;
-    HG_REQUIRE(plan->lb_slots <= 1024 - kPartOff, "hg_mel_fwd: too many mel pieces (%d)", plan->lb_slots);
+    a.mel_start = plan->mel_start; a.mel_off = plan->mel_off; a.mel_w = plan->mel_w;
+    a.nnz = plan->nnz;
     a.max_bin = 0;
     for (int m = 0; m < plan->num_mels; ++m) {
       const int last = plan->h_mel_start[m] + (plan->h_mel_off[m + 1] - plan->h_mel_off[m]) - 1;
       if (last > a.max_bin) a.max_bin = last;
     }
-    a.pairs_per_item = (frames + 1) / 2;
-    a.total_pairs = batch * a.pairs_per_item;
-    const size_t smem = mel2_smem_layout(plan->num_mels, plan->lb_per_lane).total;
+    a.groups_per_item = (frames + kFramesPerBlock - 1) / kFramesPerBlock;
+    a.total_groups = batch * a.groups_per_item;
+    const size_t smem = mel2_smem_layout(plan->num_mels, plan->nnz).total;
     HG_REQUIRE(smem <= 113 * 1024, "hg_mel_fwd: %zu bytes of shared memory per block", smem);
     static hg::PerDeviceOnce once2;
     if (once2.need(smem))
       HG_CHECK_CUDA(cudaFuncSetAttribute(mel_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int blocks_needed = (a.total_pairs + kMel2Warps - 1) / kMel2Warps;
-    const int grid = blocks_needed < 2 * sms ? blocks_needed : 2 * sms;      // two resident blocks per SM, looping
+    const int grid = a.total_groups < 2 * sms ? a.total_groups : 2 * sms;   // two resident blocks per SM, looping
     mel_kernel2<<<grid, kMel2Threads, smem, st>>>(a);
     HG_CHECK_CUDA(cudaGetLastError());
     g_hg_launches.fetch_add(1, std::memory_order_relaxed);
@@ -1160,11 +1110,8 @@ extern "C" int hg_mel_emulate_host(const hg_mel_plan* plan, const float* host_y,
           mel2_phase3_write(lane, *reinterpret_cast<float(*)[17]>(&pws[lane * 17]), power);
         float* col = host_out + static_cast<size_t>(b) * plan->num_mels * frames + f0 + h;
         for (int lane = 0; lane < 32; ++lane)
-          mel2_phase4_pieces(lane, plan->lb_per_lane, power, plan->h_lb_w.data(), plan->h_lb_idx.data(),
-                             power + kPartOff);
-        for (int lane = 0; lane < 32; ++lane)
-          mel2_phase4_log(lane, plan->num_mels, power + kPartOff, plan->h_lb_ps.data(), col,
-                          static_cast<size_t>(frames));
+          mel2_phase4(lane, plan->num_mels, power, plan->h_mel_start.data(), plan->h_mel_off.data(),
+                      plan->h_mel_w.data(), col, frames);
       }
     }
   return HG_OK;

@@ -761,15 +761,53 @@ class _SubDiscTrainer:
         self._tables[part] = t.finalize()
         return t
 
+    def _sn_forward(self, part: int, W: dict) -> None:
+        """spectral-norm layers of part `part`: one power iteration per call in train mode (u / v buffers updated in
+        place, exactly like one forward of torch.nn.utils.spectral_norm), sigma, w_eff = W / sigma — three launches
+        for ALL layers (HG_JOB_SN_* job tables) instead of three per layer.  Fills W["sn"][li] = (u, v, sigma of
+        this call, scratch) for the backward of this call's weights."""
+        from . import batched
+        bufs = self.wbufs[part]
+        training = bool(self.mods[0].training)
+        key = ("sn", training)
+        ent = bufs.get(key)
+        if ent is None:
+            shapes = [(m.weight_orig.shape[0], m.weight_orig.numel() // m.weight_orig.shape[0]) for m in self.mods]
+            ws = torch.zeros(sum(2 * r + 2 * c + 1 for r, c in shapes), dtype=torch.float32, device=self.device)
+            t = batched.JobTable(self.device)
+            views, off = [], 0
+            for li, (m, (rows, cols)) in enumerate(zip(self.mods, shapes)):
+                n = 2 * rows + 2 * cols + 1
+                w = ws[off:off + n]
+                off += n
+                views.append((w[cols + rows + 1: cols + 2 * rows + 1], w[cols + 2 * rows + 1:], w[cols + rows: cols + rows + 1],
+                              w[:cols]))
+                gx = (cols + 255) // 256
+                it = 1 if training else 0
+                nb_wv = min((rows + 7) // 8, 64)
+                nb_sc = min((rows * cols + 1023) // 1024, 256)
+                args = dict(src0=m.weight_orig, src1=m.weight_u, src2=m.weight_v, dst0=bufs["eff"][li], dst1=w)
+                if training:
+                    t.add("wtu", batched.SN_WTU, gx * ((rows + 63) // 64), 0, ints=(rows, cols, it, gx, 0), **args)
+                t.add("wv", batched.SN_WV, nb_wv, 0, ints=(rows, cols, it, gx, nb_wv), **args)
+                t.add("scale", batched.SN_SCALE, nb_sc, 0, ints=(rows, cols, it, gx, nb_sc), **args)
+            ent = bufs[key] = (t.finalize(), ws, views)
+        t, ws, views = ent
+        if training:
+            ws.zero_()
+            t.launch("wtu")
+        t.launch("wv")
+        t.launch("scale")
+        for li, v in enumerate(views):
+            W["sn"][li] = v
+
     def _prepare_weights(self, part: int) -> dict:
         """effective weights + forward banks of part `part` on the current stream: spectral-norm layers run their
         power iteration (one per call in train mode, like the reference's hook), then ONE batched launch folds /
         packs every layer"""
         W = self._weights(part, only_buffers=True)
-        bufs = self.wbufs[part]
         if self.spectral:
-            for li in range(len(self.mods)):
-                self._weights_layer(W, bufs, li, pack=False)
+            self._sn_forward(part, W)
         self._table(part).launch("fwd")
         return W
 
@@ -879,16 +917,10 @@ class _SubDiscTrainer:
         # their fold / power-iteration / pack chains are spread over the prep lanes (part 0 before part 1 per layer).
         if self.spectral or not self.fwd_valid:
             if self.spectral:
-                # the power iterations of the layers are independent chains (part 0 before part 1 per layer: the second
-                # call continues from the first's u, v): spread them over the prep lanes, then pack each part
+                # part 0 before part 1: the second call's power iteration continues from the first's u, v
                 Ws = [self._weights(pi, only_buffers=True) for pi in range(len(parts))]
-                self.prep.fork()
-                for li in range(len(self.mods)):
-                    with self.prep.lane(li):
-                        for pi, W in enumerate(Ws):
-                            self._weights_layer(W, self.wbufs[pi], li, pack=False)
-                self.prep.join()
-                for pi in range(len(parts)):
+                for pi, W in enumerate(Ws):
+                    self._sn_forward(pi, W)
                     self._table(pi).launch("fwd")
             else:
                 Ws = [self._prepare_weights(0)]
@@ -957,22 +989,32 @@ class _SubDiscTrainer:
 
     def loss_terms(self, acc: torch.Tensor, slot: int, fm: bool = True) -> None:
         """acc[slot + 0] += sum (1 - logit_r)^2, [1] += sum logit_g^2, [2] += sum (1 - logit_g)^2,
-        acc[slot + 3 + l] += sum |fmap_r[l] - fmap_g[l]| (l = 0..n_layers, the last one the logits)"""
-        L = _lib.lib()
-        G, period, st = self.G, self.period, _stream()
+        acc[slot + 3 + l] += sum |fmap_r[l] - fmap_g[l]| (l = 0..n_layers, the last one the logits) — every
+        reduction of this sub-discriminator in ONE launch (a HG_JOB_LOSS_SUM job table per geometry)."""
+        G, period = self.G, self.period
         nr = self.nreal * period
         ng = (self.nb - self.nreal) * period
-        h = G["geo"][-1][0]
-        lr, lg = G["logit"][:nr], G["logit"][nr:]
-        _lib.check(L.hg_loss_sum(lr.data_ptr(), 0, nr * h, 1, 1.0, acc[slot:].data_ptr(), st))
-        _lib.check(L.hg_loss_sum(lg.data_ptr(), 0, ng * h, 1, 0.0, acc[slot + 1:].data_ptr(), st))
-        _lib.check(L.hg_loss_sum(lg.data_ptr(), 0, ng * h, 1, 1.0, acc[slot + 2:].data_ptr(), st))
-        if fm and nr == ng:      # feature-matching sums: only the generator step reads them
-            for l, a in enumerate(G["act"]):
-                n = a[:nr].numel()
-                _lib.check(L.hg_l1_sum_bf16(a.data_ptr(), a[nr:].data_ptr(), n, acc[slot + 3 + l:].data_ptr(), st))
-            _lib.check(L.hg_loss_sum(lr.data_ptr(), lg.data_ptr(), nr * h, 0, 0.0,
-                                     acc[slot + 3 + len(G["act"]):].data_ptr(), st))
+        fm = fm and nr == ng           # feature-matching sums: only the generator step reads them
+        key = ("loss", acc.data_ptr(), slot, fm, nr, ng)
+        tab = G.get(key)
+        if tab is None:
+            from . import batched
+            tab = batched.JobTable(self.device)
+            h = G["geo"][-1][0]
+            lr, lg = G["logit"][:nr], G["logit"][nr:]
+            out = lambda i: acc.data_ptr() + 4 * (slot + i)
+            tab.add_loss_sum("sum", 1, lr, None, nr * h, 1.0, out(0))
+            tab.add_loss_sum("sum", 1, lg, None, ng * h, 0.0, out(1))
+            tab.add_loss_sum("sum", 1, lg, None, ng * h, 1.0, out(2))
+            if fm:
+                for l, a in enumerate(G["act"]):
+                    n = a[:nr].numel()
+                    if n % 8:
+                        raise RuntimeError("feature map size must be a multiple of 8 elements")
+                    tab.add_loss_sum("sum", 2, a, a[nr:], n // 8, 0.0, out(3 + l), chunk=4096)
+                tab.add_loss_sum("sum", 0, lr, lg, nr * h, 0.0, out(3 + len(G["act"])))
+            G[key] = tab.finalize()
+        tab.launch("sum")
 
     # ---- backward ------------------------------------------------------------------------------------------
     def backward_d(self) -> None:

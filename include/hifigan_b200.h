@@ -348,10 +348,21 @@ int hg_spectral_norm_bwd(const float* dw_eff, const float* w_eff, const float* u
  *                          (NULL: plain weight), src2 v -> dst0 dv, dst1 dg (hg_wgrad_finish_conv / _convtr).
  *                          i = {mode (0 conv, 1 convtr), d0, d1, k, rows_p, cin_tile, cout_g, merge, stride, padding,
  *                          shift_min, cout_p, accumulate}, tab = packed position of tap j (conv)
+ *   HG_JOB_LOSS_SUM        one block per `chunk` elements: *dst0 += partial sum (the reductions of hg_loss_sum /
+ *                          hg_l1_sum_bf16 for many tensors at once).  src0 a, src1 b.  i = {mode (0: fp32 |a - b|,
+ *                          1: fp32 (c - a)^2, 2: bf16 |a - b| counted in 16-byte groups), n low 32 bits, n high 32
+ *                          bits, chunk, c as float bits}
+ *   HG_JOB_SN_WTU / _WV / _SCALE  the three stages of hg_spectral_norm_fwd, each its own launch (phase) over all
+ *                          spectral-norm layers.  src0 W fp32 [rows][cols], src1 u, src2 v (both updated in place when
+ *                          iterate), dst0 w_eff, dst1 ws fp32 [t: cols][s: rows][sigma][u_copy: rows][v_copy: cols] with
+ *                          t zeroed beforehand.  i = {rows, cols, iterate, WTU blocks along the columns, blocks of
+ *                          this job}; blocks: WTU ceil(cols/256) * ceil(rows/64), WV min(ceil(rows/8), 64), SCALE
+ *                          min(ceil(rows*cols/1024), 256)
  */
 enum {
   HG_JOB_GEN_CONV = 0, HG_JOB_GEN_CONVTR = 1, HG_JOB_GEN_POST = 2, HG_JOB_DISC_ROW = 3, HG_JOB_TRANSPOSE_TILE = 4,
-  HG_JOB_DISC_DGRAD_TILE = 5, HG_JOB_FINISH_ROW = 6
+  HG_JOB_DISC_DGRAD_TILE = 5, HG_JOB_FINISH_ROW = 6, HG_JOB_LOSS_SUM = 7, HG_JOB_SN_WTU = 8, HG_JOB_SN_WV = 9,
+  HG_JOB_SN_SCALE = 10
 };
 typedef struct hg_prep_job {
   const void* src0;
