@@ -462,7 +462,7 @@ def run_train(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    r = measure_train(dev, rank, world, args.steps, args.warmup)
+    r = measure_train(dev, rank, world, args.steps, args.warmup, args.per_gpu_batch or TRAIN["batch"])
     clocks = sampler.stop()
     if rank != 0:
         return
@@ -470,7 +470,8 @@ def run_train(args, rank, world, local_rank):
     line = {"metric": t["metric"], "value": t["value"], "unit": t["unit"], "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": t["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": TRAIN["name"], "per_gpu_batch": r["batch"], "global_batch": t["global_batch"],
+            "config": {"workload": TRAIN["name"].replace("batch 16", f"batch {r['batch']}"), "per_gpu_batch": r["batch"],
+                       "global_batch": t["global_batch"],
                        "segment_size": TRAIN["segment"], "weights": "random init, seed 1234",
                        "numerics": "bf16 operands / activations / activation gradients, fp32 accumulate, fp32 "
                                    "parameter gradients, master weights and AdamW state",
@@ -653,6 +654,9 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + ["train"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step summary of the default line")
+    ap.add_argument("--per-gpu-batch", type=int, default=0,
+                    help="--workload train: segments per GPU (default 16 = BASELINE configs[2]; configs[3]'s global "
+                         "batch 128 is 64 / 32 / 16 at 2 / 4 / 8 GPUs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

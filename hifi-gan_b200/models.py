@@ -368,7 +368,7 @@ class _GeneratorEngine:
         packs = self.packs()
         tensors = [t for pc in packs for t in pc.tensors()] + self._post_tensors()
         if not all(pc.batchable() for pc in packs) or not all(
-                t.device == self.device and t.dtype == torch.float32 and t.is_contiguous() for t in self._post_tensors()):
+                t.device == self.post_w.device and t.dtype == torch.float32 and t.is_contiguous() for t in self._post_tensors()):
             return self._refresh_per_layer()            # parameters living elsewhere (a CPU module): staged per layer
         ptr_key = tuple(t.data_ptr() for t in tensors)
         ver_key = tuple(t._version for t in tensors)

@@ -929,11 +929,12 @@ class _SubDiscTrainer:
         else:
             Ws = [self.W_cached]
         here = torch.cuda.current_stream()
-        # the data-gradient filter banks of these weights are packed on the w-lane, beside the forward chain; the
-        # backward waits for that lane before its first data-gradient launch
-        wlane = self.lanes.streams[0]
-        wlane.wait_stream(here)
-        with torch.cuda.stream(wlane):
+        # the data-gradient filter banks of these weights: one batched launch per part, on a high-priority lane beside
+        # the forward chain (on the low-priority w-lane a many-block launch starves behind the other lanes' tensor-core
+        # kernels and holds the backward up); the backward waits for it before its first data-gradient launch
+        plane = self.prep.streams[0]
+        plane.wait_stream(here)
+        with torch.cuda.stream(plane):
             for pi in range(len(parts)):
                 self._pack_dgrad(Ws[pi], pi)
         for pi, (b0, bn) in enumerate(parts):
@@ -1030,7 +1031,7 @@ class _SubDiscTrainer:
         _lib.check(L.hg_loss_grad(lg.data_ptr(), 0, (ntot - nr) * h, 1, 0.0, 2.0 / ((ntot - nr) * h), 0.0, 0,
                                   G["dlogit"][nr:].data_ptr(), st))
         here = torch.cuda.current_stream()
-        here.wait_stream(self.lanes.streams[0])     # data-gradient packs (queued by forward on the w-lane)
+        here.wait_stream(self.prep.streams[0])      # data-gradient packs (queued by forward on the pack lane)
         if not self.spectral:
             self.dwp_flat.zero_()
         self.lanes.fork()     # both lanes join the capture here (a join of a never-forked stream would invalidate it)
@@ -1107,7 +1108,7 @@ class _SubDiscTrainer:
                                   G["dlogit"][nr:].data_ptr(), st))
         b0, bn, W = self.parts[-1] if self.spectral else (self.nreal, self.nb - self.nreal, self.parts[0][2])
         part = len(self.parts) - 1
-        torch.cuda.current_stream().wait_stream(self.lanes.streams[0])    # data-gradient packs (see forward)
+        torch.cuda.current_stream().wait_stream(self.prep.streams[0])     # data-gradient packs (see forward)
         self._backward_part(L, G, W, self.nreal, self.nb - self.nreal, want_wgrad=False, fm=True,
                             dy_audio=dy_audio, accumulate=False, nfm=nfm, part=part)
 
