@@ -225,9 +225,9 @@ class _GenLayerGrad:
             _lib.check(L.hg_pack_dgrad_weight(pc.w.data_ptr(), pc.taps, self.rows, pc.cin_p, self.wd.data_ptr(),
                                               _stream()), "hg_pack_dgrad_weight")
 
-    def add_jobs(self, table) -> None:
+    def add_jobs(self, table, finish: str = "finish") -> None:
         """this layer's share of the trainer's batched launches: phase "dgrad" = the data-gradient filter bank (tap
-        flip + transpose of the forward bank), phase "finish" = packed dW -> parameter gradients (unpack +
+        flip + transpose of the forward bank), phase `finish` = packed dW -> parameter gradients (unpack +
         weight_norm backward, accumulating)"""
         from . import batched
         pc = self.pc
@@ -239,14 +239,14 @@ class _GenLayerGrad:
         g, v = _g_v(m)
         dg = None if g is None else _gb(g)
         if pc.kind == "conv":
-            table.add("finish", batched.FINISH_ROW, pc.cout, pc.cin * pc.taps * 4, self.dwp, g, v, _gb(v), dg,
+            table.add(finish, batched.FINISH_ROW, pc.cout, pc.cin * pc.taps * 4, self.dwp, g, v, _gb(v), dg,
                       ints=(0, pc.cout, pc.cin, pc.taps, self.rows, pc.cin_p, pc.cout, 1, 0, 0, 0, 0, 1),
                       tab=range(pc.taps))
         else:
             k = m.kernel_size[0]
             nshift, smin = c_int(), c_int()
             _lib.check(_lib.lib().hg_convtr1d_geometry(k, pc.stride, m.padding[0], byref(nshift), byref(smin)))
-            table.add("finish", batched.FINISH_ROW, pc.cin, pc.cout * k * 4, self.dwp, g, v, _gb(v), dg,
+            table.add(finish, batched.FINISH_ROW, pc.cin, pc.cout * k * 4, self.dwp, g, v, _gb(v), dg,
                       ints=(1, pc.cin, pc.cout, k, pc.stride * pc.cout_p, pc.cin_p, 0, 1, pc.stride, m.padding[0],
                             smin.value, pc.cout_p, 1))
 
@@ -338,9 +338,16 @@ class GeneratorTrainer:
             off += gl.dwp_numel
         # the data-gradient banks of every layer / the finish of every packed weight gradient: one launch each
         from . import batched
+        # (finishes go per MRF branch / upsampling conv, launched on the weight-gradient lanes as soon as that
+        # branch's wgrads are queued: only the first stage's are left when the data-gradient chain ends)
         self.table = batched.JobTable(device)
-        for gl in layers:
-            gl.add_jobs(self.table)
+        self.g_pre.add_jobs(self.table, "finish_pre")
+        for i, gl in enumerate(self.g_ups):
+            gl.add_jobs(self.table, f"finish_up{i}")
+        nk_ = gen.num_kernels
+        for n, blk in enumerate(self.g_blocks):
+            for gl in blk:
+                gl.add_jobs(self.table, f"finish_{n // nk_}_{n % nk_}")
         self.table.finalize()
         # stream lanes: 0 .. nk-2 = MRF branches beside the main stream, W_LANE + j = weight-gradient work of branch j
         nk = gen.num_kernels
@@ -509,6 +516,8 @@ class GeneratorTrainer:
                 self._side(L, wl, here, w0)
                 cc.dgrad(L, g, b, t, out, mask=xa, res0=g, res1=r1, res2=r2, bias_dsts=out_bias)
             g = out
+        # this branch's packed weight gradients are all queued on its lane: finish them there
+        self._side(L, wl, here, lambda: self.table.launch(f"finish_{i}_{j}"))
         return g
 
     def _last_conv_bias_dsts(self, i: int, c: int):
@@ -574,6 +583,7 @@ class GeneratorTrainer:
             def up_grads(up=up, dx_raw=dx_raw, up_in=up_in, t=t, c=c, t_in=t_in):
                 up.bias_grad(L, dx_raw, b, t, c)               # dx_raw as [B][t][c]: phases fold into the rows
                 up.wgrad(L, up_in, dx_raw, b, t_in)            # dy viewed as [B][t_in][stride * c]
+                self.table.launch(f"finish_up{i}")
             self._side(L, self.W_LANE, main, up_grads)
             if i > 0:
                 up.dgrad(L, dx_raw, b, t_in, stages[i - 1]["g0"], mask=up_in, scale=1.0 / nk,
@@ -589,9 +599,8 @@ class GeneratorTrainer:
                     self.g_pre.dgrad(L, ws["g_pre"], b, frames, gm)
                     _lib.check(L.hg_nlc_to_ncl(gm.data_ptr(), b, frames, e.pre.cin_p, dx_mel.data_ptr(), _stream()),
                                "hg_nlc_to_ncl")
+                self.table.launch("finish_pre")
         lanes.join()
-        # every packed weight gradient is complete: unpack + weight_norm backward of ALL layers in one launch
-        self.table.launch("finish")
 
 
 # ------------------------------------------------------------------------------------------------ discriminators
@@ -643,7 +652,10 @@ class _SubDiscTrainer:
     """One DiscriminatorP / DiscriminatorS: batched (real ++ generated) forward with saved activations, losses on
     the internal layout, and the hand-written backward."""
 
-    def __init__(self, disc: nn.Module, device):
+    def __init__(self, disc: nn.Module, device, boost: int = 0):
+        """boost: added to the CUDA stream priorities of every lane of this sub-discriminator (negative = more urgent):
+        the sub-discriminator with the longest chain (the spectral-norm scale) is the step's critical path, so its
+        kernels — its weight-gradient lane included — are placed ahead of the other sub-discriminators'."""
         self.disc, self.device = disc, device
         self.period = getattr(disc, "period", 1)
         convs = list(disc.convs)
@@ -659,8 +671,8 @@ class _SubDiscTrainer:
         # the spectral-norm scale runs its real / generated halves as two parts with their own sigma (and their own
         # data-gradient filter banks), on two lanes; lane 0 is the parameter-gradient lane of this sub-discriminator
         self.bwd_parts = [self.bwd] + ([[_DiscBwdLayer(l, device) for l in self.mids]] if self.spectral else [])
-        self.lanes = _Lanes(2, device, [0, -1])      # 0: parameter-gradient lane, 1: second data-gradient chain
-        self.prep = _Lanes(4, device, [-1] * 4)      # weight preparation: independent layers side by side
+        self.lanes = _Lanes(2, device, [0 + boost, -1 + boost])   # 0: parameter-gradient lane, 1: second data-gradient chain
+        self.prep = _Lanes(4, device, [-1 + boost] * 4)           # weight preparation / data-gradient packs
         self.ws = {}
         # packed fp32 weight gradients, one region per wide layer (zeroed once per backward; the wgrad launches and
         # the batched finish accumulate)
@@ -761,45 +773,47 @@ class _SubDiscTrainer:
         self._tables[part] = t.finalize()
         return t
 
-    def _sn_forward(self, part: int, W: dict) -> None:
-        """spectral-norm layers of part `part`: one power iteration per call in train mode (u / v buffers updated in
-        place, exactly like one forward of torch.nn.utils.spectral_norm), sigma, w_eff = W / sigma — three launches
-        for ALL layers (HG_JOB_SN_* job tables) instead of three per layer.  Fills W["sn"][li] = (u, v, sigma of
-        this call, scratch) for the backward of this call's weights."""
-        from . import batched
-        bufs = self.wbufs[part]
+    def _sn_forward(self, parts: List[int], Ws: List[dict]) -> None:
+        """spectral-norm layers, for the consecutive calls `parts` of one forward: one power iteration per call in
+        train mode (u / v buffers updated in place, exactly like one forward of torch.nn.utils.spectral_norm; the
+        second call continues from the first's), sigma, w_eff = W / sigma — ONE launch for all layers and calls
+        (hg_spectral_norm_fwd_all: a thread-block cluster per layer).  Fills W["sn"][li] = (u, v, sigma of that call,
+        scratch) for the backward of that call's weights."""
+        import ctypes
         training = bool(self.mods[0].training)
-        key = ("sn", training)
-        ent = bufs.get(key)
+        key = ("sn", tuple(parts), training)
+        ent = self.__dict__.setdefault("_sn_plans", {}).get(key)
         if ent is None:
+            class SnLayer(ctypes.Structure):
+                _fields_ = [("w", ctypes.c_void_p), ("u", ctypes.c_void_p), ("v", ctypes.c_void_p),
+                            ("eff", ctypes.c_void_p * 2), ("ws", ctypes.c_void_p * 2), ("rows", ctypes.c_int32),
+                            ("cols", ctypes.c_int32)]
             shapes = [(m.weight_orig.shape[0], m.weight_orig.numel() // m.weight_orig.shape[0]) for m in self.mods]
-            ws = torch.zeros(sum(2 * r + 2 * c + 1 for r, c in shapes), dtype=torch.float32, device=self.device)
-            t = batched.JobTable(self.device)
-            views, off = [], 0
+            per = sum(2 * r + 2 * c + 1 for r, c in shapes)
+            ws = torch.zeros(len(parts) * per, dtype=torch.float32, device=self.device)
+            arr = (SnLayer * len(self.mods))()
+            views = [[] for _ in parts]
+            off = 0
             for li, (m, (rows, cols)) in enumerate(zip(self.mods, shapes)):
                 n = 2 * rows + 2 * cols + 1
-                w = ws[off:off + n]
+                arr[li].w, arr[li].u, arr[li].v = m.weight_orig.data_ptr(), m.weight_u.data_ptr(), m.weight_v.data_ptr()
+                arr[li].rows, arr[li].cols = rows, cols
+                for ci, part in enumerate(parts):
+                    w = ws[ci * per + off: ci * per + off + n]
+                    arr[li].eff[ci] = self.wbufs[part]["eff"][li].data_ptr()
+                    arr[li].ws[ci] = w.data_ptr()
+                    views[ci].append((w[cols + rows + 1: cols + 2 * rows + 1], w[cols + 2 * rows + 1:],
+                                      w[cols + rows: cols + rows + 1], w[:cols]))
                 off += n
-                views.append((w[cols + rows + 1: cols + 2 * rows + 1], w[cols + 2 * rows + 1:], w[cols + rows: cols + rows + 1],
-                              w[:cols]))
-                gx = (cols + 255) // 256
-                it = 1 if training else 0
-                nb_wv = min((rows + 7) // 8, 64)
-                nb_sc = min((rows * cols + 1023) // 1024, 256)
-                args = dict(src0=m.weight_orig, src1=m.weight_u, src2=m.weight_v, dst0=bufs["eff"][li], dst1=w)
-                if training:
-                    t.add("wtu", batched.SN_WTU, gx * ((rows + 63) // 64), 0, ints=(rows, cols, it, gx, 0), **args)
-                t.add("wv", batched.SN_WV, nb_wv, 0, ints=(rows, cols, it, gx, nb_wv), **args)
-                t.add("scale", batched.SN_SCALE, nb_sc, 0, ints=(rows, cols, it, gx, nb_sc), **args)
-            ent = bufs[key] = (t.finalize(), ws, views)
-        t, ws, views = ent
+            ent = self._sn_plans[key] = (arr, ws, views)
+        arr, ws, views = ent
         if training:
             ws.zero_()
-            t.launch("wtu")
-        t.launch("wv")
-        t.launch("scale")
-        for li, v in enumerate(views):
-            W["sn"][li] = v
+        _lib.check(_lib.lib().hg_spectral_norm_fwd_all(ctypes.addressof(arr), len(self.mods), len(parts),
+                                                       1 if training else 0, _stream()), "hg_spectral_norm_fwd_all")
+        for ci, W in enumerate(Ws):
+            for li, v in enumerate(views[ci]):
+                W["sn"][li] = v
 
     def _prepare_weights(self, part: int) -> dict:
         """effective weights + forward banks of part `part` on the current stream: spectral-norm layers run their
@@ -807,7 +821,7 @@ class _SubDiscTrainer:
         packs every layer"""
         W = self._weights(part, only_buffers=True)
         if self.spectral:
-            self._sn_forward(part, W)
+            self._sn_forward([part], [W])
         self._table(part).launch("fwd")
         return W
 
@@ -919,8 +933,8 @@ class _SubDiscTrainer:
             if self.spectral:
                 # part 0 before part 1: the second call's power iteration continues from the first's u, v
                 Ws = [self._weights(pi, only_buffers=True) for pi in range(len(parts))]
-                for pi, W in enumerate(Ws):
-                    self._sn_forward(pi, W)
+                self._sn_forward(list(range(len(parts))), Ws)
+                for pi in range(len(parts)):
                     self._table(pi).launch("fwd")
             else:
                 Ws = [self._prepare_weights(0)]
@@ -1234,8 +1248,12 @@ class DiscriminatorTrainer:
         self.flat = FlatParams(holder, device)
         for d in list(mpd.discriminators) + list(msd.discriminators):
             d.__dict__.pop("_hg_wcache", None)
+        # critical-path scheduling: the spectral-norm scale (two parts, full-rate input) has the longest chain, the
+        # second scale the next longest; their lanes outrank the period discriminators' (HG_DISC_BOOST=0 disables)
+        import os
+        boosts = [0, 0, 0] if os.environ.get("HG_DISC_BOOST") == "0" else [-2, -1, 0]
         self.subs_p = [_SubDiscTrainer(d, device) for d in mpd.discriminators]
-        self.subs_s = [_SubDiscTrainer(d, device) for d in msd.discriminators]
+        self.subs_s = [_SubDiscTrainer(d, device, boosts[min(i, 2)]) for i, d in enumerate(msd.discriminators)]
         self.subs = self.subs_p + self.subs_s
         self.nslots = 12
         # raw loss sums of the discriminator-step forward / of the generator-step forward
@@ -1243,7 +1261,8 @@ class DiscriminatorTrainer:
         self.acc_g = torch.zeros_like(self.acc_d)
         self.pooled: List[torch.Tensor] = []
         self._inv_counts: Dict[Tuple[int, int], torch.Tensor] = {}
-        self.lanes = _Lanes(len(self.subs), device, [-1] * len(self.subs))   # one per sub-discriminator
+        self.lanes = _Lanes(len(self.subs), device,                          # one per sub-discriminator
+                            [-1] * len(self.subs_p) + [-1 + boosts[min(i, 2)] for i in range(len(self.subs_s))])
         self.spans = [self.flat.span_of(d) for d in list(mpd.discriminators) + list(msd.discriminators)]
         if self.spans[0][0] != 0 or self.spans[-1][1] != self.flat.numel or any(
                 a[1] != b[0] for a, b in zip(self.spans, self.spans[1:])):

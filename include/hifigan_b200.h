@@ -313,6 +313,21 @@ int hg_spectral_norm_fwd(const float* w, float* u, float* v, int rows, int cols,
                          float* sigma_out, float* u_copy, float* v_copy, float* ws, void* stream);
 int hg_spectral_norm_bwd(const float* dw_eff, const float* w_eff, const float* u, const float* v, const float* sigma,
                          int rows, int cols, int accumulate, float* dw_orig, float* ws, void* stream);
+/* hg_spectral_norm_fwd_all — hg_spectral_norm_fwd for up to 8 layers and up to two consecutive calls (the d(y), d(y_hat)
+ * pair of one MultiScaleDiscriminator forward, src/models.py:236-244: the second call's power iteration continues from
+ * the first's u, v) in ONE launch: a thread-block cluster of 8 CTAs per layer, cluster barriers between the three
+ * dependent passes over W.  host_layers is a HOST array; per call c: eff[c] receives W / sigma_c, ws[c] (fp32,
+ * 2*rows + 2*cols + 1 floats) is laid out [t: cols][s: rows][sigma][u_copy: rows][v_copy: cols] and must have its t
+ * part zeroed beforehand when iterate != 0. */
+typedef struct hg_sn_layer {
+  const float* w;
+  float* u;
+  float* v;
+  float* eff[2];
+  float* ws[2];
+  int32_t rows, cols;
+} hg_sn_layer;
+int hg_spectral_norm_fwd_all(const hg_sn_layer* host_layers, int nlayers, int ncalls, int iterate, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Batched weight preparation / weight-gradient finishing: ONE launch for many layers.

@@ -39,5 +39,14 @@ for n, (c, t, mx) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
 ev.sort()
 t0, t1 = ev[0][0], max(s + d for s, d, _ in ev)
 print(f"span of the two replays: {(t1 - t0) / 1e3:.2f} ms")
-out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "train_kernels.json")
-json.dump([{"ts": s, "dur": d, "n": n} for s, d, n in ev], open(out, "w"))
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+full = os.path.join(root, "gpurun_out", "train_trace_full.json")
+prof.export_chrome_trace(full)
+tr = json.load(open(full))
+ks = [{"ts": e["ts"], "dur": e["dur"], "n": e["name"].replace("(anonymous namespace)::", "").replace("void ", "")[:70],
+       "s": e.get("args", {}).get("stream"), "grid": e.get("args", {}).get("grid"), "pri": e.get("args", {}).get("priority")}
+      for e in tr["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
+ks.sort(key=lambda e: e["ts"])
+json.dump(ks, open(os.path.join(root, "gpurun_out", "train_kernels.json"), "w"))
+os.remove(full)
