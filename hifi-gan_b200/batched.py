@@ -11,8 +11,7 @@ import torch
 
 from . import _lib
 
-(GEN_CONV, GEN_CONVTR, GEN_POST, DISC_ROW, TRANSPOSE_TILE, DISC_DGRAD_TILE, FINISH_ROW, LOSS_SUM, SN_WTU, SN_WV,
- SN_SCALE) = range(11)
+GEN_CONV, GEN_CONVTR, GEN_POST, DISC_ROW, TRANSPOSE_TILE, DISC_DGRAD_TILE, FINISH_ROW, LOSS_SUM = range(8)
 
 
 class PrepJob(ctypes.Structure):

@@ -280,92 +280,6 @@ __device__ void job_loss_sum(const hg_prep_job& j, int lb, float* red) {
   if (threadIdx.x == 0) atomicAdd(static_cast<float*>(j.dst0), acc);
 }
 
-// ---- spectral norm forward for many layers (torch.nn.utils.spectral_norm, dim 0, one power iteration, eps 1e-12;
-// src/models.py:194): the three kernels of hg_spectral_norm_fwd as job kinds, one launch per step for all layers.
-// src0 W fp32 [rows][cols], src1 u [rows] (in/out), src2 v [cols] (in/out), dst0 w_eff, dst1 ws: fp32
-// [t: cols][s: rows][sigma: 1][u_copy: rows][v_copy: cols] (t zeroed by the caller before HG_JOB_SN_WTU).
-// i = {rows, cols, iterate, blocks_x of the WTU grid}
-__device__ void job_sn_wtu(const hg_prep_job& j, int lb) {        // t[c] += sum_{rows of this block} W[r][c] u[r]
-  const int rows = j.i[0], cols = j.i[1], gx = j.i[3];
-  const float* w = static_cast<const float*>(j.src0);
-  const float* u = static_cast<const float*>(j.src1);
-  float* t = static_cast<float*>(j.dst1);
-  const int bx = lb % gx, by = lb / gx;
-  const int c = bx * 256 + threadIdx.x;
-  if (c >= cols) return;
-  const int r0 = by * 64, r1 = min(rows, r0 + 64);
-  float a = 0.f;
-  for (int r = r0; r < r1; ++r) a += w[static_cast<size_t>(r) * cols + c] * u[r];
-  atomicAdd(t + c, a);
-}
-__device__ void job_sn_wv(const hg_prep_job& j, int lb, int nb, float* red) {   // v = normalize(t); s = W v
-  const int rows = j.i[0], cols = j.i[1], iterate = j.i[2];
-  const float* w = static_cast<const float*>(j.src0);
-  float* v = static_cast<float*>(const_cast<void*>(j.src2));
-  float* ws = static_cast<float*>(j.dst1);
-  const float* t = ws;
-  float* sv = ws + cols;
-  float* v_copy = ws + cols + rows + 1 + rows;
-  float inv = 1.f;
-  if (iterate) {
-    float ss = 0.f;
-    for (int c = threadIdx.x; c < cols; c += 256) ss += t[c] * t[c];
-    ss = block_sum256(ss, red);
-    inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-  }
-  const float* src = iterate ? t : v;
-  // rows first (they read the OLD v when !iterate, and t otherwise), then block 0 publishes the new v
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int r = lb * 8 + warp; r < rows; r += nb * 8) {
-    const float* wr = w + static_cast<size_t>(r) * cols;
-    float a = 0.f;
-    for (int c = lane; c < cols; c += 32) a += wr[c] * src[c];
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0) sv[r] = a * inv;
-  }
-  if (lb == 0) {
-    for (int c = threadIdx.x; c < cols; c += 256) {
-      const float val = src[c] * inv;
-      v_copy[c] = val;
-      if (iterate) v[c] = val;     // in-place buffer update, as torch does in train mode; other blocks read t, not v
-    }
-  }
-}
-__device__ void job_sn_scale(const hg_prep_job& j, int lb, int nb, float* red) {   // u, sigma, w_eff = W / sigma
-  const int rows = j.i[0], cols = j.i[1], iterate = j.i[2];
-  const float* w = static_cast<const float*>(j.src0);
-  float* u = static_cast<float*>(const_cast<void*>(j.src1));
-  float* eff = static_cast<float*>(j.dst0);
-  float* ws = static_cast<float*>(j.dst1);
-  const float* sv = ws + cols;
-  float* sigma_out = ws + cols + rows;
-  float* u_copy = ws + cols + rows + 1;
-  float sigma;
-  if (iterate) {
-    float ss = 0.f;
-    for (int r = threadIdx.x; r < rows; r += 256) ss += sv[r] * sv[r];
-    ss = block_sum256(ss, red);
-    const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-    sigma = ss * inv;
-    if (lb == 0)
-      for (int r = threadIdx.x; r < rows; r += 256) {
-        const float val = sv[r] * inv;
-        u[r] = val;
-        u_copy[r] = val;
-      }
-  } else {
-    float d = 0.f;
-    for (int r = threadIdx.x; r < rows; r += 256) d += u[r] * sv[r];
-    sigma = block_sum256(d, red);
-    if (lb == 0)
-      for (int r = threadIdx.x; r < rows; r += 256) u_copy[r] = u[r];
-  }
-  if (lb == 0 && threadIdx.x == 0) *sigma_out = sigma;
-  const float inv_sigma = 1.f / sigma;
-  const long long n = static_cast<long long>(rows) * cols;
-  for (long long i = lb * 256LL + threadIdx.x; i < n; i += 256LL * nb) eff[i] = w[i] * inv_sigma;
-}
-
 __global__ void __launch_bounds__(256)
 prep_batched_kernel(const hg_prep_job* __restrict__ jobs, const int2* __restrict__ block_job) {
   extern __shared__ __align__(16) float dyn[];
@@ -381,9 +295,6 @@ prep_batched_kernel(const hg_prep_job* __restrict__ jobs, const int2* __restrict
     case HG_JOB_DISC_DGRAD_TILE: job_disc_dgrad_tile(j, bj.y, dyn); break;
     case HG_JOB_FINISH_ROW: job_finish_row(j, bj.y, red, dyn); break;
     case HG_JOB_LOSS_SUM: job_loss_sum(j, bj.y, red); break;
-    case HG_JOB_SN_WTU: job_sn_wtu(j, bj.y); break;
-    case HG_JOB_SN_WV: job_sn_wv(j, bj.y, j.i[4], red); break;
-    case HG_JOB_SN_SCALE: job_sn_scale(j, bj.y, j.i[4], red); break;
     default: break;
   }
 }

@@ -799,120 +799,6 @@ sn_bwd_apply_kernel(const float* __restrict__ d, const float* __restrict__ u, co
   }
 }
 
-// ---- spectral norm forward for ALL layers (and both calls of a step's forward) in ONE launch: a thread-block cluster
-// of 8 CTAs per layer walks the three stages of the power iteration with cluster barriers in between (the stages are
-// three dependent passes over W; as separate launches per layer they were 48 launches and, batched per stage, six
-// full-grid launches in a row on the step's critical lane).  CTA r of a cluster owns a contiguous block of rows.
-constexpr int kSnCluster = 8;
-constexpr int kSnThreads = 512;
-struct SnLayerDev {
-  const float* w; float* u; float* v;
-  float* eff[2];
-  float* ws[2];          // per call: [t: cols][s: rows][sigma][u_copy: rows][v_copy: cols], t zeroed by the host
-  int rows, cols;
-};
-struct SnClusterArgs {
-  SnLayerDev layer[8];
-  int nlayers, ncalls, iterate;
-};
-__device__ __forceinline__ float block_sum512(float v, float* red) {
-  v = warp_sum(v);
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) red[w] = v;
-  __syncthreads();
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < kSnThreads / 32; ++i) s += red[i];
-  __syncthreads();
-  return s;
-}
-__device__ __forceinline__ void cluster_barrier_mem() {
-  __threadfence();                      // global writes (t atomics, s, u, v) visible before the peers pass the barrier
-  hg::cluster_sync_all();
-}
-__global__ void __cluster_dims__(kSnCluster, 1, 1) __launch_bounds__(kSnThreads)
-sn_cluster_kernel(const SnClusterArgs a) {
-  __shared__ float red[kSnThreads / 32];
-  const int li = blockIdx.x / kSnCluster;
-  const int rank = static_cast<int>(hg::cluster_ctarank());
-  const SnLayerDev& L = a.layer[li];
-  const int rows = L.rows, cols = L.cols;
-  const int per = (rows + kSnCluster - 1) / kSnCluster;
-  const int r0 = min(rows, rank * per), r1 = min(rows, r0 + per);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const float eps = 1e-12f;
-  for (int call = 0; call < a.ncalls; ++call) {
-    float* ws = L.ws[call];
-    float* t = ws;
-    float* sv = ws + cols;
-    float* sigma_out = ws + cols + rows;
-    float* u_copy = ws + cols + rows + 1;
-    float* v_copy = ws + cols + 2 * rows + 1;
-    if (a.iterate) {
-      // stage 1: t = W^T u over this CTA's rows (coalesced along the columns)
-      for (int c = tid; c < cols; c += kSnThreads) {
-        float acc = 0.f;
-        for (int r = r0; r < r1; ++r) acc += L.w[static_cast<size_t>(r) * cols + c] * __ldcg(L.u + r);
-        if (r1 > r0) atomicAdd(t + c, acc);
-      }
-      cluster_barrier_mem();
-    }
-    // stage 2: v = normalize(t) (or the stored v); s = W v for this CTA's rows (one warp per row)
-    float inv = 1.f;
-    const float* src = a.iterate ? t : L.v;
-    if (a.iterate) {
-      float ss = 0.f;
-      for (int c = tid; c < cols; c += kSnThreads) { const float x = __ldcg(t + c); ss += x * x; }
-      ss = block_sum512(ss, red);
-      inv = 1.f / fmaxf(sqrtf(ss), eps);
-    }
-    for (int r = r0 + warp; r < r1; r += kSnThreads / 32) {
-      const float* wr = L.w + static_cast<size_t>(r) * cols;
-      float acc = 0.f;
-      for (int c = lane; c < cols; c += 32) acc += wr[c] * __ldcg(src + c);
-      acc = warp_sum(acc);
-      if (lane == 0) sv[r] = acc * inv;
-    }
-    if (rank == 0) {
-      for (int c = tid; c < cols; c += kSnThreads) {
-        const float val = __ldcg(src + c) * inv;
-        v_copy[c] = val;
-        if (a.iterate) L.v[c] = val;    // the peers read t, not v, in this stage
-      }
-    }
-    cluster_barrier_mem();
-    // stage 3: u = normalize(s) (or the stored u), sigma = u . s, w_eff = W / sigma for this CTA's rows
-    float sigma;
-    if (a.iterate) {
-      float ss = 0.f;
-      for (int r = tid; r < rows; r += kSnThreads) { const float x = __ldcg(sv + r); ss += x * x; }
-      ss = block_sum512(ss, red);
-      const float invs = 1.f / fmaxf(sqrtf(ss), eps);
-      sigma = ss * invs;
-      if (rank == 0)
-        for (int r = tid; r < rows; r += kSnThreads) {
-          const float val = __ldcg(sv + r) * invs;
-          L.u[r] = val;
-          u_copy[r] = val;
-        }
-    } else {
-      float d = 0.f;
-      for (int r = tid; r < rows; r += kSnThreads) d += __ldcg(L.u + r) * __ldcg(sv + r);
-      sigma = block_sum512(d, red);
-      if (rank == 0)
-        for (int r = tid; r < rows; r += kSnThreads) u_copy[r] = __ldcg(L.u + r);
-    }
-    if (rank == 0 && tid == 0) *sigma_out = sigma;
-    const float inv_sigma = 1.f / sigma;
-    float* eff = L.eff[call];
-    const size_t lo = static_cast<size_t>(r0) * cols, hi = static_cast<size_t>(r1) * cols;
-    for (size_t i = lo + tid; i < hi; i += kSnThreads) eff[i] = L.w[i] * inv_sigma;
-    // the next call's stage 1 reads the u this call's rank 0 just wrote (the second call of a forward continues the
-    // power iteration from the first's u, v — src/models.py:236-244 calls d(y) then d(y_hat))
-    if (call + 1 < a.ncalls) cluster_barrier_mem();
-  }
-}
-
 int blocks_for(long long n, int per = 256) {
   long long b = (n + per - 1) / per;
   if (b > 148 * 16) b = 148 * 16;
@@ -1172,27 +1058,6 @@ extern "C" int hg_spectral_norm_fwd(const float* w, float* u, float* v, int rows
   count();
   const long long n = static_cast<long long>(rows) * cols;
   sn_scale_kernel<<<blocks_for(n, 1024), 256, 0, S(stream)>>>(w, sv, u, u_copy, rows, n, iterate, eps, w_eff, sigma_out);
-  HG_CHECK_CUDA(cudaGetLastError());
-  count();
-  return HG_OK;
-}
-
-extern "C" int hg_spectral_norm_fwd_all(const hg_sn_layer* host_layers, int nlayers, int ncalls, int iterate,
-                                        void* stream) {
-  HG_REQUIRE(host_layers && nlayers >= 1 && nlayers <= 8 && ncalls >= 1 && ncalls <= 2,
-             "hg_spectral_norm_fwd_all: 1..8 layers, 1..2 calls");
-  SnClusterArgs a{};
-  a.nlayers = nlayers; a.ncalls = ncalls; a.iterate = iterate ? 1 : 0;
-  for (int i = 0; i < nlayers; ++i) {
-    const hg_sn_layer& h = host_layers[i];
-    HG_REQUIRE(h.w && h.u && h.v && h.rows > 0 && h.cols > 0, "hg_spectral_norm_fwd_all: bad layer %d", i);
-    for (int c = 0; c < ncalls; ++c) HG_REQUIRE(h.eff[c] && h.ws[c], "hg_spectral_norm_fwd_all: layer %d call %d", i, c);
-    a.layer[i].w = h.w; a.layer[i].u = h.u; a.layer[i].v = h.v;
-    a.layer[i].eff[0] = h.eff[0]; a.layer[i].eff[1] = h.eff[1];
-    a.layer[i].ws[0] = h.ws[0]; a.layer[i].ws[1] = h.ws[1];
-    a.layer[i].rows = h.rows; a.layer[i].cols = h.cols;
-  }
-  sn_cluster_kernel<<<nlayers * kSnCluster, kSnThreads, 0, S(stream)>>>(a);     // __cluster_dims__(8, 1, 1)
   HG_CHECK_CUDA(cudaGetLastError());
   count();
   return HG_OK;

@@ -683,6 +683,10 @@ class _SubDiscTrainer:
             self.dwps.append(self.dwp_flat[off:off + n])
             off += n
         self._tables = {}
+        import os
+        # A/B switches for profiles/r02_summary.md: per-layer launches (the round-1 scheme) instead of the batched ones
+        self.batch_prep = os.environ.get("HG_BATCH_D_PREP", "1") != "0"
+        self.batch_finish = os.environ.get("HG_BATCH_D_FINISH", "1") != "0"
         self.scratch = torch.empty(max(m.weight_v.numel() if hasattr(m, "weight_v") and not self.spectral
                                        else m.weight_orig.numel() if self.spectral else m.weight.numel()
                                        for m in self.mods), dtype=torch.float32, device=device)
@@ -773,55 +777,14 @@ class _SubDiscTrainer:
         self._tables[part] = t.finalize()
         return t
 
-    def _sn_forward(self, parts: List[int], Ws: List[dict]) -> None:
-        """spectral-norm layers, for the consecutive calls `parts` of one forward: one power iteration per call in
-        train mode (u / v buffers updated in place, exactly like one forward of torch.nn.utils.spectral_norm; the
-        second call continues from the first's), sigma, w_eff = W / sigma — ONE launch for all layers and calls
-        (hg_spectral_norm_fwd_all: a thread-block cluster per layer).  Fills W["sn"][li] = (u, v, sigma of that call,
-        scratch) for the backward of that call's weights."""
-        import ctypes
-        training = bool(self.mods[0].training)
-        key = ("sn", tuple(parts), training)
-        ent = self.__dict__.setdefault("_sn_plans", {}).get(key)
-        if ent is None:
-            class SnLayer(ctypes.Structure):
-                _fields_ = [("w", ctypes.c_void_p), ("u", ctypes.c_void_p), ("v", ctypes.c_void_p),
-                            ("eff", ctypes.c_void_p * 2), ("ws", ctypes.c_void_p * 2), ("rows", ctypes.c_int32),
-                            ("cols", ctypes.c_int32)]
-            shapes = [(m.weight_orig.shape[0], m.weight_orig.numel() // m.weight_orig.shape[0]) for m in self.mods]
-            per = sum(2 * r + 2 * c + 1 for r, c in shapes)
-            ws = torch.zeros(len(parts) * per, dtype=torch.float32, device=self.device)
-            arr = (SnLayer * len(self.mods))()
-            views = [[] for _ in parts]
-            off = 0
-            for li, (m, (rows, cols)) in enumerate(zip(self.mods, shapes)):
-                n = 2 * rows + 2 * cols + 1
-                arr[li].w, arr[li].u, arr[li].v = m.weight_orig.data_ptr(), m.weight_u.data_ptr(), m.weight_v.data_ptr()
-                arr[li].rows, arr[li].cols = rows, cols
-                for ci, part in enumerate(parts):
-                    w = ws[ci * per + off: ci * per + off + n]
-                    arr[li].eff[ci] = self.wbufs[part]["eff"][li].data_ptr()
-                    arr[li].ws[ci] = w.data_ptr()
-                    views[ci].append((w[cols + rows + 1: cols + 2 * rows + 1], w[cols + 2 * rows + 1:],
-                                      w[cols + rows: cols + rows + 1], w[:cols]))
-                off += n
-            ent = self._sn_plans[key] = (arr, ws, views)
-        arr, ws, views = ent
-        if training:
-            ws.zero_()
-        _lib.check(_lib.lib().hg_spectral_norm_fwd_all(ctypes.addressof(arr), len(self.mods), len(parts),
-                                                       1 if training else 0, _stream()), "hg_spectral_norm_fwd_all")
-        for ci, W in enumerate(Ws):
-            for li, v in enumerate(views[ci]):
-                W["sn"][li] = v
-
     def _prepare_weights(self, part: int) -> dict:
         """effective weights + forward banks of part `part` on the current stream: spectral-norm layers run their
         power iteration (one per call in train mode, like the reference's hook), then ONE batched launch folds /
         packs every layer"""
         W = self._weights(part, only_buffers=True)
         if self.spectral:
-            self._sn_forward([part], [W])
+            for li in range(len(self.mods)):
+                self._weights_layer(W, self.wbufs[part], li, pack=False)
         self._table(part).launch("fwd")
         return W
 
@@ -931,13 +894,28 @@ class _SubDiscTrainer:
         # their fold / power-iteration / pack chains are spread over the prep lanes (part 0 before part 1 per layer).
         if self.spectral or not self.fwd_valid:
             if self.spectral:
-                # part 0 before part 1: the second call's power iteration continues from the first's u, v
+                # the power iterations of the layers are independent chains of three small kernels (part 0 before part 1
+                # per layer: the second call continues from the first's u, v): side by side on the prep lanes.  (Batched
+                # per stage over all layers, or as one cluster launch, they were slower: a many-block launch on this
+                # lane waits for whole tensor-core kernels of the other lanes to drain — profiles/r02_summary.md.)
                 Ws = [self._weights(pi, only_buffers=True) for pi in range(len(parts))]
-                self._sn_forward(list(range(len(parts))), Ws)
+                self.prep.fork()
+                for li in range(len(self.mods)):
+                    with self.prep.lane(li):
+                        for pi, W in enumerate(Ws):
+                            self._weights_layer(W, self.wbufs[pi], li, pack=False)
+                self.prep.join()
                 for pi in range(len(parts)):
                     self._table(pi).launch("fwd")
-            else:
+            elif self.batch_prep:
                 Ws = [self._prepare_weights(0)]
+            else:
+                Ws = [self._weights(0, only_buffers=True)]
+                self.prep.fork()
+                for li in range(len(self.mods)):
+                    with self.prep.lane(li):
+                        self._weights_layer(Ws[0], self.wbufs[0], li)
+                self.prep.join()
             self.W_cached = Ws[-1]
             self.fwd_valid = True
         else:
@@ -1068,11 +1046,15 @@ class _SubDiscTrainer:
 
     def _pack_dgrad(self, W, part: int = 0) -> None:
         if self.spectral or not self.dgrad_valid:
-            t = self._table(part)
-            if t.has("dgrad"):
-                t.launch("dgrad")
-            for i in self.untiled:
-                self._bwd_bank(part)[i].pack(W["eff"][1 + i])
+            if self.batch_prep:
+                t = self._table(part)
+                if t.has("dgrad"):
+                    t.launch("dgrad")
+                for i in self.untiled:
+                    self._bwd_bank(part)[i].pack(W["eff"][1 + i])
+            else:
+                for bl, w_eff in zip(self._bwd_bank(part), W["eff"][1:-1]):
+                    bl.pack(w_eff)
             self.dgrad_valid = True
 
     # ---- one module call under torch autograd (autograd.py): forward with its own activation / weight slot ---------
@@ -1187,19 +1169,25 @@ class _SubDiscTrainer:
                                                  nseq * rows_out, nseq * rows_out, layer.groups_eff, layer.cout,
                                                  layer.k, layer.stride, 1, layer.pad, self.dwps[li].data_ptr(),
                                                  0 if sn else 1, st), "hg_conv1d_wgrad")
+                    cin_g = layer.cin // layer.groups
+                    order = (c_int * layer.k)(*layer.order)
                     if sn:
-                        cin_g = layer.cin // layer.groups
-                        order = (c_int * layer.k)(*layer.order)
                         _lib.check(L.hg_unpack_wgrad_conv(self.dwps[li].data_ptr(), layer.cout, cin_g, layer.k,
                                                           layer.cout, layer.cin_tile, layer.cout // layer.groups,
                                                           layer.merge, order, self.scratch.data_ptr(), st),
                                    "hg_unpack_wgrad_conv")
                         self._route(L, m, self.scratch, layer.cout, cin_g * layer.k, W, 1 + li, True)
+                    elif not self.batch_finish:
+                        g, v = _g_v(m)          # unpack + weight_norm backward in one launch, accumulating
+                        _lib.check(L.hg_wgrad_finish_conv(self.dwps[li].data_ptr(), layer.cout, cin_g, layer.k,
+                                                          layer.cout, layer.cin_tile, layer.cout // layer.groups,
+                                                          layer.merge, order, v.data_ptr(), g.data_ptr(), 1,
+                                                          _gb(v).data_ptr(), _gb(g).data_ptr(), st), "hg_wgrad_finish_conv")
                 side(layer_grads)
             bwd[li].dgrad(L, d_out, nseq, h_out, rows_out, rows_in, a_in[seq0:],
                           a_in[seq0 - nr:] if fm else None, nfm[li] if fm else 0.0, G["grad"][li][seq0:], _stream(),
                           flat_h_in=h_in, bias_dst=bias_of(li), pre_add=pre[li])
-        if want_wgrad and not self.spectral:
+        if want_wgrad and not self.spectral and self.batch_finish:
             side(lambda: self._table(part).launch("finish"))     # every wide layer's unpack + weight_norm backward
         # first conv (Cin = 1)
         k0, s0, p0, c0 = self.first

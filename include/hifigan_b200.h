@@ -313,22 +313,6 @@ int hg_spectral_norm_fwd(const float* w, float* u, float* v, int rows, int cols,
                          float* sigma_out, float* u_copy, float* v_copy, float* ws, void* stream);
 int hg_spectral_norm_bwd(const float* dw_eff, const float* w_eff, const float* u, const float* v, const float* sigma,
                          int rows, int cols, int accumulate, float* dw_orig, float* ws, void* stream);
-/* hg_spectral_norm_fwd_all — hg_spectral_norm_fwd for up to 8 layers and up to two consecutive calls (the d(y), d(y_hat)
- * pair of one MultiScaleDiscriminator forward, src/models.py:236-244: the second call's power iteration continues from
- * the first's u, v) in ONE launch: a thread-block cluster of 8 CTAs per layer, cluster barriers between the three
- * dependent passes over W.  host_layers is a HOST array; per call c: eff[c] receives W / sigma_c, ws[c] (fp32,
- * 2*rows + 2*cols + 1 floats) is laid out [t: cols][s: rows][sigma][u_copy: rows][v_copy: cols] and must have its t
- * part zeroed beforehand when iterate != 0. */
-typedef struct hg_sn_layer {
-  const float* w;
-  float* u;
-  float* v;
-  float* eff[2];
-  float* ws[2];
-  int32_t rows, cols;
-} hg_sn_layer;
-int hg_spectral_norm_fwd_all(const hg_sn_layer* host_layers, int nlayers, int ncalls, int iterate, void* stream);
-
 /* ------------------------------------------------------------------------------------------
  * Batched weight preparation / weight-gradient finishing: ONE launch for many layers.
  *
@@ -367,17 +351,10 @@ int hg_spectral_norm_fwd_all(const hg_sn_layer* host_layers, int nlayers, int nc
  *                          hg_l1_sum_bf16 for many tensors at once).  src0 a, src1 b.  i = {mode (0: fp32 |a - b|,
  *                          1: fp32 (c - a)^2, 2: bf16 |a - b| counted in 16-byte groups), n low 32 bits, n high 32
  *                          bits, chunk, c as float bits}
- *   HG_JOB_SN_WTU / _WV / _SCALE  the three stages of hg_spectral_norm_fwd, each its own launch (phase) over all
- *                          spectral-norm layers.  src0 W fp32 [rows][cols], src1 u, src2 v (both updated in place when
- *                          iterate), dst0 w_eff, dst1 ws fp32 [t: cols][s: rows][sigma][u_copy: rows][v_copy: cols] with
- *                          t zeroed beforehand.  i = {rows, cols, iterate, WTU blocks along the columns, blocks of
- *                          this job}; blocks: WTU ceil(cols/256) * ceil(rows/64), WV min(ceil(rows/8), 64), SCALE
- *                          min(ceil(rows*cols/1024), 256)
  */
 enum {
   HG_JOB_GEN_CONV = 0, HG_JOB_GEN_CONVTR = 1, HG_JOB_GEN_POST = 2, HG_JOB_DISC_ROW = 3, HG_JOB_TRANSPOSE_TILE = 4,
-  HG_JOB_DISC_DGRAD_TILE = 5, HG_JOB_FINISH_ROW = 6, HG_JOB_LOSS_SUM = 7, HG_JOB_SN_WTU = 8, HG_JOB_SN_WV = 9,
-  HG_JOB_SN_SCALE = 10
+  HG_JOB_DISC_DGRAD_TILE = 5, HG_JOB_FINISH_ROW = 6, HG_JOB_LOSS_SUM = 7
 };
 typedef struct hg_prep_job {
   const void* src0;

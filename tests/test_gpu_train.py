@@ -592,50 +592,6 @@ def test_spectral_norm_kernels_vs_torch(H):
         assert torch.equal(u, u0) and torch.allclose(eff.view_as(m.weight), m.weight.detach(), rtol=1e-4, atol=1e-6)
 
 
-def test_spectral_norm_cluster_kernel_vs_torch(H):
-    """hg_spectral_norm_fwd_all (one launch, a thread-block cluster per layer, two consecutive calls) against
-    torch.nn.utils.spectral_norm run twice: effective weights of both calls, the in-place u / v buffers, and the
-    per-call u, v, sigma copies the backward needs."""
-    import ctypes
-    from hifigan_b200 import _lib
-    L = _lib.lib()
-    dev = torch.device("cuda")
-
-    class SnLayer(ctypes.Structure):
-        _fields_ = [("w", ctypes.c_void_p), ("u", ctypes.c_void_p), ("v", ctypes.c_void_p), ("eff", ctypes.c_void_p * 2),
-                    ("ws", ctypes.c_void_p * 2), ("rows", ctypes.c_int32), ("cols", ctypes.c_int32)]
-    shapes = [(128, 1, 15), (1024, 64, 41), (1, 1024, 3), (256, 8, 41), (1024, 1024, 5)]
-    for iterate in (1, 0):
-        mods, keep = [], []
-        arr = (SnLayer * len(shapes))()
-        for i, shape in enumerate(shapes):
-            torch.manual_seed(sum(shape))
-            m = torch.nn.utils.spectral_norm(torch.nn.Conv1d(shape[1], shape[0], shape[2])).to(dev)
-            m.train(bool(iterate))
-            rows, cols = shape[0], shape[1] * shape[2]
-            w, u, v = m.weight_orig.detach().clone(), m.weight_u.detach().clone(), m.weight_v.detach().clone()
-            effs = [torch.empty(rows, cols, device=dev) for _ in range(2)]
-            wss = [torch.zeros(2 * rows + 2 * cols + 1, device=dev) for _ in range(2)]
-            arr[i].w, arr[i].u, arr[i].v, arr[i].rows, arr[i].cols = w.data_ptr(), u.data_ptr(), v.data_ptr(), rows, cols
-            for c in range(2):
-                arr[i].eff[c], arr[i].ws[c] = effs[c].data_ptr(), wss[c].data_ptr()
-            mods.append(m)
-            keep.append((w, u, v, effs, wss, rows, cols))
-        _lib.check(L.hg_spectral_norm_fwd_all(ctypes.addressof(arr), len(shapes), 2, iterate, _st()))
-        torch.cuda.synchronize()
-        for m, shape, (w, u, v, effs, wss, rows, cols) in zip(mods, shapes, keep):
-            for c in range(2):
-                x = torch.randn(1, shape[1], 20, device=dev)
-                m(x)                                   # one (more) power iteration in train mode, builds m.weight
-                assert torch.allclose(effs[c].view_as(m.weight), m.weight.detach(), rtol=2e-4, atol=1e-6), (shape, c)
-                ws = wss[c]
-                sigma = torch.dot(m.weight_u, torch.mv(m.weight_orig.detach().flatten(1), m.weight_v))
-                assert torch.allclose(ws[cols + rows], sigma, rtol=2e-4)
-                assert torch.allclose(ws[cols + rows + 1: cols + 2 * rows + 1], m.weight_u, rtol=2e-4, atol=1e-6)
-                assert torch.allclose(ws[cols + 2 * rows + 1:], m.weight_v, rtol=2e-4, atol=1e-6)
-            assert torch.allclose(u, m.weight_u, rtol=2e-4, atol=1e-6) and torch.allclose(v, m.weight_v, rtol=2e-4, atol=1e-6)
-
-
 def test_train_driver_checkpoints_and_resumes(H, tmp_path):
     """hifigan_b200.train_loop (UPSTREAM train.py's command line): trains on a tiny synthetic wav
     set, writes g_* / do_* files in the reference's format at the configured cadence, validates, and a second run
