@@ -84,11 +84,11 @@ def pair():
                                           c, k, d, 0.1, 0, 0, 1.0, out.data_ptr(), 0, 0.1, st()), "hg_resblock_pair_fwd")
         torch.cuda.synchronize()
         xf = x.float().transpose(1, 2)
-        t1 = F.conv1d(F.leaky_relu(xf, 0.1), p1.float().permute(1, 2, 0).contiguous(), b1, dilation=d,
-                      padding=(k - 1) * d // 2)
+        xa = F.leaky_relu(x.float(), 0.1).bfloat16().float().transpose(1, 2)      # rounded where the kernel rounds
+        t1 = F.conv1d(xa, p1.float().permute(1, 2, 0).contiguous(), b1, dilation=d, padding=(k - 1) * d // 2)
         t1 = F.leaky_relu(t1, 0.1).bfloat16().float()
         ref = (F.conv1d(t1, p2.float().permute(1, 2, 0).contiguous(), b2, padding=(k - 1) // 2) + xf).transpose(1, 2)
-        assert bool(((out.float() - ref).abs() <= 2.0 ** -6 * ref.abs() + 4e-3).all()), (c, k, d)
+        assert bool(((out.float() - ref).abs() <= 2.0 ** -8 * ref.abs() + 1.5e-2).all()), (c, k, d)
     print("pair ok", flush=True)
 
 
