@@ -111,7 +111,8 @@ _SIGNATURES = {
     "hg_convtr1d_geometry": (c_int, [c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
     "hg_pack_convtr1d_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hg_conv1d_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                              c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_float, c_void_p]),
+                              c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_float, c_void_p, c_int,
+                              c_void_p]),
     "hg_conv1d_tap_order": (c_int, [c_int, c_int, c_int, POINTER(c_int)]),
     "hg_conv1d_general_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                       c_int, c_int, c_int, c_void_p, c_float, c_void_p, c_int, c_int, c_void_p]),
@@ -128,7 +129,7 @@ _SIGNATURES = {
     "hg_resblock_single_supported": (c_int, [c_int, c_int, c_int]),
     "hg_resblock_pair_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                      c_int, c_float, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_float,
-                                     c_void_p]),
+                                     c_void_p, c_int, c_void_p]),
     "hg_float_to_int16": (c_int, [c_void_p, ctypes.c_longlong, c_float, c_void_p, c_void_p]),
     "hg_loss_sum": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_float, c_void_p, c_void_p]),
     "hg_segment_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),

@@ -86,12 +86,18 @@ struct ConvArgs {
   // every channel) and added to up to three destinations (the last convs of the MRF branches share one gradient).
   float* colsum[3];
   int colsum_mod;
+  // Ragged batches (length-bucketed inference): batch item b is only item_len[b] * item_mul rows long; the rows
+  // between that and `t` are stored as ZEROS, so that the next layer reads exactly the zero padding it would see if
+  // the item were run alone (results stay bit-identical to the per-item call).  NULL: every item is t rows long.
+  const int* item_len;
+  int item_mul;
 };
 
 // One 16-column group of one accumulator row: everything the epilogue does between the TMEM load and the
 // global stores.  `v` leaves holding the final fp32 values (zero for rows that are not stored).
-__device__ __forceinline__ void epi_group(const ConvArgs& p, bool valid, size_t off, int ch, const uint32_t (&raw)[16],
-                                          const hg::U8* r0, const hg::U8* r1, const hg::U8* r2, float (&v)[16]) {
+__device__ __forceinline__ void epi_group(const ConvArgs& p, bool valid, bool keep, size_t off, int ch,
+                                          const uint32_t (&raw)[16], const hg::U8* r0, const hg::U8* r1,
+                                          const hg::U8* r2, float (&v)[16]) {
   if (!valid) {
 #pragma unroll
     for (int e = 0; e < 16; ++e) v[e] = 0.f;
@@ -129,7 +135,7 @@ __device__ __forceinline__ void epi_group(const ConvArgs& p, bool valid, size_t 
   if (p.res1) hg::add_bf16x16(v, r1 ? *r1 : hg::ldg256(p.res1 + off));
   if (p.res2) hg::add_bf16x16(v, r2 ? *r2 : hg::ldg256(p.res2 + off));
 #pragma unroll
-  for (int e = 0; e < 16; ++e) v[e] *= p.scale;
+  for (int e = 0; e < 16; ++e) v[e] = keep ? v[e] * p.scale : 0.f;     // rows past a ragged item's end: zeros
   if (p.out_raw) {
     hg::U8 o;
 #pragma unroll
@@ -419,6 +425,7 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       const int t = it.tt * kTileM + row;
       bool valid = t < p.t;
       if (p.seq_pitch) valid = valid && ((t % p.seq_pitch) * p.seq_mul + (nt * NT) / p.seq_div < p.seq_valid);
+      const bool keep = !p.item_len || t < __ldg(p.item_len + b) * p.item_mul;
       const int ch0 = nt * NT + col0;
       const size_t off = (static_cast<size_t>(b) * p.t_pitch + (valid ? t : 0)) * p.cout + ch0;
       // residual prefetch: issued before the accumulator wait so its latency hides under the MMAs
@@ -452,7 +459,7 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         hg::tmem_ld_32x16(taddr, raw);
         hg::tmem_ld_wait();
         float v[16];
-        epi_group(p, valid, off + g * 16, ch0 + g * 16, raw, &rpre[g], kPreAll ? &rpre1[kPreAll ? g : 0] : nullptr,
+        epi_group(p, valid, keep, off + g * 16, ch0 + g * 16, raw, &rpre[g], kPreAll ? &rpre1[kPreAll ? g : 0] : nullptr,
                   kPreAll ? &rpre2[kPreAll ? g : 0] : nullptr, v);
         if (p.colsum[0]) epi_colsum16(v, lane, csum + col0 + g * 16);
       }
@@ -661,6 +668,7 @@ conv1d_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       const int t = (2 * ptt + static_cast<int>(rank)) * kTileM + row;
       bool valid = t < p.t;
       if (p.seq_pitch) valid = valid && ((t % p.seq_pitch) * p.seq_mul + (nt * NT) / p.seq_div < p.seq_valid);
+      const bool keep = !p.item_len || t < __ldg(p.item_len + b) * p.item_mul;
       const int ch0 = nt * NT + col0;
       const size_t off = (static_cast<size_t>(b) * p.t_pitch + (valid ? t : 0)) * p.cout + ch0;
       hg::U8 rpre[kGroups16];
@@ -690,7 +698,7 @@ conv1d_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         hg::tmem_ld_32x16(taddr, raw);
         hg::tmem_ld_wait();
         float v[16];
-        epi_group(p, valid, off + g * 16, ch0 + g * 16, raw, &rpre[g], kPreAll ? &rpre1[kPreAll ? g : 0] : nullptr,
+        epi_group(p, valid, keep, off + g * 16, ch0 + g * 16, raw, &rpre[g], kPreAll ? &rpre1[kPreAll ? g : 0] : nullptr,
                   kPreAll ? &rpre2[kPreAll ? g : 0] : nullptr, v);
         if (p.colsum[0]) epi_colsum16(v, lane, csum + col0 + g * 16);
       }
@@ -805,6 +813,8 @@ struct ConvExtra {
   const void* pre_add = nullptr;
   float* colsum[3] = {nullptr, nullptr, nullptr};
   int colsum_mod = 0;     // 0: the launch's output channel count
+  const int* item_len = nullptr;
+  int item_mul = 1;
 };
 
 int conv_forward(const void* x, const void* w_packed, const float* bias, int batch, int t_in_rows,
@@ -913,6 +923,7 @@ int conv_forward(const void* x, const void* w_packed, const float* bias, int bat
   p.pre_add = static_cast<const __nv_bfloat16*>(ex.pre_add);
   for (int i = 0; i < 3; ++i) p.colsum[i] = ex.colsum[i];
   p.colsum_mod = ex.colsum_mod > 0 ? ex.colsum_mod : cout;
+  p.item_len = ex.item_len; p.item_mul = ex.item_mul;
   HG_REQUIRE(!ex.colsum[1] || ex.colsum[0], "conv: bias-gradient destinations must be filled from slot 0");
   p.seq_div = ex.seq_div > 0 ? ex.seq_div : (1 << 30);
   HG_REQUIRE(ex.seq_pitch >= 0 && (ex.seq_pitch == 0 || batch == 1), "conv: flat sequences need batch == 1");
@@ -968,14 +979,17 @@ int conv_forward(const void* x, const void* w_packed, const float* bias, int bat
 extern "C" int hg_conv1d_fwd(const void* x, const void* w_packed, const float* bias, int batch, int t,
                              int cin, int cout, int ktaps, int dilation, int pad_left,
                              const void* res0, const void* res1, const void* res2, float scale,
-                             void* out_raw, void* out_act, float act_slope, void* stream) {
+                             void* out_raw, void* out_act, float act_slope, const int* item_len, int item_mul,
+                             void* stream) {
   HG_REQUIRE(cout > 0 && cout % 32 == 0, "hg_conv1d_fwd: cout=%d must be a multiple of 32", cout);
   HG_REQUIRE(cin > 0 && cin % 32 == 0, "hg_conv1d_fwd: cin=%d must be a multiple of 32", cin);
   HG_REQUIRE(ktaps > 0 && dilation > 0 && 128 + (ktaps - 1) * dilation <= 256,
              "hg_conv1d_fwd: halo too large for one TMA box (taps=%d dilation=%d)", ktaps, dilation);
   const int n_tile = (cout % 256 == 0) ? 256 : (cout % 128 == 0) ? 128 : (cout % 64 == 0) ? 64 : 32;
+  ConvExtra ex;
+  ex.item_len = item_len; ex.item_mul = item_mul > 0 ? item_mul : 1;
   return conv_forward(x, w_packed, bias, batch, t, cin, t, t, cin, cout, n_tile, 0, ktaps, 1, dilation, pad_left,
-                      res0, res1, res2, scale, out_raw, out_act, act_slope, stream);
+                      res0, res1, res2, scale, out_raw, out_act, act_slope, stream, ex);
 }
 
 extern "C" int hg_conv1d_tap_order(int ktaps, int stride, int pad_left, int* host_order) {

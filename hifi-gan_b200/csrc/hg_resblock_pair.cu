@@ -58,6 +58,10 @@ struct PairArgs {
   float scale, in_slope, out_slope;
   __nv_bfloat16* out_raw;
   __nv_bfloat16* out_act;
+  // ragged batches: item b is item_len[b] * item_mul rows long; the intermediate is zero beyond that (it is conv2's
+  // zero padding when the item runs alone) and the output rows up to t are stored as zeros.  NULL: all items t rows.
+  const int* item_len;
+  int item_mul;
 };
 
 struct PairBarriers {
@@ -271,16 +275,18 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       const float* bias = bars->b1;
       const uint32_t swz = (C == 64) ? (row & 7) : ((row >> 1) & 3);
       int tt = blockIdx.x % p.tiles_t;   // time-tile index of the current item, advanced without divisions
-      const int tt_step = gridDim.x % p.tiles_t;
+      int bb = blockIdx.x / p.tiles_t;   // its batch item
+      const int tt_step = gridDim.x % p.tiles_t, b_step = gridDim.x / p.tiles_t;
       for (int i = 0; i < (kSingle ? 0 : n_local); ++i) {
         const uint32_t a = i & 1u, ph = (i >> 1) & 1u;
         hg::mbar_wait(&bars->acc1_full[a], ph);
         hg::mbar_wait(&bars->t1_empty[a], ph ^ 1u);
         hg::tc_fence_after();
+        const int t_item = p.item_len ? min(p.t, __ldg(p.item_len + bb) * p.item_mul) : p.t;
         for (int m = 0; m < S; ++m) {
           const int grow = m * kM + row;                       // row of the item's t1 tile
           const int time = tt * p.r_out - p.pad2 + grow;       // its time step
-          const bool inside = time >= 0 && time < p.t;
+          const bool inside = time >= 0 && time < t_item;
           uint8_t* trow = t1_buf + a * p.t1_slot_bytes + static_cast<uint32_t>(grow) * kRowBytes;
 #pragma unroll
           for (int g = 0; g < kG; ++g) {
@@ -311,8 +317,8 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         hg::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) hg::mbar_arrive(&bars->t1_full[a]);
-        tt += tt_step;
-        if (tt >= p.tiles_t) tt -= p.tiles_t;
+        tt += tt_step; bb += b_step;
+        if (tt >= p.tiles_t) { tt -= p.tiles_t; ++bb; }
       }
     } else {
       // ---- E2: y = (acc2 + b2 + x + res1 + res2) * scale  ->  global
@@ -326,10 +332,11 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       // were the single largest cost of this warp role (clock64 traces).
       int n_tt = blockIdx.x % p.tiles_t, n_b = blockIdx.x / p.tiles_t, n_m = 0;
       const int tt_step = gridDim.x % p.tiles_t, b_step = gridDim.x / p.tiles_t;
-      auto next_unit_off = [&](bool& valid) -> size_t {
+      auto next_unit_off = [&](bool& valid, bool& keep) -> size_t {
         const int grow = n_m * kM + row;
         const int time = n_tt * p.r_out + grow;
         valid = grow < p.r_out && time < p.t;
+        keep = !p.item_len || time < __ldg(p.item_len + n_b) * p.item_mul;
         const size_t o = (static_cast<size_t>(n_b) * p.t + (valid ? time : 0)) * C + col0;
         if (++n_m == S) {
           n_m = 0;
@@ -339,11 +346,11 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         return o;
       };
       hg::U8 rcur[kG], rnext[kG];
-      bool valid = false, valid_next = false;
+      bool valid = false, valid_next = false, keep = true, keep_next = true;
       size_t off = 0, off_next = 0;
       const int n_units = n_local * S;
       if (n_units > 0) {
-        off_next = next_unit_off(valid_next);
+        off_next = next_unit_off(valid_next, keep_next);
         if (valid_next) {
 #pragma unroll
           for (int g = 0; g < kG; ++g) rnext[g] = hg::ldg256(p.x + off_next + g * 16);
@@ -352,11 +359,11 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       int i = 0, m = 0;
       for (int u = 0; u < n_units; ++u) {
         const uint32_t a = i & 1u, ph = (i >> 1) & 1u;
-        off = off_next; valid = valid_next;
+        off = off_next; valid = valid_next; keep = keep_next;
 #pragma unroll
         for (int g = 0; g < kG; ++g) rcur[g] = rnext[g];
         if (u + 1 < n_units) {
-          off_next = next_unit_off(valid_next);
+          off_next = next_unit_off(valid_next, keep_next);
           if (valid_next) {
 #pragma unroll
             for (int g = 0; g < kG; ++g) rnext[g] = hg::ldg256(p.x + off_next + g * 16);
@@ -402,7 +409,7 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             if (p.res1) hg::add_bf16x16(v, kPreRes ? r1[kPreRes ? g : 0] : hg::ldg256(p.res1 + off + g * 16));
             if (p.res2) hg::add_bf16x16(v, kPreRes ? r2[kPreRes ? g : 0] : hg::ldg256(p.res2 + off + g * 16));
 #pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] *= p.scale;
+            for (int e = 0; e < 16; ++e) v[e] = keep ? v[e] * p.scale : 0.f;   // rows past a ragged item's end: zeros
             if (p.out_raw) {
               hg::U8 o;
 #pragma unroll
@@ -491,7 +498,7 @@ extern "C" int hg_resblock_pair_fwd(const void* x, const void* w1_packed, const 
                                     const void* w2_packed, const float* b2, int batch, int t, int c,
                                     int ktaps, int dil1, float in_slope, const void* res1,
                                     const void* res2, float scale, void* out_raw, void* out_act,
-                                    float out_slope, void* stream) {
+                                    float out_slope, const int* item_len, int item_mul, void* stream) {
   const int single = w2_packed == nullptr;   // ResBlock2 step: one conv + residual
   HG_REQUIRE(x && w1_packed && b1 && (single || b2), "hg_resblock_pair_fwd: null input");
   HG_REQUIRE(out_raw || out_act, "hg_resblock_pair_fwd: no output requested");
@@ -518,6 +525,7 @@ extern "C" int hg_resblock_pair_fwd(const void* x, const void* w1_packed, const 
   p.scale = scale; p.in_slope = in_slope; p.out_slope = out_slope;
   p.out_raw = static_cast<__nv_bfloat16*>(out_raw);
   p.out_act = static_cast<__nv_bfloat16*>(out_act);
+  p.item_len = item_len; p.item_mul = item_mul > 0 ? item_mul : 1;
 
   CUtensorMap tx, tw1, tw2;
   const int swz = c * 2;

@@ -4,10 +4,11 @@ src/inference_e2e.py:34-57 mel -> wav) — SURVEY.md §8(f) rank 1.
 Same command lines (`--input_wavs_dir / --input_mels_dir / --output_dir / --checkpoint_file`, config.json beside
 the checkpoint, src/inference.py:68-80), same output file names and the same int16 samples.  What changes is the
 schedule: the reference runs batch 1 per file with a blocking device-to-host copy of fp32 audio per file; here files
-of EQUAL frame count are stacked into one Generator call (the Generator is zero-padded at every layer, so only
-equal-length items can share a batch without changing anyone's edge samples — results stay bit-identical to the
-per-file call), the `* MAX_WAV_VALUE -> int16` conversion runs on the device (hg_float_to_int16) and the int16
-batch crosses to pinned host memory in one copy.
+are sorted by length and stacked into length-bucketed, RAGGED batches: the kernels take per-item lengths and treat
+the rows past an item's end as the zero padding it would see alone (hg_conv1d_fwd's item_len), so every file's
+samples stay bit-identical to the per-file call while a directory of different-length utterances still fills the
+GPU.  The `* MAX_WAV_VALUE -> int16` conversion runs on the device (hg_float_to_int16) and the int16 batch crosses to
+pinned host memory in one copy.
 
     python -m hifigan_b200.inference      --checkpoint_file cp/g_02500000 [--input_wavs_dir test_files]
     python -m hifigan_b200.inference e2e  --checkpoint_file cp/g_02500000 [--input_mels_dir test_mel_files]
@@ -39,20 +40,24 @@ def audio_to_int16(y: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def bucket_by_length(items: Iterable[Tuple[str, torch.Tensor]], max_batch: int) -> List[List[Tuple[str, torch.Tensor]]]:
-    """Group (name, mel [80, F]) items of equal F into batches of at most max_batch, keeping first-seen order."""
-    groups: Dict[int, List[Tuple[str, torch.Tensor]]] = defaultdict(list)
-    order: List[int] = []
-    for name, mel in items:
+def bucket_by_length(items: Iterable[Tuple[str, torch.Tensor]], max_batch: int,
+                     max_waste: float = 0.25) -> List[List[Tuple[str, torch.Tensor]]]:
+    """Length-bucketed batches of (name, mel [80, F]) items: sorted by frame count, a batch takes up to max_batch
+    neighbours as long as the padding it implies stays below max_waste of the batch (the Generator computes the padded
+    rows too; `lengths` keeps every item's samples bit-identical to a one-file call).  max_waste = 0: equal lengths only."""
+    ordered = sorted(items, key=lambda it: int(it[1].shape[-1]))
+    batches: List[List[Tuple[str, torch.Tensor]]] = []
+    cur: List[Tuple[str, torch.Tensor]] = []
+    total = 0
+    for name, mel in ordered:
         f = int(mel.shape[-1])
-        if f not in groups:
-            order.append(f)
-        groups[f].append((name, mel))
-    batches = []
-    for f in order:
-        g = groups[f]
-        for i in range(0, len(g), max_batch):
-            batches.append(g[i:i + max_batch])
+        if cur and (len(cur) >= max_batch or 1.0 - (total + f) / (f * (len(cur) + 1)) > max_waste):
+            batches.append(cur)
+            cur, total = [], 0
+        cur.append((name, mel))
+        total += f
+    if cur:
+        batches.append(cur)
     return batches
 
 
@@ -62,13 +67,25 @@ def vocode(generator: Generator, batches, sampling_rate: int, output_dir: str, s
     if writer is None:
         from scipy.io.wavfile import write as writer
     written = []
+    dev = next(generator.parameters()).device
     for batch in batches:
-        x = torch.stack([m for _, m in batch]).to(next(generator.parameters()).device)
-        audio = audio_to_int16(generator(x).squeeze(1))                     # [B, T] int16 on the device
+        frames = [int(m.shape[-1]) for _, m in batch]
+        fmax = max(frames)
+        if min(frames) == fmax:
+            x = torch.stack([m for _, m in batch]).to(dev)
+            y = generator(x)
+        else:                                               # ragged batch: zero-padded mels + per-item lengths
+            x = torch.zeros(len(batch), batch[0][1].shape[0], fmax, dtype=torch.float32, device=dev)
+            for i, (_, m) in enumerate(batch):
+                x[i, :, : m.shape[-1]] = m.to(dev)
+            y = generator(x, lengths=torch.tensor(frames, dtype=torch.int32, device=dev))
+        audio = audio_to_int16(y.squeeze(1))                                 # [B, T] int16 on the device
         host = torch.empty(audio.shape, dtype=torch.int16).pin_memory()
         host.copy_(audio, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        for (name, _), row in zip(batch, host.numpy()):
+        hop = audio.shape[1] // fmax
+        for (name, _), row, f in zip(batch, host.numpy(), frames):
+            row = row[: f * hop]
             path = os.path.join(output_dir, os.path.splitext(name)[0] + suffix + ".wav")
             writer(path, sampling_rate, row)
             print(path)
@@ -119,7 +136,7 @@ def main(argv=None) -> None:
     parser.add_argument('--input_mels_dir', default='test_mel_files')
     parser.add_argument('--output_dir', default=None)
     parser.add_argument('--checkpoint_file', required=True)
-    parser.add_argument('--max_batch', type=int, default=64, help='files of equal length stacked per Generator call')
+    parser.add_argument('--max_batch', type=int, default=64, help='files stacked per Generator call (length-bucketed)')
     a = parser.parse_args(argv)
     if a.output_dir is None:
         a.output_dir = 'generated_files' if a.mode == 'wav' else 'generated_files_from_mel'

@@ -173,24 +173,25 @@ class _PackedConv:
 
 
 def _conv(L, x, pc: _PackedConv, batch: int, t: int, *, res=(None, None, None), scale=1.0,
-          out_raw=None, out_act=None, slope=LRELU_SLOPE) -> None:
+          out_raw=None, out_act=None, slope=LRELU_SLOPE, item=(0, 1)) -> None:
+    """item = (device pointer of int32 item lengths or 0, rows per length unit): ragged batches, see hg_conv1d_fwd"""
     p = [0 if r is None else r.data_ptr() for r in res]
     _lib.check(L.hg_conv1d_fwd(x.data_ptr(), pc.w.data_ptr(), pc.bias.data_ptr(), batch, t, pc.cin_p,
                                pc.w.shape[1], pc.taps, pc.dil, pc.pad_left, p[0], p[1], p[2], scale,
                                0 if out_raw is None else out_raw.data_ptr(),
-                               0 if out_act is None else out_act.data_ptr(), slope, _stream()),
+                               0 if out_act is None else out_act.data_ptr(), slope, item[0], item[1], _stream()),
                "hg_conv1d_fwd")
 
 
 def _pair(L, x, pc1: _PackedConv, pc2: _PackedConv, batch: int, t: int, *, res=(None, None), scale=1.0,
-          out_raw=None, out_act=None, slope=LRELU_SLOPE) -> None:
+          out_raw=None, out_act=None, slope=LRELU_SLOPE, item=(0, 1)) -> None:
     """One fused ResBlock1 step: conv2(lrelu(conv1(lrelu(x)) + b1)) + b2 + x (+ res) — hg_resblock_pair_fwd."""
     p = [0 if r is None else r.data_ptr() for r in res]
     w2, b2 = (0, 0) if pc2 is None else (pc2.w.data_ptr(), pc2.bias.data_ptr())   # None: one ResBlock2 step
     _lib.check(L.hg_resblock_pair_fwd(x.data_ptr(), pc1.w.data_ptr(), pc1.bias.data_ptr(), w2,
                                       b2, batch, t, pc1.cin_p, pc1.taps, pc1.dil, LRELU_SLOPE,
                                       p[0], p[1], scale, 0 if out_raw is None else out_raw.data_ptr(),
-                                      0 if out_act is None else out_act.data_ptr(), slope, _stream()),
+                                      0 if out_act is None else out_act.data_ptr(), slope, item[0], item[1], _stream()),
                "hg_resblock_pair_fwd")
 
 
@@ -215,7 +216,7 @@ def _block_plan(L, block: "nn.Module", packs: List[_PackedConv]) -> List[bool]:
 
 
 def _resblock_chain(L, block: "nn.Module", packs: List[_PackedConv], batch: int, t: int, c_p: int,
-                    x_raw, x_act, bufs: Dict[str, torch.Tensor], final) -> None:
+                    x_raw, x_act, bufs: Dict[str, torch.Tensor], final, item=(0, 1)) -> None:
     """Run one ResBlock (type 1: packs = [c1_0, c2_0, c1_1, ...]; type 2: packs = [c_0, c_1, ...]).
     `final(kw)` issues the LAST launch of the block (so the caller can fuse the MRF average): kw is either
     dict(pair=(pc1, pc2), x=raw_input) or dict(pc=conv, x=activated_input, res0=raw_residual).
@@ -234,10 +235,10 @@ def _resblock_chain(L, block: "nn.Module", packs: List[_PackedConv], batch: int,
             if last:
                 final(dict(pair=(pc1, pc2), x=cur_raw))
             else:
-                _pair(L, cur_raw, pc1, pc2, batch, t, out_raw=nr, out_act=na if want_act else None)
+                _pair(L, cur_raw, pc1, pc2, batch, t, out_raw=nr, out_act=na if want_act else None, item=item)
         else:
             if two_conv:
-                _conv(L, cur_act, packs[2 * i], batch, t, out_act=bufs["t1"])
+                _conv(L, cur_act, packs[2 * i], batch, t, out_act=bufs["t1"], item=item)
                 src, pc = bufs["t1"], packs[2 * i + 1]
             else:
                 src, pc = cur_act, packs[i]
@@ -245,7 +246,7 @@ def _resblock_chain(L, block: "nn.Module", packs: List[_PackedConv], batch: int,
                 final(dict(pc=pc, x=src, res0=cur_raw))
             else:
                 _conv(L, src, pc, batch, t, res=(cur_raw, None, None), out_raw=nr,
-                      out_act=na if (want_act or not two_conv) else None)
+                      out_act=na if (want_act or not two_conv) else None, item=item)
         cur_raw, cur_act = nr, na
 
 
@@ -444,9 +445,10 @@ class _GeneratorEngine:
     # Small workloads are launch-bound (64 launches per V1 forward): replay them as one CUDA graph.
     GRAPH_MAX_SAMPLES = 1 << 21
 
-    def forward(self, x: torch.Tensor, time_convs: bool = False) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, time_convs: bool = False, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
         """time_convs=True brackets the tensor-core conv launches (everything between the input transposition
-        and conv_post) with CUDA events on the launching stream -> self.last_conv_events (bench.py roofline)."""
+        and conv_post) with CUDA events on the launching stream -> self.last_conv_events (bench.py roofline).
+        lengths (int32 [B] on the device, frames per item): a ragged batch — see Generator.forward."""
         self.refresh()   # weight (re)packing stays outside any graph: it writes the same buffers in place
         b, c, frames = x.shape
         xin = x.contiguous()
@@ -455,10 +457,10 @@ class _GeneratorEngine:
         t_out = frames
         for pc in self.ups:
             t_out *= pc.stride
-        use_graph = (not time_convs and b * t_out <= self.GRAPH_MAX_SAMPLES
+        use_graph = (not time_convs and lengths is None and b * t_out <= self.GRAPH_MAX_SAMPLES
                      and not os.environ.get("HG_DISABLE_GRAPHS") and not torch.cuda.is_current_stream_capturing())
         if not use_graph:
-            return self._launch(xin, time_convs)
+            return self._launch(xin, time_convs, lengths)
         key = (b, frames, _FUSE_PAIRS)
         entry = self.graphs.get(key)
         if entry is None:
@@ -490,26 +492,30 @@ class _GeneratorEngine:
         graph.replay()
         return out
 
-    def _launch(self, xin: torch.Tensor, time_convs: bool) -> torch.Tensor:
+    def _launch(self, xin: torch.Tensor, time_convs: bool, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
         L = _lib.lib()
         gen = self.gen
         b, c, frames = xin.shape
         ws = self.workspace(b, frames)
+        lp = 0 if lengths is None else lengths.data_ptr()     # ragged batch: per-item frame counts (device int32)
+        mul = 1                                                # rows per frame at the current stage
         _lib.check(L.hg_ncl_to_nlc(xin.data_ptr(), b, c, frames, self.pre.cin_p, ws["mel"].data_ptr(), 0, 0.0,
                                    _stream()), "hg_ncl_to_nlc")
         if time_convs:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
         # conv_pre; its only consumer is leaky_relu -> ups[0] (models.py:101-104)
-        _conv(L, ws["mel"], self.pre, b, frames, out_act=ws["pre"])
+        _conv(L, ws["mel"], self.pre, b, frames, out_act=ws["pre"], item=(lp, mul))
         cur, t = ws["pre"], frames
         nk = gen.num_kernels
         for i, up in enumerate(self.ups):
             # the leaky_relu'd copy of the stage input is only needed by branches whose first step is unfused
             need_act = any(not _block_plan(L, gen.resblocks[i * nk + j], self.blocks[i * nk + j])[0]
                            for j in range(nk))
-            _conv(L, cur, up, b, t, out_raw=ws["x_raw"], out_act=ws["x_act"] if need_act else None)
+            # polyphase: one output row of this launch is `stride` samples, so its valid rows are the INPUT's
+            _conv(L, cur, up, b, t, out_raw=ws["x_raw"], out_act=ws["x_act"] if need_act else None, item=(lp, mul))
             t *= up.stride
+            mul *= up.stride
             c_p = up.cout_p
             last_stage = i == len(self.ups) - 1
             out_slope = 0.01 if last_stage else LRELU_SLOPE  # models.py:112 uses the default slope
@@ -529,11 +535,11 @@ class _GeneratorEngine:
                             others = tuple(ws[f"r{q}"] for q in range(nk - 1)) + (None,) * (3 - nk)
                         outs = dict(scale=1.0 / nk, out_act=ws["stage_out"], slope=out_slope)
                     if "pair" in kw:
-                        _pair(L, kw["x"], *kw["pair"], b, t, res=others, **outs)
+                        _pair(L, kw["x"], *kw["pair"], b, t, res=others, item=(lp, mul), **outs)
                     else:
-                        _conv(L, kw["x"], kw["pc"], b, t, res=(kw["res0"],) + others, **outs)
+                        _conv(L, kw["x"], kw["pc"], b, t, res=(kw["res0"],) + others, item=(lp, mul), **outs)
 
-                _resblock_chain(L, blk, packs, b, t, c_p, ws["x_raw"], ws["x_act"], ws, final)
+                _resblock_chain(L, blk, packs, b, t, c_p, ws["x_raw"], ws["x_act"], ws, final, item=(lp, mul))
             cur = ws["stage_out"]
         if time_convs:
             ev1.record()
@@ -579,12 +585,26 @@ class Generator(torch.nn.Module):
             engines[device] = eng
         return eng
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
         """mel [B,80,F] -> waveform [B,1,T], a fresh tensor per call like the reference.  (`self._engine(dev)
-        .forward(x)` returns the engine-owned buffer without the copy: the benchmark's device-resident path.)"""
+        .forward(x)` returns the engine-owned buffer without the copy: the benchmark's device-resident path.)
+
+        lengths (extension, inference only): int tensor [B] of frame counts for a RAGGED batch — item i is the mel
+        x[i, :, :lengths[i]] (the rest of its row is ignored) and its waveform is out[i, 0, :lengths[i] * hop]; every
+        layer treats the rows past an item's end as the zero padding the item would see if it ran alone, so the
+        samples are bit-identical to the reference's one-utterance-per-call schedule (src/inference.py:55)."""
         _require_cuda(x, "Generator.forward")
         if x.dim() != 3 or x.shape[1] != self.conv_pre.in_channels:
             raise ValueError(f"expected [B,{self.conv_pre.in_channels},F], got {tuple(x.shape)}")
+        if lengths is not None:
+            if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+                raise NotImplementedError("ragged batches are an inference feature: call under torch.no_grad()")
+            ln = torch.as_tensor(lengths).to(device=x.device, dtype=torch.int32).contiguous()
+            if ln.shape != (x.shape[0],) or int(ln.min()) < 1 or int(ln.max()) > x.shape[2]:
+                raise ValueError("lengths must be [B] frame counts within [1, F]")
+            # frames past an item's end must read as zero padding at conv_pre's input
+            mask = torch.arange(x.shape[2], device=x.device)[None, None, :] < ln[:, None, None]
+            return self._engine(x.device).forward(x * mask, lengths=ln).clone()
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
             # differentiable call (an UPSTREAM-style `loss.backward()` loop): one autograd.Function over the training
             # forward (every conv input kept) and the hand-written backward — autograd.py

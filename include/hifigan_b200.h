@@ -74,11 +74,16 @@ int hg_pack_convtr1d_weight(const float* v, const float* g, int cin, int cout, i
  * bf16 [ktaps][cout][cin]; bias fp32 [cout].  cin % 32 == 0, cout % 32 == 0.
  * The fused epilogue covers F.leaky_relu (models.py:36,38,64,103,112), the residual add (:41,67),
  * and the MRF branch average xs / num_kernels (:105-111).
+ *
+ * Ragged batches (the reference's drivers run one utterance per call, src/inference.py:55; stacking utterances of
+ * different lengths must not change anyone's samples): item_len (optional, device int32 [B]) gives every batch item
+ * its own length item_len[b] * item_mul <= t; rows between that and t are stored as ZEROS, so the next layer reads
+ * exactly the zero padding the item would see when run alone and results stay bit-identical to the per-item call.
  */
 int hg_conv1d_fwd(const void* x, const void* w_packed, const float* bias, int batch, int t, int cin,
                   int cout, int ktaps, int dilation, int pad_left, const void* res0,
                   const void* res1, const void* res2, float scale, void* out_raw, void* out_act,
-                  float act_slope, void* stream);
+                  float act_slope, const int* item_len, int item_mul, void* stream);
 
 /* hg_conv1d_general_fwd — strided and/or grouped Conv1d on the same tcgen05 kernel (the discriminator stacks:
  * DiscriminatorS src/models.py:195-204 — k=41, stride 1/2/4, groups 4/16; DiscriminatorP :133-140 — (5,1)
@@ -123,7 +128,7 @@ int hg_resblock_single_supported(int c, int ktaps, int dil1);
 int hg_resblock_pair_fwd(const void* x, const void* w1_packed, const float* b1, const void* w2_packed,
                          const float* b2, int batch, int t, int c, int ktaps, int dil1, float in_slope,
                          const void* res1, const void* res2, float scale, void* out_raw, void* out_act,
-                         float out_slope, void* stream);
+                         float out_slope, const int* item_len, int item_mul, void* stream);   /* item_*: hg_conv1d_fwd */
 
 /* ------------------------------------------------------------------------------------------
  * Discriminator ends (bandwidth-bound CUDA-core kernels).

@@ -55,7 +55,7 @@ def conv_case(L, b, t, cin, cout, k, d, mode, seed=0, with_res=True):
     pad = (k - 1) * d // 2
     _lib.check(L.hg_conv1d_fwd(x.data_ptr(), wp.data_ptr(), bias.data_ptr(), b, t, cin, cout, k, d, pad,
                                0 if res is None else res.data_ptr(), 0, 0, 0.5, out_raw.data_ptr(),
-                               out_act.data_ptr(), 0.1, st))
+                               out_act.data_ptr(), 0.1, 0, 1, st))
     torch.cuda.synchronize()
     wr = wp.float().permute(1, 2, 0).contiguous()  # [cout, cin, k] bf16-rounded
     ref = F.conv1d(x.float().transpose(1, 2), wr, bias, dilation=d, padding=pad).transpose(1, 2)
@@ -161,7 +161,7 @@ def stage_layers(b, frames):
         pad = (k - 1) * d // 2
         def run():
             _lib.check(L.hg_conv1d_fwd(x.data_ptr(), wp.data_ptr(), bias.data_ptr(), b, t, cin, cout, k, d, pad,
-                                       res.data_ptr(), 0, 0, 1.0, o1.data_ptr(), o2.data_ptr(), 0.1, st))
+                                       res.data_ptr(), 0, 0, 1.0, o1.data_ptr(), o2.data_ptr(), 0.1, 0, 1, st))
         for _ in range(2):
             run()
         torch.cuda.synchronize()
@@ -198,7 +198,7 @@ def stage_pairs(b, frames, debug=0):
                 def run():
                     _lib.check(L.hg_resblock_pair_fwd(x.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
                                                       b1.data_ptr(), b, t, c, k, d, 0.1, 0, 0, 1.0, o1.data_ptr(), 0,
-                                                      0.1, st))
+                                                      0.1, 0, 1, st))
                 for _ in range(2):
                     run()
                 torch.cuda.synchronize()

@@ -131,7 +131,7 @@ def convfloor():
         pad = (k - 1) * d // 2
         res = {}
         for name, fn in (("fwd", lambda: L.hg_conv1d_fwd(x.data_ptr(), w.data_ptr(), 0, b, t, c, c, k, d, pad, 0, 0, 0, 1.0,
-                                                         out.data_ptr(), 0, 0.1, st)),
+                                                         out.data_ptr(), 0, 0.1, 0, 1, st)),
                          ("wgrad", lambda: L.hg_conv1d_wgrad(x.data_ptr(), out.data_ptr(), b, t, c, t, t, 1, c, k, 1, d, pad,
                                                              dwp.data_ptr(), 1, st))):
             for _ in range(5):

@@ -76,7 +76,7 @@ def test_conv1d_fwd_vs_torch_fp32(H, case):
     pad = (k - 1) * d // 2
     _lib.check(L.hg_conv1d_fwd(x.data_ptr(), wp.data_ptr(), bias.data_ptr(), b, t, cin, cout, k, d, pad,
                                res[0].data_ptr(), res[1].data_ptr(), res[2].data_ptr(), 1.0 / 3,
-                               out_raw.data_ptr(), out_act.data_ptr(), 0.1, st))
+                               out_raw.data_ptr(), out_act.data_ptr(), 0.1, 0, 1, st))
     torch.cuda.synchronize()
     wr = wp.float().permute(1, 2, 0).contiguous()
     ref = F.conv1d(x.float().transpose(1, 2), wr, bias, dilation=d, padding=pad).transpose(1, 2)
@@ -90,9 +90,9 @@ def test_conv1d_rejects_bad_arguments(H):
     from hifigan_b200 import _lib
     L = _lib.lib()
     x = torch.zeros(1, 128, 64, dtype=torch.bfloat16, device="cuda")
-    rc = L.hg_conv1d_fwd(x.data_ptr(), x.data_ptr(), 0, 1, 128, 48, 64, 3, 1, 1, 0, 0, 0, 1.0, x.data_ptr(), 0, 0.1, 0)
+    rc = L.hg_conv1d_fwd(x.data_ptr(), x.data_ptr(), 0, 1, 128, 48, 64, 3, 1, 1, 0, 0, 0, 1.0, x.data_ptr(), 0, 0.1, 0, 1, 0)
     assert rc != 0 and b"multiple of 32" in L.hg_last_error()
-    rc = L.hg_conv1d_fwd(x.data_ptr(), x.data_ptr(), 0, 1, 128, 64, 64, 41, 5, 1, 0, 0, 0, 1.0, x.data_ptr(), 0, 0.1, 0)
+    rc = L.hg_conv1d_fwd(x.data_ptr(), x.data_ptr(), 0, 1, 128, 64, 64, 41, 5, 1, 0, 0, 0, 1.0, x.data_ptr(), 0, 0.1, 0, 1, 0)
     assert rc != 0 and b"halo" in L.hg_last_error()
 
 
@@ -125,7 +125,7 @@ def test_resblock_pair_vs_torch_fp32(H, c, k, d, b, t):
     out_act = torch.full((b, t, c), 7.0, dtype=torch.bfloat16, device=dev)
     _lib.check(L.hg_resblock_pair_fwd(x.data_ptr(), wp1.data_ptr(), b1.data_ptr(), wp2.data_ptr(), b2.data_ptr(),
                                       b, t, c, k, d, 0.1, r1.data_ptr(), r2.data_ptr(), 1.0 / 3,
-                                      out_raw.data_ptr(), out_act.data_ptr(), 0.01, st))
+                                      out_raw.data_ptr(), out_act.data_ptr(), 0.01, 0, 1, st))
     torch.cuda.synchronize()
     xa = F.leaky_relu(x.float(), 0.1).bfloat16().float().transpose(1, 2)
     t1 = F.conv1d(xa, wp1.float().permute(1, 2, 0).contiguous(), b1, dilation=d, padding=(k - 1) * d // 2)
@@ -158,7 +158,7 @@ def test_resblock_single_vs_torch_fp32(H, c, k, d, b, t):
     out_raw = torch.full((b, t, c), 7.0, dtype=torch.bfloat16, device=dev)
     out_act = torch.full((b, t, c), 7.0, dtype=torch.bfloat16, device=dev)
     _lib.check(L.hg_resblock_pair_fwd(x.data_ptr(), wp1.data_ptr(), b1.data_ptr(), 0, 0, b, t, c, k, d, 0.1,
-                                      r1.data_ptr(), 0, 0.5, out_raw.data_ptr(), out_act.data_ptr(), 0.1, st))
+                                      r1.data_ptr(), 0, 0.5, out_raw.data_ptr(), out_act.data_ptr(), 0.1, 0, 1, st))
     torch.cuda.synchronize()
     xa = F.leaky_relu(x.float(), 0.1).bfloat16().float().transpose(1, 2)
     y = F.conv1d(xa, wp1.float().permute(1, 2, 0).contiguous(), b1, dilation=d, padding=(k - 1) * d // 2)
@@ -732,6 +732,35 @@ def test_meldataset_class_matches_reference_rule(H, O, tmp_path):
             assert bool(((lin_g - lin_r).abs() <= 2e-3 * lin_r + 1e-6 * lin_r.max()).all())   # floor 60 dB below the peak
     with pytest.raises(ValueError, match="SR doesn't match"):
         H.MelDataset([files[0]], 8192, 1024, 80, 256, 1024, 16000, 0, 8000, shuffle=False)[0]
+
+
+@pytest.mark.parametrize("ver", ["v1", "v3"])
+def test_ragged_batch_is_bit_identical_to_per_item_calls(H, O, ver):
+    """`Generator(x, lengths=...)`: utterances of different lengths stacked in one call give, for every item, exactly
+    the samples of that item run alone (the reference's schedule, src/inference.py:55) — every layer treats the rows
+    past an item's end as zero padding.  Lengths straddle the 128-row tiles of every stage; the padded tails hold
+    garbage mel values on purpose."""
+    h = H.AttrDict(O.config(ver))
+    torch.manual_seed(21)
+    G = H.Generator(h).cuda().eval()
+    G.remove_weight_norm()
+    frames = [37, 5, 64, 23, 1, 50]
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(len(frames), 80, max(frames), generator=g).cuda()
+    hop = 256
+    with torch.no_grad():
+        y = G(x, lengths=torch.tensor(frames))
+        for i, f in enumerate(frames):
+            alone = G(x[i:i + 1, :, :f].contiguous())
+            assert torch.equal(y[i, 0, : f * hop], alone[0, 0]), (ver, i, f)
+        # and a second ragged call with other lengths through the same workspaces (stale tails must not leak)
+        frames2 = [64, 64, 2, 9, 33, 17]
+        y2 = G(x, lengths=torch.tensor(frames2))
+        for i, f in enumerate(frames2):
+            alone = G(x[i:i + 1, :, :f].contiguous())
+            assert torch.equal(y2[i, 0, : f * hop], alone[0, 0]), (ver, "second", i, f)
+    with pytest.raises(ValueError):
+        G(x, lengths=torch.tensor([1, 2, 3]))
 
 
 def test_randomised_shapes_sweep():

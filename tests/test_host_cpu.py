@@ -257,14 +257,17 @@ def test_shipped_configs_match_upstream_values():
     assert H.load_config("v3").resblock == "2" and H.load_config("v1").upsample_initial_channel == 512
 
 
-def test_inference_driver_buckets_by_exact_length():
-    """hifigan_b200.inference: only equal-length mels share a batch (zero padding at every layer of the Generator
-    makes ragged batching change edge samples), order of first appearance is kept, batches are capped."""
+def test_inference_driver_length_buckets():
+    """hifigan_b200.inference: files are sorted by length and stacked into ragged batches whose padding stays below
+    max_waste (the kernels take per-item lengths, so stacking never changes anyone's samples); batches are capped;
+    max_waste = 0 stacks equal lengths only."""
     from hifigan_b200.inference import bucket_by_length
-    items = [("a", torch.zeros(80, 10)), ("b", torch.zeros(80, 7)), ("c", torch.zeros(80, 10)),
-             ("d", torch.zeros(80, 10)), ("e", torch.zeros(80, 7))]
-    got = [[n for n, _ in b] for b in bucket_by_length(items, 2)]
-    assert got == [["a", "c"], ["d"], ["b", "e"]]
+    items = [("a", torch.zeros(80, 100)), ("b", torch.zeros(80, 70)), ("c", torch.zeros(80, 100)),
+             ("d", torch.zeros(80, 96)), ("e", torch.zeros(80, 30))]
+    got = [[n for n, _ in b] for b in bucket_by_length(items, 3)]
+    assert got == [["e"], ["b", "d", "a"], ["c"]]          # 30 alone (57 % padding with 70), then capped at 3
+    got = [[n for n, _ in b] for b in bucket_by_length(items, 8, max_waste=0.0)]
+    assert got == [["e"], ["b"], ["d"], ["a", "c"]]
     assert bucket_by_length([], 4) == []
 
 
