@@ -1,0 +1,21 @@
+#!/bin/bash
+# Multi-GPU evidence for one box of N GPUs (gpurun --gpus N -- bash tests/run_multigpu.sh N):
+#   1. data-parallel gradient equality + replica consistency on hardware (tests/dp_check.py under torchrun, via pytest)
+#   2. the training metric at BASELINE configs[3]'s global batch 128 (per-GPU batch 128 / N) and at per-GPU batch 16
+# Logs go to gpurun_out/r02_mgpu_<N>*.log
+N=${1:-2}
+mkdir -p gpurun_out
+python -m pytest tests/test_gpu_named_configs.py -q -k cfg4 > gpurun_out/r02_mgpu_${N}_dpcheck.log 2>&1
+echo "dp_check rc=$?"; tail -3 gpurun_out/r02_mgpu_${N}_dpcheck.log; cat gpurun_out/dp_check_${N}gpu.log 2>/dev/null | grep -E "worst|bit-identical"
+run() {  # per-gpu batch, tag
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29555 \
+    bench.py --gpus $N --workload train --steps 20 --warmup 5 --per-gpu-batch $1 --no-cpu-baseline 2>/dev/null | grep '^{' | tail -1 > gpurun_out/r02_mgpu_${N}_train_b$1.json
+  python - <<PY
+import json
+d=json.loads(open("gpurun_out/r02_mgpu_${N}_train_b$1.json").read())
+print("N=$N per-gpu batch $1: %.3f ms/step, %.1f segments/s, global batch %d, launches/step %.0f, clocks %s" % (d["ms_per_step"], d["value"], d["config"]["global_batch"], d["gpu_launches"]/d["steps"], d["clocks"]))
+PY
+}
+run $((128 / N))
+[ "$N" != "8" ] && run 16
+true

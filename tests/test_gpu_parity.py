@@ -759,7 +759,7 @@ def test_ragged_batch_is_bit_identical_to_per_item_calls(H, O, ver):
         for i, f in enumerate(frames2):
             alone = G(x[i:i + 1, :, :f].contiguous())
             assert torch.equal(y2[i, 0, : f * hop], alone[0, 0]), (ver, "second", i, f)
-    with pytest.raises(ValueError):
+    with torch.no_grad(), pytest.raises(ValueError):
         G(x, lengths=torch.tensor([1, 2, 3]))
 
 
