@@ -293,13 +293,16 @@ KERNEL_CLASSES = (
 )
 
 
+TRACE_REPLAYS = 2
+
+
 def train_kernel_classes(fn, args3, flop_tensor: float):
     """Per-kernel-class time of ONE training step from a CUPTI kernel trace (torch.profiler) of two graph replays
     taken AFTER the timed region: never a bench value, it only apportions the step.  Serialised kernel time exceeds
     the step time because the step's stream lanes overlap."""
     from torch.profiler import ProfilerActivity, profile as tprofile
     with tprofile(activities=[ProfilerActivity.CUDA]) as prof:
-        for _ in range(2):
+        for _ in range(TRACE_REPLAYS):
             fn(*args3)
         torch.cuda.synchronize()
     agg, other = {c: [0, 0.0] for c, _ in KERNEL_CLASSES}, [0, 0.0]
@@ -425,12 +428,17 @@ def measure_train(dev, rank, world, steps: int, warmup: int, batch: int = TRAIN[
     # of library kernels recorded when the step was captured
     per_step = ts.launches_per_step if graphed else launches / steps
     classes = None
-    if rank == 0 and not os.environ.get("HG_BENCH_NO_TRACE"):
-        try:
-            # 3 F_G + 9 F_D MACs per segment run on the tensor-core kernels except the Cin = 1 / Cout = 1 ends (< 1 %)
-            classes = train_kernel_classes(fn, (x, y3, y_mel), batch * TRAIN_FLOP_PER_SEGMENT)
-        except Exception as e:  # noqa: BLE001   (a profiler problem must not cost the measured numbers)
-            classes = {"error": f"{type(e).__name__}: {e}"[:200]}
+    if not os.environ.get("HG_BENCH_NO_TRACE"):
+        if rank == 0:
+            try:
+                # 3 F_G + 9 F_D MACs per segment run on the tensor-core kernels except the Cin = 1 / Cout = 1 ends (< 1 %)
+                classes = train_kernel_classes(fn, (x, y3, y_mel), batch * TRAIN_FLOP_PER_SEGMENT)
+            except Exception as e:  # noqa: BLE001   (a profiler problem must not cost the measured numbers)
+                classes = {"error": f"{type(e).__name__}: {e}"[:200]}
+        else:
+            for _ in range(TRACE_REPLAYS):   # the step holds the gradient all-reduces: every rank replays it with rank 0
+                fn(x, y3, y_mel)
+            torch.cuda.synchronize()
     barrier()
     return {"ms": max_over_ranks(ms), "e2e_ms": max_over_ranks(e2e_ms), "batch": batch, "kernel_classes": classes,
             "segments": sum_over_ranks(float(batch)), "launches_per_step": per_step, "graphed": graphed,

@@ -23,6 +23,11 @@ extern "C" const char* hg_last_error(void) { return g_err; }
 extern "C" const char* hg_version(void) { return "hifigan_b200 0.1 (sm_100a; tcgen05+TMA)"; }
 extern "C" int hg_abi_version(void) { return HG_ABI_VERSION; }
 extern "C" int64_t hg_launch_count(void) { return g_hg_launches.load(std::memory_order_relaxed); }
+extern "C" int hg_set_cta_limit(int max_ctas) {
+  const int old = hg::t_cta_limit;
+  hg::t_cta_limit = max_ctas > 0 ? max_ctas : 0;
+  return old;
+}
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;

@@ -945,13 +945,15 @@ int conv_forward(const void* x, const void* w_packed, const float* bias, int bat
 
   const size_t smem_bytes = 1024 + static_cast<size_t>(a_slots) * p.a_slot_bytes + w_bytes_total +
                             sizeof(Barriers) + colsum_bytes;
-  const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
+  const int sms = hg::cap_ctas(g_num_sms);
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (pair) {
     const size_t smem2 = 1024 + static_cast<size_t>(a_slots) * p.a_slot_bytes + w_bytes_total + sizeof(Barriers2) +
                          colsum_bytes;
-    rc = (n_tile == 256) ? launch2<256>(tm_x, tm_w, p, smem2, g_num_sms, st)
-                         : launch2<128>(tm_x, tm_w, p, smem2, g_num_sms, st);
+    const int grid2 = sms >= 2 ? (sms & ~1) : 2;     // whole CTA pairs
+    rc = (n_tile == 256) ? launch2<256>(tm_x, tm_w, p, smem2, grid2, st)
+                         : launch2<128>(tm_x, tm_w, p, smem2, grid2, st);
     if (rc) return rc;
     g_hg_launches.fetch_add(1, std::memory_order_relaxed);
     return HG_OK;

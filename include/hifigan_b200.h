@@ -34,6 +34,12 @@ const char* hg_last_error(void);
 int hg_abi_version(void);
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t hg_launch_count(void);
+/* Cap the persistent grids of hg_conv1d_fwd / hg_resblock_pair_fwd launched afterwards by the CALLING host thread
+ * to `max_ctas` CTAs (0 restores one CTA per SM); returns the previous value.  The kernels stride their tile lists
+ * by the grid size, so any cap is correct; it exists so that independent launch chains on different streams (the
+ * three MRF branches of one Generator stage, src/models.py:106-111) can share the GPU side by side on disjoint SM
+ * subsets — an HBM-bound k=3 branch next to a tensor-bound k=11 branch — instead of one after the other. */
+int hg_set_cta_limit(int max_ctas);
 
 /* ------------------------------------------------------------------------------------------
  * Weight preparation (replaces torch.nn.utils.weight_norm's per-forward recompute,

@@ -5,11 +5,12 @@
 # Logs go to gpurun_out/r02_mgpu_<N>*.log
 N=${1:-2}
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_named_configs.py -q -k cfg4 > gpurun_out/r02_mgpu_${N}_dpcheck.log 2>&1
+timeout 300 python -m pytest tests/test_gpu_named_configs.py -q -k cfg4 > gpurun_out/r02_mgpu_${N}_dpcheck.log 2>&1
 echo "dp_check rc=$?"; tail -3 gpurun_out/r02_mgpu_${N}_dpcheck.log; cat gpurun_out/dp_check_${N}gpu.log 2>/dev/null | grep -E "worst|bit-identical"
 run() {  # per-gpu batch, tag
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29555 \
-    bench.py --gpus $N --workload train --steps 20 --warmup 5 --per-gpu-batch $1 --no-cpu-baseline 2>/dev/null | grep '^{' | tail -1 > gpurun_out/r02_mgpu_${N}_train_b$1.json
+  timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29555 \
+    bench.py --gpus $N --workload train --steps 20 --warmup 5 --per-gpu-batch $1 --no-cpu-baseline 2> gpurun_out/r02_mgpu_${N}_train_b$1.err | grep '^{' | tail -1 > gpurun_out/r02_mgpu_${N}_train_b$1.json
+  [ -s gpurun_out/r02_mgpu_${N}_train_b$1.json ] || { echo "N=$N per-gpu batch $1: no result"; tail -5 gpurun_out/r02_mgpu_${N}_train_b$1.err; return; }
   python - <<PY
 import json
 d=json.loads(open("gpurun_out/r02_mgpu_${N}_train_b$1.json").read())
