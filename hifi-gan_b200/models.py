@@ -500,6 +500,9 @@ class _GeneratorEngine:
     # stream, its own ping-pong buffers and a share of the SMs (hg_set_cta_limit) proportional to its measured
     # run time; the last branch's final launch (which adds the other branches' results) runs after the join on
     # the whole GPU.  The first call of a shape runs the branches one after the other and times them.
+    # MEASURED (tests/lanes_ab.py, profiles/r02_summary.md section 4): bit-identical output, 56.9 ms against 56.2 ms one
+    # after the other at 64 x 1024 frames — the step is bound by SM-time under the power cap, not by idle HBM or
+    # tensor pipes — so the schedule is opt-in (HG_MRF_LANES=1, or "a,b,c" for a fixed CTA split).
     LANE_MIN_CTAS = 8
     LANE_CALIB_CALLS = 3      # call 1: branches alone; calls 2-3: side by side, split re-balanced from their run times
 
@@ -535,7 +538,7 @@ class _GeneratorEngine:
         b, c, frames = xin.shape
         ws = self.workspace(b, frames)
         nk = gen.num_kernels
-        lanes = bool(lanes and 2 <= nk <= 3 and os.environ.get("HG_MRF_LANES", "1") != "0")
+        lanes = bool(lanes and 2 <= nk <= 3 and os.environ.get("HG_MRF_LANES", "0") != "0")
         lane = self._lane_state(ws, nk) if lanes else None
         sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         if lane is not None and lane["forced"] is not None:
