@@ -108,6 +108,7 @@ _SIGNATURES = {
     "hg_abi_version": (c_int, []),
     "hg_launch_count": (c_int64, []),
     "hg_set_cta_limit": (c_int, [c_int]),
+    "hg_timestamp": (c_int, [c_void_p, c_void_p]),
     "hg_pack_conv1d_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hg_convtr1d_geometry": (c_int, [c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
     "hg_pack_convtr1d_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

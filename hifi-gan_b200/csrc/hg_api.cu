@@ -23,6 +23,20 @@ extern "C" const char* hg_last_error(void) { return g_err; }
 extern "C" const char* hg_version(void) { return "hifigan_b200 0.1 (sm_100a; tcgen05+TMA)"; }
 extern "C" int hg_abi_version(void) { return HG_ABI_VERSION; }
 extern "C" int64_t hg_launch_count(void) { return g_hg_launches.load(std::memory_order_relaxed); }
+// one thread writes the GPU's nanosecond clock: a time mark INSIDE a captured graph (events cannot be read there)
+__global__ void timestamp_kernel(unsigned long long* dst) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *dst = t;
+}
+
+extern "C" int hg_timestamp(uint64_t* dst, void* stream) {
+  HG_REQUIRE(dst != nullptr, "hg_timestamp: null destination");
+  timestamp_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<unsigned long long*>(dst));
+  HG_CHECK_CUDA(cudaGetLastError());
+  return HG_OK;
+}
+
 extern "C" int hg_set_cta_limit(int max_ctas) {
   const int old = hg::t_cta_limit;
   hg::t_cta_limit = max_ctas > 0 ? max_ctas : 0;

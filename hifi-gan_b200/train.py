@@ -13,6 +13,7 @@ fp32 parameter gradients, fp32 master weights and optimizer state.
 """
 from __future__ import annotations
 
+import os
 from ctypes import byref, c_int
 from typing import Dict, List, Optional, Tuple
 
@@ -176,6 +177,41 @@ class _Lanes:
 
     def lane(self, i: int):
         return torch.cuda.stream(self.streams[i % len(self.streams)])
+
+
+class LaneStamps:
+    """Time marks inside the (graph-replayed) step: hg_timestamp launches on the lanes, read back after the replay.
+    On with HG_LANE_STAMPS=1 (tests/lane_stamps.py) or while TrainStep calibrates the order of the gradient slices
+    (`force`); otherwise mark() is a no-op and nothing is launched."""
+
+    def __init__(self, device, slots: int = 96):
+        self.device, self.slots = device, slots
+        self.env_on = bool(os.environ.get("HG_LANE_STAMPS"))
+        self.force = False
+        self.names: List[str] = []
+        self.buf: Optional[torch.Tensor] = None
+
+    @property
+    def on(self) -> bool:
+        return self.env_on or self.force
+
+    def begin(self) -> None:
+        self.names = []                 # the step issues its marks in the same order every time it runs or is captured
+        if self.on and self.buf is None:
+            self.buf = torch.zeros(self.slots, dtype=torch.int64, device=self.device)
+
+    def mark(self, name: str) -> None:
+        if not self.on or self.buf is None or len(self.names) >= self.slots:
+            return
+        _lib.check(_lib.lib().hg_timestamp(self.buf.data_ptr() + 8 * len(self.names), _stream()), "hg_timestamp")
+        self.names.append(name)
+
+    def read(self) -> Dict[str, float]:
+        """microseconds since the step's first mark, by name (after a synchronize)"""
+        if self.buf is None or not self.names:
+            return {}
+        v = self.buf[: len(self.names)].cpu().tolist()
+        return {n: (t - v[0]) / 1e3 for n, t in zip(self.names, v)}
 
 
 def allreduce_gradients(flat: FlatParams, group=None, span: Optional[Tuple[int, int]] = None) -> float:
@@ -683,7 +719,6 @@ class _SubDiscTrainer:
             self.dwps.append(self.dwp_flat[off:off + n])
             off += n
         self._tables = {}
-        import os
         # A/B switches for profiles/r02_summary.md: per-layer launches (the round-1 scheme) instead of the batched ones
         self.batch_prep = os.environ.get("HG_BATCH_D_PREP", "1") != "0"
         self.batch_finish = os.environ.get("HG_BATCH_D_FINISH", "0") != "0"   # measured: +0.3 ms when batched (waits for the last wgrad)
@@ -1238,7 +1273,6 @@ class DiscriminatorTrainer:
             d.__dict__.pop("_hg_wcache", None)
         # critical-path scheduling: the spectral-norm scale (two parts, full-rate input) has the longest chain, the
         # second scale the next longest; their lanes outrank the period discriminators' (HG_DISC_BOOST=0 disables)
-        import os
         boosts = [0, 0, 0] if os.environ.get("HG_DISC_BOOST") == "0" else [-2, -1, 0]
         self.subs_p = [_SubDiscTrainer(d, device) for d in mpd.discriminators]
         self.subs_s = [_SubDiscTrainer(d, device, boosts[min(i, 2)]) for i, d in enumerate(msd.discriminators)]
@@ -1252,6 +1286,14 @@ class DiscriminatorTrainer:
         self.lanes = _Lanes(len(self.subs), device,                          # one per sub-discriminator
                             [-1] * len(self.subs_p) + [-1 + boosts[min(i, 2)] for i in range(len(self.subs_s))])
         self.spans = [self.flat.span_of(d) for d in list(mpd.discriminators) + list(msd.discriminators)]
+        self.order = list(range(len(self.subs)))
+        self.order_fixed = False                          # True once measured (TrainStep.step_graphed) or forced
+        forced = os.environ.get("HG_LANE_ORDER")          # e.g. "6,4,0,3,2,1,7,5": experiments (same on every rank!)
+        if forced:
+            self.order = [int(v) for v in forced.split(",")]
+            if sorted(self.order) != list(range(len(self.subs))):
+                raise ValueError("HG_LANE_ORDER must be a permutation of the sub-discriminator indices")
+            self.order_fixed = True
         if self.spans[0][0] != 0 or self.spans[-1][1] != self.flat.numel or any(
                 a[1] != b[0] for a, b in zip(self.spans, self.spans[1:])):
             raise RuntimeError("DiscriminatorTrainer: sub-discriminator parameter spans do not tile the flat buffer")
@@ -1276,7 +1318,8 @@ class DiscriminatorTrainer:
         return self.pooled[0] if i < len(self.subs_p) else self.pooled[i - len(self.subs_p)]
 
     def run_phases(self, y: torch.Tensor, y_hat: torch.Tensor, dy_audio: torch.Tensor, update: bool, lr: float, betas,
-                   world: int = 1, allreduce=None) -> Tuple[Dict[str, torch.Tensor], Dict[str, torch.Tensor]]:
+                   world: int = 1, allreduce=None, stamps: Optional[LaneStamps] = None
+                   ) -> Tuple[Dict[str, torch.Tensor], Dict[str, torch.Tensor]]:
         """The discriminator step and the discriminator half of the generator step of ONE training step, with every
         sub-discriminator running its whole chain on its own lane:
             forward -> loss sums -> backward (parameter gradients) -> AdamW on its own slice of the flat buffers
@@ -1295,17 +1338,25 @@ class DiscriminatorTrainer:
         grads = [dy_audio] + [torch.zeros(b, p.shape[1], dtype=torch.float32, device=self.device)
                               for p in self.pooled[1:]]
         np_ = len(self.subs_p)
+        mark = stamps.mark if stamps is not None else (lambda name: None)
         self.lanes.fork()
-        for i, sd in enumerate(self.subs):
+        # Python issue order = the order of the slices on NCCL's (single, in-order) stream: a slice queued behind the
+        # slice of a lane that finishes its backward later waits for it.  self.order lists the lanes by the time
+        # their backward ends in the replayed step (measured: tests/lane_stamps.py).
+        for i in self.order:
+            sd = self.subs[i]
             with self.lanes.lane(i):
                 sd.forward(self._input_of(i), b)
                 sd.loss_terms(self.acc_d, i * self.nslots, fm=False)
                 sd.backward_d()
+                mark(f"d{i}_bwd_done")
                 if world > 1:
                     # this sub-discriminator's slice of the gradient buffer, exchanged as soon as its backward is
-                    # done: the collectives run in lane order on NCCL's stream while the later lanes still compute
+                    # done: the collectives run in issue order on NCCL's stream while the later lanes still compute
                     allreduce(self.flat, self.spans[i])
-        for i, sd in enumerate(self.subs):
+                    mark(f"d{i}_allreduce_done")
+        for i in self.order:
+            sd = self.subs[i]
             with self.lanes.lane(i):
                 if update:
                     self.flat.adamw_slice(self.spans[i][0], self.spans[i][1], lr, betas, grad_scale=1.0 / world)
@@ -1313,6 +1364,7 @@ class DiscriminatorTrainer:
                 sd.forward(self._input_of(i), b)
                 sd.loss_terms(self.acc_g, i * self.nslots)
                 sd.backward_g(grads[0] if i < np_ else grads[i - np_], [2.0 / n for n in sd.numel_fmaps(b)])
+                mark(f"d{i}_gstep_done")
         self.lanes.join()
         for i in reversed(range(1, len(grads))):
             _lib.check(L.hg_avgpool_4_2_2_bwd(grads[i].data_ptr(), b, grads[i - 1].shape[1], grads[i - 1].data_ptr(),
@@ -1364,6 +1416,7 @@ class TrainStep:
         self.world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
+        self.stamps = LaneStamps(device)
 
     def _allreduce(self, flat: FlatParams, span: Optional[Tuple[int, int]] = None) -> None:
         allreduce_gradients(flat, self.pg, span)
@@ -1391,6 +1444,8 @@ class TrainStep:
             self.G.flat.set_lr(self.lr)
             self.D.flat.set_lr(self.lr)
         launches0 = _lib.launch_count()
+        self.stamps.begin()
+        self.stamps.mark("start")
         y2 = y.reshape(b, -1).contiguous().float()
         y_g = self.G.forward(x)                                # [B,1,T]
         y_g2 = y_g.view(b, -1)
@@ -1415,7 +1470,8 @@ class TrainStep:
             _lib.check(L.hg_mel_bwd(plan.handle, y_g2.data_ptr(), dmel.data_ptr(), b, y_g2.shape[1], dy.data_ptr(), ms),
                        "hg_mel_bwd")
         # ---- discriminator step, then the generator step's pass through the updated discriminators
-        dl, gl = self.D.run_phases(y2, y_g2, dy, update, self.lr, self.betas, self.world, self._allreduce)
+        self.stamps.mark("g_fwd_done")
+        dl, gl = self.D.run_phases(y2, y_g2, dy, update, self.lr, self.betas, self.world, self._allreduce, self.stamps)
         here.wait_stream(self.mel_lane)
         out["loss_mel"] = acc[0] / n_mel * 45
         out["loss_disc_f"], out["loss_disc_s"] = dl["loss_disc_f"], dl["loss_disc_s"]
@@ -1424,18 +1480,22 @@ class TrainStep:
             out[k] = gl[k]
         out["loss_gen_all"] = gl["loss_gen_s"] + gl["loss_gen_f"] + gl["loss_fm_s"] + gl["loss_fm_f"] + out["loss_mel"]
         self.dy_audio = dy
+        self.stamps.mark("g_bwd_start")
         self.G.backward(dy)
+        self.stamps.mark("g_bwd_done")
         self._allreduce(self.G.flat)
+        self.stamps.mark("g_allreduce_done")
         if update:
             self.G.flat.adamw(self.lr, self.betas, grad_scale=1.0 / self.world)
             self.G.invalidate()
+        self.stamps.mark("end")
         out["y_g_hat"] = y_g
         self.launches_per_step = _lib.launch_count() - launches0   # library kernels issued (or captured) per step
         return out
 
     @property
     def graph_active(self) -> bool:
-        return any(isinstance(v, tuple) for v in self.__dict__.get("_graphs", {}).values())
+        return any(isinstance(v, list) for v in self.__dict__.get("_graphs", {}).values())
 
     # ---- CUDA-graph replay ---------------------------------------------------------------------------------------
     def step_graphed(self, x: torch.Tensor, y: torch.Tensor, y_mel: torch.Tensor) -> Dict[str, torch.Tensor]:
@@ -1451,6 +1511,11 @@ class TrainStep:
         if entry is None:
             graphs[key] = "seen"
             return self.step(x, y, y_mel)
+        calibrate = self.world > 1 and not self.D.order_fixed
+        if isinstance(entry, list) and calibrate and entry[5] >= self.CALIBRATION_REPLAYS:
+            self._calibrate_slice_order()
+            calibrate = not self.D.order_fixed      # another round (marks stay on) or the final capture (marks off)
+            entry = graphs[key] = "seen"            # capture again below with the slices in the new order
         if entry == "seen":
             sx, sy, sm = x.clone(), y.clone(), y_mel.clone()
             torch.cuda.synchronize()
@@ -1458,6 +1523,7 @@ class TrainStep:
             # since the last update (a validation `generator(x)` between the eager and the capture step) would make
             # every refresh a host-side no-op here and the graph would replay G on stale bf16 weights for ever.
             self.G.invalidate()
+            self.stamps.force = calibrate           # the first data-parallel capture carries the lane time marks
             try:
                 g = torch.cuda.CUDAGraph()
                 # thread_local: the NCCL watchdog thread of a data-parallel run may touch the CUDA API meanwhile
@@ -1465,7 +1531,7 @@ class TrainStep:
                 # the parameter-gradient lanes
                 with torch.cuda.graph(g, stream=self.capture_stream, capture_error_mode="thread_local"):
                     out = self.step(sx, sy, sm)
-                entry = (g, sx, sy, sm, out)
+                entry = [g, sx, sy, sm, out, 0]
             except Exception as e:  # noqa: BLE001
                 import warnings
                 warnings.warn(f"hifigan_b200: CUDA graph capture of the training step failed, running eagerly ({e})")
@@ -1476,10 +1542,50 @@ class TrainStep:
                 self.G.invalidate()
                 for sd in self.D.subs:
                     sd.invalidate()
+            self.stamps.force = False
             graphs[key] = entry
         if entry == "eager":
             return self.step(x, y, y_mel)
-        g, sx, sy, sm, out = entry
+        entry[5] += 1
+        g, sx, sy, sm, out = entry[:5]
         sx.copy_(x); sy.copy_(y); sm.copy_(y_mel)
         g.replay()
         return out
+
+    # Data-parallel: the all-reduces of one NCCL communicator execute one at a time in issue order, so a gradient
+    # slice queued behind the slice of a lane whose backward ends later waits for that lane (measured at 2 GPUs,
+    # profiles/r02_summary.md section 5: the second scale discriminator ended its backward at 3.6 ms and got its
+    # slice back at 8.8 ms, behind the spectral-norm scale's).  The first data-parallel captures therefore carry
+    # hg_timestamp marks: after CALIBRATION_REPLAYS replays the lanes are re-sorted by the time their backward
+    # ended and the step is captured again — up to CALIBRATION_ROUNDS times, because the new order moves the lanes'
+    # timings — and the order with the earliest end of step is captured for good, without marks.  Rank 0 decides
+    # and broadcasts: every rank must issue the same order.
+    CALIBRATION_REPLAYS = 3
+    CALIBRATION_ROUNDS = 3
+
+    @property
+    def warmup_calls(self) -> int:
+        """step_graphed calls before the final graph replays: eager, capture, (data-parallel: calibration rounds)"""
+        if self.world == 1 or self.D.order_fixed:
+            return 2
+        return 2 + self.CALIBRATION_ROUNDS * (self.CALIBRATION_REPLAYS + 1)
+
+    def _calibrate_slice_order(self) -> None:
+        torch.cuda.synchronize()
+        t = self.stamps.read()
+        n = len(self.D.subs)
+        cal = self.__dict__.setdefault("_cal", {"tried": [], "best": None})
+        cur = list(self.D.order)
+        cal["tried"].append(cur)
+        end = t.get("end", float("inf"))
+        if cal["best"] is None or end < cal["best"][0]:
+            cal["best"] = (end, cur)
+        nxt = sorted(range(n), key=lambda i: t.get(f"d{i}_bwd_done", float(i)))
+        final = len(cal["tried"]) >= self.CALIBRATION_ROUNDS or nxt in cal["tried"]
+        msg = torch.tensor([int(final)] + (cal["best"][1] if final else nxt), dtype=torch.int64, device=self.device)
+        src = 0 if self.pg is None else torch.distributed.get_global_rank(self.pg, 0)
+        torch.distributed.broadcast(msg, src=src, group=self.pg)
+        msg = [int(v) for v in msg.cpu().tolist()]
+        self.D.order = msg[1:]
+        self.D.order_fixed = bool(msg[0])
+        self.slice_order_log = cal["tried"], cal["best"]

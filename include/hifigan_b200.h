@@ -40,6 +40,10 @@ int64_t hg_launch_count(void);
  * three MRF branches of one Generator stage, src/models.py:106-111) can share the GPU side by side on disjoint SM
  * subsets — an HBM-bound k=3 branch next to a tensor-bound k=11 branch — instead of one after the other. */
 int hg_set_cta_limit(int max_ctas);
+/* Diagnostics: a one-thread kernel on `stream` stores the GPU's %globaltimer (ns) to *dst (device memory).  Unlike a
+ * CUDA event it can be read after a graph replay: the training step marks where each discriminator lane finishes its
+ * backward, its gradient all-reduce and its generator-step pass (HG_LANE_STAMPS=1, tests/lane_stamps.py). */
+int hg_timestamp(uint64_t* dst, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Weight preparation (replaces torch.nn.utils.weight_norm's per-forward recompute,

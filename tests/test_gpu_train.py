@@ -515,7 +515,7 @@ def test_graphed_step_matches_eager(H):
             out = fn(x, ya.unsqueeze(1), y_mel)
         torch.cuda.synchronize()
         if graphed:
-            assert isinstance(ts._graphs[next(iter(ts._graphs))], tuple), "capture fell back to eager"
+            assert isinstance(ts._graphs[next(iter(ts._graphs))], list), "capture fell back to eager"
         res.append({k: out[k].item() for k in LOSS_KEYS})
     for k in LOSS_KEYS:
         assert abs(res[0][k] - res[1][k]) <= 1e-3 * abs(res[0][k]) + 1e-5, (k, res[0][k], res[1][k])
