@@ -688,6 +688,8 @@ class _SubDiscTrainer:
     """One DiscriminatorP / DiscriminatorS: batched (real ++ generated) forward with saved activations, losses on
     the internal layout, and the hand-written backward."""
 
+    W_CHAINS = 4
+
     def __init__(self, disc: nn.Module, device, boost: int = 0):
         """boost: added to the CUDA stream priorities of every lane of this sub-discriminator (negative = more urgent):
         the sub-discriminator with the longest chain (the spectral-norm scale) is the step's critical path, so its
@@ -708,7 +710,14 @@ class _SubDiscTrainer:
         # data-gradient filter banks), on two lanes; lane 0 is the parameter-gradient lane of this sub-discriminator
         self.bwd_parts = [self.bwd] + ([[_DiscBwdLayer(l, device) for l in self.mids]] if self.spectral else [])
         self.lanes = _Lanes(2, device, [0 + boost, -1 + boost])   # 0: parameter-gradient lane, 1: second data-gradient chain
-        self.prep = _Lanes(4, device, [-1 + boost] * 4)           # weight preparation / data-gradient packs
+        n_prep = 8 if self.spectral else 4                        # spectral norm: one power-iteration chain per layer
+        self.prep = _Lanes(n_prep, device, [-1 + boost] * n_prep)  # weight preparation / data-gradient packs
+        self._prefetched = None
+        # spectral norm: every layer's parameter-gradient chain (wgrad -> unpack -> <dw,w> -> apply, for both halves)
+        # is independent of the other layers': spread over W_CHAINS lanes instead of one.  (One lane made this the
+        # longest dependent chain of the whole step: 3.9 ms for 2 x 8 layers, profiles/r02_summary.md section 2.)
+        self.wl = _Lanes(self.W_CHAINS, device, [0 + boost] * self.W_CHAINS) if self.spectral else None
+        self._scr = {}
         self.ws = {}
         # packed fp32 weight gradients, one region per wide layer (zeroed once per backward; the wgrad launches and
         # the batched finish accumulate)
@@ -726,6 +735,7 @@ class _SubDiscTrainer:
                                        else m.weight_orig.numel() if self.spectral else m.weight.numel()
                                        for m in self.mods), dtype=torch.float32, device=device)
         self.db = torch.zeros(1024, dtype=torch.float32, device=device)
+        self.db_unused = torch.zeros(1024, dtype=torch.float32, device=device)    # the first conv's discarded bias column
         self.wbufs = {}
         self.fwd_valid = self.dgrad_valid = False
         self.W_cached = None
@@ -736,6 +746,16 @@ class _SubDiscTrainer:
         self.disc.__dict__.pop("_hg_wcache", None)      # the module API's own pack cache (inference-side forward)
 
     # ---- weights -------------------------------------------------------------------------------------------
+    def _scratch_of(self, chain: int) -> torch.Tensor:
+        """fp32 scratch of parameter-gradient chain `chain`: the shared one (weight_norm: one lane serialises its use)
+        or one per chain (spectral norm: the chains run side by side)"""
+        if not self.spectral:
+            return self.scratch
+        buf = self._scr.get(chain)
+        if buf is None:
+            buf = self._scr[chain] = torch.empty_like(self.scratch)
+        return buf
+
     def _weights(self, part: int, only_buffers: bool = False):
         """effective fp32 weights + forward GEMM packs of every layer, into per-part persistent buffers.
         weight_norm layers: hg_fold_weight_norm + hg_pack_disc_weight.  spectral_norm layers: one power iteration
@@ -822,6 +842,28 @@ class _SubDiscTrainer:
                 self._weights_layer(W, self.wbufs[part], li, pack=False)
         self._table(part).launch("fwd")
         return W
+
+    def prefetch_weights(self) -> None:
+        """Spectral norm only: queue the NEXT forward's power iterations (both halves) and forward banks on the prep
+        lanes, forked from the current stream, without joining them back — forward() waits for them.  The training
+        step calls this before the generator's forward: the discriminator-step weights depend on nothing the
+        generator produces, and inside the discriminator phase these small launches wait for SMs behind the other
+        lanes' persistent tensor-core kernels (measured: 0.98 -> 3.0 ms for chains that take 0.2 ms on a quiet GPU)."""
+        if not self.spectral:
+            return
+        Ws = [self._weights(pi, only_buffers=True) for pi in range(2)]
+        self.prep.fork()
+        for li in range(len(self.mods)):
+            with self.prep.lane(li):
+                for pi, W in enumerate(Ws):
+                    self._weights_layer(W, self.wbufs[pi], li, pack=False)
+        p0 = self.prep.streams[0]
+        for s_ in self.prep.streams[1:]:
+            p0.wait_stream(s_)
+        with torch.cuda.stream(p0):
+            for pi in range(2):
+                self._table(pi).launch("fwd")
+        self._prefetched = Ws
 
     def _weights_layer(self, ws, bufs, li: int, pack: bool = True) -> None:
         """fold (weight norm) or power-iterate (spectral norm) layer li and pack its forward filter bank"""
@@ -927,7 +969,13 @@ class _SubDiscTrainer:
         # and the D-step forward of the next see the same weights); spectral norm moves on every call, and its
         # second part's power iteration continues from the first's.  The layers are independent of each other, so
         # their fold / power-iteration / pack chains are spread over the prep lanes (part 0 before part 1 per layer).
-        if self.spectral or not self.fwd_valid:
+        if self.spectral and self._prefetched is not None:
+            # prefetch_weights() queued this call's power iterations and forward banks on the prep lanes
+            Ws, self._prefetched = self._prefetched, None
+            torch.cuda.current_stream().wait_stream(self.prep.streams[0])
+            self.W_cached = Ws[-1]
+            self.fwd_valid = True
+        elif self.spectral or not self.fwd_valid:
             if self.spectral:
                 # the power iterations of the layers are independent chains of three small kernels (part 0 before part 1
                 # per layer: the second call continues from the first's u, v): side by side on the prep lanes.  (Batched
@@ -964,11 +1012,15 @@ class _SubDiscTrainer:
         with torch.cuda.stream(plane):
             for pi in range(len(parts)):
                 self._pack_dgrad(Ws[pi], pi)
+        if len(parts) > 1:
+            # the second part's chain forks HERE, before the first part's launches are queued on this stream: the
+            # two halves run side by side (they wrote "wait_stream(here)" after part 0 once, and ran one after the
+            # other: 300 us of the step's critical path per forward — profiles/r02_summary.md section 2)
+            self.lanes.streams[1].wait_stream(here)
         for pi, (b0, bn) in enumerate(parts):
             W = Ws[pi]
             self.parts.append((b0, bn, W))
             if pi == 1:
-                self.lanes.streams[1].wait_stream(here)
                 with torch.cuda.stream(self.lanes.streams[1]):
                     self._forward_part(L, G, W, ycat, b0, bn, t)
             else:
@@ -1062,15 +1114,18 @@ class _SubDiscTrainer:
         if not self.spectral:
             self.dwp_flat.zero_()
         self.lanes.fork()     # both lanes join the capture here (a join of a never-forked stream would invalidate it)
+        if self.wl is not None:
+            self.wl.fork()
         for pi, (b0, bn, W) in enumerate(self.parts):
-            if pi == 1:                       # spectral norm: the generated half's chain on the second lane
-                self.lanes.streams[1].wait_stream(here)
-                with torch.cuda.stream(self.lanes.streams[1]):
+            if pi == 1:                       # spectral norm: the generated half's chain on the second lane,
+                with torch.cuda.stream(self.lanes.streams[1]):     # beside the real half's (forked just above)
                     self._backward_part(L, G, W, b0, bn, want_wgrad=True, fm=False, dy_audio=None, accumulate=True,
                                         part=pi)
             else:
                 self._backward_part(L, G, W, b0, bn, want_wgrad=True, fm=False, dy_audio=None, accumulate=True,
                                     part=pi)
+        if self.wl is not None:
+            self.wl.join()
         self.lanes.join()
 
     def _bwd_bank(self, part: int):
@@ -1121,8 +1176,12 @@ class _SubDiscTrainer:
         if want_wgrad and not self.spectral:
             self.dwp_flat.zero_()
         self.lanes.fork()
+        if self.wl is not None:
+            self.wl.fork()
         self._backward_part(L, G, W, 0, nb, want_wgrad=want_wgrad, fm=False, dy_audio=dy_audio, accumulate=True,
                             part=slot, pre_adds=pre_adds)
+        if self.wl is not None:
+            self.wl.join()
         self.lanes.join()
 
     def backward_g(self, dy_audio: torch.Tensor, nfm: List[float]) -> None:
@@ -1158,12 +1217,15 @@ class _SubDiscTrainer:
         act_last = G["act"][-1]
         post = self.mods[-1]
         here = torch.cuda.current_stream()
-        wlane = self.lanes.streams[0]
 
-        def side(fn):
+        def side(fn, chain: int):
+            # weight_norm: one w-lane, one scratch.  Spectral norm: chain c (one layer) on lane c % W_CHAINS with a
+            # scratch of its own; both halves of a layer use the same lane, so their accumulation into the layer's
+            # gradient stays ordered
+            wlane = self.wl.streams[chain % self.W_CHAINS] if self.spectral else self.lanes.streams[0]
             wlane.wait_stream(here)
             with torch.cuda.stream(wlane):
-                fn()
+                fn(self._scratch_of(chain))
 
         # fm_r for the generated half is the real half of the same buffer (seq - nr)
         fm_r_last = act_last[seq0 - nr:].data_ptr() if fm else 0
@@ -1175,16 +1237,16 @@ class _SubDiscTrainer:
                                            nfm[nl] if fm else 0.0, _p(pre[nl]), G["grad"][-1][seq0:].data_ptr(), 0, 0,
                                            bias_of(nl), _stream()), "hg_disc_last_conv_bwd")
         if want_wgrad:
-            def post_grads():
-                self.scratch[: c_last * self.kpost].zero_()
+            def post_grads(scratch):
+                scratch[: c_last * self.kpost].zero_()
                 self.db.zero_()
                 _lib.check(L.hg_disc_last_conv_bwd(act_last[seq0:].data_ptr(), W["wp"].data_ptr(),
                                                    G["dlogit"][seq0:].data_ptr(), nseq, h_last, rows_last, c_last,
-                                                   self.kpost, LRELU_SLOPE, 0, 0.0, 0, 0, self.scratch.data_ptr(),
+                                                   self.kpost, LRELU_SLOPE, 0, 0.0, 0, 0, scratch.data_ptr(),
                                                    self.db.data_ptr(), 0, _stream()), "hg_disc_last_conv_bwd")
-                self._route(L, post, self.scratch, 1, c_last * self.kpost, W, len(self.mods) - 1, True)
+                self._route(L, post, scratch, 1, c_last * self.kpost, W, len(self.mods) - 1, True)
                 self._bias(post, self.db[:1], True)
-            side(post_grads)
+            side(post_grads, 0)
         for li in reversed(range(nl)):
             layer = self.mids[li]
             m = self.mods[1 + li]
@@ -1193,8 +1255,8 @@ class _SubDiscTrainer:
             d_out = G["grad"][1 + li][seq0:]
             a_in = G["act"][li]
             if want_wgrad:
-                def layer_grads(layer=layer, m=m, li=li, h_out=h_out, rows_out=rows_out, rows_in=rows_in, d_out=d_out,
-                                a_in=a_in):
+                def layer_grads(scratch, layer=layer, m=m, li=li, h_out=h_out, rows_out=rows_out, rows_in=rows_in,
+                                d_out=d_out, a_in=a_in):
                     st = _stream()
                     sn = hasattr(m, "weight_orig")
                     # weight_norm layers: dwps[li] was zeroed with the whole region (zero_wgrads) and is finished by
@@ -1209,35 +1271,35 @@ class _SubDiscTrainer:
                     if sn:
                         _lib.check(L.hg_unpack_wgrad_conv(self.dwps[li].data_ptr(), layer.cout, cin_g, layer.k,
                                                           layer.cout, layer.cin_tile, layer.cout // layer.groups,
-                                                          layer.merge, order, self.scratch.data_ptr(), st),
+                                                          layer.merge, order, scratch.data_ptr(), st),
                                    "hg_unpack_wgrad_conv")
-                        self._route(L, m, self.scratch, layer.cout, cin_g * layer.k, W, 1 + li, True)
+                        self._route(L, m, scratch, layer.cout, cin_g * layer.k, W, 1 + li, True)
                     elif not self.batch_finish:
                         g, v = _g_v(m)          # unpack + weight_norm backward in one launch, accumulating
                         _lib.check(L.hg_wgrad_finish_conv(self.dwps[li].data_ptr(), layer.cout, cin_g, layer.k,
                                                           layer.cout, layer.cin_tile, layer.cout // layer.groups,
                                                           layer.merge, order, v.data_ptr(), g.data_ptr(), 1,
                                                           _gb(v).data_ptr(), _gb(g).data_ptr(), st), "hg_wgrad_finish_conv")
-                side(layer_grads)
+                side(layer_grads, nl - li)
             bwd[li].dgrad(L, d_out, nseq, h_out, rows_out, rows_in, a_in[seq0:],
                           a_in[seq0 - nr:] if fm else None, nfm[li] if fm else 0.0, G["grad"][li][seq0:], _stream(),
                           flat_h_in=h_in, bias_dst=bias_of(li), pre_add=pre[li])
         if want_wgrad and not self.spectral and self.batch_finish:
-            side(lambda: self._table(part).launch("finish"))     # every wide layer's unpack + weight_norm backward
+            side(lambda scratch: self._table(part).launch("finish"), 0)   # every wide layer's unpack + weight_norm backward
         # first conv (Cin = 1)
         k0, s0, p0, c0 = self.first
         m0 = self.mods[0]
         if want_wgrad:
-            def first_grads():
-                self.scratch[: c0 * k0].zero_()
+            def first_grads(scratch):
+                scratch[: c0 * k0].zero_()
                 # the kernel's own bias column (summed from the bf16 gradient) lands in the db scratch and is not
                 # used: the first conv's bias gradient came from the fp32 sums of the launch that produced grad[0]
                 _lib.check(L.hg_disc_first_conv_bwd(self.ycat[b0:].data_ptr(), W["w0"].data_ptr(),
                                                     G["grad"][0][seq0:].data_ptr(), bn, self.t, period, k0, s0, p0, c0,
-                                                    geo[0][1], self.scratch.data_ptr(), self.db.data_ptr(), 0,
+                                                    geo[0][1], scratch.data_ptr(), self.db_unused.data_ptr(), 0,
                                                     _stream()), "hg_disc_first_conv_bwd")
-                self._route(L, m0, self.scratch, c0, k0, W, 0, True)
-            side(first_grads)
+                self._route(L, m0, scratch, c0, k0, W, 0, True)
+            side(first_grads, nl + 1)
         if dy_audio is not None:
             _lib.check(L.hg_disc_first_conv_bwd(self.ycat[b0:].data_ptr(), W["w0"].data_ptr(),
                                                 G["grad"][0][seq0:].data_ptr(), bn, self.t, period, k0, s0, p0, c0,
@@ -1273,7 +1335,8 @@ class DiscriminatorTrainer:
             d.__dict__.pop("_hg_wcache", None)
         # critical-path scheduling: the spectral-norm scale (two parts, full-rate input) has the longest chain, the
         # second scale the next longest; their lanes outrank the period discriminators' (HG_DISC_BOOST=0 disables)
-        boosts = [0, 0, 0] if os.environ.get("HG_DISC_BOOST") == "0" else [-2, -1, 0]
+        env = os.environ.get("HG_DISC_BOOST", "")
+        boosts = [0, 0, 0] if env == "0" else [int(v) for v in env.split(",")] if "," in env else [-2, -1, 0]
         self.subs_p = [_SubDiscTrainer(d, device) for d in mpd.discriminators]
         self.subs_s = [_SubDiscTrainer(d, device, boosts[min(i, 2)]) for i, d in enumerate(msd.discriminators)]
         self.subs = self.subs_p + self.subs_s
@@ -1447,6 +1510,8 @@ class TrainStep:
         self.stamps.begin()
         self.stamps.mark("start")
         y2 = y.reshape(b, -1).contiguous().float()
+        for sd in self.D.subs:
+            sd.prefetch_weights()                              # spectral-norm weights of the D step, beside G's forward
         y_g = self.G.forward(x)                                # [B,1,T]
         y_g2 = y_g.view(b, -1)
         out: Dict[str, torch.Tensor] = {}
