@@ -716,7 +716,10 @@ class _SubDiscTrainer:
         # spectral norm: every layer's parameter-gradient chain (wgrad -> unpack -> <dw,w> -> apply, for both halves)
         # is independent of the other layers': spread over W_CHAINS lanes instead of one.  (One lane made this the
         # longest dependent chain of the whole step: 3.9 ms for 2 x 8 layers, profiles/r02_summary.md section 2.)
-        self.wl = _Lanes(self.W_CHAINS, device, [0 + boost] * self.W_CHAINS) if self.spectral else None
+        # weight_norm sub-discriminators: one lane (measured with 1 / 2 / 4 / 8: 12.01 / 12.01 / 12.06-12.12 / 12.10 ms —
+        # their chains are short and the phase is bound by SM-time; HG_W_CHAINS overrides)
+        self.n_chains = self.W_CHAINS if self.spectral else max(1, int(os.environ.get("HG_W_CHAINS", 1)))
+        self.wl = _Lanes(self.n_chains, device, [0 + boost] * self.n_chains)
         self._scr = {}
         self.ws = {}
         # packed fp32 weight gradients, one region per wide layer (zeroed once per backward; the wgrad launches and
@@ -731,9 +734,6 @@ class _SubDiscTrainer:
         # A/B switches for profiles/r02_summary.md: per-layer launches (the round-1 scheme) instead of the batched ones
         self.batch_prep = os.environ.get("HG_BATCH_D_PREP", "1") != "0"
         self.batch_finish = os.environ.get("HG_BATCH_D_FINISH", "0") != "0"   # measured: +0.3 ms when batched (waits for the last wgrad)
-        self.scratch = torch.empty(max(m.weight_v.numel() if hasattr(m, "weight_v") and not self.spectral
-                                       else m.weight_orig.numel() if self.spectral else m.weight.numel()
-                                       for m in self.mods), dtype=torch.float32, device=device)
         self.db = torch.zeros(1024, dtype=torch.float32, device=device)
         self.db_unused = torch.zeros(1024, dtype=torch.float32, device=device)    # the first conv's discarded bias column
         self.wbufs = {}
@@ -747,13 +747,14 @@ class _SubDiscTrainer:
 
     # ---- weights -------------------------------------------------------------------------------------------
     def _scratch_of(self, chain: int) -> torch.Tensor:
-        """fp32 scratch of parameter-gradient chain `chain`: the shared one (weight_norm: one lane serialises its use)
-        or one per chain (spectral norm: the chains run side by side)"""
-        if not self.spectral:
-            return self.scratch
+        """fp32 scratch of parameter-gradient chain `chain` (0: conv_post, 1..nl: the wide layers from the last to the
+        first, nl + 1: the first conv), sized for that layer's weight: the chains run side by side"""
         buf = self._scr.get(chain)
         if buf is None:
-            buf = self._scr[chain] = torch.empty_like(self.scratch)
+            nl = len(self.mids)
+            m = self.mods[-1] if chain == 0 else self.mods[0] if chain == nl + 1 else self.mods[1 + nl - chain]
+            w = m.weight_orig if hasattr(m, "weight_orig") else m.weight_v if hasattr(m, "weight_v") else m.weight
+            buf = self._scr[chain] = torch.empty(w.numel(), dtype=torch.float32, device=self.device)
         return buf
 
     def _weights(self, part: int, only_buffers: bool = False):
@@ -1114,8 +1115,7 @@ class _SubDiscTrainer:
         if not self.spectral:
             self.dwp_flat.zero_()
         self.lanes.fork()     # both lanes join the capture here (a join of a never-forked stream would invalidate it)
-        if self.wl is not None:
-            self.wl.fork()
+        self.wl.fork()
         for pi, (b0, bn, W) in enumerate(self.parts):
             if pi == 1:                       # spectral norm: the generated half's chain on the second lane,
                 with torch.cuda.stream(self.lanes.streams[1]):     # beside the real half's (forked just above)
@@ -1124,8 +1124,7 @@ class _SubDiscTrainer:
             else:
                 self._backward_part(L, G, W, b0, bn, want_wgrad=True, fm=False, dy_audio=None, accumulate=True,
                                     part=pi)
-        if self.wl is not None:
-            self.wl.join()
+        self.wl.join()
         self.lanes.join()
 
     def _bwd_bank(self, part: int):
@@ -1176,12 +1175,10 @@ class _SubDiscTrainer:
         if want_wgrad and not self.spectral:
             self.dwp_flat.zero_()
         self.lanes.fork()
-        if self.wl is not None:
-            self.wl.fork()
+        self.wl.fork()
         self._backward_part(L, G, W, 0, nb, want_wgrad=want_wgrad, fm=False, dy_audio=dy_audio, accumulate=True,
                             part=slot, pre_adds=pre_adds)
-        if self.wl is not None:
-            self.wl.join()
+        self.wl.join()
         self.lanes.join()
 
     def backward_g(self, dy_audio: torch.Tensor, nfm: List[float]) -> None:
@@ -1219,10 +1216,10 @@ class _SubDiscTrainer:
         here = torch.cuda.current_stream()
 
         def side(fn, chain: int):
-            # weight_norm: one w-lane, one scratch.  Spectral norm: chain c (one layer) on lane c % W_CHAINS with a
-            # scratch of its own; both halves of a layer use the same lane, so their accumulation into the layer's
-            # gradient stays ordered
-            wlane = self.wl.streams[chain % self.W_CHAINS] if self.spectral else self.lanes.streams[0]
+            # chain c (one layer's parameter gradients) runs on lane c % n_chains with a scratch of its own; the two
+            # halves of a spectral-norm layer use the same lane, so their accumulation into the layer's gradient
+            # stays ordered
+            wlane = self.wl.streams[chain % self.n_chains]
             wlane.wait_stream(here)
             with torch.cuda.stream(wlane):
                 fn(self._scratch_of(chain))
@@ -1285,6 +1282,8 @@ class _SubDiscTrainer:
                           a_in[seq0 - nr:] if fm else None, nfm[li] if fm else 0.0, G["grad"][li][seq0:], _stream(),
                           flat_h_in=h_in, bias_dst=bias_of(li), pre_add=pre[li])
         if want_wgrad and not self.spectral and self.batch_finish:
+            for s_ in self.wl.streams[1:]:                       # the batched finish reads every layer's wgrad
+                self.wl.streams[0].wait_stream(s_)
             side(lambda scratch: self._table(part).launch("finish"), 0)   # every wide layer's unpack + weight_norm backward
         # first conv (Cin = 1)
         k0, s0, p0, c0 = self.first
@@ -1333,10 +1332,12 @@ class DiscriminatorTrainer:
         self.flat = FlatParams(holder, device)
         for d in list(mpd.discriminators) + list(msd.discriminators):
             d.__dict__.pop("_hg_wcache", None)
-        # critical-path scheduling: the spectral-norm scale (two parts, full-rate input) has the longest chain, the
-        # second scale the next longest; their lanes outrank the period discriminators' (HG_DISC_BOOST=0 disables)
+        # scheduling: the scale discriminators' chains (k = 41 grouped convs, spectral norm) are long and narrow, the
+        # period discriminators' short and wide; the scales' lanes outrank the periods' so that they are done by the
+        # time the periods fill the GPU (HG_DISC_BOOST="a,b,c" sets the three boosts, "0" disables; measured
+        # -2,-1,-1: 11.86 ms, 0,0,0: 11.98, -2,-1,0: 12.12, -2,-2,-2: 12.9 in round 2)
         env = os.environ.get("HG_DISC_BOOST", "")
-        boosts = [0, 0, 0] if env == "0" else [int(v) for v in env.split(",")] if "," in env else [-2, -1, 0]
+        boosts = [0, 0, 0] if env == "0" else [int(v) for v in env.split(",")] if "," in env else [-2, -1, -1]
         self.subs_p = [_SubDiscTrainer(d, device) for d in mpd.discriminators]
         self.subs_s = [_SubDiscTrainer(d, device, boosts[min(i, 2)]) for i, d in enumerate(msd.discriminators)]
         self.subs = self.subs_p + self.subs_s
