@@ -408,8 +408,9 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             hg::add_bf16x16(v, rcur[g]);
             if (p.res1) hg::add_bf16x16(v, kPreRes ? r1[kPreRes ? g : 0] : hg::ldg256(p.res1 + off + g * 16));
             if (p.res2) hg::add_bf16x16(v, kPreRes ? r2[kPreRes ? g : 0] : hg::ldg256(p.res2 + off + g * 16));
+            const float sc = keep ? p.scale : 0.f;                             // rows past a ragged item's end: zeros
 #pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = keep ? v[e] * p.scale : 0.f;   // rows past a ragged item's end: zeros
+            for (int e = 0; e < 16; ++e) v[e] *= sc;
             if (p.out_raw) {
               hg::U8 o;
 #pragma unroll
