@@ -95,10 +95,21 @@ struct ConvArgs {
 
 // One 16-column group of one accumulator row: everything the epilogue does between the TMEM load and the
 // global stores.  `v` leaves holding the final fp32 values (zero for rows that are not stored).
-// kLean: the forward instantiation — no feature-matching / pre-add / mask terms (they belong to hg_conv1d_dgrad).
-// Carrying those warp-uniform branches in the inference kernels cost 9 % of the whole forward (55.4 -> 50.4 ms at
-// 64 x 1024 frames, profiles/r02_summary.md section 4), so they are compiled out.
-template <bool kLean>
+// kEpi selects what the epilogue is compiled with:
+//   0  forward: bias, residuals, scale, raw / activated outputs
+//   1  forward over flat sequences (the discriminators' layout): + the gap-row test
+//   2  data gradient of a discriminator / generator step: + leaky_relu mask, fp32 bias-gradient sums
+//   3  data gradient of the generator step through a discriminator: + mask, feature-matching sign term
+//   4  everything (+ the pre-add of an incoming feature-map gradient: the autograd path)
+//   5  forward with the two extra addends of an MRF-final launch (flavours 0 and 1 take one residual only)
+// Carrying the warp-uniform branches of the full epilogue in every kernel cost 9 % of the inference forward
+// (55.4 -> 50.4 ms at 64 x 1024 frames) and 0.4 ms of the 11.9 ms training step (profiles/r02_summary.md).
+__host__ __device__ constexpr bool epi_mask(int k) { return k >= 2; }
+__host__ __device__ constexpr bool epi_sums(int k) { return k == 2 || k == 4; }
+__host__ __device__ constexpr bool epi_fm(int k) { return k == 3 || k == 4; }
+__host__ __device__ constexpr bool epi_pre(int k) { return k == 4; }
+__host__ __device__ constexpr bool epi_mrf(int k) { return k >= 2; }   // second / third addend (res1, res2)
+template <int kEpi>
 __device__ __forceinline__ void epi_group(const ConvArgs& p, bool valid, bool keep, size_t off, int ch,
                                           const uint32_t (&raw)[16], const hg::U8* r0, const hg::U8* r1,
                                           const hg::U8* r2, float (&v)[16]) {
@@ -116,7 +127,7 @@ __device__ __forceinline__ void epi_group(const ConvArgs& p, bool valid, bool ke
       v[4 * q] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
     }
   }
-  if (!kLean && p.fm_g) {
+  if (epi_fm(kEpi) && p.fm_g) {
     const hg::U8 fg = hg::ldg256(p.fm_g + off), fr = hg::ldg256(p.fm_r + off);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -125,8 +136,8 @@ __device__ __forceinline__ void epi_group(const ConvArgs& p, bool valid, bool ke
       v[2 * i + 1] += p.fm_coef * ((a.y > r.y) ? 1.f : (a.y < r.y) ? -1.f : 0.f);
     }
   }
-  if (!kLean && p.pre_add) hg::add_bf16x16(v, hg::ldg256(p.pre_add + off));
-  if (!kLean && p.mask) {
+  if (epi_pre(kEpi) && p.pre_add) hg::add_bf16x16(v, hg::ldg256(p.pre_add + off));
+  if (epi_mask(kEpi) && p.mask) {
     const hg::U8 mk = hg::ldg256(p.mask + off);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -136,8 +147,8 @@ __device__ __forceinline__ void epi_group(const ConvArgs& p, bool valid, bool ke
     }
   }
   if (p.res0) hg::add_bf16x16(v, *r0);
-  if (p.res1) hg::add_bf16x16(v, r1 ? *r1 : hg::ldg256(p.res1 + off));
-  if (p.res2) hg::add_bf16x16(v, r2 ? *r2 : hg::ldg256(p.res2 + off));
+  if (epi_mrf(kEpi) && p.res1) hg::add_bf16x16(v, r1 ? *r1 : hg::ldg256(p.res1 + off));
+  if (epi_mrf(kEpi) && p.res2) hg::add_bf16x16(v, r2 ? *r2 : hg::ldg256(p.res2 + off));
   const float sc = keep ? p.scale : 0.f;                               // rows past a ragged item's end: zeros
 #pragma unroll
   for (int e = 0; e < 16; ++e) v[e] *= sc;
@@ -225,7 +236,7 @@ struct TileIter {
 
 // KC = channels per K chunk: 64 -> 128-byte rows / SWIZZLE_128B, 32 -> 64-byte rows / SWIZZLE_64B.
 // NT = output channels per tile (UMMA N).
-template <int KC, int NT, bool kLean>
+template <int KC, int NT, int kEpi>
 __global__ void __launch_bounds__(kThreads, 1)
 conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                  const ConvArgs p) {
@@ -417,19 +428,19 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     float* csum = reinterpret_cast<float*>(bars + 1);
     const int epi_tid = threadIdx.x - 64;
     int cs_nt = -1;
-    if (!kLean && p.colsum[0]) {
+    if (epi_sums(kEpi) && p.colsum[0]) {
       for (int c = epi_tid; c < NT; c += kEpiWarps * 32) csum[c] = 0.f;
       epi_bar_sync();
     }
     for (TileIter it(p); it.tile < p.num_tiles; it.next()) {
       const int nt = it.nt, b = it.b;
-      if (!kLean && p.colsum[0] && nt != cs_nt) {
+      if (epi_sums(kEpi) && p.colsum[0] && nt != cs_nt) {
         if (cs_nt >= 0) epi_colsum_flush<NT>(p, csum, cs_nt, epi_tid);
         cs_nt = nt;
       }
       const int t = it.tt * kTileM + row;
       bool valid = t < p.t;
-      if (!kLean && p.seq_pitch) valid = valid && ((t % p.seq_pitch) * p.seq_mul + (nt * NT) / p.seq_div < p.seq_valid);
+      if (kEpi >= 1 && p.seq_pitch) valid = valid && ((t % p.seq_pitch) * p.seq_mul + (nt * NT) / p.seq_div < p.seq_valid);
       const bool keep = !p.item_len || t < __ldg(p.item_len + b) * p.item_mul;
       const int ch0 = nt * NT + col0;
       const size_t off = (static_cast<size_t>(b) * p.t_pitch + (valid ? t : 0)) * p.cout + ch0;
@@ -443,7 +454,7 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       // (loading them at the point of use exposed their latency: +0.3 .. +1.2 ms on those launches)
       constexpr bool kPreAll = kGroups16 <= 4;
       hg::U8 rpre1[kPreAll ? kGroups16 : 1], rpre2[kPreAll ? kGroups16 : 1];
-      if (kPreAll && valid) {
+      if (epi_mrf(kEpi) && kPreAll && valid) {
         if (p.res1) {
 #pragma unroll
           for (int g = 0; g < kGroups16; ++g) rpre1[kPreAll ? g : 0] = hg::ldg256(p.res1 + off + g * 16);
@@ -464,16 +475,16 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         hg::tmem_ld_32x16(taddr, raw);
         hg::tmem_ld_wait();
         float v[16];
-        epi_group<kLean>(p, valid, keep, off + g * 16, ch0 + g * 16, raw, &rpre[g], kPreAll ? &rpre1[kPreAll ? g : 0] : nullptr,
+        epi_group<kEpi>(p, valid, keep, off + g * 16, ch0 + g * 16, raw, &rpre[g], kPreAll ? &rpre1[kPreAll ? g : 0] : nullptr,
                   kPreAll ? &rpre2[kPreAll ? g : 0] : nullptr, v);
-        if (!kLean && p.colsum[0]) epi_colsum16(v, lane, csum + col0 + g * 16);
+        if (epi_sums(kEpi) && p.colsum[0]) epi_colsum16(v, lane, csum + col0 + g * 16);
       }
       hg::tc_fence_before();
       __syncwarp();
       if (lane == 0) hg::mbar_arrive(&bars->acc_empty[acc]);
       ++acc_it;
     }
-    if (!kLean && p.colsum[0] && cs_nt >= 0) epi_colsum_flush<NT>(p, csum, cs_nt, epi_tid);
+    if (epi_sums(kEpi) && p.colsum[0] && cs_nt >= 0) epi_colsum_flush<NT>(p, csum, cs_nt, epi_tid);
   }
 
   hg::tc_fence_before();
@@ -500,7 +511,7 @@ struct Barriers2 {
   uint32_t pad;
 };
 
-template <int NT, bool kLean>
+template <int NT, int kEpi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv1d_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                   const ConvArgs p) {
@@ -659,20 +670,20 @@ conv1d_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     float* csum = reinterpret_cast<float*>(bars + 1);
     const int epi_tid = threadIdx.x - 64;
     int cs_nt = -1;
-    if (!kLean && p.colsum[0]) {
+    if (epi_sums(kEpi) && p.colsum[0]) {
       for (int c = epi_tid; c < NT; c += kEpiWarps * 32) csum[c] = 0.f;
       epi_bar_sync();
     }
     for (int pt = cluster_id; pt < num_pt; pt += n_clusters) {
       int nt, ptt, b;
       decode(pt, nt, ptt, b);
-      if (!kLean && p.colsum[0] && nt != cs_nt) {
+      if (epi_sums(kEpi) && p.colsum[0] && nt != cs_nt) {
         if (cs_nt >= 0) epi_colsum_flush<NT>(p, csum, cs_nt, epi_tid);
         cs_nt = nt;
       }
       const int t = (2 * ptt + static_cast<int>(rank)) * kTileM + row;
       bool valid = t < p.t;
-      if (!kLean && p.seq_pitch) valid = valid && ((t % p.seq_pitch) * p.seq_mul + (nt * NT) / p.seq_div < p.seq_valid);
+      if (kEpi >= 1 && p.seq_pitch) valid = valid && ((t % p.seq_pitch) * p.seq_mul + (nt * NT) / p.seq_div < p.seq_valid);
       const bool keep = !p.item_len || t < __ldg(p.item_len + b) * p.item_mul;
       const int ch0 = nt * NT + col0;
       const size_t off = (static_cast<size_t>(b) * p.t_pitch + (valid ? t : 0)) * p.cout + ch0;
@@ -683,7 +694,7 @@ conv1d_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       }
       constexpr bool kPreAll = kGroups16 <= 4;
       hg::U8 rpre1[kPreAll ? kGroups16 : 1], rpre2[kPreAll ? kGroups16 : 1];
-      if (kPreAll && valid) {
+      if (epi_mrf(kEpi) && kPreAll && valid) {
         if (p.res1) {
 #pragma unroll
           for (int g = 0; g < kGroups16; ++g) rpre1[kPreAll ? g : 0] = hg::ldg256(p.res1 + off + g * 16);
@@ -703,9 +714,9 @@ conv1d_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         hg::tmem_ld_32x16(taddr, raw);
         hg::tmem_ld_wait();
         float v[16];
-        epi_group<kLean>(p, valid, keep, off + g * 16, ch0 + g * 16, raw, &rpre[g], kPreAll ? &rpre1[kPreAll ? g : 0] : nullptr,
+        epi_group<kEpi>(p, valid, keep, off + g * 16, ch0 + g * 16, raw, &rpre[g], kPreAll ? &rpre1[kPreAll ? g : 0] : nullptr,
                   kPreAll ? &rpre2[kPreAll ? g : 0] : nullptr, v);
-        if (!kLean && p.colsum[0]) epi_colsum16(v, lane, csum + col0 + g * 16);
+        if (epi_sums(kEpi) && p.colsum[0]) epi_colsum16(v, lane, csum + col0 + g * 16);
       }
       hg::tc_fence_before();
       __syncwarp();
@@ -715,7 +726,7 @@ conv1d_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       }
       ++acc_it;
     }
-    if (!kLean && p.colsum[0] && cs_nt >= 0) epi_colsum_flush<NT>(p, csum, cs_nt, epi_tid);
+    if (epi_sums(kEpi) && p.colsum[0] && cs_nt >= 0) epi_colsum_flush<NT>(p, csum, cs_nt, epi_tid);
   }
 
   hg::tc_fence_before();
@@ -737,38 +748,48 @@ int device_props() {
   return HG_OK;
 }
 
-template <int KC, int NT, bool kLean>
+template <int KC, int NT, int kEpi>
 int launch_as(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const ConvArgs& p, size_t smem_bytes,
               int grid, cudaStream_t st) {
   static hg::PerDeviceOnce once;  // per instantiation
   if (once.need())
-    HG_CHECK_CUDA(cudaFuncSetAttribute(conv1d_tc_kernel<KC, NT, kLean>,
+    HG_CHECK_CUDA(cudaFuncSetAttribute(conv1d_tc_kernel<KC, NT, kEpi>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
-  conv1d_tc_kernel<KC, NT, kLean><<<grid, kThreads, smem_bytes, st>>>(tm_x, tm_w, p);
+  conv1d_tc_kernel<KC, NT, kEpi><<<grid, kThreads, smem_bytes, st>>>(tm_x, tm_w, p);
   HG_CHECK_CUDA(cudaGetLastError());
   return HG_OK;
 }
 
-// the forward instantiation serves every launch without backward-pass epilogue terms, flat sequences or bias sums
-bool is_lean(const ConvArgs& p) {
-  return !p.mask && !p.fm_g && !p.pre_add && !p.colsum[0] && p.seq_pitch == 0;
+// the cheapest epilogue flavour that serves this launch
+int epi_flavour(const ConvArgs& p) {
+  if (p.pre_add || (p.fm_g && p.colsum[0])) return 4;
+  if (p.fm_g) return 3;
+  if (p.mask || p.colsum[0]) return 2;
+  if (p.res1 || p.res2) return 5;
+  return p.seq_pitch ? 1 : 0;
 }
 
 template <int KC, int NT>
 int launch(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const ConvArgs& p, size_t smem_bytes,
            int grid, cudaStream_t st) {
-  return is_lean(p) ? launch_as<KC, NT, true>(tm_x, tm_w, p, smem_bytes, grid, st)
-                    : launch_as<KC, NT, false>(tm_x, tm_w, p, smem_bytes, grid, st);
+  switch (epi_flavour(p)) {
+    case 0: return launch_as<KC, NT, 0>(tm_x, tm_w, p, smem_bytes, grid, st);
+    case 1: return launch_as<KC, NT, 1>(tm_x, tm_w, p, smem_bytes, grid, st);
+    case 2: return launch_as<KC, NT, 2>(tm_x, tm_w, p, smem_bytes, grid, st);
+    case 3: return launch_as<KC, NT, 3>(tm_x, tm_w, p, smem_bytes, grid, st);
+    case 5: return launch_as<KC, NT, 5>(tm_x, tm_w, p, smem_bytes, grid, st);
+    default: return launch_as<KC, NT, 4>(tm_x, tm_w, p, smem_bytes, grid, st);
+  }
 }
 
-template <int NT, bool kLean>
+template <int NT, int kEpi>
 int launch2_as(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const ConvArgs& p, size_t smem_bytes, int grid,
                cudaStream_t st) {
   static hg::PerDeviceOnce once;
   if (once.need())
-    HG_CHECK_CUDA(cudaFuncSetAttribute(conv1d_tc2_kernel<NT, kLean>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    HG_CHECK_CUDA(cudaFuncSetAttribute(conv1d_tc2_kernel<NT, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        g_max_smem));
-  conv1d_tc2_kernel<NT, kLean><<<grid, kThreads, smem_bytes, st>>>(tm_x, tm_w, p);   // __cluster_dims__(2,1,1)
+  conv1d_tc2_kernel<NT, kEpi><<<grid, kThreads, smem_bytes, st>>>(tm_x, tm_w, p);   // __cluster_dims__(2,1,1)
   HG_CHECK_CUDA(cudaGetLastError());
   return HG_OK;
 }
@@ -776,8 +797,14 @@ int launch2_as(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const ConvArgs&
 template <int NT>
 int launch2(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const ConvArgs& p, size_t smem_bytes, int grid,
             cudaStream_t st) {
-  return is_lean(p) ? launch2_as<NT, true>(tm_x, tm_w, p, smem_bytes, grid, st)
-                    : launch2_as<NT, false>(tm_x, tm_w, p, smem_bytes, grid, st);
+  switch (epi_flavour(p)) {
+    case 0: return launch2_as<NT, 0>(tm_x, tm_w, p, smem_bytes, grid, st);
+    case 1: return launch2_as<NT, 1>(tm_x, tm_w, p, smem_bytes, grid, st);
+    case 2: return launch2_as<NT, 2>(tm_x, tm_w, p, smem_bytes, grid, st);
+    case 3: return launch2_as<NT, 3>(tm_x, tm_w, p, smem_bytes, grid, st);
+    case 5: return launch2_as<NT, 5>(tm_x, tm_w, p, smem_bytes, grid, st);
+    default: return launch2_as<NT, 4>(tm_x, tm_w, p, smem_bytes, grid, st);
+  }
 }
 
 int g_use_2cta = -1;
