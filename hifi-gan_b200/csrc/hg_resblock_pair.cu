@@ -81,7 +81,11 @@ __device__ __forceinline__ uint32_t lrelu_bf16x2(uint32_t w, __nv_bfloat162 slop
 }
 
 // C = channels = UMMA N = K-chunk width: 64 -> SWIZZLE_128B rows of 128 B, 32 -> SWIZZLE_64B rows of 64 B.
-template <int C, bool kSingle>
+// kMrf = true: the general instantiation (MRF-final launches: two extra addends, scale, activated output; ragged
+// batches).  kMrf = false: the plain step "one residual in, raw out, every item t rows long, scale 1" — 15 of the 18
+// pair launches of a V1 forward.  The output role is the kernel's bottleneck at C = 32: compiled without the other
+// paths it takes 0.86 -> 0.76 ms (k = 3) and 0.89 -> 0.75 ms (k = 7) per launch at 64 x 1024 frames.
+template <int C, bool kSingle, bool kMrf>
 __global__ void __launch_bounds__(pair_threads(C), 1)
 resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
                      const __grid_constant__ CUtensorMap tm_w2, const PairArgs p) {
@@ -282,7 +286,7 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         hg::mbar_wait(&bars->acc1_full[a], ph);
         hg::mbar_wait(&bars->t1_empty[a], ph ^ 1u);
         hg::tc_fence_after();
-        const int t_item = p.item_len ? min(p.t, __ldg(p.item_len + bb) * p.item_mul) : p.t;
+        const int t_item = (kMrf && p.item_len) ? min(p.t, __ldg(p.item_len + bb) * p.item_mul) : p.t;
         for (int m = 0; m < S; ++m) {
           const int grow = m * kM + row;                       // row of the item's t1 tile
           const int time = tt * p.r_out - p.pad2 + grow;       // its time step
@@ -336,7 +340,7 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         const int grow = n_m * kM + row;
         const int time = n_tt * p.r_out + grow;
         valid = grow < p.r_out && time < p.t;
-        keep = !p.item_len || time < __ldg(p.item_len + n_b) * p.item_mul;
+        keep = !kMrf || !p.item_len || time < __ldg(p.item_len + n_b) * p.item_mul;
         const size_t o = (static_cast<size_t>(n_b) * p.t + (valid ? time : 0)) * C + col0;
         if (++n_m == S) {
           n_m = 0;
@@ -371,7 +375,7 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         }
         // MRF-final launch: the two extra addends of this unit, issued before the accumulator wait
         // (C = 64 runs 704 threads under an 80-register cap: it keeps loading them at the point of use)
-        constexpr bool kPreRes = (C == 32);
+        constexpr bool kPreRes = kMrf && (C == 32);
         hg::U8 r1[kPreRes ? kG : 1], r2[kPreRes ? kG : 1];
         if (kPreRes && valid && p.res1) {
 #pragma unroll
@@ -406,18 +410,20 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
               v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + bq.w;
             }
             hg::add_bf16x16(v, rcur[g]);
-            if (p.res1) hg::add_bf16x16(v, kPreRes ? r1[kPreRes ? g : 0] : hg::ldg256(p.res1 + off + g * 16));
-            if (p.res2) hg::add_bf16x16(v, kPreRes ? r2[kPreRes ? g : 0] : hg::ldg256(p.res2 + off + g * 16));
-            const float sc = keep ? p.scale : 0.f;                             // rows past a ragged item's end: zeros
+            if (kMrf && p.res1) hg::add_bf16x16(v, kPreRes ? r1[kPreRes ? g : 0] : hg::ldg256(p.res1 + off + g * 16));
+            if (kMrf && p.res2) hg::add_bf16x16(v, kPreRes ? r2[kPreRes ? g : 0] : hg::ldg256(p.res2 + off + g * 16));
+            if (kMrf) {
+              const float sc = keep ? p.scale : 0.f;                           // rows past a ragged item's end: zeros
 #pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] *= sc;
+              for (int e = 0; e < 16; ++e) v[e] *= sc;
+            }
             if (p.out_raw) {
               hg::U8 o;
 #pragma unroll
               for (int q = 0; q < 8; ++q) o.v[q] = hg::pack_bf16x2(v[2 * q], v[2 * q + 1]);
               hg::stg256(p.out_raw + off + g * 16, o);
             }
-            if (p.out_act) {
+            if (kMrf && p.out_act) {
               hg::U8 o;
 #pragma unroll
               for (int q = 0; q < 8; ++q)
@@ -439,16 +445,24 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 
 int g_sms = 0, g_smem = 0;
 
-template <int C, bool kSingle>
-int launch_pair(const CUtensorMap& tx, const CUtensorMap& tw1, const CUtensorMap& tw2, const PairArgs& p,
+template <int C, bool kSingle, bool kMrf>
+int launch_pair_as(const CUtensorMap& tx, const CUtensorMap& tw1, const CUtensorMap& tw2, const PairArgs& p,
                 size_t smem_bytes, int grid, cudaStream_t st) {
   static hg::PerDeviceOnce once;
   if (once.need())
-    HG_CHECK_CUDA(cudaFuncSetAttribute(resblock_pair_kernel<C, kSingle>,
+    HG_CHECK_CUDA(cudaFuncSetAttribute(resblock_pair_kernel<C, kSingle, kMrf>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem));
-  resblock_pair_kernel<C, kSingle><<<grid, pair_threads(C), smem_bytes, st>>>(tx, tw1, tw2, p);
+  resblock_pair_kernel<C, kSingle, kMrf><<<grid, pair_threads(C), smem_bytes, st>>>(tx, tw1, tw2, p);
   HG_CHECK_CUDA(cudaGetLastError());
   return HG_OK;
+}
+
+template <int C, bool kSingle>
+int launch_pair(const CUtensorMap& tx, const CUtensorMap& tw1, const CUtensorMap& tw2, const PairArgs& p,
+                size_t smem_bytes, int grid, cudaStream_t st) {
+  const bool mrf = p.res1 || p.res2 || p.out_act || p.item_len || p.scale != 1.f;   // anything beyond the plain step
+  return mrf ? launch_pair_as<C, kSingle, true>(tx, tw1, tw2, p, smem_bytes, grid, st)
+             : launch_pair_as<C, kSingle, false>(tx, tw1, tw2, p, smem_bytes, grid, st);
 }
 
 size_t pair_smem_bytes(int c, int ktaps, int dil1, int subs, int x_slots, int single, PairArgs* out) {
