@@ -283,7 +283,7 @@ KERNEL_CLASSES = (
     # (class, substrings of the kernel name): tensor-core implicit GEMMs first, then the bandwidth-bound helpers
     ("conv fwd + dgrad (tcgen05)", ("conv1d_tc_kernel", "conv1d_tc2_kernel", "resblock_pair_kernel")),
     ("wgrad (tcgen05)", ("wgrad_tc_kernel",)),
-    ("weight prep (fold / pack / spectral norm)", ("pack_", "fold_weight", "sn_")),
+    ("weight prep (fold / pack / spectral norm; batched job tables)", ("pack_", "fold_weight", "sn_", "prep_batched")),
     ("wgrad finish / weight-norm bwd", ("wgrad_finish", "weight_norm_bwd", "unpack_wgrad")),
     ("cin=1 / cout=1 ends, pooling", ("disc_first", "disc_last", "conv_post", "avgpool", "ncl_to_nlc")),
     ("losses + mel", ("loss_", "l1_sum", "mel_")),
