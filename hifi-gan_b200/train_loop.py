@@ -102,6 +102,14 @@ def normalize_fork(audio: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------------ driver
+def epoch_learning_rate(h, epoch: int) -> float:
+    """Learning rate of 0-based epoch `epoch`: UPSTREAM's `ExponentialLR(optim, gamma=h.lr_decay, last_epoch=last_epoch)`
+    stepped once per epoch.  From scratch that is lr * gamma^epoch; on resume (last_epoch = the saved epoch, the
+    optimizer's `initial_lr` restored from the do_* file) torch's closed form gives the same value for the epoch
+    that is re-run and the ones after it (tests/test_host_cpu.py checks both against torch's scheduler)."""
+    return float(h.learning_rate) * float(h.lr_decay) ** int(epoch)
+
+
 def train(rank: int, a, h, local_rank: int = None) -> Dict[str, float]:
     """rank = global rank (gradient exchange, batch shard, logging); local_rank = the GPU of this process."""
     world = h.num_gpus if h.num_gpus > 1 else 1
@@ -159,8 +167,7 @@ def train(rank: int, a, h, local_rank: int = None) -> Dict[str, float]:
     batches_per_epoch = max(1, n_items // (per_rank * world))
     last = {}
     for epoch in range(max(0, last_epoch), a.training_epochs):
-        ts.lr = h.learning_rate * (h.lr_decay ** epoch)             # ExponentialLR(gamma=lr_decay, last_epoch); the
-        #                                                             captured graph reads it from device memory
+        ts.lr = epoch_learning_rate(h, epoch)                        # the captured graph reads it from device memory
         if rank == 0:
             start = time.time()
             print("Epoch: {}".format(epoch + 1))

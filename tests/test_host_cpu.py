@@ -375,3 +375,28 @@ def test_bench_reference_arm_contract(workload):
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     other = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, cwd=ROOT, timeout=600, env=env)
     assert other.returncode == 0 and not [l for l in other.stdout.splitlines() if l.startswith("{")]
+
+
+def test_epoch_learning_rate_matches_torch_exponential_lr():
+    """train_loop.epoch_learning_rate vs the reference's scheduler (UPSTREAM train.py: ExponentialLR(gamma=h.lr_decay,
+    last_epoch=last_epoch), one scheduler.step() per epoch): from scratch, and resumed from a do_* file saved in epoch 2."""
+    from hifigan_b200.train_loop import epoch_learning_rate
+    h = H.AttrDict(dict(learning_rate=2e-4, lr_decay=0.999, adam_b1=0.8, adam_b2=0.99))
+    p = [torch.nn.Parameter(torch.zeros(1))]
+    opt = torch.optim.AdamW(p, h.learning_rate, betas=[h.adam_b1, h.adam_b2])
+    sch = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=h.lr_decay, last_epoch=-1)
+    saved = None
+    for epoch in range(5):
+        assert opt.param_groups[0]["lr"] == pytest.approx(epoch_learning_rate(h, epoch), rel=1e-12)
+        p[0].grad = torch.ones(1)
+        opt.step()
+        if epoch == 2:
+            saved = opt.state_dict()          # what a do_* file written during epoch 2 holds
+        sch.step()
+    opt2 = torch.optim.AdamW(p, h.learning_rate, betas=[h.adam_b1, h.adam_b2])
+    opt2.load_state_dict(saved)
+    sch2 = torch.optim.lr_scheduler.ExponentialLR(opt2, gamma=h.lr_decay, last_epoch=2)
+    for epoch in range(2, 6):                 # UPSTREAM resumes with `for epoch in range(max(0, last_epoch), ...)`
+        assert opt2.param_groups[0]["lr"] == pytest.approx(epoch_learning_rate(h, epoch), rel=1e-12)
+        opt2.step()
+        sch2.step()
