@@ -644,7 +644,7 @@ def test_train_driver_checkpoints_and_resumes(H, tmp_path):
 
 
 @pytest.mark.gpu
-def test_train_loop_validate_matches_oracle():
+def test_train_loop_validate_matches_oracle(H):
     """train_loop.validate (UPSTREAM validation: mean over files of L1(mel(y), mel(G(mel(y)))) on whole utterances,
     fmax_for_loss) against the same number from the CPU oracle's generator_forward + mel_spectrogram."""
     from hifigan_b200 import train_loop
