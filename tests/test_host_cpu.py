@@ -400,3 +400,36 @@ def test_epoch_learning_rate_matches_torch_exponential_lr():
         assert opt2.param_groups[0]["lr"] == pytest.approx(epoch_learning_rate(h, epoch), rel=1e-12)
         opt2.step()
         sch2.step()
+
+
+def test_cta_limit_is_a_per_thread_setting_that_returns_the_previous_value():
+    """hg_set_cta_limit (include/hifigan_b200.h): host-only state, no CUDA call."""
+    import threading
+    L = _lib.lib()
+    assert L.hg_set_cta_limit(0) == 0
+    assert L.hg_set_cta_limit(48) == 0 and L.hg_set_cta_limit(-5) == 48 and L.hg_set_cta_limit(0) == 0   # negative -> off
+    L.hg_set_cta_limit(40)
+    seen = []
+    t = threading.Thread(target=lambda: seen.append(L.hg_set_cta_limit(0)))
+    t.start(); t.join()
+    assert seen == [0]                      # another thread starts unlimited
+    assert L.hg_set_cta_limit(0) == 40      # and did not touch this thread's value
+
+
+def test_mrf_lane_split_gives_even_cta_counts_that_fill_the_gpu():
+    from hifigan_b200.models import _GeneratorEngine
+    for weights in ([1.0, 1.0, 1.0], [5.2, 6.1, 7.2], [0.01, 1.0, 1.0], [2.1, 3.0, 5.2], [1.0, 3.0]):
+        s = _GeneratorEngine._split_ctas(weights, 148, _GeneratorEngine.LANE_MIN_CTAS)
+        assert sum(s) == 148 and all(v % 2 == 0 and v >= _GeneratorEngine.LANE_MIN_CTAS for v in s), (weights, s)
+        if len(set(weights)) == len(weights):
+            assert s.index(max(s)) == weights.index(max(weights))
+
+
+def test_lane_stamps_are_off_unless_asked_for(monkeypatch):
+    """TrainStep's time marks launch nothing by default (they would change the step's launch count)."""
+    from hifigan_b200.train import LaneStamps
+    monkeypatch.delenv("HG_LANE_STAMPS", raising=False)
+    st = LaneStamps(torch.device("cpu"))
+    st.begin()
+    st.mark("start")                        # no-op: would need the CUDA library otherwise
+    assert not st.on and st.names == [] and st.read() == {}
