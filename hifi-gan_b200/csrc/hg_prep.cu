@@ -172,6 +172,72 @@ conv_post_tanh_kernel(const __nv_bfloat16* __restrict__ x, const float* __restri
   }
 }
 
+// conv_post + tanh, register-window version for the shapes the configs use (C = 32 channels, k = 7).  The kernel
+// above re-reads every staged input row from shared memory once per tap and converts it again (ncu, round 2: 29
+// warp-instructions per output sample, 0.78 ms per 16.8 M samples, 18 % of the HBM rate).  Here a thread owns
+// kPost2R CONSECUTIVE outputs and walks the channels in slabs of 4: the kPost2R + K - 1 rows of a slab are read and
+// converted once into registers and feed all K taps of all kPost2R outputs (224 FMAs per output, ~50 other
+// instructions instead of ~700).  kPost2R is odd and the staged row pitch is C*2 + 8 bytes, so the 8-byte row reads of
+// a half-warp (thread stride 9 x 72 B = 81 x 8 B) fall on distinct bank pairs.  Outputs leave through shared memory
+// so the global stores stay coalesced.  Measured: 0.781 -> 0.486 ms per 64 x 262 144 samples.
+constexpr int kPost2R = 9;
+template <int C, int K, int kPost2Threads>
+__global__ void __launch_bounds__(kPost2Threads)
+conv_post_tanh_kernel2(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                       const float* __restrict__ bias, int t, float* __restrict__ y) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  constexpr int kPost2Tile = kPost2R * kPost2Threads;
+  constexpr int kPitch = C * 2 + 8;
+  constexpr int kRows = kPost2Tile + K - 1;
+  constexpr int kWin = kPost2R + K - 1;
+  float* ws = reinterpret_cast<float*>(sm);              // [K][C]
+  uint8_t* xs = sm + ((K * C * 4 + 15) & ~15);           // [kRows][kPitch]
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * kPost2Tile;
+  for (int i = threadIdx.x; i < K * C; i += kPost2Threads) ws[i] = w[(i % C) * K + i / C];
+  constexpr int kVec = C / 8;                             // 16-byte global loads per row
+  const __nv_bfloat16* xb = x + static_cast<size_t>(b) * t * C;
+  for (int i = threadIdx.x; i < kRows * kVec; i += kPost2Threads) {
+    const int r = i / kVec, vq = i % kVec;
+    const int tt = t0 + r - K / 2;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (tt >= 0 && tt < t) val = *reinterpret_cast<const uint4*>(xb + static_cast<size_t>(tt) * C + vq * 8);
+    uint2* dst = reinterpret_cast<uint2*>(xs + r * kPitch + vq * 16);     // rows are 8-byte aligned only
+    dst[0] = make_uint2(val.x, val.y);
+    dst[1] = make_uint2(val.z, val.w);
+  }
+  __syncthreads();
+  float acc[kPost2R];
+  const float b0 = bias ? bias[0] : 0.f;
+#pragma unroll
+  for (int o = 0; o < kPost2R; ++o) acc[o] = b0;
+  const uint8_t* base = xs + static_cast<size_t>(threadIdx.x) * kPost2R * kPitch;
+#pragma unroll 1
+  for (int q = 0; q < C / 4; ++q) {
+    float xr[kWin][4];
+#pragma unroll
+    for (int r = 0; r < kWin; ++r) {
+      const uint2 v = *reinterpret_cast<const uint2*>(base + r * kPitch + q * 8);
+      const float2 lo = hg::unpack_bf16x2(v.x), hi = hg::unpack_bf16x2(v.y);
+      xr[r][0] = lo.x; xr[r][1] = lo.y; xr[r][2] = hi.x; xr[r][3] = hi.y;
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const float4 wv = *reinterpret_cast<const float4*>(ws + j * C + q * 4);
+#pragma unroll
+      for (int o = 0; o < kPost2R; ++o)
+        acc[o] += xr[o + j][0] * wv.x + xr[o + j][1] * wv.y + xr[o + j][2] * wv.z + xr[o + j][3] * wv.w;
+    }
+  }
+  __syncthreads();                                        // everyone is done reading the staged rows
+  float* ys = reinterpret_cast<float*>(xs);
+#pragma unroll
+  for (int o = 0; o < kPost2R; ++o) ys[threadIdx.x * kPost2R + o] = tanhf(acc[o]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < kPost2Tile; i += kPost2Threads)
+    if (t0 + i < t) y[static_cast<size_t>(b) * t + t0 + i] = ys[i];
+}
+
 // out[b][i] = i < valid[b] ? pool[start[b] + i] : 0   (MelDataset crop / right zero-pad, meldataset.py:141-150)
 __global__ void segment_gather_kernel(const float* __restrict__ pool, const long long* __restrict__ start,
                                       const int* __restrict__ valid, int seg, float* __restrict__ out) {
@@ -302,12 +368,36 @@ extern "C" int hg_nlc_to_ncl(const void* x, int batch, int t, int c, float* out,
   return HG_OK;
 }
 
+template <int TH>
+static int launch_post2(const __nv_bfloat16* x, const float* w, const float* bias, int batch, int t, float* y,
+                        cudaStream_t st) {
+  constexpr int tile = kPost2R * TH;
+  constexpr size_t smem = ((7 * 32 * 4 + 15) & ~15) + static_cast<size_t>(tile + 7 - 1) * (32 * 2 + 8);
+  static hg::PerDeviceOnce once;
+  if (once.need())
+    HG_CHECK_CUDA(cudaFuncSetAttribute(conv_post_tanh_kernel2<32, 7, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+  dim3 grid((t + tile - 1) / tile, batch);
+  conv_post_tanh_kernel2<32, 7, TH><<<grid, TH, smem, st>>>(x, w, bias, t, y);
+  HG_CHECK_CUDA(cudaGetLastError());
+  return HG_OK;
+}
+
 extern "C" int hg_conv_post_tanh_fwd(const void* x, const float* w, const float* bias, int batch,
                                      int t, int c, int k, float* y, void* stream) {
   HG_REQUIRE(x && w && y, "hg_conv_post_tanh_fwd: null pointer");
   HG_REQUIRE(batch > 0 && t > 0 && c > 0 && c % 8 == 0 && k > 0 && (k & 1) && k <= 15,
              "hg_conv_post_tanh_fwd: bad shape (c %% 8 == 0, odd k <= 15 required)");
   HG_REQUIRE(batch <= 65535, "hg_conv_post_tanh_fwd: batch too large");
+  if (c == 32 && k == 7 && !getenv("HG_POST_V1")) {       // every shipped config (conv_post: 32 -> 1, k = 7)
+    // 64 threads x 9 outputs per block (42 KB of staged rows, 5 blocks per SM): 0.486 ms per 16.8 M samples against
+    // 0.609 ms with 128 threads and 0.781 ms for the kernel above (profiles/r02_summary.md section 4)
+    const int rc = launch_post2<64>(static_cast<const __nv_bfloat16*>(x), w, bias, batch, t, y,
+                                    static_cast<cudaStream_t>(stream));
+    if (rc) return rc;
+    g_hg_launches.fetch_add(1, std::memory_order_relaxed);
+    return HG_OK;
+  }
   const size_t smem = ((k * c * 4 + 15) & ~15) + static_cast<size_t>(kPostTile + k - 1) * (c * 2 + 16);
   HG_REQUIRE(smem <= 200 * 1024, "hg_conv_post_tanh_fwd: window does not fit shared memory");
   dim3 grid((t + kPostTile - 1) / kPostTile, batch);
